@@ -1,0 +1,1071 @@
+/*
+ * jpeg_oracle_decode.c -- CPU restatement of the reference's Huffman decode path.
+ * TEST INFRASTRUCTURE ONLY (see jpeg_oracle.h).  Build: -O2 -ffp-contract=off.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/src/JpegLibrary unless stated otherwise).
+ */
+#include "jpeg_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* JpegZigZag.cs:27-38: zig-zag index -> natural (row-major) index */
+static const uint8_t kZigzagToNatural[64] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+/* ------------------------------------------------------------------------- */
+/* Huffman decoding table: JpegHuffmanDecodingTable.cs:293-390                */
+typedef struct {
+    int present;
+    uint8_t values[256];
+    uint16_t maxcode[18];
+    uint8_t valoffset[19];
+    uint8_t la_size[256];   /* look-ahead Entry.CodeSize   */
+    uint8_t la_sym[256];    /* look-ahead Entry.SymbolValue */
+} huff_table;
+
+static int huff_build(huff_table *t, const uint8_t bits[16], const uint8_t *vals, int nvals)
+{
+    uint8_t huffsize[257];
+    uint16_t huffcode[257];
+    int k = 0;
+    memset(t, 0, sizeof(*t));
+    /* GenerateSizeTable :293-309 */
+    for (int i = 1; i <= 16; i++)
+        for (int j = 0; j < bits[i - 1]; j++) huffsize[k++] = (uint8_t)i;
+    huffsize[k] = 0;
+    if (k != nvals || k > 256) return -1;
+    /* GenerateCodeTable :311-337 */
+    if (k > 0) {
+        int kk = 0, code = 0, si = huffsize[0];
+        for (;;) {
+            do {
+                huffcode[kk] = (uint16_t)code;
+                code++;
+                kk++;
+            } while (huffsize[kk] == si);
+            if (huffsize[kk] == 0) break;
+            do {
+                code <<= 1;
+                si++;
+            } while (huffsize[kk] != si);
+        }
+    }
+    /* Configure :339-376 */
+    memcpy(t->values, vals, (size_t)nvals);
+    int p = 0;
+    for (int l = 1; l <= 16; l++) {
+        if (bits[l - 1] != 0) {
+            int offset = p - huffcode[p];
+            t->valoffset[l] = (uint8_t)offset;
+            p += bits[l - 1];
+            uint16_t mc = huffcode[p - 1];
+            mc = (uint16_t)(mc << (16 - l));
+            mc = (uint16_t)(mc | (uint32_t)((1 << (16 - l)) - 1));
+            t->maxcode[l] = mc;
+        } else {
+            t->maxcode[l] = 0;
+        }
+    }
+    t->valoffset[18] = 0;
+    t->maxcode[17] = 0xFFFF;
+    p = 0;
+    for (int l = 1; l <= 8; l++) {
+        for (int i = 0; i < bits[l - 1]; i++, p++) {
+            /* FillByteLookupTable :378-390 */
+            int free_bits = 8 - l;
+            int code = (uint8_t)(huffcode[p] << free_bits);
+            for (int j = 0; j < (1 << free_bits); j++) {
+                t->la_size[code + j] = (uint8_t)l;
+                t->la_sym[code + j] = t->values[p];
+            }
+        }
+    }
+    t->present = 1;
+    return 0;
+}
+
+/* Lookup/LookupSlow :73-113. returns size in *size, symbol in return; size>16 => error */
+static inline int huff_lookup(const huff_table *t, int code16, int *size)
+{
+    int high8 = code16 >> 8;
+    if (t->la_size[high8] != 0) {
+        *size = t->la_size[high8];
+        return t->la_sym[high8];
+    }
+    int s = 9;
+    while (code16 > t->maxcode[s]) s++;
+    *size = s;
+    if (s > 16) return -1;
+    code16 >>= (16 - s);
+    return t->values[(t->valoffset[s] + code16) & 0xFF];
+}
+
+/* ------------------------------------------------------------------------- */
+/* JpegBitReader.cs                                                           */
+typedef struct {
+    const uint8_t *p, *end;
+    uint64_t buffer;
+    int bits;
+    int next_marker;
+} bit_reader;
+
+static void br_init(bit_reader *r, const uint8_t *p, const uint8_t *end)
+{
+    r->p = p;
+    r->end = end;
+    r->buffer = 0;
+    r->bits = 0;
+    r->next_marker = 0;
+}
+
+/* FillBuffer :95-138 */
+static int br_fill(bit_reader *r)
+{
+    while (r->bits < 32) {
+        if (r->next_marker != 0) return r->bits;
+        if (r->p >= r->end) break;
+        uint8_t b = *r->p++;
+        if (b == 0xFF) {
+            if (r->p >= r->end) break; /* stream ended prematurely */
+            uint8_t b2 = *r->p;
+            if (b2 == 0xFF) continue; /* padding byte */
+            r->p++;
+            if (b2 != 0) {
+                r->next_marker = b2;
+                break;
+            }
+            b = 0xFF;
+        }
+        r->buffer = (r->buffer << 8) | b;
+        r->bits += 8;
+    }
+    return r->bits;
+}
+
+/* PeekBits :157-172 */
+static inline int br_peek(bit_reader *r, int length, int *peeked)
+{
+    int bits = r->bits;
+    if (bits < length) {
+        bits = br_fill(r);
+        if (bits < length) {
+            *peeked = bits;
+            return (int)((((uint32_t)r->buffer) << (length - bits)) & ((1u << length) - 1u)) |
+                   ((1 << (length - bits)) - 1);
+        }
+    }
+    *peeked = length;
+    return (int)(r->buffer >> (bits - length)) & ((1 << length) - 1);
+}
+
+/* TryAdvanceBits :175-187 */
+static inline int br_advance(bit_reader *r, int length)
+{
+    if (r->bits < length) {
+        if (br_fill(r) < length) return 0;
+    }
+    r->bits -= length;
+    return 1;
+}
+
+/* TryReadBits :190-204 */
+static inline int br_read(bit_reader *r, int length, int *out)
+{
+    if (r->bits < length) {
+        if (br_fill(r) < length) return 0;
+    }
+    r->bits -= length;
+    *out = (int)(r->buffer >> r->bits) & (int)((1u << length) - 1u);
+    return 1;
+}
+
+/* AdvanceAlignByte :29-33 */
+static void br_align(bit_reader *r)
+{
+    r->bits -= r->bits % 8;
+    br_fill(r);
+}
+
+/* TryReadMarker :140-149 */
+static int br_read_marker(bit_reader *r)
+{
+    if (r->bits == 0) {
+        int m = r->next_marker;
+        r->next_marker = 0;
+        return m;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    int component_index, h, v, hs, vs;
+    const huff_table *dc, *ac;
+    const uint16_t *qt;
+    int dc_pred;
+} dec_component; /* JpegHuffmanDecodingComponent.cs */
+
+typedef struct {
+    jo_image *img;
+    const uint8_t *data;
+    size_t len;
+    huff_table huff[2][4];
+    uint16_t qt[4][64];
+    int qt_present[4];
+    int restart_interval;
+    int have_frame;
+    /* progressive decoder state: `_components` slots survive across scans
+       (JpegHuffmanProgressiveScanDecoder.cs:21,69) */
+    dec_component slots[JO_MAX_COMP];
+    int slot_valid[JO_MAX_COMP];
+    int16_t dummy[64];
+    int err;
+} dec_ctx;
+
+static int fail(dec_ctx *c, int code, const char *msg)
+{
+    if (!c->err) {
+        c->err = code;
+        snprintf(c->img->error, sizeof(c->img->error), "%s", msg);
+    }
+    return code;
+}
+
+/* DecodeHuffmanCode JpegHuffmanScanDecoder.cs:81-88 */
+static inline int decode_huff(dec_ctx *c, bit_reader *r, const huff_table *t)
+{
+    int peeked, size;
+    int bits = br_peek(r, 16, &peeked);
+    int sym = huff_lookup(t, bits, &size);
+    if (sym < 0) {
+        fail(c, JO_ERR_INVALID_DATA, "Invalid Huffman code encountered.");
+        return 0;
+    }
+    if (size > peeked) size = peeked;
+    br_advance(r, size);
+    return sym;
+}
+
+/* ReceiveAndExtend JpegHuffmanScanDecoder.cs:100-115 */
+static inline int receive_extend(dec_ctx *c, bit_reader *r, int length)
+{
+    int v;
+    if (length > 16) { /* not representable in the reference's 32-bit reads either */
+        fail(c, JO_ERR_INVALID_DATA, "Invalid magnitude category.");
+        return 0;
+    }
+    if (!br_read(r, length, &v)) {
+        fail(c, JO_ERR_INVALID_DATA, "The bit stream ended prematurely.");
+        return 0;
+    }
+    return v - ((((v + v) >> length) - 1) & ((1 << length) - 1));
+}
+
+/* InitDecodeComponents JpegHuffmanScanDecoder.cs:17-72 */
+static int init_components(dec_ctx *c, const jo_scan_info *s, dec_component *comps)
+{
+    jo_image *im = c->img;
+    for (int i = 0; i < s->ncomp; i++) {
+        int ci = s->comp_index[i];
+        dec_component *dc = &comps[i];
+        dc->component_index = ci;
+        dc->h = im->comp_h[ci];
+        dc->v = im->comp_v[ci];
+        dc->dc = c->huff[0][s->td[i]].present ? &c->huff[0][s->td[i]] : NULL;
+        dc->ac = c->huff[1][s->ta[i]].present ? &c->huff[1][s->ta[i]] : NULL;
+        dc->qt = c->qt_present[im->comp_tq[ci]] ? c->qt[im->comp_tq[ci]] : NULL;
+        dc->hs = im->hmax / dc->h;
+        dc->vs = im->vmax / dc->v;
+        dc->dc_pred = 0;
+    }
+    return s->ncomp;
+}
+
+static inline int16_t *coef_block(jo_image *im, int ci, int bx, int by)
+{
+    return im->coef[ci] + ((size_t)by * im->coef_w[ci] + bx) * 64;
+}
+
+/* ReadBlockBaseline JpegHuffmanBaselineScanDecoder.cs:179-222 */
+static void read_block_baseline(dec_ctx *c, bit_reader *r, dec_component *comp, int16_t *blk)
+{
+    int t = decode_huff(c, r, comp->dc);
+    if (t != 0) t = receive_extend(c, r, t);
+    t += comp->dc_pred;
+    comp->dc_pred = t;
+    blk[0] = (int16_t)t;
+    for (int i = 1; i < 64;) {
+        int s = decode_huff(c, r, comp->ac);
+        int rr = s >> 4;
+        s &= 15;
+        if (s != 0) {
+            i += rr;
+            s = receive_extend(c, r, s);
+            blk[i < 63 ? i : 63] = (int16_t)s;
+            i++;
+        } else {
+            if (rr == 0) break;
+            i += 16;
+        }
+        if (c->err) return;
+    }
+}
+
+/* ProcessScan JpegHuffmanBaselineScanDecoder.cs:51-177 (entropy part only; the
+   per-block dequant/IDCT/write is applied afterwards from the coefficient store,
+   which is equivalent because blocks are independent) */
+static int scan_baseline(dec_ctx *c, const jo_scan_info *s)
+{
+    jo_image *im = c->img;
+    dec_component comps[JO_MAX_COMP];
+    int n = init_components(c, s, comps);
+    for (int i = 0; i < n; i++) {
+        if (!comps[i].dc || !comps[i].ac)
+            return fail(c, JO_ERR_INVALID_DATA, "Huffman table of component is not defined.");
+        if (!comps[i].qt)
+            return fail(c, JO_ERR_INVALID_DATA, "Quantization table of component is not defined.");
+        memcpy(im->qt[comps[i].component_index], comps[i].qt, 128);
+    }
+    bit_reader r;
+    br_init(&r, c->data + s->entropy_offset, c->data + c->len);
+    int restart = s->restart_interval;
+    int before = restart;
+    for (int row = 0; row < im->mcus_per_col; row++) {
+        for (int col = 0; col < im->mcus_per_line; col++) {
+            for (int k = 0; k < n; k++) {
+                dec_component *comp = &comps[k];
+                for (int y = 0; y < comp->v; y++)
+                    for (int x = 0; x < comp->h; x++) {
+                        /* Q2: every scan is walked as MCU-interleaved over the frame grid
+                           using the component's own h,v (:107-136) */
+                        int16_t *blk = coef_block(im, comp->component_index, col * comp->h + x,
+                                                  row * comp->v + y);
+                        memset(blk, 0, 128); /* outputBuffer = default :121 */
+                        read_block_baseline(c, &r, comp, blk);
+                        if (c->err) return c->err;
+                    }
+            }
+            /* restart :139-163 */
+            if (restart > 0 && (--before) == 0) {
+                br_align(&r);
+                int m = br_read_marker(&r);
+                if (m == 0xD9) return JO_OK;
+                if (!(m >= 0xD0 && m <= 0xD7))
+                    return fail(c, JO_ERR_INVALID_OP, "Expect restart marker.");
+                before = restart;
+                for (int k = 0; k < n; k++) comps[k].dc_pred = 0;
+            }
+        }
+    }
+    return JO_OK;
+}
+
+/* ---- progressive: JpegHuffmanProgressiveScanDecoder.cs -------------------- */
+typedef struct {
+    int restart, before, eobrun;
+} prog_state;
+
+/* GetBlockReference JpegBlockAllocator.cs:93-114 (dummy block for out-of-range) */
+static inline int16_t *prog_block(dec_ctx *c, int ci, int bx, int by)
+{
+    jo_image *im = c->img;
+    if (bx >= im->alloc_w[ci] || by >= im->alloc_h[ci]) return c->dummy;
+    return coef_block(im, ci, bx, by);
+}
+
+/* HandleRestart :196-224.  returns 1 continue, 0 stop (EOI), <0 error */
+static int prog_restart(dec_ctx *c, bit_reader *r, prog_state *st)
+{
+    if (st->restart > 0 && (--st->before) == 0) {
+        br_align(r);
+        int m = br_read_marker(r);
+        if (m == 0xD9) return 0;
+        if (!(m >= 0xD0 && m <= 0xD7)) return fail(c, JO_ERR_INVALID_OP, "Expect restart marker.");
+        st->before = st->restart;
+        st->eobrun = 0;
+        for (int i = 0; i < c->img->ncomp; i++) c->slots[i].dc_pred = 0; /* all _components :217 */
+    }
+    return 1;
+}
+
+/* ReadBlockProgressiveDC :227-253 */
+static void prog_dc(dec_ctx *c, bit_reader *r, dec_component *comp, const jo_scan_info *s,
+                    int16_t *blk)
+{
+    if (s->ah == 0) {
+        int v = decode_huff(c, r, comp->dc);
+        if (v != 0) v = receive_extend(c, r, v);
+        v += comp->dc_pred;
+        comp->dc_pred = v;
+        blk[0] = (int16_t)(v << s->al);
+    } else {
+        int bit;
+        if (!br_read(r, 1, &bit)) {
+            fail(c, JO_ERR_INVALID_DATA, "Unexpected end of JPEG data stream.");
+            return;
+        }
+        blk[0] |= (int16_t)(bit << s->al);
+    }
+}
+
+/* ReadBlockProgressiveACRefined :313-419 */
+static void prog_ac_refine(dec_ctx *c, bit_reader *r, const huff_table *ac, const jo_scan_info *s,
+                           int *eobrun, int16_t *blk)
+{
+    int start = s->ss, end = s->se;
+    int p1 = 1 << s->al;
+    int m1 = (-1) * (1 << s->al);
+    int k = start;
+    int bit;
+    if (*eobrun == 0) {
+        for (; k <= end; k++) {
+            int sym = decode_huff(c, r, ac);
+            if (c->err) return;
+            int rr = sym >> 4;
+            int sv = sym & 15;
+            if (sv != 0) {
+                if (!br_read(r, 1, &bit)) {
+                    fail(c, JO_ERR_INVALID_DATA, "Unexpected end of JPEG data stream.");
+                    return;
+                }
+                sv = bit != 0 ? p1 : m1;
+            } else {
+                if (rr != 15) {
+                    *eobrun = 1 << rr;
+                    if (rr != 0) {
+                        if (!br_read(r, rr, &bit)) {
+                            fail(c, JO_ERR_INVALID_DATA, "Unexpected end of JPEG data stream.");
+                            return;
+                        }
+                        *eobrun += bit;
+                    }
+                    break;
+                }
+            }
+            do {
+                int16_t *coef = &blk[k];
+                if (*coef != 0) {
+                    if (!br_read(r, 1, &bit)) {
+                        fail(c, JO_ERR_INVALID_DATA, "Unexpected end of JPEG data stream.");
+                        return;
+                    }
+                    if (bit != 0) {
+                        if ((*coef & p1) == 0) *coef = (int16_t)(*coef + (int16_t)(*coef >= 0 ? p1 : m1));
+                    }
+                } else {
+                    if (--rr < 0) break;
+                }
+                k++;
+            } while (k <= end);
+            if (sv != 0 && k < 64) blk[k] = (int16_t)sv;
+        }
+    }
+    if (*eobrun > 0) {
+        for (; k <= end; k++) {
+            int16_t *coef = &blk[k];
+            if (*coef != 0) {
+                if (!br_read(r, 1, &bit)) {
+                    fail(c, JO_ERR_INVALID_DATA, "Unexpected end of JPEG data stream.");
+                    return;
+                }
+                if (bit != 0) {
+                    if ((*coef & p1) == 0) *coef = (int16_t)(*coef + (int16_t)(*coef > 0 ? p1 : m1));
+                }
+            }
+        }
+        --*eobrun;
+    }
+}
+
+/* ReadBlockProgressiveAC :255-311 */
+static void prog_ac(dec_ctx *c, bit_reader *r, const huff_table *ac, const jo_scan_info *s,
+                    int *eobrun, int16_t *blk)
+{
+    if (s->ah == 0) {
+        if (*eobrun != 0) {
+            --*eobrun;
+            return;
+        }
+        for (int i = s->ss; i <= s->se; i++) {
+            int sym = decode_huff(c, r, ac);
+            if (c->err) return;
+            int rr = sym >> 4;
+            int sv = sym & 15;
+            i += rr;
+            if (sv != 0) {
+                sv = receive_extend(c, r, sv);
+                blk[i < 63 ? i : 63] = (int16_t)(sv << s->al);
+            } else if (rr != 15) {
+                *eobrun = 1 << rr;
+                if (rr != 0) {
+                    int bits;
+                    if (!br_read(r, rr, &bits)) {
+                        fail(c, JO_ERR_INVALID_DATA, "Unexpected end of JPEG data stream.");
+                        return;
+                    }
+                    *eobrun += bits;
+                }
+                --*eobrun;
+                break;
+            }
+        }
+    } else {
+        prog_ac_refine(c, r, ac, s, eobrun, blk);
+    }
+}
+
+/* ProcessScan :57-90 + interleaved :92-138 + non-interleaved :140-194 */
+static int scan_progressive(dec_ctx *c, const jo_scan_info *s)
+{
+    jo_image *im = c->img;
+    int n = init_components(c, s, c->slots);
+    for (int i = 0; i < n; i++) {
+        c->slot_valid[i] = 1;
+        if (!c->slots[i].qt)
+            return fail(c, JO_ERR_INVALID_DATA, "Quantization table of component is not defined.");
+    }
+    prog_state st = {s->restart_interval, s->restart_interval, 0};
+    bit_reader r;
+    br_init(&r, c->data + s->entropy_offset, c->data + c->len);
+    if (n == 1) {
+        dec_component *comp = &c->slots[0];
+        int ci = comp->component_index;
+        int wb = (im->width + 8 * comp->hs - 1) / (8 * comp->hs);
+        int hb = (im->height + 8 * comp->vs - 1) / (8 * comp->vs);
+        if (s->ss == 0) {
+            if (!comp->dc) return fail(c, JO_ERR_INVALID_DATA, "Huffman table is not defined.");
+        } else if (!comp->ac)
+            return fail(c, JO_ERR_INVALID_DATA, "Huffman table is not defined.");
+        for (int by = 0; by < hb; by++)
+            for (int bx = 0; bx < wb; bx++) {
+                int16_t *blk = prog_block(c, ci, bx, by);
+                if (s->ss == 0)
+                    prog_dc(c, &r, comp, s, blk);
+                else
+                    prog_ac(c, &r, comp->ac, s, &st.eobrun, blk);
+                if (c->err) return c->err;
+                int rc = prog_restart(c, &r, &st);
+                if (rc <= 0) return rc;
+            }
+    } else {
+        for (int i = 0; i < n; i++)
+            if (!c->slots[i].dc) return fail(c, JO_ERR_INVALID_DATA, "Huffman table is not defined.");
+        for (int row = 0; row < im->mcus_per_col; row++)
+            for (int col = 0; col < im->mcus_per_line; col++) {
+                for (int k = 0; k < n; k++) {
+                    dec_component *comp = &c->slots[k];
+                    for (int y = 0; y < comp->v; y++)
+                        for (int x = 0; x < comp->h; x++) {
+                            int16_t *blk = prog_block(c, comp->component_index, col * comp->h + x,
+                                                      row * comp->v + y);
+                            prog_dc(c, &r, comp, s, blk);
+                            if (c->err) return c->err;
+                        }
+                }
+                int rc = prog_restart(c, &r, &st);
+                if (rc <= 0) return rc;
+            }
+    }
+    return JO_OK;
+}
+
+/* ------------------------------------------------------------------------- */
+/* FastFloatingPointDCT.cs:79-185 -- one 1-D pass over "rows" V0..V7 of s,      */
+/* element-wise per column (the Vector4 lanes).                                */
+static void idct_pass(const float *s, float *d)
+{
+    const float C_1_175876 = 1.175875602f, C_1_961571 = -1.961570560f, C_0_390181 = -0.390180644f,
+                C_0_899976 = -0.899976223f, C_2_562915 = -2.562915447f, C_0_298631 = 0.298631336f,
+                C_2_053120 = 2.053119869f, C_3_072711 = 3.072711026f, C_1_501321 = 1.501321110f,
+                C_0_541196 = 0.541196100f, C_1_847759 = -1.847759065f, C_0_765367 = 0.765366865f;
+    for (int c = 0; c < 8; c++) {
+        float my1 = s[8 + c], my7 = s[56 + c];
+        float mz0 = my1 + my7;
+        float my3 = s[24 + c];
+        float mz2 = my3 + my7;
+        float my5 = s[40 + c];
+        float mz1 = my3 + my5;
+        float mz3 = my1 + my5;
+        float mz4 = (mz0 + mz1) * C_1_175876;
+        mz2 = (mz2 * C_1_961571) + mz4;
+        mz3 = (mz3 * C_0_390181) + mz4;
+        mz0 = mz0 * C_0_899976;
+        mz1 = mz1 * C_2_562915;
+        float mb3 = (my7 * C_0_298631) + mz0 + mz2;
+        float mb2 = (my5 * C_2_053120) + mz1 + mz3;
+        float mb1 = (my3 * C_3_072711) + mz1 + mz2;
+        float mb0 = (my1 * C_1_501321) + mz0 + mz3;
+        float my2 = s[16 + c], my6 = s[48 + c];
+        mz4 = (my2 + my6) * C_0_541196;
+        float my0 = s[c], my4 = s[32 + c];
+        mz0 = my0 + my4;
+        mz1 = my0 - my4;
+        mz2 = mz4 + (my6 * C_1_847759);
+        mz3 = mz4 + (my2 * C_0_765367);
+        my0 = mz0 + mz3;
+        my3 = mz0 - mz3;
+        my1 = mz1 + mz2;
+        my2 = mz1 - mz2;
+        d[c] = my0 + mb0;
+        d[56 + c] = my0 - mb0;
+        d[8 + c] = my1 + mb1;
+        d[48 + c] = my1 - mb1;
+        d[16 + c] = my2 + mb2;
+        d[40 + c] = my2 - mb2;
+        d[24 + c] = my3 + mb3;
+        d[32 + c] = my3 - mb3;
+    }
+}
+
+static void transpose8(const float *s, float *d)
+{
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) d[j * 8 + i] = s[i * 8 + j];
+}
+
+/* DequantizeBlockAndUnZigZag ScanDecoder/JpegScanDecoder.cs:50-62,
+   TransformIDCT FastFloatingPointDCT.cs:54-70,
+   ShiftDataLevel ScanDecoder/JpegScanDecoder.cs:64-73 (MathF.Round = half-to-even) */
+void jo_dequant_idct_block(const int16_t coef_zz[64], const uint16_t q_zz[64], int level_shift,
+                           int16_t out[64])
+{
+    float src[64], tmp[64], dst[64];
+    for (int i = 0; i < 64; i++)
+        src[kZigzagToNatural[i]] = (float)((int)q_zz[i] * (int)coef_zz[i]);
+    transpose8(src, tmp);
+    idct_pass(tmp, dst);
+    transpose8(dst, tmp);
+    idct_pass(tmp, dst);
+    for (int i = 0; i < 64; i++) {
+        float v = dst[i] * 0.125f;
+        out[i] = (int16_t)((int)rintf(v) + level_shift);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* apps/JpegDecode/JpegYCbCrToRgbConverter.cs:25-131: table construction       */
+static int g_crr[256], g_cbb[256], g_crg[256], g_cbg[256], g_yt[256];
+static pthread_once_t g_color_once = PTHREAD_ONCE_INIT;
+
+static int fix16(float x) { return (int)((double)x * 65536.0 + 0.5); } /* Fix :123-126 */
+static int code2v(int c, float rb, float rw, float cr)
+{ /* Code2V :128-131 */
+    return (int)(((float)(c - (int)rb) * cr) / ((int)(rw - rb) != 0 ? (rw - rb) : 1.0f));
+}
+static void color_init(void)
+{
+    float luma_r = 299 / 1000.0f, luma_g = 587 / 1000.0f, luma_b = 114 / 1000.0f;
+    float f1 = 2 - 2 * luma_r;
+    int d1 = fix16(f1);
+    float f2 = luma_r * f1 / luma_g;
+    int d2 = -fix16(f2);
+    float f3 = 2 - 2 * luma_b;
+    int d3 = fix16(f3);
+    float f4 = luma_b * f3 / luma_g;
+    int d4 = -fix16(f4);
+    for (int i = 0, x = -128; i < 256; i++, x++) {
+        int cr = code2v(x, 128.0f - 128.0f, 255.0f - 128.0f, 127);
+        int cb = code2v(x, 128.0f - 128.0f, 255.0f - 128.0f, 127);
+        g_crr[i] = (d1 * cr + 32768) >> 16;
+        g_cbb[i] = (d3 * cb + 32768) >> 16;
+        g_crg[i] = d2 * cr;
+        g_cbg[i] = d4 * cb + 32768;
+        g_yt[i] = code2v(x + 128, 0.0f, 255.0f, 255);
+    }
+}
+static inline uint8_t clamp_table(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+/* ConvertYCbCr8ToRgb24 :171-205 */
+void jo_ycbcr_to_rgb(const uint8_t *ycbcr, uint8_t *rgb, size_t n)
+{
+    pthread_once(&g_color_once, color_init);
+    for (size_t i = 0; i < n; i++) {
+        int y = ycbcr[3 * i], cb = ycbcr[3 * i + 1], cr = ycbcr[3 * i + 2];
+        int yv = g_yt[y];
+        rgb[3 * i] = clamp_table(yv + g_crr[cr]);
+        rgb[3 * i + 1] = clamp_table(yv + ((g_cbg[cb] + g_crg[cr]) >> 16));
+        rgb[3 * i + 2] = clamp_table(yv + g_cbb[cb]);
+    }
+}
+
+/* ------------------------------------------------------------------------- */
+/* IDCT + replicate + write for every block of the store.
+   Baseline: ...BaselineScanDecoder.cs:119-134 + WriteBlock/WriteBlockSlow :225-268.
+   Progressive: Dispose :421-466 + JpegBlockAllocator.Flush :120-190.          */
+static void render_planes(dec_ctx *c)
+{
+    jo_image *im = c->img;
+    int W = im->width, H = im->height;
+    int shift = 1 << (im->precision - 1);
+    for (int ci = 0; ci < im->ncomp; ci++) {
+        int hs = im->hmax / im->comp_h[ci], vs = im->vmax / im->comp_v[ci];
+        int16_t *plane = im->planes + (size_t)ci * W * H;
+        int gw = im->sof == 2 ? im->alloc_w[ci] : im->coef_w[ci];
+        int gh = im->sof == 2 ? im->alloc_h[ci] : im->coef_h[ci];
+        for (int by = 0; by < gh; by++)
+            for (int bx = 0; bx < gw; bx++) {
+                int16_t px[64];
+                jo_dequant_idct_block(coef_block(im, ci, bx, by), im->qt[ci], shift, px);
+                int x0 = bx * 8 * hs, y0 = by * 8 * vs;
+                for (int yy = 0; yy < 8 * vs; yy++) {
+                    int y = y0 + yy;
+                    if (y >= H) break;
+                    for (int xx = 0; xx < 8 * hs; xx++) {
+                        int x = x0 + xx;
+                        if (x >= W) break;
+                        plane[(size_t)y * W + x] = px[(yy / vs) * 8 + (xx / hs)];
+                    }
+                }
+            }
+    }
+}
+
+/* apps/JpegDecode/DecodeAction.cs:38-74 with JpegBufferOutputWriter8Bit.cs:28-60 /
+   JpegBufferOutputWriterGreaterThan8Bit.cs:34-68 */
+static void render_rgb(dec_ctx *c)
+{
+    jo_image *im = c->img;
+    size_t n = (size_t)im->width * im->height;
+    int shift = im->precision > 8 ? im->precision - 8 : 0;
+    for (size_t i = 0; i < n; i++) {
+        for (int ci = 0; ci < 3; ci++) {
+            int v;
+            if (ci < im->ncomp) {
+                v = im->planes[(size_t)ci * n + i] >> shift;
+                v = v < 0 ? 0 : (v > 255 ? 255 : v);
+            } else
+                v = 128;
+            im->ycbcr[3 * i + ci] = (uint8_t)v;
+        }
+    }
+    jo_ycbcr_to_rgb(im->ycbcr, im->rgb, n);
+}
+
+/* ------------------------------------------------------------------------- */
+/* Marker walk: JpegDecoder.Decode :509-550, ProcessMarkerForDecode :558-617,
+   JpegReader.TryReadMarker JpegReader.cs:120-158.  Q1 (TryReadLength bug,
+   JpegReader.cs:174) is NOT reproduced: lengths are read correctly.           */
+static int read_marker(const uint8_t *d, size_t len, size_t *pos)
+{
+    size_t p = *pos;
+    while (p + 1 < len) {
+        if (d[p] == 0xFF) {
+            if (d[p + 1] == 0xFF) {
+                p += 1;
+                continue;
+            }
+            if (d[p + 1] == 0x00) {
+                p += 2;
+                continue;
+            }
+            *pos = p + 2;
+            return d[p + 1];
+        }
+        const uint8_t *q = memchr(d + p, 0xFF, len - p);
+        if (!q) {
+            *pos = len;
+            return -1;
+        }
+        p = (size_t)(q - d);
+    }
+    *pos = len;
+    return -1;
+}
+
+static int parse_frame(dec_ctx *c, int sof, const uint8_t *b, size_t n)
+{
+    jo_image *im = c->img;
+    if (n < 6) return fail(c, JO_ERR_INVALID_DATA, "Failed to parse frame header.");
+    im->sof = sof;
+    im->precision = b[0];
+    im->height = (b[1] << 8) | b[2];
+    im->width = (b[3] << 8) | b[4];
+    im->ncomp = b[5];
+    if (im->ncomp < 1 || im->ncomp > JO_MAX_COMP || n < 6 + 3 * (size_t)im->ncomp)
+        return fail(c, JO_ERR_INVALID_DATA, "Failed to parse frame header.");
+    if (im->width == 0 || im->height == 0 || im->precision < 2 || im->precision > 16)
+        return fail(c, JO_ERR_INVALID_DATA, "Failed to parse frame header.");
+    im->hmax = im->vmax = 1;
+    for (int i = 0; i < im->ncomp; i++) {
+        im->comp_id[i] = b[6 + 3 * i];
+        im->comp_h[i] = b[7 + 3 * i] >> 4;
+        im->comp_v[i] = b[7 + 3 * i] & 15;
+        im->comp_tq[i] = b[8 + 3 * i];
+        if (im->comp_h[i] < 1 || im->comp_h[i] > 4 || im->comp_v[i] < 1 || im->comp_v[i] > 4 ||
+            im->comp_tq[i] > 3)
+            return fail(c, JO_ERR_INVALID_DATA, "Failed to parse frame header.");
+        if (im->comp_h[i] > im->hmax) im->hmax = im->comp_h[i];
+        if (im->comp_v[i] > im->vmax) im->vmax = im->comp_v[i];
+    }
+    im->mcus_per_line = (im->width + 8 * im->hmax - 1) / (8 * im->hmax);
+    im->mcus_per_col = (im->height + 8 * im->vmax - 1) / (8 * im->vmax);
+    int wblk = (im->width + 7) / 8, hblk = (im->height + 7) / 8;
+    for (int i = 0; i < im->ncomp; i++) {
+        int hs = im->hmax / im->comp_h[i], vs = im->vmax / im->comp_v[i];
+        im->coef_w[i] = im->mcus_per_line * im->comp_h[i];
+        im->coef_h[i] = im->mcus_per_col * im->comp_v[i];
+        im->alloc_w[i] = (wblk + hs - 1) / hs; /* JpegBlockAllocator.cs:52-62 */
+        im->alloc_h[i] = (hblk + vs - 1) / vs;
+        free(im->coef[i]);
+        im->coef[i] = calloc((size_t)im->coef_w[i] * im->coef_h[i] * 64, sizeof(int16_t));
+        if (!im->coef[i]) return fail(c, JO_ERR_NOMEM, "out of memory");
+    }
+    c->have_frame = 1;
+    return JO_OK;
+}
+
+static int parse_dht(dec_ctx *c, const uint8_t *b, size_t n)
+{
+    while (n > 0) {
+        if (n < 17) return fail(c, JO_ERR_INVALID_DATA, "Failed to parse Huffman table.");
+        int tc = b[0] >> 4, th = b[0] & 15;
+        int count = 0;
+        for (int i = 0; i < 16; i++) count += b[1 + i];
+        if (count > 256 || n < 17 + (size_t)count || tc > 1 || th > 3)
+            return fail(c, JO_ERR_INVALID_DATA, "Failed to parse Huffman table.");
+        if (huff_build(&c->huff[tc][th], b + 1, b + 17, count))
+            return fail(c, JO_ERR_INVALID_DATA, "Failed to parse Huffman table.");
+        b += 17 + count;
+        n -= 17 + (size_t)count;
+    }
+    return JO_OK;
+}
+
+static int parse_dqt(dec_ctx *c, const uint8_t *b, size_t n)
+{
+    while (n > 0) {
+        int pq = b[0] >> 4, tq = b[0] & 15;
+        size_t need = pq ? 129 : 65;
+        if (pq > 1 || tq > 3 || n < need)
+            return fail(c, JO_ERR_INVALID_DATA, "Failed to parse quantization table.");
+        for (int i = 0; i < 64; i++)
+            c->qt[tq][i] = pq ? (uint16_t)((b[1 + 2 * i] << 8) | b[2 + 2 * i]) : b[1 + i];
+        c->qt_present[tq] = 1;
+        b += need;
+        n -= need;
+    }
+    return JO_OK;
+}
+
+static int parse_sos(dec_ctx *c, const uint8_t *b, size_t n, jo_scan_info *s)
+{
+    jo_image *im = c->img;
+    if (n < 1) return fail(c, JO_ERR_INVALID_DATA, "Failed to parse scan header.");
+    s->ncomp = b[0];
+    if (s->ncomp < 1 || s->ncomp > JO_MAX_COMP || n < 1 + 2 * (size_t)s->ncomp + 3)
+        return fail(c, JO_ERR_INVALID_DATA, "Failed to parse scan header.");
+    for (int i = 0; i < s->ncomp; i++) {
+        int sel = b[1 + 2 * i];
+        int found = -1;
+        for (int j = 0; j < im->ncomp; j++)
+            if (im->comp_id[j] == sel) found = j; /* last match wins :44-51 */
+        if (found < 0) return fail(c, JO_ERR_INVALID_DATA, "The specified component is missing.");
+        s->comp_index[i] = found;
+        s->td[i] = b[2 + 2 * i] >> 4;
+        s->ta[i] = b[2 + 2 * i] & 15;
+        if (s->td[i] > 3 || s->ta[i] > 3)
+            return fail(c, JO_ERR_INVALID_DATA, "Failed to parse scan header.");
+    }
+    const uint8_t *t = b + 1 + 2 * s->ncomp;
+    s->ss = t[0];
+    s->se = t[1];
+    s->ah = t[2] >> 4;
+    s->al = t[2] & 15;
+    s->restart_interval = c->restart_interval;
+    return JO_OK;
+}
+
+int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
+{
+    dec_ctx *c = calloc(1, sizeof(dec_ctx));
+    memset(img, 0, sizeof(*img));
+    if (!c) return JO_ERR_NOMEM;
+    c->img = img;
+    c->data = data;
+    c->len = len;
+    size_t pos = 0;
+    int rc = JO_OK;
+    if (len < 2 || data[0] != 0xFF || data[1] != 0xD8) {
+        rc = fail(c, JO_ERR_INVALID_DATA, "Marker StartOfImage not found.");
+        goto done;
+    }
+    pos = 2;
+    int eoi = 0;
+    while (!eoi && pos < len) {
+        int m = read_marker(data, len, &pos);
+        if (m < 0) {
+            rc = fail(c, JO_ERR_INVALID_DATA, "No marker found.");
+            break;
+        }
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (m == 0xD9) {
+            eoi = 1;
+            break;
+        }
+        /* everything else carries a length */
+        if (pos + 2 > len) {
+            rc = fail(c, JO_ERR_INVALID_DATA, "Unexpected end of input data when reading segment length.");
+            break;
+        }
+        size_t seglen = ((size_t)data[pos] << 8) | data[pos + 1];
+        if (seglen < 2 || pos + seglen > len) {
+            rc = fail(c, JO_ERR_INVALID_DATA, "Unexpected end of input data reached.");
+            break;
+        }
+        const uint8_t *body = data + pos + 2;
+        size_t blen = seglen - 2;
+        pos += seglen;
+        switch (m) {
+        case 0xC0: case 0xC1: case 0xC2:
+            rc = parse_frame(c, m - 0xC0, body, blen);
+            break;
+        case 0xC3: case 0xC9: case 0xCA:
+            rc = fail(c, JO_ERR_UNSUPPORTED, "SOF3/SOF9/SOF10 are outside the oracle's scope.");
+            break;
+        case 0xC5: case 0xC6: case 0xC7: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
+            rc = fail(c, JO_ERR_INVALID_DATA, "This type of JPEG stream is not supported.");
+            break;
+        case 0xC4:
+            rc = parse_dht(c, body, blen);
+            break;
+        case 0xDB:
+            rc = parse_dqt(c, body, blen);
+            break;
+        case 0xDD:
+            if (blen < 2) rc = fail(c, JO_ERR_INVALID_DATA, "Unexpected end of input data when reading segment content.");
+            else c->restart_interval = (body[0] << 8) | body[1];
+            break;
+        case 0xDA: {
+            if (!c->have_frame) {
+                rc = fail(c, JO_ERR_INVALID_DATA, "Scan header appears before frame header.");
+                break;
+            }
+            if (img->nscans >= JO_MAX_SCANS) {
+                rc = fail(c, JO_ERR_UNSUPPORTED, "too many scans");
+                break;
+            }
+            jo_scan_info *s = &img->scans[img->nscans];
+            rc = parse_sos(c, body, blen, s);
+            if (rc) break;
+            s->entropy_offset = pos;
+            img->nscans++;
+            rc = img->sof == 2 ? scan_progressive(c, s) : scan_baseline(c, s);
+            /* the marker loop re-finds the next marker by scanning the entropy data */
+            break;
+        }
+        default:
+            break; /* ProcessOtherMarker: skipped */
+        }
+        if (rc) break;
+    }
+    img->consumed = pos;
+    if (!rc && !c->have_frame) rc = fail(c, JO_ERR_INVALID_OP, "Frame header was not found.");
+    if (!rc && img->sof == 2) {
+        /* Dispose quirk (P6): quant tables come from `_components` slots as left by the
+           last scans (:431-462); slot i is used for MCU component position i. */
+        for (int i = 0; i < img->ncomp; i++) {
+            if (!c->slot_valid[i]) {
+                rc = fail(c, JO_ERR_INVALID_DATA, "progressive frame without scans for a slot");
+                break;
+            }
+        }
+        if (!rc) {
+            /* The reference walks slots in order and uses slot.ComponentIndex; emulate by
+               resolving, for each slot, which component it renders and with which table. */
+            int seen[JO_MAX_COMP] = {0};
+            for (int i = 0; i < img->ncomp; i++) {
+                int ci = c->slots[i].component_index;
+                memcpy(img->qt[ci], c->slots[i].qt, 128);
+                seen[ci]++;
+            }
+            for (int i = 0; i < img->ncomp; i++)
+                if (seen[i] != 1) {
+                    rc = fail(c, JO_ERR_UNSUPPORTED,
+                              "progressive scan order leaves component slots inconsistent (P6 quirk)");
+                    break;
+                }
+        }
+    }
+    if (!rc && (flags & (JO_WANT_PLANES | JO_WANT_RGB))) {
+        size_t n = (size_t)img->width * img->height;
+        img->planes = malloc(n * img->ncomp * sizeof(int16_t));
+        if (!img->planes) rc = fail(c, JO_ERR_NOMEM, "out of memory");
+        else {
+            render_planes(c);
+            if ((flags & JO_WANT_RGB) && (img->ncomp == 1 || img->ncomp == 3)) {
+                img->ycbcr = malloc(3 * n);
+                img->rgb = malloc(3 * n);
+                if (!img->ycbcr || !img->rgb) rc = fail(c, JO_ERR_NOMEM, "out of memory");
+                else render_rgb(c);
+            }
+        }
+    }
+done:
+    free(c);
+    return rc;
+}
+
+void jo_free(jo_image *img)
+{
+    for (int i = 0; i < JO_MAX_COMP; i++) {
+        free(img->coef[i]);
+        img->coef[i] = NULL;
+    }
+    free(img->planes);
+    free(img->ycbcr);
+    free(img->rgb);
+    img->planes = NULL;
+    img->ycbcr = img->rgb = NULL;
+}
+
+/* ------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t *const *data;
+    const size_t *len;
+    uint8_t *const *out;
+    int n;
+    int next;
+    int failed;
+    pthread_mutex_t mu;
+} batch_job;
+
+static void *batch_worker(void *arg)
+{
+    batch_job *j = arg;
+    for (;;) {
+        pthread_mutex_lock(&j->mu);
+        int i = j->next++;
+        pthread_mutex_unlock(&j->mu);
+        if (i >= j->n) break;
+        jo_image im;
+        int rc = jo_decode(j->data[i], j->len[i], JO_WANT_RGB, &im);
+        if (rc == JO_OK && im.rgb && j->out && j->out[i])
+            memcpy(j->out[i], im.rgb, (size_t)3 * im.width * im.height);
+        if (rc != JO_OK || !im.rgb) {
+            pthread_mutex_lock(&j->mu);
+            j->failed++;
+            pthread_mutex_unlock(&j->mu);
+        }
+        jo_free(&im);
+    }
+    return NULL;
+}
+
+int jo_decode_batch_rgb(const uint8_t *const *data, const size_t *len, int n, int threads,
+                        uint8_t *const *out)
+{
+    batch_job j = {data, len, out, n, 0, 0, PTHREAD_MUTEX_INITIALIZER};
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, batch_worker, &j);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    return j.failed;
+}
