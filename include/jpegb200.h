@@ -1,0 +1,180 @@
+/*
+ * jpegb200.h -- C-ABI of the B200-native JPEG hot path (libjpegb200.so).
+ *
+ * This is the drop-in boundary for yigolden/JpegLibrary's per-block hot path
+ * (SURVEY.md section 8b).  The reference has no FFI of its own (it is 100 % managed C#);
+ * the entry points below are what a `JpegLibrary.Cuda` P/Invoke layer binds so that
+ *
+ *   JpegScanDecoder.ProcessScan            (src/JpegLibrary/ScanDecoder/JpegScanDecoder.cs:14)
+ *   JpegHuffmanBaselineScanDecoder         (ScanDecoder/JpegHuffmanBaselineScanDecoder.cs:51-268)
+ *   JpegHuffmanProgressiveScanDecoder      (ScanDecoder/JpegHuffmanProgressiveScanDecoder.cs:57-470)
+ *   JpegBlockOutputWriter.WriteBlock sinks (JpegBlockOutputWriter.cs:17; app sinks
+ *                                           apps/JpegDecode/JpegBufferOutputWriter8Bit.cs:28-60,
+ *                                           apps/JpegDecode/JpegYCbCrToRgbConverter.cs:171-205)
+ *   JpegEncoder.TransformBlocks / BuildHuffmanTables / WritePreparedScanData
+ *                                          (JpegEncoder.cs:414-483, 491-597, 605-656)
+ *
+ * run on the GPU.  Marker and header parsing stays on the host (JpegDecoder.Identify /
+ * the marker loop JpegDecoder.cs:509-617); the host hands parsed headers down in
+ * jb_image_desc.  The library never parses markers except restart-marker discovery.
+ *
+ * Conventions: plain C, blittable structs, status-code returns (0 = ok, negative
+ * codes map 1:1 to the reference's exception classes), no exceptions or aborts
+ * across the ABI, no global state besides an explicit context.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * JB_ERR_NO_DEVICE.
+ */
+#ifndef JPEGB200_H
+#define JPEGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JB_API __attribute__((visibility("default")))
+
+/* ---- status codes (reference exception each one maps to) ------------------ */
+#define JB_OK 0
+#define JB_ERR_INVALID_DATA (-1)      /* InvalidDataException  (JpegDecoder.cs:365-375)          */
+#define JB_ERR_INVALID_OPERATION (-2) /* InvalidOperationException, incl. "Expect restart marker."
+                                         (ScanDecoder/JpegHuffmanBaselineScanDecoder.cs:151-154) */
+#define JB_ERR_NOT_SUPPORTED (-3)     /* NotSupportedException (JpegDecoder.cs:627-630)          */
+#define JB_ERR_ARGUMENT (-4)          /* ArgumentException / ArgumentOutOfRange / ArgumentNull   */
+#define JB_ERR_NO_DEVICE (-5)         /* no CUDA device / driver: there is no CPU fallback       */
+#define JB_ERR_CUDA (-6)              /* CUDA runtime failure; see jb_last_error                 */
+#define JB_ERR_NOMEM (-7)
+
+#define JB_MAX_COMPONENTS 4
+
+/* ---- output formats of the decode path ------------------------------------ */
+#define JB_OUT_RGB24 0      /* D9+D10+D11: replicate, clamp, YCbCr->RGB; 3 B/pixel             */
+#define JB_OUT_RGBA32 1     /* same, A = 255 (JpegYCbCrToRgbConverter.cs:134-169)              */
+#define JB_OUT_YCBCR888 2   /* D9+D10 only: what JpegBufferOutputWriter8Bit leaves in memory   */
+#define JB_OUT_PLANAR_I16 3 /* D9 only: unclamped int16 component planes [c][H][W] -- exactly the
+                               samples WriteBlock receives; the compatibility path replays
+                               WriteBlock calls from it on the host                            */
+#define JB_OUT_COEFFICIENTS 4 /* D4/P3-P5 only: zig-zag int16 blocks with absolute DC, in the device
+                                 store layout described by jb_coef_layout                       */
+
+/* DHT as it appears in the stream (JpegHuffmanDecodingTable.TryParse :249-291) */
+typedef struct jb_huff_spec {
+    uint8_t table_class; /* 0 = DC, 1 = AC */
+    uint8_t identifier;  /* 0..3 */
+    uint8_t bits[16];
+    uint8_t values[256];
+    uint16_t value_count;
+} jb_huff_spec;
+
+/* One SOS (JpegScanHeader.cs) with the tables in force when it was met. */
+typedef struct jb_scan_desc {
+    uint8_t component_count;                       /* Ns */
+    uint8_t component_index[JB_MAX_COMPONENTS];    /* index into the frame's components */
+    int16_t dc_table[JB_MAX_COMPONENTS];           /* index into jb_image_desc.tables, -1 = undefined */
+    int16_t ac_table[JB_MAX_COMPONENTS];
+    uint8_t ss, se, ah, al;
+    uint32_t restart_interval;                     /* DRI in force (JpegDecoder.cs:635-650) */
+    uint64_t entropy_offset;                       /* first entropy-coded byte, relative to data */
+    uint64_t entropy_length;                       /* bytes up to (not including) the next non-RST marker */
+} jb_scan_desc;
+
+/* One image: everything JpegDecoder.Identify + the marker loop know before the hot path. */
+typedef struct jb_image_desc {
+    const uint8_t *data; /* host pointer (pinned memory from jb_pinned_alloc avoids a staging copy) */
+    uint64_t length;
+    uint8_t sof;         /* 0 baseline, 1 extended, 2 progressive (JpegMarker.StartOfFrame0..2) */
+    uint8_t precision;   /* P */
+    uint8_t component_count;
+    uint8_t reserved0;
+    uint16_t width, height;
+    uint8_t h[JB_MAX_COMPONENTS], v[JB_MAX_COMPONENTS];
+    uint16_t quant[JB_MAX_COMPONENTS][64]; /* zig-zag order; the table each component is rendered with */
+    uint32_t scan_count;
+    const jb_scan_desc *scans;
+    uint32_t table_count;
+    const jb_huff_spec *tables;
+} jb_image_desc;
+
+/* Where one image's result goes. */
+typedef struct jb_output_desc {
+    void *dst;          /* device pointer if on_device, else host pointer (pinned preferred) */
+    uint64_t pitch;     /* bytes per pixel row (plane row for PLANAR_I16); 0 = tightly packed */
+    uint64_t capacity;  /* bytes available at dst */
+    int32_t format;     /* JB_OUT_* */
+    int32_t on_device;
+} jb_output_desc;
+
+/* Layout of the device coefficient store of one image (JB_OUT_COEFFICIENTS). */
+typedef struct jb_coef_layout {
+    int32_t interleaved;            /* 1: [mcu][block-in-mcu][64] scan order (baseline);
+                                       0: per-component planes of MCU-padded block grids (progressive) */
+    int32_t mcus_per_line, mcus_per_column, blocks_per_mcu;
+    int32_t comp_block_offset[JB_MAX_COMPONENTS]; /* interleaved: first block-in-mcu index of comp;
+                                                     planar: first block of the component's plane */
+    int32_t comp_blocks_w[JB_MAX_COMPONENTS], comp_blocks_h[JB_MAX_COMPONENTS];
+    uint64_t total_blocks;
+} jb_coef_layout;
+
+typedef struct jb_ctx jb_ctx;
+typedef struct jb_batch jb_batch;
+
+/* ---- context ---------------------------------------------------------------- */
+JB_API int jb_device_count(void);
+JB_API int jb_ctx_create(int device, jb_ctx **out);
+JB_API void jb_ctx_destroy(jb_ctx *ctx);
+/* Message of the last failure on this context (image index + detail). */
+JB_API const char *jb_last_error(jb_ctx *ctx);
+/* cudaStream_t the context launches its kernels on (for CUDA-event timing by the caller). */
+JB_API void *jb_ctx_stream(jb_ctx *ctx);
+JB_API int jb_ctx_synchronize(jb_ctx *ctx);
+
+/* ---- memory ------------------------------------------------------------------- */
+JB_API int jb_pinned_alloc(jb_ctx *ctx, size_t bytes, void **out);
+JB_API int jb_pinned_free(jb_ctx *ctx, void *p);
+JB_API int jb_device_alloc(jb_ctx *ctx, size_t bytes, void **out);
+JB_API int jb_device_free(jb_ctx *ctx, void *p);
+JB_API int jb_memcpy_d2h(jb_ctx *ctx, void *dst_host, const void *src_device, size_t bytes);
+JB_API int jb_memcpy_h2d(jb_ctx *ctx, void *dst_device, const void *src_host, size_t bytes);
+
+/* ---- decode path: replaces JpegScanDecoder.ProcessScan + Dispose for a batch ---- */
+/* Validates the descriptors, builds device Huffman/quant tables, allocates the device
+   input + coefficient store.  Nothing is copied or launched yet. */
+JB_API int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_output_desc *outputs,
+                                  int count, jb_batch **out);
+/* H2D of the compressed bytes (cudaMemcpyAsync on the context stream). */
+JB_API int jb_decode_batch_upload(jb_batch *b);
+/* Launches the decode kernels (restart scan, Huffman, IDCT+colour) on the context stream;
+   results land in device memory (the outputs' dst when on_device, else a device staging area). */
+JB_API int jb_decode_batch_launch(jb_batch *b);
+/* D2H of results for outputs with on_device == 0, then waits and collects per-image status. */
+JB_API int jb_decode_batch_finish(jb_batch *b);
+/* upload + launch + finish. Returns the first non-zero per-image status (or 0). */
+JB_API int jb_decode_batch_run(jb_batch *b);
+/* Per-image status codes after finish (JB_OK / JB_ERR_*). */
+JB_API int jb_decode_batch_status(jb_batch *b, int32_t *status, int count);
+JB_API int jb_decode_batch_coef_layout(jb_batch *b, int image, jb_coef_layout *out);
+/* Number of kernels launched by the last jb_decode_batch_launch. */
+JB_API int jb_decode_batch_launch_count(jb_batch *b);
+/* Per-kernel timing of one extra profiled launch: fills names/ms for up to `cap` kernels,
+   returns the number of kernels. Uses CUDA events on the context stream. */
+JB_API int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap);
+JB_API void jb_decode_batch_destroy(jb_batch *b);
+
+/* One-call convenience: create + run + destroy. */
+JB_API int jb_decode(jb_ctx *ctx, const jb_image_desc *images, const jb_output_desc *outputs, int count,
+                     int32_t *status);
+
+/* ---- stand-alone stages (unit-parity entry points) ------------------------------ */
+/* D6-D11 on caller-provided coefficient blocks (device pointers): the IDCT+colour kernel alone.
+   `coef` uses the layout jb_coef_layout describes for `image`. */
+JB_API int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const int16_t *coef_device,
+                                       const jb_output_desc *output);
+
+JB_API const char *jb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,447 @@
+"""Python mirror of the reference's public surface for the hot path, over the C-ABI.
+
+Same names, argument meaning and error behaviour as the C# API (PascalCase kept on purpose so
+the parity tests read like the reference's own tests):
+
+    JpegDecoder.SetInput / Identify / SetOutputWriter / Decode      (src/JpegLibrary/JpegDecoder.cs:49,75,501,509)
+    JpegBlockOutputWriter.WriteBlock                                (src/JpegLibrary/JpegBlockOutputWriter.cs:17)
+
+The marker walk runs on the host (libjpegb200_host.so); everything per-block runs on the GPU
+through libjpegb200.so.  Recognised GPU-aware writers (CudaOutputWriter) never see WriteBlock:
+kernels store straight into their buffer.  Any other JpegBlockOutputWriter gets the
+compatibility path: unclamped int16 planes come back from the GPU and the reference's exact
+WriteBlock call sequence is replayed on the host.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+
+class InvalidDataException(Exception):
+    pass
+
+
+class InvalidOperationException(Exception):
+    pass
+
+
+class NotSupportedException(Exception):
+    pass
+
+
+class ArgumentException(Exception):
+    pass
+
+
+class CudaRuntimeError(RuntimeError):
+    pass
+
+
+def _raise(code, msg):
+    msg = msg.decode() if isinstance(msg, bytes) else msg
+    if code == N.JB_ERR_INVALID_DATA:
+        raise InvalidDataException(msg)
+    if code == N.JB_ERR_INVALID_OPERATION:
+        raise InvalidOperationException(msg)
+    if code == N.JB_ERR_NOT_SUPPORTED:
+        raise NotSupportedException(msg)
+    if code == N.JB_ERR_ARGUMENT:
+        raise ArgumentException(msg)
+    if code == N.JB_ERR_NO_DEVICE:
+        raise CudaRuntimeError("no CUDA device: jpeglibrary_b200 has no CPU fallback")
+    raise CudaRuntimeError(f"jpegb200 error {code}: {msg}")
+
+
+class Context:
+    """jb_ctx wrapper: one per GPU."""
+
+    _default = {}
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        rc = N.cuda.jb_ctx_create(device, C.byref(h))
+        if rc:
+            _raise(rc, "jb_ctx_create failed")
+        self.handle = h
+        self.device = device
+
+    @classmethod
+    def default(cls, device=0):
+        if device not in cls._default:
+            cls._default[device] = cls(device)
+        return cls._default[device]
+
+    def last_error(self):
+        return N.cuda.jb_last_error(self.handle).decode()
+
+    def check(self, rc):
+        if rc:
+            _raise(rc, self.last_error())
+
+    @property
+    def stream(self):
+        return N.cuda.jb_ctx_stream(self.handle)
+
+    def synchronize(self):
+        self.check(N.cuda.jb_ctx_synchronize(self.handle))
+
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(N.cuda.jb_device_alloc(self.handle, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, ptr):
+        N.cuda.jb_device_free(self.handle, C.c_void_p(ptr))
+
+    def pinned_alloc(self, nbytes):
+        p = C.c_void_p()
+        self.check(N.cuda.jb_pinned_alloc(self.handle, nbytes, C.byref(p)))
+        return p.value
+
+    def pinned_free(self, ptr):
+        N.cuda.jb_pinned_free(self.handle, C.c_void_p(ptr))
+
+    def pinned_array(self, nbytes):
+        """numpy uint8 view of a fresh pinned allocation (freed with pinned_free(arr.ctypes.data))."""
+        p = self.pinned_alloc(nbytes)
+        return np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p))
+
+    def d2h(self, dst: np.ndarray, src_ptr):
+        self.check(N.cuda.jb_memcpy_d2h(self.handle, dst.ctypes.data, C.c_void_p(src_ptr), dst.nbytes))
+
+    def h2d(self, dst_ptr, src: np.ndarray):
+        self.check(N.cuda.jb_memcpy_h2d(self.handle, C.c_void_p(dst_ptr), src.ctypes.data, src.nbytes))
+
+
+class Parsed:
+    """Result of the host marker walk for one stream (owns the native descriptor)."""
+
+    def __init__(self, data):
+        self._buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        h = C.c_void_p()
+        rc = N.host.jbh_parse(self._buf.ctypes.data, self._buf.size, C.byref(h))
+        if rc:
+            _raise(rc, N.host.jbh_last_parse_error())
+        self.handle = h
+        self.desc = N.host.jbh_desc(h).contents
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            N.host.jbh_free(h)
+            self.handle = None
+
+    @property
+    def consumed(self):
+        return N.host.jbh_consumed(self.handle)
+
+
+# ------------------------------------------------------------------------------------------
+class JpegBlockOutputWriter:
+    """src/JpegLibrary/JpegBlockOutputWriter.cs:8-18"""
+
+    def WriteBlock(self, blockRef, componentIndex, x, y):
+        raise NotImplementedError
+
+
+class CudaOutputWriter(JpegBlockOutputWriter):
+    """Recognised GPU-aware sink: the kernels write `format` pixels straight into `buffer`
+    (a numpy array in host memory, or an int device pointer with on_device=True) with the
+    semantics of apps/JpegDecode (JpegBufferOutputWriter8Bit + JpegYCbCrToRgbConverter).
+    WriteBlock is never called."""
+
+    def __init__(self, buffer, format=N.JB_OUT_RGB24, pitch=0, on_device=False, capacity=0):
+        self.buffer = buffer
+        self.format = format
+        self.pitch = pitch
+        self.on_device = on_device
+        self.capacity = capacity if on_device else (buffer.nbytes if capacity == 0 else capacity)
+
+    def _output_desc(self):
+        o = N.OutputDesc()
+        o.dst = self.buffer if self.on_device else self.buffer.ctypes.data
+        o.pitch = self.pitch
+        o.capacity = self.capacity
+        o.format = self.format
+        o.on_device = 1 if self.on_device else 0
+        return o
+
+    def WriteBlock(self, blockRef, componentIndex, x, y):  # pragma: no cover
+        raise InvalidOperationException("CudaOutputWriter is filled by the GPU, not by WriteBlock calls")
+
+
+class JpegDecoder:
+    """Mirror of JpegLibrary.JpegDecoder for the Huffman DCT path."""
+
+    def __init__(self, context=None):
+        self._ctx = context
+        self._input = None
+        self._parsed = None
+        self._writer = None
+
+    # JpegDecoder.cs:49-62
+    def SetInput(self, data):
+        self._input = data
+        self._parsed = None
+
+    # JpegDecoder.cs:75-105
+    def Identify(self, loadQuantizationTables=False):
+        if self._input is None or len(self._input) == 0:
+            raise InvalidOperationException("Input buffer is not specified.")
+        self._parsed = Parsed(self._input)
+        return self._parsed.consumed
+
+    def _frame(self):
+        if self._parsed is None:
+            raise InvalidOperationException("Call Identify() before this operation.")
+        return self._parsed.desc
+
+    Width = property(lambda s: s._frame().width)
+    Height = property(lambda s: s._frame().height)
+    Precision = property(lambda s: s._frame().precision)
+    NumberOfComponents = property(lambda s: s._frame().component_count)
+
+    def GetMaximumHorizontalSampling(self):
+        d = self._frame()
+        return max(d.h[i] for i in range(d.component_count))
+
+    def GetMaximumVerticalSampling(self):
+        d = self._frame()
+        return max(d.v[i] for i in range(d.component_count))
+
+    def GetHorizontalSampling(self, componentIndex):
+        d = self._frame()
+        if not 0 <= componentIndex < d.component_count:
+            raise ArgumentException("componentIndex")
+        return d.h[componentIndex]
+
+    def GetVerticalSampling(self, componentIndex):
+        d = self._frame()
+        if not 0 <= componentIndex < d.component_count:
+            raise ArgumentException("componentIndex")
+        return d.v[componentIndex]
+
+    # JpegDecoder.cs:501
+    def SetOutputWriter(self, outputWriter):
+        if outputWriter is None:
+            raise ArgumentException("outputWriter")
+        self._writer = outputWriter
+
+    # JpegDecoder.cs:509-550
+    def Decode(self):
+        if self._input is None or len(self._input) == 0:
+            raise InvalidOperationException("Input buffer is not specified.")
+        if self._writer is None:
+            raise InvalidOperationException("The output buffer is not specified.")
+        if self._parsed is None:
+            self._parsed = Parsed(self._input)
+        ctx = self._ctx or Context.default()
+        d = self._parsed.desc
+        if isinstance(self._writer, CudaOutputWriter):
+            out = self._writer._output_desc()
+            ctx.check(N.cuda.jb_decode(ctx.handle, C.byref(d), C.byref(out), 1, None))
+            return
+        # compatibility path: unclamped planes from the GPU, WriteBlock replay on the host
+        W, H, n = d.width, d.height, d.component_count
+        planes = np.empty((n, H, W), dtype=np.int16)
+        out = CudaOutputWriter(planes, N.JB_OUT_PLANAR_I16)._output_desc()
+        ctx.check(N.cuda.jb_decode(ctx.handle, C.byref(d), C.byref(out), 1, None))
+        _replay_write_blocks(d, planes, self._writer)
+
+
+def _replay_write_blocks(d, planes, writer):
+    """Issue the reference's WriteBlock sequence from full-resolution planes.
+
+    Baseline/extended: MCU order, components in scan order, v rows x h cols of blocks, each block
+    expanded into hs x vs replicated 8x8 blocks (JpegHuffmanBaselineScanDecoder.cs:99-137, 238-268).
+    Progressive: per component, block rows then columns (JpegBlockAllocator.Flush :120-149)."""
+    n, H, W = planes.shape
+    hmax = max(d.h[i] for i in range(n))
+    vmax = max(d.v[i] for i in range(n))
+    mcus_x = (W + 8 * hmax - 1) // (8 * hmax)
+    mcus_y = (H + 8 * vmax - 1) // (8 * vmax)
+    padded = np.zeros((n, mcus_y * 8 * vmax, mcus_x * 8 * hmax), dtype=np.int16)
+    padded[:, :H, :W] = planes
+    # samples outside the image are never observable through a clipping writer; blocks that
+    # start outside still get a call, like in the reference
+
+    def emit(ci, x, y):
+        blk = np.ascontiguousarray(padded[ci, y:y + 8, x:x + 8]).reshape(64)
+        writer.WriteBlock(blk, ci, x, y)
+
+    if d.sof != 2:
+        sc = d.scans[0]
+        order = [sc.component_index[i] for i in range(sc.component_count)]
+        for my in range(mcus_y):
+            for mx in range(mcus_x):
+                for ci in order:
+                    h, v = d.h[ci], d.v[ci]
+                    hs, vs = hmax // h, vmax // v
+                    for by in range(v):
+                        for bx in range(h):
+                            x0 = (mx * hmax + bx) * 8  # :134; h is 1 or hmax on the GPU path
+                            y0 = (my * vmax + by) * 8
+                            for sv in range(vs):
+                                for sh in range(hs):
+                                    emit(ci, x0 + 8 * sh, y0 + 8 * sv)
+    else:
+        wblk, hblk = (W + 7) // 8, (H + 7) // 8
+        for ci in range(n):
+            hs, vs = hmax // d.h[ci], vmax // d.v[ci]
+            cw, ch = (wblk + hs - 1) // hs, (hblk + vs - 1) // vs
+            for row in range(ch):
+                for col in range(cw):
+                    for sv in range(vs):
+                        for sh in range(hs):
+                            emit(ci, col * hs * 8 + 8 * sh, row * vs * 8 + 8 * sv)
+
+
+# ------------------------------------------------------------------------------------------
+class JpegBatchDecoder:
+    """Batch facade: one Decode() exposes a single image of parallelism, a batch
+    exposes thousands of restart segments.  Streams are parsed on host threads, staged into one
+    device arena and decoded by three kernel launches for the whole batch."""
+
+    def __init__(self, blobs, format=N.JB_OUT_RGB24, context=None, device_output=True, parse_threads=8,
+                 host_outputs=None):
+        self.ctx = context or Context.default()
+        n = len(blobs)
+        self.count = n
+        self._bufs = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
+        lens = (C.c_uint64 * n)(*[b.size for b in self._bufs])
+        self._parsed = (C.c_void_p * n)()
+        failed = N.host.jbh_parse_batch(ptrs, lens, n, parse_threads, self._parsed)
+        if failed:
+            self._free_parsed()
+            raise InvalidDataException(f"{failed} of {n} streams failed the marker walk")
+        self.descs = (N.ImageDesc * n)()
+        N.host.jbh_collect_descs(self._parsed, n, self.descs)
+        self.format = format
+        bpp = {N.JB_OUT_RGB24: 3, N.JB_OUT_RGBA32: 4, N.JB_OUT_YCBCR888: 3}.get(format)
+        self.outs = (N.OutputDesc * n)()
+        self.sizes = []
+        self._dev_out = None
+        self.host_outputs = host_outputs
+        total = 0
+        offs = []
+        for i in range(n):
+            d = self.descs[i]
+            if format == N.JB_OUT_PLANAR_I16:
+                sz = d.width * d.height * 2 * d.component_count
+            elif format == N.JB_OUT_COEFFICIENTS:
+                raise ArgumentException("use JpegDecoder for coefficient output")
+            else:
+                sz = d.width * d.height * bpp
+            offs.append(total)
+            self.sizes.append(sz)
+            total += (sz + 255) // 256 * 256
+        self.total_out_bytes = total
+        if device_output:
+            self._dev_out = self.ctx.device_alloc(max(total, 256))
+        elif host_outputs is None:
+            self.host_outputs = self.ctx.pinned_array(max(total, 256))
+            self._own_pinned = True
+        self.offsets = offs
+        for i in range(n):
+            o = self.outs[i]
+            o.dst = (self._dev_out + offs[i]) if device_output else (self.host_outputs.ctypes.data + offs[i])
+            o.pitch = 0
+            o.capacity = self.sizes[i]
+            o.format = format
+            o.on_device = 1 if device_output else 0
+        h = C.c_void_p()
+        rc = N.cuda.jb_decode_batch_create(self.ctx.handle, self.descs, self.outs, n, C.byref(h))
+        if rc:
+            self.close()
+            _raise(rc, self.ctx.last_error())
+        self.handle = h
+
+    def upload(self):
+        self.ctx.check(N.cuda.jb_decode_batch_upload(self.handle))
+
+    def launch(self):
+        self.ctx.check(N.cuda.jb_decode_batch_launch(self.handle))
+
+    def finish(self):
+        self.ctx.check(N.cuda.jb_decode_batch_finish(self.handle))
+
+    def run(self):
+        self.ctx.check(N.cuda.jb_decode_batch_run(self.handle))
+
+    def launch_count(self):
+        return N.cuda.jb_decode_batch_launch_count(self.handle)
+
+    def profile(self):
+        names = ((C.c_char * 48) * 8)()
+        ms = (C.c_float * 8)()
+        k = N.cuda.jb_decode_batch_profile(self.handle, names, ms, 8)
+        if k < 0:
+            _raise(k, self.ctx.last_error())
+        return [(names[i].value.decode(), ms[i]) for i in range(k)]
+
+    def status(self):
+        st = (C.c_int32 * self.count)()
+        N.cuda.jb_decode_batch_status(self.handle, st, self.count)
+        return list(st)
+
+    def read_output(self, i):
+        """Copy image i's result to a new numpy array (test helper)."""
+        d = self.descs[i]
+        a = np.empty(self.sizes[i], dtype=np.uint8)
+        if self._dev_out is not None:
+            self.ctx.d2h(a, self._dev_out + self.offsets[i])
+        else:
+            a[:] = self.host_outputs[self.offsets[i]:self.offsets[i] + self.sizes[i]]
+        if self.format == N.JB_OUT_PLANAR_I16:
+            return a.view(np.int16).reshape(d.component_count, d.height, d.width)
+        return a.reshape(d.height, d.width, -1)
+
+    def _free_parsed(self):
+        for i in range(self.count):
+            if self._parsed[i]:
+                N.host.jbh_free(self._parsed[i])
+                self._parsed[i] = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            N.cuda.jb_decode_batch_destroy(self.handle)
+            self.handle = None
+        if getattr(self, "_dev_out", None):
+            self.ctx.device_free(self._dev_out)
+            self._dev_out = None
+        if getattr(self, "_own_pinned", False) and self.host_outputs is not None:
+            self.ctx.pinned_free(self.host_outputs.ctypes.data)
+            self.host_outputs = None
+            self._own_pinned = False
+        self._free_parsed()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def decode_coefficients(data, context=None):
+    """Entropy-decode one stream on the GPU and return (layout, int16 blocks[total, 64])."""
+    ctx = context or Context.default()
+    p = Parsed(data)
+    d = p.desc
+    hmax = max(d.h[i] for i in range(d.component_count))
+    vmax = max(d.v[i] for i in range(d.component_count))
+    mcus = ((d.width + 8 * hmax - 1) // (8 * hmax)) * ((d.height + 8 * vmax - 1) // (8 * vmax))
+    bpm = sum(d.h[i] * d.v[i] for i in range(d.component_count))
+    buf = np.zeros((mcus * bpm, 64), dtype=np.int16)
+    out = CudaOutputWriter(buf, N.JB_OUT_COEFFICIENTS)._output_desc()
+    h = C.c_void_p()
+    ctx.check(N.cuda.jb_decode_batch_create(ctx.handle, C.byref(d), C.byref(out), 1, C.byref(h)))
+    try:
+        ctx.check(N.cuda.jb_decode_batch_run(h))
+        lay = N.CoefLayout()
+        N.cuda.jb_decode_batch_coef_layout(h, 0, C.byref(lay))
+    finally:
+        N.cuda.jb_decode_batch_destroy(h)
+    return lay, buf

@@ -1,0 +1,81 @@
+// jb_device.cuh -- device-side data structures shared by the decode kernels.
+//
+// Data layout in HBM (see DESIGN.md "Data layout"):
+//   * compressed bytes: one arena, every image's entropy-coded segment starts 256-B aligned;
+//   * restart-marker index: uint32 per marker, (byte position << 4) | (RSTn index, or 8 for a terminator);
+//   * coefficient store: int16 blocks of 64 in ZIG-ZAG order with absolute DC.  Baseline frames use
+//     MCU scan order [mcu][block-in-mcu][64]; progressive frames use per-component planes of
+//     MCU-padded block grids (non-interleaved scans address blocks by component coordinates);
+//   * pixels: caller-provided pitch-linear buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define JB_LUT_BITS 10
+#define JB_LUT_SIZE (1 << JB_LUT_BITS)
+#define JB_MAX_BLOCKS_PER_MCU 10
+#define JB_MAX_TABLE_SLOTS 8
+
+// Huffman decoding table, device form.  Built on the host by *simulating* the reference's
+// JpegHuffmanDecodingTable.Lookup/LookupSlow (JpegHuffmanDecodingTable.cs:73-113) for every
+// 10-bit prefix, so every code -- valid or not -- resolves exactly as in the reference.
+struct __align__(16) JbHuffTable {
+    uint16_t lut[JB_LUT_SIZE]; // (symbol << 8) | code size; size 0 => slow path
+    uint16_t maxcode[20];      // reference _maxCode[0..17] (left-aligned 16-bit), padded
+    uint8_t valoffset[24];     // reference _valOffset[0..18], padded
+    uint8_t values[256];
+};
+static_assert(sizeof(JbHuffTable) % 16 == 0, "table must be copyable as uint4");
+
+struct JbDevImage {
+    // compressed input
+    uint64_t data_off;   // offset of the entropy-coded bytes in the device arena (256-B aligned)
+    uint32_t data_len;   // upper bound of entropy-coded length (bytes)
+    // restart structure
+    uint32_t dri;        // MCUs per restart interval (0: none)
+    uint32_t nseg;       // number of restart segments = ceil(total_mcus / dri) (1 if dri == 0)
+    uint32_t mark_base;  // first entry of this image in the marker index
+    uint32_t mark_cap;   // entries reserved (nseg + 1)
+    // geometry
+    uint32_t total_mcus, mcus_per_line, mcus_per_col;
+    uint16_t width, height;
+    uint8_t ncomp, precision, bpm, sof;
+    uint8_t hmax, vmax;
+    uint8_t comp_h[4], comp_v[4];
+    uint8_t comp_blk_off[4];            // first block-in-mcu of each component (interleaved layout)
+    uint8_t blk_comp[JB_MAX_BLOCKS_PER_MCU]; // component of block-in-mcu b
+    uint8_t blk_dc[JB_MAX_BLOCKS_PER_MCU];   // table slot (0..7) of block b
+    uint8_t blk_ac[JB_MAX_BLOCKS_PER_MCU];
+    uint16_t table_index[JB_MAX_TABLE_SLOTS]; // slot -> index into the device table array
+    uint8_t ntables;
+    uint8_t pad0[3];
+    // coefficient store
+    uint64_t coef_off;   // first block of this image in the coefficient store (in blocks)
+    uint32_t quant_off;  // first of ncomp quant tables (64 x uint16 each) in the quant array
+    // output
+    uint64_t out_ptr;    // device address of the image's pixels
+    uint64_t out_pitch;
+    int32_t out_format;
+    int32_t pad1;
+};
+
+// per-image result of K0 (restart scan)
+struct JbScanResult {
+    uint32_t nmarkers;   // entries written to the marker index (RSTn + at most one terminator)
+    uint32_t end_pos;    // position of the terminator marker (or data_len)
+    uint32_t end_marker; // terminator marker byte (0 if none found)
+    uint32_t pad;
+};
+
+// work item of the IDCT+colour kernel: a CTA renders a strip of consecutive MCUs of one MCU row
+struct JbTileWork {
+    uint32_t image;
+    uint32_t mcu_row;
+    uint32_t mcu_col0;
+    uint32_t nmcu;
+};
+
+// status bits written by kernels (per image)
+#define JB_ST_BAD_CODE 1u        // invalid Huffman code / magnitude category  -> InvalidDataException
+#define JB_ST_PREMATURE_END 2u   // ran out of bits inside a segment            -> InvalidDataException
+#define JB_ST_EXPECT_RST 4u      // restart marker missing / misplaced          -> InvalidOperationException

@@ -1,0 +1,750 @@
+// jpegb200.cu -- C-ABI shim (include/jpegb200.h) over the sm_100a decode kernels.
+//
+// Host responsibilities kept here (everything else is the caller's marker loop):
+//   * derive geometry from the parsed headers exactly like the reference's scan decoders
+//     (JpegHuffmanBaselineScanDecoder ctor :23-49, InitDecodeComponents JpegHuffmanScanDecoder.cs:17-72);
+//   * build device Huffman tables from the raw DHT by simulating the reference's table
+//     construction + lookup (JpegHuffmanDecodingTable.cs:293-390, :73-113);
+//   * stage compressed bytes into one device arena, launch K0/K1/K2 on one stream, move results.
+// There is no CPU decode path in this library.
+#include "../../include/jpegb200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "jb_device.cuh"
+#include "k_entropy_decode.cuh"
+#include "k_idct_color.cuh"
+
+struct jb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    cudaDeviceProp prop{};
+};
+
+#define JB_CUDA(ctx, call)                                                                       \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            char buf_[256];                                                                      \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                     __FILE__, __LINE__);                                                        \
+            (ctx)->error = buf_;                                                                 \
+            return JB_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+static int fail(jb_ctx *ctx, int code, const char *fmt, int image, const char *detail)
+{
+    char buf[320];
+    snprintf(buf, sizeof buf, fmt, image, detail);
+    ctx->error = buf;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Huffman table: reference construction, then a 10-bit LUT obtained by simulating the reference lookup
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct RefTable { // JpegHuffmanDecodingTable fields
+    uint8_t values[256];
+    uint16_t maxcode[18];
+    uint8_t valoffset[19];
+    uint8_t la_size[256], la_sym[256];
+};
+
+bool build_ref_table(const jb_huff_spec &s, RefTable &t)
+{
+    memset(&t, 0, sizeof t);
+    uint8_t huffsize[257];
+    uint16_t huffcode[257];
+    int k = 0;
+    for (int l = 1; l <= 16; l++)
+        for (int j = 0; j < s.bits[l - 1]; j++) {
+            if (k >= 256) return false;
+            huffsize[k++] = (uint8_t)l;
+        }
+    huffsize[k] = 0;
+    if (k != s.value_count) return false;
+    if (k > 0) {
+        int kk = 0, code = 0, si = huffsize[0];
+        for (;;) {
+            do {
+                huffcode[kk++] = (uint16_t)code++;
+            } while (huffsize[kk] == si);
+            if (huffsize[kk] == 0) break;
+            do {
+                code <<= 1;
+                si++;
+            } while (huffsize[kk] != si);
+        }
+    }
+    memcpy(t.values, s.values, (size_t)k);
+    int p = 0;
+    for (int l = 1; l <= 16; l++) {
+        if (s.bits[l - 1]) {
+            t.valoffset[l] = (uint8_t)(p - huffcode[p]);
+            p += s.bits[l - 1];
+            uint16_t mc = (uint16_t)(huffcode[p - 1] << (16 - l));
+            t.maxcode[l] = (uint16_t)(mc | ((1u << (16 - l)) - 1u));
+        } else
+            t.maxcode[l] = 0; // the reference leaves 0 here (not -1): reproduced on purpose
+    }
+    t.maxcode[17] = 0xFFFF;
+    p = 0;
+    for (int l = 1; l <= 8; l++)
+        for (int i = 0; i < s.bits[l - 1]; i++, p++) {
+            int fb = 8 - l;
+            int code = (uint8_t)(huffcode[p] << fb);
+            for (int j = 0; j < (1 << fb); j++) {
+                t.la_size[code + j] = (uint8_t)l;
+                t.la_sym[code + j] = t.values[p];
+            }
+        }
+    return true;
+}
+
+// returns size (1..17) and symbol as the reference's Lookup would
+void ref_lookup(const RefTable &t, int code16, int &size, int &sym)
+{
+    int h = code16 >> 8;
+    if (t.la_size[h]) {
+        size = t.la_size[h];
+        sym = t.la_sym[h];
+        return;
+    }
+    size = 9;
+    while (code16 > t.maxcode[size]) size++;
+    sym = size > 16 ? 0 : t.values[(t.valoffset[size] + (code16 >> (16 - size))) & 0xFF];
+}
+
+bool build_device_table(const jb_huff_spec &s, JbHuffTable &d)
+{
+    RefTable t;
+    if (!build_ref_table(s, t)) return false;
+    memset(&d, 0, sizeof d);
+    for (int p = 0; p < JB_LUT_SIZE; p++) {
+        int lo = p << (16 - JB_LUT_BITS), hi = lo | ((1 << (16 - JB_LUT_BITS)) - 1);
+        int s1, y1, s2, y2;
+        ref_lookup(t, lo, s1, y1);
+        ref_lookup(t, hi, s2, y2);
+        if (s1 == s2 && y1 == y2 && s1 <= JB_LUT_BITS) d.lut[p] = (uint16_t)((y1 << 8) | s1);
+    }
+    memcpy(d.maxcode, t.maxcode, sizeof t.maxcode);
+    memcpy(d.valoffset, t.valoffset, sizeof t.valoffset);
+    memcpy(d.values, t.values, 256);
+    return true;
+}
+
+struct ImagePlan {
+    JbDevImage dev{};
+    uint64_t entropy_off = 0, entropy_len = 0; // in the host blob
+    uint64_t out_bytes = 0;                    // bytes of the result
+    uint64_t total_blocks = 0;
+    jb_output_desc out{};
+    void *dev_out = nullptr; // device address the kernels write (user's or staging)
+    jb_coef_layout layout{};
+};
+
+} // namespace
+
+struct jb_batch {
+    jb_ctx *ctx = nullptr;
+    int count = 0;
+    std::vector<ImagePlan> plans;
+    std::vector<const uint8_t *> host_data;
+    std::vector<JbHuffTable> tables;
+    std::vector<uint16_t> quant;
+    // device
+    uint8_t *d_arena = nullptr;
+    uint64_t arena_bytes = 0;
+    JbDevImage *d_images = nullptr;
+    JbHuffTable *d_tables = nullptr;
+    uint16_t *d_quant = nullptr;
+    uint32_t *d_marks = nullptr;
+    uint64_t marks_count = 0;
+    JbScanResult *d_scan = nullptr;
+    int16_t *d_coef = nullptr;
+    uint64_t coef_blocks = 0;
+    uint32_t *d_status = nullptr;
+    uint8_t *d_out_staging = nullptr;
+    uint64_t out_staging_bytes = 0;
+    std::vector<uint32_t> h_status;
+    uint32_t max_k1_ctas = 0, max_k2_tiles = 0;
+    bool need_render = false;
+    int launches = 0;
+    bool uploaded_meta = false;
+};
+
+static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *jb_version(void) { return "jpegb200 0.1 (sm_100a)"; }
+
+int jb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int jb_ctx_create(int device, jb_ctx **out)
+{
+    if (!out) return JB_ERR_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return JB_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return JB_ERR_ARGUMENT;
+    jb_ctx *c = new (std::nothrow) jb_ctx;
+    if (!c) return JB_ERR_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return JB_ERR_CUDA;
+    }
+    *out = c;
+    return JB_OK;
+}
+
+void jb_ctx_destroy(jb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *jb_last_error(jb_ctx *ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+void *jb_ctx_stream(jb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int jb_ctx_synchronize(jb_ctx *ctx)
+{
+    if (!ctx) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+int jb_pinned_alloc(jb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return JB_OK;
+}
+int jb_pinned_free(jb_ctx *ctx, void *p)
+{
+    if (!ctx) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaFreeHost(p));
+    return JB_OK;
+}
+int jb_device_alloc(jb_ctx *ctx, size_t bytes, void **out)
+{
+    if (!ctx || !out) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaMalloc(out, bytes));
+    return JB_OK;
+}
+int jb_device_free(jb_ctx *ctx, void *p)
+{
+    if (!ctx) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaFree(p));
+    return JB_OK;
+}
+int jb_memcpy_d2h(jb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+int jb_memcpy_h2d(jb_ctx *ctx, void *dst, const void *src, size_t bytes)
+{
+    if (!ctx) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return JB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan one image: geometry, layout, validation
+// ------------------------------------------------------------------------------------------------
+static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl,
+                      std::vector<JbHuffTable> &tables, std::map<std::string, int> &table_ids,
+                      std::vector<uint16_t> &quant)
+{
+    if (!im.data || im.length == 0) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "no input data");
+    if (im.component_count < 1 || im.component_count > JB_MAX_COMPONENTS)
+        return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad component count");
+    if (im.width == 0 || im.height == 0) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "empty frame");
+    if (im.sof > 1)
+        return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
+                    "only SOF0/SOF1 Huffman frames are handled by this build of the GPU path");
+    if (im.precision < 2 || im.precision > 16)
+        return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
+    if (im.scan_count != 1 || !im.scans)
+        return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
+                    "sequential frames must consist of one interleaved scan (reference quirk Q2)");
+    const jb_scan_desc &sc = im.scans[0];
+    if (sc.component_count != im.component_count)
+        return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
+                    "sequential scan must contain every frame component (reference quirk Q2)");
+
+    JbDevImage &d = pl.dev;
+    int hmax = 1, vmax = 1;
+    for (int c = 0; c < im.component_count; c++) {
+        if (im.h[c] < 1 || im.h[c] > 4 || im.v[c] < 1 || im.v[c] > 4)
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sampling factor");
+        hmax = std::max<int>(hmax, im.h[c]);
+        vmax = std::max<int>(vmax, im.v[c]);
+    }
+    for (int c = 0; c < im.component_count; c++) {
+        int hs = hmax / im.h[c], vs = vmax / im.v[c];
+        // the reference places a component's blocks at (mcu*Hmax + x)*8 and replicates by Hmax/h
+        // (JpegHuffmanBaselineScanDecoder.cs:134,238-268): self-consistent only for h in {1, Hmax}
+        bool ok = (im.h[c] == 1 || im.h[c] == hmax) && (im.v[c] == 1 || im.v[c] == vmax) &&
+                  (hs == 1 || hs == 2 || hs == 4) && (vs == 1 || vs == 2 || vs == 4);
+        if (!ok)
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
+                        "sampling factors must be 1 or the maximum, ratio 1/2/4 (reference quirk Q2)");
+    }
+    d.width = im.width;
+    d.height = im.height;
+    d.ncomp = im.component_count;
+    d.precision = im.precision;
+    d.sof = im.sof;
+    d.hmax = (uint8_t)hmax;
+    d.vmax = (uint8_t)vmax;
+    d.mcus_per_line = (im.width + 8 * hmax - 1) / (8 * hmax);
+    d.mcus_per_col = (im.height + 8 * vmax - 1) / (8 * vmax);
+    d.total_mcus = d.mcus_per_line * d.mcus_per_col;
+
+    // scan-order MCU layout
+    int bpm = 0;
+    std::map<int, int> slot_of_table;
+    bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
+    for (int i = 0; i < sc.component_count; i++) {
+        int c = sc.component_index[i];
+        if (c >= im.component_count || seen[c])
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+        seen[c] = true;
+        d.comp_h[c] = im.h[c];
+        d.comp_v[c] = im.v[c];
+        d.comp_blk_off[c] = (uint8_t)bpm;
+        int tabs[2] = {sc.dc_table[i], sc.ac_table[i]};
+        int slots[2];
+        for (int k = 0; k < 2; k++) {
+            if (tabs[k] < 0 || (uint32_t)tabs[k] >= im.table_count || !im.tables)
+                return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
+            const jb_huff_spec &hs = im.tables[tabs[k]];
+            if (hs.table_class != k)
+                return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table class mismatch");
+            auto it = slot_of_table.find(tabs[k]);
+            if (it == slot_of_table.end()) {
+                std::string key(reinterpret_cast<const char *>(&hs), sizeof hs);
+                auto g = table_ids.find(key);
+                int gid;
+                if (g == table_ids.end()) {
+                    JbHuffTable t;
+                    if (!build_device_table(hs, t))
+                        return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
+                    gid = (int)tables.size();
+                    tables.push_back(t);
+                    table_ids.emplace(std::move(key), gid);
+                } else
+                    gid = g->second;
+                int slot = (int)slot_of_table.size();
+                if (slot >= JB_MAX_TABLE_SLOTS) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "too many tables");
+                d.table_index[slot] = (uint16_t)gid;
+                slot_of_table[tabs[k]] = slot;
+                slots[k] = slot;
+            } else
+                slots[k] = it->second;
+        }
+        for (int b = 0; b < im.h[c] * im.v[c]; b++) {
+            if (bpm >= JB_MAX_BLOCKS_PER_MCU) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "MCU too large");
+            d.blk_comp[bpm] = (uint8_t)c;
+            d.blk_dc[bpm] = (uint8_t)slots[0];
+            d.blk_ac[bpm] = (uint8_t)slots[1];
+            bpm++;
+        }
+    }
+    d.bpm = (uint8_t)bpm;
+    d.ntables = (uint8_t)slot_of_table.size();
+    d.dri = sc.restart_interval;
+    d.nseg = d.dri ? (d.total_mcus + d.dri - 1) / d.dri : 1;
+    d.mark_cap = d.nseg + 1;
+    if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
+    pl.entropy_off = sc.entropy_offset;
+    pl.entropy_len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length, im.length - sc.entropy_offset)
+                                       : im.length - sc.entropy_offset;
+    if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
+    d.data_len = (uint32_t)pl.entropy_len;
+    pl.total_blocks = (uint64_t)d.total_mcus * bpm;
+
+    d.quant_off = (uint32_t)quant.size();
+    for (int c = 0; c < im.component_count; c++)
+        for (int i = 0; i < 64; i++) quant.push_back(im.quant[c][i]);
+
+    // layout descriptor
+    jb_coef_layout &L = pl.layout;
+    L.interleaved = 1;
+    L.mcus_per_line = (int)d.mcus_per_line;
+    L.mcus_per_column = (int)d.mcus_per_col;
+    L.blocks_per_mcu = bpm;
+    for (int c = 0; c < im.component_count; c++) {
+        L.comp_block_offset[c] = d.comp_blk_off[c];
+        L.comp_blocks_w[c] = (int)d.mcus_per_line * im.h[c];
+        L.comp_blocks_h[c] = (int)d.mcus_per_col * im.v[c];
+    }
+    L.total_blocks = pl.total_blocks;
+
+    // output
+    if (outp) {
+        pl.out = *outp;
+        const int fmt = outp->format;
+        uint64_t pitch = outp->pitch, bytes = 0;
+        switch (fmt) {
+        case JB_OUT_RGB24:
+        case JB_OUT_YCBCR888:
+            if (!pitch) pitch = (uint64_t)im.width * 3;
+            if (pitch < (uint64_t)im.width * 3) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "pitch too small");
+            bytes = pitch * im.height;
+            break;
+        case JB_OUT_RGBA32:
+            if (!pitch) pitch = (uint64_t)im.width * 4;
+            if (pitch < (uint64_t)im.width * 4) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "pitch too small");
+            bytes = pitch * im.height;
+            break;
+        case JB_OUT_PLANAR_I16:
+            if (!pitch) pitch = (uint64_t)im.width * 2;
+            if (pitch < (uint64_t)im.width * 2 || (pitch & 1)) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "bad pitch");
+            bytes = pitch * im.height * im.component_count;
+            break;
+        case JB_OUT_COEFFICIENTS:
+            pitch = 0;
+            bytes = pl.total_blocks * 128;
+            break;
+        default:
+            return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "unknown output format");
+        }
+        if ((fmt == JB_OUT_RGB24 || fmt == JB_OUT_RGBA32 || fmt == JB_OUT_YCBCR888) && im.component_count != 1 &&
+            im.component_count != 3)
+            // apps/JpegDecode/DecodeAction.cs:30-34
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "This color space is not supported");
+        if (!outp->dst) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "null destination");
+        if (outp->capacity && outp->capacity < bytes)
+            return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "Destination buffer is too small.");
+        d.out_pitch = pitch;
+        d.out_format = fmt;
+        pl.out_bytes = bytes;
+    }
+    return JB_OK;
+}
+
+int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_output_desc *outputs, int count,
+                           jb_batch **out)
+{
+    if (!ctx || !images || !outputs || !out || count <= 0) return JB_ERR_ARGUMENT;
+    *out = nullptr;
+    if (count > 65535) return fail(ctx, JB_ERR_ARGUMENT, "batch of %d: %s", count, "at most 65535 images per batch");
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    jb_batch *b = new (std::nothrow) jb_batch;
+    if (!b) return JB_ERR_NOMEM;
+    b->ctx = ctx;
+    b->count = count;
+    b->plans.resize(count);
+    b->host_data.resize(count);
+    std::map<std::string, int> table_ids;
+    uint64_t arena = 0, marks = 0, blocks = 0, staging = 0;
+    for (int i = 0; i < count; i++) {
+        int rc = plan_image(ctx, i, images[i], outputs + i, b->plans[i], b->tables, table_ids, b->quant);
+        if (rc) {
+            delete b;
+            return rc;
+        }
+        ImagePlan &pl = b->plans[i];
+        b->host_data[i] = images[i].data + pl.entropy_off;
+        pl.dev.data_off = arena;
+        arena += align_up(pl.entropy_len + 64, 256);
+        pl.dev.mark_base = (uint32_t)marks;
+        marks += pl.dev.mark_cap;
+        pl.dev.coef_off = blocks;
+        blocks += pl.total_blocks;
+        if (pl.out.format != JB_OUT_COEFFICIENTS) b->need_render = true;
+        if (!pl.out.on_device) {
+            staging = align_up(staging, 256);
+            pl.dev_out = reinterpret_cast<void *>(staging); // offset for now
+            staging += pl.out_bytes;
+        } else
+            pl.dev_out = pl.out.dst;
+        b->max_k1_ctas = std::max(b->max_k1_ctas, (pl.dev.nseg + JB_K1_THREADS - 1) / JB_K1_THREADS);
+        uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
+        uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
+        b->max_k2_tiles = std::max(b->max_k2_tiles, strips * pl.dev.mcus_per_col);
+    }
+    b->arena_bytes = arena + 256;
+    b->marks_count = marks;
+    b->coef_blocks = blocks;
+    b->out_staging_bytes = staging;
+    b->h_status.assign(count, 0);
+
+#define JB_CUDA_B(call)                                            \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) {                                   \
+            ctx->error = std::string(#call " failed: ") + cudaGetErrorString(e_); \
+            jb_decode_batch_destroy(b);                            \
+            return e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA; \
+        }                                                          \
+    } while (0)
+    JB_CUDA_B(cudaMalloc(&b->d_arena, b->arena_bytes));
+    JB_CUDA_B(cudaMalloc(&b->d_images, sizeof(JbDevImage) * count));
+    JB_CUDA_B(cudaMalloc(&b->d_tables, sizeof(JbHuffTable) * b->tables.size()));
+    JB_CUDA_B(cudaMalloc(&b->d_quant, sizeof(uint16_t) * b->quant.size()));
+    JB_CUDA_B(cudaMalloc(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1)));
+    JB_CUDA_B(cudaMalloc(&b->d_scan, sizeof(JbScanResult) * count));
+    JB_CUDA_B(cudaMalloc(&b->d_coef, blocks * 128));
+    JB_CUDA_B(cudaMalloc(&b->d_status, sizeof(uint32_t) * count));
+    if (staging) JB_CUDA_B(cudaMalloc(&b->d_out_staging, staging));
+    for (int i = 0; i < count; i++) {
+        ImagePlan &pl = b->plans[i];
+        if (!pl.out.on_device) pl.dev_out = b->d_out_staging + reinterpret_cast<uint64_t>(pl.dev_out);
+        pl.dev.out_ptr = reinterpret_cast<uint64_t>(pl.dev_out);
+    }
+    // metadata upload (small): images, tables, quant
+    std::vector<JbDevImage> h_images(count);
+    for (int i = 0; i < count; i++) h_images[i] = b->plans[i].dev;
+    JB_CUDA_B(cudaMemcpyAsync(b->d_images, h_images.data(), sizeof(JbDevImage) * count, cudaMemcpyHostToDevice, ctx->stream));
+    JB_CUDA_B(cudaMemcpyAsync(b->d_tables, b->tables.data(), sizeof(JbHuffTable) * b->tables.size(), cudaMemcpyHostToDevice, ctx->stream));
+    JB_CUDA_B(cudaMemcpyAsync(b->d_quant, b->quant.data(), sizeof(uint16_t) * b->quant.size(), cudaMemcpyHostToDevice, ctx->stream));
+    JB_CUDA_B(cudaStreamSynchronize(ctx->stream));
+    JB_CUDA_B(cudaFuncSetAttribute(jb_k1_huff_segments, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * 4096)));
+#undef JB_CUDA_B
+    *out = b;
+    return JB_OK;
+}
+
+int jb_decode_batch_upload(jb_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < b->count; i++) {
+        const ImagePlan &pl = b->plans[i];
+        JB_CUDA(ctx, cudaMemcpyAsync(b->d_arena + pl.dev.data_off, b->host_data[i], pl.entropy_len,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return JB_OK;
+}
+
+static int launch_kernels(jb_batch *b, cudaEvent_t *ev, int *nev)
+{
+    jb_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    int launches = 0, e = 0;
+    auto mark = [&]() {
+        if (ev) cudaEventRecord(ev[e++], st);
+    };
+    mark();
+    JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+    jb_k0_restart_scan<<<b->count, JB_K0_THREADS, 0, st>>>(b->d_images, b->d_arena, b->d_marks, b->d_scan);
+    launches++;
+    mark();
+    {
+        dim3 grid(b->max_k1_ctas, b->count);
+        size_t smem = JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * 4096;
+        jb_k1_huff_segments<<<grid, JB_K1_THREADS, smem, st>>>(b->d_images, b->d_tables, b->d_arena, b->d_marks,
+                                                               b->d_scan, b->d_coef, b->d_status);
+        launches++;
+    }
+    mark();
+    if (b->need_render) {
+        dim3 grid(b->max_k2_tiles, b->count);
+        jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant);
+        launches++;
+    }
+    mark();
+    JB_CUDA(ctx, cudaGetLastError());
+    b->launches = launches;
+    if (nev) *nev = e;
+    return JB_OK;
+}
+
+int jb_decode_batch_launch(jb_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    JB_CUDA(b->ctx, cudaSetDevice(b->ctx->device));
+    return launch_kernels(b, nullptr, nullptr);
+}
+
+int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
+{
+    if (!b || !names || !ms || cap < 3) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaEvent_t ev[4];
+    for (auto &x : ev) JB_CUDA(ctx, cudaEventCreate(&x));
+    int nev = 0;
+    int rc = launch_kernels(b, ev, &nev);
+    if (rc) return rc;
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    static const char *kn[3] = {"jb_k0_restart_scan", "jb_k1_huff_segments", "jb_k2_idct_color"};
+    int n = nev - 1;
+    for (int i = 0; i < n && i < cap; i++) {
+        snprintf(names[i], 48, "%s", kn[i]);
+        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+    return n;
+}
+
+int jb_decode_batch_finish(jb_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < b->count; i++) {
+        const ImagePlan &pl = b->plans[i];
+        const void *src = pl.dev_out;
+        if (pl.out.format == JB_OUT_COEFFICIENTS) {
+            src = b->d_coef + pl.dev.coef_off * 64;
+            JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes,
+                                         pl.out.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+        } else if (!pl.out.on_device) {
+            JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    JB_CUDA(ctx, cudaMemcpyAsync(b->h_status.data(), b->d_status, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int first = JB_OK;
+    for (int i = 0; i < b->count; i++) {
+        uint32_t s = b->h_status[i];
+        int code = JB_OK;
+        if (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) code = JB_ERR_INVALID_DATA;
+        else if (s & JB_ST_EXPECT_RST) code = JB_ERR_INVALID_OPERATION;
+        if (code && !first) {
+            first = code;
+            char buf[200];
+            snprintf(buf, sizeof buf, "image %d: %s", i,
+                     code == JB_ERR_INVALID_DATA ? "Failed to decode JPEG data. Invalid Huffman code or premature end of the bit stream."
+                                                 : "Expect restart marker.");
+            ctx->error = buf;
+        }
+    }
+    return first;
+}
+
+int jb_decode_batch_run(jb_batch *b)
+{
+    int rc = jb_decode_batch_upload(b);
+    if (rc) return rc;
+    rc = jb_decode_batch_launch(b);
+    if (rc) return rc;
+    return jb_decode_batch_finish(b);
+}
+
+int jb_decode_batch_status(jb_batch *b, int32_t *status, int count)
+{
+    if (!b || !status) return JB_ERR_ARGUMENT;
+    for (int i = 0; i < count && i < b->count; i++) {
+        uint32_t s = b->h_status[i];
+        status[i] = (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) ? JB_ERR_INVALID_DATA
+                    : (s & JB_ST_EXPECT_RST)                     ? JB_ERR_INVALID_OPERATION
+                                                                 : JB_OK;
+    }
+    return JB_OK;
+}
+
+int jb_decode_batch_coef_layout(jb_batch *b, int image, jb_coef_layout *out)
+{
+    if (!b || !out || image < 0 || image >= b->count) return JB_ERR_ARGUMENT;
+    *out = b->plans[image].layout;
+    return JB_OK;
+}
+
+int jb_decode_batch_launch_count(jb_batch *b) { return b ? b->launches : 0; }
+
+void jb_decode_batch_destroy(jb_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->d_arena);
+    cudaFree(b->d_images);
+    cudaFree(b->d_tables);
+    cudaFree(b->d_quant);
+    cudaFree(b->d_marks);
+    cudaFree(b->d_scan);
+    cudaFree(b->d_coef);
+    cudaFree(b->d_status);
+    cudaFree(b->d_out_staging);
+    delete b;
+}
+
+int jb_decode(jb_ctx *ctx, const jb_image_desc *images, const jb_output_desc *outputs, int count, int32_t *status)
+{
+    jb_batch *b = nullptr;
+    int rc = jb_decode_batch_create(ctx, images, outputs, count, &b);
+    if (rc) return rc;
+    rc = jb_decode_batch_run(b);
+    if (status) jb_decode_batch_status(b, status, count);
+    jb_decode_batch_destroy(b);
+    return rc;
+}
+
+int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const int16_t *coef_device,
+                                const jb_output_desc *output)
+{
+    if (!ctx || !image || !coef_device || !output) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ImagePlan pl;
+    std::vector<JbHuffTable> tables;
+    std::map<std::string, int> ids;
+    std::vector<uint16_t> quant;
+    int rc = plan_image(ctx, 0, *image, output, pl, tables, ids, quant);
+    if (rc) return rc;
+    if (output->format == JB_OUT_COEFFICIENTS) return JB_ERR_ARGUMENT;
+    void *d_out = output->dst;
+    if (!output->on_device) JB_CUDA(ctx, cudaMalloc(&d_out, pl.out_bytes));
+    pl.dev.out_ptr = reinterpret_cast<uint64_t>(d_out);
+    pl.dev.coef_off = 0;
+    pl.dev.quant_off = 0;
+    JbDevImage *d_im = nullptr;
+    uint16_t *d_q = nullptr;
+    JB_CUDA(ctx, cudaMalloc(&d_im, sizeof(JbDevImage)));
+    JB_CUDA(ctx, cudaMalloc(&d_q, quant.size() * 2));
+    JB_CUDA(ctx, cudaMemcpyAsync(d_im, &pl.dev, sizeof(JbDevImage), cudaMemcpyHostToDevice, ctx->stream));
+    JB_CUDA(ctx, cudaMemcpyAsync(d_q, quant.data(), quant.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
+    uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
+    dim3 grid(strips * pl.dev.mcus_per_col, 1);
+    jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q);
+    JB_CUDA(ctx, cudaGetLastError());
+    if (!output->on_device)
+        JB_CUDA(ctx, cudaMemcpyAsync(output->dst, d_out, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!output->on_device) cudaFree(d_out);
+    cudaFree(d_im);
+    cudaFree(d_q);
+    return JB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,258 @@
+// k_idct_color.cuh -- K2: dequantise + un-zigzag + fp32 IDCT + level shift + pixel replication +
+// clamp + YCbCr->RGB, fused, one pass from the coefficient store to pitch-linear pixels.
+//
+// Replaces:
+//   DequantizeBlockAndUnZigZag / ShiftDataLevel   (ScanDecoder/JpegScanDecoder.cs:50-73)
+//   FastFloatingPointDCT.TransformIDCT            (FastFloatingPointDCT.cs:54-185)
+//   WriteBlock / WriteBlockSlow (replication)     (ScanDecoder/JpegHuffmanBaselineScanDecoder.cs:225-268,
+//                                                  JpegBlockAllocator.cs:151-190)
+//   JpegBufferOutputWriter8Bit.WriteBlock         (apps/JpegDecode/JpegBufferOutputWriter8Bit.cs:28-60)
+//   JpegBufferOutputWriterGreaterThan8Bit         (apps/JpegDecode/JpegBufferOutputWriterGreaterThan8Bit.cs:34-68)
+//   JpegYCbCrToRgbConverter.ConvertYCbCr8ToRgb24  (apps/JpegDecode/JpegYCbCrToRgbConverter.cs:134-205)
+//
+// Bit-exactness: the reference IDCT is fp32 with separately rounded multiplies and adds in a fixed
+// order (RyuJIT never contracts).  Every operation below is an explicit __fmul_rn/__fadd_rn/__fsub_rn,
+// which nvcc never fuses into FMA, so the int16 samples are bit-identical to the reference's.
+#pragma once
+#include "jb_device.cuh"
+
+#define JB_K2_MAX_BLOCKS 48
+#define JB_K2_THREADS (JB_K2_MAX_BLOCKS * 8)
+#define JB_K2_BLOCK_STRIDE 72 // floats per block in shared memory (64 + 8: conflict-free transposes)
+
+__constant__ uint8_t jb_c_zigzag[64] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+    41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+    30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// One 1-D pass of FastFloatingPointDCT.IDCT8x4_{Left,Right}Part (FastFloatingPointDCT.cs:79-185),
+// same operations in the same order.  y[] in, d[] out.
+__device__ __forceinline__ void jb_idct8(const float y[8], float d[8])
+{
+    const float C_1_175876 = 1.175875602f, C_1_961571 = -1.961570560f, C_0_390181 = -0.390180644f,
+                C_0_899976 = -0.899976223f, C_2_562915 = -2.562915447f, C_0_298631 = 0.298631336f,
+                C_2_053120 = 2.053119869f, C_3_072711 = 3.072711026f, C_1_501321 = 1.501321110f,
+                C_0_541196 = 0.541196100f, C_1_847759 = -1.847759065f, C_0_765367 = 0.765366865f;
+    const float my1 = y[1], my7 = y[7], my3 = y[3], my5 = y[5];
+    float mz0 = __fadd_rn(my1, my7);
+    float mz2 = __fadd_rn(my3, my7);
+    float mz1 = __fadd_rn(my3, my5);
+    float mz3 = __fadd_rn(my1, my5);
+    float mz4 = __fmul_rn(__fadd_rn(mz0, mz1), C_1_175876);
+    mz2 = __fadd_rn(__fmul_rn(mz2, C_1_961571), mz4);
+    mz3 = __fadd_rn(__fmul_rn(mz3, C_0_390181), mz4);
+    mz0 = __fmul_rn(mz0, C_0_899976);
+    mz1 = __fmul_rn(mz1, C_2_562915);
+    const float mb3 = __fadd_rn(__fadd_rn(__fmul_rn(my7, C_0_298631), mz0), mz2);
+    const float mb2 = __fadd_rn(__fadd_rn(__fmul_rn(my5, C_2_053120), mz1), mz3);
+    const float mb1 = __fadd_rn(__fadd_rn(__fmul_rn(my3, C_3_072711), mz1), mz2);
+    const float mb0 = __fadd_rn(__fadd_rn(__fmul_rn(my1, C_1_501321), mz0), mz3);
+    const float my2 = y[2], my6 = y[6], my0 = y[0], my4 = y[4];
+    mz4 = __fmul_rn(__fadd_rn(my2, my6), C_0_541196);
+    mz0 = __fadd_rn(my0, my4);
+    mz1 = __fsub_rn(my0, my4);
+    mz2 = __fadd_rn(mz4, __fmul_rn(my6, C_1_847759));
+    mz3 = __fadd_rn(mz4, __fmul_rn(my2, C_0_765367));
+    const float a0 = __fadd_rn(mz0, mz3);
+    const float a3 = __fsub_rn(mz0, mz3);
+    const float a1 = __fadd_rn(mz1, mz2);
+    const float a2 = __fsub_rn(mz1, mz2);
+    d[0] = __fadd_rn(a0, mb0);
+    d[7] = __fsub_rn(a0, mb0);
+    d[1] = __fadd_rn(a1, mb1);
+    d[6] = __fsub_rn(a1, mb1);
+    d[2] = __fadd_rn(a2, mb2);
+    d[5] = __fsub_rn(a2, mb2);
+    d[3] = __fadd_rn(a3, mb3);
+    d[4] = __fsub_rn(a3, mb3);
+}
+
+__device__ __forceinline__ int jb_clamp255(int v) { return min(max(v, 0), 255); }
+
+// apps/JpegDecode/JpegYCbCrToRgbConverter.cs:93-121 evaluated in fp32 as the C# does:
+// d1 = Fix(2-2*0.299) = 91881, d2 = -Fix(0.299*f1/0.587) = -46802, d3 = Fix(2-2*0.114) = 116130,
+// d4 = -Fix(0.114*f3/0.587) = -22553; Code2V is the identity for the default reference black/white.
+__device__ __forceinline__ void jb_ycc_to_rgb(int y, int cb, int cr, int &r, int &g, int &b)
+{
+    const int cbv = cb - 128, crv = cr - 128;
+    r = jb_clamp255(y + ((91881 * crv + 32768) >> 16));
+    g = jb_clamp255(y + ((-22553 * cbv + 32768 + -46802 * crv) >> 16));
+    b = jb_clamp255(y + ((116130 * cbv + 32768) >> 16));
+}
+
+struct JbK2Geom {
+    int plane_off[4]; // sample offset of each component plane in s_plane
+    int plane_pitch[4];
+    int hshift[4], vshift[4];
+};
+
+__global__ void __launch_bounds__(JB_K2_THREADS)
+jb_k2_idct_color(const JbDevImage *__restrict__ images,
+                 const int16_t *__restrict__ coef, const uint16_t *__restrict__ quant)
+{
+    __shared__ __align__(16) float s_f[JB_K2_MAX_BLOCKS * JB_K2_BLOCK_STRIDE];
+    __shared__ __align__(16) int16_t s_plane[JB_K2_MAX_BLOCKS * 64];
+    __shared__ uint16_t s_q[4 * 64];
+    __shared__ JbDevImage s_im;
+    __shared__ JbK2Geom s_g;
+
+    // grid = (tiles per image, images); a tile is a strip of consecutive MCUs of one MCU row
+    JbTileWork tw;
+    tw.image = blockIdx.y;
+    const int tid = threadIdx.x;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + tw.image);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
+        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K2_THREADS) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int ncomp = s_im.ncomp, bpm = s_im.bpm;
+    {
+        const uint32_t tile_mcus = JB_K2_MAX_BLOCKS / bpm;
+        const uint32_t strips = (s_im.mcus_per_line + tile_mcus - 1) / tile_mcus;
+        tw.mcu_row = blockIdx.x / strips;
+        tw.mcu_col0 = (blockIdx.x - tw.mcu_row * strips) * tile_mcus;
+        tw.nmcu = min(tile_mcus, s_im.mcus_per_line - tw.mcu_col0);
+        if (tw.mcu_row >= s_im.mcus_per_col) return;
+    }
+    const int nmcu = tw.nmcu;
+    if (tid < ncomp * 64) s_q[tid] = quant[s_im.quant_off + tid];
+    if (tid == 0) {
+        int off = 0;
+        for (int c = 0; c < ncomp; c++) {
+            s_g.plane_off[c] = off;
+            s_g.plane_pitch[c] = nmcu * s_im.comp_h[c] * 8;
+            off += nmcu * s_im.comp_h[c] * s_im.comp_v[c] * 64;
+            int hs = s_im.hmax / s_im.comp_h[c], vs = s_im.vmax / s_im.comp_v[c];
+            s_g.hshift[c] = hs == 4 ? 2 : hs == 2 ? 1 : 0;
+            s_g.vshift[c] = vs == 4 ? 2 : vs == 2 ? 1 : 0;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ phase A: dequant + IDCT
+    const int nblk = nmcu * bpm;
+    const int j = tid >> 3, r = tid & 7;
+    const unsigned wm = __ballot_sync(0xFFFFFFFFu, j < nblk); // the 8 threads of a block share a warp
+    if (j < nblk) {
+        const int m = j / bpm, b = j - m * bpm;
+        const int c = s_im.blk_comp[b];
+        const uint64_t blk0 = s_im.coef_off + ((uint64_t)tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0) * bpm;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(coef + (blk0 + j) * 64) + r);
+        const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+        float *fb = s_f + j * JB_K2_BLOCK_STRIDE;
+        const uint16_t *q = s_q + c * 64;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int z = r * 8 + e;
+            const int cv = (int)(int16_t)((wv[e >> 1] >> ((e & 1) * 16)) & 0xFFFF);
+            // product in int32, then int -> float (JpegScanDecoder.cs:60)
+            fb[jb_c_zigzag[z]] = __int2float_rn((int)q[z] * cv);
+        }
+        __syncwarp(wm);
+        // pass 1: 1-D IDCT along row r of the block (src.TransposeInto(temp); IDCT8x4 on temp)
+        float y[8], d[8];
+        {
+            const float4 lo = *reinterpret_cast<const float4 *>(fb + r * 8);
+            const float4 hi = *reinterpret_cast<const float4 *>(fb + r * 8 + 4);
+            y[0] = lo.x; y[1] = lo.y; y[2] = lo.z; y[3] = lo.w;
+            y[4] = hi.x; y[5] = hi.y; y[6] = hi.z; y[7] = hi.w;
+        }
+        jb_idct8(y, d);
+        __syncwarp(wm);
+#pragma unroll
+        for (int k = 0; k < 8; k++) fb[k * 8 + r] = d[k]; // O1[k][r]
+        __syncwarp(wm);
+        // pass 2: for column k = r: 1-D IDCT over O1[k][0..7]
+        {
+            const float4 lo = *reinterpret_cast<const float4 *>(fb + r * 8);
+            const float4 hi = *reinterpret_cast<const float4 *>(fb + r * 8 + 4);
+            y[0] = lo.x; y[1] = lo.y; y[2] = lo.z; y[3] = lo.w;
+            y[4] = hi.x; y[5] = hi.y; y[6] = hi.z; y[7] = hi.w;
+        }
+        jb_idct8(y, d);
+        // scale, round half-to-even, level shift (MultiplyInplace(0.125) + ShiftDataLevel)
+        const int shift = 1 << (s_im.precision - 1);
+        const int bi = b - s_im.comp_blk_off[c];
+        const int hc = s_im.comp_h[c];
+        const int bx = m * hc + bi % hc, by = bi / hc;
+        int16_t *pl = s_plane + s_g.plane_off[c] + (by * 8) * s_g.plane_pitch[c] + bx * 8 + r;
+#pragma unroll
+        for (int mrow = 0; mrow < 8; mrow++) {
+            const int v = __float2int_rn(__fmul_rn(d[mrow], 0.125f)) + shift;
+            pl[mrow * s_g.plane_pitch[c]] = (int16_t)v;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------ phase B: replicate + colour + store
+    const int W = s_im.width, H = s_im.height;
+    const int TW = nmcu * 8 * s_im.hmax, TH = 8 * s_im.vmax;
+    const int x0 = tw.mcu_col0 * 8 * s_im.hmax, y0 = tw.mcu_row * 8 * s_im.vmax;
+    const int fmt = s_im.out_format;
+    const int pshift = s_im.precision > 8 ? s_im.precision - 8 : 0;
+    uint8_t *out = reinterpret_cast<uint8_t *>(s_im.out_ptr);
+    const uint64_t pitch = s_im.out_pitch;
+    const int groups_per_row = TW >> 2;
+    const int ngroups = groups_per_row * TH;
+
+    for (int g = tid; g < ngroups; g += JB_K2_THREADS) {
+        const int gy = g / groups_per_row, gx = (g - gy * groups_per_row) << 2;
+        const int x = x0 + gx, yy = y0 + gy;
+        if (yy >= H || x >= W) continue;
+        const int npx = min(4, W - x);
+        int s[3][4];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (c < ncomp) {
+                const int16_t *row = s_plane + s_g.plane_off[c] + (gy >> s_g.vshift[c]) * s_g.plane_pitch[c];
+#pragma unroll
+                for (int p = 0; p < 4; p++) s[c][p] = row[(gx + p) >> s_g.hshift[c]];
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; p++) s[c][p] = 128 << pshift;
+            }
+        }
+        if (fmt == 3 /* JB_OUT_PLANAR_I16 */) {
+            for (int c = 0; c < ncomp; c++) {
+                int16_t *dst = reinterpret_cast<int16_t *>(out + ((uint64_t)c * H + yy) * pitch) + x;
+                if (c < 3) {
+                    for (int p = 0; p < npx; p++) dst[p] = (int16_t)s[c][p];
+                } else {
+                    const int16_t *row = s_plane + s_g.plane_off[c] + (gy >> s_g.vshift[c]) * s_g.plane_pitch[c];
+                    for (int p = 0; p < npx; p++) dst[p] = row[(gx + p) >> s_g.hshift[c]];
+                }
+            }
+            continue;
+        }
+        uint8_t px[16];
+        const int bpp = fmt == 1 ? 4 : 3;
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            // JpegBufferOutputWriter8Bit.ClampTo8Bit / GreaterThan8Bit: (sample >> (P-8)) clamped
+            const int yv = jb_clamp255(s[0][p] >> pshift);
+            const int cb = jb_clamp255(s[1][p] >> pshift);
+            const int cr = jb_clamp255(s[2][p] >> pshift);
+            if (fmt == 2 /* JB_OUT_YCBCR888 */) {
+                px[p * 3] = (uint8_t)yv; px[p * 3 + 1] = (uint8_t)cb; px[p * 3 + 2] = (uint8_t)cr;
+            } else {
+                int rr, gg, bb;
+                jb_ycc_to_rgb(yv, cb, cr, rr, gg, bb);
+                px[p * bpp] = (uint8_t)rr; px[p * bpp + 1] = (uint8_t)gg; px[p * bpp + 2] = (uint8_t)bb;
+                if (bpp == 4) px[p * 4 + 3] = 255;
+            }
+        }
+        uint8_t *dst = out + (uint64_t)yy * pitch + (uint64_t)x * bpp;
+        const int nbytes = npx * bpp;
+        if (npx == 4 && ((reinterpret_cast<uint64_t>(dst) & 3u) == 0)) {
+            uint32_t *d32 = reinterpret_cast<uint32_t *>(dst);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i * 4 < nbytes)
+                    d32[i] = px[i * 4] | (px[i * 4 + 1] << 8) | (px[i * 4 + 2] << 16) | ((uint32_t)px[i * 4 + 3] << 24);
+            }
+        } else {
+            for (int i = 0; i < nbytes; i++) dst[i] = px[i];
+        }
+    }
+}
