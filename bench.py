@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- decoded MP/s of the batched 4K 4:2:0 SOF0 decode hot path on N B200s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A step = one pass of the hot path (restart scan + Huffman decode + IDCT/colour)
+over one batch of synthetic JPEGs already resident in HBM; `e2e` is the same metric through the
+public API with host buffers (marker walk, H2D of the compressed bytes, kernels, D2H of the RGB).
+`--impl reference` times the reference algorithm's CPU restatement (oracle/, the reference's own
+C# cannot run here: no .NET) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT = 3840, 2160
+MP_PER_IMAGE = WIDTH * HEIGHT / 1e6
+
+
+def _gen_one(args):
+    import synth
+    i, w, h, kw = args
+    return synth.encode_jpeg(synth.synth_rgb(i, w, h), **kw)
+
+
+def make_blobs(distinct, width, height, **kw):
+    """`distinct` synthetic JPEGs (seeds 1000+i), generated on a process pool (data generation only)."""
+    jobs = [(i, width, height, kw) for i in range(distinct)]
+    procs = min(distinct, max(1, (os.cpu_count() or 2) // 2), 32)
+    if procs <= 1:
+        return [_gen_one(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(procs) as pool:
+        return pool.map(_gen_one, jobs)
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md 'clocks line')."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference(blobs, threads, images):
+    """Decode `images` streams to RGB24 with the oracle on `threads` host threads; returns MP/s."""
+    import oracle_ffi as O
+    sample = [blobs[i % len(blobs)] for i in range(images)]
+    O.decode_batch_rgb(sample[:min(2, images)], min(2, threads))  # warm the library / page cache
+    t0 = time.perf_counter()
+    failed = O.decode_batch_rgb(sample, threads)
+    dt = time.perf_counter() - t0
+    assert failed == 0
+    return images * MP_PER_IMAGE / dt, dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    blobs = make_blobs(min(args.distinct, 8), WIDTH, HEIGHT, quality=85, subsampling="4:2:0", restart_marker_rows=1) \
+        if False else make_blobs(min(args.distinct, 8), WIDTH, HEIGHT, quality=85, subsampling="4:2:0", restart_rows=1)
+    images = max(threads, min(2 * threads, 256))
+    for _ in range(args.warmup):
+        cpu_reference(blobs, threads, max(2, images // 4))
+    t0 = time.perf_counter()
+    tot = 0
+    for _ in range(args.steps):
+        cpu_reference(blobs, threads, images)
+        tot += images
+    dt = time.perf_counter() - t0
+    val = tot * MP_PER_IMAGE / dt
+    line = {
+        "impl": "reference", "metric": "decoded_megapixels_per_second", "value": val, "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16/fp32", "data": "synthetic",
+        "config": {"workload": "configs[1]: batch of synthetic 3840x2160 4:2:0 SOF0 JPEGs, q85, DRI=240 (one MCU row)",
+                   "images_per_step": images},
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": threads, "kind": "port",
+                         "sample": f"{images} images per step x {args.steps} steps, one image per task, "
+                                   "C restatement of the reference algorithm (reference .NET runtime unavailable)"},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic images (replicated to --batch)")
+    ap.add_argument("--e2e-batch", type=int, default=64, help="images per step of the host-buffer (e2e) leg")
+    ap.add_argument("--cpu-images", type=int, default=0, help="images of the cpu_baseline sample (0: auto)")
+    ap.add_argument("--no-restart", action="store_true", help="configs[2]: same batch without restart markers")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import jpeglibrary_b200 as J
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: jpeglibrary_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    ctx = J.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+
+    # ---------------------------------------------------------------- inputs (synthetic, seeds 1000+i)
+    kw = dict(quality=85, subsampling="4:2:0")
+    if not args.no_restart:
+        kw["restart_rows"] = 1
+    blobs = make_blobs(args.distinct, WIDTH, HEIGHT, **kw)
+    # pinned host copies (the e2e leg copies from pinned memory; replicas share the host bytes)
+    pinned = []
+    for b in blobs:
+        a = ctx.pinned_array(len(b))
+        a[:] = np.frombuffer(b, dtype=np.uint8)
+        pinned.append(a)
+    batch_blobs = [pinned[i % len(pinned)] for i in range(args.batch)]
+    comp_bytes = sum(b.size for b in batch_blobs)
+
+    # ---------------------------------------------------------------- resident-input leg ("value")
+    dec = J.JpegBatchDecoder(batch_blobs, J.JB_OUT_RGB24, context=ctx, device_output=True,
+                             parse_threads=min(32, os.cpu_count() or 1))
+    dec.upload()
+    ctx.synchronize()
+    for _ in range(args.warmup):
+        dec.launch()
+    ctx.synchronize()
+    # correctness gate on the bench inputs themselves: first image vs the oracle
+    if rank == 0:
+        import oracle_ffi as O
+        ref = O.decode(blobs[0])
+        got = dec.read_output(0)
+        maxdiff = int(np.abs(got.astype(int) - ref.rgb.astype(int)).max())
+        assert maxdiff <= 1, f"bench output differs from the oracle by {maxdiff}"
+    else:
+        maxdiff = None
+    dec.finish()
+    assert dec.status() == [0] * args.batch
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dec.set_profiling(True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        dec.launch()
+    ev1.record(stream)
+    ctx.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    kernels = dec.profile()  # [(name, avg ms per launch)] measured with CUDA events on the launch stream
+    dec.set_profiling(False)
+    launches = dec.launch_count() * args.steps
+
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_images = args.batch * world * args.steps
+    value = total_images * MP_PER_IMAGE / (ms_max / 1e3)
+
+    # ---------------------------------------------------------------- e2e leg (host buffers, public API)
+    eb = min(args.e2e_batch, args.batch)
+    e2e_blobs = batch_blobs[:eb]
+    host_out = ctx.pinned_array(eb * ((WIDTH * HEIGHT * 3 + 255) // 256 * 256))
+
+    def e2e_step():
+        with J.JpegBatchDecoder(e2e_blobs, J.JB_OUT_RGB24, context=ctx, device_output=False,
+                                host_outputs=host_out, parse_threads=min(32, os.cpu_count() or 1)) as d2:
+            d2.run()
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    t = torch.tensor([e2e_dt], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = eb * world * e2e_steps * MP_PER_IMAGE / float(t.item())
+    e2e_h2d = sum(b.size for b in e2e_blobs)
+    e2e_d2h = eb * WIDTH * HEIGHT * 3
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    nblocks = (WIDTH // 8) * (HEIGHT // 8) * 3 // 2  # 194 400 for 4K 4:2:0
+    alg = {  # ALGORITHMIC bytes per launch, for the whole batch
+        "jb_k0_restart_scan": comp_bytes,
+        "jb_k1_huff_segments": comp_bytes + 128 * nblocks * args.batch,
+        "jb_k2_idct_color": (128 * nblocks + 3 * WIDTH * HEIGHT) * args.batch,
+    }
+    dom = max(kernels, key=lambda kv: kv[1]) if kernels else ("none", float("nan"))
+    achieved = alg.get(dom[0], 0) / (dom[1] / 1e3) / 1e9 if kernels else float("nan")
+    roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": {k: v for k, v in kernels},
+                "kernel_gbs": {k: alg[k] / (v / 1e3) / 1e9 for k, v in kernels if k in alg and v > 0},
+                "pipeline_frac_of_peak": ((comp_bytes + 3 * WIDTH * HEIGHT * args.batch) / (ms / args.steps / 1e3) / 1e9) / peak}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        images = args.cpu_images or max(threads, min(2 * threads, 128))
+        v, dt = cpu_reference(blobs, threads, images)
+        cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
+               "sample": f"{images} of the batch's images, one image per task on {threads} threads ({dt:.1f} s wall), "
+                         "C restatement of the reference algorithm (reference .NET runtime unavailable)"}
+
+    if rank == 0:
+        line = {
+            "metric": "decoded_megapixels_per_second", "value": value, "unit": "MP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16/fp32",
+            "data": "synthetic",
+            "config": {"workload": ("configs[2]: 3840x2160 4:2:0 SOF0 q85, no restart markers" if args.no_restart else
+                                    "configs[1]: batch of synthetic 3840x2160 4:2:0 SOF0 JPEGs, q85, DRI=240 (one MCU row)"),
+                       "images_per_gpu_per_step": args.batch, "distinct_images": args.distinct,
+                       "compressed_bytes_per_step": comp_bytes, "output": "RGB24 device-resident",
+                       "l2": "inputs larger than L2 (compressed 1.7 GB + 25 GB coefficient store per step)",
+                       "compressed_gb_per_s": comp_bytes * world * args.steps / (ms_max / 1e3) / 1e9,
+                       "max_abs_rgb_diff_vs_oracle": maxdiff},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": e2e_h2d, "d2h_bytes_per_step": e2e_d2h,
+                    "images_per_step": eb, "includes": "marker walk + plan + H2D + kernels + D2H of RGB24 to pinned host"},
+            "gpu_launches": launches,
+            "roofline": roofline,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

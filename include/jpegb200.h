@@ -157,8 +157,11 @@ JB_API int jb_decode_batch_status(jb_batch *b, int32_t *status, int count);
 JB_API int jb_decode_batch_coef_layout(jb_batch *b, int image, jb_coef_layout *out);
 /* Number of kernels launched by the last jb_decode_batch_launch. */
 JB_API int jb_decode_batch_launch_count(jb_batch *b);
-/* Per-kernel timing of one extra profiled launch: fills names/ms for up to `cap` kernels,
-   returns the number of kernels. Uses CUDA events on the context stream. */
+/* Per-kernel timing with CUDA events on the context stream.  While profiling is on, every
+   jb_decode_batch_launch brackets each kernel with event records (no host synchronisation);
+   jb_decode_batch_profile then waits for the stream and returns, per kernel, the AVERAGE duration
+   in ms over all launches since profiling was switched on.  Returns the number of kernels. */
+JB_API int jb_decode_batch_set_profiling(jb_batch *b, int on);
 JB_API int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap);
 JB_API void jb_decode_batch_destroy(jb_batch *b);
 

@@ -374,6 +374,9 @@ class JpegBatchDecoder:
     def launch_count(self):
         return N.cuda.jb_decode_batch_launch_count(self.handle)
 
+    def set_profiling(self, on):
+        self.ctx.check(N.cuda.jb_decode_batch_set_profiling(self.handle, 1 if on else 0))
+
     def profile(self):
         names = ((C.c_char * 48) * 8)()
         ms = (C.c_float * 8)()

@@ -182,7 +182,8 @@ struct jb_batch {
     uint32_t max_k1_ctas = 0, max_k2_tiles = 0;
     bool need_render = false;
     int launches = 0;
-    bool uploaded_meta = false;
+    bool profiling = false;
+    std::vector<cudaEvent_t> events; // 4 per profiled launch
 };
 
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -213,6 +214,13 @@ int jb_ctx_create(int device, jb_ctx **out)
         cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         delete c;
         return JB_ERR_CUDA;
+    }
+    // batch objects allocate from the stream-ordered pool; keep freed memory cached so that creating
+    // the next batch of a streaming workload costs no cudaMalloc
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     *out = c;
     return JB_OK;
@@ -391,7 +399,9 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     d.mark_cap = d.nseg + 1;
     if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
     pl.entropy_off = sc.entropy_offset;
-    pl.entropy_len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length, im.length - sc.entropy_offset)
+    // entropy_length excludes the marker that ends the scan; the two marker bytes are staged too so
+    // that the restart scan sees the terminator (EOI after a complete interval is legal, :145-150)
+    pl.entropy_len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
                                        : im.length - sc.entropy_offset;
     if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
     d.data_len = (uint32_t)pl.entropy_len;
@@ -513,15 +523,15 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             return e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA; \
         }                                                          \
     } while (0)
-    JB_CUDA_B(cudaMalloc(&b->d_arena, b->arena_bytes));
-    JB_CUDA_B(cudaMalloc(&b->d_images, sizeof(JbDevImage) * count));
-    JB_CUDA_B(cudaMalloc(&b->d_tables, sizeof(JbHuffTable) * b->tables.size()));
-    JB_CUDA_B(cudaMalloc(&b->d_quant, sizeof(uint16_t) * b->quant.size()));
-    JB_CUDA_B(cudaMalloc(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1)));
-    JB_CUDA_B(cudaMalloc(&b->d_scan, sizeof(JbScanResult) * count));
-    JB_CUDA_B(cudaMalloc(&b->d_coef, blocks * 128));
-    JB_CUDA_B(cudaMalloc(&b->d_status, sizeof(uint32_t) * count));
-    if (staging) JB_CUDA_B(cudaMalloc(&b->d_out_staging, staging));
+    JB_CUDA_B(cudaMallocAsync(&b->d_arena, b->arena_bytes, ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_images, sizeof(JbDevImage) * count, ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_tables, sizeof(JbHuffTable) * b->tables.size(), ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1), ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_scan, sizeof(JbScanResult) * count, ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_coef, blocks * 128, ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, ctx->stream));
+    if (staging) JB_CUDA_B(cudaMallocAsync(&b->d_out_staging, staging, ctx->stream));
     for (int i = 0; i < count; i++) {
         ImagePlan &pl = b->plans[i];
         if (!pl.out.on_device) pl.dev_out = b->d_out_staging + reinterpret_cast<uint64_t>(pl.dev_out);
@@ -554,16 +564,23 @@ int jb_decode_batch_upload(jb_batch *b)
     return JB_OK;
 }
 
-static int launch_kernels(jb_batch *b, cudaEvent_t *ev, int *nev)
+static const char *kKernelNames[3] = {"jb_k0_restart_scan", "jb_k1_huff_segments", "jb_k2_idct_color"};
+
+static int launch_kernels(jb_batch *b)
 {
     jb_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
-    int launches = 0, e = 0;
+    int launches = 0;
     auto mark = [&]() {
-        if (ev) cudaEventRecord(ev[e++], st);
+        if (!b->profiling) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) {
+            cudaEventRecord(e, st);
+            b->events.push_back(e);
+        }
     };
-    mark();
     JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+    mark();
     jb_k0_restart_scan<<<b->count, JB_K0_THREADS, 0, st>>>(b->d_images, b->d_arena, b->d_marks, b->d_scan);
     launches++;
     mark();
@@ -583,7 +600,6 @@ static int launch_kernels(jb_batch *b, cudaEvent_t *ev, int *nev)
     mark();
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
-    if (nev) *nev = e;
     return JB_OK;
 }
 
@@ -591,7 +607,22 @@ int jb_decode_batch_launch(jb_batch *b)
 {
     if (!b) return JB_ERR_ARGUMENT;
     JB_CUDA(b->ctx, cudaSetDevice(b->ctx->device));
-    return launch_kernels(b, nullptr, nullptr);
+    return launch_kernels(b);
+}
+
+static void clear_events(jb_batch *b)
+{
+    for (cudaEvent_t e : b->events) cudaEventDestroy(e);
+    b->events.clear();
+}
+
+int jb_decode_batch_set_profiling(jb_batch *b, int on)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    clear_events(b);
+    b->profiling = on != 0;
+    return JB_OK;
 }
 
 int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
@@ -599,20 +630,21 @@ int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
     if (!b || !names || !ms || cap < 3) return JB_ERR_ARGUMENT;
     jb_ctx *ctx = b->ctx;
     JB_CUDA(ctx, cudaSetDevice(ctx->device));
-    cudaEvent_t ev[4];
-    for (auto &x : ev) JB_CUDA(ctx, cudaEventCreate(&x));
-    int nev = 0;
-    int rc = launch_kernels(b, ev, &nev);
-    if (rc) return rc;
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    static const char *kn[3] = {"jb_k0_restart_scan", "jb_k1_huff_segments", "jb_k2_idct_color"};
-    int n = nev - 1;
-    for (int i = 0; i < n && i < cap; i++) {
-        snprintf(names[i], 48, "%s", kn[i]);
-        cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    const size_t nlaunch = b->events.size() / 4;
+    if (nlaunch == 0) return 0;
+    double acc[3] = {0, 0, 0};
+    for (size_t l = 0; l < nlaunch; l++)
+        for (int k = 0; k < 3; k++) {
+            float t = 0;
+            cudaEventElapsedTime(&t, b->events[l * 4 + k], b->events[l * 4 + k + 1]);
+            acc[k] += t;
+        }
+    for (int k = 0; k < 3; k++) {
+        snprintf(names[k], 48, "%s", kKernelNames[k]);
+        ms[k] = (float)(acc[k] / (double)nlaunch);
     }
-    for (auto &x : ev) cudaEventDestroy(x);
-    return n;
+    return 3;
 }
 
 int jb_decode_batch_finish(jb_batch *b)
@@ -687,15 +719,16 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    cudaFree(b->d_arena);
-    cudaFree(b->d_images);
-    cudaFree(b->d_tables);
-    cudaFree(b->d_quant);
-    cudaFree(b->d_marks);
-    cudaFree(b->d_scan);
-    cudaFree(b->d_coef);
-    cudaFree(b->d_status);
-    cudaFree(b->d_out_staging);
+    clear_events(b);
+    if (b->d_arena) cudaFreeAsync(b->d_arena, b->ctx->stream);
+    if (b->d_images) cudaFreeAsync(b->d_images, b->ctx->stream);
+    if (b->d_tables) cudaFreeAsync(b->d_tables, b->ctx->stream);
+    if (b->d_quant) cudaFreeAsync(b->d_quant, b->ctx->stream);
+    if (b->d_marks) cudaFreeAsync(b->d_marks, b->ctx->stream);
+    if (b->d_scan) cudaFreeAsync(b->d_scan, b->ctx->stream);
+    if (b->d_coef) cudaFreeAsync(b->d_coef, b->ctx->stream);
+    if (b->d_status) cudaFreeAsync(b->d_status, b->ctx->stream);
+    if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
     delete b;
 }
 
