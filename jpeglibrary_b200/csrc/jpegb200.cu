@@ -545,7 +545,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMemcpyAsync(b->d_quant, b->quant.data(), sizeof(uint16_t) * b->quant.size(), cudaMemcpyHostToDevice, ctx->stream));
     JB_CUDA_B(cudaStreamSynchronize(ctx->stream));
     JB_CUDA_B(cudaFuncSetAttribute(jb_k1_huff_segments, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * 4096)));
+                                   (int)(JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * JB_K1_STAGE_BYTES)));
 #undef JB_CUDA_B
     *out = b;
     return JB_OK;
@@ -586,7 +586,7 @@ static int launch_kernels(jb_batch *b)
     mark();
     {
         dim3 grid(b->max_k1_ctas, b->count);
-        size_t smem = JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * 4096;
+        size_t smem = JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * JB_K1_STAGE_BYTES;
         jb_k1_huff_segments<<<grid, JB_K1_THREADS, smem, st>>>(b->d_images, b->d_tables, b->d_arena, b->d_marks,
                                                                b->d_scan, b->d_coef, b->d_status);
         launches++;

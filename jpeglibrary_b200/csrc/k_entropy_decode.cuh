@@ -128,67 +128,95 @@ jb_k0_restart_scan(const JbDevImage *__restrict__ images, const uint8_t *__restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bit reader: 64-bit MSB-first window (hi:lo), refilled 32 bits at a time from the stuffed
-// byte stream.  FF 00 -> FF, FF FF -> fill byte skipped; at the segment end the window is padded
-// with 1-bits exactly like PeekBits does (JpegBitReader.cs:166) and `pad` counts them so that
-// consuming padding as magnitude bits is reported like ReceiveAndExtend's failure.
+// Bit reader: 64-bit MSB-first window (hi:lo) refilled 32 bits at a time from the stuffed byte
+// stream.  The stream is read as aligned 32-bit words kept in registers (w0,w1 = the two words
+// under the read position, w2 = software prefetch of the next one), so un-stuffing (FF 00 -> FF),
+// fill bytes (FF FF) and misalignment are handled by register arithmetic without extra loads.
+// At the segment end the window is padded with 1-bits exactly like PeekBits does
+// (JpegBitReader.cs:166); `pad` counts them so that consuming padding as magnitude bits is
+// reported like ReceiveAndExtend's failure (JpegHuffmanScanDecoder.cs:100-110).
 // ---------------------------------------------------------------------------------------------
 struct JbBitReader {
-    const uint8_t *data;
+    const uint8_t *data; // 256-byte aligned
     uint32_t pos, end;
+    uint32_t w0, w1, w2;
     uint32_t hi, lo;
     int n;   // valid bits in hi:lo
     int pad; // of which padding (always the last `pad` bits)
 
+    __device__ __forceinline__ uint32_t ldw(uint32_t byte_off) const
+    {
+        return __ldg(reinterpret_cast<const uint32_t *>(data + byte_off));
+    }
     __device__ __forceinline__ void init(const uint8_t *d, uint32_t start, uint32_t stop)
     {
         data = d; pos = start; end = stop; hi = lo = 0; n = 0; pad = 0;
+        const uint32_t wp = start & ~3u;
+        w0 = ldw(wp); w1 = ldw(wp + 4); w2 = ldw(wp + 8);
     }
     __device__ __forceinline__ void put(uint32_t w, int bits)
-    { // append `bits` (8..32) bits held left-aligned in w; requires n <= 32
+    { // append `bits` (0..32) bits held left-aligned in w; requires n <= 32
         hi |= __funnelshift_rc(w, 0u, n);
         lo |= __funnelshift_rc(0u, w, n);
         n += bits;
     }
-    __device__ __noinline__ void refill_slow()
+    __device__ __forceinline__ void advance(uint32_t nbytes)
+    { // nbytes <= 4
+        const uint32_t np = pos + nbytes;
+        if ((np ^ pos) & ~3u) {
+            w0 = w1; w1 = w2;
+            w2 = ldw((np & ~3u) + 8);
+        }
+        pos = np;
+    }
+    __device__ __forceinline__ uint32_t candidate() const
+    { // the 4 bytes at pos, first byte in the most significant position
+        return __byte_perm(w0, w1, 0x0123u + 0x1111u * (pos & 3u));
+    }
+    __device__ __forceinline__ void refill_slow(uint32_t cw)
     {
-        // byte-wise: handles stuffing, fill bytes, misalignment and the segment end
-        uint32_t w = 0;
+        uint32_t w = 0, consumed = 0;
         int bits = 0;
-        while (bits < 32) {
-            if (pos >= end) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (consumed > (uint32_t)i) continue; // the zero of an FF00 pair
+            const uint32_t p = pos + i;
+            if (p >= end) {
                 w |= 0xFFFFFFFFu >> bits;
                 pad += 32 - bits;
                 bits = 32;
                 break;
             }
-            uint32_t b = data[pos++];
+            const uint32_t b = (cw >> (24 - 8 * i)) & 0xFF;
             if (b == 0xFF) {
-                uint32_t b2 = pos < end ? data[pos] : 0xD9u;
-                if (b2 == 0xFF) continue; // fill byte
-                if (b2 == 0) pos++;       // stuffed zero
-                else {                    // a marker inside the segment: treat as its end
-                    pos = end;
-                    continue;
+                if (i == 3) break; // successor not in the candidate: next refill starts at this FF
+                const uint32_t b2 = (cw >> (16 - 8 * i)) & 0xFF;
+                if (b2 == 0xFF) { consumed = i + 1; continue; } // fill byte
+                if (b2 != 0) { // a marker inside the segment: it ends here
+                    end = p;
+                    w |= 0xFFFFFFFFu >> bits;
+                    pad += 32 - bits;
+                    bits = 32;
+                    break;
                 }
-            }
+                consumed = i + 2; // stuffed zero
+            } else
+                consumed = i + 1;
             w |= b << (24 - bits);
             bits += 8;
-            if ((pos & 3u) == 0 && pos + 4 <= end) break; // aligned again: let the fast path go on
         }
+        advance(consumed);
         put(w, bits);
     }
     __device__ __forceinline__ void refill()
     { // call when n <= 32
-        if ((pos & 3u) == 0 && pos + 4 <= end) {
-            uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(data + pos));
-            if (jb_ff_bytes(w) == 0) {
-                pos += 4;
-                put(__byte_perm(w, 0, 0x0123), 32);
-                return;
-            }
+        const uint32_t cw = candidate();
+        if (pos + 4 <= end && jb_ff_bytes(cw) == 0) {
+            put(cw, 32);
+            advance(4);
+            return;
         }
-        refill_slow();
+        refill_slow(cw);
     }
     __device__ __forceinline__ void ensure32()
     {
@@ -228,18 +256,20 @@ __device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1a: one thread per restart segment; a warp's 32 lanes decode 32 consecutive segments of the
-// same image block-synchronously (all lanes are on the same block-in-MCU, so table selection is
-// warp-uniform).  Each lane assembles its current 8x8 block in a skewed shared-memory staging tile;
-// after every block the warp flushes the 32 blocks with coalesced 128-bit stores (8 lanes per
-// block), so every coefficient block leaves the SM as one full 128-byte line.
+// K1a: one thread per restart segment, 32 consecutive segments of one image per warp.
+// Every lane runs the same flat loop -- one Huffman symbol per iteration -- over its own segment,
+// so lanes never wait for each other at block boundaries.  Each lane assembles its current 8x8
+// block in a rotated shared-memory staging tile; whenever lanes complete blocks, the whole warp
+// flushes them one after the other with one coalesced 128-byte store per block (lane j moves
+// word j), so every coefficient block leaves the SM as one full line and is written exactly once.
 // ---------------------------------------------------------------------------------------------
 #define JB_K1_WARPS 4
 #define JB_K1_THREADS (JB_K1_WARPS * 32)
+#define JB_K1_STAGE_BYTES (32 * 128)
 
-__device__ __forceinline__ uint32_t jb_stage_chunk(int lane, int chunk)
-{ // 16-byte slot of (block of `lane`, 16-byte chunk 0..7): skewed so that flushes are conflict-free
-    return (uint32_t)(lane * 8 + ((chunk + lane) & 7));
+__device__ __forceinline__ uint32_t jb_stage_word(int lane, int word)
+{ // 32-bit word `word` (0..31) of lane's block; 16-byte chunks rotated by lane -> conflict-free flush
+    return (uint32_t)(lane * 32 + ((((word >> 2) + lane) & 7) << 2) + (word & 3));
 }
 
 __global__ void __launch_bounds__(JB_K1_THREADS)
@@ -250,127 +280,136 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
 {
     extern __shared__ uint4 jb_smem[];
     __shared__ JbDevImage s_im;
-    JbHuffTable *s_tab = reinterpret_cast<JbHuffTable *>(jb_smem);
     // grid = (CTAs per image, images): a CTA decodes JB_K1_THREADS consecutive segments of one image
-    struct { uint32_t image, first_seg; } wk = {blockIdx.y, blockIdx.x * JB_K1_THREADS};
+    const uint32_t image = blockIdx.y, first_seg = blockIdx.x * JB_K1_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (wk.first_seg >= images[wk.image].nseg) return;
-
+    if (first_seg >= images[image].nseg) return;
     {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + wk.image);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
         for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K1_THREADS) dst[i] = src[i];
     }
     __syncthreads();
+    JbHuffTable *s_tab = reinterpret_cast<JbHuffTable *>(jb_smem);
     const int ntab = s_im.ntables;
     for (int t = 0; t < ntab; t++) {
         const uint4 *src = reinterpret_cast<const uint4 *>(tables + s_im.table_index[t]);
         uint4 *dst = reinterpret_cast<uint4 *>(s_tab + t);
         for (int i = tid; i < (int)(sizeof(JbHuffTable) / 16); i += JB_K1_THREADS) dst[i] = __ldg(src + i);
     }
-    uint4 *s_stage = jb_smem + (JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable)) / 16 + wid * 256;
-    for (int i = lane; i < 256; i += 32) s_stage[i] = make_uint4(0, 0, 0, 0);
+    uint32_t *s_stage = reinterpret_cast<uint32_t *>(jb_smem + (JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable)) / 16) +
+                        wid * (JB_K1_STAGE_BYTES / 4);
+    for (int i = lane; i < JB_K1_STAGE_BYTES / 4; i += 32) s_stage[i] = 0;
     __syncthreads();
 
     const uint32_t nseg = s_im.nseg;
-    const uint32_t seg = wk.first_seg + tid;
+    const uint32_t seg = first_seg + tid;
     const uint32_t dri = s_im.dri ? s_im.dri : s_im.total_mcus;
     const int bpm = s_im.bpm;
-    const JbScanResult sr = scanres[wk.image];
+    const JbScanResult sr = scanres[image];
     const uint8_t *data = arena + s_im.data_off;
     const uint32_t *mk = marks + s_im.mark_base;
 
     // segment bounds from the marker index
-    uint32_t my_nmcu = 0, start = 0, stop = 0;
-    uint32_t err = 0;
+    uint32_t nblocks = 0, start = 0, stop = 0, err = 0;
     bool last_needs_marker = false;
     if (seg < nseg) {
-        my_nmcu = min(dri, s_im.total_mcus - seg * dri);
+        const uint32_t my_nmcu = min(dri, s_im.total_mcus - seg * dri);
+        nblocks = my_nmcu * bpm;
         if (seg > 0) {
             if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
-            else { err |= JB_ST_EXPECT_RST; my_nmcu = 0; }
+            else { err |= JB_ST_EXPECT_RST; nblocks = 0; }
         }
         stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
         // the reference expects RSTn or EOI right after every *complete* interval
         // (JpegHuffmanBaselineScanDecoder.cs:139-154)
         last_needs_marker = s_im.dri != 0 && my_nmcu == dri;
     }
-    const uint32_t warp_nmcu = __reduce_max_sync(0xFFFFFFFFu, my_nmcu);
+    const bool had_work = nblocks > 0;
 
     JbBitReader br;
     br.init(data, start, stop);
-    int pred0 = 0, pred1 = 0, pred2 = 0, pred3 = 0;
     int16_t *stage16 = reinterpret_cast<int16_t *>(s_stage);
+    // per-lane decoder state
+    uint32_t done = 0;     // blocks completed by this lane
+    int b = 0;             // block-in-mcu of the current block
+    int k = 0;             // next zig-zag index; 0 = the DC symbol comes next
+    int pred_cur = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0; // DC predictors (current component / saved)
+    int comp = s_im.blk_comp[0];
+    const JbHuffTable *dct = s_tab + s_im.blk_dc[0], *act = s_tab + s_im.blk_ac[0];
+    bool active = nblocks > 0;
 
-    // global address of this warp's first lane's first block, and the per-lane stride
-    const uint64_t warp_blk0 = s_im.coef_off + (uint64_t)(wk.first_seg + wid * 32) * dri * bpm;
-    const uint64_t lane_stride = (uint64_t)dri * bpm; // blocks between consecutive segments
+    // first block of this warp's lane 0 and the stride between consecutive segments (in blocks)
+    const uint64_t warp_blk0 = s_im.coef_off + (uint64_t)(first_seg + wid * 32) * dri * bpm;
+    const uint32_t lane_stride = dri * bpm;
 
-    for (uint32_t mcu = 0; mcu < warp_nmcu; mcu++) {
-        const bool active = mcu < my_nmcu;
-        for (int b = 0; b < bpm; b++) {
-            if (active) {
-                const int comp = s_im.blk_comp[b];
-                const JbHuffTable *dct = s_tab + s_im.blk_dc[b];
-                const JbHuffTable *act = s_tab + s_im.blk_ac[b];
-                // ---- DC (ReadBlockBaseline :187-196)
-                br.ensure32();
-                uint32_t e = jb_huff_lookup(dct, br.peek16());
-                if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 1; }
-                br.skip(e & 0xFF);
-                int t = (int)(e >> 8);
-                if (t > 16) { err |= JB_ST_BAD_CODE; t = 0; }
-                int diff = 0;
-                if (t != 0) diff = jb_extend((int)br.take(t), t);
-                int pred = comp == 0 ? pred0 : comp == 1 ? pred1 : comp == 2 ? pred2 : pred3;
-                pred += diff;
-                if (comp == 0) pred0 = pred; else if (comp == 1) pred1 = pred; else if (comp == 2) pred2 = pred; else pred3 = pred;
-                stage16[jb_stage_chunk(lane, 0) * 8] = (int16_t)pred;
-                // ---- AC (:199-221)
-                for (int i = 1; i < 64;) {
-                    br.ensure32();
-                    uint32_t e2 = jb_huff_lookup(act, br.peek16());
-                    if (e2 == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; break; }
-                    br.skip(e2 & 0xFF);
-                    const int s = (e2 >> 8) & 15, r = (int)(e2 >> 12);
-                    if (s != 0) {
-                        i += r;
-                        const int v = jb_extend((int)br.take(s), s);
-                        const int k = min(i, 63);
-                        stage16[jb_stage_chunk(lane, k >> 3) * 8 + (k & 7)] = (int16_t)v;
-                        i++;
-                    } else {
-                        if (r == 0) break;
-                        i += 16;
-                    }
-                }
+    while (__any_sync(0xFFFFFFFFu, active)) {
+        bool finished = false;
+        if (active) {
+            br.ensure32();
+            const bool is_dc = k == 0;
+            uint32_t e = jb_huff_lookup(is_dc ? dct : act, br.peek16());
+            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; if (!is_dc) k = 64; }
+            br.skip(e & 0xFF);
+            const int sym = (int)(e >> 8);
+            int s = is_dc ? sym : (sym & 15);
+            const int r = is_dc ? 0 : (sym >> 4);
+            if (s > 16) { err |= JB_ST_BAD_CODE; s = 0; }
+            int v = 0;
+            if (s != 0) v = jb_extend((int)br.take(s), s);
+            if (is_dc) {
+                // ReadBlockBaseline :187-196
+                v += pred_cur;
+                pred_cur = v;
+                const uint32_t w = jb_stage_word(lane, 0);
+                stage16[w * 2] = (int16_t)v;
+                k = 1;
+            } else if (s != 0) {
+                // :206-211
+                k += r;
+                const int z = min(k, 63);
+                stage16[jb_stage_word(lane, z >> 1) * 2 + (z & 1)] = (int16_t)v;
+                k++;
+            } else {
+                k = r == 0 ? 64 : k + 16; // EOB, or any other s==0 symbol skips 16 (:213-219)
             }
-            __syncwarp();
-            // ---- cooperative flush: 8 lanes per block, 4 blocks per instruction
-            const uint32_t amask = __ballot_sync(0xFFFFFFFFu, active);
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int bl = it * 4 + (lane >> 3); // whose block
-                const int ch = lane & 7;
-                if ((amask >> bl) & 1u) {
-                    const uint32_t slot = jb_stage_chunk(bl, ch);
-                    uint4 v = s_stage[slot];
-                    s_stage[slot] = make_uint4(0, 0, 0, 0);
-                    uint64_t blk = warp_blk0 + (uint64_t)bl * lane_stride + (uint64_t)mcu * bpm + b;
-                    reinterpret_cast<uint4 *>(coef + blk * 64)[ch] = v;
-                }
+            finished = k >= 64;
+        }
+        // ---- cooperative flush of the blocks completed in this iteration
+        uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
+        while (fin) {
+            const int L = __ffs(fin) - 1;
+            fin &= fin - 1;
+            const uint32_t dl = __shfl_sync(0xFFFFFFFFu, done, L);
+            const uint32_t sw = jb_stage_word(L, lane);
+            const uint32_t val = s_stage[sw];
+            s_stage[sw] = 0;
+            const uint64_t blk = warp_blk0 + (uint64_t)L * lane_stride + dl;
+            reinterpret_cast<uint32_t *>(coef + blk * 64)[lane] = val;
+        }
+        if (finished) {
+            done++;
+            k = 0;
+            if (++b == bpm) b = 0;
+            const int nc = s_im.blk_comp[b];
+            if (nc != comp) {
+                if (comp == 0) p0 = pred_cur; else if (comp == 1) p1 = pred_cur; else if (comp == 2) p2 = pred_cur; else p3 = pred_cur;
+                pred_cur = nc == 0 ? p0 : nc == 1 ? p1 : nc == 2 ? p2 : p3;
+                comp = nc;
             }
-            __syncwarp();
+            dct = s_tab + s_im.blk_dc[b];
+            act = s_tab + s_im.blk_ac[b];
+            active = done < nblocks;
         }
     }
 
-    if (seg < nseg && my_nmcu > 0) {
+    if (had_work) {
         // bits consumed beyond the real data => "The bit stream ended prematurely."
         if (br.n < br.pad) err |= JB_ST_PREMATURE_END;
         if (last_needs_marker && !(err & JB_ST_PREMATURE_END)) {
             // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may
             // remain before the marker (fill bytes FF are skipped by FillBuffer)
-            int real = br.n - br.pad;
+            const int real = br.n - br.pad;
             uint32_t p = br.pos;
             while (p < stop && data[p] == 0xFF) p++;
             bool marker_ok = seg < sr.nmarkers; // an RSTn or terminator follows this segment
@@ -378,5 +417,5 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
             if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
         }
     }
-    if (err) atomicOr(status + wk.image, err);
+    if (err) atomicOr(status + image, err);
 }
