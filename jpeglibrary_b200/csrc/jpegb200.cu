@@ -22,6 +22,7 @@
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
 #include "k_idct_color.cuh"
+#include "k_idct_color_fast.cuh"
 
 struct jb_ctx {
     int device = 0;
@@ -157,6 +158,55 @@ struct ImagePlan {
 
 } // namespace
 
+
+// Which K2 kernel renders this image: >= 0 fast variant (fmt * 8 + shape), -1 generic.
+static int k2_variant(const JbDevImage &d)
+{
+    if (d.precision != 8 || d.out_format > JB_OUT_YCBCR888) return -1;
+    int shape;
+    if (d.ncomp == 1) {
+        if (d.comp_h[0] != 1 || d.comp_v[0] != 1) return -1;
+        shape = 0;
+    } else if (d.ncomp == 3) {
+        if (d.comp_h[1] != 1 || d.comp_v[1] != 1 || d.comp_h[2] != 1 || d.comp_v[2] != 1) return -1;
+        const int hs = d.comp_h[0], vs = d.comp_v[0];
+        if (hs > 2 || vs > 2) return -1;
+        // blocks of an MCU must come in frame order Y..., Cb, Cr
+        if (d.comp_blk_off[0] != 0 || d.comp_blk_off[1] != hs * vs || d.comp_blk_off[2] != hs * vs + 1) return -1;
+        shape = hs == 1 ? (vs == 1 ? 1 : 3) : (vs == 1 ? 2 : 4);
+    } else
+        return -1;
+    return d.out_format * 8 + shape;
+}
+
+static uint32_t k2_fast_tiles(const JbDevImage &d)
+{
+    const uint32_t tile_mcus = JB_K2F_BLOCKS / d.bpm;
+    return (d.mcus_per_line + tile_mcus - 1) / tile_mcus * d.mcus_per_col;
+}
+
+template <int FMT>
+static void launch_k2_fast_fmt(int shape, dim3 grid, cudaStream_t st, const JbDevImage *im, const int16_t *coef,
+                               const uint16_t *q, const uint32_t *list, int tpc)
+{
+    switch (shape) {
+    case 0: jb_k2_idct_color_fast<FMT, 1, 1, 1><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
+    case 1: jb_k2_idct_color_fast<FMT, 3, 1, 1><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
+    case 2: jb_k2_idct_color_fast<FMT, 3, 2, 1><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
+    case 3: jb_k2_idct_color_fast<FMT, 3, 1, 2><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
+    default: jb_k2_idct_color_fast<FMT, 3, 2, 2><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
+    }
+}
+
+static void launch_k2_fast(int variant, dim3 grid, cudaStream_t st, const JbDevImage *im, const int16_t *coef,
+                           const uint16_t *q, const uint32_t *list, int tpc)
+{
+    const int fmt = variant / 8, shape = variant % 8;
+    if (fmt == 0) launch_k2_fast_fmt<0>(shape, grid, st, im, coef, q, list, tpc);
+    else if (fmt == 1) launch_k2_fast_fmt<1>(shape, grid, st, im, coef, q, list, tpc);
+    else launch_k2_fast_fmt<2>(shape, grid, st, im, coef, q, list, tpc);
+}
+
 struct jb_batch {
     jb_ctx *ctx = nullptr;
     int count = 0;
@@ -179,7 +229,16 @@ struct jb_batch {
     uint8_t *d_out_staging = nullptr;
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
-    uint32_t max_k1_ctas = 0, max_k2_tiles = 0;
+    uint32_t max_k1_ctas = 0;
+    // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
+    struct RenderGroup {
+        int variant;               // fast: fmt * 8 + shape (0 grey, 1 444, 2 422, 3 440, 4 420); -1 generic
+        std::vector<uint32_t> images;
+        uint32_t max_tiles = 0;
+        uint32_t list_off = 0;     // offset into d_image_list
+    };
+    std::vector<RenderGroup> groups;
+    uint32_t *d_image_list = nullptr;
     bool need_render = false;
     int launches = 0;
     bool profiling = false;
@@ -504,9 +563,25 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         } else
             pl.dev_out = pl.out.dst;
         b->max_k1_ctas = std::max(b->max_k1_ctas, (pl.dev.nseg + JB_K1_THREADS - 1) / JB_K1_THREADS);
-        uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
-        uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
-        b->max_k2_tiles = std::max(b->max_k2_tiles, strips * pl.dev.mcus_per_col);
+        if (pl.out.format != JB_OUT_COEFFICIENTS) {
+            const int variant = k2_variant(pl.dev);
+            jb_batch::RenderGroup *g = nullptr;
+            for (auto &x : b->groups)
+                if (x.variant == variant) g = &x;
+            if (!g) {
+                b->groups.emplace_back();
+                g = &b->groups.back();
+                g->variant = variant;
+            }
+            g->images.push_back((uint32_t)i);
+            uint32_t tiles;
+            if (variant >= 0) tiles = k2_fast_tiles(pl.dev);
+            else {
+                uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
+                tiles = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus * pl.dev.mcus_per_col;
+            }
+            g->max_tiles = std::max(g->max_tiles, tiles);
+        }
     }
     b->arena_bytes = arena + 256;
     b->marks_count = marks;
@@ -532,6 +607,14 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMallocAsync(&b->d_coef, blocks * 128, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, ctx->stream));
     if (staging) JB_CUDA_B(cudaMallocAsync(&b->d_out_staging, staging, ctx->stream));
+    std::vector<uint32_t> h_list;
+    for (auto &g : b->groups) {
+        g.list_off = (uint32_t)h_list.size();
+        h_list.insert(h_list.end(), g.images.begin(), g.images.end());
+    }
+    JB_CUDA_B(cudaMallocAsync(&b->d_image_list, sizeof(uint32_t) * std::max<size_t>(h_list.size(), 1), ctx->stream));
+    if (!h_list.empty())
+        JB_CUDA_B(cudaMemcpyAsync(b->d_image_list, h_list.data(), sizeof(uint32_t) * h_list.size(), cudaMemcpyHostToDevice, ctx->stream));
     for (int i = 0; i < count; i++) {
         ImagePlan &pl = b->plans[i];
         if (!pl.out.on_device) pl.dev_out = b->d_out_staging + reinterpret_cast<uint64_t>(pl.dev_out);
@@ -592,9 +675,18 @@ static int launch_kernels(jb_batch *b)
         launches++;
     }
     mark();
-    if (b->need_render) {
-        dim3 grid(b->max_k2_tiles, b->count);
-        jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant);
+    for (const auto &g : b->groups) {
+        const uint32_t *list = b->d_image_list + g.list_off;
+        if (g.variant >= 0) {
+            // a CTA walks `tpc` consecutive strips so that its per-thread constants are set up once
+            uint64_t total = (uint64_t)g.max_tiles * g.images.size();
+            int tpc = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16)));
+            dim3 grid((g.max_tiles + tpc - 1) / tpc, (unsigned)g.images.size());
+            launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc);
+        } else {
+            dim3 grid(g.max_tiles, (unsigned)g.images.size());
+            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list);
+        }
         launches++;
     }
     mark();
@@ -729,6 +821,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_coef) cudaFreeAsync(b->d_coef, b->ctx->stream);
     if (b->d_status) cudaFreeAsync(b->d_status, b->ctx->stream);
     if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
+    if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
     delete b;
 }
 
@@ -769,7 +862,7 @@ int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const i
     uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
     uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
     dim3 grid(strips * pl.dev.mcus_per_col, 1);
-    jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q);
+    jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q, nullptr);
     JB_CUDA(ctx, cudaGetLastError());
     if (!output->on_device)
         JB_CUDA(ctx, cudaMemcpyAsync(output->dst, d_out, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));

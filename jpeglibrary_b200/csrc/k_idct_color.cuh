@@ -88,7 +88,8 @@ struct JbK2Geom {
 
 __global__ void __launch_bounds__(JB_K2_THREADS)
 jb_k2_idct_color(const JbDevImage *__restrict__ images,
-                 const int16_t *__restrict__ coef, const uint16_t *__restrict__ quant)
+                 const int16_t *__restrict__ coef, const uint16_t *__restrict__ quant,
+                 const uint32_t *__restrict__ image_list)
 {
     __shared__ __align__(16) float s_f[JB_K2_MAX_BLOCKS * JB_K2_BLOCK_STRIDE];
     __shared__ __align__(16) int16_t s_plane[JB_K2_MAX_BLOCKS * 64];
@@ -98,7 +99,7 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
 
     // grid = (tiles per image, images); a tile is a strip of consecutive MCUs of one MCU row
     JbTileWork tw;
-    tw.image = blockIdx.y;
+    tw.image = image_list ? image_list[blockIdx.y] : blockIdx.y;
     const int tid = threadIdx.x;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(images + tw.image);
