@@ -19,8 +19,11 @@
 // Huffman decoding table, device form.  Built on the host by *simulating* the reference's
 // JpegHuffmanDecodingTable.Lookup/LookupSlow (JpegHuffmanDecodingTable.cs:73-113) for every
 // 10-bit prefix, so every code -- valid or not -- resolves exactly as in the reference.
+#define JB_LUT2_SUBTABLES 8
 struct __align__(16) JbHuffTable {
-    uint16_t lut[JB_LUT_SIZE]; // (symbol << 8) | code size; size 0 => slow path
+    uint16_t lut[JB_LUT_SIZE]; // (symbol << 8) | code size; size 0 => escape: high byte = 1 + second-level
+                               // sub-table (indexed by the remaining 6 bits), or 0 => slow path
+    uint16_t lut2[JB_LUT2_SUBTABLES * 64]; // (symbol << 8) | code size; 0 => slow path
     uint16_t maxcode[20];      // reference _maxCode[0..17] (left-aligned 16-bit), padded
     uint8_t valoffset[24];     // reference _valOffset[0..18], padded
     uint8_t values[256];

@@ -140,6 +140,25 @@ bool build_device_table(const jb_huff_spec &s, JbHuffTable &d)
         ref_lookup(t, hi, s2, y2);
         if (s1 == s2 && y1 == y2 && s1 <= JB_LUT_BITS) d.lut[p] = (uint16_t)((y1 << 8) | s1);
     }
+    // second level: for the first few prefixes that need more than 10 bits, resolve the remaining
+    // 6 bits by the same simulation (10 + 6 = all 16 bits the reference ever looks at)
+    int nsub = 0;
+    for (int p = JB_LUT_SIZE - 1; p >= 0 && nsub < JB_LUT2_SUBTABLES; p--) { // long codes sit at the top
+        if (d.lut[p] != 0) continue;
+        bool any = false;
+        for (int x = 0; x < 64; x++) {
+            int sz, sy;
+            ref_lookup(t, (p << 6) | x, sz, sy);
+            if (sz <= 16) {
+                d.lut2[nsub * 64 + x] = (uint16_t)((sy << 8) | sz);
+                any = true;
+            }
+        }
+        if (any) {
+            d.lut[p] = (uint16_t)((nsub + 1) << 8);
+            nsub++;
+        }
+    }
     memcpy(d.maxcode, t.maxcode, sizeof t.maxcode);
     memcpy(d.valoffset, t.valoffset, sizeof t.valoffset);
     memcpy(d.values, t.values, 256);
@@ -230,6 +249,7 @@ struct jb_batch {
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
     uint32_t max_k1_ctas = 0;
+    int max_tables = 1; // most Huffman tables any image refers to (sizes K1's shared memory)
     // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
     struct RenderGroup {
         int variant;               // fast: fmt * 8 + shape (0 grey, 1 444, 2 422, 3 440, 4 420); -1 generic
@@ -563,6 +583,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         } else
             pl.dev_out = pl.out.dst;
         b->max_k1_ctas = std::max(b->max_k1_ctas, (pl.dev.nseg + JB_K1_THREADS - 1) / JB_K1_THREADS);
+        b->max_tables = std::max<int>(b->max_tables, pl.dev.ntables);
         if (pl.out.format != JB_OUT_COEFFICIENTS) {
             const int variant = k2_variant(pl.dev);
             jb_batch::RenderGroup *g = nullptr;
@@ -669,9 +690,9 @@ static int launch_kernels(jb_batch *b)
     mark();
     {
         dim3 grid(b->max_k1_ctas, b->count);
-        size_t smem = JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * JB_K1_STAGE_BYTES;
+        size_t smem = b->max_tables * sizeof(JbHuffTable) + JB_K1_WARPS * JB_K1_STAGE_BYTES;
         jb_k1_huff_segments<<<grid, JB_K1_THREADS, smem, st>>>(b->d_images, b->d_tables, b->d_arena, b->d_marks,
-                                                               b->d_scan, b->d_coef, b->d_status);
+                                                               b->d_scan, b->d_coef, b->d_status, b->max_tables);
         launches++;
     }
     mark();

@@ -129,9 +129,11 @@ jb_k0_restart_scan(const JbDevImage *__restrict__ images, const uint8_t *__restr
 
 // ---------------------------------------------------------------------------------------------
 // Bit reader: 64-bit MSB-first window (hi:lo) refilled 32 bits at a time from the stuffed byte
-// stream.  The stream is read as aligned 32-bit words kept in registers (w0,w1 = the two words
-// under the read position, w2 = software prefetch of the next one), so un-stuffing (FF 00 -> FF),
-// fill bytes (FF FF) and misalignment are handled by register arithmetic without extra loads.
+// stream.  The stream is read as aligned 32-bit words held in registers (w0 = word under the read
+// position, w1 = next, w2 = software prefetch), so the common refill is: "position aligned, no
+// 0xFF in w0" -> append the byte-swapped word.  Everything else (FF 00 -> FF, FF FF fill bytes,
+// misalignment after a stuffed pair or at the segment start, the segment end) goes through a
+// byte-wise path that works on the registers and returns as soon as the position is aligned again.
 // At the segment end the window is padded with 1-bits exactly like PeekBits does
 // (JpegBitReader.cs:166); `pad` counts them so that consuming padding as magnitude bits is
 // reported like ReceiveAndExtend's failure (JpegHuffmanScanDecoder.cs:100-110).
@@ -160,63 +162,53 @@ struct JbBitReader {
         lo |= __funnelshift_rc(0u, w, n);
         n += bits;
     }
-    __device__ __forceinline__ void advance(uint32_t nbytes)
-    { // nbytes <= 4
-        const uint32_t np = pos + nbytes;
-        if ((np ^ pos) & ~3u) {
-            w0 = w1; w1 = w2;
-            w2 = ldw((np & ~3u) + 8);
-        }
-        pos = np;
+    __device__ __forceinline__ void next_word()
+    { // pos has just become a multiple of 4
+        w0 = w1; w1 = w2;
+        w2 = ldw(pos + 8);
     }
-    __device__ __forceinline__ uint32_t candidate() const
-    { // the 4 bytes at pos, first byte in the most significant position
-        return __byte_perm(w0, w1, 0x0123u + 0x1111u * (pos & 3u));
-    }
-    __device__ __forceinline__ void refill_slow(uint32_t cw)
+    __device__ __forceinline__ void refill_slow()
     {
-        uint32_t w = 0, consumed = 0;
+        uint32_t w = 0;
         int bits = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (consumed > (uint32_t)i) continue; // the zero of an FF00 pair
-            const uint32_t p = pos + i;
-            if (p >= end) {
+        do {
+            if (pos >= end) {
                 w |= 0xFFFFFFFFu >> bits;
                 pad += 32 - bits;
                 bits = 32;
                 break;
             }
-            const uint32_t b = (cw >> (24 - 8 * i)) & 0xFF;
+            const uint32_t o = pos & 3u;
+            const uint32_t b = (w0 >> (8 * o)) & 0xFF;
             if (b == 0xFF) {
-                if (i == 3) break; // successor not in the candidate: next refill starts at this FF
-                const uint32_t b2 = (cw >> (16 - 8 * i)) & 0xFF;
-                if (b2 == 0xFF) { consumed = i + 1; continue; } // fill byte
-                if (b2 != 0) { // a marker inside the segment: it ends here
-                    end = p;
-                    w |= 0xFFFFFFFFu >> bits;
-                    pad += 32 - bits;
-                    bits = 32;
-                    break;
+                const uint32_t b2 = o < 3 ? (w0 >> (8 * o + 8)) & 0xFF : w1 & 0xFF;
+                if (b2 != 0xFF && b2 != 0) { // a marker inside the segment: it ends here
+                    end = pos;
+                    continue;
                 }
-                consumed = i + 2; // stuffed zero
-            } else
-                consumed = i + 1;
-            w |= b << (24 - bits);
-            bits += 8;
-        }
-        advance(consumed);
+                if (b2 == 0) { // stuffed zero: FF is data, skip both bytes
+                    w |= 0xFFu << (24 - bits);
+                    bits += 8;
+                    if (((++pos) & 3u) == 0) next_word();
+                }
+                // (fill byte: the first FF is dropped)
+            } else {
+                w |= b << (24 - bits);
+                bits += 8;
+            }
+            if (((++pos) & 3u) == 0) next_word();
+        } while (bits < 32 && (pos & 3u) != 0);
         put(w, bits);
     }
     __device__ __forceinline__ void refill()
     { // call when n <= 32
-        const uint32_t cw = candidate();
-        if (pos + 4 <= end && jb_ff_bytes(cw) == 0) {
-            put(cw, 32);
-            advance(4);
+        if ((pos & 3u) == 0 && pos + 4 <= end && jb_ff_bytes(w0) == 0) {
+            put(__byte_perm(w0, 0, 0x0123), 32);
+            pos += 4;
+            next_word();
             return;
         }
-        refill_slow(cw);
+        refill_slow();
     }
     __device__ __forceinline__ void ensure32()
     {
@@ -242,12 +234,9 @@ __device__ __forceinline__ int jb_extend(int v, int nbits)
     return v - ((((v + v) >> nbits) - 1) & ((1 << nbits) - 1));
 }
 
-// returns (symbol << 8) | size, or 0xFFFFFFFF for an invalid code
-__device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_t code16)
+// LookupSlow, JpegHuffmanDecodingTable.cs:88-113; returns (symbol << 8) | size or 0xFFFFFFFF
+__device__ __noinline__ uint32_t jb_huff_lookup_slow(const JbHuffTable *t, uint32_t code16)
 {
-    uint32_t e = t->lut[code16 >> (16 - JB_LUT_BITS)];
-    if ((e & 0xFF) != 0) return e;
-    // LookupSlow, JpegHuffmanDecodingTable.cs:88-113
     int size = 9;
     while (code16 > t->maxcode[size]) size++;
     if (size > 16) return 0xFFFFFFFFu;
@@ -255,31 +244,46 @@ __device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_
     return (sym << 8) | (uint32_t)size;
 }
 
+// returns (symbol << 8) | size, or 0xFFFFFFFF for an invalid code
+__device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_t code16)
+{
+    uint32_t e = t->lut[code16 >> (16 - JB_LUT_BITS)];
+    if ((e & 0xFF) != 0) return e;
+    if (e != 0) {
+        e = t->lut2[((e >> 8) - 1) * 64 + (code16 & 63)];
+        if (e != 0) return e;
+    }
+    return jb_huff_lookup_slow(t, code16);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1a: one thread per restart segment, 32 consecutive segments of one image per warp.
 // Every lane runs the same flat loop -- one Huffman symbol per iteration -- over its own segment,
 // so lanes never wait for each other at block boundaries.  Each lane assembles its current 8x8
-// block in a rotated shared-memory staging tile; whenever lanes complete blocks, the whole warp
-// flushes them one after the other with one coalesced 128-byte store per block (lane j moves
-// word j), so every coefficient block leaves the SM as one full line and is written exactly once.
+// block in a rotated shared-memory staging tile; whenever lanes complete blocks, the warp flushes
+// them two at a time (16 lanes x 8 bytes per block), so every coefficient block leaves the SM as
+// one full 128-byte line and is written exactly once.
 // ---------------------------------------------------------------------------------------------
-#define JB_K1_WARPS 4
+#define JB_K1_WARPS 8
 #define JB_K1_THREADS (JB_K1_WARPS * 32)
 #define JB_K1_STAGE_BYTES (32 * 128)
 
-__device__ __forceinline__ uint32_t jb_stage_word(int lane, int word)
-{ // 32-bit word `word` (0..31) of lane's block; 16-byte chunks rotated by lane -> conflict-free flush
-    return (uint32_t)(lane * 32 + ((((word >> 2) + lane) & 7) << 2) + (word & 3));
+__device__ __forceinline__ uint32_t jb_stage_off(int lane, int z)
+{ // byte offset of coefficient z of lane's block inside the warp's staging tile; 8-byte pairs are
+  // rotated by the lane index: per-lane scattered stores spread over the banks and the 16-lane
+  // flush reads are conflict-free
+    return (uint32_t)(lane * 128 + ((((z >> 2) + lane) & 15) << 3) + ((z & 3) << 1));
 }
 
 __global__ void __launch_bounds__(JB_K1_THREADS)
 jb_k1_huff_segments(const JbDevImage *__restrict__ images,
                     const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
                     const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
-                    int16_t *__restrict__ coef, uint32_t *__restrict__ status)
+                    int16_t *__restrict__ coef, uint32_t *__restrict__ status, int table_slots)
 {
     extern __shared__ uint4 jb_smem[];
     __shared__ JbDevImage s_im;
+    __shared__ uint32_t s_binfo[JB_MAX_BLOCKS_PER_MCU]; // per block-in-mcu: comp<<28 | ac table off/16 <<14 | dc table off/16
     // grid = (CTAs per image, images): a CTA decodes JB_K1_THREADS consecutive segments of one image
     const uint32_t image = blockIdx.y, first_seg = blockIdx.x * JB_K1_THREADS;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -297,9 +301,13 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
         uint4 *dst = reinterpret_cast<uint4 *>(s_tab + t);
         for (int i = tid; i < (int)(sizeof(JbHuffTable) / 16); i += JB_K1_THREADS) dst[i] = __ldg(src + i);
     }
-    uint32_t *s_stage = reinterpret_cast<uint32_t *>(jb_smem + (JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable)) / 16) +
-                        wid * (JB_K1_STAGE_BYTES / 4);
-    for (int i = lane; i < JB_K1_STAGE_BYTES / 4; i += 32) s_stage[i] = 0;
+    if (tid < JB_MAX_BLOCKS_PER_MCU)
+        s_binfo[tid] = ((uint32_t)s_im.blk_comp[tid] << 28) |
+                       ((uint32_t)(s_im.blk_ac[tid] * (sizeof(JbHuffTable) / 16)) << 14) |
+                       (uint32_t)(s_im.blk_dc[tid] * (sizeof(JbHuffTable) / 16));
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(jb_smem) + (size_t)table_slots * sizeof(JbHuffTable) +
+                       wid * JB_K1_STAGE_BYTES;
+    for (int i = lane; i < JB_K1_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
     const uint32_t nseg = s_im.nseg;
@@ -311,44 +319,41 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
     const uint32_t *mk = marks + s_im.mark_base;
 
     // segment bounds from the marker index
-    uint32_t nblocks = 0, start = 0, stop = 0, err = 0;
+    uint32_t left = 0, start = 0, stop = 0, err = 0; // left = blocks this lane still has to decode
     bool last_needs_marker = false;
     if (seg < nseg) {
         const uint32_t my_nmcu = min(dri, s_im.total_mcus - seg * dri);
-        nblocks = my_nmcu * bpm;
+        left = my_nmcu * bpm;
         if (seg > 0) {
             if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
-            else { err |= JB_ST_EXPECT_RST; nblocks = 0; }
+            else { err |= JB_ST_EXPECT_RST; left = 0; }
         }
         stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
         // the reference expects RSTn or EOI right after every *complete* interval
         // (JpegHuffmanBaselineScanDecoder.cs:139-154)
         last_needs_marker = s_im.dri != 0 && my_nmcu == dri;
     }
-    const bool had_work = nblocks > 0;
+    const bool had_work = left > 0;
 
     JbBitReader br;
     br.init(data, start, stop);
-    int16_t *stage16 = reinterpret_cast<int16_t *>(s_stage);
     // per-lane decoder state
-    uint32_t done = 0;     // blocks completed by this lane
-    int b = 0;             // block-in-mcu of the current block
-    int k = 0;             // next zig-zag index; 0 = the DC symbol comes next
+    int b = 0; // block-in-mcu of the current block
+    int k = 0; // next zig-zag index; 0 = the DC symbol comes next
     int pred_cur = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0; // DC predictors (current component / saved)
-    int comp = s_im.blk_comp[0];
-    const JbHuffTable *dct = s_tab + s_im.blk_dc[0], *act = s_tab + s_im.blk_ac[0];
-    bool active = nblocks > 0;
+    uint32_t binfo = s_binfo[0];
+    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(s_tab);
+    // address of this lane's current block in the coefficient store
+    uint8_t *gptr = reinterpret_cast<uint8_t *>(coef) + (s_im.coef_off + (uint64_t)seg * dri * bpm) * 128;
+    const uint32_t lane8 = (lane & 15) * 8;
 
-    // first block of this warp's lane 0 and the stride between consecutive segments (in blocks)
-    const uint64_t warp_blk0 = s_im.coef_off + (uint64_t)(first_seg + wid * 32) * dri * bpm;
-    const uint32_t lane_stride = dri * bpm;
-
-    while (__any_sync(0xFFFFFFFFu, active)) {
+    while (__any_sync(0xFFFFFFFFu, left != 0)) {
         bool finished = false;
-        if (active) {
+        if (left != 0) {
             br.ensure32();
             const bool is_dc = k == 0;
-            uint32_t e = jb_huff_lookup(is_dc ? dct : act, br.peek16());
+            const uint32_t toff = (is_dc ? binfo : (binfo >> 14)) & 0x3FFFu;
+            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + toff * 16), br.peek16());
             if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; if (!is_dc) k = 64; }
             br.skip(e & 0xFF);
             const int sym = (int)(e >> 8);
@@ -361,45 +366,47 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
                 // ReadBlockBaseline :187-196
                 v += pred_cur;
                 pred_cur = v;
-                const uint32_t w = jb_stage_word(lane, 0);
-                stage16[w * 2] = (int16_t)v;
+                *reinterpret_cast<int16_t *>(s_stage + jb_stage_off(lane, 0)) = (int16_t)v;
                 k = 1;
             } else if (s != 0) {
                 // :206-211
                 k += r;
-                const int z = min(k, 63);
-                stage16[jb_stage_word(lane, z >> 1) * 2 + (z & 1)] = (int16_t)v;
+                *reinterpret_cast<int16_t *>(s_stage + jb_stage_off(lane, min(k, 63))) = (int16_t)v;
                 k++;
             } else {
                 k = r == 0 ? 64 : k + 16; // EOB, or any other s==0 symbol skips 16 (:213-219)
             }
             finished = k >= 64;
         }
-        // ---- cooperative flush of the blocks completed in this iteration
+        // ---- cooperative flush of the blocks completed in this iteration, two per round:
+        //      lanes 0-15 move the lowest finished lane's block, lanes 16-31 the next one
         uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
         while (fin) {
-            const int L = __ffs(fin) - 1;
-            fin &= fin - 1;
-            const uint32_t dl = __shfl_sync(0xFFFFFFFFu, done, L);
-            const uint32_t sw = jb_stage_word(L, lane);
-            const uint32_t val = s_stage[sw];
-            s_stage[sw] = 0;
-            const uint64_t blk = warp_blk0 + (uint64_t)L * lane_stride + dl;
-            reinterpret_cast<uint32_t *>(coef + blk * 64)[lane] = val;
+            const uint32_t fin2 = fin & (fin - 1);
+            const uint32_t pick = (lane & 16) ? fin2 : fin;
+            const int L = __ffs(pick) - 1; // -1: nothing for this half
+            const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)reinterpret_cast<uint64_t>(gptr), L & 31);
+            const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(reinterpret_cast<uint64_t>(gptr) >> 32), L & 31);
+            if (L >= 0) {
+                uint2 *sp = reinterpret_cast<uint2 *>(s_stage + L * 128 + ((((lane & 15) + L) & 15) << 3));
+                const uint2 val = *sp;
+                *sp = make_uint2(0, 0);
+                *reinterpret_cast<uint2 *>((((uint64_t)ghi << 32) | glo) + lane8) = val;
+            }
+            fin = fin2 & (fin2 - 1);
         }
         if (finished) {
-            done++;
+            left--;
+            gptr += 128;
             k = 0;
             if (++b == bpm) b = 0;
-            const int nc = s_im.blk_comp[b];
-            if (nc != comp) {
+            const uint32_t ni = s_binfo[b];
+            if ((ni ^ binfo) >> 28) {
+                const int comp = binfo >> 28, nc = ni >> 28;
                 if (comp == 0) p0 = pred_cur; else if (comp == 1) p1 = pred_cur; else if (comp == 2) p2 = pred_cur; else p3 = pred_cur;
                 pred_cur = nc == 0 ? p0 : nc == 1 ? p1 : nc == 2 ? p2 : p3;
-                comp = nc;
             }
-            dct = s_tab + s_im.blk_dc[b];
-            act = s_tab + s_im.blk_ac[b];
-            active = done < nblocks;
+            binfo = ni;
         }
     }
 

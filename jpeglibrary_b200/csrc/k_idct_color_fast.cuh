@@ -136,20 +136,34 @@ jb_k2_idct_color_fast(const JbDevImage *__restrict__ images, const int16_t *__re
     float *fb = s_f + j * JB_K2F_F_STRIDE;
     bool bulk_pending = false;
 
-    for (int it = 0; it < tiles_per_cta; it++) {
-        const uint32_t tile = blockIdx.x * tiles_per_cta + it;
-        if (tile >= ntiles) break;
-        const uint32_t mcu_row = tile / strips;
-        const uint32_t mcu_col0 = (tile - mcu_row * strips) * TILE_MCUS;
+    // strips are walked with incremental (row, column) counters and the next strip's coefficients are
+    // prefetched into registers while the current strip is transformed (hides the HBM latency)
+    uint32_t tile = blockIdx.x * tiles_per_cta;
+    uint32_t mcu_row = tile / strips;
+    uint32_t strip = tile - mcu_row * strips;
+    const uint32_t tile_end = min(tile + (uint32_t)tiles_per_cta, ntiles);
+    auto load_raw = [&](uint32_t row, uint32_t st) -> uint4 {
+        const uint32_t col0 = st * TILE_MCUS;
+        const int nm = (int)min((uint32_t)TILE_MCUS, mcus_per_line - col0);
+        if (m >= nm) return make_uint4(0, 0, 0, 0);
+        const uint64_t blk0 = s_im.coef_off + ((uint64_t)row * mcus_per_line + col0) * BPM;
+        return __ldg(reinterpret_cast<const uint4 *>(coef + (blk0 + j) * 64) + r);
+    };
+    uint4 raw_next = make_uint4(0, 0, 0, 0);
+    if (tile < tile_end) raw_next = load_raw(mcu_row, strip);
+
+    for (; tile < tile_end; tile++) {
+        const uint32_t mcu_col0 = strip * TILE_MCUS;
         const int nmcu = (int)min((uint32_t)TILE_MCUS, mcus_per_line - mcu_col0);
         const bool valid = m < nmcu;
+        const uint32_t cur_row = mcu_row;
+        // advance the counters and issue the next strip's loads
+        if (++strip == strips) { strip = 0; mcu_row++; }
+        const uint4 raw = raw_next;
+        if (tile + 1 < tile_end) raw_next = load_raw(mcu_row, strip);
 
         // ------------------------------------------------ phase A
-        if (valid) {
-            const uint64_t blk0 = s_im.coef_off + ((uint64_t)mcu_row * mcus_per_line + mcu_col0) * BPM;
-            const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(coef + (blk0 + j) * 64) + r);
-            *reinterpret_cast<uint4 *>(rawb + r * 8) = raw;
-        }
+        if (valid) *reinterpret_cast<uint4 *>(rawb + r * 8) = raw;
         __syncwarp(wm);
         float y[8], d[8];
         if (valid) {
@@ -267,7 +281,7 @@ jb_k2_idct_color_fast(const JbDevImage *__restrict__ images, const int16_t *__re
             }
         }
         // ------------------------------------------------ phase C: staging tile -> global
-        const int x0 = mcu_col0 * 8 * HS, y0 = mcu_row * TH;
+        const int x0 = mcu_col0 * 8 * HS, y0 = cur_row * TH;
         const int rows = min(TH, H - y0);
         const int row_bytes = min(ROW_BYTES, (W - x0) * BPP);
         if (bulk_ok && row_bytes == ROW_BYTES) {
