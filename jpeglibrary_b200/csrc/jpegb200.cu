@@ -248,8 +248,7 @@ struct jb_batch {
     uint8_t *d_out_staging = nullptr;
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
-    uint32_t max_k1_ctas = 0;
-    int max_tables = 1; // most Huffman tables any image refers to (sizes K1's shared memory)
+    uint32_t max_nseg = 1; // most restart segments any image has (sizes K1's CTAs)
     // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
     struct RenderGroup {
         int variant;               // fast: fmt * 8 + shape (0 grey, 1 444, 2 422, 3 440, 4 420); -1 generic
@@ -582,8 +581,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             staging += pl.out_bytes;
         } else
             pl.dev_out = pl.out.dst;
-        b->max_k1_ctas = std::max(b->max_k1_ctas, (pl.dev.nseg + JB_K1_THREADS - 1) / JB_K1_THREADS);
-        b->max_tables = std::max<int>(b->max_tables, pl.dev.ntables);
+        b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
         if (pl.out.format != JB_OUT_COEFFICIENTS) {
             const int variant = k2_variant(pl.dev);
             jb_batch::RenderGroup *g = nullptr;
@@ -648,8 +646,6 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMemcpyAsync(b->d_tables, b->tables.data(), sizeof(JbHuffTable) * b->tables.size(), cudaMemcpyHostToDevice, ctx->stream));
     JB_CUDA_B(cudaMemcpyAsync(b->d_quant, b->quant.data(), sizeof(uint16_t) * b->quant.size(), cudaMemcpyHostToDevice, ctx->stream));
     JB_CUDA_B(cudaStreamSynchronize(ctx->stream));
-    JB_CUDA_B(cudaFuncSetAttribute(jb_k1_huff_segments, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(JB_MAX_TABLE_SLOTS * sizeof(JbHuffTable) + JB_K1_WARPS * JB_K1_STAGE_BYTES)));
 #undef JB_CUDA_B
     *out = b;
     return JB_OK;
@@ -689,10 +685,14 @@ static int launch_kernels(jb_batch *b)
     launches++;
     mark();
     {
-        dim3 grid(b->max_k1_ctas, b->count);
-        size_t smem = b->max_tables * sizeof(JbHuffTable) + JB_K1_WARPS * JB_K1_STAGE_BYTES;
-        jb_k1_huff_segments<<<grid, JB_K1_THREADS, smem, st>>>(b->d_images, b->d_tables, b->d_arena, b->d_marks,
-                                                               b->d_scan, b->d_coef, b->d_status, b->max_tables);
+        // one warp per 32 segments; a CTA never spans images, so pick the CTA size that wastes the
+        // fewest warp slots for this batch (at most JB_K1_MAX_WARPS warps)
+        const uint32_t warps = std::min<uint32_t>(JB_K1_MAX_WARPS, (b->max_nseg + 31) / 32);
+        const uint32_t threads = warps * 32;
+        dim3 grid((b->max_nseg + threads - 1) / threads, b->count);
+        size_t smem = warps * JB_K1_STAGE_BYTES;
+        jb_k1_huff_segments<<<grid, threads, smem, st>>>(b->d_images, b->d_tables, b->d_arena, b->d_marks,
+                                                         b->d_scan, b->d_coef, b->d_status);
         launches++;
     }
     mark();

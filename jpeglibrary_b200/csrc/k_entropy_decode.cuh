@@ -148,7 +148,9 @@ struct JbBitReader {
 
     __device__ __forceinline__ uint32_t ldw(uint32_t byte_off) const
     {
-        return __ldg(reinterpret_cast<const uint32_t *>(data + byte_off));
+        uint32_t v; // streamed once: keep it out of L1, which holds the Huffman tables
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(data + byte_off));
+        return v;
     }
     __device__ __forceinline__ void init(const uint8_t *d, uint32_t start, uint32_t stop)
     {
@@ -238,19 +240,21 @@ __device__ __forceinline__ int jb_extend(int v, int nbits)
 __device__ __noinline__ uint32_t jb_huff_lookup_slow(const JbHuffTable *t, uint32_t code16)
 {
     int size = 9;
-    while (code16 > t->maxcode[size]) size++;
+    while (code16 > __ldg(&t->maxcode[size])) size++;
     if (size > 16) return 0xFFFFFFFFu;
-    uint32_t sym = t->values[(t->valoffset[size] + (code16 >> (16 - size))) & 0xFF];
+    uint32_t sym = __ldg(&t->values[(__ldg(&t->valoffset[size]) + (code16 >> (16 - size))) & 0xFF]);
     return (sym << 8) | (uint32_t)size;
 }
 
-// returns (symbol << 8) | size, or 0xFFFFFFFF for an invalid code
+// returns (symbol << 8) | size, or 0xFFFFFFFF for an invalid code.  The tables (a few KB, shared by
+// every lane of every warp) are read through the read-only path and stay L1-resident; keeping them
+// out of shared memory is what lets all restart segments of a 1024-image batch be resident at once.
 __device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_t code16)
 {
-    uint32_t e = t->lut[code16 >> (16 - JB_LUT_BITS)];
+    uint32_t e = __ldg(&t->lut[code16 >> (16 - JB_LUT_BITS)]);
     if ((e & 0xFF) != 0) return e;
     if (e != 0) {
-        e = t->lut2[((e >> 8) - 1) * 64 + (code16 & 63)];
+        e = __ldg(&t->lut2[((e >> 8) - 1) * 64 + (code16 & 63)]);
         if (e != 0) return e;
     }
     return jb_huff_lookup_slow(t, code16);
@@ -264,8 +268,7 @@ __device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_
 // them two at a time (16 lanes x 8 bytes per block), so every coefficient block leaves the SM as
 // one full 128-byte line and is written exactly once.
 // ---------------------------------------------------------------------------------------------
-#define JB_K1_WARPS 8
-#define JB_K1_THREADS (JB_K1_WARPS * 32)
+#define JB_K1_MAX_WARPS 8 // warps per CTA are chosen at launch: ceil(segments per image / 32), at most 8
 #define JB_K1_STAGE_BYTES (32 * 128)
 
 __device__ __forceinline__ uint32_t jb_stage_off(int lane, int z)
@@ -275,38 +278,30 @@ __device__ __forceinline__ uint32_t jb_stage_off(int lane, int z)
     return (uint32_t)(lane * 128 + ((((z >> 2) + lane) & 15) << 3) + ((z & 3) << 1));
 }
 
-__global__ void __launch_bounds__(JB_K1_THREADS)
+__global__ void __launch_bounds__(JB_K1_MAX_WARPS * 32)
 jb_k1_huff_segments(const JbDevImage *__restrict__ images,
                     const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
                     const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
-                    int16_t *__restrict__ coef, uint32_t *__restrict__ status, int table_slots)
+                    int16_t *__restrict__ coef, uint32_t *__restrict__ status)
 {
     extern __shared__ uint4 jb_smem[];
     __shared__ JbDevImage s_im;
-    __shared__ uint32_t s_binfo[JB_MAX_BLOCKS_PER_MCU]; // per block-in-mcu: comp<<28 | ac table off/16 <<14 | dc table off/16
-    // grid = (CTAs per image, images): a CTA decodes JB_K1_THREADS consecutive segments of one image
-    const uint32_t image = blockIdx.y, first_seg = blockIdx.x * JB_K1_THREADS;
+    __shared__ uint2 s_binfo[JB_MAX_BLOCKS_PER_MCU]; // per block-in-mcu: x = comp<<28 | dc table offset/16, y = ac table offset/16
+    // grid = (CTAs per image, images): a CTA decodes blockDim.x consecutive segments of one image
+    const uint32_t image = blockIdx.y, first_seg = blockIdx.x * blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (first_seg >= images[image].nseg) return;
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
-        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K1_THREADS) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    JbHuffTable *s_tab = reinterpret_cast<JbHuffTable *>(jb_smem);
-    const int ntab = s_im.ntables;
-    for (int t = 0; t < ntab; t++) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tables + s_im.table_index[t]);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_tab + t);
-        for (int i = tid; i < (int)(sizeof(JbHuffTable) / 16); i += JB_K1_THREADS) dst[i] = __ldg(src + i);
-    }
-    if (tid < JB_MAX_BLOCKS_PER_MCU)
-        s_binfo[tid] = ((uint32_t)s_im.blk_comp[tid] << 28) |
-                       ((uint32_t)(s_im.blk_ac[tid] * (sizeof(JbHuffTable) / 16)) << 14) |
-                       (uint32_t)(s_im.blk_dc[tid] * (sizeof(JbHuffTable) / 16));
-    uint8_t *s_stage = reinterpret_cast<uint8_t *>(jb_smem) + (size_t)table_slots * sizeof(JbHuffTable) +
-                       wid * JB_K1_STAGE_BYTES;
+    if (tid < JB_MAX_BLOCKS_PER_MCU) // table offsets in units of 16 bytes from the device table array
+        s_binfo[tid] = make_uint2(((uint32_t)s_im.blk_comp[tid] << 28) |
+                                      (uint32_t)(s_im.table_index[s_im.blk_dc[tid]] * (sizeof(JbHuffTable) / 16)),
+                                  (uint32_t)(s_im.table_index[s_im.blk_ac[tid]] * (sizeof(JbHuffTable) / 16)));
+    uint8_t *s_stage = reinterpret_cast<uint8_t *>(jb_smem) + wid * JB_K1_STAGE_BYTES;
     for (int i = lane; i < JB_K1_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
@@ -341,8 +336,8 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
     int b = 0; // block-in-mcu of the current block
     int k = 0; // next zig-zag index; 0 = the DC symbol comes next
     int pred_cur = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0; // DC predictors (current component / saved)
-    uint32_t binfo = s_binfo[0];
-    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(s_tab);
+    uint2 binfo = s_binfo[0];
+    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(tables);
     // address of this lane's current block in the coefficient store
     uint8_t *gptr = reinterpret_cast<uint8_t *>(coef) + (s_im.coef_off + (uint64_t)seg * dri * bpm) * 128;
     const uint32_t lane8 = (lane & 15) * 8;
@@ -352,8 +347,8 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
         if (left != 0) {
             br.ensure32();
             const bool is_dc = k == 0;
-            const uint32_t toff = (is_dc ? binfo : (binfo >> 14)) & 0x3FFFu;
-            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + toff * 16), br.peek16());
+            const uint32_t toff = is_dc ? (binfo.x & 0x0FFFFFFFu) : binfo.y;
+            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)toff * 16), br.peek16());
             if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; if (!is_dc) k = 64; }
             br.skip(e & 0xFF);
             const int sym = (int)(e >> 8);
@@ -400,9 +395,9 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
             gptr += 128;
             k = 0;
             if (++b == bpm) b = 0;
-            const uint32_t ni = s_binfo[b];
-            if ((ni ^ binfo) >> 28) {
-                const int comp = binfo >> 28, nc = ni >> 28;
+            const uint2 ni = s_binfo[b];
+            if ((ni.x ^ binfo.x) >> 28) {
+                const int comp = binfo.x >> 28, nc = ni.x >> 28;
                 if (comp == 0) p0 = pred_cur; else if (comp == 1) p1 = pred_cur; else if (comp == 2) p2 = pred_cur; else p3 = pred_cur;
                 pred_cur = nc == 0 ? p0 : nc == 1 ? p1 : nc == 2 ? p2 : p3;
             }
