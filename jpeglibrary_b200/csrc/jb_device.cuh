@@ -52,6 +52,11 @@ struct JbDevImage {
     uint16_t table_index[JB_MAX_TABLE_SLOTS]; // slot -> index into the device table array
     uint8_t ntables;
     uint8_t pad0[3];
+    // self-synchronising decode (scans without restart markers)
+    uint32_t use_selfsync; // 1: K1b path
+    uint32_t sub_base;     // first sub-sequence slot of this image in the sub-sequence arrays
+    uint32_t sub_cap;      // slots reserved
+    uint32_t pad2;
     // coefficient store
     uint64_t coef_off;   // first block of this image in the coefficient store (in blocks)
     uint32_t quant_off;  // first of ncomp quant tables (64 x uint16 each) in the quant array

@@ -21,6 +21,7 @@
 
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
+#include "k_entropy_selfsync.cuh"
 #include "k_idct_color.cuh"
 #include "k_idct_color_fast.cuh"
 
@@ -54,6 +55,8 @@ static int fail(jb_ctx *ctx, int code, const char *fmt, int image, const char *d
 // ------------------------------------------------------------------------------------------------
 // Huffman table: reference construction, then a 10-bit LUT obtained by simulating the reference lookup
 // ------------------------------------------------------------------------------------------------
+#define JB_SS_ROUNDS 5 // synchronisation rounds after the guess round (the last one must change nothing)
+
 namespace {
 
 struct RefTable { // JpegHuffmanDecodingTable fields
@@ -249,6 +252,17 @@ struct jb_batch {
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
     uint32_t max_nseg = 1; // most restart segments any image has (sizes K1's CTAs)
+    // self-synchronising path (images without restart markers)
+    std::vector<uint32_t> seg_images, ss_images; // K1a / K1b image lists
+    uint32_t ss_list_off = 0, seg_list_off = 0;
+    uint32_t ss_max_sub = 0;
+    uint64_t ss_total_sub = 0;
+    uint8_t *d_clean = nullptr;
+    uint32_t *d_clean_len = nullptr;
+    JbSubState *d_exits = nullptr, *d_used = nullptr;
+    JbSubInfo *d_info = nullptr;
+    uint32_t *d_changed = nullptr; // one counter per synchronisation round
+    bool ss_converged = true;
     // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
     struct RenderGroup {
         int variant;               // fast: fmt * 8 + shape (0 grey, 1 444, 2 422, 3 440, 4 420); -1 generic
@@ -475,6 +489,7 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     d.dri = sc.restart_interval;
     d.nseg = d.dri ? (d.total_mcus + d.dri - 1) / d.dri : 1;
     d.mark_cap = d.nseg + 1;
+    // scans without restart markers are decoded by speculative sub-sequences (K1b) unless tiny
     if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
     pl.entropy_off = sc.entropy_offset;
     // entropy_length excludes the marker that ends the scan; the two marker bytes are staged too so
@@ -483,6 +498,8 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
                                        : im.length - sc.entropy_offset;
     if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
     d.data_len = (uint32_t)pl.entropy_len;
+    d.use_selfsync = (d.dri == 0 && pl.entropy_len >= 1024) ? 1u : 0u;
+    d.sub_cap = d.use_selfsync ? (uint32_t)((pl.entropy_len * 8 + JB_SUBSEQ_BITS - 1) / JB_SUBSEQ_BITS) + 1 : 0;
     pl.total_blocks = (uint64_t)d.total_mcus * bpm;
 
     d.quant_off = (uint32_t)quant.size();
@@ -581,7 +598,15 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             staging += pl.out_bytes;
         } else
             pl.dev_out = pl.out.dst;
-        b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
+        if (pl.dev.use_selfsync) {
+            pl.dev.sub_base = (uint32_t)b->ss_total_sub;
+            b->ss_total_sub += pl.dev.sub_cap;
+            b->ss_max_sub = std::max(b->ss_max_sub, pl.dev.sub_cap);
+            b->ss_images.push_back((uint32_t)i);
+        } else {
+            b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
+            b->seg_images.push_back((uint32_t)i);
+        }
         if (pl.out.format != JB_OUT_COEFFICIENTS) {
             const int variant = k2_variant(pl.dev);
             jb_batch::RenderGroup *g = nullptr;
@@ -627,6 +652,18 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, ctx->stream));
     if (staging) JB_CUDA_B(cudaMallocAsync(&b->d_out_staging, staging, ctx->stream));
     std::vector<uint32_t> h_list;
+    b->seg_list_off = 0;
+    h_list.insert(h_list.end(), b->seg_images.begin(), b->seg_images.end());
+    b->ss_list_off = (uint32_t)h_list.size();
+    h_list.insert(h_list.end(), b->ss_images.begin(), b->ss_images.end());
+    if (!b->ss_images.empty()) {
+        JB_CUDA_B(cudaMallocAsync(&b->d_clean, b->arena_bytes, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_clean_len, sizeof(uint32_t) * count, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_exits, sizeof(JbSubState) * b->ss_total_sub, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_used, sizeof(JbSubState) * b->ss_total_sub, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_info, sizeof(JbSubInfo) * b->ss_total_sub, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_changed, sizeof(uint32_t) * 64, ctx->stream));
+    }
     for (auto &g : b->groups) {
         g.list_off = (uint32_t)h_list.size();
         h_list.insert(h_list.end(), g.images.begin(), g.images.end());
@@ -666,6 +703,8 @@ int jb_decode_batch_upload(jb_batch *b)
 
 static const char *kKernelNames[3] = {"jb_k0_restart_scan", "jb_k1_huff_segments", "jb_k2_idct_color"};
 
+static int launch_render(jb_batch *b, int *launches);
+
 static int launch_kernels(jb_batch *b)
 {
     jb_ctx *ctx = b->ctx;
@@ -684,32 +723,35 @@ static int launch_kernels(jb_batch *b)
     jb_k0_restart_scan<<<b->count, JB_K0_THREADS, 0, st>>>(b->d_images, b->d_arena, b->d_marks, b->d_scan);
     launches++;
     mark();
-    {
+    if (!b->seg_images.empty()) {
         // one warp per 32 segments; a CTA never spans images, so pick the CTA size that wastes the
         // fewest warp slots for this batch (at most JB_K1_MAX_WARPS warps)
         const uint32_t warps = std::min<uint32_t>(JB_K1_MAX_WARPS, (b->max_nseg + 31) / 32);
         const uint32_t threads = warps * 32;
-        dim3 grid((b->max_nseg + threads - 1) / threads, b->count);
+        dim3 grid((b->max_nseg + threads - 1) / threads, (unsigned)b->seg_images.size());
         size_t smem = warps * JB_K1_STAGE_BYTES;
-        jb_k1_huff_segments<<<grid, threads, smem, st>>>(b->d_images, b->d_tables, b->d_arena, b->d_marks,
-                                                         b->d_scan, b->d_coef, b->d_status);
+        jb_k1_huff_segments<<<grid, threads, smem, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_tables,
+                                                         b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status);
         launches++;
+    }
+    if (!b->ss_images.empty()) {
+        const uint32_t *list = b->d_image_list + b->ss_list_off;
+        const unsigned nimg = (unsigned)b->ss_images.size();
+        jb_k1b_unstuff<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_clean, b->d_clean_len);
+        JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t) * 64, st));
+        dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
+        jb_k1b_sync<true><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+                                                          b->d_exits, b->d_used, b->d_info, b->d_changed);
+        for (int r = 1; r <= JB_SS_ROUNDS; r++)
+            jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+                                                               b->d_exits, b->d_used, b->d_info, b->d_changed + r);
+        jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status);
+        jb_k1b_write<<<grid, JB_K1B_THREADS, (JB_K1B_THREADS / 32) * JB_K1_STAGE_BYTES, st>>>(
+            b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
+        launches += 4 + JB_SS_ROUNDS;
     }
     mark();
-    for (const auto &g : b->groups) {
-        const uint32_t *list = b->d_image_list + g.list_off;
-        if (g.variant >= 0) {
-            // a CTA walks `tpc` consecutive strips so that its per-thread constants are set up once
-            uint64_t total = (uint64_t)g.max_tiles * g.images.size();
-            int tpc = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16)));
-            dim3 grid((g.max_tiles + tpc - 1) / tpc, (unsigned)g.images.size());
-            launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc);
-        } else {
-            dim3 grid(g.max_tiles, (unsigned)g.images.size());
-            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list);
-        }
-        launches++;
-    }
+    launch_render(b, &launches);
     mark();
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
@@ -754,10 +796,74 @@ int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
             acc[k] += t;
         }
     for (int k = 0; k < 3; k++) {
-        snprintf(names[k], 48, "%s", kKernelNames[k]);
+        const char *nm = kKernelNames[k];
+        if (k == 1 && b->seg_images.empty()) nm = "jb_k1b_selfsync_chain";
+        else if (k == 1 && !b->ss_images.empty()) nm = "jb_k1_segments+selfsync";
+        snprintf(names[k], 48, "%s", nm);
         ms[k] = (float)(acc[k] / (double)nlaunch);
     }
     return 3;
+}
+
+static int launch_render(jb_batch *b, int *launches)
+{
+    cudaStream_t st = b->ctx->stream;
+    for (const auto &g : b->groups) {
+        const uint32_t *list = b->d_image_list + g.list_off;
+        if (g.variant >= 0) {
+            // a CTA walks `tpc` consecutive strips so that its per-thread constants are set up once
+            uint64_t total = (uint64_t)g.max_tiles * g.images.size();
+            int tpc = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16)));
+            dim3 grid((g.max_tiles + tpc - 1) / tpc, (unsigned)g.images.size());
+            launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc);
+        } else {
+            dim3 grid(g.max_tiles, (unsigned)g.images.size());
+            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list);
+        }
+        (*launches)++;
+    }
+    return JB_OK;
+}
+
+// slow path of the self-synchronising decoder: iterate rounds until one changes nothing, then redo
+// prefix sums, coefficient output and rendering
+static int resync_and_rerun(jb_batch *b)
+{
+    jb_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    const uint32_t *list = b->d_image_list + b->ss_list_off;
+    const unsigned nimg = (unsigned)b->ss_images.size();
+    dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
+    for (int iter = 0; iter < 100000; iter++) {
+        uint32_t changed = 0;
+        JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t), st));
+        jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+                                                           b->d_exits, b->d_used, b->d_info, b->d_changed);
+        JB_CUDA(ctx, cudaMemcpyAsync(&changed, b->d_changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        JB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (changed == 0) break;
+    }
+    // the prefix-sum kernel works in place on d_info: re-derive the per-sub-sequence counts first
+    // (a round over unchanged entries does not rewrite them), by one full round from the final states
+    JB_CUDA(ctx, cudaMemsetAsync(b->d_used, 0xFF, sizeof(JbSubState) * b->ss_total_sub, st));
+    jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+                                                       b->d_exits, b->d_used, b->d_info, b->d_changed);
+    jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status);
+    jb_k1b_write<<<grid, JB_K1B_THREADS, (JB_K1B_THREADS / 32) * JB_K1_STAGE_BYTES, st>>>(
+        b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
+    int dummy = 0;
+    launch_render(b, &dummy);
+    JB_CUDA(ctx, cudaGetLastError());
+    // results were possibly copied out before: copy again
+    for (int i = 0; i < b->count; i++) {
+        const ImagePlan &pl = b->plans[i];
+        if (pl.out.format == JB_OUT_COEFFICIENTS)
+            JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, b->d_coef + pl.dev.coef_off * 64, pl.out_bytes,
+                                         pl.out.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        else if (!pl.out.on_device)
+            JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, pl.dev_out, pl.out_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    return JB_OK;
 }
 
 int jb_decode_batch_finish(jb_batch *b)
@@ -774,6 +880,17 @@ int jb_decode_batch_finish(jb_batch *b)
                                          pl.out.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
         } else if (!pl.out.on_device) {
             JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    if (!b->ss_images.empty()) {
+        // the last synchronisation round must not have changed anything; otherwise (sub-sequences that
+        // need more than JB_SS_ROUNDS hops to synchronise: rare) keep iterating and redo the output
+        uint32_t last = 0;
+        JB_CUDA(ctx, cudaMemcpyAsync(&last, b->d_changed + JB_SS_ROUNDS, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (last != 0) {
+            int rc = resync_and_rerun(b);
+            if (rc) return rc;
         }
     }
     JB_CUDA(ctx, cudaMemcpyAsync(b->h_status.data(), b->d_status, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost,
@@ -843,6 +960,12 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_status) cudaFreeAsync(b->d_status, b->ctx->stream);
     if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
     if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
+    if (b->d_clean) cudaFreeAsync(b->d_clean, b->ctx->stream);
+    if (b->d_clean_len) cudaFreeAsync(b->d_clean_len, b->ctx->stream);
+    if (b->d_exits) cudaFreeAsync(b->d_exits, b->ctx->stream);
+    if (b->d_used) cudaFreeAsync(b->d_used, b->ctx->stream);
+    if (b->d_info) cudaFreeAsync(b->d_info, b->ctx->stream);
+    if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
     delete b;
 }
 

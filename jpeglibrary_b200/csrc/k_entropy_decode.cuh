@@ -279,7 +279,7 @@ __device__ __forceinline__ uint32_t jb_stage_off(int lane, int z)
 }
 
 __global__ void __launch_bounds__(JB_K1_MAX_WARPS * 32)
-jb_k1_huff_segments(const JbDevImage *__restrict__ images,
+jb_k1_huff_segments(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
                     const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
                     const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
                     int16_t *__restrict__ coef, uint32_t *__restrict__ status)
@@ -288,7 +288,7 @@ jb_k1_huff_segments(const JbDevImage *__restrict__ images,
     __shared__ JbDevImage s_im;
     __shared__ uint2 s_binfo[JB_MAX_BLOCKS_PER_MCU]; // per block-in-mcu: x = comp<<28 | dc table offset/16, y = ac table offset/16
     // grid = (CTAs per image, images): a CTA decodes blockDim.x consecutive segments of one image
-    const uint32_t image = blockIdx.y, first_seg = blockIdx.x * blockDim.x;
+    const uint32_t image = image_list[blockIdx.y], first_seg = blockIdx.x * blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (first_seg >= images[image].nseg) return;
     {

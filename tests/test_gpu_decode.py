@@ -104,6 +104,43 @@ def test_synthetic_streams(kw):
     assert diff.max() <= 1
 
 
+NO_RESTART_SHAPES = [
+    dict(width=1920, height=1080, subsampling="4:2:0", quality=85),   # ~800 sub-sequences, several CTAs
+    dict(width=1280, height=720, subsampling="4:4:4", quality=92),
+    dict(width=1000, height=700, subsampling="4:2:2", quality=75, optimize=True),
+    dict(width=900, height=600, gray=True, quality=90),
+    dict(width=512, height=512, subsampling="4:2:0", quality=30),     # long zero runs, EOB-heavy blocks
+    dict(width=700, height=500, subsampling="4:2:0", quality=100),    # quant tables of ones: long blocks
+]
+
+
+@pytest.mark.parametrize("kw", NO_RESTART_SHAPES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_self_synchronising_decode_without_restart_markers(kw):
+    """configs[2]: speculative sub-sequence decode + sync rounds + DC prefix must reproduce the
+    sequential decoder bit for bit."""
+    kw = dict(kw)
+    w, h = kw.pop("width"), kw.pop("height")
+    blob = synth.encode_jpeg(synth.synth_rgb(21, w, h), **kw)
+    assert J.Parsed(blob).desc.scans[0].restart_interval == 0
+    check_coefficients(blob)
+    o = O.decode(blob)
+    assert np.array_equal(gpu_planes(blob), o.planes)
+    assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
+
+
+def test_self_sync_equals_restart_decode_on_same_pixels():
+    """Size-independent property at the bench's full size: the same 4K pixels coded with and without
+    restart markers must give identical coefficients through the two different GPU entropy paths."""
+    rgb = synth.synth_rgb(1, 3840, 2160)
+    a = synth.encode_jpeg(rgb, restart_rows=1)
+    b = synth.encode_jpeg(rgb)
+    _, ca = J.decode_coefficients(a)
+    _, cb = J.decode_coefficients(b)
+    assert np.array_equal(ca, cb)
+    want = O.scan_order_coefficients(O.decode(b, want_rgb=False)).reshape(-1, 64)
+    assert np.array_equal(cb, want)
+
+
 def test_batch_of_mixed_images_device_resident():
     blobs = [synth.synth_jpeg(i, 320 + 16 * i, 240 - 8 * i, restart_rows=1, subsampling="4:2:0" if i % 2 else "4:4:4")
              for i in range(6)]
@@ -111,7 +148,9 @@ def test_batch_of_mixed_images_device_resident():
     with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
         b.run()
         assert b.status() == [0] * len(blobs)
-        assert b.launch_count() == 2 + 2  # restart scan + Huffman + one IDCT/colour launch per sampling layout (4:2:0, 4:4:4)
+        # restart scan + segment Huffman + self-sync chain for lake.jpg (unstuff, guess round, 5 sync
+        # rounds, prefix sums, write) + one IDCT/colour launch per sampling layout (4:2:0, 4:4:4)
+        assert b.launch_count() == 1 + 1 + (4 + 5) + 2
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run
