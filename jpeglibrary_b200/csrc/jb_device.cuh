@@ -57,6 +57,12 @@ struct JbDevImage {
     uint32_t sub_base;     // first sub-sequence slot of this image in the sub-sequence arrays
     uint32_t sub_cap;      // slots reserved
     uint32_t pad2;
+    // progressive frames: per-scan descriptors and a planar coefficient store
+    uint32_t scan_base, nscans;     // JbDevScan entries of this image
+    uint32_t planar;                // 1: per-component planes of MCU-padded block grids
+    uint32_t comp_plane_off[4];     // first block of each component plane (relative to coef_off)
+    uint32_t comp_plane_w[4];       // blocks per row of each plane
+    uint32_t pad3;
     // coefficient store
     uint64_t coef_off;   // first block of this image in the coefficient store (in blocks)
     uint32_t quant_off;  // first of ncomp quant tables (64 x uint16 each) in the quant array
@@ -67,7 +73,30 @@ struct JbDevImage {
     int32_t pad1;
 };
 
-// per-image result of K0 (restart scan)
+// byte range K0 indexes: one per sequential image, one per scan of a progressive image
+struct JbScanRange {
+    uint64_t data_off;
+    uint32_t data_len;
+    uint32_t mark_base, mark_cap;
+    uint32_t pad;
+};
+
+// one SOS of a progressive frame (JpegHuffmanProgressiveScanDecoder.ProcessScan, :57-90)
+struct JbDevScan {
+    uint64_t data_off;   // arena offset of the scan's entropy-coded bytes
+    uint32_t data_len;
+    uint32_t range;      // index into the K0 ranges / results
+    uint32_t mark_base;
+    uint32_t dri, nseg;
+    uint32_t nunits;     // MCUs (interleaved scan) or blocks (single-component scan)
+    uint32_t wb, hb;     // single-component scans: block grid of the component (:146-147)
+    uint8_t ncomp, ss, se, ah, al;
+    uint8_t comp[4];
+    uint8_t pad[3];
+    uint16_t dc_tab[4], ac_tab[4]; // device table indices, 0xFFFF = not defined
+};
+
+// per-range result of K0 (restart scan)
 struct JbScanResult {
     uint32_t nmarkers;   // entries written to the marker index (RSTn + at most one terminator)
     uint32_t end_pos;    // position of the terminator marker (or data_len)

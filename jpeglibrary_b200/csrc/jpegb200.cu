@@ -22,6 +22,7 @@
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
 #include "k_entropy_selfsync.cuh"
+#include "k_entropy_progressive.cuh"
 #include "k_idct_color.cuh"
 #include "k_idct_color_fast.cuh"
 
@@ -176,6 +177,8 @@ struct ImagePlan {
     jb_output_desc out{};
     void *dev_out = nullptr; // device address the kernels write (user's or staging)
     jb_coef_layout layout{};
+    std::vector<JbDevScan> scans;          // progressive frames
+    std::vector<uint64_t> scan_host_off;   // host offset of every scan's entropy bytes
 };
 
 } // namespace
@@ -252,6 +255,14 @@ struct jb_batch {
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
     uint32_t max_nseg = 1; // most restart segments any image has (sizes K1's CTAs)
+    // progressive frames
+    std::vector<uint32_t> prog_images;
+    uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1;
+    uint64_t prog_coef_first = 0, prog_coef_blocks = 0; // contiguous slice of the store, zeroed per launch
+    std::vector<JbDevScan> h_scans;
+    std::vector<JbScanRange> h_ranges;
+    JbDevScan *d_scans = nullptr;
+    JbScanRange *d_ranges = nullptr;
     // self-synchronising path (images without restart markers)
     std::vector<uint32_t> seg_images, ss_images; // K1a / K1b image lists
     uint32_t ss_list_off = 0, seg_list_off = 0;
@@ -381,6 +392,185 @@ int jb_memcpy_h2d(jb_ctx *ctx, void *dst, const void *src, size_t bytes)
     return JB_OK;
 }
 
+static int plan_output(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl)
+{
+    JbDevImage &d = pl.dev;
+    // output
+    if (outp) {
+        pl.out = *outp;
+        const int fmt = outp->format;
+        uint64_t pitch = outp->pitch, bytes = 0;
+        switch (fmt) {
+        case JB_OUT_RGB24:
+        case JB_OUT_YCBCR888:
+            if (!pitch) pitch = (uint64_t)im.width * 3;
+            if (pitch < (uint64_t)im.width * 3) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "pitch too small");
+            bytes = pitch * im.height;
+            break;
+        case JB_OUT_RGBA32:
+            if (!pitch) pitch = (uint64_t)im.width * 4;
+            if (pitch < (uint64_t)im.width * 4) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "pitch too small");
+            bytes = pitch * im.height;
+            break;
+        case JB_OUT_PLANAR_I16:
+            if (!pitch) pitch = (uint64_t)im.width * 2;
+            if (pitch < (uint64_t)im.width * 2 || (pitch & 1)) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "bad pitch");
+            bytes = pitch * im.height * im.component_count;
+            break;
+        case JB_OUT_COEFFICIENTS:
+            pitch = 0;
+            bytes = pl.total_blocks * 128;
+            break;
+        default:
+            return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "unknown output format");
+        }
+        if ((fmt == JB_OUT_RGB24 || fmt == JB_OUT_RGBA32 || fmt == JB_OUT_YCBCR888) && im.component_count != 1 &&
+            im.component_count != 3)
+            // apps/JpegDecode/DecodeAction.cs:30-34
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "This color space is not supported");
+        if (!outp->dst) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "null destination");
+        if (outp->capacity && outp->capacity < bytes)
+            return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "Destination buffer is too small.");
+        d.out_pitch = pitch;
+        d.out_format = fmt;
+        pl.out_bytes = bytes;
+    }
+    return JB_OK;
+}
+
+
+// table lookup/creation shared by both frame types: returns the device table index or -1
+static int intern_table(const jb_image_desc &im, int t, int want_class, std::vector<JbHuffTable> &tables,
+                        std::map<std::string, int> &table_ids)
+{
+    if (t < 0 || (uint32_t)t >= im.table_count || !im.tables) return -1;
+    const jb_huff_spec &hs = im.tables[t];
+    if (hs.table_class != want_class) return -1;
+    std::string key(reinterpret_cast<const char *>(&hs), sizeof hs);
+    auto g = table_ids.find(key);
+    if (g != table_ids.end()) return g->second;
+    JbHuffTable d;
+    if (!build_device_table(hs, d)) return -2;
+    int gid = (int)tables.size();
+    tables.push_back(d);
+    table_ids.emplace(std::move(key), gid);
+    return gid;
+}
+
+// SOF2: JpegHuffmanProgressiveScanDecoder ctor (:23-55) + per-scan set-up (:57-90, :140-147)
+static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl,
+                            std::vector<JbHuffTable> &tables, std::map<std::string, int> &table_ids,
+                            std::vector<uint16_t> &quant)
+{
+    JbDevImage &d = pl.dev;
+    if (im.precision < 2 || im.precision > 16) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
+    if (im.scan_count < 1 || !im.scans) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "no scans");
+    int hmax = 1, vmax = 1;
+    for (int c = 0; c < im.component_count; c++) {
+        if (im.h[c] < 1 || im.h[c] > 4 || im.v[c] < 1 || im.v[c] > 4)
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sampling factor");
+        hmax = std::max<int>(hmax, im.h[c]);
+        vmax = std::max<int>(vmax, im.v[c]);
+    }
+    for (int c = 0; c < im.component_count; c++) {
+        int hs = hmax / im.h[c], vs = vmax / im.v[c];
+        bool ok = (im.h[c] == 1 || im.h[c] == hmax) && (im.v[c] == 1 || im.v[c] == vmax) &&
+                  (hs == 1 || hs == 2 || hs == 4) && (vs == 1 || vs == 2 || vs == 4);
+        if (!ok)
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
+                        "sampling factors must be 1 or the maximum, ratio 1/2/4 (reference quirk Q2)");
+    }
+    d.width = im.width; d.height = im.height; d.ncomp = im.component_count; d.precision = im.precision; d.sof = 2;
+    d.hmax = (uint8_t)hmax; d.vmax = (uint8_t)vmax;
+    d.mcus_per_line = (im.width + 8 * hmax - 1) / (8 * hmax);
+    d.mcus_per_col = (im.height + 8 * vmax - 1) / (8 * vmax);
+    d.total_mcus = d.mcus_per_line * d.mcus_per_col;
+    d.planar = 1;
+    int bpm = 0;
+    uint64_t blocks = 0;
+    jb_coef_layout &L = pl.layout;
+    for (int c = 0; c < im.component_count; c++) {
+        d.comp_h[c] = im.h[c]; d.comp_v[c] = im.v[c];
+        d.comp_blk_off[c] = (uint8_t)bpm;
+        for (int k = 0; k < im.h[c] * im.v[c]; k++) {
+            if (bpm >= JB_MAX_BLOCKS_PER_MCU) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "MCU too large");
+            d.blk_comp[bpm++] = (uint8_t)c;
+        }
+        d.comp_plane_off[c] = (uint32_t)blocks;
+        d.comp_plane_w[c] = d.mcus_per_line * im.h[c];
+        L.comp_block_offset[c] = (int)blocks;
+        L.comp_blocks_w[c] = (int)(d.mcus_per_line * im.h[c]);
+        L.comp_blocks_h[c] = (int)(d.mcus_per_col * im.v[c]);
+        blocks += (uint64_t)d.mcus_per_line * im.h[c] * d.mcus_per_col * im.v[c];
+    }
+    d.bpm = (uint8_t)bpm;
+    pl.total_blocks = blocks;
+    L.interleaved = 0; L.mcus_per_line = (int)d.mcus_per_line; L.mcus_per_column = (int)d.mcus_per_col;
+    L.blocks_per_mcu = bpm; L.total_blocks = blocks;
+    d.dri = 0; d.nseg = 1; d.mark_cap = 0; d.use_selfsync = 0;
+
+    // the whole tail of the file from the first scan on is staged once; scans point into it
+    uint64_t lo = im.length, hi = 0;
+    for (uint32_t si = 0; si < im.scan_count; si++) {
+        const jb_scan_desc &sc = im.scans[si];
+        if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
+        uint64_t len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
+                                         : im.length - sc.entropy_offset;
+        lo = std::min(lo, sc.entropy_offset);
+        hi = std::max(hi, sc.entropy_offset + len);
+    }
+    pl.entropy_off = lo;
+    pl.entropy_len = hi - lo;
+    if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scans larger than 256 MiB");
+    d.data_len = (uint32_t)pl.entropy_len;
+    const int wblk = (im.width + 7) / 8, hblk = (im.height + 7) / 8;
+    for (uint32_t si = 0; si < im.scan_count; si++) {
+        const jb_scan_desc &sc = im.scans[si];
+        JbDevScan ds{};
+        ds.ncomp = sc.component_count;
+        ds.ss = sc.ss; ds.se = sc.se; ds.ah = sc.ah; ds.al = sc.al;
+        if (sc.component_count < 1 || sc.component_count > im.component_count || sc.se > 63 || sc.ss > sc.se || sc.al > 13)
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
+        if (sc.component_count > 1 && sc.ss != 0)
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "interleaved progressive scans carry DC only");
+        for (int i = 0; i < sc.component_count; i++) {
+            int c = sc.component_index[i];
+            if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+            ds.comp[i] = (uint8_t)c;
+            int dc = intern_table(im, sc.dc_table[i], 0, tables, table_ids);
+            int ac = intern_table(im, sc.ac_table[i], 1, tables, table_ids);
+            if (dc == -2 || ac == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
+            // :100-104, :149-152, :168-172: the table a scan actually uses must be defined
+            const bool need_dc = sc.ss == 0 && sc.ah == 0, need_ac = sc.ss != 0;
+            if ((need_dc && dc < 0) || (need_ac && ac < 0))
+                return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
+            ds.dc_tab[i] = dc < 0 ? 0xFFFF : (uint16_t)dc;
+            ds.ac_tab[i] = ac < 0 ? 0xFFFF : (uint16_t)ac;
+        }
+        if (sc.component_count == 1) {
+            const int c = sc.component_index[0];
+            const int hs = hmax / im.h[c], vs = vmax / im.v[c];
+            ds.wb = (uint32_t)((im.width + 8 * hs - 1) / (8 * hs));
+            ds.hb = (uint32_t)((im.height + 8 * vs - 1) / (8 * vs));
+            (void)wblk; (void)hblk;
+            ds.nunits = ds.wb * ds.hb;
+        } else
+            ds.nunits = d.total_mcus;
+        ds.dri = sc.restart_interval;
+        ds.nseg = ds.dri ? (ds.nunits + ds.dri - 1) / ds.dri : 1;
+        uint64_t len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
+                                         : im.length - sc.entropy_offset;
+        ds.data_len = (uint32_t)len;
+        pl.scan_host_off.push_back(sc.entropy_offset - lo);
+        pl.scans.push_back(ds);
+    }
+    d.nscans = (uint32_t)pl.scans.size();
+    d.quant_off = (uint32_t)quant.size();
+    for (int c = 0; c < im.component_count; c++)
+        for (int i = 0; i < 64; i++) quant.push_back(im.quant[c][i]);
+    return plan_output(ctx, idx, im, outp, pl);
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan one image: geometry, layout, validation
 // ------------------------------------------------------------------------------------------------
@@ -392,9 +582,10 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     if (im.component_count < 1 || im.component_count > JB_MAX_COMPONENTS)
         return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad component count");
     if (im.width == 0 || im.height == 0) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "empty frame");
-    if (im.sof > 1)
+    if (im.sof > 2)
         return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
-                    "only SOF0/SOF1 Huffman frames are handled by this build of the GPU path");
+                    "only SOF0/SOF1/SOF2 Huffman frames are handled by the GPU path");
+    if (im.sof == 2) return plan_progressive(ctx, idx, im, outp, pl, tables, table_ids, quant);
     if (im.precision < 2 || im.precision > 16)
         return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
     if (im.scan_count != 1 || !im.scans)
@@ -519,47 +710,7 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     }
     L.total_blocks = pl.total_blocks;
 
-    // output
-    if (outp) {
-        pl.out = *outp;
-        const int fmt = outp->format;
-        uint64_t pitch = outp->pitch, bytes = 0;
-        switch (fmt) {
-        case JB_OUT_RGB24:
-        case JB_OUT_YCBCR888:
-            if (!pitch) pitch = (uint64_t)im.width * 3;
-            if (pitch < (uint64_t)im.width * 3) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "pitch too small");
-            bytes = pitch * im.height;
-            break;
-        case JB_OUT_RGBA32:
-            if (!pitch) pitch = (uint64_t)im.width * 4;
-            if (pitch < (uint64_t)im.width * 4) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "pitch too small");
-            bytes = pitch * im.height;
-            break;
-        case JB_OUT_PLANAR_I16:
-            if (!pitch) pitch = (uint64_t)im.width * 2;
-            if (pitch < (uint64_t)im.width * 2 || (pitch & 1)) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "bad pitch");
-            bytes = pitch * im.height * im.component_count;
-            break;
-        case JB_OUT_COEFFICIENTS:
-            pitch = 0;
-            bytes = pl.total_blocks * 128;
-            break;
-        default:
-            return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "unknown output format");
-        }
-        if ((fmt == JB_OUT_RGB24 || fmt == JB_OUT_RGBA32 || fmt == JB_OUT_YCBCR888) && im.component_count != 1 &&
-            im.component_count != 3)
-            // apps/JpegDecode/DecodeAction.cs:30-34
-            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "This color space is not supported");
-        if (!outp->dst) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "null destination");
-        if (outp->capacity && outp->capacity < bytes)
-            return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "Destination buffer is too small.");
-        d.out_pitch = pitch;
-        d.out_format = fmt;
-        pl.out_bytes = bytes;
-    }
-    return JB_OK;
+    return plan_output(ctx, idx, im, outp, pl);
 }
 
 int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_output_desc *outputs, int count,
@@ -589,8 +740,10 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         arena += align_up(pl.entropy_len + 64, 256);
         pl.dev.mark_base = (uint32_t)marks;
         marks += pl.dev.mark_cap;
-        pl.dev.coef_off = blocks;
-        blocks += pl.total_blocks;
+        if (pl.dev.sof != 2) { // sequential frames first; progressive stores follow as one slice
+            pl.dev.coef_off = blocks;
+            blocks += pl.total_blocks;
+        }
         if (pl.out.format != JB_OUT_COEFFICIENTS) b->need_render = true;
         if (!pl.out.on_device) {
             staging = align_up(staging, 256);
@@ -598,7 +751,9 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             staging += pl.out_bytes;
         } else
             pl.dev_out = pl.out.dst;
-        if (pl.dev.use_selfsync) {
+        if (pl.dev.sof == 2) {
+            b->prog_images.push_back((uint32_t)i);
+        } else if (pl.dev.use_selfsync) {
             pl.dev.sub_base = (uint32_t)b->ss_total_sub;
             b->ss_total_sub += pl.dev.sub_cap;
             b->ss_max_sub = std::max(b->ss_max_sub, pl.dev.sub_cap);
@@ -627,6 +782,38 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             g->max_tiles = std::max(g->max_tiles, tiles);
         }
     }
+    // progressive frames: coefficient slice, per-scan K0 ranges and marker slots
+    b->h_ranges.resize(count);
+    for (int i = 0; i < count; i++) {
+        ImagePlan &pl = b->plans[i];
+        JbScanRange &r = b->h_ranges[i];
+        r = JbScanRange{};
+        if (pl.dev.sof != 2) {
+            r.data_off = pl.dev.data_off; r.data_len = pl.dev.data_len;
+            r.mark_base = pl.dev.mark_base; r.mark_cap = pl.dev.mark_cap;
+        }
+    }
+    b->prog_coef_first = blocks;
+    for (uint32_t i : b->prog_images) {
+        ImagePlan &pl = b->plans[i];
+        pl.dev.coef_off = blocks;
+        blocks += pl.total_blocks;
+        pl.dev.scan_base = (uint32_t)b->h_scans.size();
+        b->prog_max_scans = std::max<uint32_t>(b->prog_max_scans, (uint32_t)pl.scans.size());
+        for (size_t k = 0; k < pl.scans.size(); k++) {
+            JbDevScan ds = pl.scans[k];
+            ds.data_off = pl.dev.data_off + pl.scan_host_off[k];
+            ds.range = (uint32_t)b->h_ranges.size();
+            ds.mark_base = (uint32_t)marks;
+            JbScanRange r{};
+            r.data_off = ds.data_off; r.data_len = ds.data_len; r.mark_base = ds.mark_base; r.mark_cap = ds.nseg + 1;
+            marks += r.mark_cap;
+            b->h_ranges.push_back(r);
+            b->h_scans.push_back(ds);
+            b->prog_max_nseg = std::max(b->prog_max_nseg, ds.nseg);
+        }
+    }
+    b->prog_coef_blocks = blocks - b->prog_coef_first;
     b->arena_bytes = arena + 256;
     b->marks_count = marks;
     b->coef_blocks = blocks;
@@ -647,7 +834,12 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMallocAsync(&b->d_tables, sizeof(JbHuffTable) * b->tables.size(), ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1), ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_scan, sizeof(JbScanResult) * count, ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_scan, sizeof(JbScanResult) * b->h_ranges.size(), ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_ranges, sizeof(JbScanRange) * b->h_ranges.size(), ctx->stream));
+    JB_CUDA_B(cudaMallocAsync(&b->d_scans, sizeof(JbDevScan) * std::max<size_t>(b->h_scans.size(), 1), ctx->stream));
+    JB_CUDA_B(cudaMemcpyAsync(b->d_ranges, b->h_ranges.data(), sizeof(JbScanRange) * b->h_ranges.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!b->h_scans.empty())
+        JB_CUDA_B(cudaMemcpyAsync(b->d_scans, b->h_scans.data(), sizeof(JbDevScan) * b->h_scans.size(), cudaMemcpyHostToDevice, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_coef, blocks * 128, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, ctx->stream));
     if (staging) JB_CUDA_B(cudaMallocAsync(&b->d_out_staging, staging, ctx->stream));
@@ -656,6 +848,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     h_list.insert(h_list.end(), b->seg_images.begin(), b->seg_images.end());
     b->ss_list_off = (uint32_t)h_list.size();
     h_list.insert(h_list.end(), b->ss_images.begin(), b->ss_images.end());
+    b->prog_list_off = (uint32_t)h_list.size();
+    h_list.insert(h_list.end(), b->prog_images.begin(), b->prog_images.end());
     if (!b->ss_images.empty()) {
         JB_CUDA_B(cudaMallocAsync(&b->d_clean, b->arena_bytes, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_clean_len, sizeof(uint32_t) * count, ctx->stream));
@@ -720,7 +914,7 @@ static int launch_kernels(jb_batch *b)
     };
     JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
     mark();
-    jb_k0_restart_scan<<<b->count, JB_K0_THREADS, 0, st>>>(b->d_images, b->d_arena, b->d_marks, b->d_scan);
+    jb_k0_restart_scan<<<(unsigned)b->h_ranges.size(), JB_K0_THREADS, 0, st>>>(b->d_ranges, b->d_arena, b->d_marks, b->d_scan);
     launches++;
     mark();
     if (!b->seg_images.empty()) {
@@ -751,6 +945,18 @@ static int launch_kernels(jb_batch *b)
         launches += 4 + JB_SS_ROUNDS;
     }
     mark();
+    if (!b->prog_images.empty()) {
+        // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
+        JB_CUDA(ctx, cudaMemsetAsync(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
+        const int lanes = b->prog_max_nseg > 1 ? 32 : 1; // serial streams: one lane per warp
+        dim3 grid((b->prog_max_nseg + lanes - 1) / lanes, (unsigned)b->prog_images.size());
+        for (uint32_t sidx = 0; sidx < b->prog_max_scans; sidx++) {
+            jb_k1c_progressive_scan<<<grid, 32, 0, st>>>(b->d_images, b->d_image_list + b->prog_list_off, b->d_scans, (int)sidx,
+                                                         b->d_tables, b->d_arena, b->d_marks, b->d_scan, b->d_coef,
+                                                         b->d_status, lanes);
+            launches++;
+        }
+    }
     launch_render(b, &launches);
     mark();
     JB_CUDA(ctx, cudaGetLastError());
@@ -960,6 +1166,8 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_status) cudaFreeAsync(b->d_status, b->ctx->stream);
     if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
     if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
+    if (b->d_scans) cudaFreeAsync(b->d_scans, b->ctx->stream);
+    if (b->d_ranges) cudaFreeAsync(b->d_ranges, b->ctx->stream);
     if (b->d_clean) cudaFreeAsync(b->d_clean, b->ctx->stream);
     if (b->d_clean_len) cudaFreeAsync(b->d_clean_len, b->ctx->stream);
     if (b->d_exits) cudaFreeAsync(b->d_exits, b->ctx->stream);

@@ -27,7 +27,7 @@ __device__ __forceinline__ uint32_t jb_ff_bytes(uint32_t w)
 // callers re-check each flagged byte, so this is only used as a fast reject.
 
 template <typename F>
-__device__ __forceinline__ void jb_foreach_marker(const uint32_t w[5], uint32_t pos0, uint32_t len, F f)
+__device__ __forceinline__ void jb_foreach_marker(const uint32_t w[5], uint32_t pos0, uint32_t len, uint32_t skew, F f)
 {
     // w[0..3] = 16 bytes at pos0, w[4] low byte = look-ahead byte
     if ((jb_ff_bytes(w[0]) | jb_ff_bytes(w[1]) | jb_ff_bytes(w[2]) | jb_ff_bytes(w[3])) == 0) return;
@@ -35,17 +35,19 @@ __device__ __forceinline__ void jb_foreach_marker(const uint32_t w[5], uint32_t 
     for (int i = 0; i < 16; i++) {
         uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
         uint32_t nb = (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFF;
-        if (b == 0xFF && nb != 0 && nb != 0xFF && pos0 + i + 1 < len) f(pos0 + i, nb);
+        if (b == 0xFF && nb != 0 && nb != 0xFF && pos0 + i + 1 < len && pos0 + i >= skew) f(pos0 + i - skew, nb);
     }
 }
 
 __global__ void __launch_bounds__(JB_K0_THREADS)
-jb_k0_restart_scan(const JbDevImage *__restrict__ images, const uint8_t *__restrict__ arena,
+jb_k0_restart_scan(const JbScanRange *__restrict__ ranges, const uint8_t *__restrict__ arena,
                    uint32_t *__restrict__ marks, JbScanResult *__restrict__ results)
 {
-    const JbDevImage &im = images[blockIdx.x];
-    const uint8_t *data = arena + im.data_off;
-    const uint32_t len = im.data_len;
+    const JbScanRange &im = ranges[blockIdx.x];
+    // ranges of progressive scans start at arbitrary bytes: index from the enclosing 16-byte line
+    const uint32_t skew = (uint32_t)(im.data_off & 15u);
+    const uint8_t *data = arena + (im.data_off - skew);
+    const uint32_t len = im.data_len ? im.data_len + skew : 0;
     const uint32_t cap = im.mark_cap;
     uint32_t *out = marks + im.mark_base;
 
@@ -70,7 +72,7 @@ jb_k0_restart_scan(const JbDevImage *__restrict__ images, const uint8_t *__restr
             w[4] = __ldg(reinterpret_cast<const uint32_t *>(data + pos0 + 16));
         }
         uint32_t cnt = 0;
-        jb_foreach_marker(w, pos0, len, [&](uint32_t, uint32_t) { cnt++; });
+        jb_foreach_marker(w, pos0, len, skew, [&](uint32_t, uint32_t) { cnt++; });
         if (!__syncthreads_or(cnt != 0)) continue;
 
         // block-wide exclusive scan of cnt (rare path: only tiles that contain a marker)
@@ -90,7 +92,7 @@ jb_k0_restart_scan(const JbDevImage *__restrict__ images, const uint8_t *__restr
             total += t;
         }
         uint32_t idx = s_base + warp_off + incl - cnt;
-        jb_foreach_marker(w, pos0, len, [&](uint32_t pos, uint32_t m) {
+        jb_foreach_marker(w, pos0, len, skew, [&](uint32_t pos, uint32_t m) {
             const bool rst = (m & 0xF8u) == 0xD0u;
             if (idx < cap) out[idx] = (pos << 4) | (rst ? (m & 7u) : 8u);
             if (!rst) {
@@ -110,13 +112,13 @@ jb_k0_restart_scan(const JbDevImage *__restrict__ images, const uint8_t *__restr
     if (tid == 0) {
         JbScanResult r;
         uint32_t n = s_base;
-        r.end_pos = len;
+        r.end_pos = len - skew;
         r.end_marker = 0;
         if (s_term_idx != 0xFFFFFFFFu) {
             n = s_term_idx + 1;
             if (s_term_idx < cap) {
                 r.end_pos = out[s_term_idx] >> 4;
-                r.end_marker = data[r.end_pos + 1];
+                r.end_marker = data[r.end_pos + skew + 1];
             } else {
                 r.end_pos = s_term_pos;
             }

@@ -138,8 +138,16 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
     if (j < nblk) {
         const int m = j / bpm, b = j - m * bpm;
         const int c = s_im.blk_comp[b];
-        const uint64_t blk0 = s_im.coef_off + ((uint64_t)tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0) * bpm;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(coef + (blk0 + j) * 64) + r);
+        uint64_t blk;
+        if (!s_im.planar) {
+            blk = s_im.coef_off + ((uint64_t)tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0) * bpm + j;
+        } else { // progressive: per-component planes of MCU-padded block grids
+            const int bi0 = b - s_im.comp_blk_off[c], hc0 = s_im.comp_h[c];
+            blk = s_im.coef_off + s_im.comp_plane_off[c] +
+                  (uint64_t)(tw.mcu_row * s_im.comp_v[c] + bi0 / hc0) * s_im.comp_plane_w[c] +
+                  (tw.mcu_col0 + m) * hc0 + bi0 % hc0;
+        }
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(coef + blk * 64) + r);
         const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
         float *fb = s_f + j * JB_K2_BLOCK_STRIDE;
         const uint16_t *q = s_q + c * 64;

@@ -142,12 +142,19 @@ jb_k2_idct_color_fast(const JbDevImage *__restrict__ images, const int16_t *__re
     uint32_t mcu_row = tile / strips;
     uint32_t strip = tile - mcu_row * strips;
     const uint32_t tile_end = min(tile + (uint32_t)tiles_per_cta, ntiles);
+    // progressive frames keep their coefficients in per-component planes (bx, by are the block's
+    // position inside the strip's component plane, which starts at MCU column col0)
+    const bool planar = s_im.planar != 0;
+    const uint64_t plane_base = s_im.coef_off + s_im.comp_plane_off[c];
+    const uint32_t plane_w = s_im.comp_plane_w[c];
     auto load_raw = [&](uint32_t row, uint32_t st) -> uint4 {
         const uint32_t col0 = st * TILE_MCUS;
         const int nm = (int)min((uint32_t)TILE_MCUS, mcus_per_line - col0);
         if (m >= nm) return make_uint4(0, 0, 0, 0);
-        const uint64_t blk0 = s_im.coef_off + ((uint64_t)row * mcus_per_line + col0) * BPM;
-        return __ldg(reinterpret_cast<const uint4 *>(coef + (blk0 + j) * 64) + r);
+        uint64_t blk;
+        if (!planar) blk = s_im.coef_off + ((uint64_t)row * mcus_per_line + col0) * BPM + j;
+        else         blk = plane_base + (uint64_t)(row * (c == 0 ? VS : 1) + by) * plane_w + (col0 * (c == 0 ? HS : 1) + bx);
+        return __ldg(reinterpret_cast<const uint4 *>(coef + blk * 64) + r);
     };
     uint4 raw_next = make_uint4(0, 0, 0, 0);
     if (tile < tile_end) raw_next = load_raw(mcu_row, strip);

@@ -203,9 +203,77 @@ def test_error_codes_follow_reference_exceptions():
     dec.SetOutputWriter(J.CudaOutputWriter(np.zeros(100, np.uint8)))
     with pytest.raises(J.ArgumentException):
         dec.Decode()
-    # progressive frames are not on this build's GPU path yet: explicit error, no CPU fallback
+
+
+# ------------------------------------------------------------------------------------------ progressive
+def check_progressive_coefficients(blob):
+    o = O.decode(blob, want_rgb=False)
+    lay, coef = J.decode_coefficients(blob)
+    assert lay.interleaved == 0
+    for c in range(o.ncomp):
+        w, h = lay.comp_blocks_w[c], lay.comp_blocks_h[c]
+        assert (w, h) == (o.coef_w[c], o.coef_h[c])
+        plane = coef[lay.comp_block_offset[c]:lay.comp_block_offset[c] + w * h].reshape(h, w, 64)
+        aw, ah = o.alloc_w[c], o.alloc_h[c]  # blocks outside the reference allocator's grid hit its dummy block
+        assert np.array_equal(plane[:ah, :aw], o.coef[c][:ah, :aw]), f"component {c}"
+    return o
+
+
+@pytest.mark.parametrize("name", ["progress.jpg", "yellowcat_progressive_restart.jpg"])
+def test_progressive_golden_assets(name, golden):
+    blob = golden_bytes(name)
+    o = check_progressive_coefficients(blob)
+    planes = gpu_planes(blob)
+    assert hashlib.sha256(np.ascontiguousarray(planes).tobytes()).hexdigest() == golden["assets"][name]["planes_i16_sha256"]
+    assert np.array_equal(planes, o.planes)
+    o = O.decode(blob)
+    assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
+
+
+PROGRESSIVE_SHAPES = [
+    dict(width=1920, height=1080, subsampling="4:4:4", quality=85),          # configs[3] shape
+    dict(width=333, height=211, subsampling="4:2:0", quality=85),            # ragged, MCU padding blocks
+    dict(width=640, height=480, subsampling="4:2:0", quality=90, restart_blocks=7),
+    dict(width=200, height=120, subsampling="4:2:2", quality=75, restart_blocks=4),
+    dict(width=160, height=96, gray=True, quality=90),
+    dict(width=256, height=256, subsampling="4:4:4", quality=95, optimize=True),
+]
+
+
+@pytest.mark.parametrize("kw", PROGRESSIVE_SHAPES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_progressive_synthetic(kw):
+    kw = dict(kw)
+    w, h = kw.pop("width"), kw.pop("height")
+    blob = synth.encode_jpeg(synth.synth_rgb(9, w, h), progressive=True, **kw)
+    assert J.Parsed(blob).desc.sof == 2
+    check_progressive_coefficients(blob)
+    o = O.decode(blob)
+    assert np.array_equal(gpu_planes(blob), o.planes)
+    assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
+
+
+def test_progressive_complete_last_interval_quirk():
+    """Reference quirk: when a progressive scan ends exactly on a restart-interval boundary, HandleRestart
+    (JpegHuffmanProgressiveScanDecoder.cs:196-224) demands RSTn or EOI, but the next marker is DHT/SOS ->
+    InvalidOperationException("Expect restart marker.").  The GPU path reports the same error."""
+    blob = synth.synth_jpeg(9, 640, 480, progressive=True, restart_rows=2)
+    with pytest.raises(O.OracleError) as e:
+        O.decode(blob)
+    assert e.value.code == -2
     dec = J.JpegDecoder()
-    dec.SetInput(golden_bytes("progress.jpg"))
-    dec.SetOutputWriter(J.CudaOutputWriter(np.zeros((486, 341, 3), np.uint8)))
-    with pytest.raises(J.NotSupportedException):
+    dec.SetInput(blob)
+    dec.SetOutputWriter(J.CudaOutputWriter(np.zeros((480, 640, 3), np.uint8)))
+    with pytest.raises(J.InvalidOperationException):
         dec.Decode()
+
+
+def test_progressive_and_sequential_in_one_batch():
+    blobs = [synth.synth_jpeg(3, 320, 240, progressive=True, subsampling="4:4:4"),
+             synth.synth_jpeg(4, 320, 240, restart_rows=1),
+             golden_bytes("progress.jpg"),
+             synth.synth_jpeg(5, 640, 360)]
+    with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
+        b.run()
+        assert b.status() == [0] * len(blobs)
+        for i, blob in enumerate(blobs):
+            assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
