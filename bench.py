@@ -120,8 +120,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    blobs = make_blobs(min(args.distinct, 8), WIDTH, HEIGHT, quality=85, subsampling="4:2:0", restart_marker_rows=1) \
-        if False else make_blobs(min(args.distinct, 8), WIDTH, HEIGHT, quality=85, subsampling="4:2:0", restart_rows=1)
+    blobs = make_blobs(min(args.distinct, 8), WIDTH, HEIGHT, quality=85, subsampling="4:2:0", restart_rows=1)
     images = max(threads, min(2 * threads, 256))
     for _ in range(args.warmup):
         cpu_reference(blobs, threads, max(2, images // 4))
@@ -157,8 +156,13 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=64, help="images per step of the host-buffer (e2e) leg")
     ap.add_argument("--cpu-images", type=int, default=0, help="images of the cpu_baseline sample (0: auto)")
     ap.add_argument("--no-restart", action="store_true", help="configs[2]: same batch without restart markers")
+    ap.add_argument("--progressive", action="store_true", help="configs[3]: 1920x1080 4:4:4 progressive SOF2 batch")
     args = ap.parse_args()
 
+    global WIDTH, HEIGHT, MP_PER_IMAGE
+    if args.progressive:
+        WIDTH, HEIGHT = 1920, 1080
+        MP_PER_IMAGE = WIDTH * HEIGHT / 1e6
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,7 +190,9 @@ def main():
 
     # ---------------------------------------------------------------- inputs (synthetic, seeds 1000+i)
     kw = dict(quality=85, subsampling="4:2:0")
-    if not args.no_restart:
+    if args.progressive:
+        kw = dict(quality=85, subsampling="4:4:4", progressive=True)
+    elif not args.no_restart:
         kw["restart_rows"] = 1
     blobs = make_blobs(args.distinct, WIDTH, HEIGHT, **kw)
     # pinned host copies (the e2e leg copies from pinned memory; replicas share the host bytes)
@@ -273,10 +279,13 @@ def main():
 
     # ---------------------------------------------------------------- roofline of the dominant kernel
     peak, peak_src = measured_peak()
-    nblocks = (WIDTH // 8) * (HEIGHT // 8) * 3 // 2  # 194 400 for 4K 4:2:0
+    nblocks = (WIDTH // 8) * (HEIGHT // 8) * (3 if args.progressive else 3) // (1 if args.progressive else 2)  # 194 400 for 4K 4:2:0
     alg = {  # ALGORITHMIC bytes per launch, for the whole batch
         "jb_k0_restart_scan": comp_bytes,
         "jb_k1_huff_segments": comp_bytes + 128 * nblocks * args.batch,
+        "jb_k1b_selfsync_chain": comp_bytes + 128 * nblocks * args.batch,
+        "jb_k1_segments+selfsync": comp_bytes + 128 * nblocks * args.batch,
+        "jb_k1c_progressive_scans": comp_bytes + 128 * nblocks * args.batch,
         "jb_k2_idct_color": (128 * nblocks + 3 * WIDTH * HEIGHT) * args.batch,
     }
     dom = max(kernels, key=lambda kv: kv[1]) if kernels else ("none", float("nan"))
@@ -303,7 +312,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16/fp32",
             "data": "synthetic",
-            "config": {"workload": ("configs[2]: 3840x2160 4:2:0 SOF0 q85, no restart markers" if args.no_restart else
+            "config": {"workload": ("configs[3]: 1920x1080 4:4:4 progressive SOF2 q85 (10 scans)" if args.progressive else
+                                    "configs[2]: 3840x2160 4:2:0 SOF0 q85, no restart markers" if args.no_restart else
                                     "configs[1]: batch of synthetic 3840x2160 4:2:0 SOF0 JPEGs, q85, DRI=240 (one MCU row)"),
                        "images_per_gpu_per_step": args.batch, "distinct_images": args.distinct,
                        "compressed_bytes_per_step": comp_bytes, "output": "RGB24 device-resident",

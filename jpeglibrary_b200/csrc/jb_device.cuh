@@ -92,7 +92,8 @@ struct JbDevScan {
     uint32_t wb, hb;     // single-component scans: block grid of the component (:146-147)
     uint8_t ncomp, ss, se, ah, al;
     uint8_t comp[4];
-    uint8_t pad[3];
+    uint8_t level;       // dependency level: scans of one level touch disjoint (component, band) sets
+    uint8_t pad[2];
     uint16_t dc_tab[4], ac_tab[4]; // device table indices, 0xFFFF = not defined
 };
 

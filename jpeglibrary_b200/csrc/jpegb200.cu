@@ -257,7 +257,7 @@ struct jb_batch {
     uint32_t max_nseg = 1; // most restart segments any image has (sizes K1's CTAs)
     // progressive frames
     std::vector<uint32_t> prog_images;
-    uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1;
+    uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1, prog_levels = 0;
     uint64_t prog_coef_first = 0, prog_coef_blocks = 0; // contiguous slice of the store, zeroed per launch
     std::vector<JbDevScan> h_scans;
     std::vector<JbScanRange> h_ranges;
@@ -561,6 +561,16 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
         uint64_t len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
                                          : im.length - sc.entropy_offset;
         ds.data_len = (uint32_t)len;
+        // dependency level (JPEG scans commute unless they share a component and overlap in band)
+        int level = 0;
+        for (size_t e = 0; e < pl.scans.size(); e++) {
+            const JbDevScan &pe = pl.scans[e];
+            bool share = false;
+            for (int a = 0; a < ds.ncomp; a++)
+                for (int bq = 0; bq < pe.ncomp; bq++) share |= ds.comp[a] == pe.comp[bq];
+            if (share && !(ds.se < pe.ss || pe.se < ds.ss)) level = std::max<int>(level, pe.level + 1);
+        }
+        ds.level = (uint8_t)level;
         pl.scan_host_off.push_back(sc.entropy_offset - lo);
         pl.scans.push_back(ds);
     }
@@ -811,6 +821,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             b->h_ranges.push_back(r);
             b->h_scans.push_back(ds);
             b->prog_max_nseg = std::max(b->prog_max_nseg, ds.nseg);
+            b->prog_levels = std::max<uint32_t>(b->prog_levels, ds.level + 1u);
         }
     }
     b->prog_coef_blocks = blocks - b->prog_coef_first;
@@ -944,19 +955,19 @@ static int launch_kernels(jb_batch *b)
             b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
         launches += 4 + JB_SS_ROUNDS;
     }
-    mark();
     if (!b->prog_images.empty()) {
         // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
         JB_CUDA(ctx, cudaMemsetAsync(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
         const int lanes = b->prog_max_nseg > 1 ? 32 : 1; // serial streams: one lane per warp
-        dim3 grid((b->prog_max_nseg + lanes - 1) / lanes, (unsigned)b->prog_images.size());
-        for (uint32_t sidx = 0; sidx < b->prog_max_scans; sidx++) {
-            jb_k1c_progressive_scan<<<grid, 32, 0, st>>>(b->d_images, b->d_image_list + b->prog_list_off, b->d_scans, (int)sidx,
+        dim3 grid((b->prog_max_nseg + lanes - 1) / lanes, (unsigned)b->prog_images.size(), b->prog_max_scans);
+        for (uint32_t level = 0; level < b->prog_levels; level++) {
+            jb_k1c_progressive_scan<<<grid, 32, 0, st>>>(b->d_images, b->d_image_list + b->prog_list_off, b->d_scans, (int)level,
                                                          b->d_tables, b->d_arena, b->d_marks, b->d_scan, b->d_coef,
                                                          b->d_status, lanes);
             launches++;
         }
     }
+    mark();
     launch_render(b, &launches);
     mark();
     JB_CUDA(ctx, cudaGetLastError());
@@ -1003,7 +1014,8 @@ int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
         }
     for (int k = 0; k < 3; k++) {
         const char *nm = kKernelNames[k];
-        if (k == 1 && b->seg_images.empty()) nm = "jb_k1b_selfsync_chain";
+        if (k == 1 && b->seg_images.empty() && b->ss_images.empty()) nm = "jb_k1c_progressive_scans";
+        else if (k == 1 && b->seg_images.empty() && b->prog_images.empty()) nm = "jb_k1b_selfsync_chain";
         else if (k == 1 && !b->ss_images.empty()) nm = "jb_k1_segments+selfsync";
         snprintf(names[k], 48, "%s", nm);
         ms[k] = (float)(acc[k] / (double)nlaunch);

@@ -9,9 +9,11 @@
 // grid in HBM, zero-initialised per batch; blocks the reference routes to its shared dummy block
 // (out-of-range MCU padding, :108-111) simply land in the padding here and are never rendered.
 //
-// Parallelism: one thread per (image, restart segment) of scan number `scan_index`; scans of one
-// image are serialised by launching one kernel per scan index (a scan refines what earlier scans
-// wrote).  Refinement scans read coefficient history, so they cannot be decoded speculatively;
+// Parallelism: one thread per (image, scan, restart segment).  A scan only depends on earlier scans
+// that touch the same component with an overlapping spectral band (refinement of what they wrote), so
+// the host sorts scans into dependency levels and launches one kernel per level: libjpeg's 10-scan
+// script needs 4 launches ({DC}, {Y 1-5, Cr, Cb, Y 6-63}, {Y refine, DC refine, Cr refine, Cb refine},
+// {Y refine}).  Refinement scans read coefficient history, so they cannot be decoded speculatively;
 // streams without restart markers expose one thread per image and scan (batch-level parallelism only).
 // One lane per warp is used in that case so that every serial stream gets its own scheduler slot.
 #pragma once
@@ -26,15 +28,17 @@ __device__ __forceinline__ uint32_t jb_prog_bits(JbBitReader &br, int k)
 
 __global__ void __launch_bounds__(32)
 jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-                        const JbDevScan *__restrict__ scans, int scan_index, const JbHuffTable *__restrict__ tables,
+                        const JbDevScan *__restrict__ scans, int level, const JbHuffTable *__restrict__ tables,
                         const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
                         const JbScanResult *__restrict__ scanres, int16_t *__restrict__ coef,
                         uint32_t *__restrict__ status, int lanes_per_warp)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
-    if ((uint32_t)scan_index >= im.nscans) return;
+    const uint32_t scan_index = blockIdx.z; // every scan of the requested dependency level runs concurrently
+    if (scan_index >= im.nscans) return;
     const JbDevScan &sc = scans[im.scan_base + scan_index];
+    if (sc.level != level) return;
     const int lane = threadIdx.x;
     if (lane >= lanes_per_warp) return;
     const uint32_t seg = blockIdx.x * lanes_per_warp + lane;
