@@ -191,3 +191,70 @@ def decode_batch_rgb(blobs, threads, keep_output=False):
     ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
     lens = (C.c_size_t * n)(*[a.size for a in arrs])
     return lib().jo_decode_batch_rgb(ptrs, lens, n, threads, None)
+
+
+class EncodedResult:
+    pass
+
+
+def std_quant_table(chroma, quality):
+    out = np.empty(64, dtype=np.uint16)
+    lib().jo_std_quant_table(1 if chroma else 0, quality, out.ctypes.data)
+    return out
+
+
+def rgb_to_ycbcr(rgb):
+    a = np.ascontiguousarray(rgb, dtype=np.uint8)
+    out = np.empty_like(a)
+    lib().jo_rgb_to_ycbcr(a.ctypes.data, out.ctypes.data, a.size // 3)
+    return out
+
+
+def build_huffman_table(freq):
+    f = np.ascontiguousarray(freq, dtype=np.uint32)
+    bits = np.zeros(16, dtype=np.uint8)
+    vals = np.zeros(256, dtype=np.uint8)
+    n = lib().jo_build_huffman_table(f.ctypes.data, bits.ctypes.data, vals.ctypes.data)
+    return bits, vals[:n].copy()
+
+
+def encode_ycbcr(ycbcr, quality=75, subsampling=(2, 2), gray=False):
+    """apps/JpegEncode/EncodeAction.cs:37-63 with --optimize-coding: Annex-K tables scaled by quality,
+    Y h x v / Cb,Cr 1x1, four optimised Huffman tables."""
+    a = np.ascontiguousarray(ycbcr, dtype=np.uint8)
+    H, W = a.shape[:2]
+    p = EncodeParams()
+    p.width, p.height = W, H
+    p.ncomp = 1 if gray else 3
+    p.optimize = 1
+    for c in range(p.ncomp):
+        p.h[c], p.v[c] = (subsampling if c == 0 and not gray else (1, 1))
+        p.tq[c] = p.td[c] = p.ta[c] = 0 if c == 0 else 1
+    for t in range(2):
+        q = std_quant_table(t, quality)
+        for i in range(64):
+            p.qt[t][i] = int(q[i])
+        p.qt_present[t] = 1
+    e = Encoded()
+    rc = lib().jo_encode_ycbcr(a.ctypes.data, C.byref(p), C.byref(e))
+    try:
+        if rc:
+            raise OracleError(rc, e.error.decode())
+        r = EncodedResult()
+        r.bytes = bytes(np.ctypeslib.as_array(e.bytes, shape=(e.len,)))
+        r.scan_offset, r.scan_len = e.scan_offset, e.scan_len
+        r.coef = []
+        for c in range(p.ncomp):
+            n = e.alloc_w[c] * e.alloc_h[c] * 64
+            r.coef.append(np.ctypeslib.as_array(e.coef[c], shape=(n,)).copy().reshape(e.alloc_h[c], e.alloc_w[c], 64))
+        r.hist = np.array([[list(e.hist[cls][t]) for t in range(4)] for cls in range(2)], dtype=np.uint32)
+        r.dht = {}
+        for cls in range(2):
+            for t in range(4):
+                n = e.dht_nvals[cls][t]
+                if n:
+                    r.dht[(cls, t)] = (np.array(list(e.dht_bits[cls][t]), dtype=np.uint8),
+                                       np.array(list(e.dht_vals[cls][t])[:n], dtype=np.uint8))
+        return r
+    finally:
+        lib().jo_encoded_free(C.byref(e))
