@@ -175,6 +175,54 @@ JB_API int jb_decode(jb_ctx *ctx, const jb_image_desc *images, const jb_output_d
 JB_API int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const int16_t *coef_device,
                                        const jb_output_desc *output);
 
+/* ---- encode path: replaces JpegEncoder.TransformBlocks / BuildHuffmanTables / WritePreparedScanData
+   (JpegEncoder.cs:414-483, 491-597, 605-656) for a batch.  The host keeps writing SOI/DQT/SOF0/DHT/SOS/EOI
+   (JpegEncoder.Encode :255-290) around the scan bytes this path produces. ------------------------------- */
+#define JB_IN_RGB24 0     /* interleaved RGB; converted like apps/JpegEncode/JpegRgbToYCbCrConverter.cs:64-93 */
+#define JB_IN_YCBCR888 1  /* interleaved YCbCr as JpegBufferInputReader reads it (apps/JpegEncode/JpegBufferInputReader.cs) */
+#define JB_IN_GRAY8 2
+
+typedef struct jb_encode_desc {
+    const void *pixels;   /* host (pinned preferred) or device pointer */
+    uint64_t pitch;       /* bytes per row; 0 = tightly packed */
+    int32_t on_device;
+    int32_t format;       /* JB_IN_* */
+    uint16_t width, height;
+    uint8_t component_count;                 /* 1 or 3 */
+    uint8_t h[JB_MAX_COMPONENTS], v[JB_MAX_COMPONENTS];   /* AddComponent sampling factors (JpegEncoder.cs:175) */
+    uint8_t tq[JB_MAX_COMPONENTS], td[JB_MAX_COMPONENTS], ta[JB_MAX_COMPONENTS];
+    uint8_t reserved[3];
+    uint16_t quant[4][64];                   /* SetQuantizationTable, zig-zag order, by identifier */
+    uint8_t quant_present[4];
+} jb_encode_desc;
+
+typedef struct jb_encode_batch jb_encode_batch;
+
+JB_API int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count, jb_encode_batch **out);
+/* H2D of host pixels, then colour conversion + downsample + FDCT + quantisation (E1-E5) and the symbol
+   histograms (E6), all on the context stream. */
+JB_API int jb_encode_batch_transform(jb_encode_batch *b);
+/* Histograms for a host-side table builder (the reference's JpegHuffmanEncodingTableBuilder):
+   out[image][class*4 + id][256].  Synchronises. */
+JB_API int jb_encode_batch_histograms(jb_encode_batch *b, uint32_t *out, int count);
+/* Either build the optimised tables on the GPU (same algorithm, one thread per table) ... */
+JB_API int jb_encode_batch_build_tables(jb_encode_batch *b);
+/* ... or install tables built by the host (DHT form). */
+JB_API int jb_encode_batch_set_table(jb_encode_batch *b, int image, const jb_huff_spec *table);
+/* Bit lengths, prefix sum, parallel bit packing, byte stuffing (E8, E9). */
+JB_API int jb_encode_batch_pack(jb_encode_batch *b);
+/* Waits; returns the first per-image error. */
+JB_API int jb_encode_batch_finish(jb_encode_batch *b);
+JB_API int jb_encode_batch_get_table(jb_encode_batch *b, int image, int table_class, int identifier, jb_huff_spec *out);
+JB_API int jb_encode_batch_scan_length(jb_encode_batch *b, int image, uint64_t *length);
+JB_API int jb_encode_batch_read_scan(jb_encode_batch *b, int image, uint8_t *dst_host, uint64_t capacity);
+/* Quantised zig-zag coefficient blocks in MCU scan order (parity checks, JpegOptimizer-style reuse). */
+JB_API int jb_encode_batch_read_coefficients(jb_encode_batch *b, int image, int16_t *dst_host, uint64_t capacity_blocks);
+JB_API int jb_encode_batch_launch_count(jb_encode_batch *b);
+JB_API void jb_encode_batch_destroy(jb_encode_batch *b);
+/* The table builder on the host (JpegHuffmanEncodingTableBuilder.Build(optimal: false), :62-176). */
+JB_API int jb_build_huffman_table(const uint32_t frequencies[256], int table_class, int identifier, jb_huff_spec *out);
+
 JB_API const char *jb_version(void);
 
 #ifdef __cplusplus

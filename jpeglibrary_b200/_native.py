@@ -61,6 +61,19 @@ class CoefLayout(C.Structure):
                 ("total_blocks", C.c_uint64)]
 
 
+JB_IN_RGB24 = 0
+JB_IN_YCBCR888 = 1
+JB_IN_GRAY8 = 2
+
+
+class EncodeDesc(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("pitch", C.c_uint64), ("on_device", C.c_int32), ("format", C.c_int32),
+                ("width", C.c_uint16), ("height", C.c_uint16), ("component_count", C.c_uint8),
+                ("h", C.c_uint8 * 4), ("v", C.c_uint8 * 4), ("tq", C.c_uint8 * 4), ("td", C.c_uint8 * 4),
+                ("ta", C.c_uint8 * 4), ("reserved", C.c_uint8 * 3), ("quant", (C.c_uint16 * 64) * 4),
+                ("quant_present", C.c_uint8 * 4)]
+
+
 def _load(name):
     path = os.path.join(_LIBDIR, name)
     if not os.path.exists(path):
@@ -101,6 +114,20 @@ _sigs = {
         "jb_decode_batch_profile": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.c_int]),
         "jb_decode_batch_destroy": (None, [_vp]),
         "jb_decode": (C.c_int, [_vp, C.POINTER(ImageDesc), C.POINTER(OutputDesc), C.c_int, C.POINTER(C.c_int32)]),
+        "jb_encode_batch_create": (C.c_int, [_vp, C.POINTER(EncodeDesc), C.c_int, C.POINTER(_vp)]),
+        "jb_encode_batch_transform": (C.c_int, [_vp]),
+        "jb_encode_batch_histograms": (C.c_int, [_vp, _vp, C.c_int]),
+        "jb_encode_batch_build_tables": (C.c_int, [_vp]),
+        "jb_encode_batch_set_table": (C.c_int, [_vp, C.c_int, C.POINTER(HuffSpec)]),
+        "jb_encode_batch_pack": (C.c_int, [_vp]),
+        "jb_encode_batch_finish": (C.c_int, [_vp]),
+        "jb_encode_batch_get_table": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(HuffSpec)]),
+        "jb_encode_batch_scan_length": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint64)]),
+        "jb_encode_batch_read_scan": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
+        "jb_encode_batch_read_coefficients": (C.c_int, [_vp, C.c_int, _vp, C.c_uint64]),
+        "jb_encode_batch_launch_count": (C.c_int, [_vp]),
+        "jb_encode_batch_destroy": (None, [_vp]),
+        "jb_build_huffman_table": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(HuffSpec)]),
         "jb_render_from_coefficients": (C.c_int, [_vp, C.POINTER(ImageDesc), _vp, C.POINTER(OutputDesc)]),
     },
     host: {

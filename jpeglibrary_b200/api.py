@@ -448,3 +448,252 @@ def decode_coefficients(data, context=None):
     finally:
         N.cuda.jb_decode_batch_destroy(h)
     return lay, buf
+
+
+# ==========================================================================================
+# Encoder mirror (src/JpegLibrary/JpegEncoder.cs, JpegBlockInputReader.cs)
+# ==========================================================================================
+# JpegStandardQuantizationTable.cs:9-31 (zig-zag order)
+_STD_LUMA = [16, 11, 12, 14, 12, 10, 16, 14, 13, 14, 18, 17, 16, 19, 24, 40, 26, 24, 22, 22, 24, 49, 35, 37,
+             29, 40, 58, 51, 61, 60, 57, 51, 56, 55, 64, 72, 92, 78, 64, 68, 87, 69, 55, 56, 80, 109, 81, 87,
+             95, 98, 103, 104, 103, 62, 77, 113, 121, 112, 100, 120, 92, 101, 103, 99]
+_STD_CHROMA = [17, 18, 18, 24, 21, 24, 47, 26, 26, 47, 99, 66, 56, 66, 99, 99] + [99] * 48
+
+
+class JpegQuantizationTable:
+    """(ElementPrecision, Identifier, Elements in zig-zag order) -- JpegQuantizationTable.cs"""
+
+    def __init__(self, elementPrecision, identifier, elements):
+        self.ElementPrecision, self.Identifier, self.Elements = elementPrecision, identifier, list(elements)
+
+
+class JpegStandardQuantizationTable:
+    @staticmethod
+    def GetLuminanceTable(elementPrecision, identifier):
+        return JpegQuantizationTable(elementPrecision, identifier, _STD_LUMA)
+
+    @staticmethod
+    def GetChrominanceTable(elementPrecision, identifier):
+        return JpegQuantizationTable(elementPrecision, identifier, _STD_CHROMA)
+
+    @staticmethod
+    def ScaleByQuality(table, quality):  # JpegStandardQuantizationTable.cs:64-89
+        if not 0 <= quality <= 100:
+            raise ArgumentException("quality")
+        scale = 5000 // quality if quality < 50 else 200 - quality * 2
+        return JpegQuantizationTable(table.ElementPrecision, table.Identifier,
+                                     [min(max((x * scale + 50) // 100, 1), 255) for x in table.Elements])
+
+
+class JpegBlockInputReader:
+    """src/JpegLibrary/JpegBlockInputReader.cs:8-28"""
+    Width = 0
+    Height = 0
+
+    def ReadBlock(self, blockRef, componentIndex, x, y):
+        raise NotImplementedError
+
+
+class CudaInputReader(JpegBlockInputReader):
+    """Recognised GPU-aware source: interleaved pixels (RGB24 converted like apps/JpegEncode, YCbCr888 as
+    JpegBufferInputReader reads them, or grey) in a numpy array or device memory.  ReadBlock is never called."""
+
+    def __init__(self, pixels, width=None, height=None, format=N.JB_IN_RGB24, on_device=False, pitch=0):
+        self.pixels, self.format, self.on_device, self.pitch = pixels, format, on_device, pitch
+        if not on_device:
+            self.pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+            height, width = self.pixels.shape[:2]
+        self.Width, self.Height = width, height
+
+
+def _marker_segment(marker, payload):
+    return bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + payload
+
+
+class JpegEncoder:
+    """Mirror of JpegLibrary.JpegEncoder (baseline SOF0, optimised or caller-provided Huffman tables)."""
+
+    def __init__(self, context=None):
+        self._ctx = context
+        self._input = None
+        self._output = None
+        self._quant = []          # SetQuantizationTable order
+        self._tables = []         # (class, id, spec-or-None) in SetHuffmanTable order
+        self._components = []
+        self.MostOptimalCoding = False
+        self.use_host_table_builder = False  # True: histograms -> jb_build_huffman_table on the host
+
+    def SetInputReader(self, inputReader):   # :84
+        if inputReader is None:
+            raise ArgumentException("inputReader")
+        self._input = inputReader
+
+    def SetOutput(self, output):             # :93 (anything with .write / bytearray)
+        if output is None:
+            raise ArgumentException("output")
+        self._output = output
+
+    def SetQuantizationTable(self, table):   # :102-135
+        if table is None or not table.Elements:
+            raise ArgumentException("Quantization table is not initialized.")
+        self._quant = [t for t in self._quant if t.Identifier != table.Identifier] + [table]
+
+    def SetHuffmanTable(self, isDcTable, identifier, table=None):  # :137-147; None = build an optimised table
+        cls = 0 if isDcTable else 1
+        self._tables = [t for t in self._tables if (t[0], t[1]) != (cls, identifier)] + [(cls, identifier, table)]
+
+    def AddComponent(self, componentIndex, quantizationTableIdentifier, huffmanDcTableIdentifier,
+                     huffmanAcTableIdentifier, horizontalSubsampling, verticalSubsampling):  # :175-240
+        if horizontalSubsampling not in (1, 2, 4):
+            raise ArgumentException("Subsampling factor can only be 1, 2 or 4.")
+        if verticalSubsampling not in (1, 2, 4):
+            raise ArgumentException("Subsampling factor can only be 1, 2 or 4.")
+        if any(c[0] == componentIndex for c in self._components):
+            raise ArgumentException("The component index is already used by another component.")
+        if not any(t.Identifier == quantizationTableIdentifier for t in self._quant):
+            raise ArgumentException("Quantization table is not defined.")
+        if not any((t[0], t[1]) == (0, huffmanDcTableIdentifier) for t in self._tables):
+            raise ArgumentException("Huffman table is not defined.")
+        if not any((t[0], t[1]) == (1, huffmanAcTableIdentifier) for t in self._tables):
+            raise ArgumentException("Huffman table is not defined.")
+        self._components.append((componentIndex, quantizationTableIdentifier, huffmanDcTableIdentifier,
+                                 huffmanAcTableIdentifier, horizontalSubsampling, verticalSubsampling))
+
+    def _reader_pixels(self):
+        r = self._input
+        if isinstance(r, CudaInputReader):
+            return r
+        # compatibility path: replay ReadBlock over the full-resolution grid (the reference asks for exactly
+        # these blocks, JpegEncoder.cs:743-786) into an interleaved buffer
+        n = len(self._components)
+        W, H = r.Width, r.Height
+        buf = np.zeros(((H + 7) // 8 * 8, (W + 7) // 8 * 8, n), dtype=np.uint8)
+        blk = np.zeros(64, dtype=np.int16)
+        for ci in range(n):
+            for y in range(0, H, 8):
+                for x in range(0, W, 8):
+                    r.ReadBlock(blk, ci, x, y)
+                    buf[y:y + 8, x:x + 8, ci] = blk.reshape(8, 8).astype(np.uint8)
+        pix = np.ascontiguousarray(buf[:H, :W] if n == 3 else buf[:H, :W, 0])
+        return CudaInputReader(pix, format=N.JB_IN_YCBCR888 if n == 3 else N.JB_IN_GRAY8)
+
+    def _desc(self, reader):
+        d = N.EncodeDesc()
+        d.pixels = reader.pixels if reader.on_device else reader.pixels.ctypes.data
+        d.pitch = reader.pitch
+        d.on_device = 1 if reader.on_device else 0
+        d.format = reader.format
+        d.width, d.height = reader.Width, reader.Height
+        d.component_count = len(self._components)
+        for i, (_, tq, td, ta, h, v) in enumerate(self._components):
+            d.h[i], d.v[i], d.tq[i], d.td[i], d.ta[i] = h, v, tq, td, ta
+        for t in self._quant:
+            for k in range(64):
+                d.quant[t.Identifier][k] = t.Elements[k]
+            d.quant_present[t.Identifier] = 1
+        return d
+
+    # :255-290
+    def Encode(self):
+        if self._input is None:
+            raise InvalidOperationException("Input is not specified.")
+        if self._output is None:
+            raise InvalidOperationException("Output is not specified.")
+        if not self._components:
+            raise InvalidOperationException("No component is specified.")
+        if self.MostOptimalCoding:
+            raise NotSupportedException("package-merge table construction is not on the GPU path")
+        ctx = self._ctx or Context.default()
+        reader = self._reader_pixels()
+        desc = self._desc(reader)
+        h = C.c_void_p()
+        ctx.check(N.cuda.jb_encode_batch_create(ctx.handle, C.byref(desc), 1, C.byref(h)))
+        try:
+            ctx.check(N.cuda.jb_encode_batch_transform(h))
+            build = [t for t in self._tables if t[2] is None]
+            if build and not self.use_host_table_builder:
+                ctx.check(N.cuda.jb_encode_batch_build_tables(h))
+            elif build:
+                hist = np.zeros((8, 256), dtype=np.uint32)
+                ctx.check(N.cuda.jb_encode_batch_histograms(h, hist.ctypes.data, 1))
+                for cls, ident, _ in build:
+                    spec = N.HuffSpec()
+                    rc = N.cuda.jb_build_huffman_table(hist[cls * 4 + ident].ctypes.data, cls, ident, C.byref(spec))
+                    if rc:
+                        raise InvalidOperationException("No symbol is recorded.")
+                    ctx.check(N.cuda.jb_encode_batch_set_table(h, 0, C.byref(spec)))
+            for cls, ident, spec in self._tables:
+                if spec is not None:
+                    ctx.check(N.cuda.jb_encode_batch_set_table(h, 0, C.byref(spec)))
+            ctx.check(N.cuda.jb_encode_batch_pack(h))
+            ctx.check(N.cuda.jb_encode_batch_finish(h))
+            n = C.c_uint64()
+            N.cuda.jb_encode_batch_scan_length(h, 0, C.byref(n))
+            scan = np.empty(n.value, dtype=np.uint8)
+            ctx.check(N.cuda.jb_encode_batch_read_scan(h, 0, scan.ctypes.data, scan.size))
+            specs = []
+            for cls, ident, _ in self._tables:
+                s = N.HuffSpec()
+                ctx.check(N.cuda.jb_encode_batch_get_table(h, 0, cls, ident, C.byref(s)))
+                if s.value_count == 0:
+                    raise InvalidOperationException("No symbol is recorded.")
+                specs.append(s)
+            self.last_tables = specs
+            nblk = 0
+            W, H = reader.Width, reader.Height
+            hmax = max(c[4] for c in self._components)
+            vmax = max(c[5] for c in self._components)
+            nblk = ((W + 8 * hmax - 1) // (8 * hmax)) * ((H + 8 * vmax - 1) // (8 * vmax)) * sum(c[4] * c[5] for c in self._components)
+            coef = np.empty((nblk, 64), dtype=np.int16)
+            ctx.check(N.cuda.jb_encode_batch_read_coefficients(h, 0, coef.ctypes.data, nblk))
+            self.last_coefficients = coef
+        finally:
+            N.cuda.jb_encode_batch_destroy(h)
+        self._write(self.assemble(reader.Width, reader.Height, specs, scan.tobytes()))
+
+    def assemble(self, width, height, specs, scan):
+        """Stream layout of JpegEncoder.Encode (:255-290, :305-408): SOI, DQT (all tables, one segment),
+        SOF0, DHT (all tables, one segment, insertion order), SOS, entropy-coded data, EOI."""
+        out = bytearray(b"\xff\xd8")
+        dqt = bytearray()
+        for t in self._quant:
+            dqt += bytes([(t.ElementPrecision << 4) | (t.Identifier & 15)]) + bytes(t.Elements)
+        out += _marker_segment(0xDB, bytes(dqt))
+        sof = bytes([8]) + height.to_bytes(2, "big") + width.to_bytes(2, "big") + bytes([len(self._components)])
+        for ci, tq, _, _, h, v in self._components:
+            sof += bytes([ci, (h << 4) | v, tq])
+        out += _marker_segment(0xC0, sof)
+        dht = bytearray()
+        for s in specs:
+            dht += bytes([(s.table_class << 4) | (s.identifier & 15)]) + bytes(s.bits) + bytes(s.values[:s.value_count])
+        out += _marker_segment(0xC4, bytes(dht))
+        sos = bytes([len(self._components)])
+        for ci, _, td, ta, _, _ in self._components:
+            sos += bytes([ci, (td << 4) | ta])
+        out += _marker_segment(0xDA, sos + bytes([0, 63, 0]))
+        out += scan + b"\xff\xd9"
+        return bytes(out)
+
+    def _write(self, data):
+        if hasattr(self._output, "write"):
+            self._output.write(data)
+        else:
+            self._output += data
+
+
+def encode_rgb(rgb, quality=75, subsampling=(2, 2), context=None, host_builder=False):
+    """apps/JpegEncode/EncodeAction.cs:37-63 with --optimize-coding, on the GPU. Returns (bytes, encoder)."""
+    enc = JpegEncoder(context)
+    enc.use_host_table_builder = host_builder
+    enc.SetQuantizationTable(JpegStandardQuantizationTable.ScaleByQuality(JpegStandardQuantizationTable.GetLuminanceTable(0, 0), quality))
+    enc.SetQuantizationTable(JpegStandardQuantizationTable.ScaleByQuality(JpegStandardQuantizationTable.GetChrominanceTable(0, 1), quality))
+    for isdc, ident in ((True, 0), (False, 0), (True, 1), (False, 1)):
+        enc.SetHuffmanTable(isdc, ident)
+    enc.AddComponent(1, 0, 0, 0, subsampling[0], subsampling[1])
+    enc.AddComponent(2, 1, 1, 1, 1, 1)
+    enc.AddComponent(3, 1, 1, 1, 1, 1)
+    enc.SetInputReader(CudaInputReader(rgb, format=N.JB_IN_RGB24))
+    out = bytearray()
+    enc.SetOutput(out)
+    enc.Encode()
+    return bytes(out), enc

@@ -1238,3 +1238,354 @@ int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const i
 }
 
 } // extern "C"
+
+// =================================================================================================
+// Encode path
+// =================================================================================================
+#include "k_encode.cuh"
+
+struct jb_encode_batch {
+    jb_ctx *ctx = nullptr;
+    int count = 0;
+    std::vector<JbEncImage> images;
+    std::vector<jb_encode_desc> descs;
+    std::vector<uint16_t> quant;
+    struct Group { int nc, hs, vs; std::vector<uint32_t> list; uint32_t max_tiles = 0; uint32_t list_off = 0; };
+    std::vector<Group> groups;
+    std::vector<uint64_t> pix_bytes, pix_dev_off;
+    uint32_t max_blocks = 0;
+    // device
+    JbEncImage *d_images = nullptr;
+    uint16_t *d_quant = nullptr;
+    uint32_t *d_list = nullptr;
+    uint8_t *d_pixels = nullptr; // staging for host inputs
+    int16_t *d_coef = nullptr;
+    uint32_t *d_hist = nullptr;
+    JbEncTable *d_tables = nullptr;
+    JbHSym *d_scratch = nullptr;
+    uint32_t *d_bits = nullptr;
+    unsigned long long *d_totals = nullptr;
+    uint8_t *d_raw = nullptr, *d_out = nullptr;
+    uint32_t *d_out_len = nullptr, *d_status = nullptr;
+    uint64_t coef_blocks = 0, raw_bytes = 0, out_bytes = 0, pixel_bytes = 0;
+    std::vector<uint32_t> h_out_len, h_status;
+    std::vector<JbEncTable> h_tables;
+    bool tables_on_host_valid = false;
+    int launches = 0;
+};
+
+static void launch_k3(int nc, int hs, int vs, dim3 grid, cudaStream_t st, const JbEncImage *im, const uint32_t *list,
+                      const uint16_t *q, int16_t *coef)
+{
+    if (nc == 1) jb_k3_fdct_quant<1, 1, 1><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
+    else if (hs == 1 && vs == 1) jb_k3_fdct_quant<3, 1, 1><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
+    else if (hs == 2 && vs == 1) jb_k3_fdct_quant<3, 2, 1><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
+    else if (hs == 1 && vs == 2) jb_k3_fdct_quant<3, 1, 2><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
+    else jb_k3_fdct_quant<3, 2, 2><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
+}
+
+extern "C" {
+
+void jb_encode_batch_destroy(jb_encode_batch *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStream_t st = b->ctx->stream;
+    cudaStreamSynchronize(st);
+    void *ptrs[] = {b->d_images, b->d_quant, b->d_list, b->d_pixels, b->d_coef, b->d_hist, b->d_tables, b->d_scratch,
+                    b->d_bits, b->d_totals, b->d_raw, b->d_out, b->d_out_len, b->d_status};
+    for (void *p : ptrs)
+        if (p) cudaFreeAsync(p, st);
+    delete b;
+}
+
+int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count, jb_encode_batch **out)
+{
+    if (!ctx || !images || !out || count <= 0 || count > 65535) return JB_ERR_ARGUMENT;
+    *out = nullptr;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    jb_encode_batch *b = new (std::nothrow) jb_encode_batch;
+    if (!b) return JB_ERR_NOMEM;
+    b->ctx = ctx;
+    b->count = count;
+    b->images.resize(count);
+    b->descs.assign(images, images + count);
+    b->pix_bytes.resize(count);
+    b->pix_dev_off.resize(count);
+    uint64_t blocks = 0, raw = 0, outb = 0, pixels = 0;
+    for (int i = 0; i < count; i++) {
+        const jb_encode_desc &e = images[i];
+        JbEncImage &d = b->images[i];
+        d = JbEncImage{};
+        auto bad = [&](int code, const char *msg) { delete b; return fail(ctx, code, "image %d: %s", i, msg); };
+        if (!e.pixels || e.width == 0 || e.height == 0) return bad(JB_ERR_ARGUMENT, "no input pixels");
+        if (e.component_count != 1 && e.component_count != 3) return bad(JB_ERR_NOT_SUPPORTED, "1 or 3 components");
+        if ((e.component_count == 1) != (e.format == JB_IN_GRAY8)) return bad(JB_ERR_ARGUMENT, "pixel format does not match the component count");
+        for (int c = 0; c < e.component_count; c++) {
+            // AddComponent: factors must be 1, 2 or 4 (JpegEncoder.cs:177-184); tables must be defined (:199-203)
+            if ((e.h[c] != 1 && e.h[c] != 2 && e.h[c] != 4) || (e.v[c] != 1 && e.v[c] != 2 && e.v[c] != 4))
+                return bad(JB_ERR_ARGUMENT, "Subsampling factor can only be 1, 2 or 4.");
+            if (e.tq[c] > 3 || !e.quant_present[e.tq[c]]) return bad(JB_ERR_ARGUMENT, "Quantization table is not defined.");
+            if (e.td[c] > 3 || e.ta[c] > 3) return bad(JB_ERR_ARGUMENT, "Huffman table is not defined.");
+        }
+        int hs = e.h[0], vs = e.v[0];
+        if (hs > 2 || vs > 2) return bad(JB_ERR_NOT_SUPPORTED, "luma sampling factor 4 is not on the GPU path");
+        if (e.component_count == 3 && (e.h[1] != 1 || e.v[1] != 1 || e.h[2] != 1 || e.v[2] != 1))
+            return bad(JB_ERR_NOT_SUPPORTED, "chroma must be sampled 1x1");
+        if (e.component_count == 1 && (hs != 1 || vs != 1)) return bad(JB_ERR_NOT_SUPPORTED, "grey frames must be sampled 1x1");
+        // reference quirk Q4: MCU-padding blocks alias the allocator's dummy block and are encoded with
+        // stale data; only frames whose block grid needs no such padding are handled
+        const int wblk = (e.width + 7) / 8, hblk = (e.height + 7) / 8;
+        if (wblk % hs != 0 || hblk % vs != 0)
+            return bad(JB_ERR_NOT_SUPPORTED, "frame needs MCU padding blocks, which the reference encodes from a stale dummy block (quirk Q4)");
+        d.width = e.width; d.height = e.height; d.ncomp = e.component_count;
+        d.hs = (uint8_t)hs; d.vs = (uint8_t)vs; d.in_format = (uint8_t)e.format;
+        d.mcus_per_line = (e.width + 8 * hs - 1) / (8 * hs);
+        d.mcus_per_col = (e.height + 8 * vs - 1) / (8 * vs);
+        d.total_mcus = d.mcus_per_line * d.mcus_per_col;
+        int bpm = 0;
+        for (int c = 0; c < e.component_count; c++) {
+            d.comp_td[c] = e.td[c]; d.comp_ta[c] = e.ta[c];
+            for (int k = 0; k < e.h[c] * e.v[c]; k++) d.blk_comp[bpm++] = (uint8_t)c;
+        }
+        d.bpm = (uint8_t)bpm;
+        d.quant_off = (uint32_t)b->quant.size();
+        for (int c = 0; c < e.component_count; c++)
+            for (int k = 0; k < 64; k++) b->quant.push_back(e.quant[e.tq[c]][k]);
+        const uint64_t nblk = (uint64_t)d.total_mcus * bpm;
+        d.coef_off = blocks; d.bits_off = blocks;
+        blocks += nblk;
+        b->max_blocks = std::max<uint32_t>(b->max_blocks, (uint32_t)nblk);
+        d.raw_off = raw; d.raw_cap = align_up(nblk * 96 + 4096, 256); // 768 bits per block on average
+        raw += d.raw_cap;
+        d.out_off = outb; d.out_cap = align_up(d.raw_cap + d.raw_cap / 8 + 256, 256);
+        outb += d.out_cap;
+        d.table_base = (uint32_t)i * 8;
+        const int bpp = e.format == JB_IN_GRAY8 ? 1 : 3;
+        d.pix_pitch = e.pitch ? e.pitch : (uint64_t)e.width * bpp;
+        if (d.pix_pitch < (uint64_t)e.width * bpp) return bad(JB_ERR_ARGUMENT, "pitch too small");
+        b->pix_bytes[i] = d.pix_pitch * e.height;
+        if (!e.on_device) { b->pix_dev_off[i] = pixels; pixels += align_up(b->pix_bytes[i], 256); }
+        jb_encode_batch::Group *g = nullptr;
+        for (auto &x : b->groups) if (x.nc == e.component_count && x.hs == hs && x.vs == vs) g = &x;
+        if (!g) { b->groups.push_back({e.component_count, hs, vs, {}, 0, 0}); g = &b->groups.back(); }
+        g->list.push_back((uint32_t)i);
+        const uint32_t tile_mcus = JB_K3_BLOCKS / bpm;
+        g->max_tiles = std::max(g->max_tiles, (d.mcus_per_line + tile_mcus - 1) / tile_mcus * d.mcus_per_col);
+    }
+    b->coef_blocks = blocks; b->raw_bytes = raw; b->out_bytes = outb; b->pixel_bytes = pixels;
+    b->h_out_len.assign(count, 0);
+    b->h_status.assign(count, 0);
+    cudaStream_t st = ctx->stream;
+#define JB_CUDA_E(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            ctx->error = std::string(#call " failed: ") + cudaGetErrorString(e_);                \
+            jb_encode_batch_destroy(b);                                                          \
+            return e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA;                  \
+        }                                                                                        \
+    } while (0)
+    JB_CUDA_E(cudaMallocAsync(&b->d_images, sizeof(JbEncImage) * count, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_list, sizeof(uint32_t) * count, st));
+    if (pixels) JB_CUDA_E(cudaMallocAsync(&b->d_pixels, pixels, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_coef, blocks * 128, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_hist, sizeof(uint32_t) * 8 * 256 * count, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_tables, sizeof(JbEncTable) * 8 * count, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_scratch, sizeof(JbHSym) * 257 * 8 * count, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_bits, sizeof(uint32_t) * blocks, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_totals, sizeof(unsigned long long) * count, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_raw, raw, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_out, outb, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_out_len, sizeof(uint32_t) * count, st));
+    JB_CUDA_E(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, st));
+    for (int i = 0; i < count; i++)
+        b->images[i].pix_ptr = images[i].on_device ? reinterpret_cast<uint64_t>(images[i].pixels)
+                                                   : reinterpret_cast<uint64_t>(b->d_pixels + b->pix_dev_off[i]);
+    std::vector<uint32_t> list;
+    for (auto &g : b->groups) { g.list_off = (uint32_t)list.size(); list.insert(list.end(), g.list.begin(), g.list.end()); }
+    JB_CUDA_E(cudaMemcpyAsync(b->d_images, b->images.data(), sizeof(JbEncImage) * count, cudaMemcpyHostToDevice, st));
+    JB_CUDA_E(cudaMemcpyAsync(b->d_quant, b->quant.data(), sizeof(uint16_t) * b->quant.size(), cudaMemcpyHostToDevice, st));
+    JB_CUDA_E(cudaMemcpyAsync(b->d_list, list.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, st));
+    JB_CUDA_E(cudaMemsetAsync(b->d_tables, 0, sizeof(JbEncTable) * 8 * count, st));
+    JB_CUDA_E(cudaStreamSynchronize(st));
+#undef JB_CUDA_E
+    *out = b;
+    return JB_OK;
+}
+
+int jb_encode_batch_transform(jb_encode_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < b->count; i++)
+        if (!b->descs[i].on_device)
+            JB_CUDA(ctx, cudaMemcpyAsync(b->d_pixels + b->pix_dev_off[i], b->descs[i].pixels, b->pix_bytes[i], cudaMemcpyHostToDevice, st));
+    JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+    JB_CUDA(ctx, cudaMemsetAsync(b->d_hist, 0, sizeof(uint32_t) * 8 * 256 * b->count, st));
+    b->launches = 0;
+    for (const auto &g : b->groups) {
+        dim3 grid(g.max_tiles, (unsigned)g.list.size());
+        launch_k3(g.nc, g.hs, g.vs, grid, st, b->d_images, b->d_list + g.list_off, b->d_quant, b->d_coef);
+        b->launches++;
+    }
+    dim3 hgrid((b->max_blocks + 255) / 256, b->count);
+    jb_k3b_histogram<<<hgrid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_hist);
+    b->launches++;
+    JB_CUDA(ctx, cudaGetLastError());
+    return JB_OK;
+}
+
+int jb_encode_batch_histograms(jb_encode_batch *b, uint32_t *out, int count)
+{
+    if (!b || !out || count < 0 || count > b->count) return JB_ERR_ARGUMENT;
+    JB_CUDA(b->ctx, cudaMemcpyAsync(out, b->d_hist, sizeof(uint32_t) * 8 * 256 * count, cudaMemcpyDeviceToHost, b->ctx->stream));
+    JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    return JB_OK;
+}
+
+int jb_encode_batch_build_tables(jb_encode_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    const int n = 8 * b->count;
+    jb_k3c_build_tables<<<(n + 31) / 32, 32, 0, b->ctx->stream>>>(b->d_hist, b->d_tables, b->d_scratch, n);
+    b->launches++;
+    b->tables_on_host_valid = false;
+    JB_CUDA(b->ctx, cudaGetLastError());
+    return JB_OK;
+}
+
+static bool spec_to_enc_table(const jb_huff_spec &s, JbEncTable &t)
+{
+    memset(&t, 0, sizeof t);
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; l++) {
+        t.bits[l - 1] = s.bits[l - 1];
+        for (int i = 0; i < s.bits[l - 1]; i++, k++) {
+            if (k >= s.value_count) return false;
+            t.vals[k] = s.values[k];
+            t.code[s.values[k]] = (uint16_t)code;
+            t.len[s.values[k]] = (uint8_t)l;
+            code++;
+        }
+        code <<= 1;
+    }
+    t.nvals = (uint32_t)k;
+    return k == s.value_count;
+}
+
+int jb_encode_batch_set_table(jb_encode_batch *b, int image, const jb_huff_spec *table)
+{
+    if (!b || !table || image < 0 || image >= b->count || table->table_class > 1 || table->identifier > 3) return JB_ERR_ARGUMENT;
+    JbEncTable t;
+    if (!spec_to_enc_table(*table, t)) return fail(b->ctx, JB_ERR_ARGUMENT, "image %d: %s", image, "malformed Huffman table");
+    JB_CUDA(b->ctx, cudaMemcpyAsync(b->d_tables + image * 8 + table->table_class * 4 + table->identifier, &t, sizeof t,
+                                    cudaMemcpyHostToDevice, b->ctx->stream));
+    JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream)); // `t` lives on this stack frame
+    b->tables_on_host_valid = false;
+    return JB_OK;
+}
+
+int jb_encode_batch_pack(jb_encode_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaMemsetAsync(b->d_raw, 0, b->raw_bytes, st));
+    dim3 grid((b->max_blocks + 255) / 256, b->count);
+    jb_k4a_block_bits<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits);
+    jb_k4b_scan<<<b->count, 1024, 0, st>>>(b->d_images, b->d_bits, b->d_totals);
+    jb_k4c_pack<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits, b->d_totals, b->d_raw, b->d_status);
+    jb_k4d_stuff<<<b->count, 256, 0, st>>>(b->d_images, b->d_totals, b->d_raw, b->d_out, b->d_out_len, b->d_status);
+    b->launches += 4;
+    JB_CUDA(ctx, cudaGetLastError());
+    return JB_OK;
+}
+
+int jb_encode_batch_finish(jb_encode_batch *b)
+{
+    if (!b) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    JB_CUDA(ctx, cudaMemcpyAsync(b->h_out_len.data(), b->d_out_len, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(ctx, cudaMemcpyAsync(b->h_status.data(), b->d_status, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost, st));
+    b->h_tables.resize((size_t)8 * b->count);
+    JB_CUDA(ctx, cudaMemcpyAsync(b->h_tables.data(), b->d_tables, sizeof(JbEncTable) * 8 * b->count, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(ctx, cudaStreamSynchronize(st));
+    b->tables_on_host_valid = true;
+    for (int i = 0; i < b->count; i++)
+        if (b->h_status[i]) return fail(ctx, JB_ERR_NOMEM, "image %d: %s", i, "entropy-coded data exceeds the reserved space");
+    // a symbol that occurs but has no code (host-provided table that does not cover the data)
+    return JB_OK;
+}
+
+int jb_encode_batch_get_table(jb_encode_batch *b, int image, int table_class, int identifier, jb_huff_spec *out)
+{
+    if (!b || !out || image < 0 || image >= b->count || table_class < 0 || table_class > 1 || identifier < 0 || identifier > 3)
+        return JB_ERR_ARGUMENT;
+    if (!b->tables_on_host_valid) {
+        b->h_tables.resize((size_t)8 * b->count);
+        JB_CUDA(b->ctx, cudaMemcpyAsync(b->h_tables.data(), b->d_tables, sizeof(JbEncTable) * 8 * b->count, cudaMemcpyDeviceToHost, b->ctx->stream));
+        JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+        b->tables_on_host_valid = true;
+    }
+    const JbEncTable &t = b->h_tables[(size_t)image * 8 + table_class * 4 + identifier];
+    memset(out, 0, sizeof *out);
+    out->table_class = (uint8_t)table_class;
+    out->identifier = (uint8_t)identifier;
+    memcpy(out->bits, t.bits, 16);
+    memcpy(out->values, t.vals, 256);
+    out->value_count = (uint16_t)t.nvals;
+    return JB_OK;
+}
+
+int jb_encode_batch_scan_length(jb_encode_batch *b, int image, uint64_t *length)
+{
+    if (!b || !length || image < 0 || image >= b->count) return JB_ERR_ARGUMENT;
+    *length = b->h_out_len[image];
+    return JB_OK;
+}
+
+int jb_encode_batch_read_scan(jb_encode_batch *b, int image, uint8_t *dst, uint64_t capacity)
+{
+    if (!b || !dst || image < 0 || image >= b->count) return JB_ERR_ARGUMENT;
+    const uint64_t n = b->h_out_len[image];
+    if (capacity < n) return fail(b->ctx, JB_ERR_ARGUMENT, "image %d: %s", image, "Destination buffer is too small.");
+    JB_CUDA(b->ctx, cudaMemcpyAsync(dst, b->d_out + b->images[image].out_off, n, cudaMemcpyDeviceToHost, b->ctx->stream));
+    JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    return JB_OK;
+}
+
+int jb_encode_batch_read_coefficients(jb_encode_batch *b, int image, int16_t *dst, uint64_t capacity_blocks)
+{
+    if (!b || !dst || image < 0 || image >= b->count) return JB_ERR_ARGUMENT;
+    const uint64_t n = (uint64_t)b->images[image].total_mcus * b->images[image].bpm;
+    if (capacity_blocks < n) return JB_ERR_ARGUMENT;
+    JB_CUDA(b->ctx, cudaMemcpyAsync(dst, b->d_coef + b->images[image].coef_off * 64, n * 128, cudaMemcpyDeviceToHost, b->ctx->stream));
+    JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
+    return JB_OK;
+}
+
+int jb_encode_batch_launch_count(jb_encode_batch *b) { return b ? b->launches : 0; }
+
+int jb_build_huffman_table(const uint32_t frequencies[256], int table_class, int identifier, jb_huff_spec *out)
+{
+    if (!frequencies || !out) return JB_ERR_ARGUMENT;
+    JbEncTable t;
+    std::vector<JbHSym> scratch(257);
+    const int n = jb_build_encoder_table(frequencies, &t, scratch.data());
+    if (n == 0) return JB_ERR_INVALID_OPERATION; // "No symbol is recorded." (JpegHuffmanEncodingTableBuilder.cs:83-86)
+    memset(out, 0, sizeof *out);
+    out->table_class = (uint8_t)table_class;
+    out->identifier = (uint8_t)identifier;
+    memcpy(out->bits, t.bits, 16);
+    memcpy(out->values, t.vals, 256);
+    out->value_count = (uint16_t)n;
+    return JB_OK;
+}
+
+} // extern "C"
