@@ -697,3 +697,85 @@ def encode_rgb(rgb, quality=75, subsampling=(2, 2), context=None, host_builder=F
     enc.SetOutput(out)
     enc.Encode()
     return bytes(out), enc
+
+
+class JpegBatchEncoder:
+    """Batch facade for the encoder path: N frames -> N baseline JPEG streams with optimised tables
+    (apps/JpegEncode semantics).  Frames are numpy arrays (host) or (device_ptr, width, height) tuples."""
+
+    def __init__(self, frames, quality=75, subsampling=(2, 2), context=None, format=N.JB_IN_RGB24):
+        self.ctx = context or Context.default()
+        n = len(frames)
+        self.count = n
+        self.enc = JpegEncoder(self.ctx)
+        e = self.enc
+        e.SetQuantizationTable(JpegStandardQuantizationTable.ScaleByQuality(JpegStandardQuantizationTable.GetLuminanceTable(0, 0), quality))
+        e.SetQuantizationTable(JpegStandardQuantizationTable.ScaleByQuality(JpegStandardQuantizationTable.GetChrominanceTable(0, 1), quality))
+        for isdc, ident in ((True, 0), (False, 0), (True, 1), (False, 1)):
+            e.SetHuffmanTable(isdc, ident)
+        e.AddComponent(1, 0, 0, 0, subsampling[0], subsampling[1])
+        e.AddComponent(2, 1, 1, 1, 1, 1)
+        e.AddComponent(3, 1, 1, 1, 1, 1)
+        self.descs = (N.EncodeDesc * n)()
+        self._keep = []
+        self.sizes = []
+        for i, f in enumerate(frames):
+            if isinstance(f, tuple):
+                r = CudaInputReader(f[0], width=f[1], height=f[2], format=format, on_device=True)
+            else:
+                r = CudaInputReader(f, format=format)
+                self._keep.append(r)
+            self.descs[i] = e._desc(r)
+            self.sizes.append((r.Width, r.Height))
+        h = C.c_void_p()
+        self.ctx.check(N.cuda.jb_encode_batch_create(self.ctx.handle, self.descs, n, C.byref(h)))
+        self.handle = h
+
+    def launch(self):
+        """transform + on-device table build + pack, all asynchronous on the context stream"""
+        self.ctx.check(N.cuda.jb_encode_batch_transform(self.handle))
+        self.ctx.check(N.cuda.jb_encode_batch_build_tables(self.handle))
+        self.ctx.check(N.cuda.jb_encode_batch_pack(self.handle))
+
+    def finish(self):
+        self.ctx.check(N.cuda.jb_encode_batch_finish(self.handle))
+
+    def launch_count(self):
+        return N.cuda.jb_encode_batch_launch_count(self.handle)
+
+    def scan_length(self, i):
+        n = C.c_uint64()
+        N.cuda.jb_encode_batch_scan_length(self.handle, i, C.byref(n))
+        return n.value
+
+    def stream(self, i):
+        """Complete JPEG stream of frame i (headers written on the host like JpegEncoder.Encode)."""
+        scan = np.empty(self.scan_length(i), dtype=np.uint8)
+        self.ctx.check(N.cuda.jb_encode_batch_read_scan(self.handle, i, scan.ctypes.data, scan.size))
+        specs = []
+        for cls, ident, _ in self.enc._tables:
+            s = N.HuffSpec()
+            self.ctx.check(N.cuda.jb_encode_batch_get_table(self.handle, i, cls, ident, C.byref(s)))
+            specs.append(s)
+        return self.enc.assemble(self.sizes[i][0], self.sizes[i][1], specs, scan.tobytes())
+
+    def read_all_scans(self, out: np.ndarray):
+        """D2H of every frame's scan bytes into `out` (pinned), returns the byte offsets."""
+        offs, pos = [], 0
+        for i in range(self.count):
+            n = self.scan_length(i)
+            self.ctx.check(N.cuda.jb_encode_batch_read_scan(self.handle, i, out.ctypes.data + pos, out.size - pos))
+            offs.append((pos, n))
+            pos += n
+        return offs
+
+    def close(self):
+        if getattr(self, "handle", None):
+            N.cuda.jb_encode_batch_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
