@@ -358,10 +358,8 @@ def main():
     dec.set_profiling(False)
     launches = dec.launch_count() * args.steps
 
-    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    from jpeglibrary_b200.sharding import max_over_ranks
+    ms_max = max_over_ranks(ms, device=f"cuda:{local_rank}")  # whole-job time = slowest rank's device time
     total_images = args.batch * world * args.steps
     value = total_images * MP_PER_IMAGE / (ms_max / 1e3)
 
