@@ -172,7 +172,7 @@ def run_encode(args, rank, local_rank, world):
     for i in range(batch):
         ctx.h2d(dev + i * fbytes, pinned[i % len(pinned)])
     enc = J.JpegBatchEncoder([(dev + i * fbytes, WIDTH, HEIGHT) for i in range(batch)], quality=75, context=ctx)
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 1)):
         enc.launch()
     enc.finish()
     # correctness gate: frame 0's stream equals the oracle's byte for byte
@@ -324,7 +324,9 @@ def main():
                              parse_threads=min(32, os.cpu_count() or 1))
     dec.upload()
     ctx.synchronize()
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # sampled from the warm-up on: the timed region itself lasts only a few hundred ms
+    for _ in range(max(args.warmup, 1)):
         dec.launch()
     ctx.synchronize()
     # correctness gate on the bench inputs themselves: first image vs the oracle
@@ -339,10 +341,8 @@ def main():
     dec.finish()
     assert dec.status() == [0] * args.batch
 
-    sampler = ClockSampler(local_rank)
     barrier()
     torch.cuda.synchronize()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dec.set_profiling(True)
     ev0.record(stream)
