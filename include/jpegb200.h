@@ -181,6 +181,9 @@ JB_API int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, 
 #define JB_IN_RGB24 0     /* interleaved RGB; converted like apps/JpegEncode/JpegRgbToYCbCrConverter.cs:64-93 */
 #define JB_IN_YCBCR888 1  /* interleaved YCbCr as JpegBufferInputReader reads it (apps/JpegEncode/JpegBufferInputReader.cs) */
 #define JB_IN_GRAY8 2
+#define JB_IN_COEFFICIENTS 3 /* `pixels` is a DEVICE pointer to quantised zig-zag blocks in MCU scan order (the layout
+                                JB_OUT_COEFFICIENTS produces): transcoding, JpegOptimizer.Scan/Optimize
+                                (JpegOptimizer.cs:72-154, 546-879) without any DCT */
 
 typedef struct jb_encode_desc {
     const void *pixels;   /* host (pinned preferred) or device pointer */

@@ -64,6 +64,7 @@ class CoefLayout(C.Structure):
 JB_IN_RGB24 = 0
 JB_IN_YCBCR888 = 1
 JB_IN_GRAY8 = 2
+JB_IN_COEFFICIENTS = 3
 
 
 class EncodeDesc(C.Structure):

@@ -779,3 +779,173 @@ class JpegBatchEncoder:
 
     def __exit__(self, *a):
         self.close()
+
+
+# ==========================================================================================
+# Optimizer mirror (src/JpegLibrary/JpegOptimizer.cs): lossless transcode with optimised Huffman tables
+# ==========================================================================================
+class JpegOptimizer:
+    """Scan(): entropy-decode on the GPU (K0/K1), histogram the symbols (K3b), build optimised tables (K3c).
+    Optimize(strip): re-pack the same coefficients with the new tables (K4) and rewrite the stream like
+    JpegOptimizer.Optimize (:546-647): SOI/APP0/SOF copied, the first DHT/DQT replaced by all tables, SOS
+    copied with the new scan data, other segments dropped when `strip`.  No DCT is involved.
+    Restart intervals are refused (the reference itself drops DRI with strip=True while keeping RSTn: quirk Q6)."""
+
+    def __init__(self, context=None):
+        self._ctx = context
+        self._input = None
+        self._output = None
+        self._parsed = None
+        self._batch = None
+        self._coef_dev = None
+        self.MostOptimalCoding = False
+
+    def SetInput(self, data):      # :54-70
+        self._input = data
+        self._close()
+
+    def SetOutput(self, output):   # :537
+        if output is None:
+            raise ArgumentException("output")
+        self._output = output
+
+    def _close(self):
+        ctx = self._ctx or (Context._default.get(0) if Context._default else None)
+        if self._batch is not None:
+            N.cuda.jb_encode_batch_destroy(self._batch)
+            self._batch = None
+        if self._coef_dev is not None and ctx is not None:
+            ctx.device_free(self._coef_dev)
+            self._coef_dev = None
+
+    def __del__(self):
+        try:
+            self._close()
+        except Exception:
+            pass
+
+    def Scan(self):                # :72-154
+        if self._input is None or len(self._input) == 0:
+            raise InvalidOperationException("Input buffer is not specified.")
+        if self.MostOptimalCoding:
+            raise NotSupportedException("package-merge table construction is not on the GPU path")
+        ctx = self._ctx or Context.default()
+        self._close()
+        p = Parsed(self._input)
+        d = p.desc
+        if d.sof > 1:
+            raise InvalidDataException("Progressive JPEG is not supported currently.")
+        if d.scan_count < 1:
+            raise InvalidDataException("No image data is read.")
+        sc = d.scans[0]
+        if sc.restart_interval != 0:
+            raise NotSupportedException("restart intervals are not transcoded on the GPU path (reference quirk Q6)")
+        hmax = max(d.h[i] for i in range(d.component_count))
+        vmax = max(d.v[i] for i in range(d.component_count))
+        nblk = ((d.width + 8 * hmax - 1) // (8 * hmax)) * ((d.height + 8 * vmax - 1) // (8 * vmax)) * \
+            sum(d.h[i] * d.v[i] for i in range(d.component_count))
+        self._nblk = nblk
+        self._coef_dev = ctx.device_alloc(nblk * 128)
+        out = CudaOutputWriter(self._coef_dev, N.JB_OUT_COEFFICIENTS, on_device=True, capacity=nblk * 128)._output_desc()
+        ctx.check(N.cuda.jb_decode(ctx.handle, C.byref(d), C.byref(out), 1, None))
+        # transcode descriptor: components in SCAN order (that is the store's block order)
+        e = N.EncodeDesc()
+        e.pixels, e.on_device, e.format = self._coef_dev, 1, N.JB_IN_COEFFICIENTS
+        e.width, e.height, e.component_count = d.width, d.height, sc.component_count
+        self._table_order = []
+        for i in range(sc.component_count):
+            c = sc.component_index[i]
+            e.h[i], e.v[i] = d.h[c], d.v[c]
+            td = d.tables[sc.dc_table[i]].identifier
+            ta = d.tables[sc.ac_table[i]].identifier
+            e.td[i], e.ta[i] = td, ta
+            for key in ((0, td), (1, ta)):   # GetOrCreateTableBuilder order (:394-395)
+                if key not in self._table_order:
+                    self._table_order.append(key)
+        h = C.c_void_p()
+        ctx.check(N.cuda.jb_encode_batch_create(ctx.handle, C.byref(e), 1, C.byref(h)))
+        self._batch = h
+        ctx.check(N.cuda.jb_encode_batch_transform(h))
+        ctx.check(N.cuda.jb_encode_batch_build_tables(h))
+        self._parsed = p
+
+    def Optimize(self, strip=True):  # :546-647
+        if self._batch is None:
+            raise InvalidOperationException()
+        if self._output is None:
+            raise InvalidOperationException()
+        ctx = self._ctx or Context.default()
+        h = self._batch
+        ctx.check(N.cuda.jb_encode_batch_pack(h))
+        ctx.check(N.cuda.jb_encode_batch_finish(h))
+        n = C.c_uint64()
+        N.cuda.jb_encode_batch_scan_length(h, 0, C.byref(n))
+        scan = np.empty(n.value, dtype=np.uint8)
+        ctx.check(N.cuda.jb_encode_batch_read_scan(h, 0, scan.ctypes.data, scan.size))
+        specs = []
+        for cls, ident in self._table_order:
+            s = N.HuffSpec()
+            ctx.check(N.cuda.jb_encode_batch_get_table(h, 0, cls, ident, C.byref(s)))
+            specs.append(s)
+        self.last_tables = specs
+        data = bytes(self._input)
+        # quantisation tables in definition order, latest definition wins (ProcessDefineQuantizationTable)
+        qts = {}
+        pos = 2
+        segs = []  # (marker, payload_start, payload_end)
+        while pos + 2 <= len(data):
+            if data[pos] != 0xFF:
+                pos += 1
+                continue
+            m = data[pos + 1]
+            if m == 0xFF:
+                pos += 1
+                continue
+            if m == 0xD9:
+                segs.append((m, pos + 2, pos + 2))
+                break
+            if m == 0x00 or 0xD0 <= m <= 0xD7 or m == 0xD8:
+                pos += 2
+                continue
+            if pos + 4 > len(data):
+                raise InvalidDataException("Unexpected end of input data when reading segment length.")
+            ln = int.from_bytes(data[pos + 2:pos + 4], "big")
+            segs.append((m, pos + 4, pos + 2 + ln))
+            if m == 0xDB:
+                q = data[pos + 4:pos + 2 + ln]
+                i = 0
+                while i < len(q):
+                    size = 129 if q[i] >> 4 else 65
+                    qts[q[i] & 15] = q[i:i + size]
+                    i += size
+            pos += 2 + ln
+            if m == 0xDA:
+                sc = self._parsed.desc.scans[0]
+                pos = sc.entropy_offset + sc.entropy_length
+        out = bytearray(b"\xff\xd8")
+        dht_written = dqt_written = False
+        for m, a, b in segs:
+            payload = data[a:b]
+            if m in (0xE0, 0xC0, 0xC1):
+                out += _marker_segment(m, payload)
+            elif m == 0xC4:
+                if not dht_written:
+                    body = bytearray()
+                    for s in specs:
+                        body += bytes([(s.table_class << 4) | (s.identifier & 15)]) + bytes(s.bits) + bytes(s.values[:s.value_count])
+                    out += _marker_segment(0xC4, bytes(body))
+                    dht_written = True
+            elif m == 0xDB:
+                if not dqt_written:
+                    out += _marker_segment(0xDB, b"".join(qts[k] for k in qts))
+                    dqt_written = True
+            elif m == 0xDA:
+                out += _marker_segment(0xDA, payload) + scan.tobytes()
+            elif m == 0xD9:
+                out += b"\xff\xd9"
+            elif not strip:
+                out += _marker_segment(m, payload)
+        if hasattr(self._output, "write"):
+            self._output.write(bytes(out))
+        else:
+            self._output += out

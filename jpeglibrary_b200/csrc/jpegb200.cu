@@ -1319,16 +1319,24 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         d = JbEncImage{};
         auto bad = [&](int code, const char *msg) { delete b; return fail(ctx, code, "image %d: %s", i, msg); };
         if (!e.pixels || e.width == 0 || e.height == 0) return bad(JB_ERR_ARGUMENT, "no input pixels");
-        if (e.component_count != 1 && e.component_count != 3) return bad(JB_ERR_NOT_SUPPORTED, "1 or 3 components");
-        if ((e.component_count == 1) != (e.format == JB_IN_GRAY8)) return bad(JB_ERR_ARGUMENT, "pixel format does not match the component count");
+        const bool import = e.format == JB_IN_COEFFICIENTS;
+        if (import && !e.on_device) return bad(JB_ERR_ARGUMENT, "coefficient input must be device memory");
+        if (import && (e.component_count < 1 || e.component_count > 4)) return bad(JB_ERR_ARGUMENT, "bad component count");
+        if (!import && e.component_count != 1 && e.component_count != 3) return bad(JB_ERR_NOT_SUPPORTED, "1 or 3 components");
+        if (!import && (e.component_count == 1) != (e.format == JB_IN_GRAY8)) return bad(JB_ERR_ARGUMENT, "pixel format does not match the component count");
         for (int c = 0; c < e.component_count; c++) {
             // AddComponent: factors must be 1, 2 or 4 (JpegEncoder.cs:177-184); tables must be defined (:199-203)
             if ((e.h[c] != 1 && e.h[c] != 2 && e.h[c] != 4) || (e.v[c] != 1 && e.v[c] != 2 && e.v[c] != 4))
                 return bad(JB_ERR_ARGUMENT, "Subsampling factor can only be 1, 2 or 4.");
-            if (e.tq[c] > 3 || !e.quant_present[e.tq[c]]) return bad(JB_ERR_ARGUMENT, "Quantization table is not defined.");
+            if (!import && (e.tq[c] > 3 || !e.quant_present[e.tq[c]])) return bad(JB_ERR_ARGUMENT, "Quantization table is not defined.");
             if (e.td[c] > 3 || e.ta[c] > 3) return bad(JB_ERR_ARGUMENT, "Huffman table is not defined.");
         }
         int hs = e.h[0], vs = e.v[0];
+        if (import) { // geometry only: hs, vs = maximum sampling factors
+            hs = vs = 1;
+            for (int c = 0; c < e.component_count; c++) { hs = std::max<int>(hs, e.h[c]); vs = std::max<int>(vs, e.v[c]); }
+        }
+        if (!import) {
         if (hs > 2 || vs > 2) return bad(JB_ERR_NOT_SUPPORTED, "luma sampling factor 4 is not on the GPU path");
         if (e.component_count == 3 && (e.h[1] != 1 || e.v[1] != 1 || e.h[2] != 1 || e.v[2] != 1))
             return bad(JB_ERR_NOT_SUPPORTED, "chroma must be sampled 1x1");
@@ -1338,6 +1346,7 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         const int wblk = (e.width + 7) / 8, hblk = (e.height + 7) / 8;
         if (wblk % hs != 0 || hblk % vs != 0)
             return bad(JB_ERR_NOT_SUPPORTED, "frame needs MCU padding blocks, which the reference encodes from a stale dummy block (quirk Q4)");
+        }
         d.width = e.width; d.height = e.height; d.ncomp = e.component_count;
         d.hs = (uint8_t)hs; d.vs = (uint8_t)vs; d.in_format = (uint8_t)e.format;
         d.mcus_per_line = (e.width + 8 * hs - 1) / (8 * hs);
@@ -1346,12 +1355,15 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         int bpm = 0;
         for (int c = 0; c < e.component_count; c++) {
             d.comp_td[c] = e.td[c]; d.comp_ta[c] = e.ta[c];
-            for (int k = 0; k < e.h[c] * e.v[c]; k++) d.blk_comp[bpm++] = (uint8_t)c;
+            for (int k = 0; k < e.h[c] * e.v[c]; k++) {
+                if (bpm >= JB_MAX_BLOCKS_PER_MCU) return bad(JB_ERR_INVALID_DATA, "MCU too large");
+                d.blk_comp[bpm++] = (uint8_t)c;
+            }
         }
         d.bpm = (uint8_t)bpm;
         d.quant_off = (uint32_t)b->quant.size();
         for (int c = 0; c < e.component_count; c++)
-            for (int k = 0; k < 64; k++) b->quant.push_back(e.quant[e.tq[c]][k]);
+            for (int k = 0; k < 64; k++) b->quant.push_back(import ? 1 : e.quant[e.tq[c]][k]);
         const uint64_t nblk = (uint64_t)d.total_mcus * bpm;
         d.coef_off = blocks; d.bits_off = blocks;
         blocks += nblk;
@@ -1363,9 +1375,10 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         d.table_base = (uint32_t)i * 8;
         const int bpp = e.format == JB_IN_GRAY8 ? 1 : 3;
         d.pix_pitch = e.pitch ? e.pitch : (uint64_t)e.width * bpp;
-        if (d.pix_pitch < (uint64_t)e.width * bpp) return bad(JB_ERR_ARGUMENT, "pitch too small");
-        b->pix_bytes[i] = d.pix_pitch * e.height;
+        if (!import && d.pix_pitch < (uint64_t)e.width * bpp) return bad(JB_ERR_ARGUMENT, "pitch too small");
+        b->pix_bytes[i] = import ? nblk * 128 : d.pix_pitch * e.height;
         if (!e.on_device) { b->pix_dev_off[i] = pixels; pixels += align_up(b->pix_bytes[i], 256); }
+        if (import) continue; // no transform kernel: blocks are copied into the store
         jb_encode_batch::Group *g = nullptr;
         for (auto &x : b->groups) if (x.nc == e.component_count && x.hs == hs && x.vs == vs) g = &x;
         if (!g) { b->groups.push_back({e.component_count, hs, vs, {}, 0, 0}); g = &b->groups.back(); }
@@ -1407,7 +1420,7 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
     for (auto &g : b->groups) { g.list_off = (uint32_t)list.size(); list.insert(list.end(), g.list.begin(), g.list.end()); }
     JB_CUDA_E(cudaMemcpyAsync(b->d_images, b->images.data(), sizeof(JbEncImage) * count, cudaMemcpyHostToDevice, st));
     JB_CUDA_E(cudaMemcpyAsync(b->d_quant, b->quant.data(), sizeof(uint16_t) * b->quant.size(), cudaMemcpyHostToDevice, st));
-    JB_CUDA_E(cudaMemcpyAsync(b->d_list, list.data(), sizeof(uint32_t) * count, cudaMemcpyHostToDevice, st));
+    if (!list.empty()) JB_CUDA_E(cudaMemcpyAsync(b->d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice, st));
     JB_CUDA_E(cudaMemsetAsync(b->d_tables, 0, sizeof(JbEncTable) * 8 * count, st));
     JB_CUDA_E(cudaStreamSynchronize(st));
 #undef JB_CUDA_E
@@ -1421,9 +1434,12 @@ int jb_encode_batch_transform(jb_encode_batch *b)
     jb_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     JB_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (int i = 0; i < b->count; i++)
-        if (!b->descs[i].on_device)
+    for (int i = 0; i < b->count; i++) {
+        if (b->descs[i].format == JB_IN_COEFFICIENTS)
+            JB_CUDA(ctx, cudaMemcpyAsync(b->d_coef + b->images[i].coef_off * 64, b->descs[i].pixels, b->pix_bytes[i], cudaMemcpyDeviceToDevice, st));
+        else if (!b->descs[i].on_device)
             JB_CUDA(ctx, cudaMemcpyAsync(b->d_pixels + b->pix_dev_off[i], b->descs[i].pixels, b->pix_bytes[i], cudaMemcpyHostToDevice, st));
+    }
     JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
     JB_CUDA(ctx, cudaMemsetAsync(b->d_hist, 0, sizeof(uint32_t) * 8 * 256 * b->count, st));
     b->launches = 0;
