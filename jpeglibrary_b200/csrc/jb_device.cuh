@@ -27,10 +27,18 @@ struct __align__(16) JbHuffTable {
     uint16_t maxcode[20];      // reference _maxCode[0..17] (left-aligned 16-bit), padded
     uint8_t valoffset[24];     // reference _valOffset[0..18], padded
     uint8_t values[256];
+    uint32_t cls;              // 0 = DC, 1 = AC
+    uint32_t pad[3];
 };
 static_assert(sizeof(JbHuffTable) % 16 == 0, "table must be copyable as uint4");
 
-struct JbDevImage {
+struct __align__(16) JbDevImage {
+    // flat restart-segment decode (K0b/K1): per block-in-mcu x = DC table, y = AC table (32-bit word offsets into
+    // the JbHuffTable32 array), z = component
+    uint4 binfo[JB_MAX_BLOCKS_PER_MCU];
+    uint64_t clean_off;  // this image's base offset in the clean (un-stuffed) arena
+    uint32_t seg_base;   // global index of the image's first restart segment in the batch
+    uint32_t pad4;
     // compressed input
     uint64_t data_off;   // offset of the entropy-coded bytes in the device arena (256-B aligned)
     uint32_t data_len;   // upper bound of entropy-coded length (bytes)
@@ -63,6 +71,8 @@ struct JbDevImage {
     uint32_t comp_plane_off[4];     // first block of each component plane (relative to coef_off)
     uint32_t comp_plane_w[4];       // blocks per row of each plane
     uint32_t pad3;
+    // lossless (SOF3): predictor selection Ss and 2^(P-Pt-1); planes reuse comp_plane_off (x64 samples) / comp_plane_w (samples per row)
+    int32_t ll_predictor, ll_initial;
     // coefficient store
     uint64_t coef_off;   // first block of this image in the coefficient store (in blocks)
     uint32_t quant_off;  // first of ncomp quant tables (64 x uint16 each) in the quant array

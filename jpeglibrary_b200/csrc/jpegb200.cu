@@ -21,10 +21,12 @@
 
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
+#include "k_entropy_flat.cuh"
 #include "k_entropy_selfsync.cuh"
 #include "k_entropy_progressive.cuh"
 #include "k_idct_color.cuh"
 #include "k_idct_color_fast.cuh"
+#include "k_lossless.cuh"
 
 struct jb_ctx {
     int device = 0;
@@ -166,7 +168,28 @@ bool build_device_table(const jb_huff_spec &s, JbHuffTable &d)
     memcpy(d.maxcode, t.maxcode, sizeof t.maxcode);
     memcpy(d.valoffset, t.valoffset, sizeof t.valoffset);
     memcpy(d.values, t.values, 256);
+    d.cls = s.table_class;
     return true;
+}
+
+// the same table with 32-bit entries that carry what ReadBlockBaseline does with the symbol (K1)
+void build_device_table32(const JbHuffTable &t, JbHuffTable32 &d)
+{
+    memset(&d, 0, sizeof d);
+    auto conv = [&](uint16_t e) -> uint32_t {
+        if ((e & 0xFF) == 0) return 0;
+        const uint32_t v = jb_entry32(t.cls, e >> 8, e & 0xFF);
+        return v == JB_E32_BAD ? 0u : v; // resolved (and flagged) by the slow path
+    };
+    for (int p = 0; p < JB_LUT_SIZE; p++) {
+        const uint16_t e = t.lut[p];
+        d.lut[p] = (e & 0xFF) ? conv(e) : (uint32_t)(e & 0xFF00); // escape: byte 1 = 1 + sub-table
+    }
+    for (int p = 0; p < JB_LUT2_SUBTABLES * 64; p++) d.lut2[p] = conv(t.lut2[p]);
+    memcpy(d.maxcode, t.maxcode, sizeof d.maxcode);
+    memcpy(d.valoffset, t.valoffset, sizeof d.valoffset);
+    memcpy(d.values, t.values, 256);
+    d.cls = t.cls;
 }
 
 struct ImagePlan {
@@ -254,7 +277,13 @@ struct jb_batch {
     uint8_t *d_out_staging = nullptr;
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
-    uint32_t max_nseg = 1; // most restart segments any image has (sizes K1's CTAs)
+    uint32_t max_nseg = 1; // most restart segments any image of the K0b/K1 path has
+    // flat restart-segment path (K0b + K1)
+    std::vector<JbHuffTable32> tables32;
+    JbHuffTable32 *d_tables32 = nullptr;
+    uint32_t total_segs = 0;
+    JbSegDesc *d_segs = nullptr;
+    uint8_t *d_clean_seg = nullptr;
     // progressive frames
     std::vector<uint32_t> prog_images;
     uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1, prog_levels = 0;
@@ -266,6 +295,9 @@ struct jb_batch {
     // self-synchronising path (images without restart markers)
     std::vector<uint32_t> seg_images, ss_images; // K1a / K1b image lists
     uint32_t ss_list_off = 0, seg_list_off = 0;
+    // lossless frames (SOF3)
+    std::vector<uint32_t> ll_images;
+    uint32_t ll_list_off = 0, ll_max_nseg = 1, ll_max_pixels = 0;
     uint32_t ss_max_sub = 0;
     uint64_t ss_total_sub = 0;
     uint8_t *d_clean = nullptr;
@@ -286,7 +318,8 @@ struct jb_batch {
     bool need_render = false;
     int launches = 0;
     bool profiling = false;
-    std::vector<cudaEvent_t> events; // 4 per profiled launch
+    std::vector<cudaEvent_t> events;       // profiling: one event per named mark
+    std::vector<const char *> event_names; // name of the interval that ENDS at the event (nullptr: start of a launch)
 };
 
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
@@ -581,6 +614,90 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
     return plan_output(ctx, idx, im, outp, pl);
 }
 
+// SOF3: JpegHuffmanLosslessScanDecoder ctor + ProcessScan set-up (ScanDecoder/JpegHuffmanLosslessScanDecoder.cs:23-83),
+// JpegPartialScanlineAllocator plane geometry (JpegPartialScanlineAllocator.cs:35-60)
+static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl,
+                         std::vector<JbHuffTable> &tables, std::map<std::string, int> &table_ids)
+{
+    JbDevImage &d = pl.dev;
+    if (im.precision < 2 || im.precision > 16) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
+    if (im.scan_count != 1 || !im.scans || im.scans[0].component_count != im.component_count)
+        return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "lossless frames must consist of one interleaved scan");
+    if (outp && outp->format == JB_OUT_COEFFICIENTS)
+        return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "lossless frames have no DCT coefficients");
+    const jb_scan_desc &sc = im.scans[0];
+    if (sc.al >= im.precision) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad point transform");
+    int hmax = 1, vmax = 1;
+    for (int c = 0; c < im.component_count; c++) {
+        if (im.h[c] < 1 || im.h[c] > 4 || im.v[c] < 1 || im.v[c] > 4)
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sampling factor");
+        hmax = std::max<int>(hmax, im.h[c]);
+        vmax = std::max<int>(vmax, im.v[c]);
+    }
+    d.width = im.width; d.height = im.height; d.ncomp = im.component_count; d.precision = im.precision; d.sof = 3;
+    d.hmax = (uint8_t)hmax; d.vmax = (uint8_t)vmax;
+    d.mcus_per_line = (im.width + hmax - 1) / hmax;   // :33-34: one MCU = hmax x vmax samples
+    d.mcus_per_col = (im.height + vmax - 1) / vmax;
+    d.total_mcus = d.mcus_per_line * d.mcus_per_col;
+    d.ll_predictor = sc.ss;
+    d.ll_initial = 1 << (im.precision - sc.al - 1);
+    uint64_t blocks = 0;
+    for (int c = 0; c < im.component_count; c++) {
+        if (hmax % im.h[c] || vmax % im.v[c])
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "sampling factors must divide the maximum");
+        const int hs = hmax / im.h[c], vs = vmax / im.v[c];
+        const uint32_t w = (im.width + hs - 1) / hs, h = (im.height + vs - 1) / vs;
+        // the reference indexes scanline[colMcu*h + x] / GetScanlineSpan(rowMcu*v + y): an MCU grid that
+        // overhangs the component plane throws there
+        if (d.mcus_per_line * im.h[c] > w || d.mcus_per_col * im.v[c] > h)
+            return fail(ctx, JB_ERR_INVALID_OPERATION, "image %d: %s", idx, "lossless MCU grid overhangs the component plane");
+        d.comp_plane_off[c] = (uint32_t)blocks;
+        d.comp_plane_w[c] = w;
+        blocks += ((uint64_t)w * h + 63) / 64;
+    }
+    pl.total_blocks = blocks;
+    int bpm = 0;
+    std::map<int, int> slot_of_table;
+    bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
+    for (int i = 0; i < sc.component_count; i++) {
+        const int c = sc.component_index[i];
+        if (c >= im.component_count || seen[c]) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+        seen[c] = true;
+        d.comp_h[c] = im.h[c]; d.comp_v[c] = im.v[c];
+        d.comp_blk_off[c] = (uint8_t)bpm;
+        const int gid = intern_table(im, sc.dc_table[i], 0, tables, table_ids);
+        if (gid == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
+        if (gid < 0) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
+        auto it = slot_of_table.find(gid);
+        int slot;
+        if (it == slot_of_table.end()) {
+            slot = (int)slot_of_table.size();
+            if (slot >= JB_MAX_TABLE_SLOTS) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "too many tables");
+            d.table_index[slot] = (uint16_t)gid;
+            slot_of_table[gid] = slot;
+        } else
+            slot = it->second;
+        for (int k = 0; k < im.h[c] * im.v[c]; k++) {
+            if (bpm >= JB_MAX_BLOCKS_PER_MCU) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "MCU too large");
+            d.blk_comp[bpm] = (uint8_t)c;
+            d.blk_dc[bpm] = (uint8_t)slot;
+            bpm++;
+        }
+    }
+    d.bpm = (uint8_t)bpm;
+    d.ntables = (uint8_t)slot_of_table.size();
+    d.dri = sc.restart_interval;
+    d.nseg = d.dri ? (d.total_mcus + d.dri - 1) / d.dri : 1;
+    d.mark_cap = d.nseg + 1;
+    if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
+    pl.entropy_off = sc.entropy_offset;
+    pl.entropy_len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
+                                       : im.length - sc.entropy_offset;
+    if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
+    d.data_len = (uint32_t)pl.entropy_len;
+    return plan_output(ctx, idx, im, outp, pl);
+}
+
 // ------------------------------------------------------------------------------------------------
 // plan one image: geometry, layout, validation
 // ------------------------------------------------------------------------------------------------
@@ -592,10 +709,11 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     if (im.component_count < 1 || im.component_count > JB_MAX_COMPONENTS)
         return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad component count");
     if (im.width == 0 || im.height == 0) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "empty frame");
-    if (im.sof > 2)
+    if (im.sof > 3)
         return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
-                    "only SOF0/SOF1/SOF2 Huffman frames are handled by the GPU path");
+                    "only SOF0/SOF1/SOF2/SOF3 Huffman frames are handled by the GPU path");
     if (im.sof == 2) return plan_progressive(ctx, idx, im, outp, pl, tables, table_ids, quant);
+    if (im.sof == 3) return plan_lossless(ctx, idx, im, outp, pl, tables, table_ids);
     if (im.precision < 2 || im.precision > 16)
         return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
     if (im.scan_count != 1 || !im.scans)
@@ -687,6 +805,9 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     }
     d.bpm = (uint8_t)bpm;
     d.ntables = (uint8_t)slot_of_table.size();
+    for (int k = 0; k < bpm; k++)
+        d.binfo[k] = make_uint4((uint32_t)(d.table_index[d.blk_dc[k]] * (sizeof(JbHuffTable32) / 4)),
+                                (uint32_t)(d.table_index[d.blk_ac[k]] * (sizeof(JbHuffTable32) / 4)), d.blk_comp[k], 0);
     d.dri = sc.restart_interval;
     d.nseg = d.dri ? (d.total_mcus + d.dri - 1) / d.dri : 1;
     d.mark_cap = d.nseg + 1;
@@ -763,6 +884,10 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             pl.dev_out = pl.out.dst;
         if (pl.dev.sof == 2) {
             b->prog_images.push_back((uint32_t)i);
+        } else if (pl.dev.sof == 3) {
+            b->ll_images.push_back((uint32_t)i);
+            b->ll_max_nseg = std::max(b->ll_max_nseg, pl.dev.nseg);
+            b->ll_max_pixels = std::max<uint32_t>(b->ll_max_pixels, (uint32_t)pl.dev.width * pl.dev.height);
         } else if (pl.dev.use_selfsync) {
             pl.dev.sub_base = (uint32_t)b->ss_total_sub;
             b->ss_total_sub += pl.dev.sub_cap;
@@ -771,8 +896,11 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         } else {
             b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
             b->seg_images.push_back((uint32_t)i);
+            pl.dev.seg_base = b->total_segs;
+            pl.dev.clean_off = pl.dev.data_off + 32ull * b->total_segs;
+            b->total_segs += pl.dev.nseg;
         }
-        if (pl.out.format != JB_OUT_COEFFICIENTS) {
+        if (pl.out.format != JB_OUT_COEFFICIENTS && pl.dev.sof != 3) {
             const int variant = k2_variant(pl.dev);
             jb_batch::RenderGroup *g = nullptr;
             for (auto &x : b->groups)
@@ -843,6 +971,20 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMallocAsync(&b->d_arena, b->arena_bytes, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_images, sizeof(JbDevImage) * count, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_tables, sizeof(JbHuffTable) * b->tables.size(), ctx->stream));
+    if (b->total_segs) {
+        if (b->tables.size() * (sizeof(JbHuffTable32) / 4) >= (1ull << 32)) {
+            ctx->error = "too many distinct Huffman tables in one batch";
+            jb_decode_batch_destroy(b);
+            return JB_ERR_NOT_SUPPORTED;
+        }
+        b->tables32.resize(b->tables.size());
+        for (size_t t = 0; t < b->tables.size(); t++) build_device_table32(b->tables[t], b->tables32[t]);
+        JB_CUDA_B(cudaMallocAsync(&b->d_tables32, sizeof(JbHuffTable32) * b->tables32.size(), ctx->stream));
+        JB_CUDA_B(cudaMemcpyAsync(b->d_tables32, b->tables32.data(), sizeof(JbHuffTable32) * b->tables32.size(),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_segs, sizeof(JbSegDesc) * b->total_segs, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_clean_seg, b->arena_bytes + 32ull * b->total_segs + 256, ctx->stream));
+    }
     JB_CUDA_B(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1), ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_scan, sizeof(JbScanResult) * b->h_ranges.size(), ctx->stream));
@@ -861,6 +1003,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     h_list.insert(h_list.end(), b->ss_images.begin(), b->ss_images.end());
     b->prog_list_off = (uint32_t)h_list.size();
     h_list.insert(h_list.end(), b->prog_images.begin(), b->prog_images.end());
+    b->ll_list_off = (uint32_t)h_list.size();
+    h_list.insert(h_list.end(), b->ll_images.begin(), b->ll_images.end());
     if (!b->ss_images.empty()) {
         JB_CUDA_B(cudaMallocAsync(&b->d_clean, b->arena_bytes, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_clean_len, sizeof(uint32_t) * count, ctx->stream));
@@ -906,8 +1050,6 @@ int jb_decode_batch_upload(jb_batch *b)
     return JB_OK;
 }
 
-static const char *kKernelNames[3] = {"jb_k0_restart_scan", "jb_k1_huff_segments", "jb_k2_idct_color"};
-
 static int launch_render(jb_batch *b, int *launches);
 
 static int launch_kernels(jb_batch *b)
@@ -915,29 +1057,32 @@ static int launch_kernels(jb_batch *b)
     jb_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     int launches = 0;
-    auto mark = [&]() {
+    auto mark = [&](const char *name) {
         if (!b->profiling) return;
         cudaEvent_t e;
         if (cudaEventCreate(&e) == cudaSuccess) {
             cudaEventRecord(e, st);
             b->events.push_back(e);
+            b->event_names.push_back(name);
         }
     };
     JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
-    mark();
+    mark(nullptr);
     jb_k0_restart_scan<<<(unsigned)b->h_ranges.size(), JB_K0_THREADS, 0, st>>>(b->d_ranges, b->d_arena, b->d_marks, b->d_scan);
     launches++;
-    mark();
+    mark("jb_k0_restart_scan");
     if (!b->seg_images.empty()) {
         // one warp per 32 segments; a CTA never spans images, so pick the CTA size that wastes the
         // fewest warp slots for this batch (at most JB_K1_MAX_WARPS warps)
-        const uint32_t warps = std::min<uint32_t>(JB_K1_MAX_WARPS, (b->max_nseg + 31) / 32);
-        const uint32_t threads = warps * 32;
-        dim3 grid((b->max_nseg + threads - 1) / threads, (unsigned)b->seg_images.size());
-        size_t smem = warps * JB_K1_STAGE_BYTES;
-        jb_k1_huff_segments<<<grid, threads, smem, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_tables,
-                                                         b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status);
-        launches++;
+        dim3 ugrid((b->max_nseg + JB_K0B_WARPS - 1) / JB_K0B_WARPS, (unsigned)b->seg_images.size());
+        jb_k0b_unstuff_segments<<<ugrid, JB_K0B_WARPS * 32, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_arena,
+                                                                    b->d_marks, b->d_scan, b->d_clean_seg, b->d_segs, b->d_status);
+        mark("jb_k0b_unstuff_segments");
+        jb_k1_huff_flat<<<(b->total_segs + JB_K1F_THREADS - 1) / JB_K1F_THREADS, JB_K1F_THREADS, 0, st>>>(
+            b->d_images, b->d_segs, b->total_segs, b->d_tables32, reinterpret_cast<const uint32_t *>(b->d_clean_seg), b->d_coef,
+            b->d_status);
+        mark("jb_k1_huff_segments");
+        launches += 2;
     }
     if (!b->ss_images.empty()) {
         const uint32_t *list = b->d_image_list + b->ss_list_off;
@@ -954,6 +1099,7 @@ static int launch_kernels(jb_batch *b)
         jb_k1b_write<<<grid, JB_K1B_THREADS, (JB_K1B_THREADS / 32) * JB_K1_STAGE_BYTES, st>>>(
             b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
         launches += 4 + JB_SS_ROUNDS;
+        mark("jb_k1b_selfsync_chain");
     }
     if (!b->prog_images.empty()) {
         // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
@@ -966,10 +1112,23 @@ static int launch_kernels(jb_batch *b)
                                                          b->d_status, lanes);
             launches++;
         }
+        mark("jb_k1c_progressive_scans");
     }
-    mark();
+    if (!b->ll_images.empty()) {
+        const uint32_t *list = b->d_image_list + b->ll_list_off;
+        const unsigned nimg = (unsigned)b->ll_images.size();
+        const int lanes = b->ll_max_nseg > 1 ? 32 : 1;
+        dim3 grid((b->ll_max_nseg + lanes - 1) / lanes, nimg);
+        jb_k1d_lossless_entropy<<<grid, 32, 0, st>>>(b->d_images, list, b->d_tables, b->d_arena, b->d_marks, b->d_scan, b->d_coef,
+                                                    b->d_status, lanes);
+        jb_k1d_lossless_predict<<<nimg, 32 * JB_MAX_COMPONENTS_DEV, 0, st>>>(b->d_images, list, b->d_coef);
+        dim3 ogrid((b->ll_max_pixels + 255) / 256, nimg);
+        jb_k5_lossless_output<<<ogrid, 256, 0, st>>>(b->d_images, list, b->d_coef);
+        launches += 3;
+        mark("jb_k1d_lossless");
+    }
     launch_render(b, &launches);
-    mark();
+    mark("jb_k2_idct_color");
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
     return JB_OK;
@@ -986,6 +1145,7 @@ static void clear_events(jb_batch *b)
 {
     for (cudaEvent_t e : b->events) cudaEventDestroy(e);
     b->events.clear();
+    b->event_names.clear();
 }
 
 int jb_decode_batch_set_profiling(jb_batch *b, int on)
@@ -999,28 +1159,32 @@ int jb_decode_batch_set_profiling(jb_batch *b, int on)
 
 int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
 {
-    if (!b || !names || !ms || cap < 3) return JB_ERR_ARGUMENT;
+    if (!b || !names || !ms || cap < 1) return JB_ERR_ARGUMENT;
     jb_ctx *ctx = b->ctx;
     JB_CUDA(ctx, cudaSetDevice(ctx->device));
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const size_t nlaunch = b->events.size() / 4;
-    if (nlaunch == 0) return 0;
-    double acc[3] = {0, 0, 0};
-    for (size_t l = 0; l < nlaunch; l++)
-        for (int k = 0; k < 3; k++) {
-            float t = 0;
-            cudaEventElapsedTime(&t, b->events[l * 4 + k], b->events[l * 4 + k + 1]);
-            acc[k] += t;
-        }
-    for (int k = 0; k < 3; k++) {
-        const char *nm = kKernelNames[k];
-        if (k == 1 && b->seg_images.empty() && b->ss_images.empty()) nm = "jb_k1c_progressive_scans";
-        else if (k == 1 && b->seg_images.empty() && b->prog_images.empty()) nm = "jb_k1b_selfsync_chain";
-        else if (k == 1 && !b->ss_images.empty()) nm = "jb_k1_segments+selfsync";
-        snprintf(names[k], 48, "%s", nm);
-        ms[k] = (float)(acc[k] / (double)nlaunch);
+    // average duration per launch of every named interval, in order of first appearance
+    std::vector<const char *> order;
+    std::vector<double> acc;
+    size_t nlaunch = 0;
+    for (size_t i = 0; i < b->events.size(); i++) {
+        const char *nm = b->event_names[i];
+        if (!nm) { nlaunch++; continue; }
+        if (i == 0) continue;
+        float t = 0;
+        cudaEventElapsedTime(&t, b->events[i - 1], b->events[i]);
+        size_t k = 0;
+        while (k < order.size() && strcmp(order[k], nm) != 0) k++;
+        if (k == order.size()) { order.push_back(nm); acc.push_back(0); }
+        acc[k] += t;
     }
-    return 3;
+    if (nlaunch == 0) return 0;
+    int n = 0;
+    for (size_t k = 0; k < order.size() && n < cap; k++, n++) {
+        snprintf(names[n], 48, "%s", order[k]);
+        ms[n] = (float)(acc[k] / (double)nlaunch);
+    }
+    return n;
 }
 
 static int launch_render(jb_batch *b, int *launches)
@@ -1186,6 +1350,9 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_used) cudaFreeAsync(b->d_used, b->ctx->stream);
     if (b->d_info) cudaFreeAsync(b->d_info, b->ctx->stream);
     if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
+    if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
+    if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);
+    if (b->d_clean_seg) cudaFreeAsync(b->d_clean_seg, b->ctx->stream);
     delete b;
 }
 

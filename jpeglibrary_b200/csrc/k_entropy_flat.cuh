@@ -1,0 +1,273 @@
+// k_entropy_flat.cuh -- K0b (per-segment un-stuffing) and K1 (flat restart-segment Huffman decode).
+//
+// Replaces, for a whole batch of images at once:
+//   JpegBitReader.FillBuffer / PeekBits / TryReadBits / AdvanceAlignByte   (JpegBitReader.cs:29-204)
+//   JpegHuffmanDecodingTable.Lookup / LookupSlow                            (JpegHuffmanDecodingTable.cs:73-113)
+//   DecodeHuffmanCode / ReceiveAndExtend                                    (ScanDecoder/JpegHuffmanScanDecoder.cs:81-115)
+//   ReadBlockBaseline + MCU loop + restart handling                         (ScanDecoder/JpegHuffmanBaselineScanDecoder.cs:99-222)
+//
+// Design (B200): the decoder is instruction-issue bound, so everything data dependent that is not the
+// Huffman symbol itself is moved out of the per-symbol loop:
+//   * K0b rewrites every restart segment as a "clean" stream: FF 00 -> FF, fill bytes dropped
+//     (JpegBitReader.cs:108-128), bytes stored big-endian per 32-bit word and followed by 16 bytes of
+//     1-bits (PeekBits pads with ones, :166).  The decoder's refill is then one predicated word append.
+//   * Huffman tables carry 32-bit entries that already hold everything the symbol step needs
+//     (bits to consume, code length, zig-zag run, zig-zag advance), built on the host by simulating the
+//     reference's Lookup/LookupSlow, so DC and AC symbols share one branch-free step.
+//   * Segments of the whole batch are numbered globally (image-major): warps are always full, whatever
+//     the number of segments per image.
+#pragma once
+#include "jb_device.cuh"
+
+// one restart segment of the batch, written by K0b
+struct __align__(16) JbSegDesc {
+    uint32_t word_off;   // first 32-bit word of the segment's clean stream
+    uint32_t nbits;      // clean bits in the segment
+    uint32_t nblocks;    // blocks to decode (0: nothing to do)
+    uint32_t flags;      // bit 0: a restart marker / EOI must follow; bit 1: it does
+    uint64_t coef_block; // first block of the segment in the coefficient store
+    uint32_t image;
+    uint32_t pad;
+};
+
+#define JB_K0B_WARPS 4
+
+// K0b: one warp per restart segment.  HBM-bound: reads the compressed bytes once, writes them once.
+__global__ void __launch_bounds__(JB_K0B_WARPS * 32)
+jb_k0b_unstuff_segments(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                        const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
+                        const JbScanResult *__restrict__ scanres, uint8_t *__restrict__ clean,
+                        JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status)
+{
+    const uint32_t image = image_list[blockIdx.y];
+    const JbDevImage &im = images[image];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t seg = blockIdx.x * JB_K0B_WARPS + wid;
+    if (seg >= im.nseg) return;
+    const JbScanResult sr = scanres[image];
+    const uint32_t *mk = marks + im.mark_base;
+    const uint8_t *data = arena + im.data_off;
+    const uint32_t dri = im.dri ? im.dri : im.total_mcus;
+    const uint32_t my_nmcu = min(dri, im.total_mcus - seg * dri);
+    uint32_t start = 0;
+    bool reachable = true;
+    if (seg > 0) {
+        if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
+        else reachable = false; // the previous interval is not followed by RSTn: "Expect restart marker."
+    }
+    uint32_t stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
+    if (!reachable || stop < start) stop = start;
+    // the reference expects RSTn or EOI right after every *complete* interval (JpegHuffmanBaselineScanDecoder.cs:139-154)
+    uint32_t flags = (im.dri != 0 && my_nmcu == dri) ? 1u : 0u;
+    bool marker_ok = seg < sr.nmarkers;
+    if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u; // EOI ends the scan
+    if (marker_ok) flags |= 2u;
+
+    // clean stream position: 32 spare bytes per segment make room for alignment and padding
+    const uint64_t cs = (im.clean_off + start + 32ull * seg + 15ull) & ~15ull;
+    uint8_t *out = clean + cs;
+    uint32_t total = 0;
+    for (uint32_t base = start & ~15u; base < stop; base += 512) {
+        const uint32_t chunk = base + lane * 16;
+        uint32_t w[4] = {0, 0, 0, 0}, pb = 0, nb = 0;
+        if (chunk < stop) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + chunk));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            nb = __ldg(data + chunk + 16); // the arena is padded: the over-read is safe
+            if (chunk > 0) pb = __ldg(data + chunk - 1);
+        }
+        uint32_t keep = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t pos = chunk + i;
+            const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
+            const uint32_t bn = i < 15 ? (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFF : nb;
+            uint32_t bp = i > 0 ? (w[(i - 1) >> 2] >> (((i - 1) & 3) * 8)) & 0xFF : pb;
+            if (pos == start) bp = 0;
+            const bool drop = (b == 0xFF && bn == 0xFF) || (b == 0 && bp == 0xFF);
+            if (pos >= start && pos < stop && !drop) keep |= 1u << i;
+        }
+        const uint32_t cnt = __popc(keep);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        uint32_t j = total + incl - cnt;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            if (keep & (1u << i)) {
+                out[j ^ 3u] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+                j++;
+            }
+        total += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    __syncwarp();
+    if (lane < 16) out[(total + lane) ^ 3u] = 0xFF; // pad with 1-bits (JpegBitReader.cs:166)
+    if (lane == 0) {
+        JbSegDesc d;
+        d.word_off = (uint32_t)(cs >> 2);
+        d.nbits = total * 8;
+        d.nblocks = reachable ? my_nmcu * im.bpm : 0;
+        d.flags = flags;
+        d.coef_block = im.coef_off + (uint64_t)seg * dri * im.bpm;
+        d.image = image;
+        d.pad = 0;
+        segs[im.seg_base + seg] = d;
+        if (!reachable) atomicOr(status + image, JB_ST_EXPECT_RST);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Huffman table, 32-bit entries: byte 0 = bits to consume (code + magnitude), byte 1 = code length,
+// byte 2 = zig-zag run before the coefficient, byte 3 = zig-zag advance after the symbol.
+// byte 0 == 0: escape; byte 1 = 1 + second-level sub-table (indexed by the next 6 bits) or 0 = slow path.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) JbHuffTable32 {
+    uint32_t lut[JB_LUT_SIZE];
+    uint32_t lut2[JB_LUT2_SUBTABLES * 64];
+    uint16_t maxcode[20];  // reference _maxCode[0..17] (left-aligned 16-bit), padded
+    uint8_t valoffset[24]; // reference _valOffset[0..18], padded
+    uint8_t values[256];
+    uint32_t cls;          // 0 = DC, 1 = AC
+    uint32_t pad[3];
+};
+static_assert(sizeof(JbHuffTable32) % 16 == 0, "table size");
+
+#define JB_E32_BAD 0xFFFFFFFFu
+
+// ReadBlockBaseline's use of a decoded symbol (JpegHuffmanBaselineScanDecoder.cs:187-219)
+__host__ __device__ inline uint32_t jb_entry32(uint32_t cls, uint32_t sym, uint32_t len)
+{
+    uint32_t s, run, adv;
+    if (cls == 0) {
+        if (sym > 16) return JB_E32_BAD;
+        s = sym; run = 0; adv = 1;
+    } else {
+        s = sym & 15; run = sym >> 4;
+        adv = s ? run + 1 : (run == 0 ? 64 : 16); // EOB; any other s == 0 symbol skips 16 (:213-219)
+    }
+    return (len + s) | (len << 8) | (run << 16) | (adv << 24);
+}
+
+// LookupSlow, JpegHuffmanDecodingTable.cs:88-113
+__device__ __noinline__ uint32_t jb_huff32_slow(const JbHuffTable32 *t, uint32_t code16)
+{
+    int size = 9;
+    while (code16 > __ldg(&t->maxcode[size])) size++;
+    if (size > 16) return JB_E32_BAD;
+    const uint32_t sym = __ldg(&t->values[(__ldg(&t->valoffset[size]) + (code16 >> (16 - size))) & 0xFF]);
+    return jb_entry32(__ldg(&t->cls), sym, (uint32_t)size);
+}
+
+__device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32_t e, uint32_t code16)
+{
+    if (e != 0) {
+        e = __ldg(&t->lut2[((e >> 8) - 1) * 64 + (code16 & 63)]);
+        if (e != 0) return e;
+    }
+    return jb_huff32_slow(t, code16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one thread per restart segment of the batch.  Each lane assembles its current block in a private
+// 128-byte shared-memory slot (zig-zag order) and moves it to the coefficient store as one full line
+// when the block is complete; the per-symbol step is branch-free apart from that.
+// ---------------------------------------------------------------------------------------------
+#define JB_K1F_THREADS 128
+#define JB_K1F_SLOT 144 // 128 bytes of coefficients + 16 bytes holding the four DC predictors
+
+__global__ void __launch_bounds__(JB_K1F_THREADS)
+jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restrict__ segs, uint32_t nsegs,
+                const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ clean_words,
+                int16_t *__restrict__ coef, uint32_t *__restrict__ status)
+{
+    __shared__ __align__(16) uint8_t s_slots[JB_K1F_THREADS * JB_K1F_SLOT];
+    const uint32_t g = blockIdx.x * JB_K1F_THREADS + threadIdx.x;
+    uint8_t *st = s_slots + threadIdx.x * JB_K1F_SLOT;
+#pragma unroll
+    for (int i = 0; i < JB_K1F_SLOT / 16; i++) reinterpret_cast<uint4 *>(st)[i] = make_uint4(0, 0, 0, 0);
+    if (g >= nsegs) return;
+    const JbSegDesc d = segs[g];
+    uint32_t left = d.nblocks;
+    if (left == 0) return;
+    const JbDevImage *im = images + d.image;
+    const uint32_t bpm = im->bpm;
+    const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
+
+    // bit window: hi:lo hold n valid bits, left-aligned; wnext is the prefetched next word
+    const uint32_t wend = d.word_off + ((d.nbits + 31) >> 5) + 2; // an all-ones padding word
+    uint32_t wofs = d.word_off;
+    uint32_t hi = __ldg(clean_words + wofs), lo = __ldg(clean_words + wofs + 1), wnext = __ldg(clean_words + wofs + 2);
+    wofs = min(wofs + 3, wend);
+    int n = 64;
+    uint32_t used = 0, err = 0;
+
+    uint32_t b = 0, k = 0; // block-in-mcu; next zig-zag index (0: the DC symbol comes next)
+    int pred = 0;
+    uint4 bi = __ldg(&im->binfo[0]); // x: DC table (word offset), y: AC table, z: component
+    uint4 *gptr = reinterpret_cast<uint4 *>(coef + d.coef_block * 64);
+
+    while (left != 0) {
+        if (n < 32) {
+            hi |= wnext >> n;
+            lo |= __funnelshift_r(0u, wnext, n);
+            n += 32;
+            wnext = __ldg(clean_words + wofs);
+            wofs = min(wofs + 1, wend);
+        }
+        const bool is_dc = k == 0;
+        const uint32_t toff = is_dc ? bi.x : bi.y;
+        uint32_t e = __ldg(tab_words + toff + (hi >> (32 - JB_LUT_BITS)));
+        if ((e & 0xFFu) == 0) {
+            e = jb_huff32_escape(reinterpret_cast<const JbHuffTable32 *>(tab_words + toff), e, hi >> 16);
+            if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
+                err |= JB_ST_BAD_CODE;
+                e = is_dc ? 0x01000101u : 0x40000101u;
+            }
+        }
+        const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
+        const uint32_t s = total - len;
+        // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
+        const uint32_t x = __funnelshift_l(lo, hi, len);
+        const uint32_t neg = ~(uint32_t)((int32_t)x >> 31); // all ones when the leading magnitude bit is 0
+        const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+        int v = (int)((t ^ neg) - neg);
+        hi = __funnelshift_lc(lo, hi, total);
+        lo = __funnelshift_lc(0u, lo, total);
+        n -= (int)total;
+        used += total;
+        const uint32_t pos = min(k + run, 63u);
+        if (is_dc) { v += pred; pred = v; }
+        if (s != 0 || is_dc) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
+        k += adv;
+        if (k >= 64) {
+            // block complete: one full 128-byte line to the coefficient store, slot cleared for the next block
+            uint4 *sp = reinterpret_cast<uint4 *>(st);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint4 q = sp[i];
+                sp[i] = make_uint4(0, 0, 0, 0);
+                gptr[i] = q;
+            }
+            gptr += 8;
+            left--;
+            k = 0;
+            b = b + 1 == bpm ? 0 : b + 1;
+            const uint4 ni = __ldg(&im->binfo[b]);
+            if (ni.z != bi.z) { // DC predictors are per component (:187-196)
+                int *pp = reinterpret_cast<int *>(st + 128);
+                pp[bi.z] = pred;
+                pred = pp[ni.z];
+            }
+            bi = ni;
+        }
+    }
+    // bits consumed beyond the real data => "The bit stream ended prematurely."
+    if (used > d.nbits) err |= JB_ST_PREMATURE_END;
+    // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may remain before
+    // the marker (fill bytes were dropped by K0b like FillBuffer does)
+    else if ((d.flags & 1u) && (d.nbits - used >= 8 || !(d.flags & 2u))) err |= JB_ST_EXPECT_RST;
+    if (err) atomicOr(status + d.image, err);
+}

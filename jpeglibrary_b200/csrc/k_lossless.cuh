@@ -1,0 +1,176 @@
+// k_lossless.cuh -- K1d/K5: lossless (SOF3) Huffman frames.
+//
+// Replaces JpegHuffmanLosslessScanDecoder.ProcessScan (ScanDecoder/JpegHuffmanLosslessScanDecoder.cs:52-205),
+// ReadSampleLossless (:207-223) and the JpegPartialScanlineAllocator flush with pixel replication
+// (JpegPartialScanlineAllocator.cs:103-220).
+//
+//   jb_k1d_lossless_entropy  one thread per (image, restart segment): Huffman-decode the difference of every
+//                            sample of the segment's MCUs into the component planes (mod 2^16, as the reference's
+//                            (short) cast makes the reconstruction arithmetic modular)
+//   jb_k1d_lossless_predict  one thread per (image, component): raster-order reconstruction with the reference's
+//                            predictor selection rules, which are a pure function of the sample position:
+//                            first MCU row or first MCU after a restart -> 1-D/initial rules (:109-139),
+//                            first MCU column -> Rb (:141-144), else predictor Ss (:145-159)
+//   jb_k5_lossless_output    replicate to full resolution + the same sinks as K2 (planar int16 / YCbCr888 / RGB)
+#pragma once
+#include "jb_device.cuh"
+#include "k_entropy_decode.cuh"
+#include "k_idct_color.cuh"
+
+#define JB_MAX_COMPONENTS_DEV 4
+
+__global__ void __launch_bounds__(32)
+jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                        const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
+                        const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
+                        int16_t *__restrict__ store, uint32_t *__restrict__ status, int lanes_per_warp)
+{
+    const uint32_t image = image_list[blockIdx.y];
+    const JbDevImage &im = images[image];
+    const int lane = threadIdx.x;
+    if (lane >= lanes_per_warp) return;
+    const uint32_t seg = blockIdx.x * lanes_per_warp + lane;
+    if (seg >= im.nseg) return;
+    const JbScanResult sr = scanres[image];
+    const uint32_t *mk = marks + im.mark_base;
+    const uint8_t *data = arena + im.data_off;
+    const uint32_t per_seg = im.dri ? im.dri : im.total_mcus;
+    const uint32_t first = seg * per_seg, count = min(per_seg, im.total_mcus - first);
+    uint32_t start = 0, err = 0;
+    if (seg > 0) {
+        if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
+        else { atomicOr(status + image, JB_ST_EXPECT_RST); return; }
+    }
+    const uint32_t stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
+    JbBitReader br;
+    br.init(data, start, stop);
+    int16_t *base = store + im.coef_off * 64;
+    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(tables);
+    for (uint32_t u = first; u < first + count && !err; u++) {
+        const uint32_t row = u / im.mcus_per_line, col = u - row * im.mcus_per_line;
+        for (int b = 0; b < im.bpm; b++) { // blk_comp lists the scan's components, h*v samples each, in scan order
+            const int c = im.blk_comp[b];
+            const int h = im.comp_h[c], bi = b - im.comp_blk_off[c];
+            const int x = bi % h, y = bi / h;
+            br.ensure32();
+            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)im.table_index[im.blk_dc[b]] * sizeof(JbHuffTable)),
+                                        br.peek16());
+            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; break; }
+            br.skip(e & 0xFF);
+            const int t = (int)(e >> 8);
+            int d = 0;
+            if (t == 16) d = 32768;
+            else if (t > 16) { err |= JB_ST_BAD_CODE; break; }
+            else if (t != 0) d = jb_extend((int)br.take(t), t);
+            base[(size_t)im.comp_plane_off[c] * 64 + (size_t)(row * im.comp_v[c] + y) * im.comp_plane_w[c] + col * h + x] = (int16_t)d;
+        }
+    }
+    if (br.n < br.pad) err |= JB_ST_PREMATURE_END;
+    if (!err && im.dri != 0 && count == per_seg) {
+        const int real = br.n - br.pad;
+        uint32_t p = br.pos;
+        while (p < stop && data[p] == 0xFF) p++;
+        bool marker_ok = seg < sr.nmarkers;
+        if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u;
+        if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
+    }
+    if (err) atomicOr(status + image, err);
+}
+
+__device__ __forceinline__ int jb_lossless_px(int predictor, int ra, int rb, int rc)
+{
+    switch (predictor) {
+    case 1: return ra;
+    case 2: return rb;
+    case 3: return rc;
+    case 4: return ra + rb - rc;
+    case 5: return ra + ((rb - rc) >> 1);
+    case 6: return rb + ((ra - rc) >> 1);
+    case 7: return (ra + rb) >> 1;
+    default: return 0;
+    }
+}
+
+// One warp per (image, component).  The predictors only look at the left, upper and upper-left neighbours, so
+// 32 consecutive rows are reconstructed as a wavefront: lane l handles row r0 + l and runs l columns behind lane
+// l - 1, whose last two outputs arrive by shuffle (Rb, Rc); Ra is the lane's own previous output.
+__global__ void __launch_bounds__(32 * JB_MAX_COMPONENTS_DEV)
+jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                        int16_t *__restrict__ store)
+{
+    const JbDevImage &im = images[image_list[blockIdx.x]];
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (c >= im.ncomp) return;
+    const int h = im.comp_h[c], v = im.comp_v[c];
+    const int w = (int)im.comp_plane_w[c], rows = (int)im.mcus_per_col * v, cols = (int)im.mcus_per_line * h;
+    int16_t *plane = store + im.coef_off * 64 + (size_t)im.comp_plane_off[c] * 64;
+    const int predictor = im.ll_predictor, initial = im.ll_initial;
+    const uint32_t dri = im.dri, mpl = im.mcus_per_line;
+    for (int r0 = 0; r0 < rows; r0 += 32) {
+        const int cy = r0 + lane;
+        const bool rowok = cy < rows;
+        int16_t *line = plane + (size_t)cy * w;
+        const int row = cy / v, y = cy - row * v;
+        int ra = 0, rb = 0, rc = 0, out = 0;
+        for (int t = 0; t < cols + 31; t++) {
+            int above = __shfl_up_sync(0xFFFFFFFFu, out, 1);
+            const int cx = t - lane;
+            const bool act = rowok && cx >= 0 && cx < cols;
+            if (lane == 0) above = (act && cy > 0) ? (int)__ldcg(line - w + cx) : 0; // last row of the previous band
+            rc = rb;
+            rb = above;
+            if (act) {
+                const int col = cx / h, x = cx - col * h;
+                const bool after_restart = dri > 0 && ((uint32_t)row * mpl + (uint32_t)col) % dri == 0;
+                int pred;
+                if (row == 0 || after_restart) { // :109-139
+                    if (col == 0 && x == 0) pred = initial;
+                    else pred = jb_lossless_px(predictor, ra, y == 0 ? initial : rb, y == 0 ? initial : rc);
+                } else if (col == 0) {           // :141-144
+                    pred = rb;
+                } else {                         // :145-159
+                    pred = jb_lossless_px(predictor, ra, rb, rc);
+                }
+                out = (int16_t)(line[cx] + pred);
+                line[cx] = (int16_t)out;
+                ra = out;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// one thread per output pixel
+__global__ void __launch_bounds__(256)
+jb_k5_lossless_output(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                      const int16_t *__restrict__ store)
+{
+    const JbDevImage &im = images[image_list[blockIdx.y]];
+    const int W = im.width, H = im.height;
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= (uint32_t)W * H) return;
+    const int yy = i / W, x = i - yy * W;
+    int s[4] = {0, 0, 0, 0};
+    for (int c = 0; c < im.ncomp; c++) {
+        const int hs = im.hmax / im.comp_h[c], vs = im.vmax / im.comp_v[c];
+        s[c] = store[im.coef_off * 64 + (size_t)im.comp_plane_off[c] * 64 + (size_t)(yy / vs) * im.comp_plane_w[c] + x / hs];
+    }
+    uint8_t *out = reinterpret_cast<uint8_t *>(im.out_ptr);
+    const uint64_t pitch = im.out_pitch;
+    const int fmt = im.out_format;
+    if (fmt == 3) {
+        for (int c = 0; c < im.ncomp; c++) reinterpret_cast<int16_t *>(out + ((uint64_t)c * H + yy) * pitch)[x] = (int16_t)s[c];
+        return;
+    }
+    const int pshift = im.precision > 8 ? im.precision - 8 : 0;
+    const int yv = jb_clamp255(s[0] >> pshift);
+    const int cb = im.ncomp == 3 ? jb_clamp255(s[1] >> pshift) : 128;
+    const int cr = im.ncomp == 3 ? jb_clamp255(s[2] >> pshift) : 128;
+    const int bpp = fmt == 1 ? 4 : 3;
+    uint8_t *dst = out + (uint64_t)yy * pitch + (uint64_t)x * bpp;
+    if (fmt == 2) { dst[0] = (uint8_t)yv; dst[1] = (uint8_t)cb; dst[2] = (uint8_t)cr; return; }
+    int r, g, b;
+    jb_ycc_to_rgb(yv, cb, cr, r, g, b);
+    dst[0] = (uint8_t)r; dst[1] = (uint8_t)g; dst[2] = (uint8_t)b;
+    if (bpp == 4) dst[3] = 255;
+}

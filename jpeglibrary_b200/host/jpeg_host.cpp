@@ -202,7 +202,7 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
                 if (td > 3 || ta > 3) return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse scan header.");
                 s.dc_table[i] = (int16_t)huff_latest[0][td];
                 s.ac_table[i] = (int16_t)huff_latest[1][ta];
-                if (!qt_present[comp_tq[found]])
+                if (im.sof != 3 && !qt_present[comp_tq[found]]) // lossless frames carry no DQT
                     return perr(JB_ERR_INVALID_DATA, seg_at, "Quantization table of component is not defined.");
                 // table the component is rendered with: baseline = at its scan; progressive = slot state
                 slot_comp[i] = found;

@@ -226,6 +226,9 @@ typedef struct {
     dec_component slots[JO_MAX_COMP];
     int slot_valid[JO_MAX_COMP];
     int16_t dummy[64];
+    /* lossless (SOF3): component sample planes at component resolution */
+    int16_t *ll_plane[JO_MAX_COMP];
+    int ll_w[JO_MAX_COMP], ll_h[JO_MAX_COMP];
     int err;
 } dec_ctx;
 
@@ -576,6 +579,115 @@ static int scan_progressive(dec_ctx *c, const jo_scan_info *s)
     return JO_OK;
 }
 
+/* ---- lossless: ScanDecoder/JpegHuffmanLosslessScanDecoder.cs:52-223 ----------- */
+/* ReadSampleLossless :207-223 */
+static int read_sample_lossless(dec_ctx *c, bit_reader *r, const huff_table *t)
+{
+    int v = decode_huff(c, r, t);
+    if (v == 16) return 32768;
+    if (v != 0) return receive_extend(c, r, v);
+    return 0;
+}
+
+static int scan_lossless(dec_ctx *c, const jo_scan_info *s)
+{
+    jo_image *im = c->img;
+    dec_component comps[JO_MAX_COMP];
+    int n = init_components(c, s, comps);
+    for (int i = 0; i < n; i++)
+        if (!comps[i].dc) return fail(c, JO_ERR_INVALID_DATA, "Huffman table of component is not defined.");
+    const int mpl = (im->width + im->hmax - 1) / im->hmax, mpc = (im->height + im->vmax - 1) / im->vmax; /* :33-34 */
+    for (int ci = 0; ci < im->ncomp; ci++) {
+        int hs = im->hmax / im->comp_h[ci], vs = im->vmax / im->comp_v[ci];
+        c->ll_w[ci] = (im->width + hs - 1) / hs;   /* JpegPartialScanlineAllocator.cs:44-45 */
+        c->ll_h[ci] = (im->height + vs - 1) / vs;
+        /* the reference indexes scanline[colMcu*h + x] / GetScanlineSpan(rowMcu*v + y): frames whose MCU grid
+           overhangs the component planes throw there */
+        if (mpl * im->comp_h[ci] > c->ll_w[ci] || mpc * im->comp_v[ci] > c->ll_h[ci])
+            return fail(c, JO_ERR_INVALID_OP, "lossless MCU grid overhangs the component plane (ArgumentOutOfRange in the reference)");
+        if (!c->ll_plane[ci]) c->ll_plane[ci] = calloc((size_t)c->ll_w[ci] * c->ll_h[ci], sizeof(int16_t));
+        if (!c->ll_plane[ci]) return fail(c, JO_ERR_NOMEM, "out of memory");
+    }
+    bit_reader r;
+    br_init(&r, c->data + s->entropy_offset, c->data + c->len);
+    const int restart = s->restart_interval;
+    int before = restart;
+    const int predictor = s->ss;
+    const int initial = 1 << (im->precision - s->al - 1);
+    for (int row = 0; row < mpc; row++) {
+        for (int col = 0; col < mpl; col++) {
+            for (int k = 0; k < n; k++) {
+                dec_component *comp = &comps[k];
+                const int ci = comp->component_index, h = comp->h, v = comp->v;
+                const int ox = col * h, oy = row * v, w = c->ll_w[ci];
+                for (int y = 0; y < v; y++) {
+                    int16_t *line = c->ll_plane[ci] + (size_t)(oy + y) * w;
+                    int16_t *last = (y == 0 && row == 0) ? NULL : c->ll_plane[ci] + (size_t)(oy + y - 1) * w;
+                    for (int x = 0; x < h; x++) {
+                        int d = read_sample_lossless(c, &r, comp->dc);
+                        if (c->err) return c->err;
+                        if (row == 0 || (restart > 0 && before == restart)) {
+                            if (col == 0 && x == 0) d += initial;
+                            else {
+                                int ra = line[ox + x - 1];
+                                int rb = y == 0 ? initial : last[ox + x];
+                                int rc = y == 0 ? initial : last[ox + x - 1];
+                                switch (predictor) {
+                                case 1: d += ra; break;
+                                case 2: d += rb; break;
+                                case 3: d += rc; break;
+                                case 4: d += ra + rb - rc; break;
+                                case 5: d += ra + ((rb - rc) >> 1); break;
+                                case 6: d += rb + ((ra - rc) >> 1); break;
+                                case 7: d += (ra + rb) >> 1; break;
+                                default: break;
+                                }
+                            }
+                        } else if (col == 0) {
+                            d += last[ox + x];
+                        } else {
+                            int ra = line[ox + x - 1], rb = last[ox + x], rc = last[ox + x - 1];
+                            switch (predictor) {
+                            case 1: d += ra; break;
+                            case 2: d += rb; break;
+                            case 3: d += rc; break;
+                            case 4: d += ra + rb - rc; break;
+                            case 5: d += ra + ((rb - rc) >> 1); break;
+                            case 6: d += rb + ((ra - rc) >> 1); break;
+                            case 7: d += (ra + rb) >> 1; break;
+                            default: break;
+                            }
+                        }
+                        line[ox + x] = (int16_t)d;
+                    }
+                }
+            }
+            if (restart > 0 && (--before) == 0) {
+                br_align(&r);
+                int m = br_read_marker(&r);
+                if (m == 0xD9) return JO_OK;
+                if (!(m >= 0xD0 && m <= 0xD7)) return fail(c, JO_ERR_INVALID_OP, "Expect restart marker.");
+                before = restart;
+            }
+        }
+    }
+    return JO_OK;
+}
+
+/* JpegPartialScanlineAllocator.FlushCore/WriteBlock :103-220: component planes -> full resolution by replication */
+static void render_lossless_planes(dec_ctx *c)
+{
+    jo_image *im = c->img;
+    const int W = im->width, H = im->height;
+    for (int ci = 0; ci < im->ncomp; ci++) {
+        int hs = im->hmax / im->comp_h[ci], vs = im->vmax / im->comp_v[ci];
+        int16_t *plane = im->planes + (size_t)ci * W * H;
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++)
+                plane[(size_t)y * W + x] = c->ll_plane[ci] ? c->ll_plane[ci][(size_t)(y / vs) * c->ll_w[ci] + x / hs] : 0;
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* FastFloatingPointDCT.cs:79-185 -- one 1-D pass over "rows" V0..V7 of s,      */
 /* element-wise per column (the Vector4 lanes).                                */
@@ -923,11 +1035,11 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
         size_t blen = seglen - 2;
         pos += seglen;
         switch (m) {
-        case 0xC0: case 0xC1: case 0xC2:
+        case 0xC0: case 0xC1: case 0xC2: case 0xC3:
             rc = parse_frame(c, m - 0xC0, body, blen);
             break;
-        case 0xC3: case 0xC9: case 0xCA:
-            rc = fail(c, JO_ERR_UNSUPPORTED, "SOF3/SOF9/SOF10 are outside the oracle's scope.");
+        case 0xC9: case 0xCA:
+            rc = fail(c, JO_ERR_UNSUPPORTED, "SOF9/SOF10 (arithmetic coding) are outside the oracle's scope.");
             break;
         case 0xC5: case 0xC6: case 0xC7: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
             rc = fail(c, JO_ERR_INVALID_DATA, "This type of JPEG stream is not supported.");
@@ -956,7 +1068,7 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
             if (rc) break;
             s->entropy_offset = pos;
             img->nscans++;
-            rc = img->sof == 2 ? scan_progressive(c, s) : scan_baseline(c, s);
+            rc = img->sof == 2 ? scan_progressive(c, s) : img->sof == 3 ? scan_lossless(c, s) : scan_baseline(c, s);
             /* the marker loop re-finds the next marker by scanning the entropy data */
             break;
         }
@@ -998,7 +1110,8 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
         img->planes = malloc(n * img->ncomp * sizeof(int16_t));
         if (!img->planes) rc = fail(c, JO_ERR_NOMEM, "out of memory");
         else {
-            render_planes(c);
+            if (img->sof == 3) render_lossless_planes(c);
+            else render_planes(c);
             if ((flags & JO_WANT_RGB) && (img->ncomp == 1 || img->ncomp == 3)) {
                 img->ycbcr = malloc(3 * n);
                 img->rgb = malloc(3 * n);
@@ -1008,6 +1121,7 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
         }
     }
 done:
+    for (int i = 0; i < JO_MAX_COMP; i++) free(c->ll_plane[i]);
     free(c);
     return rc;
 }

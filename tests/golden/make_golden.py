@@ -32,7 +32,7 @@ FILES = [
     "huffman_sequential/testorig12.jpg",
     "huffman_progressive/progress.jpg",
     "huffman_progressive/yellowcat_progressive_restart.jpg",
-]
+] + ["huffman_lossless/lossless%d_s22.jpg" % i for i in range(1, 8)]
 IDENTIFY = {  # MetadataIdentifyTests.cs
     "cramps.jpg": dict(Width=800, Height=607, NumberOfComponents=1, Precision=8, JpegStreamSize=137766),
     "testorig12.jpg": dict(Width=227, Height=149, NumberOfComponents=3, Precision=12, JpegStreamSize=12394),

@@ -54,3 +54,159 @@ def encode_jpeg(rgb, quality=85, subsampling="4:2:0", restart_rows=0, restart_bl
 
 def synth_jpeg(i, width, height, **kw):
     return encode_jpeg(synth_rgb(i, width, height), **kw)
+
+
+# --------------------------------------------------------------------------------------------------
+# Lossless (SOF3) test streams.  Pillow cannot write them, so this is a small encoder that inverts the
+# decoder rules of ScanDecoder/JpegHuffmanLosslessScanDecoder.cs:84-178 (prediction from already coded
+# samples, first-row / first-column / after-restart special cases, modulo-2^16 differences, category 16
+# = 32768 without extra bits).  Data generation only; the oracle is the checker.
+# --------------------------------------------------------------------------------------------------
+def _lossless_predict(predictor, ra, rb, rc):
+    if predictor == 1:
+        return ra
+    if predictor == 2:
+        return rb
+    if predictor == 3:
+        return rc
+    if predictor == 4:
+        return ra + rb - rc
+    if predictor == 5:
+        return ra + ((rb - rc) >> 1)
+    if predictor == 6:
+        return rb + ((ra - rc) >> 1)
+    if predictor == 7:
+        return (ra + rb) >> 1
+    return 0
+
+
+def _s16(v):
+    v &= 0xFFFF
+    return v - 0x10000 if v & 0x8000 else v
+
+
+def encode_lossless(planes, precision=8, predictor=1, point_transform=0, sampling=None, restart=0):
+    """planes: list of 2-D integer arrays at COMPONENT resolution (already divided by 2^Pt), component c of
+    size (mcus_y * v_c, mcus_x * h_c).  Returns a complete SOF3 stream with one interleaved scan."""
+    n = len(planes)
+    sampling = sampling or [(1, 1)] * n
+    hmax = max(h for h, _ in sampling)
+    vmax = max(v for _, v in sampling)
+    mcus_y = planes[0].shape[0] // sampling[0][1]
+    mcus_x = planes[0].shape[1] // sampling[0][0]
+    width, height = mcus_x * hmax, mcus_y * vmax
+    for p, (h, v) in zip(planes, sampling):
+        assert p.shape == (mcus_y * v, mcus_x * h)
+    # one table for every component: categories 0..16, all 5-bit codes except the last two (6 bits)
+    bits = [0, 0, 0, 0, 15, 2] + [0] * 10
+    vals = list(range(17))
+    codes, code, k = {}, 0, 0
+    for ln in range(1, 17):
+        for _ in range(bits[ln - 1]):
+            codes[vals[k]] = (code, ln)
+            code += 1
+            k += 1
+        code <<= 1
+    initial = 1 << (precision - point_transform - 1)
+    rec = [np.zeros(p.shape, dtype=np.int64) for p in planes]  # what the decoder will hold (as int16)
+    out = bytearray()
+    acc = nbits = 0
+
+    def put(value, length):
+        nonlocal acc, nbits
+        acc = (acc << length) | (value & ((1 << length) - 1))
+        nbits += length
+        while nbits >= 8:
+            b = (acc >> (nbits - 8)) & 0xFF
+            out.append(b)
+            if b == 0xFF:
+                out.append(0)
+            nbits -= 8
+        acc &= (1 << nbits) - 1
+
+    def flush():
+        nonlocal acc, nbits
+        if nbits:
+            put((1 << (8 - nbits)) - 1, 8 - nbits)
+
+    before, rst = restart, 0
+    for row in range(mcus_y):
+        for col in range(mcus_x):
+            for c in range(n):
+                h, v = sampling[c]
+                for y in range(v):
+                    cy = row * v + y
+                    for x in range(h):
+                        cx = col * h + x
+                        r = rec[c]
+                        if row == 0 or (restart > 0 and before == restart):
+                            if col == 0 and x == 0:
+                                pred = initial
+                            else:
+                                ra = r[cy, cx - 1]
+                                rb = initial if y == 0 else r[cy - 1, cx]
+                                rc = initial if y == 0 else r[cy - 1, cx - 1]
+                                pred = _lossless_predict(predictor, ra, rb, rc)
+                        elif col == 0:
+                            pred = r[cy - 1, cx]
+                        else:
+                            pred = _lossless_predict(predictor, r[cy, cx - 1], r[cy - 1, cx], r[cy - 1, cx - 1])
+                        want = _s16(int(planes[c][cy, cx]))
+                        diff = (want - int(pred)) & 0xFFFF
+                        if diff == 0x8000:
+                            put(*codes[16])
+                        else:
+                            d = _s16(diff)
+                            cat = abs(d).bit_length()
+                            put(*codes[cat])
+                            if cat:
+                                put(d if d >= 0 else d - 1, cat)
+                        r[cy, cx] = want
+            if restart > 0:
+                before -= 1
+                if before == 0 and not (row == mcus_y - 1 and col == mcus_x - 1):
+                    flush()
+                    out += bytes([0xFF, 0xD0 + (rst & 7)])
+                    rst += 1
+                    before = restart
+    flush()
+
+    def seg(marker, payload):
+        return bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + payload
+
+    s = bytearray(b"\xff\xd8")
+    sof = bytes([precision]) + height.to_bytes(2, "big") + width.to_bytes(2, "big") + bytes([n])
+    for c, (h, v) in enumerate(sampling):
+        sof += bytes([c + 1, (h << 4) | v, 0])
+    s += seg(0xC3, sof)
+    s += seg(0xC4, bytes([0x00]) + bytes(bits) + bytes(vals))
+    if restart:
+        s += seg(0xDD, restart.to_bytes(2, "big"))
+    sos = bytes([n])
+    for c in range(n):
+        sos += bytes([c + 1, 0x00])
+    s += seg(0xDA, sos + bytes([predictor, 0, point_transform]))
+    s += out + b"\xff\xd9"
+    return bytes(s)
+
+
+def synth_lossless(i, width, height, precision=8, predictor=1, point_transform=0, sampling=None, restart=0, ncomp=3):
+    """SOF3 stream of synthetic content; width/height are at full resolution and must be MCU multiples."""
+    rng = np.random.default_rng(2000 + i)
+    sampling = sampling or [(1, 1)] * ncomp
+    hmax = max(h for h, _ in sampling)
+    vmax = max(v for _, v in sampling)
+    assert width % hmax == 0 and height % vmax == 0
+    base = synth_rgb(i, width, height).astype(np.int64)
+    planes = []
+    for c, (h, v) in enumerate(sampling):
+        p = base[::vmax // v, ::hmax // h, c % 3]
+        p = (p << max(0, precision - 8)) >> point_transform if precision >= 8 else p >> (8 - precision + point_transform)
+        if precision > 8:
+            p = p + rng.integers(0, 1 << (precision - 8 - point_transform), size=p.shape)
+        planes.append(np.ascontiguousarray(p))
+    blob = encode_lossless(planes, precision, predictor, point_transform, sampling, restart)
+    # what a decoder must return: the coded samples as int16, replicated to full resolution
+    full = np.stack([np.repeat(np.repeat(p, vmax // v, axis=0), hmax // h, axis=1)
+                     for p, (h, v) in zip(planes, sampling)]).astype(np.uint16).view(np.int16)
+    return blob, full

@@ -148,9 +148,9 @@ def test_batch_of_mixed_images_device_resident():
     with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
         b.run()
         assert b.status() == [0] * len(blobs)
-        # restart scan + segment Huffman + self-sync chain for lake.jpg (unstuff, guess round, 5 sync
-        # rounds, prefix sums, write) + one IDCT/colour launch per sampling layout (4:2:0, 4:4:4)
-        assert b.launch_count() == 1 + 1 + (4 + 5) + 2
+        # restart scan + segment un-stuff + segment Huffman + self-sync chain for lake.jpg (unstuff, guess
+        # round, 5 sync rounds, prefix sums, write) + one IDCT/colour launch per sampling layout (4:2:0, 4:4:4)
+        assert b.launch_count() == 1 + 2 + (4 + 5) + 2
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run
@@ -277,3 +277,55 @@ def test_progressive_and_sequential_in_one_batch():
         assert b.status() == [0] * len(blobs)
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
+
+
+# ------------------------------------------------------------------------------------------ lossless (SOF3)
+LOSSLESS_ASSETS = ["lossless%d_s22.jpg" % i for i in range(1, 8)]
+
+
+@pytest.mark.parametrize("name", LOSSLESS_ASSETS)
+def test_lossless_golden_assets_bit_exact(name, golden):
+    """SOF3 output must be bit-exact (north_star): predictors 1..7 of the reference's own assets."""
+    blob = golden_bytes(name)
+    planes = gpu_planes(blob)
+    assert hashlib.sha256(np.ascontiguousarray(planes).tobytes()).hexdigest() == golden["assets"][name]["planes_i16_sha256"]
+    o = O.decode(blob)
+    assert np.array_equal(planes, o.planes)
+    assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
+    assert np.array_equal(gpu_pixels(blob), o.rgb)
+
+
+LOSSLESS_SHAPES = [
+    dict(width=40, height=24, predictor=1),
+    dict(width=33, height=17, predictor=4, restart=5, ncomp=1),
+    dict(width=48, height=32, predictor=7, sampling=[(2, 2), (1, 1), (1, 1)], restart=6),
+    dict(width=30, height=20, predictor=5, precision=16),
+    dict(width=30, height=20, predictor=6, precision=12, point_transform=2),
+    dict(width=200, height=150, predictor=2, restart=200),              # several 32-row bands, one interval per row
+    dict(width=256, height=96, predictor=3, sampling=[(2, 1), (1, 1), (1, 1)], restart=64),
+    dict(width=1, height=1, predictor=1, ncomp=1),
+]
+
+
+@pytest.mark.parametrize("kw", LOSSLESS_SHAPES, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_lossless_synthetic(kw):
+    kw = dict(kw)
+    w, h = kw.pop("width"), kw.pop("height")
+    blob, coded = synth.synth_lossless(5, w, h, **kw)
+    assert J.Parsed(blob).desc.sof == 3
+    planes = gpu_planes(blob)
+    assert np.array_equal(planes, coded)                      # round trip: what was coded comes back
+    assert np.array_equal(planes, O.decode(blob, want_rgb=False).planes)
+
+
+def test_lossless_missing_restart_marker():
+    blob = bytearray(synth.synth_lossless(5, 64, 32, restart=16)[0])
+    i = blob.find(b"\xff\xd1")
+    blob[i + 1] = 0x00
+    with pytest.raises(O.OracleError):
+        O.decode(bytes(blob))
+    dec = J.JpegDecoder()
+    dec.SetInput(bytes(blob))
+    dec.SetOutputWriter(J.CudaOutputWriter(np.zeros((3, 32, 64), np.int16), J.JB_OUT_PLANAR_I16))
+    with pytest.raises((J.InvalidOperationException, J.InvalidDataException)):
+        dec.Decode()

@@ -14,7 +14,8 @@ import pytest
 import oracle_ffi as O
 from conftest import GOLDEN_DIR, REFERENCE_ASSETS, golden_bytes
 
-ASSETS = ["cramps.jpg", "lake.jpg", "testorig12.jpg", "progress.jpg", "yellowcat_progressive_restart.jpg"]
+ASSETS = ["cramps.jpg", "lake.jpg", "testorig12.jpg", "progress.jpg", "yellowcat_progressive_restart.jpg"] + \
+    ["lossless%d_s22.jpg" % i for i in range(1, 8)]
 
 
 def expected16(planes, precision):
@@ -85,3 +86,22 @@ def test_oracle_errors():
     with pytest.raises(O.OracleError) as e:
         O.decode(bytes(blob))
     assert e.value.code in (-1, -2)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(width=40, height=24, predictor=1),
+    dict(width=33, height=17, predictor=4, restart=5, ncomp=1),
+    dict(width=48, height=32, predictor=7, sampling=[(2, 2), (1, 1), (1, 1)], restart=6),
+    dict(width=30, height=20, predictor=5, precision=16),            # category 16 / (short) wrap-around
+    dict(width=30, height=20, predictor=6, precision=12, point_transform=2),
+], ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_oracle_decodes_synthetic_lossless_streams(kw):
+    """The test-only SOF3 generator (tests/synth.py) and the oracle (pinned by the 7 lossless goldens) agree:
+    decoding returns the samples that were coded, replicated to full resolution."""
+    import synth
+    kw = dict(kw)
+    w, h = kw.pop("width"), kw.pop("height")
+    blob, coded = synth.synth_lossless(3, w, h, **kw)
+    d = O.decode(blob, want_rgb=False)
+    assert (d.sof, d.width, d.height) == (3, w, h)
+    assert np.array_equal(d.planes, coded)
