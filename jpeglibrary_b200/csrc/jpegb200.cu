@@ -1078,7 +1078,13 @@ static int launch_kernels(jb_batch *b)
         jb_k0b_unstuff_segments<<<ugrid, JB_K0B_WARPS * 32, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_arena,
                                                                     b->d_marks, b->d_scan, b->d_clean_seg, b->d_segs, b->d_status);
         mark("jb_k0b_unstuff_segments");
-        jb_k1_huff_flat<<<(b->total_segs + JB_K1F_THREADS - 1) / JB_K1F_THREADS, JB_K1F_THREADS, 0, st>>>(
+        // CTA size: all segments resident in one wave when the batch allows it (one CTA per SM, up to 1024 lanes)
+        const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+        uint32_t threads = ((b->total_segs + sms - 1) / sms + 31) / 32 * 32;
+        threads = std::min<uint32_t>(JB_K1F_MAX_THREADS, std::max<uint32_t>(128, threads));
+        const size_t smem = jb_k1f_smem_bytes((int)threads);
+        JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1_huff_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb_k1f_smem_bytes(JB_K1F_MAX_THREADS)));
+        jb_k1_huff_flat<<<(b->total_segs + threads - 1) / threads, threads, smem, st>>>(
             b->d_images, b->d_segs, b->total_segs, b->d_tables32, reinterpret_cast<const uint32_t *>(b->d_clean_seg), b->d_coef,
             b->d_status);
         mark("jb_k1_huff_segments");

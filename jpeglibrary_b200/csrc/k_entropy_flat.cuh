@@ -172,98 +172,183 @@ __device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32
 
 // ---------------------------------------------------------------------------------------------
 // K1: one thread per restart segment of the batch.  Each lane assembles its current block in a private
-// 128-byte shared-memory slot (zig-zag order) and moves it to the coefficient store as one full line
-// when the block is complete; the per-symbol step is branch-free apart from that.
+// 128-byte shared-memory slot (zig-zag order); the per-symbol step is branch-free.  Completed blocks are
+// moved to the coefficient store by the whole warp -- 8 lanes x 16 bytes per block, up to four blocks per
+// round -- so that the load/store pipe sees full-width instructions (a per-lane copy issues 24 LSU
+// instructions for the two lanes that finish in an average iteration).
+// The Huffman look-up tables of the CTA's images live in shared memory (a look-up that misses L1 would
+// stall all 32 lanes for an L2 round trip on nearly every symbol); a CTA whose images use more than
+// JB_K1F_TABLES distinct tables reads the others through the read-only path.
+// The CTA size is chosen at launch so that all segments of a batch are resident in one wave when possible.
 // ---------------------------------------------------------------------------------------------
-#define JB_K1F_THREADS 128
-#define JB_K1F_SLOT 144 // 128 bytes of coefficients + 16 bytes holding the four DC predictors
+#define JB_K1F_MAX_THREADS 1024
+#define JB_K1F_TABLES 4
+#define JB_K1F_TABLE_WORDS (JB_LUT_SIZE + JB_LUT2_SUBTABLES * 64)
+// per-lane slot: 128 B coefficients | 16 B DC predictors | 10 x {DC table, AC table | component << 14} (uint16 pairs)
+#define JB_K1F_SLOT 192
+#define JB_K1F_NOTAB 0x3FFFu // table reference: not cached in shared memory
+__host__ __device__ inline size_t jb_k1f_smem_bytes(int threads)
+{
+    return (size_t)JB_K1F_TABLES * JB_K1F_TABLE_WORDS * 4 + (size_t)threads * (JB_K1F_SLOT + 4);
+}
 
-__global__ void __launch_bounds__(JB_K1F_THREADS)
+__global__ void __launch_bounds__(JB_K1F_MAX_THREADS, 1)
 jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restrict__ segs, uint32_t nsegs,
                 const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ clean_words,
                 int16_t *__restrict__ coef, uint32_t *__restrict__ status)
 {
-    __shared__ __align__(16) uint8_t s_slots[JB_K1F_THREADS * JB_K1F_SLOT];
-    const uint32_t g = blockIdx.x * JB_K1F_THREADS + threadIdx.x;
-    uint8_t *st = s_slots + threadIdx.x * JB_K1F_SLOT;
+    extern __shared__ __align__(16) uint8_t jb_k1f_smem[];
+    __shared__ uint32_t s_tab_id[JB_K1F_TABLES];
+    __shared__ uint32_t s_ntab;
+    const int tid = threadIdx.x, nthreads = blockDim.x, lane = tid & 31;
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(jb_k1f_smem);
+    uint8_t *s_slots = jb_k1f_smem + JB_K1F_TABLES * JB_K1F_TABLE_WORDS * 4;
+    uint32_t *s_img = reinterpret_cast<uint32_t *>(s_slots + (size_t)nthreads * JB_K1F_SLOT);
+    uint8_t *st = s_slots + tid * JB_K1F_SLOT;
+    uint8_t *warp_slots = s_slots + (tid & ~31) * JB_K1F_SLOT;
+    const uint32_t g = blockIdx.x * nthreads + tid;
 #pragma unroll
-    for (int i = 0; i < JB_K1F_SLOT / 16; i++) reinterpret_cast<uint4 *>(st)[i] = make_uint4(0, 0, 0, 0);
-    if (g >= nsegs) return;
-    const JbSegDesc d = segs[g];
+    for (int i = 0; i < 9; i++) reinterpret_cast<uint4 *>(st)[i] = make_uint4(0, 0, 0, 0);
+    JbSegDesc d;
+    d.nblocks = 0; d.image = 0xFFFFFFFFu;
+    if (g < nsegs) d = segs[g];
+    s_img[tid] = d.nblocks ? d.image : 0xFFFFFFFFu;
+    __syncthreads();
+    if (tid == 0) { // the CTA's table set: segments are numbered image-major, so images come in runs
+        uint32_t n = 0, prev = 0xFFFFFFFFu;
+        for (int i = 0; i < nthreads; i++) {
+            const uint32_t im = s_img[i];
+            if (im == prev || im == 0xFFFFFFFFu) continue;
+            prev = im;
+            const int nt = images[im].ntables;
+            for (int k = 0; k < nt; k++) {
+                const uint32_t id = images[im].table_index[k];
+                uint32_t j = 0;
+                while (j < n && s_tab_id[j] != id) j++;
+                if (j == n && n < JB_K1F_TABLES) s_tab_id[n++] = id;
+            }
+        }
+        s_ntab = n;
+    }
+    __syncthreads();
+    const uint32_t ntab = s_ntab;
+    for (uint32_t t = 0; t < ntab; t++) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables + s_tab_id[t]); // lut and lut2 are the first members
+        uint4 *dst = reinterpret_cast<uint4 *>(s_tab + t * JB_K1F_TABLE_WORDS);
+        for (int i = tid; i < JB_K1F_TABLE_WORDS / 4; i += nthreads) dst[i] = __ldg(src + i);
+    }
     uint32_t left = d.nblocks;
-    if (left == 0) return;
-    const JbDevImage *im = images + d.image;
-    const uint32_t bpm = im->bpm;
+    const JbDevImage *im = images + (left ? d.image : 0);
+    const uint32_t bpm = left ? im->bpm : 0;
+    uint32_t *s_bi = reinterpret_cast<uint32_t *>(st + 144);
+    for (uint32_t k = 0; k < bpm; k++) {
+        const uint4 bi = __ldg(&im->binfo[k]);
+        const uint32_t ids[2] = {bi.x / (uint32_t)(sizeof(JbHuffTable32) / 4), bi.y / (uint32_t)(sizeof(JbHuffTable32) / 4)};
+        uint32_t ref[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            uint32_t j = 0;
+            while (j < ntab && s_tab_id[j] != ids[c]) j++;
+            ref[c] = j < ntab ? j * JB_K1F_TABLE_WORDS : JB_K1F_NOTAB;
+        }
+        s_bi[k] = ref[0] | ((ref[1] | (bi.z << 14)) << 16);
+    }
+    __syncthreads();
     const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
 
     // bit window: hi:lo hold n valid bits, left-aligned; wnext is the prefetched next word
     const uint32_t wend = d.word_off + ((d.nbits + 31) >> 5) + 2; // an all-ones padding word
     uint32_t wofs = d.word_off;
-    uint32_t hi = __ldg(clean_words + wofs), lo = __ldg(clean_words + wofs + 1), wnext = __ldg(clean_words + wofs + 2);
+    uint32_t hi = 0, lo = 0, wnext = 0;
+    if (left) {
+        hi = __ldg(clean_words + wofs); lo = __ldg(clean_words + wofs + 1); wnext = __ldg(clean_words + wofs + 2);
+    }
     wofs = min(wofs + 3, wend);
     int n = 64;
     uint32_t used = 0, err = 0;
 
     uint32_t b = 0, k = 0; // block-in-mcu; next zig-zag index (0: the DC symbol comes next)
     int pred = 0;
-    uint4 bi = __ldg(&im->binfo[0]); // x: DC table (word offset), y: AC table, z: component
-    uint4 *gptr = reinterpret_cast<uint4 *>(coef + d.coef_block * 64);
+    uint32_t bi = s_bi[0]; // low half: DC table, high half: AC table | component << 14 (shared-memory word offsets)
+    uint64_t gptr = reinterpret_cast<uint64_t>(coef + d.coef_block * 64);
 
-    while (left != 0) {
-        if (n < 32) {
-            hi |= wnext >> n;
-            lo |= __funnelshift_r(0u, wnext, n);
-            n += 32;
-            wnext = __ldg(clean_words + wofs);
-            wofs = min(wofs + 1, wend);
-        }
-        const bool is_dc = k == 0;
-        const uint32_t toff = is_dc ? bi.x : bi.y;
-        uint32_t e = __ldg(tab_words + toff + (hi >> (32 - JB_LUT_BITS)));
-        if ((e & 0xFFu) == 0) {
-            e = jb_huff32_escape(reinterpret_cast<const JbHuffTable32 *>(tab_words + toff), e, hi >> 16);
-            if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
-                err |= JB_ST_BAD_CODE;
-                e = is_dc ? 0x01000101u : 0x40000101u;
+    while (__any_sync(0xFFFFFFFFu, left != 0)) {
+        if (left != 0) {
+            if (n < 32) {
+                hi |= wnext >> n;
+                lo |= __funnelshift_r(0u, wnext, n);
+                n += 32;
+                wnext = __ldg(clean_words + wofs);
+                wofs = min(wofs + 1, wend);
             }
-        }
-        const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
-        const uint32_t s = total - len;
-        // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
-        const uint32_t x = __funnelshift_l(lo, hi, len);
-        const uint32_t neg = ~(uint32_t)((int32_t)x >> 31); // all ones when the leading magnitude bit is 0
-        const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
-        int v = (int)((t ^ neg) - neg);
-        hi = __funnelshift_lc(lo, hi, total);
-        lo = __funnelshift_lc(0u, lo, total);
-        n -= (int)total;
-        used += total;
-        const uint32_t pos = min(k + run, 63u);
-        if (is_dc) { v += pred; pred = v; }
-        if (s != 0 || is_dc) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
-        k += adv;
-        if (k >= 64) {
-            // block complete: one full 128-byte line to the coefficient store, slot cleared for the next block
-            uint4 *sp = reinterpret_cast<uint4 *>(st);
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint4 q = sp[i];
-                sp[i] = make_uint4(0, 0, 0, 0);
-                gptr[i] = q;
+            const bool is_dc = k == 0;
+            const uint32_t toff = (is_dc ? bi : (bi >> 16)) & 0x3FFFu;
+            uint32_t e = 0;
+            if (toff != JB_K1F_NOTAB) e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
+            if ((e & 0xFFu) == 0) {
+                uint32_t e2 = 0;
+                if (e != 0) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
+                if (e2 == 0) { // table not cached, or a code longer than 16 bits / not in the second level
+                    const uint4 gi = __ldg(&im->binfo[b]);
+                    const uint32_t goff = is_dc ? gi.x : gi.y;
+                    if (toff == JB_K1F_NOTAB) e = __ldg(tab_words + goff + (hi >> (32 - JB_LUT_BITS)));
+                    e2 = (e & 0xFFu) ? e : jb_huff32_escape(reinterpret_cast<const JbHuffTable32 *>(tab_words + goff), e, hi >> 16);
+                }
+                e = e2;
+                if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
+                    err |= JB_ST_BAD_CODE;
+                    e = is_dc ? 0x01000101u : 0x40000101u;
+                }
             }
-            gptr += 8;
+            const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
+            const uint32_t s = total - len;
+            // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
+            const uint32_t x = __funnelshift_l(lo, hi, len);
+            const uint32_t neg = ~(uint32_t)((int32_t)x >> 31); // all ones when the leading magnitude bit is 0
+            const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+            int v = (int)((t ^ neg) - neg);
+            hi = __funnelshift_lc(lo, hi, total);
+            lo = __funnelshift_lc(0u, lo, total);
+            n -= (int)total;
+            used += total;
+            const uint32_t pos = min(k + run, 63u);
+            if (is_dc) { v += pred; pred = v; }
+            if (s != 0 || is_dc) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
+            k += adv;
+        }
+        // ---- completed blocks leave the SM as full 128-byte lines: lanes 8g..8g+7 move the g-th finished lane's block
+        const bool finished = k >= 64;
+        uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
+        while (fin) {
+            const uint32_t f1 = fin & (fin - 1), f2 = f1 & (f1 - 1), f3 = f2 & (f2 - 1);
+            const uint32_t grp = lane >> 3;
+            const uint32_t pick = grp == 0 ? fin : grp == 1 ? f1 : grp == 2 ? f2 : f3;
+            const int L = __ffs(pick) - 1; // -1: nothing for this group
+            const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)gptr, L & 31);
+            const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(gptr >> 32), L & 31);
+            if (L >= 0) {
+                uint4 *sp = reinterpret_cast<uint4 *>(warp_slots + L * JB_K1F_SLOT) + (lane & 7);
+                const uint4 q = *sp;
+                *sp = make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4 *>(((uint64_t)ghi << 32) | glo)[lane & 7] = q;
+            }
+            fin = f3 & (f3 - 1);
+        }
+        if (finished) {
+            gptr += 128;
             left--;
             k = 0;
             b = b + 1 == bpm ? 0 : b + 1;
-            const uint4 ni = __ldg(&im->binfo[b]);
-            if (ni.z != bi.z) { // DC predictors are per component (:187-196)
+            const uint32_t ni = s_bi[b];
+            if ((ni ^ bi) >> 30) { // DC predictors are per component (:187-196)
                 int *pp = reinterpret_cast<int *>(st + 128);
-                pp[bi.z] = pred;
-                pred = pp[ni.z];
+                pp[bi >> 30] = pred;
+                pred = pp[ni >> 30];
             }
             bi = ni;
         }
     }
+    if (d.nblocks == 0) return;
     // bits consumed beyond the real data => "The bit stream ended prematurely."
     if (used > d.nbits) err |= JB_ST_PREMATURE_END;
     // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may remain before
