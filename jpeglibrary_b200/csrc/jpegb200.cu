@@ -26,6 +26,7 @@
 #include "k_entropy_progressive.cuh"
 #include "k_idct_color.cuh"
 #include "k_idct_color_fast.cuh"
+#include "k_idct_color_warp.cuh"
 #include "k_lossless.cuh"
 
 struct jb_ctx {
@@ -208,9 +209,12 @@ struct ImagePlan {
 
 
 // Which K2 kernel renders this image: >= 0 fast variant (fmt * 8 + shape), -1 generic.
-static int k2_variant(const JbDevImage &d)
+static int k2_variant(const JbDevImage &d, const std::vector<uint16_t> &quant)
 {
     if (d.precision != 8 || d.out_format > JB_OUT_YCBCR888) return -1;
+    // the fast kernel dequantises through the fp32 mantissa: exact for |q * c| < 2^22
+    for (int i = 0; i < d.ncomp * 64; i++)
+        if (quant[d.quant_off + i] > 255) return -1;
     int shape;
     if (d.ncomp == 1) {
         if (d.comp_h[0] != 1 || d.comp_v[0] != 1) return -1;
@@ -229,8 +233,8 @@ static int k2_variant(const JbDevImage &d)
 
 static uint32_t k2_fast_tiles(const JbDevImage &d)
 {
-    const uint32_t tile_mcus = JB_K2F_BLOCKS / d.bpm;
-    return (d.mcus_per_line + tile_mcus - 1) / tile_mcus * d.mcus_per_col;
+    const uint32_t unit_mcus = d.ncomp == 1 ? 16 : 32 / d.bpm; // MCUs a warp renders per iteration (k_idct_color_warp.cuh)
+    return (d.mcus_per_line + unit_mcus - 1) / unit_mcus * d.mcus_per_col;
 }
 
 template <int FMT>
@@ -238,11 +242,11 @@ static void launch_k2_fast_fmt(int shape, dim3 grid, cudaStream_t st, const JbDe
                                const uint16_t *q, const uint32_t *list, int tpc)
 {
     switch (shape) {
-    case 0: jb_k2_idct_color_fast<FMT, 1, 1, 1><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
-    case 1: jb_k2_idct_color_fast<FMT, 3, 1, 1><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
-    case 2: jb_k2_idct_color_fast<FMT, 3, 2, 1><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
-    case 3: jb_k2_idct_color_fast<FMT, 3, 1, 2><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
-    default: jb_k2_idct_color_fast<FMT, 3, 2, 2><<<grid, JB_K2F_THREADS, 0, st>>>(im, coef, q, list, tpc); break;
+    case 0: jb_k2_idct_color_warp<FMT, 1, 1, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
+    case 1: jb_k2_idct_color_warp<FMT, 3, 1, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
+    case 2: jb_k2_idct_color_warp<FMT, 3, 2, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
+    case 3: jb_k2_idct_color_warp<FMT, 3, 1, 2><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
+    default: jb_k2_idct_color_warp<FMT, 3, 2, 2><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
     }
 }
 
@@ -901,7 +905,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             b->total_segs += pl.dev.nseg;
         }
         if (pl.out.format != JB_OUT_COEFFICIENTS && pl.dev.sof != 3) {
-            const int variant = k2_variant(pl.dev);
+            const int variant = k2_variant(pl.dev, b->quant);
             jb_batch::RenderGroup *g = nullptr;
             for (auto &x : b->groups)
                 if (x.variant == variant) g = &x;
@@ -1199,10 +1203,11 @@ static int launch_render(jb_batch *b, int *launches)
     for (const auto &g : b->groups) {
         const uint32_t *list = b->d_image_list + g.list_off;
         if (g.variant >= 0) {
-            // a CTA walks `tpc` consecutive strips so that its per-thread constants are set up once
+            // a warp walks `tpc` consecutive units so that its per-lane constants are set up once
             uint64_t total = (uint64_t)g.max_tiles * g.images.size();
-            int tpc = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16)));
-            dim3 grid((g.max_tiles + tpc - 1) / tpc, (unsigned)g.images.size());
+            int tpc = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16 * 8)));
+            const uint32_t per_cta = (uint32_t)tpc * JB_K2W_WARPS;
+            dim3 grid((g.max_tiles + per_cta - 1) / per_cta, (unsigned)g.images.size());
             launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc);
         } else {
             dim3 grid(g.max_tiles, (unsigned)g.images.size());

@@ -1,0 +1,335 @@
+// k_idct_color_warp.cuh -- K2 (fast path, second generation): dequantise + un-zigzag + fp32 IDCT + level
+// shift + clamp + chroma replication + YCbCr->RGB for 8-bit frames (same coverage and the same bit-exact
+// arithmetic as k_idct_color_fast.cuh; see the notes there and in k_idct_color.cuh).
+//
+// What changed, and why (profiles/r1d_decode.txt): the first generation spent 2/3 of its issue slots around
+// the fixed fp32 arithmetic -- gathers, two shared-memory transposes per block, uniform-datapath address
+// arithmetic -- and its top stall was the CTA barrier between phases.  Here
+//   * ONE THREAD OWNS ONE 8x8 BLOCK: its 64 coefficients arrive as eight 128-bit shared-memory loads, the
+//     un-zigzag is a compile-time register permutation, both IDCT passes run in registers (16 independent
+//     1-D transforms: plenty of ILP), no transposes;
+//   * A WARP OWNS A UNIT of 32/BPM consecutive MCUs (4:2:0: 5 MCUs = 30 blocks = 80x16 pixels) end to end:
+//     load -> IDCT -> colour -> store, synchronised with __syncwarp only, so warps drift freely and hide each
+//     other's latencies;
+//   * the unit's coefficient blocks are contiguous in the store (MCU scan order) and come in by 16-byte
+//     cp.async copies that are issued one unit ahead; RGB rows leave as cp.async.bulk shared->global copies
+//     issued by 16 lanes in parallel;
+//   * dequantisation is an integer multiply-add onto the magic number 1.5*2^23 followed by one fp32 subtract
+//     ((float)(q*c) exactly, for |q*c| < 2^22), which keeps the conversions off the quarter-rate XU pipe.
+#pragma once
+#include "jb_device.cuh"
+#include "k_idct_color.cuh"
+#include "k_idct_color_fast.cuh"
+
+#define JB_K2W_WARPS 4
+#define JB_K2W_RAW_STRIDE 144 // bytes per block in the raw tile: 128 + 16 so that the eight 128-bit loads of the
+                              // eight lanes of a quarter warp hit different banks
+
+// natural (row-major) index -> zig-zag index (JpegZigZag.cs:15-25), usable as a compile-time constant
+__host__ __device__ constexpr int jb_nat2zz_c(int n)
+{
+    constexpr int t[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                           41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                           46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+    return t[n];
+}
+
+template <int R>
+__device__ __forceinline__ void jb_k2w_row(const uint32_t (&pk)[32], const uint32_t *__restrict__ qn, float (&d1)[64])
+{
+    // natural row R: dequantise (DequantizeBlockAndUnZigZag, JpegScanDecoder.cs:50-62) and transform along the row
+    const uint4 q0 = *reinterpret_cast<const uint4 *>(qn + R * 8);
+    const uint4 q1 = *reinterpret_cast<const uint4 *>(qn + R * 8 + 4);
+    const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float y[8], d[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int z = jb_nat2zz_c(R * 8 + e);
+        const uint32_t w = pk[z >> 1];
+        const int c = (z & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xFFFFu);
+        // (float)(q*c): the integer product lands in the mantissa of 1.5*2^23, the subtraction is exact
+        y[e] = __fsub_rn(__int_as_float(c * (int)q[e] + 0x4B400000), 12582912.0f);
+    }
+    jb_idct8(y, d);
+#pragma unroll
+    for (int e = 0; e < 8; e++) d1[R * 8 + e] = d[e];
+}
+
+template <int C>
+__device__ __forceinline__ void jb_k2w_col(const float (&d1)[64], uint32_t (&rows)[16])
+{
+    float y[8], d[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) y[k] = d1[k * 8 + C];
+    jb_idct8(y, d); // along column C
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // MultiplyInplace(0.125) + MathF.Round (half-to-even) + level shift in one fma, then clamp to 0..255
+        const float t = __fmaf_rn(d[k], 0.125f, 12582912.0f + 128.0f);
+        const uint32_t v = (uint32_t)__viaddmin_s32_relu(__float_as_int(t), -0x4B400000, 255);
+        if ((C & 3) == 0) rows[k * 2 + (C >> 2)] = v;
+        else rows[k * 2 + (C >> 2)] |= v << (8 * (C & 3));
+    }
+}
+
+// FMT: 0 RGB24, 1 RGBA32, 2 YCBCR888.  HS,VS: chroma subsampling (1 or 2).  NC: 1 or 3 components.
+template <int FMT, int NC, int HS, int VS>
+__global__ void __launch_bounds__(JB_K2W_WARPS * 32, 4)
+jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__restrict__ coef,
+                      const uint16_t *__restrict__ quant, const uint32_t *__restrict__ image_list,
+                      int units_per_warp)
+{
+    constexpr int BPM = NC == 1 ? 1 : (HS * VS + 2);
+    constexpr int UM = NC == 1 ? 16 : 32 / BPM; // MCUs per unit (grey: 16, which keeps the tiles inside 48 KB)
+    constexpr int NB = UM * BPM;                // blocks (= busy lanes) per unit
+    constexpr int TW = UM * 8 * HS;             // unit width in pixels (luma)
+    constexpr int TH = 8 * VS;                  // unit height
+    constexpr int CW = UM * 8;                  // chroma plane width
+    constexpr int BPP = FMT == 1 ? 4 : 3;
+    constexpr int ROW_BYTES = TW * BPP;
+    constexpr int CHUNKS = NB * 8;              // 16-byte pieces of the unit's coefficient blocks
+    static_assert(ROW_BYTES % 16 == 0, "rows must be bulk-copyable");
+
+    __shared__ __align__(16) uint8_t s_raw[JB_K2W_WARPS][NB * JB_K2W_RAW_STRIDE];
+    __shared__ __align__(16) uint8_t s_y[JB_K2W_WARPS][TW * TH];
+    __shared__ __align__(16) uint8_t s_c[JB_K2W_WARPS][2][NC == 1 ? 16 : CW * 8];
+    __shared__ __align__(128) uint8_t s_stage[JB_K2W_WARPS][TH * ROW_BYTES];
+    __shared__ __align__(16) uint32_t s_qn[NC * 64]; // quantisers in NATURAL order, one table per component
+    __shared__ JbDevImage s_im;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t image = image_list[blockIdx.y];
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
+        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K2W_WARPS * 32) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32)
+        s_qn[i] = quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
+    __syncthreads();
+
+    // ---- per-lane constants: which block of the unit this lane owns
+    const int j = lane;                         // block index inside the unit (scan order)
+    const int m = j / BPM, b = j - m * BPM;
+    int c = 0, bx, by;                          // component, block position inside the unit's component plane
+    if (NC == 1 || b < HS * VS) {
+        bx = m * HS + (b % HS);
+        by = b / HS;
+    } else {
+        c = b - HS * VS + 1;
+        bx = m;
+        by = 0;
+    }
+    const uint32_t *qn = s_qn + c * 64;
+    const int W = s_im.width, H = s_im.height;
+    const uint32_t mcus_per_line = s_im.mcus_per_line;
+    const uint32_t upr = (mcus_per_line + UM - 1) / UM; // units per MCU row
+    const uint32_t nunits = upr * s_im.mcus_per_col;
+    uint8_t *const out = reinterpret_cast<uint8_t *>(s_im.out_ptr);
+    const uint64_t pitch = s_im.out_pitch;
+    const bool bulk_ok = ((s_im.out_ptr | pitch) & 15u) == 0;
+    const bool planar = s_im.planar != 0;
+    uint8_t *raw = s_raw[wid];
+    uint8_t *yplane = s_y[wid];
+    uint8_t *stage = s_stage[wid];
+
+    uint32_t unit = (blockIdx.x * JB_K2W_WARPS + wid) * (uint32_t)units_per_warp;
+    const uint32_t unit_end = min(unit + (uint32_t)units_per_warp, nunits);
+    if (unit >= unit_end) return;
+    uint32_t mcu_row = unit / upr;
+    uint32_t ucol = unit - mcu_row * upr;
+
+    // 16-byte cp.async copies of one unit's coefficient blocks into the padded raw tile
+    auto fetch = [&](uint32_t row, uint32_t uc) {
+        const uint32_t col0 = uc * UM;
+        const int nm = (int)min((uint32_t)UM, mcus_per_line - col0);
+#pragma unroll
+        for (int i0 = 0; i0 < CHUNKS; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < CHUNKS) {
+                const int jb = i >> 3, part = i & 7;
+                const int mm = jb / BPM;
+                if (mm < nm) {
+                    uint64_t blk;
+                    if (!planar) blk = s_im.coef_off + ((uint64_t)row * mcus_per_line + col0) * BPM + jb;
+                    else {
+                        const int bb = jb - mm * BPM;
+                        int cc = 0, pbx, pby;
+                        if (NC == 1 || bb < HS * VS) { pbx = mm * HS + (bb % HS); pby = bb / HS; }
+                        else { cc = bb - HS * VS + 1; pbx = mm; pby = 0; }
+                        blk = s_im.coef_off + s_im.comp_plane_off[cc] +
+                              (uint64_t)(row * (cc == 0 ? VS : 1) + pby) * s_im.comp_plane_w[cc] + (col0 * (cc == 0 ? HS : 1) + pbx);
+                    }
+                    const void *src = reinterpret_cast<const uint8_t *>(coef + blk * 64) + part * 16;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(jb_smem_u32(raw + jb * JB_K2W_RAW_STRIDE + part * 16)),
+                                 "l"(src)
+                                 : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(mcu_row, ucol);
+    bool bulk_pending = false;
+
+    for (; unit < unit_end; unit++) {
+        const uint32_t mcu_col0 = ucol * UM;
+        const int nmcu = (int)min((uint32_t)UM, mcus_per_line - mcu_col0);
+        const bool valid = j < NB && m < nmcu;
+        const uint32_t cur_row = mcu_row;
+        if (++ucol == upr) { ucol = 0; mcu_row++; }
+
+        // ------------------------------------------------ phase A: one block per lane, all in registers
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        uint32_t pk[32];
+        if (valid) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(raw + j * JB_K2W_RAW_STRIDE);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint4 v = rp[i];
+                pk[4 * i] = v.x; pk[4 * i + 1] = v.y; pk[4 * i + 2] = v.z; pk[4 * i + 3] = v.w;
+            }
+        }
+        __syncwarp();
+        if (unit + 1 < unit_end) fetch(mcu_row, ucol); // the raw tile is free again: prefetch the next unit
+        if (valid) {
+            float d1[64];
+            jb_k2w_row<0>(pk, qn, d1); jb_k2w_row<1>(pk, qn, d1); jb_k2w_row<2>(pk, qn, d1); jb_k2w_row<3>(pk, qn, d1);
+            jb_k2w_row<4>(pk, qn, d1); jb_k2w_row<5>(pk, qn, d1); jb_k2w_row<6>(pk, qn, d1); jb_k2w_row<7>(pk, qn, d1);
+            uint32_t rows[16];
+            jb_k2w_col<0>(d1, rows); jb_k2w_col<1>(d1, rows); jb_k2w_col<2>(d1, rows); jb_k2w_col<3>(d1, rows);
+            jb_k2w_col<4>(d1, rows); jb_k2w_col<5>(d1, rows); jb_k2w_col<6>(d1, rows); jb_k2w_col<7>(d1, rows);
+            uint8_t *pl = (c == 0 ? yplane + (by * 8) * TW : s_c[wid][c - 1]) + bx * 8;
+            const int pp = c == 0 ? TW : CW;
+#pragma unroll
+            for (int k = 0; k < 8; k++) *reinterpret_cast<uint2 *>(pl + k * pp) = make_uint2(rows[2 * k], rows[2 * k + 1]);
+        }
+        // the staging tile must be free: the previous unit's bulk stores have to have read it
+        if (bulk_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+
+        // ------------------------------------------------ phase B: 4-pixel groups -> staging tile
+        constexpr int GROUPS = TW / 4;
+        constexpr int ITEMS = GROUPS * (TH / VS);
+#pragma unroll 1
+        for (int item = lane; item < ITEMS; item += 32) {
+            const int cy = item / GROUPS, gx = (item - cy * GROUPS) * 4;
+            JbChromaTerms t0, t1, t2, t3;
+            uint32_t cb4 = 0x80808080u, cr4 = 0x80808080u; // grey: Cb = Cr = 128 (DecodeAction.cs:58-66)
+            if (NC == 3) {
+                if (HS == 2) {
+                    cb4 = *reinterpret_cast<const uint16_t *>(s_c[wid][0] + cy * CW + (gx >> 1));
+                    cr4 = *reinterpret_cast<const uint16_t *>(s_c[wid][1] + cy * CW + (gx >> 1));
+                } else {
+                    cb4 = *reinterpret_cast<const uint32_t *>(s_c[wid][0] + cy * CW + gx);
+                    cr4 = *reinterpret_cast<const uint32_t *>(s_c[wid][1] + cy * CW + gx);
+                }
+            }
+            if (FMT != 2) {
+                t0 = jb_chroma_terms(cb4 & 0xFF, cr4 & 0xFF);
+                t1 = jb_chroma_terms((cb4 >> 8) & 0xFF, (cr4 >> 8) & 0xFF);
+                if (HS == 1) {
+                    t2 = jb_chroma_terms((cb4 >> 16) & 0xFF, (cr4 >> 16) & 0xFF);
+                    t3 = jb_chroma_terms(cb4 >> 24, cr4 >> 24);
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < VS; rr++) {
+                const int py = cy * VS + rr;
+                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(yplane + py * TW + gx);
+                uint32_t o0, o1, o2, o3 = 0;
+                if (FMT == 2) {
+                    uint32_t cbx, crx; // 4 chroma bytes for the 4 pixels
+                    if (HS == 2) {
+                        cbx = __byte_perm(cb4, 0, 0x1100);
+                        crx = __byte_perm(cr4, 0, 0x1100);
+                    } else {
+                        cbx = cb4;
+                        crx = cr4;
+                    }
+                    // bytes: y0 cb0 cr0 y1 | cb1 cr1 y2 cb2 | cr2 y3 cb3 cr3
+                    const uint32_t a = __byte_perm(y4, cbx, 0x1040);
+                    o0 = __byte_perm(a, crx, 0x3410);
+                    const uint32_t bq = __byte_perm(cbx, crx, 0x2051);
+                    o1 = __byte_perm(bq, y4, 0x3610);
+                    const uint32_t cq = __byte_perm(crx, cbx, 0x3702);
+                    o2 = __byte_perm(cq, y4, 0x3270);
+                } else {
+                    const uint32_t y01 = __byte_perm(y4, 0, 0x4140); // two 16-bit lanes: y0, y1
+                    const uint32_t y23 = __byte_perm(y4, 0, 0x4342);
+                    uint32_t r01, g01, b01, r23, g23, b23;
+                    if (HS == 2) {
+                        r01 = jb_addclamp2(y01, t0.r2); g01 = jb_addclamp2(y01, t0.g2); b01 = jb_addclamp2(y01, t0.b2);
+                        r23 = jb_addclamp2(y23, t1.r2); g23 = jb_addclamp2(y23, t1.g2); b23 = jb_addclamp2(y23, t1.b2);
+                    } else {
+                        const uint32_t ra = __byte_perm(t0.r2, t1.r2, 0x5410), ga = __byte_perm(t0.g2, t1.g2, 0x5410),
+                                       ba = __byte_perm(t0.b2, t1.b2, 0x5410);
+                        const uint32_t rb = __byte_perm(t2.r2, t3.r2, 0x5410), gb = __byte_perm(t2.g2, t3.g2, 0x5410),
+                                       bb = __byte_perm(t2.b2, t3.b2, 0x5410);
+                        r01 = jb_addclamp2(y01, ra); g01 = jb_addclamp2(y01, ga); b01 = jb_addclamp2(y01, ba);
+                        r23 = jb_addclamp2(y23, rb); g23 = jb_addclamp2(y23, gb); b23 = jb_addclamp2(y23, bb);
+                    }
+                    if (FMT == 0) {
+                        // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+                        const uint32_t rg01 = __byte_perm(r01, g01, 0x6240);
+                        const uint32_t rg23 = __byte_perm(r23, g23, 0x6240);
+                        o0 = __byte_perm(rg01, b01, 0x2410);
+                        const uint32_t t = __byte_perm(rg01, b01, 0x0063);
+                        o1 = __byte_perm(t, rg23, 0x5410);
+                        o2 = __byte_perm(b23, rg23, 0x2760);
+                    } else {
+                        o0 = __byte_perm(__byte_perm(r01, g01, 0x0040), b01, 0x0410) | 0xFF000000u;
+                        o1 = __byte_perm(__byte_perm(r01, g01, 0x0062), b01, 0x0610) | 0xFF000000u;
+                        o2 = __byte_perm(__byte_perm(r23, g23, 0x0040), b23, 0x0410) | 0xFF000000u;
+                        o3 = __byte_perm(__byte_perm(r23, g23, 0x0062), b23, 0x0610) | 0xFF000000u;
+                    }
+                }
+                uint32_t *dst = reinterpret_cast<uint32_t *>(stage + py * ROW_BYTES + gx * BPP);
+                if (BPP == 4) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(o0, o1, o2, o3);
+                } else {
+                    dst[0] = o0; dst[1] = o1; dst[2] = o2;
+                }
+            }
+        }
+        // ------------------------------------------------ phase C: staging tile -> global
+        const int x0 = mcu_col0 * 8 * HS, y0 = cur_row * TH;
+        const int rows_out = min(TH, H - y0);
+        const int row_bytes = min(ROW_BYTES, (W - x0) * BPP);
+        if (bulk_ok && row_bytes == ROW_BYTES) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane < rows_out) {
+                uint8_t *g = out + (uint64_t)(y0 + lane) * pitch + (uint64_t)x0 * BPP;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(g),
+                             "r"(jb_smem_u32(stage + lane * ROW_BYTES)), "n"(ROW_BYTES)
+                             : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            bulk_pending = true;
+        } else {
+            __syncwarp();
+            const int words = row_bytes >> 2;
+            for (int i = lane; i < rows_out * words; i += 32) {
+                const int rr = i / words, wv = i - rr * words;
+                uint8_t *g = out + (uint64_t)(y0 + rr) * pitch + (uint64_t)x0 * BPP;
+                const uint32_t v = *reinterpret_cast<const uint32_t *>(stage + rr * ROW_BYTES + wv * 4);
+                if ((reinterpret_cast<uint64_t>(g) & 3u) == 0) reinterpret_cast<uint32_t *>(g)[wv] = v;
+                else {
+                    g[wv * 4] = (uint8_t)v; g[wv * 4 + 1] = (uint8_t)(v >> 8);
+                    g[wv * 4 + 2] = (uint8_t)(v >> 16); g[wv * 4 + 3] = (uint8_t)(v >> 24);
+                }
+            }
+            const int tail = row_bytes & 3;
+            if (tail)
+                for (int i = lane; i < rows_out * tail; i += 32) {
+                    const int rr = i / tail, tb = (row_bytes & ~3) + i % tail;
+                    out[(uint64_t)(y0 + rr) * pitch + (uint64_t)x0 * BPP + tb] = stage[rr * ROW_BYTES + tb];
+                }
+            __syncwarp(); // the staging tile is reused by the next unit
+        }
+    }
+    if (bulk_pending) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
