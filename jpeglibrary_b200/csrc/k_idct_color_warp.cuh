@@ -14,8 +14,9 @@
 //   * the unit's coefficient blocks are contiguous in the store (MCU scan order) and come in by 16-byte
 //     cp.async copies that are issued one unit ahead; RGB rows leave as cp.async.bulk shared->global copies
 //     issued by 16 lanes in parallel;
-//   * dequantisation is an integer multiply-add onto the magic number 1.5*2^23 followed by one fp32 subtract
-//     ((float)(q*c) exactly, for |q*c| < 2^22), which keeps the conversions off the quarter-rate XU pipe.
+//   * dequantisation converts the 16-bit halves of the packed coefficient pairs directly (I2F.S16 on the XU
+//     pipe, which nothing else in this kernel uses) and multiplies by the fp32 quantiser: two issue slots per
+//     coefficient, none of them on the ALU pipe, which is the busiest one here.
 #pragma once
 #include "jb_device.cuh"
 #include "k_idct_color.cuh"
@@ -35,20 +36,22 @@ __host__ __device__ constexpr int jb_nat2zz_c(int n)
 }
 
 template <int R>
-__device__ __forceinline__ void jb_k2w_row(const uint32_t (&pk)[32], const uint32_t *__restrict__ qn, float (&d1)[64])
+__device__ __forceinline__ void jb_k2w_row(const uint32_t (&pk)[32], const float *__restrict__ qn, float (&d1)[64])
 {
     // natural row R: dequantise (DequantizeBlockAndUnZigZag, JpegScanDecoder.cs:50-62) and transform along the row
-    const uint4 q0 = *reinterpret_cast<const uint4 *>(qn + R * 8);
-    const uint4 q1 = *reinterpret_cast<const uint4 *>(qn + R * 8 + 4);
-    const uint32_t q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const float4 q0 = *reinterpret_cast<const float4 *>(qn + R * 8);
+    const float4 q1 = *reinterpret_cast<const float4 *>(qn + R * 8 + 4);
+    const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
     float y[8], d[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int z = jb_nat2zz_c(R * 8 + e);
-        const uint32_t w = pk[z >> 1];
-        const int c = (z & 1) ? ((int)w >> 16) : (int)(int16_t)(w & 0xFFFFu);
-        // (float)(q*c): the integer product lands in the mantissa of 1.5*2^23, the subtraction is exact
-        y[e] = __fsub_rn(__int_as_float(c * (int)q[e] + 0x4B400000), 12582912.0f);
+        // (float)(q*c) == fmul(float(q), float(c)): both round the same exact integer once.  The conversion reads
+        // the 16-bit half of the packed pair directly (I2F.S16 on the otherwise idle XU pipe).
+        float cf;
+        if (z & 1) asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, hi; }" : "=f"(cf) : "r"(pk[z >> 1]));
+        else asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, lo; }" : "=f"(cf) : "r"(pk[z >> 1]));
+        y[e] = __fmul_rn(q[e], cf);
     }
     jb_idct8(y, d);
 #pragma unroll
@@ -94,7 +97,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     __shared__ __align__(16) uint8_t s_y[JB_K2W_WARPS][TW * TH];
     __shared__ __align__(16) uint8_t s_c[JB_K2W_WARPS][2][NC == 1 ? 16 : CW * 8];
     __shared__ __align__(128) uint8_t s_stage[JB_K2W_WARPS][TH * ROW_BYTES];
-    __shared__ __align__(16) uint32_t s_qn[NC * 64]; // quantisers in NATURAL order, one table per component
+    __shared__ __align__(16) float s_qn[NC * 64]; // quantisers in NATURAL order, one table per component
     __shared__ JbDevImage s_im;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -106,7 +109,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     }
     __syncthreads();
     for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32)
-        s_qn[i] = quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
+        s_qn[i] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
     __syncthreads();
 
     // ---- per-lane constants: which block of the unit this lane owns
@@ -121,7 +124,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         bx = m;
         by = 0;
     }
-    const uint32_t *qn = s_qn + c * 64;
+    const float *qn = s_qn + c * 64;
     const int W = s_im.width, H = s_im.height;
     const uint32_t mcus_per_line = s_im.mcus_per_line;
     const uint32_t upr = (mcus_per_line + UM - 1) / UM; // units per MCU row
@@ -140,27 +143,32 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     uint32_t mcu_row = unit / upr;
     uint32_t ucol = unit - mcu_row * upr;
 
-    // 16-byte cp.async copies of one unit's coefficient blocks into the padded raw tile
+    // 16-byte cp.async copies of one unit's coefficient blocks into the padded raw tile.  In the interleaved
+    // store the unit's blocks are contiguous: chunk i = 32 r + lane comes from base + 16 i and goes to
+    // 144 (i / 8) + 16 (i % 8), i.e. both sides advance by a constant per round.
+    const uint32_t raw_lane = jb_smem_u32(raw) + lane * 16 + (lane >> 3) * 16;
     auto fetch = [&](uint32_t row, uint32_t uc) {
         const uint32_t col0 = uc * UM;
         const int nm = (int)min((uint32_t)UM, mcus_per_line - col0);
+        if (!planar) {
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(coef + (s_im.coef_off + ((uint64_t)row * mcus_per_line + col0) * BPM) * 64) + lane * 16;
+            const int limit = nm * BPM * 8 - lane;
 #pragma unroll
-        for (int i0 = 0; i0 < CHUNKS; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < CHUNKS) {
+            for (int r = 0; r < (CHUNKS + 31) / 32; r++)
+                if (r * 32 < limit)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_lane + r * (4 * JB_K2W_RAW_STRIDE)), "l"(src + r * 512) : "memory");
+        } else {
+#pragma unroll 1
+            for (int i = lane; i < CHUNKS; i += 32) {
                 const int jb = i >> 3, part = i & 7;
                 const int mm = jb / BPM;
                 if (mm < nm) {
-                    uint64_t blk;
-                    if (!planar) blk = s_im.coef_off + ((uint64_t)row * mcus_per_line + col0) * BPM + jb;
-                    else {
-                        const int bb = jb - mm * BPM;
-                        int cc = 0, pbx, pby;
-                        if (NC == 1 || bb < HS * VS) { pbx = mm * HS + (bb % HS); pby = bb / HS; }
-                        else { cc = bb - HS * VS + 1; pbx = mm; pby = 0; }
-                        blk = s_im.coef_off + s_im.comp_plane_off[cc] +
-                              (uint64_t)(row * (cc == 0 ? VS : 1) + pby) * s_im.comp_plane_w[cc] + (col0 * (cc == 0 ? HS : 1) + pbx);
-                    }
+                    const int bb = jb - mm * BPM;
+                    int cc = 0, pbx, pby;
+                    if (NC == 1 || bb < HS * VS) { pbx = mm * HS + (bb % HS); pby = bb / HS; }
+                    else { cc = bb - HS * VS + 1; pbx = mm; pby = 0; }
+                    const uint64_t blk = s_im.coef_off + s_im.comp_plane_off[cc] +
+                                         (uint64_t)(row * (cc == 0 ? VS : 1) + pby) * s_im.comp_plane_w[cc] + (col0 * (cc == 0 ? HS : 1) + pbx);
                     const void *src = reinterpret_cast<const uint8_t *>(coef + blk * 64) + part * 16;
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(jb_smem_u32(raw + jb * JB_K2W_RAW_STRIDE + part * 16)),
                                  "l"(src)
