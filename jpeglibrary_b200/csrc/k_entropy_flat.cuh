@@ -270,6 +270,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     uint32_t b = 0, k = 0; // block-in-mcu; next zig-zag index (0: the DC symbol comes next)
     int pred = 0;
     uint32_t bi = s_bi[0]; // low half: DC table, high half: AC table | component << 14 (shared-memory word offsets)
+    uint32_t tdc = bi & 0x3FFFu, tac = (bi >> 16) & 0x3FFFu;
     uint64_t gptr = reinterpret_cast<uint64_t>(coef + d.coef_block * 64);
 
     while (__any_sync(0xFFFFFFFFu, left != 0)) {
@@ -282,7 +283,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                 wofs = min(wofs + 1, wend);
             }
             const bool is_dc = k == 0;
-            const uint32_t toff = (is_dc ? bi : (bi >> 16)) & 0x3FFFu;
+            const uint32_t toff = is_dc ? tdc : tac;
             uint32_t e = 0;
             if (toff != JB_K1F_NOTAB) e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
             if ((e & 0xFFu) == 0) {
@@ -318,21 +319,23 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
         }
         // ---- completed blocks leave the SM as full 128-byte lines: lanes 8g..8g+7 move the g-th finished lane's block
         const bool finished = k >= 64;
-        uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
-        while (fin) {
-            const uint32_t f1 = fin & (fin - 1), f2 = f1 & (f1 - 1), f3 = f2 & (f2 - 1);
-            const uint32_t grp = lane >> 3;
-            const uint32_t pick = grp == 0 ? fin : grp == 1 ? f1 : grp == 2 ? f2 : f3;
-            const int L = __ffs(pick) - 1; // -1: nothing for this group
-            const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)gptr, L & 31);
-            const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(gptr >> 32), L & 31);
-            if (L >= 0) {
-                uint4 *sp = reinterpret_cast<uint4 *>(warp_slots + L * JB_K1F_SLOT) + (lane & 7);
-                const uint4 q = *sp;
-                *sp = make_uint4(0, 0, 0, 0);
-                reinterpret_cast<uint4 *>(((uint64_t)ghi << 32) | glo)[lane & 7] = q;
-            }
-            fin = f3 & (f3 - 1);
+        const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
+        if (fin) {
+            // every group of 8 lanes moves the finished blocks of its own 8 lanes, one block per round
+            uint32_t mine = (fin >> (lane & 24)) & 0xFFu;
+            do {
+                const int t = 31 - __clz((int)mine); // highest finished lane of the group; -1: none left
+                const int L = (lane & 24) + (t & 7);
+                const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)gptr, L);
+                const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(gptr >> 32), L);
+                if (t >= 0) {
+                    uint4 *sp = reinterpret_cast<uint4 *>(warp_slots + L * JB_K1F_SLOT) + (lane & 7);
+                    const uint4 q = *sp;
+                    *sp = make_uint4(0, 0, 0, 0);
+                    reinterpret_cast<uint4 *>(((uint64_t)ghi << 32) | glo)[lane & 7] = q;
+                }
+                mine &= ~(1u << (t & 31));
+            } while (__any_sync(0xFFFFFFFFu, mine != 0));
         }
         if (finished) {
             gptr += 128;
@@ -346,6 +349,8 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                 pred = pp[ni >> 30];
             }
             bi = ni;
+            tdc = ni & 0x3FFFu;
+            tac = (ni >> 16) & 0x3FFFu;
         }
     }
     if (d.nblocks == 0) return;
