@@ -395,7 +395,7 @@ def main():
     nblocks = (WIDTH // 8) * (HEIGHT // 8) * (3 if args.progressive else 3) // (1 if args.progressive else 2)  # 194 400 for 4K 4:2:0
     alg = {  # ALGORITHMIC bytes per launch, for the whole batch
         "jb_k0_restart_scan": comp_bytes,
-        "jb_k0b_unstuff_segments": 2 * comp_bytes,
+        "jb_k0b_segment_descs": 0,
         "jb_k1_huff_segments": comp_bytes + 128 * nblocks * args.batch,
         "jb_k1b_selfsync_chain": comp_bytes + 128 * nblocks * args.batch,
         "jb_k1_segments+selfsync": comp_bytes + 128 * nblocks * args.batch,

@@ -36,9 +36,8 @@ struct __align__(16) JbDevImage {
     // flat restart-segment decode (K0b/K1): per block-in-mcu x = DC table, y = AC table (32-bit word offsets into
     // the JbHuffTable32 array), z = component
     uint4 binfo[JB_MAX_BLOCKS_PER_MCU];
-    uint64_t clean_off;  // this image's base offset in the clean (un-stuffed) arena
     uint32_t seg_base;   // global index of the image's first restart segment in the batch
-    uint32_t pad4;
+    uint32_t pad4[3];
     // compressed input
     uint64_t data_off;   // offset of the entropy-coded bytes in the device arena (256-B aligned)
     uint32_t data_len;   // upper bound of entropy-coded length (bytes)

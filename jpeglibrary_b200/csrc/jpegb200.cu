@@ -287,7 +287,6 @@ struct jb_batch {
     JbHuffTable32 *d_tables32 = nullptr;
     uint32_t total_segs = 0;
     JbSegDesc *d_segs = nullptr;
-    uint8_t *d_clean_seg = nullptr;
     // progressive frames
     std::vector<uint32_t> prog_images;
     uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1, prog_levels = 0;
@@ -901,7 +900,6 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
             b->seg_images.push_back((uint32_t)i);
             pl.dev.seg_base = b->total_segs;
-            pl.dev.clean_off = pl.dev.data_off + 32ull * b->total_segs;
             b->total_segs += pl.dev.nseg;
         }
         if (pl.out.format != JB_OUT_COEFFICIENTS && pl.dev.sof != 3) {
@@ -987,7 +985,11 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         JB_CUDA_B(cudaMemcpyAsync(b->d_tables32, b->tables32.data(), sizeof(JbHuffTable32) * b->tables32.size(),
                                   cudaMemcpyHostToDevice, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_segs, sizeof(JbSegDesc) * b->total_segs, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_clean_seg, b->arena_bytes + 32ull * b->total_segs + 256, ctx->stream));
+        if (b->arena_bytes >= (1ull << 34)) {
+            ctx->error = "compressed batch larger than 16 GiB";
+            jb_decode_batch_destroy(b);
+            return JB_ERR_NOT_SUPPORTED;
+        }
     }
     JB_CUDA_B(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1), ctx->stream));
@@ -1078,10 +1080,10 @@ static int launch_kernels(jb_batch *b)
     if (!b->seg_images.empty()) {
         // one warp per 32 segments; a CTA never spans images, so pick the CTA size that wastes the
         // fewest warp slots for this batch (at most JB_K1_MAX_WARPS warps)
-        dim3 ugrid((b->max_nseg + JB_K0B_WARPS - 1) / JB_K0B_WARPS, (unsigned)b->seg_images.size());
-        jb_k0b_unstuff_segments<<<ugrid, JB_K0B_WARPS * 32, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_arena,
-                                                                    b->d_marks, b->d_scan, b->d_clean_seg, b->d_segs, b->d_status);
-        mark("jb_k0b_unstuff_segments");
+        dim3 ugrid((b->max_nseg + JB_K0B_THREADS - 1) / JB_K0B_THREADS, (unsigned)b->seg_images.size());
+        jb_k0b_segment_descs<<<ugrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
+                                                              b->d_segs, b->d_status);
+        mark("jb_k0b_segment_descs");
         // CTA size: all segments resident in one wave when the batch allows it (one CTA per SM, up to 1024 lanes)
         const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
         uint32_t threads = ((b->total_segs + sms - 1) / sms + 31) / 32 * 32;
@@ -1089,7 +1091,7 @@ static int launch_kernels(jb_batch *b)
         const size_t smem = jb_k1f_smem_bytes((int)threads);
         JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1_huff_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb_k1f_smem_bytes(JB_K1F_MAX_THREADS)));
         jb_k1_huff_flat<<<(b->total_segs + threads - 1) / threads, threads, smem, st>>>(
-            b->d_images, b->d_segs, b->total_segs, b->d_tables32, reinterpret_cast<const uint32_t *>(b->d_clean_seg), b->d_coef,
+            b->d_images, b->d_segs, b->total_segs, b->d_tables32, reinterpret_cast<const uint32_t *>(b->d_arena), b->d_coef,
             b->d_status);
         mark("jb_k1_huff_segments");
         launches += 2;
@@ -1363,7 +1365,6 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
     if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
     if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);
-    if (b->d_clean_seg) cudaFreeAsync(b->d_clean_seg, b->ctx->stream);
     delete b;
 }
 

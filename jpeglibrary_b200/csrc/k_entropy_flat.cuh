@@ -21,32 +21,29 @@
 
 // one restart segment of the batch, written by K0b
 struct __align__(16) JbSegDesc {
-    uint32_t word_off;   // first 32-bit word of the segment's clean stream
-    uint32_t nbits;      // clean bits in the segment
+    uint32_t word0;      // arena word (4-byte) index of the word that holds the segment's first byte
+    uint32_t lead;       // bytes of that word in front of the segment (0..3)
+    uint32_t nbytes;     // length of the segment in the stuffed stream
     uint32_t nblocks;    // blocks to decode (0: nothing to do)
-    uint32_t flags;      // bit 0: a restart marker / EOI must follow; bit 1: it does
     uint64_t coef_block; // first block of the segment in the coefficient store
     uint32_t image;
-    uint32_t pad;
+    uint32_t flags;      // bit 0: a restart marker / EOI must follow; bit 1: it does
 };
 
-#define JB_K0B_WARPS 4
+#define JB_K0B_THREADS 128
 
-// K0b: one warp per restart segment.  HBM-bound: reads the compressed bytes once, writes them once.
-__global__ void __launch_bounds__(JB_K0B_WARPS * 32)
-jb_k0b_unstuff_segments(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-                        const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
-                        const JbScanResult *__restrict__ scanres, uint8_t *__restrict__ clean,
-                        JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status)
+// K0b: restart-segment descriptors from K0's marker index (one thread per segment; a few microseconds).
+__global__ void __launch_bounds__(JB_K0B_THREADS)
+jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                     const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
+                     JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t seg = blockIdx.x * JB_K0B_WARPS + wid;
+    const uint32_t seg = blockIdx.x * JB_K0B_THREADS + threadIdx.x;
     if (seg >= im.nseg) return;
     const JbScanResult sr = scanres[image];
     const uint32_t *mk = marks + im.mark_base;
-    const uint8_t *data = arena + im.data_off;
     const uint32_t dri = im.dri ? im.dri : im.total_mcus;
     const uint32_t my_nmcu = min(dri, im.total_mcus - seg * dri);
     uint32_t start = 0;
@@ -62,61 +59,17 @@ jb_k0b_unstuff_segments(const JbDevImage *__restrict__ images, const uint32_t *_
     bool marker_ok = seg < sr.nmarkers;
     if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u; // EOI ends the scan
     if (marker_ok) flags |= 2u;
-
-    // clean stream position: 32 spare bytes per segment make room for alignment and padding
-    const uint64_t cs = (im.clean_off + start + 32ull * seg + 15ull) & ~15ull;
-    uint8_t *out = clean + cs;
-    uint32_t total = 0;
-    for (uint32_t base = start & ~15u; base < stop; base += 512) {
-        const uint32_t chunk = base + lane * 16;
-        uint32_t w[4] = {0, 0, 0, 0}, pb = 0, nb = 0;
-        if (chunk < stop) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + chunk));
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            nb = __ldg(data + chunk + 16); // the arena is padded: the over-read is safe
-            if (chunk > 0) pb = __ldg(data + chunk - 1);
-        }
-        uint32_t keep = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t pos = chunk + i;
-            const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
-            const uint32_t bn = i < 15 ? (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFF : nb;
-            uint32_t bp = i > 0 ? (w[(i - 1) >> 2] >> (((i - 1) & 3) * 8)) & 0xFF : pb;
-            if (pos == start) bp = 0;
-            const bool drop = (b == 0xFF && bn == 0xFF) || (b == 0 && bp == 0xFF);
-            if (pos >= start && pos < stop && !drop) keep |= 1u << i;
-        }
-        const uint32_t cnt = __popc(keep);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        uint32_t j = total + incl - cnt;
-#pragma unroll
-        for (int i = 0; i < 16; i++)
-            if (keep & (1u << i)) {
-                out[j ^ 3u] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
-                j++;
-            }
-        total += __shfl_sync(0xFFFFFFFFu, incl, 31);
-    }
-    __syncwarp();
-    if (lane < 16) out[(total + lane) ^ 3u] = 0xFF; // pad with 1-bits (JpegBitReader.cs:166)
-    if (lane == 0) {
-        JbSegDesc d;
-        d.word_off = (uint32_t)(cs >> 2);
-        d.nbits = total * 8;
-        d.nblocks = reachable ? my_nmcu * im.bpm : 0;
-        d.flags = flags;
-        d.coef_block = im.coef_off + (uint64_t)seg * dri * im.bpm;
-        d.image = image;
-        d.pad = 0;
-        segs[im.seg_base + seg] = d;
-        if (!reachable) atomicOr(status + image, JB_ST_EXPECT_RST);
-    }
+    JbSegDesc d;
+    const uint64_t a0 = im.data_off + start;
+    d.word0 = (uint32_t)(a0 >> 2);
+    d.lead = (uint32_t)(a0 & 3u);
+    d.nbytes = stop - start;
+    d.nblocks = reachable ? my_nmcu * im.bpm : 0;
+    d.coef_block = im.coef_off + (uint64_t)seg * dri * im.bpm;
+    d.image = image;
+    d.flags = flags;
+    segs[im.seg_base + seg] = d;
+    if (!reachable) atomicOr(status + image, JB_ST_EXPECT_RST);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -136,6 +89,11 @@ struct __align__(16) JbHuffTable32 {
 static_assert(sizeof(JbHuffTable32) % 16 == 0, "table size");
 
 #define JB_E32_BAD 0xFFFFFFFFu
+
+// byte-permute selectors that left-align the kept bytes of a little-endian word in stream (big-endian) order:
+// index = 4-bit mask of kept bytes (bit i = memory byte i), unused result bytes select the zero operand
+__constant__ uint16_t jb_c_keepsel[16] = {0x4444, 0x0444, 0x1444, 0x0144, 0x2444, 0x0244, 0x1244, 0x0124,
+                                          0x3444, 0x0344, 0x1344, 0x0134, 0x2344, 0x0234, 0x1234, 0x0123};
 
 // ReadBlockBaseline's use of a decoded symbol (JpegHuffmanBaselineScanDecoder.cs:187-219)
 __host__ __device__ inline uint32_t jb_entry32(uint32_t cls, uint32_t sym, uint32_t len)
@@ -194,7 +152,7 @@ __host__ __device__ inline size_t jb_k1f_smem_bytes(int threads)
 
 __global__ void __launch_bounds__(JB_K1F_MAX_THREADS, 1)
 jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restrict__ segs, uint32_t nsegs,
-                const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ clean_words,
+                const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ arena_words,
                 int16_t *__restrict__ coef, uint32_t *__restrict__ status)
 {
     extern __shared__ __align__(16) uint8_t jb_k1f_smem[];
@@ -256,16 +214,24 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     __syncthreads();
     const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
 
-    // bit window: hi:lo hold n valid bits, left-aligned; wnext is the prefetched next word
-    const uint32_t wend = d.word_off + ((d.nbits + 31) >> 5) + 2; // an all-ones padding word
-    uint32_t wofs = d.word_off;
-    uint32_t hi = 0, lo = 0, wnext = 0;
+    // Bit window: hi:lo hold n valid bits, left-aligned, fed 32 bits at a time from the STUFFED stream
+    // (JpegBitReader.FillBuffer, JpegBitReader.cs:95-138).  The common refill -- a whole word inside the
+    // segment without any 0xFF byte and no stuffed FF pending -- appends the byte-swapped word; everything else
+    // (FF 00 -> FF, FF FF fill bytes, the partial first and last words, the 1-bit padding behind the segment
+    // that PeekBits produces, :166) takes the byte-wise path below.  `pad` counts padding bits: they are always
+    // the last bits of the window.
+    const uint32_t a0r = d.lead, a1r = d.lead + d.nbytes;     // segment bytes, relative to word0 * 4
+    const uint32_t endw = d.word0 + (a1r >> 2);               // first word not entirely inside the segment
+    uint32_t wabs = d.word0;
+    uint32_t lim = a0r ? 0u : endw;                           // fast refills while wabs < lim (0: byte-wise path)
+    bool carry = false;                                       // the last byte appended was a stuffed 0xFF candidate
+    uint32_t hi = 0, lo = 0, wnext = 0, wnext2 = 0; // wnext: word at wabs, wnext2: the one after (both prefetched)
     if (left) {
-        hi = __ldg(clean_words + wofs); lo = __ldg(clean_words + wofs + 1); wnext = __ldg(clean_words + wofs + 2);
+        wnext = __ldg(arena_words + wabs);
+        wnext2 = __ldg(arena_words + wabs + 1);
     }
-    wofs = min(wofs + 3, wend);
-    int n = 64;
-    uint32_t used = 0, err = 0;
+    int n = 0, pad = 0;
+    uint32_t err = 0;
 
     uint32_t b = 0, k = 0; // block-in-mcu; next zig-zag index (0: the DC symbol comes next)
     int pred = 0;
@@ -275,12 +241,63 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
 
     while (__any_sync(0xFFFFFFFFu, left != 0)) {
         if (left != 0) {
-            if (n < 32) {
-                hi |= wnext >> n;
-                lo |= __funnelshift_r(0u, wnext, n);
-                n += 32;
-                wnext = __ldg(clean_words + wofs);
-                wofs = min(wofs + 1, wend);
+            while (n < 32) {
+                const uint32_t w = wnext;
+                const uint32_t nw = ~w;
+                // 0x80 in every byte of w that is 0xFF (exact)
+                const uint32_t F = ~(((nw & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | nw) & 0x80808080u;
+                if (F == 0 && wabs < lim) {
+                    const uint32_t be = __byte_perm(w, 0, 0x0123);
+                    hi |= be >> n;
+                    lo |= __funnelshift_r(0u, be, n);
+                    n += 32;
+                } else if (wabs < endw && (wabs != d.word0 || a0r == 0)) {
+                    // a whole word inside the segment with 0xFF bytes or a pending stuffed zero: FF FF -> the first
+                    // FF is a fill byte, FF 00 -> the zero is stuffing (JpegBitReader.cs:108-128), done on all
+                    // four bytes at once
+                    const uint32_t Z = ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u;  // bytes that are 0x00
+                    const uint32_t NF = (F >> 8) | ((wnext2 & 0xFFu) == 0xFFu ? 0x80000000u : 0u); // next byte is FF
+                    const uint32_t PF = (F << 8) | (carry ? 0x80u : 0u);                       // previous byte is FF
+                    const uint32_t K = ~((F & NF) | (Z & PF)) & 0x80808080u;
+                    const uint32_t km = ((K >> 7) * 0x01020408u) >> 24;
+                    const uint32_t outw = __byte_perm(w, 0, jb_c_keepsel[km]);
+                    carry = (F >> 31) != 0;
+                    lim = carry ? 0u : endw;
+                    hi |= outw >> n;
+                    lo |= __funnelshift_r(0u, outw, n);
+                    n += 8 * __popc(km);
+                } else {
+                    // the partial first / last word of the segment and the 1-bit padding behind it
+                    const uint32_t rel = (wabs - d.word0) * 4;
+                    const uint32_t nb = wnext2 & 0xFFu;
+                    uint32_t outw = 0, prv = carry ? 0xFFu : 0u;
+                    int bits = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t p = rel + i, bv = (w >> (8 * i)) & 0xFFu;
+                        const uint32_t nx = i < 3 ? (w >> (8 * i + 8)) & 0xFFu : nb;
+                        if (p >= a1r) { // behind the segment: 1-bits
+                            outw |= 0xFFu << (24 - bits);
+                            bits += 8;
+                            pad += 8;
+                        } else if (p >= a0r) {
+                            const uint32_t pv = p == a0r ? 0u : prv;
+                            if (!((bv == 0xFFu && nx == 0xFFu) || (bv == 0u && pv == 0xFFu))) {
+                                outw |= bv << (24 - bits);
+                                bits += 8;
+                            }
+                        }
+                        prv = bv;
+                    }
+                    carry = rel + 3 < a1r && (w >> 24) == 0xFFu;
+                    lim = carry ? 0u : endw;
+                    hi |= outw >> n;
+                    lo |= __funnelshift_r(0u, outw, n);
+                    n += bits;
+                }
+                wabs = min(wabs + 1, endw + 1);
+                wnext = wnext2;
+                wnext2 = __ldg(arena_words + wabs + 1);
             }
             const bool is_dc = k == 0;
             const uint32_t toff = is_dc ? tdc : tac;
@@ -311,7 +328,6 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
             hi = __funnelshift_lc(lo, hi, total);
             lo = __funnelshift_lc(0u, lo, total);
             n -= (int)total;
-            used += total;
             const uint32_t pos = min(k + run, 63u);
             if (is_dc) { v += pred; pred = v; }
             if (s != 0 || is_dc) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
@@ -355,9 +371,14 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     }
     if (d.nblocks == 0) return;
     // bits consumed beyond the real data => "The bit stream ended prematurely."
-    if (used > d.nbits) err |= JB_ST_PREMATURE_END;
-    // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may remain before
-    // the marker (fill bytes were dropped by K0b like FillBuffer does)
-    else if ((d.flags & 1u) && (d.nbits - used >= 8 || !(d.flags & 2u))) err |= JB_ST_EXPECT_RST;
+    if (n < pad) err |= JB_ST_PREMATURE_END;
+    else if (d.flags & 1u) {
+        // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may remain before the
+        // marker (fill bytes FF are skipped by FillBuffer)
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(arena_words + d.word0);
+        uint32_t p = max((wabs - d.word0) * 4, a0r);
+        while (p < a1r && bytes[p] == 0xFFu) p++;
+        if (n - pad >= 8 || p < a1r || !(d.flags & 2u)) err |= JB_ST_EXPECT_RST;
+    }
     if (err) atomicOr(status + d.image, err);
 }
