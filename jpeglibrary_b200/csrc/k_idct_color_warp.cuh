@@ -35,6 +35,20 @@ __host__ __device__ constexpr int jb_nat2zz_c(int n)
     return t[n];
 }
 
+// jb_chroma_terms with the -128 offsets folded into the rounding constants: (a*(c-128) + r) >> 16 is
+// (a*c + (r - 128*a)) >> 16 in exact integer arithmetic
+__device__ __forceinline__ JbChromaTerms jb_k2w_chroma_terms(uint32_t cb, uint32_t cr)
+{
+    const int rt = (91881 * (int)cr + (32768 - 128 * 91881)) >> 16;
+    const int gt = (-22553 * (int)cb + (-46802 * (int)cr + (32768 + 128 * 22553 + 128 * 46802))) >> 16;
+    const int bt = (116130 * (int)cb + (32768 - 128 * 116130)) >> 16;
+    JbChromaTerms t;
+    t.r2 = __byte_perm((uint32_t)rt, 0, 0x1010);
+    t.g2 = __byte_perm((uint32_t)gt, 0, 0x1010);
+    t.b2 = __byte_perm((uint32_t)bt, 0, 0x1010);
+    return t;
+}
+
 template <int R>
 __device__ __forceinline__ void jb_k2w_row(const uint32_t (&pk)[32], const float *__restrict__ qn, float (&d1)[64])
 {
@@ -71,7 +85,7 @@ __device__ __forceinline__ void jb_k2w_col(const float (&d1)[64], uint32_t (&row
         const float t = __fmaf_rn(d[k], 0.125f, 12582912.0f + 128.0f);
         const uint32_t v = (uint32_t)__viaddmin_s32_relu(__float_as_int(t), -0x4B400000, 255);
         if ((C & 3) == 0) rows[k * 2 + (C >> 2)] = v;
-        else rows[k * 2 + (C >> 2)] |= v << (8 * (C & 3));
+        else rows[k * 2 + (C >> 2)] += v << (8 * (C & 3)); // disjoint bytes: one shift-add (LEA)
     }
 }
 
@@ -98,6 +112,10 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     __shared__ __align__(16) uint8_t s_c[JB_K2W_WARPS][2][NC == 1 ? 16 : CW * 8];
     __shared__ __align__(128) uint8_t s_stage[JB_K2W_WARPS][TH * ROW_BYTES];
     __shared__ __align__(16) float s_qn[NC * 64]; // quantisers in NATURAL order, one table per component
+    constexpr int GROUPS = TW / 4;                // phase B works on items of 4 pixels x VS rows (one chroma row)
+    constexpr int ITEMS = GROUPS * (TH / VS);
+    static_assert(ITEMS % 32 == 0, "items must spread evenly over the lanes");
+    __shared__ uint32_t s_item[ITEMS];            // per item: chroma | luma << 10 | (staging >> 2) << 21 byte offsets
     __shared__ JbDevImage s_im;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -110,6 +128,11 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     __syncthreads();
     for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32)
         s_qn[i] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
+    for (int i = tid; i < ITEMS; i += JB_K2W_WARPS * 32) {
+        const int cy = i / GROUPS, gx = (i - cy * GROUPS) * 4;
+        s_item[i] = (uint32_t)(cy * CW + gx / HS) | ((uint32_t)(cy * VS * TW + gx) << 10) |
+                    ((uint32_t)((cy * VS * ROW_BYTES + gx * BPP) >> 2) << 21);
+    }
     __syncthreads();
 
     // ---- per-lane constants: which block of the unit this lane owns
@@ -219,34 +242,34 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         __syncwarp();
 
         // ------------------------------------------------ phase B: 4-pixel groups -> staging tile
-        constexpr int GROUPS = TW / 4;
-        constexpr int ITEMS = GROUPS * (TH / VS);
-#pragma unroll 1
-        for (int item = lane; item < ITEMS; item += 32) {
-            const int cy = item / GROUPS, gx = (item - cy * GROUPS) * 4;
+#pragma unroll
+        for (int it = 0; it < ITEMS / 32; it++) {
+            const uint32_t io = s_item[it * 32 + lane];
+            const uint8_t *cp = s_c[wid][0] + (io & 1023u);
+            const uint8_t *yp = yplane + ((io >> 10) & 2047u);
+            uint8_t *sp = stage + ((io >> 21) << 2);
             JbChromaTerms t0, t1, t2, t3;
             uint32_t cb4 = 0x80808080u, cr4 = 0x80808080u; // grey: Cb = Cr = 128 (DecodeAction.cs:58-66)
             if (NC == 3) {
                 if (HS == 2) {
-                    cb4 = *reinterpret_cast<const uint16_t *>(s_c[wid][0] + cy * CW + (gx >> 1));
-                    cr4 = *reinterpret_cast<const uint16_t *>(s_c[wid][1] + cy * CW + (gx >> 1));
+                    cb4 = *reinterpret_cast<const uint16_t *>(cp);
+                    cr4 = *reinterpret_cast<const uint16_t *>(cp + CW * 8);
                 } else {
-                    cb4 = *reinterpret_cast<const uint32_t *>(s_c[wid][0] + cy * CW + gx);
-                    cr4 = *reinterpret_cast<const uint32_t *>(s_c[wid][1] + cy * CW + gx);
+                    cb4 = *reinterpret_cast<const uint32_t *>(cp);
+                    cr4 = *reinterpret_cast<const uint32_t *>(cp + CW * 8);
                 }
             }
             if (FMT != 2) {
-                t0 = jb_chroma_terms(cb4 & 0xFF, cr4 & 0xFF);
-                t1 = jb_chroma_terms((cb4 >> 8) & 0xFF, (cr4 >> 8) & 0xFF);
+                t0 = jb_k2w_chroma_terms(cb4 & 0xFF, cr4 & 0xFF);
+                t1 = jb_k2w_chroma_terms(__byte_perm(cb4, 0, 0x4441), __byte_perm(cr4, 0, 0x4441));
                 if (HS == 1) {
-                    t2 = jb_chroma_terms((cb4 >> 16) & 0xFF, (cr4 >> 16) & 0xFF);
-                    t3 = jb_chroma_terms(cb4 >> 24, cr4 >> 24);
+                    t2 = jb_k2w_chroma_terms(__byte_perm(cb4, 0, 0x4442), __byte_perm(cr4, 0, 0x4442));
+                    t3 = jb_k2w_chroma_terms(cb4 >> 24, cr4 >> 24);
                 }
             }
 #pragma unroll
             for (int rr = 0; rr < VS; rr++) {
-                const int py = cy * VS + rr;
-                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(yplane + py * TW + gx);
+                const uint32_t y4 = *reinterpret_cast<const uint32_t *>(yp + rr * TW);
                 uint32_t o0, o1, o2, o3 = 0;
                 if (FMT == 2) {
                     uint32_t cbx, crx; // 4 chroma bytes for the 4 pixels
@@ -294,7 +317,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
                         o3 = __byte_perm(__byte_perm(r23, g23, 0x0062), b23, 0x0610) | 0xFF000000u;
                     }
                 }
-                uint32_t *dst = reinterpret_cast<uint32_t *>(stage + py * ROW_BYTES + gx * BPP);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(sp + rr * ROW_BYTES);
                 if (BPP == 4) {
                     *reinterpret_cast<uint4 *>(dst) = make_uint4(o0, o1, o2, o3);
                 } else {
