@@ -37,7 +37,8 @@ struct __align__(16) JbDevImage {
     // the JbHuffTable32 array), z = component
     uint4 binfo[JB_MAX_BLOCKS_PER_MCU];
     uint32_t seg_base;   // global index of the image's first restart segment in the batch
-    uint32_t pad4[3];
+    uint32_t tmap_shift; // log2 of the element size of the output tensor map (x coordinates are in elements)
+    uint64_t tmap_ptr;   // device address of the CUtensorMap of the pixel output (0: no TMA tensor stores)
     // compressed input
     uint64_t data_off;   // offset of the entropy-coded bytes in the device arena (256-B aligned)
     uint32_t data_len;   // upper bound of entropy-coded length (bytes)

@@ -9,6 +9,7 @@
 // There is no CPU decode path in this library.
 #include "../../include/jpegb200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -29,11 +30,16 @@
 #include "k_idct_color_warp.cuh"
 #include "k_lossless.cuh"
 
+typedef CUresult (*jb_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 struct jb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string error;
     cudaDeviceProp prop{};
+    jb_tmap_encode_fn tmap_encode = nullptr; // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
 };
 
 #define JB_CUDA(ctx, call)                                                                       \
@@ -318,6 +324,7 @@ struct jb_batch {
     };
     std::vector<RenderGroup> groups;
     uint32_t *d_image_list = nullptr;
+    CUtensorMap *d_tmaps = nullptr; // one per image (TMA tensor stores of the pixel output)
     bool need_render = false;
     int launches = 0;
     bool profiling = false;
@@ -360,6 +367,15 @@ int jb_ctx_create(int device, jb_ctx **out)
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t keep = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            c->tmap_encode = reinterpret_cast<jb_tmap_encode_fn>(fn);
+        else
+            cudaGetLastError();
     }
     *out = c;
     return JB_OK;
@@ -1031,6 +1047,46 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         if (!pl.out.on_device) pl.dev_out = b->d_out_staging + reinterpret_cast<uint64_t>(pl.dev_out);
         pl.dev.out_ptr = reinterpret_cast<uint64_t>(pl.dev_out);
     }
+    // tensor maps for the fast renderer's 2-D TMA stores: tensor = [H rows][W * bpp bytes], box = one unit
+    if (ctx->tmap_encode) {
+        std::vector<CUtensorMap> maps(count);
+        bool any = false;
+        for (int i = 0; i < count; i++) {
+            ImagePlan &pl = b->plans[i];
+            const JbDevImage &d = pl.dev;
+            if (d.sof == 3 || pl.out.format > JB_OUT_YCBCR888 || k2_variant(d, b->quant) < 0) continue;
+            if ((d.out_ptr | d.out_pitch) & 15u) continue;
+            const uint32_t bpp = pl.out.format == JB_OUT_RGBA32 ? 4 : 3;
+            const uint32_t unit_mcus = d.ncomp == 1 ? 16 : 32 / d.bpm;
+            const uint32_t box_bytes = unit_mcus * 8 * d.hmax * bpp, box_rows = 8u * d.vmax;
+            const uint64_t row_bytes = (uint64_t)d.width * bpp;
+            uint32_t shift;
+            if (box_bytes <= 256) shift = 0;
+            else if (row_bytes % 2 == 0 && box_bytes / 2 <= 256) shift = 1;
+            else if (row_bytes % 4 == 0 && box_bytes / 4 <= 256) shift = 2;
+            else continue;
+            const CUtensorMapDataType dt = shift == 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                           : shift == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+            const cuuint64_t gdim[2] = {row_bytes >> shift, d.height};
+            const cuuint64_t gstr[1] = {d.out_pitch};
+            const cuuint32_t box[2] = {box_bytes >> shift, box_rows};
+            const cuuint32_t estr[2] = {1, 1};
+            if (ctx->tmap_encode(&maps[i], dt, 2, reinterpret_cast<void *>(d.out_ptr), gdim, gstr, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                continue;
+            pl.dev.tmap_shift = shift;
+            pl.dev.tmap_ptr = 1; // patched below once the device array exists
+            any = true;
+        }
+        if (any) {
+            JB_CUDA_B(cudaMallocAsync(&b->d_tmaps, sizeof(CUtensorMap) * count, ctx->stream));
+            JB_CUDA_B(cudaMemcpyAsync(b->d_tmaps, maps.data(), sizeof(CUtensorMap) * count, cudaMemcpyHostToDevice, ctx->stream));
+            JB_CUDA_B(cudaStreamSynchronize(ctx->stream)); // `maps` goes out of scope
+            for (int i = 0; i < count; i++)
+                if (b->plans[i].dev.tmap_ptr) b->plans[i].dev.tmap_ptr = reinterpret_cast<uint64_t>(b->d_tmaps + i);
+        }
+    }
     // metadata upload (small): images, tables, quant
     std::vector<JbDevImage> h_images(count);
     for (int i = 0; i < count; i++) h_images[i] = b->plans[i].dev;
@@ -1363,6 +1419,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_used) cudaFreeAsync(b->d_used, b->ctx->stream);
     if (b->d_info) cudaFreeAsync(b->d_info, b->ctx->stream);
     if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
+    if (b->d_tmaps) cudaFreeAsync(b->d_tmaps, b->ctx->stream);
     if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
     if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);
     delete b;

@@ -12,8 +12,9 @@
 //     load -> IDCT -> colour -> store, synchronised with __syncwarp only, so warps drift freely and hide each
 //     other's latencies;
 //   * the unit's coefficient blocks are contiguous in the store (MCU scan order) and come in by 16-byte
-//     cp.async copies that are issued one unit ahead; RGB rows leave as cp.async.bulk shared->global copies
-//     issued by 16 lanes in parallel;
+//     cp.async copies that are issued one unit ahead; the unit's pixels leave as ONE 2-D TMA tensor store
+//     (cp.async.bulk.tensor, SASS UTMASTG) through a per-image tensor map, which also clips at the image edges
+//     (per-row bulk copies / plain stores remain for destinations that are not 16-byte aligned);
 //   * dequantisation converts the 16-bit halves of the packed coefficient pairs directly (I2F.S16 on the XU
 //     pipe, which nothing else in this kernel uses) and multiplies by the fp32 quantiser: two issue slots per
 //     coefficient, none of them on the ALU pipe, which is the busiest one here.
@@ -155,6 +156,8 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     uint8_t *const out = reinterpret_cast<uint8_t *>(s_im.out_ptr);
     const uint64_t pitch = s_im.out_pitch;
     const bool bulk_ok = ((s_im.out_ptr | pitch) & 15u) == 0;
+    const uint64_t tmap = s_im.tmap_ptr;
+    const int tmap_shift = (int)s_im.tmap_shift;
     const bool planar = s_im.planar != 0;
     uint8_t *raw = s_raw[wid];
     uint8_t *yplane = s_y[wid];
@@ -329,7 +332,18 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         const int x0 = mcu_col0 * 8 * HS, y0 = cur_row * TH;
         const int rows_out = min(TH, H - y0);
         const int row_bytes = min(ROW_BYTES, (W - x0) * BPP);
-        if (bulk_ok && row_bytes == ROW_BYTES) {
+        if (tmap) {
+            // one 2-D TMA tensor store for the whole unit; the hardware clips at the right and bottom image edges
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap),
+                             "r"((x0 * BPP) >> tmap_shift), "r"(y0), "r"(jb_smem_u32(stage))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            bulk_pending = true;
+        } else if (bulk_ok && row_bytes == ROW_BYTES) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> async proxy
             __syncwarp();
             if (lane < rows_out) {
