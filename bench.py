@@ -104,6 +104,24 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, images):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json, written by
+    profiles/make_traffic.py), scaled from the profiled batch to `images`; None when no capture covers it."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        doc = json.load(open(p))
+        return doc["kernels"][kernel]["dram_bytes_per_image"] * images, doc.get("source")
+    except Exception:
+        return None, None
+
+
+def cpu_sample_size(blobs, threads, target_s=12.0):
+    """Images for a cpu_baseline sample of about `target_s` seconds: calibrated on one image per thread."""
+    _, dt = cpu_reference(blobs, threads, threads)
+    per_round = max(dt, 1e-3)
+    return int(max(threads, min(4096, threads * round(target_s / per_round))))
+
+
 def cpu_reference(blobs, threads, images):
     """Decode `images` streams to RGB24 with the oracle on `threads` host threads; returns MP/s."""
     import oracle_ffi as O
@@ -404,8 +422,10 @@ def main():
     }
     dom = max(kernels, key=lambda kv: kv[1]) if kernels else ("none", float("nan"))
     achieved = alg.get(dom[0], 0) / (dom[1] / 1e3) / 1e9 if kernels else float("nan")
+    traffic, traffic_src = measured_traffic(dom[0], args.batch) if not (args.progressive or args.no_restart) else (None, None)
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg.get(dom[0], 0),
                 "kernel_ms": {k: v for k, v in kernels},
                 "kernel_gbs": {k: alg[k] / (v / 1e3) / 1e9 for k, v in kernels if k in alg and v > 0},
                 "pipeline_frac_of_peak": ((comp_bytes + 3 * WIDTH * HEIGHT * args.batch) / (ms / args.steps / 1e3) / 1e9) / peak}
@@ -414,7 +434,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
-        images = args.cpu_images or max(threads, min(2 * threads, 128))
+        images = args.cpu_images or cpu_sample_size(blobs, threads)
         v, dt = cpu_reference(blobs, threads, images)
         cpu = {"value": v, "unit": "MP/s", "cores": threads, "kind": "port",
                "sample": f"{images} of the batch's images, one image per task on {threads} threads ({dt:.1f} s wall), "

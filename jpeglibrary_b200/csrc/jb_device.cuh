@@ -64,7 +64,7 @@ struct __align__(16) JbDevImage {
     uint32_t use_selfsync; // 1: K1b path
     uint32_t sub_base;     // first sub-sequence slot of this image in the sub-sequence arrays
     uint32_t sub_cap;      // slots reserved
-    uint32_t pad2;
+    uint32_t chunk_base;   // first 64 KB un-stuff chunk of this image in the per-chunk counters
     // progressive frames: per-scan descriptors and a planar coefficient store
     uint32_t scan_base, nscans;     // JbDevScan entries of this image
     uint32_t planar;                // 1: per-component planes of MCU-padded block grids

@@ -314,6 +314,8 @@ struct jb_batch {
     JbSubState *d_exits = nullptr, *d_used = nullptr;
     JbSubInfo *d_info = nullptr;
     uint32_t *d_changed = nullptr; // one counter per synchronisation round
+    uint32_t *d_chunk_kept = nullptr; // kept bytes per 64 KB un-stuff chunk
+    uint32_t ss_total_chunks = 0, ss_max_chunks = 0;
     bool ss_converged = true;
     // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
     struct RenderGroup {
@@ -912,6 +914,10 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             b->ss_total_sub += pl.dev.sub_cap;
             b->ss_max_sub = std::max(b->ss_max_sub, pl.dev.sub_cap);
             b->ss_images.push_back((uint32_t)i);
+            const uint32_t nchunks = (uint32_t)((pl.entropy_len + JB_K1B_CHUNK - 1) / JB_K1B_CHUNK);
+            pl.dev.chunk_base = b->ss_total_chunks;
+            b->ss_total_chunks += nchunks;
+            b->ss_max_chunks = std::max(b->ss_max_chunks, nchunks);
         } else {
             b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
             b->seg_images.push_back((uint32_t)i);
@@ -989,8 +995,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMallocAsync(&b->d_arena, b->arena_bytes, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_images, sizeof(JbDevImage) * count, ctx->stream));
     JB_CUDA_B(cudaMallocAsync(&b->d_tables, sizeof(JbHuffTable) * b->tables.size(), ctx->stream));
-    if (b->total_segs) {
-        if (b->tables.size() * (sizeof(JbHuffTable32) / 4) >= (1ull << 32)) {
+    if (b->total_segs || !b->ss_images.empty()) {
+        if (b->tables.size() * (sizeof(JbHuffTable32) / 4) >= (1ull << 31)) {
             ctx->error = "too many distinct Huffman tables in one batch";
             jb_decode_batch_destroy(b);
             return JB_ERR_NOT_SUPPORTED;
@@ -1000,7 +1006,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         JB_CUDA_B(cudaMallocAsync(&b->d_tables32, sizeof(JbHuffTable32) * b->tables32.size(), ctx->stream));
         JB_CUDA_B(cudaMemcpyAsync(b->d_tables32, b->tables32.data(), sizeof(JbHuffTable32) * b->tables32.size(),
                                   cudaMemcpyHostToDevice, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_segs, sizeof(JbSegDesc) * b->total_segs, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_segs, sizeof(JbSegDesc) * std::max<uint32_t>(b->total_segs, 1), ctx->stream));
         if (b->arena_bytes >= (1ull << 34)) {
             ctx->error = "compressed batch larger than 16 GiB";
             jb_decode_batch_destroy(b);
@@ -1034,6 +1040,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         JB_CUDA_B(cudaMallocAsync(&b->d_used, sizeof(JbSubState) * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_info, sizeof(JbSubInfo) * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_changed, sizeof(uint32_t) * 64, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_chunk_kept, sizeof(uint32_t) * std::max<uint32_t>(b->ss_total_chunks, 1), ctx->stream));
     }
     for (auto &g : b->groups) {
         g.list_off = (uint32_t)h_list.size();
@@ -1155,18 +1162,21 @@ static int launch_kernels(jb_batch *b)
     if (!b->ss_images.empty()) {
         const uint32_t *list = b->d_image_list + b->ss_list_off;
         const unsigned nimg = (unsigned)b->ss_images.size();
-        jb_k1b_unstuff<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_clean, b->d_clean_len);
+        dim3 ugrid(b->ss_max_chunks, nimg);
+        jb_k1b_count<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept);
+        jb_k1b_copy<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept, b->d_clean, b->d_clean_len);
         JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t) * 64, st));
         dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
-        jb_k1b_sync<true><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+        jb_k1b_sync<true><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
                                                           b->d_exits, b->d_used, b->d_info, b->d_changed);
         for (int r = 1; r <= JB_SS_ROUNDS; r++)
-            jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+            jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
                                                                b->d_exits, b->d_used, b->d_info, b->d_changed + r);
         jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status);
-        jb_k1b_write<<<grid, JB_K1B_THREADS, (JB_K1B_THREADS / 32) * JB_K1_STAGE_BYTES, st>>>(
-            b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
-        launches += 4 + JB_SS_ROUNDS;
+        JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1b_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JB_K1B_WRITE_SMEM));
+        jb_k1b_write<<<grid, JB_K1B_THREADS, JB_K1B_WRITE_SMEM, st>>>(
+            b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
+        launches += 5 + JB_SS_ROUNDS;
         mark("jb_k1b_selfsync_chain");
     }
     if (!b->prog_images.empty()) {
@@ -1288,7 +1298,7 @@ static int resync_and_rerun(jb_batch *b)
     for (int iter = 0; iter < 100000; iter++) {
         uint32_t changed = 0;
         JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t), st));
-        jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+        jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
                                                            b->d_exits, b->d_used, b->d_info, b->d_changed);
         JB_CUDA(ctx, cudaMemcpyAsync(&changed, b->d_changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         JB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1297,11 +1307,11 @@ static int resync_and_rerun(jb_batch *b)
     // the prefix-sum kernel works in place on d_info: re-derive the per-sub-sequence counts first
     // (a round over unchanged entries does not rewrite them), by one full round from the final states
     JB_CUDA(ctx, cudaMemsetAsync(b->d_used, 0xFF, sizeof(JbSubState) * b->ss_total_sub, st));
-    jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len,
+    jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
                                                        b->d_exits, b->d_used, b->d_info, b->d_changed);
     jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status);
-    jb_k1b_write<<<grid, JB_K1B_THREADS, (JB_K1B_THREADS / 32) * JB_K1_STAGE_BYTES, st>>>(
-        b->d_images, list, b->d_tables, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
+    jb_k1b_write<<<grid, JB_K1B_THREADS, JB_K1B_WRITE_SMEM, st>>>(
+        b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
     int dummy = 0;
     launch_render(b, &dummy);
     JB_CUDA(ctx, cudaGetLastError());
@@ -1419,6 +1429,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_used) cudaFreeAsync(b->d_used, b->ctx->stream);
     if (b->d_info) cudaFreeAsync(b->d_info, b->ctx->stream);
     if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
+    if (b->d_chunk_kept) cudaFreeAsync(b->d_chunk_kept, b->ctx->stream);
     if (b->d_tmaps) cudaFreeAsync(b->d_tmaps, b->ctx->stream);
     if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
     if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);

@@ -8,7 +8,8 @@
 // true decoder after a few hundred bits (measured on the bench images: mean 730 bits, 99.4 % within
 // 4096).  Pipeline, all kernels batched over images:
 //
-//   U  jb_k1b_unstuff      raw scan bytes -> "clean" stream (FF00 -> FF, terminator cut, 1-padded)
+//   U  jb_k1b_count/_copy  raw scan bytes -> "clean" stream (FF00 -> FF, fill bytes dropped, 1-padded), in 64 KB
+//                          chunks: kept bytes per chunk, then every chunk compacts to its prefix offset
 //   S0 jb_k1b_sync<0>      every thread decodes its 4096-bit sub-sequence from the guess
 //                          (p = start, b = 0, k = 0) and records its exit state
 //   Sr jb_k1b_sync<1>      every thread whose predecessor's exit state changed re-decodes from that
@@ -23,9 +24,12 @@
 #pragma once
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
+#include "k_entropy_flat.cuh"
 
 #define JB_SUBSEQ_BITS 4096u
-#define JB_K1B_THREADS 128
+#define JB_K1B_THREADS 256
+#define JB_K1B_CHUNK 65536u   // bytes of stuffed stream per un-stuff CTA
+#define JB_K1B_TABLES 4       // Huffman tables cached in shared memory per CTA (one image per CTA)
 
 struct __align__(8) JbSubState { // decoder state at a symbol boundary (always moved as one 64-bit word)
     uint32_t p;     // bit position in the clean stream
@@ -38,62 +42,83 @@ struct JbSubInfo {  // what one sub-sequence contributes (valid once the entry s
 };
 
 // ---------------------------------------------------------------------------------------------
-// U: unstuff.  One CTA per image walks the scan in 4 KB tiles: a byte is dropped iff it is the 00 of
-// an FF 00 pair; the stream ends at the first FF xx with xx not in {00, FF} (JpegBitReader.cs:108-128;
-// FF FF fill bytes only occur in front of that marker and are cut with it).  The clean stream is
-// padded with 0xFF bytes (PeekBits pads with 1-bits, JpegBitReader.cs:166).
+// U: unstuff, chunk-parallel.  A byte is dropped iff it is the 00 of an FF 00 pair or an FF followed by
+// another FF (fill byte); the stream ends at the marker K0 found (JpegBitReader.cs:108-128).  Pass 1
+// counts the kept bytes of every 64 KB chunk, pass 2 compacts each chunk to the sum of the counts in
+// front of it.  The clean stream is padded with 0xFF bytes (PeekBits pads with 1-bits, :166).
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t jb_k1b_keep16(const uint8_t *data, uint32_t pos0, uint32_t end, uint32_t (&w)[4])
+{ // keep mask of the 16 bytes at pos0 (pos0 is 16-byte aligned); bytes at or behind `end` are not kept
+    w[0] = w[1] = w[2] = w[3] = 0;
+    if (pos0 >= end) return 0;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos0));
+    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    const uint32_t nb = __ldg(data + pos0 + 16); // the arena is padded: safe
+    const uint32_t pb = pos0 ? __ldg(data + pos0 - 1) : 0u;
+    uint32_t keep = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
+        const uint32_t bn = i < 15 ? (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFF : nb;
+        const uint32_t bp = i > 0 ? (w[(i - 1) >> 2] >> (((i - 1) & 3) * 8)) & 0xFF : pb;
+        const bool drop = (b == 0xFF && bn == 0xFF) || (b == 0 && bp == 0xFF);
+        if (pos0 + i < end && !drop) keep |= 1u << i;
+    }
+    return keep;
+}
+
 __global__ void __launch_bounds__(256)
-jb_k1b_unstuff(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-               const uint8_t *__restrict__ arena, uint8_t *__restrict__ clean, uint32_t *__restrict__ clean_len)
+jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+             const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres, uint32_t *__restrict__ chunk_kept)
 {
-    const uint32_t image = image_list[blockIdx.x];
+    const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
+    const uint32_t end = min(scanres[image].end_pos, im.data_len);
+    const uint32_t c0 = blockIdx.x * JB_K1B_CHUNK;
+    if (c0 >= end && blockIdx.x > 0) return;
+    const uint8_t *data = arena + im.data_off;
+    uint32_t cnt = 0, w[4];
+    for (uint32_t pos0 = c0 + threadIdx.x * 16; pos0 < c0 + JB_K1B_CHUNK; pos0 += 256 * 16)
+        cnt += __popc(jb_k1b_keep16(data, pos0, end, w));
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_kept[im.chunk_base + blockIdx.x] = s_cnt;
+}
+
+__global__ void __launch_bounds__(256)
+jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+            const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres,
+            const uint32_t *__restrict__ chunk_kept, uint8_t *__restrict__ clean, uint32_t *__restrict__ clean_len)
+{
+    const uint32_t image = image_list[blockIdx.y];
+    const JbDevImage &im = images[image];
+    const uint32_t end = min(scanres[image].end_pos, im.data_len);
+    const uint32_t c0 = blockIdx.x * JB_K1B_CHUNK;
+    if (c0 >= end && blockIdx.x > 0) return;
     const uint8_t *data = arena + im.data_off;
     uint8_t *out = clean + im.data_off;
-    const uint32_t len = im.data_len;
     __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_base, s_end;
+    __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_base = 0; s_end = 0xFFFFFFFFu; }
+    if (tid == 0) {
+        uint32_t base = 0;
+        for (uint32_t i = 0; i < blockIdx.x; i++) base += chunk_kept[im.chunk_base + i];
+        s_base = base;
+    }
     __syncthreads();
-    for (uint32_t tile = 0; tile < len; tile += 256 * 16) {
-        const uint32_t pos0 = tile + tid * 16;
-        uint32_t w[5] = {0, 0, 0, 0, 0};
-        uint32_t prev = 0;
-        if (pos0 < len) {
-            uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos0));
-            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-            w[4] = __ldg(reinterpret_cast<const uint32_t *>(data + pos0 + 16));
-            if (pos0 > 0) prev = data[pos0 - 1];
-        }
-        // terminator inside my 16 bytes?
-        uint32_t term = 0xFFFFFFFFu;
-        if (jb_ff_bytes(w[0]) | jb_ff_bytes(w[1]) | jb_ff_bytes(w[2]) | jb_ff_bytes(w[3])) {
-#pragma unroll
-            for (int i = 15; i >= 0; i--) {
-                const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
-                const uint32_t nb = (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFF;
-                if (b == 0xFF && nb != 0 && pos0 + i + 1 < len) term = pos0 + i; // FF FF counts too (fill before a marker)
-            }
-        }
-        if (term != 0xFFFFFFFFu) atomicMin(&s_end, term);
-        __syncthreads();
-        const uint32_t end = min(s_end, len);
-        // keep mask
-        uint32_t keep = 0, cnt = 0;
-        uint32_t pb = prev;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
-            const bool k = pos0 + i < end && !(b == 0 && pb == 0xFF);
-            if (k) { keep |= 1u << i; cnt++; }
-            pb = b;
-        }
+    for (uint32_t tile = c0; tile < c0 + JB_K1B_CHUNK && tile < end; tile += 256 * 16) {
+        uint32_t w[4];
+        const uint32_t keep = jb_k1b_keep16(data, tile + tid * 16, end, w);
+        const uint32_t cnt = __popc(keep);
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
             if (lane >= d) incl += t;
         }
         if (lane == 31) s_warp[wid] = incl;
@@ -111,66 +136,111 @@ jb_k1b_unstuff(const JbDevImage *__restrict__ images, const uint32_t *__restrict
         __syncthreads();
         if (tid == 0) s_base += total;
         __syncthreads();
-        if (s_end != 0xFFFFFFFFu) break;
     }
-    __syncthreads();
-    const uint32_t n = s_base;
-    if (tid < 64) out[n + tid] = 0xFF; // padding (the arena keeps 64 spare bytes per image)
-    if (tid == 0) clean_len[image] = n;
+    // the chunk that holds the end of the stream pads it and publishes the clean length
+    if (c0 + JB_K1B_CHUNK >= end) {
+        const uint32_t n = s_base;
+        if (tid < 64) out[n + tid] = 0xFF; // padding (the arena keeps 64 spare bytes per image)
+        if (tid == 0) clean_len[image] = n;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Bit reader over the clean stream: aligned big-endian words, branch-free 32-bit refill.
+// Shared set-up of the sync and write kernels: a CTA works on consecutive sub-sequences of ONE image, so the
+// image's Huffman look-up tables (32-bit entries, k_entropy_flat.cuh) sit in shared memory together with the
+// per-block table references.  s_bi[b] = {DC table, AC table, component}; table references are shared-memory
+// word offsets or JB_K1B_GLOBAL | word offset into the global table array.
 // ---------------------------------------------------------------------------------------------
+#define JB_K1B_GLOBAL 0x80000000u
+#define JB_K1B_TABLE_WORDS (JB_LUT_SIZE + JB_LUT2_SUBTABLES * 64)
+
+__device__ __forceinline__ void jb_k1b_setup(const JbDevImage &im, const JbHuffTable32 *__restrict__ tables,
+                                             uint32_t *s_tab, uint4 *s_bi, int tid)
+{
+    __shared__ uint32_t s_ids[JB_K1B_TABLES];
+    __shared__ uint32_t s_n;
+    if (tid == 0) {
+        uint32_t n = 0;
+        for (int k = 0; k < im.ntables && n < JB_K1B_TABLES; k++) s_ids[n++] = im.table_index[k];
+        s_n = n;
+    }
+    __syncthreads();
+    const uint32_t ntab = s_n;
+    for (uint32_t t = 0; t < ntab; t++) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tables + s_ids[t]);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_tab + t * JB_K1B_TABLE_WORDS);
+        for (int i = tid; i < JB_K1B_TABLE_WORDS / 4; i += JB_K1B_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid < JB_MAX_BLOCKS_PER_MCU) {
+        uint32_t ref[2];
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const uint32_t id = im.table_index[c ? im.blk_ac[tid] : im.blk_dc[tid]];
+            uint32_t j = 0;
+            while (j < ntab && s_ids[j] != id) j++;
+            ref[c] = j < ntab ? j * JB_K1B_TABLE_WORDS : (JB_K1B_GLOBAL | (uint32_t)(id * (sizeof(JbHuffTable32) / 4)));
+        }
+        s_bi[tid] = make_uint4(ref[0], ref[1], im.blk_comp[tid], 0);
+    }
+    __syncthreads();
+}
+
+// one Huffman symbol from the window's top bits: table entry (k_entropy_flat.cuh format) or JB_E32_BAD
+__device__ __forceinline__ uint32_t jb_k1b_lookup(const uint32_t *s_tab, const uint32_t *tab_words, uint32_t toff, uint32_t hi)
+{
+    uint32_t e;
+    if (toff & JB_K1B_GLOBAL) e = __ldg(tab_words + (toff & ~JB_K1B_GLOBAL) + (hi >> (32 - JB_LUT_BITS)));
+    else e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
+    if ((e & 0xFFu) == 0) {
+        uint32_t e2 = 0;
+        if (e != 0 && !(toff & JB_K1B_GLOBAL)) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
+        if (e2 == 0) {
+            // second-level miss or a table that is not cached: resolve against the table in global memory
+            const uint32_t goff = (toff & JB_K1B_GLOBAL) ? (toff & ~JB_K1B_GLOBAL) : 0xFFFFFFFFu;
+            if (goff != 0xFFFFFFFFu) e2 = jb_huff32_escape(reinterpret_cast<const JbHuffTable32 *>(tab_words + goff), e, hi >> 16);
+            else e2 = 0; // cached table: the caller resolves it (it knows the table's global index)
+        }
+        e = e2;
+    }
+    return e;
+}
+
+// Bit reader over the clean stream: aligned big-endian words, one predicated 32-bit refill per symbol.
 struct JbCleanReader {
-    const uint8_t *data; // 256-byte aligned, 1-padded
-    uint32_t wpos;       // byte offset of the next aligned word to load
+    const uint32_t *words; // clean stream of the image (word pointer)
+    uint32_t wpos;         // index of the next word to load
     uint32_t hi, lo;
     int n;
-
-    __device__ __forceinline__ uint32_t ldw(uint32_t off) const
-    {
-        return __byte_perm(__ldg(reinterpret_cast<const uint32_t *>(data + off)), 0, 0x0123);
-    }
     __device__ __forceinline__ void seek(const uint8_t *d, uint32_t bitpos)
     {
-        data = d;
-        const uint32_t byte = bitpos >> 3;
-        wpos = byte & ~3u;
-        hi = ldw(wpos);
-        lo = ldw(wpos + 4);
-        wpos += 8;
+        words = reinterpret_cast<const uint32_t *>(d);
+        wpos = bitpos >> 5;
+        hi = __byte_perm(__ldg(words + wpos), 0, 0x0123);
+        lo = __byte_perm(__ldg(words + wpos + 1), 0, 0x0123);
+        wpos += 2;
         n = 64;
-        skip_any((int)(bitpos - (byte & ~3u) * 8)); // 0..31
+        const int sk = (int)(bitpos & 31u);
+        hi = __funnelshift_l(lo, hi, sk);
+        lo <<= sk;
+        n -= sk;
     }
-    __device__ __forceinline__ uint32_t position() const { return wpos * 8 - (uint32_t)n; }
+    __device__ __forceinline__ uint32_t position() const { return wpos * 32 - (uint32_t)n; }
     __device__ __forceinline__ void refill()
-    { // when n <= 32
-        const uint32_t w = ldw(wpos);
-        wpos += 4;
-        hi |= __funnelshift_rc(w, 0u, n);
-        lo |= __funnelshift_rc(0u, w, n);
-        n += 32;
+    { // keeps n >= 32
+        if (n < 32) {
+            const uint32_t w = __byte_perm(__ldg(words + wpos), 0, 0x0123);
+            wpos++;
+            hi |= w >> n;
+            lo |= __funnelshift_r(0u, w, n);
+            n += 32;
+        }
     }
-    __device__ __forceinline__ void ensure32() { if (n <= 32) refill(); }
-    __device__ __forceinline__ uint32_t peek16() const { return hi >> 16; }
-    __device__ __forceinline__ void skip_any(int k)
-    { // 0..31
-        hi = __funnelshift_l(lo, hi, k);
-        lo <<= k;
-        n -= k;
+    __device__ __forceinline__ void skip(uint32_t total)
+    { // 0..32
+        hi = __funnelshift_lc(lo, hi, total);
+        lo = __funnelshift_lc(0u, lo, total);
+        n -= (int)total;
     }
-    __device__ __forceinline__ uint32_t take(int k)
-    { // 1..16
-        const uint32_t v = hi >> (32 - k);
-        skip_any(k);
-        return v;
-    }
-};
-
-struct JbSubGeom {
-    uint32_t image, sub, nsub, start_bit, end_bit, total_bits;
-    bool active;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -181,94 +251,94 @@ struct JbSubGeom {
 template <bool ROUND0>
 __global__ void __launch_bounds__(JB_K1B_THREADS)
 jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-            const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ clean,
+            const JbHuffTable32 *__restrict__ tables, const uint8_t *__restrict__ clean,
             const uint32_t *__restrict__ clean_len, JbSubState *exits, JbSubState *__restrict__ used,
             JbSubInfo *__restrict__ info, uint32_t *__restrict__ changed)
 {
-    __shared__ JbDevImage s_im;
-    __shared__ uint2 s_binfo[JB_MAX_BLOCKS_PER_MCU];
+    __shared__ __align__(16) uint32_t s_tab[JB_K1B_TABLES * JB_K1B_TABLE_WORDS];
+    __shared__ uint4 s_bi[JB_MAX_BLOCKS_PER_MCU];
+    __shared__ int s_dc[JB_K1B_THREADS][4];
     const uint32_t image = image_list[blockIdx.y];
+    const JbDevImage &im = images[image];
     const int tid = threadIdx.x;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
-        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K1B_THREADS) dst[i] = src[i];
-    }
-    __syncthreads();
-    const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
     const uint32_t total_bits = clean_len[image] * 8;
     if (blockIdx.x * JB_K1B_THREADS * JB_SUBSEQ_BITS >= total_bits && blockIdx.x > 0) return;
-    if (tid < JB_MAX_BLOCKS_PER_MCU)
-        s_binfo[tid] = make_uint2(((uint32_t)s_im.blk_comp[tid] << 28) |
-                                      (uint32_t)(s_im.table_index[s_im.blk_dc[tid]] * (sizeof(JbHuffTable) / 16)),
-                                  (uint32_t)(s_im.table_index[s_im.blk_ac[tid]] * (sizeof(JbHuffTable) / 16)));
-    __syncthreads();
+    const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
     const uint32_t start_bit = sub * JB_SUBSEQ_BITS;
-    if (start_bit >= total_bits) return;
     const uint32_t end_bit = start_bit + JB_SUBSEQ_BITS; // the last one simply runs into the padding
-    const uint32_t gi = s_im.sub_base + sub;
-
+    const uint32_t gi = im.sub_base + sub;
+    bool work = start_bit < total_bits;
     JbSubState entry;
-    if (sub == 0) { entry.p = 0; entry.bk = 0; }
-    else if (ROUND0) { entry.p = start_bit; entry.bk = 0; }
-    else {
-        // one 64-bit load: a neighbour may be rewriting its exit state in this very round
-        const unsigned long long raw = *reinterpret_cast<const volatile unsigned long long *>(&exits[gi - 1]);
-        entry.p = (uint32_t)raw; entry.bk = (uint32_t)(raw >> 32);
+    entry.p = 0; entry.bk = 0;
+    if (work) {
+        if (sub == 0) { entry.p = 0; entry.bk = 0; }
+        else if (ROUND0) { entry.p = start_bit; entry.bk = 0; }
+        else {
+            // one 64-bit load: a neighbour may be rewriting its exit state in this very round
+            const unsigned long long raw = *reinterpret_cast<const volatile unsigned long long *>(&exits[gi - 1]);
+            entry.p = (uint32_t)raw; entry.bk = (uint32_t)(raw >> 32);
+        }
+        if (!ROUND0) {
+            const JbSubState u = used[gi];
+            if (u.p == entry.p && u.bk == entry.bk) work = false; // nothing new: my exit state stands
+        }
     }
-    if (!ROUND0) {
-        const JbSubState u = used[gi];
-        if (u.p == entry.p && u.bk == entry.bk) return; // nothing new: my exit state stands
-        atomicAdd(changed, 1u);
-    }
+    if (!ROUND0 && !__syncthreads_or(work)) return; // the usual case after round 1: nobody in this CTA re-decodes
+    jb_k1b_setup(im, tables, s_tab, s_bi, tid);
+    if (!work) return;
+    if (!ROUND0) atomicAdd(changed, 1u);
     *reinterpret_cast<uint2 *>(&used[gi]) = make_uint2(entry.p, entry.bk);
 
-    const int bpm = s_im.bpm;
-    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(tables);
+    const uint32_t bpm = im.bpm;
+    const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
     JbCleanReader br;
-    br.seek(clean + s_im.data_off, entry.p);
-    int b = (int)(entry.bk >> 8), k = (int)(entry.bk & 0xFF);
-    uint2 binfo = s_binfo[b];
+    br.seek(clean + im.data_off, entry.p);
+    uint32_t b = entry.bk >> 8, k = entry.bk & 0xFF;
+    uint4 bi = s_bi[b];
     uint32_t nblk = 0;
-    int dc0 = 0, dc1 = 0, dc2 = 0, dc3 = 0;
+    int *dcs = s_dc[tid];
+    dcs[0] = dcs[1] = dcs[2] = dcs[3] = 0;
+    int dcur = 0; // DC-difference sum of the current component
     uint32_t p = entry.p;
     // a sub-sequence holds at most 4096 symbols (>= 1 bit each); the guard also bounds corrupt data
     for (int guard = 0; p < end_bit && guard < 2 * (int)JB_SUBSEQ_BITS; guard++) {
-        br.ensure32();
+        br.refill();
         const bool is_dc = k == 0;
-        const uint32_t toff = is_dc ? (binfo.x & 0x0FFFFFFFu) : binfo.y;
-        uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)toff * 16), br.peek16());
-        if (e == 0xFFFFFFFFu) e = 0x0001u; // invalid code while speculating: keep moving
-        br.skip_any(e & 0xFF);
-        const int sym = (int)(e >> 8);
-        int s = is_dc ? sym : (sym & 15);
-        const int r = is_dc ? 0 : (sym >> 4);
-        if (s > 16) s = 0;
-        if (is_dc) {
-            int v = 0;
-            if (s != 0) v = jb_extend((int)br.take(s), s);
-            const int comp = binfo.x >> 28;
-            if (comp == 0) dc0 += v; else if (comp == 1) dc1 += v; else if (comp == 2) dc2 += v; else dc3 += v;
-            nblk++;
-            k = 1;
-        } else if (s != 0) {
-            br.skip_any(s);
-            k += r + 1;
-        } else {
-            k = r == 0 ? 64 : k + 16;
+        const uint32_t toff = is_dc ? bi.x : bi.y;
+        uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, br.hi);
+        if (e == 0) {
+            const uint32_t id = im.table_index[is_dc ? im.blk_dc[b] : im.blk_ac[b]];
+            const uint32_t e1 = s_tab[toff + (br.hi >> (32 - JB_LUT_BITS))];
+            e = jb_huff32_escape(tables + id, e1, br.hi >> 16);
         }
+        if (e == JB_E32_BAD) e = is_dc ? 0x01000101u : 0x40000101u; // invalid code while speculating: keep moving
+        const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, adv = e >> 24;
+        const uint32_t s = total - len;
+        const uint32_t x = __funnelshift_l(br.lo, br.hi, len);
+        const uint32_t neg = ~(uint32_t)((int32_t)x >> 31);
+        const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+        const int v = (int)((t ^ neg) - neg);
+        br.skip(total);
+        if (is_dc) { dcur += v; nblk++; }
+        k += adv;
         if (k >= 64) {
             k = 0;
-            if (++b == bpm) b = 0;
-            binfo = s_binfo[b];
+            b = b + 1 == bpm ? 0 : b + 1;
+            const uint4 ni = s_bi[b];
+            if (ni.z != bi.z) {
+                dcs[bi.z] += dcur;
+                dcur = 0;
+            }
+            bi = ni;
         }
         p = br.position();
     }
+    dcs[bi.z] += dcur;
     *reinterpret_cast<volatile unsigned long long *>(&exits[gi]) =
-        (unsigned long long)p | ((unsigned long long)(((uint32_t)b << 8) | (uint32_t)k) << 32);
+        (unsigned long long)p | ((unsigned long long)((b << 8) | k) << 32);
     JbSubInfo inf;
     inf.nblk = nblk;
-    inf.dc[0] = dc0; inf.dc[1] = dc1; inf.dc[2] = dc2; inf.dc[3] = dc3;
+    inf.dc[0] = dcs[0]; inf.dc[1] = dcs[1]; inf.dc[2] = dcs[2]; inf.dc[3] = dcs[3];
     info[gi] = inf;
 }
 
@@ -335,138 +405,129 @@ jb_k1b_scan(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// W: final decode + coefficient output.  Same symbol semantics and staging/flush scheme as K1a.
+// W: final decode + coefficient output.  Same symbol step, staging slots and warp-cooperative 128-byte line
+// flush as K1 (k_entropy_flat.cuh).
 // ---------------------------------------------------------------------------------------------
+#define JB_K1B_SLOT 144 // 128 B coefficients + 16 B DC predictors per lane
+#define JB_K1B_WRITE_SMEM (JB_K1B_TABLES * JB_K1B_TABLE_WORDS * 4 + JB_K1B_THREADS * JB_K1B_SLOT)
+
 __global__ void __launch_bounds__(JB_K1B_THREADS)
 jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-             const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ clean,
+             const JbHuffTable32 *__restrict__ tables, const uint8_t *__restrict__ clean,
              const uint32_t *__restrict__ clean_len, const JbSubState *__restrict__ exits,
              const JbSubInfo *__restrict__ info, int16_t *__restrict__ coef, uint32_t *__restrict__ status)
 {
-    extern __shared__ uint4 jb_smem[];
-    __shared__ JbDevImage s_im;
-    __shared__ uint2 s_binfo[JB_MAX_BLOCKS_PER_MCU];
+    extern __shared__ __align__(16) uint8_t jb_k1b_smem[];
+    __shared__ uint4 s_bi[JB_MAX_BLOCKS_PER_MCU];
+    uint32_t *s_tab = reinterpret_cast<uint32_t *>(jb_k1b_smem);
+    uint8_t *s_slots = jb_k1b_smem + JB_K1B_TABLES * JB_K1B_TABLE_WORDS * 4;
     const uint32_t image = image_list[blockIdx.y];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
-        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K1B_THREADS) dst[i] = src[i];
-    }
-    __syncthreads();
+    const JbDevImage &im = images[image];
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t total_bits = clean_len[image] * 8;
     if (blockIdx.x * JB_K1B_THREADS * JB_SUBSEQ_BITS >= total_bits && blockIdx.x > 0) return;
-    if (tid < JB_MAX_BLOCKS_PER_MCU)
-        s_binfo[tid] = make_uint2(((uint32_t)s_im.blk_comp[tid] << 28) |
-                                      (uint32_t)(s_im.table_index[s_im.blk_dc[tid]] * (sizeof(JbHuffTable) / 16)),
-                                  (uint32_t)(s_im.table_index[s_im.blk_ac[tid]] * (sizeof(JbHuffTable) / 16)));
-    uint8_t *s_stage = reinterpret_cast<uint8_t *>(jb_smem) + wid * JB_K1_STAGE_BYTES;
-    for (int i = lane; i < JB_K1_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
+    uint8_t *st = s_slots + tid * JB_K1B_SLOT;
+    uint8_t *warp_slots = s_slots + (tid & ~31) * JB_K1B_SLOT;
+#pragma unroll
+    for (int i = 0; i < JB_K1B_SLOT / 16; i++) reinterpret_cast<uint4 *>(st)[i] = make_uint4(0, 0, 0, 0);
+    jb_k1b_setup(im, tables, s_tab, s_bi, tid);
 
     const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
     const uint32_t start_bit = sub * JB_SUBSEQ_BITS;
     const uint32_t end_bit = start_bit + JB_SUBSEQ_BITS;
-    const uint32_t gi = s_im.sub_base + sub;
-    const uint32_t total_blocks = s_im.total_mcus * s_im.bpm;
-    const int bpm = s_im.bpm;
-    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(tables);
+    const uint32_t gi = im.sub_base + sub;
+    const uint32_t total_blocks = im.total_mcus * im.bpm;
+    const uint32_t bpm = im.bpm;
+    const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
 
     bool active = start_bit < total_bits;
     JbCleanReader br;
-    int b = 0, k = 0;
-    uint32_t blk = 0; // index of the block being decoded (scan order)
-    int pred[4] = {0, 0, 0, 0};
-    bool skipping = false; // tail of a block owned by the previous sub-sequence
+    uint32_t b = 0, k = 0;
+    uint32_t blk = 0;       // index of the block being decoded (scan order)
+    bool skipping = false;  // tail of a block owned by the previous sub-sequence
     uint32_t err = 0;
+    int *pp = reinterpret_cast<int *>(st + 128);
     if (active) {
         JbSubState entry;
         if (sub == 0) { entry.p = 0; entry.bk = 0; }
         else entry = exits[gi - 1];
         const JbSubInfo base = info[gi];
         blk = base.nblk;
-        pred[0] = base.dc[0]; pred[1] = base.dc[1]; pred[2] = base.dc[2]; pred[3] = base.dc[3];
-        b = (int)(entry.bk >> 8);
-        k = (int)(entry.bk & 0xFF);
+        pp[0] = base.dc[0]; pp[1] = base.dc[1]; pp[2] = base.dc[2]; pp[3] = base.dc[3];
+        b = entry.bk >> 8;
+        k = entry.bk & 0xFF;
         skipping = k != 0;
-        br.seek(clean + s_im.data_off, entry.p);
+        br.seek(clean + im.data_off, entry.p);
         if (entry.p >= end_bit && !skipping) active = false; // predecessor already covered my range
         if (blk >= total_blocks && !skipping) active = false;
     } else {
-        br.data = clean; br.wpos = 0; br.hi = br.lo = 0; br.n = 64;
+        br.words = reinterpret_cast<const uint32_t *>(clean); br.wpos = 0; br.hi = br.lo = 0; br.n = 64;
     }
-    uint2 binfo = s_binfo[b];
-    int pred_cur = 0;
-    {
-        const int comp = binfo.x >> 28;
-        pred_cur = comp == 0 ? pred[0] : comp == 1 ? pred[1] : comp == 2 ? pred[2] : pred[3];
-    }
-    uint8_t *gptr = reinterpret_cast<uint8_t *>(coef) + (s_im.coef_off + (uint64_t)blk) * 128;
-    const uint32_t lane8 = (lane & 15) * 8;
+    uint4 bi = s_bi[b];
+    int pred = pp[bi.z];
+    uint64_t gptr = reinterpret_cast<uint64_t>(coef + (im.coef_off + (uint64_t)blk) * 64);
     int guard = 0;
 
     while (__any_sync(0xFFFFFFFFu, active)) {
-        bool finished = false; // completed a block that this lane owns
         if (active) {
-            br.ensure32();
+            br.refill();
             const bool is_dc = k == 0;
-            const uint32_t toff = is_dc ? (binfo.x & 0x0FFFFFFFu) : binfo.y;
-            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)toff * 16), br.peek16());
-            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; if (!is_dc) k = 64; }
-            br.skip_any(e & 0xFF);
-            const int sym = (int)(e >> 8);
-            int s = is_dc ? sym : (sym & 15);
-            const int r = is_dc ? 0 : (sym >> 4);
-            if (s > 16) { err |= JB_ST_BAD_CODE; s = 0; }
-            int v = 0;
-            if (s != 0) v = jb_extend((int)br.take(s), s);
-            if (is_dc) {
-                v += pred_cur;
-                pred_cur = v;
-                *reinterpret_cast<int16_t *>(s_stage + jb_stage_off(lane, 0)) = (int16_t)v;
-                k = 1;
-            } else if (s != 0) {
-                k += r;
-                if (!skipping) *reinterpret_cast<int16_t *>(s_stage + jb_stage_off(lane, min(k, 63))) = (int16_t)v;
-                k++;
-            } else {
-                k = r == 0 ? 64 : k + 16;
+            const uint32_t toff = is_dc ? bi.x : bi.y;
+            uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, br.hi);
+            if (e == 0) {
+                const uint32_t id = im.table_index[is_dc ? im.blk_dc[b] : im.blk_ac[b]];
+                const uint32_t e1 = s_tab[toff + (br.hi >> (32 - JB_LUT_BITS))];
+                e = jb_huff32_escape(tables + id, e1, br.hi >> 16);
             }
+            if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
+                err |= JB_ST_BAD_CODE;
+                e = is_dc ? 0x01000101u : 0x40000101u;
+            }
+            const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
+            const uint32_t s = total - len;
+            const uint32_t x = __funnelshift_l(br.lo, br.hi, len);
+            const uint32_t neg = ~(uint32_t)((int32_t)x >> 31);
+            const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+            int v = (int)((t ^ neg) - neg);
+            br.skip(total);
+            const uint32_t pos = min(k + run, 63u);
+            if (is_dc) { v += pred; pred = v; }
+            if ((s != 0 || is_dc) && !skipping) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
+            k += adv;
             if (++guard > 4 * (int)JB_SUBSEQ_BITS) { err |= JB_ST_BAD_CODE; active = false; }
-            finished = k >= 64 && !skipping;
         }
-        uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
-        while (fin) {
-            const uint32_t fin2 = fin & (fin - 1);
-            const uint32_t pick = (lane & 16) ? fin2 : fin;
-            const int L = __ffs(pick) - 1;
-            const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)reinterpret_cast<uint64_t>(gptr), L & 31);
-            const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(reinterpret_cast<uint64_t>(gptr) >> 32), L & 31);
-            if (L >= 0) {
-                uint2 *sp = reinterpret_cast<uint2 *>(s_stage + L * 128 + ((((lane & 15) + L) & 15) << 3));
-                const uint2 val = *sp;
-                *sp = make_uint2(0, 0);
-                *reinterpret_cast<uint2 *>((((uint64_t)ghi << 32) | glo) + lane8) = val;
-            }
-            fin = fin2 & (fin2 - 1);
+        const bool finished = active && k >= 64 && !skipping; // completed a block that this lane owns
+        const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
+        if (fin) {
+            uint32_t mine = (fin >> (lane & 24)) & 0xFFu;
+            do {
+                const int t = 31 - __clz((int)mine);
+                const int L = (lane & 24) + (t & 7);
+                const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)gptr, L);
+                const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(gptr >> 32), L);
+                if (t >= 0) {
+                    uint4 *sp = reinterpret_cast<uint4 *>(warp_slots + L * JB_K1B_SLOT) + (lane & 7);
+                    const uint4 q = *sp;
+                    *sp = make_uint4(0, 0, 0, 0);
+                    reinterpret_cast<uint4 *>(((uint64_t)ghi << 32) | glo)[lane & 7] = q;
+                }
+                mine &= ~(1u << (t & 31));
+            } while (__any_sync(0xFFFFFFFFu, mine != 0));
         }
         if (active && k >= 64) {
             // block boundary
             k = 0;
-            if (++b == bpm) b = 0;
-            const uint2 ni = s_binfo[b];
+            b = b + 1 == bpm ? 0 : b + 1;
+            const uint4 ni = s_bi[b];
             if (!skipping) {
                 blk++;
                 gptr += 128;
             }
-            if ((ni.x ^ binfo.x) >> 28) {
-                const int comp = binfo.x >> 28, nc = ni.x >> 28;
-                if (!skipping) {
-                    if (comp == 0) pred[0] = pred_cur; else if (comp == 1) pred[1] = pred_cur; else if (comp == 2) pred[2] = pred_cur; else pred[3] = pred_cur;
-                }
-                pred_cur = nc == 0 ? pred[0] : nc == 1 ? pred[1] : nc == 2 ? pred[2] : pred[3];
+            if (ni.z != bi.z) { // DC predictors are per component
+                if (!skipping) pp[bi.z] = pred;
+                pred = pp[ni.z];
             }
-            binfo = ni;
+            bi = ni;
             skipping = false;
             const uint32_t p = br.position();
             if (blk == total_blocks && p > total_bits) err |= JB_ST_PREMATURE_END; // ran into the padding

@@ -148,9 +148,9 @@ def test_batch_of_mixed_images_device_resident():
     with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
         b.run()
         assert b.status() == [0] * len(blobs)
-        # restart scan + segment un-stuff + segment Huffman + self-sync chain for lake.jpg (unstuff, guess
-        # round, 5 sync rounds, prefix sums, write) + one IDCT/colour launch per sampling layout (4:2:0, 4:4:4)
-        assert b.launch_count() == 1 + 2 + (4 + 5) + 2
+        # restart scan + segment descriptors + segment Huffman + self-sync chain for lake.jpg (un-stuff count and
+        # copy, guess round, 5 sync rounds, prefix sums, write) + one IDCT/colour launch per sampling layout
+        assert b.launch_count() == 1 + 2 + (5 + 5) + 2
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run
