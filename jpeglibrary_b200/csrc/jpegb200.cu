@@ -316,6 +316,8 @@ struct jb_batch {
     uint32_t *d_changed = nullptr; // one counter per synchronisation round
     uint32_t *d_chunk_kept = nullptr; // kept bytes per 64 KB un-stuff chunk
     uint32_t ss_total_chunks = 0, ss_max_chunks = 0;
+    int ss_shift = JB_SUBSEQ_MIN_SHIFT; // log2 of the sub-sequence length in bits
+    JbSubCheck *d_checks = nullptr;
     bool ss_converged = true;
     // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
     struct RenderGroup {
@@ -842,7 +844,7 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
     d.data_len = (uint32_t)pl.entropy_len;
     d.use_selfsync = (d.dri == 0 && pl.entropy_len >= 1024) ? 1u : 0u;
-    d.sub_cap = d.use_selfsync ? (uint32_t)((pl.entropy_len * 8 + JB_SUBSEQ_BITS - 1) / JB_SUBSEQ_BITS) + 1 : 0;
+    d.sub_cap = 0; // set once the batch's sub-sequence length is known
     pl.total_blocks = (uint64_t)d.total_mcus * bpm;
 
     d.quant_off = (uint32_t)quant.size();
@@ -879,7 +881,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     b->plans.resize(count);
     b->host_data.resize(count);
     std::map<std::string, int> table_ids;
-    uint64_t arena = 0, marks = 0, blocks = 0, staging = 0;
+    uint64_t arena = 0, marks = 0, blocks = 0, staging = 0, ss_bits = 0;
     for (int i = 0; i < count; i++) {
         int rc = plan_image(ctx, i, images[i], outputs + i, b->plans[i], b->tables, table_ids, b->quant);
         if (rc) {
@@ -910,10 +912,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             b->ll_max_nseg = std::max(b->ll_max_nseg, pl.dev.nseg);
             b->ll_max_pixels = std::max<uint32_t>(b->ll_max_pixels, (uint32_t)pl.dev.width * pl.dev.height);
         } else if (pl.dev.use_selfsync) {
-            pl.dev.sub_base = (uint32_t)b->ss_total_sub;
-            b->ss_total_sub += pl.dev.sub_cap;
-            b->ss_max_sub = std::max(b->ss_max_sub, pl.dev.sub_cap);
             b->ss_images.push_back((uint32_t)i);
+            ss_bits += pl.entropy_len * 8;
             const uint32_t nchunks = (uint32_t)((pl.entropy_len + JB_K1B_CHUNK - 1) / JB_K1B_CHUNK);
             pl.dev.chunk_base = b->ss_total_chunks;
             b->ss_total_chunks += nchunks;
@@ -943,6 +943,17 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             }
             g->max_tiles = std::max(g->max_tiles, tiles);
         }
+    }
+    // sub-sequence length of the self-synchronising path: about 300k sub-sequences per batch keep the GPU full,
+    // longer ones make the final write pass cheaper (fewer block tails decoded twice, longer uniform loops)
+    b->ss_shift = JB_SUBSEQ_MIN_SHIFT;
+    while (b->ss_shift < JB_SUBSEQ_MAX_SHIFT && (ss_bits >> (b->ss_shift + 1)) >= 300000) b->ss_shift++;
+    for (uint32_t i : b->ss_images) {
+        ImagePlan &pl = b->plans[i];
+        pl.dev.sub_cap = (uint32_t)((pl.entropy_len * 8 + (1ull << b->ss_shift) - 1) >> b->ss_shift) + 1;
+        pl.dev.sub_base = (uint32_t)b->ss_total_sub;
+        b->ss_total_sub += pl.dev.sub_cap;
+        b->ss_max_sub = std::max(b->ss_max_sub, pl.dev.sub_cap);
     }
     // progressive frames: coefficient slice, per-scan K0 ranges and marker slots
     b->h_ranges.resize(count);
@@ -1040,6 +1051,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         JB_CUDA_B(cudaMallocAsync(&b->d_used, sizeof(JbSubState) * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_info, sizeof(JbSubInfo) * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_changed, sizeof(uint32_t) * 64, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_checks, sizeof(JbSubCheck) * JB_SUBSEQ_CHECKS * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_chunk_kept, sizeof(uint32_t) * std::max<uint32_t>(b->ss_total_chunks, 1), ctx->stream));
     }
     for (auto &g : b->groups) {
@@ -1167,15 +1179,15 @@ static int launch_kernels(jb_batch *b)
         jb_k1b_copy<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept, b->d_clean, b->d_clean_len);
         JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t) * 64, st));
         dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
-        jb_k1b_sync<true><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
-                                                          b->d_exits, b->d_used, b->d_info, b->d_changed);
+        jb_k1b_sync<0><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
+                                                       b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
         for (int r = 1; r <= JB_SS_ROUNDS; r++)
-            jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
-                                                               b->d_exits, b->d_used, b->d_info, b->d_changed + r);
-        jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status);
+            jb_k1b_sync<1><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
+                                                           b->d_used, b->d_info, b->d_checks, b->d_changed + r, b->ss_shift);
+        jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status, b->ss_shift);
         JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1b_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JB_K1B_WRITE_SMEM));
         jb_k1b_write<<<grid, JB_K1B_THREADS, JB_K1B_WRITE_SMEM, st>>>(
-            b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
+            b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status, b->ss_shift);
         launches += 5 + JB_SS_ROUNDS;
         mark("jb_k1b_selfsync_chain");
     }
@@ -1298,8 +1310,8 @@ static int resync_and_rerun(jb_batch *b)
     for (int iter = 0; iter < 100000; iter++) {
         uint32_t changed = 0;
         JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t), st));
-        jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
-                                                           b->d_exits, b->d_used, b->d_info, b->d_changed);
+        jb_k1b_sync<2><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
+                                                       b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
         JB_CUDA(ctx, cudaMemcpyAsync(&changed, b->d_changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         JB_CUDA(ctx, cudaStreamSynchronize(st));
         if (changed == 0) break;
@@ -1307,11 +1319,11 @@ static int resync_and_rerun(jb_batch *b)
     // the prefix-sum kernel works in place on d_info: re-derive the per-sub-sequence counts first
     // (a round over unchanged entries does not rewrite them), by one full round from the final states
     JB_CUDA(ctx, cudaMemsetAsync(b->d_used, 0xFF, sizeof(JbSubState) * b->ss_total_sub, st));
-    jb_k1b_sync<false><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len,
-                                                       b->d_exits, b->d_used, b->d_info, b->d_changed);
-    jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status);
+    jb_k1b_sync<2><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
+                                                   b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
+    jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status, b->ss_shift);
     jb_k1b_write<<<grid, JB_K1B_THREADS, JB_K1B_WRITE_SMEM, st>>>(
-        b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status);
+        b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status, b->ss_shift);
     int dummy = 0;
     launch_render(b, &dummy);
     JB_CUDA(ctx, cudaGetLastError());
@@ -1430,6 +1442,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_info) cudaFreeAsync(b->d_info, b->ctx->stream);
     if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
     if (b->d_chunk_kept) cudaFreeAsync(b->d_chunk_kept, b->ctx->stream);
+    if (b->d_checks) cudaFreeAsync(b->d_checks, b->ctx->stream);
     if (b->d_tmaps) cudaFreeAsync(b->d_tmaps, b->ctx->stream);
     if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
     if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);

@@ -26,7 +26,9 @@
 #include "k_entropy_decode.cuh"
 #include "k_entropy_flat.cuh"
 
-#define JB_SUBSEQ_BITS 4096u
+#define JB_SUBSEQ_MIN_SHIFT 12  // sub-sequences are 2^shift bits long; the host picks the shift per batch (12..15):
+#define JB_SUBSEQ_MAX_SHIFT 15  // long ones make the write pass as efficient as the restart-segment decoder
+#define JB_SUBSEQ_CHECKS 16     // checkpoints per sub-sequence (re-decodes stop at the first one they reproduce)
 #define JB_K1B_THREADS 256
 #define JB_K1B_CHUNK 65536u   // bytes of stuffed stream per un-stuff CTA
 #define JB_K1B_TABLES 4       // Huffman tables cached in shared memory per CTA (one image per CTA)
@@ -39,6 +41,15 @@ struct __align__(8) JbSubState { // decoder state at a symbol boundary (always m
 struct JbSubInfo {  // what one sub-sequence contributes (valid once the entry states converged)
     uint32_t nblk;  // blocks whose DC symbol starts inside it
     int32_t dc[4];  // sum of the DC differences of those blocks, per component
+};
+
+// Decoder state at the first symbol boundary at or behind a checkpoint position, with what the sub-sequence
+// contributes FROM there to its end (a function of that state alone, whatever happened in front of it).  A later
+// round that arrives at the same (p, bk) is on the same trajectory from there on.
+struct __align__(16) JbSubCheck {
+    uint32_t p, bk, nblk;
+    int32_t dc[4];
+    uint32_t pad;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -248,13 +259,29 @@ struct JbCleanReader {
 // predecessor's exit state if it differs from the entry used last time.
 // `exits`/`used` are indexed by sub_base + sub.  `changed` counts re-decodes in this round.
 // ---------------------------------------------------------------------------------------------
-template <bool ROUND0>
+// checkpoints [from, to) were written with prefix sums in this pass: turn them into suffix sums (total - prefix)
+__device__ __forceinline__ void jb_k1b_close_checks(JbSubCheck *checks, uint32_t from, uint32_t to, const JbSubInfo &total)
+{
+    for (uint32_t i = from; i < to; i++) {
+        JbSubCheck c = checks[i];
+        c.nblk = total.nblk - c.nblk;
+#pragma unroll
+        for (int q = 0; q < 4; q++) c.dc[q] = total.dc[q] - c.dc[q];
+        checks[i] = c;
+    }
+}
+
+// MODE 0: guess round.  MODE 1: re-decode from the predecessor's exit state if it changed, stopping at the first
+// checkpoint that reproduces the previous trajectory.  MODE 2: like 1 but always to the end (rebuilds `info`).
+template <int MODE>
 __global__ void __launch_bounds__(JB_K1B_THREADS)
 jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
             const JbHuffTable32 *__restrict__ tables, const uint8_t *__restrict__ clean,
             const uint32_t *__restrict__ clean_len, JbSubState *exits, JbSubState *__restrict__ used,
-            JbSubInfo *__restrict__ info, uint32_t *__restrict__ changed)
+            JbSubInfo *__restrict__ info, JbSubCheck *__restrict__ checks, uint32_t *__restrict__ changed, int sub_shift)
 {
+    constexpr bool ROUND0 = MODE == 0;
+    const uint32_t sub_bits = 1u << sub_shift;
     __shared__ __align__(16) uint32_t s_tab[JB_K1B_TABLES * JB_K1B_TABLE_WORDS];
     __shared__ uint4 s_bi[JB_MAX_BLOCKS_PER_MCU];
     __shared__ int s_dc[JB_K1B_THREADS][4];
@@ -262,12 +289,13 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     const JbDevImage &im = images[image];
     const int tid = threadIdx.x;
     const uint32_t total_bits = clean_len[image] * 8;
-    if (blockIdx.x * JB_K1B_THREADS * JB_SUBSEQ_BITS >= total_bits && blockIdx.x > 0) return;
+    if ((uint64_t)blockIdx.x * JB_K1B_THREADS * sub_bits >= total_bits && blockIdx.x > 0) return;
     const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
-    const uint32_t start_bit = sub * JB_SUBSEQ_BITS;
-    const uint32_t end_bit = start_bit + JB_SUBSEQ_BITS; // the last one simply runs into the padding
+    const uint64_t start64 = (uint64_t)sub << sub_shift;
+    const uint32_t start_bit = (uint32_t)start64;
+    const uint32_t end_bit = start_bit + sub_bits; // the last one simply runs into the padding
     const uint32_t gi = im.sub_base + sub;
-    bool work = start_bit < total_bits;
+    bool work = start64 < total_bits;
     JbSubState entry;
     entry.p = 0; entry.bk = 0;
     if (work) {
@@ -300,8 +328,33 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     dcs[0] = dcs[1] = dcs[2] = dcs[3] = 0;
     int dcur = 0; // DC-difference sum of the current component
     uint32_t p = entry.p;
-    // a sub-sequence holds at most 4096 symbols (>= 1 bit each); the guard also bounds corrupt data
-    for (int guard = 0; p < end_bit && guard < 2 * (int)JB_SUBSEQ_BITS; guard++) {
+    const uint32_t cp_bits = sub_bits / JB_SUBSEQ_CHECKS;
+    uint32_t next_cp = start_bit + cp_bits, cpj = 1;
+    JbSubCheck *my_checks = checks + (size_t)gi * JB_SUBSEQ_CHECKS;
+    // a sub-sequence holds at most sub_bits symbols (>= 1 bit each); the guard also bounds corrupt data
+    for (uint32_t guard = 0; p < end_bit && guard < 2 * sub_bits; guard++) {
+        while (p >= next_cp && cpj < JB_SUBSEQ_CHECKS) {
+            JbSubCheck now;
+            now.p = p; now.bk = (b << 8) | k; now.nblk = nblk; now.pad = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) now.dc[c] = dcs[c] + ((uint32_t)c == bi.z ? dcur : 0);
+            if (MODE == 1) {
+                const JbSubCheck old = my_checks[cpj];
+                if (old.p == now.p && old.bk == now.bk) {
+                    // same state at the same bit as last time: the rest of the sub-sequence decodes identically
+                    JbSubInfo inf;
+                    inf.nblk = now.nblk + old.nblk;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) inf.dc[c] = now.dc[c] + old.dc[c];
+                    info[gi] = inf;
+                    jb_k1b_close_checks(my_checks, 1, cpj, inf);
+                    return; // the exit state stands
+                }
+            }
+            my_checks[cpj] = now; // prefix sums for now; turned into suffix sums when the totals are known
+            cpj++;
+            next_cp += cp_bits;
+        }
         br.refill();
         const bool is_dc = k == 0;
         const uint32_t toff = is_dc ? bi.x : bi.y;
@@ -340,6 +393,7 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     inf.nblk = nblk;
     inf.dc[0] = dcs[0]; inf.dc[1] = dcs[1]; inf.dc[2] = dcs[2]; inf.dc[3] = dcs[3];
     info[gi] = inf;
+    jb_k1b_close_checks(my_checks, 1, cpj, inf);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -347,12 +401,12 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 jb_k1b_scan(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-            const uint32_t *__restrict__ clean_len, JbSubInfo *__restrict__ info, uint32_t *__restrict__ status)
+            const uint32_t *__restrict__ clean_len, JbSubInfo *__restrict__ info, uint32_t *__restrict__ status, int sub_shift)
 {
     const uint32_t image = image_list[blockIdx.x];
     const JbDevImage &im = images[image];
     const uint32_t total_bits = clean_len[image] * 8;
-    const uint32_t nsub = (total_bits + JB_SUBSEQ_BITS - 1) / JB_SUBSEQ_BITS;
+    const uint32_t nsub = (uint32_t)(((uint64_t)total_bits + (1u << sub_shift) - 1) >> sub_shift);
     JbSubInfo *a = info + im.sub_base;
     __shared__ int s_w[8][5];
     __shared__ int s_carry[5];
@@ -415,9 +469,10 @@ __global__ void __launch_bounds__(JB_K1B_THREADS)
 jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
              const JbHuffTable32 *__restrict__ tables, const uint8_t *__restrict__ clean,
              const uint32_t *__restrict__ clean_len, const JbSubState *__restrict__ exits,
-             const JbSubInfo *__restrict__ info, int16_t *__restrict__ coef, uint32_t *__restrict__ status)
+             const JbSubInfo *__restrict__ info, int16_t *__restrict__ coef, uint32_t *__restrict__ status, int sub_shift)
 {
     extern __shared__ __align__(16) uint8_t jb_k1b_smem[];
+    const uint32_t sub_bits = 1u << sub_shift;
     __shared__ uint4 s_bi[JB_MAX_BLOCKS_PER_MCU];
     uint32_t *s_tab = reinterpret_cast<uint32_t *>(jb_k1b_smem);
     uint8_t *s_slots = jb_k1b_smem + JB_K1B_TABLES * JB_K1B_TABLE_WORDS * 4;
@@ -425,7 +480,7 @@ jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     const JbDevImage &im = images[image];
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t total_bits = clean_len[image] * 8;
-    if (blockIdx.x * JB_K1B_THREADS * JB_SUBSEQ_BITS >= total_bits && blockIdx.x > 0) return;
+    if ((uint64_t)blockIdx.x * JB_K1B_THREADS * sub_bits >= total_bits && blockIdx.x > 0) return;
     uint8_t *st = s_slots + tid * JB_K1B_SLOT;
     uint8_t *warp_slots = s_slots + (tid & ~31) * JB_K1B_SLOT;
 #pragma unroll
@@ -433,14 +488,15 @@ jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     jb_k1b_setup(im, tables, s_tab, s_bi, tid);
 
     const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
-    const uint32_t start_bit = sub * JB_SUBSEQ_BITS;
-    const uint32_t end_bit = start_bit + JB_SUBSEQ_BITS;
+    const uint64_t start64 = (uint64_t)sub << sub_shift;
+    const uint32_t start_bit = (uint32_t)start64;
+    const uint32_t end_bit = start_bit + sub_bits;
     const uint32_t gi = im.sub_base + sub;
     const uint32_t total_blocks = im.total_mcus * im.bpm;
     const uint32_t bpm = im.bpm;
     const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
 
-    bool active = start_bit < total_bits;
+    bool active = start64 < total_bits;
     JbCleanReader br;
     uint32_t b = 0, k = 0;
     uint32_t blk = 0;       // index of the block being decoded (scan order)
@@ -466,7 +522,7 @@ jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     uint4 bi = s_bi[b];
     int pred = pp[bi.z];
     uint64_t gptr = reinterpret_cast<uint64_t>(coef + (im.coef_off + (uint64_t)blk) * 64);
-    int guard = 0;
+    uint32_t guard = 0;
 
     while (__any_sync(0xFFFFFFFFu, active)) {
         if (active) {
@@ -494,7 +550,7 @@ jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
             if (is_dc) { v += pred; pred = v; }
             if ((s != 0 || is_dc) && !skipping) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
             k += adv;
-            if (++guard > 4 * (int)JB_SUBSEQ_BITS) { err |= JB_ST_BAD_CODE; active = false; }
+            if (++guard > 4 * sub_bits) { err |= JB_ST_BAD_CODE; active = false; }
         }
         const bool finished = active && k >= 64 && !skipping; // completed a block that this lane owns
         const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
