@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -318,6 +319,7 @@ struct jb_batch {
     uint32_t ss_total_chunks = 0, ss_max_chunks = 0;
     int ss_shift = JB_SUBSEQ_MIN_SHIFT; // log2 of the sub-sequence length in bits
     JbSubCheck *d_checks = nullptr;
+    JbSegDesc *d_sub_segs = nullptr; // descriptors of the sub-sequences for the final decode
     bool ss_converged = true;
     // K2 launch groups: images that share a kernel variant (fast: format x sampling; 255 = generic)
     struct RenderGroup {
@@ -335,6 +337,23 @@ struct jb_batch {
     std::vector<cudaEvent_t> events;       // profiling: one event per named mark
     std::vector<const char *> event_names; // name of the interval that ENDS at the event (nullptr: start of a launch)
 };
+
+// K1 over `nsegs` descriptors: CTA size chosen so that all of them are resident in one wave when the batch allows
+// it (one CTA per SM, up to 1024 lanes)
+template <bool CLEAN>
+static int launch_k1_flat(jb_batch *b, const JbSegDesc *segs, uint32_t nsegs, const uint8_t *stream)
+{
+    jb_ctx *ctx = b->ctx;
+    const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
+    uint32_t threads = ((nsegs + sms - 1) / sms + 31) / 32 * 32;
+    threads = std::min<uint32_t>(JB_K1F_MAX_THREADS, std::max<uint32_t>(128, threads));
+    const size_t smem = jb_k1f_smem_bytes((int)threads);
+    JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1_huff_flat<CLEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)jb_k1f_smem_bytes(JB_K1F_MAX_THREADS)));
+    jb_k1_huff_flat<CLEAN><<<(nsegs + threads - 1) / threads, threads, smem, ctx->stream>>>(
+        b->d_images, segs, nsegs, b->d_tables32, reinterpret_cast<const uint32_t *>(stream), b->d_coef, b->d_status);
+    return JB_OK;
+}
 
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
@@ -948,6 +967,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     // longer ones make the final write pass cheaper (fewer block tails decoded twice, longer uniform loops)
     b->ss_shift = JB_SUBSEQ_MIN_SHIFT;
     while (b->ss_shift < JB_SUBSEQ_MAX_SHIFT && (ss_bits >> (b->ss_shift + 1)) >= 300000) b->ss_shift++;
+    if (const char *e = getenv("JB_SS_SHIFT")) // tuning knob
+        b->ss_shift = std::min(JB_SUBSEQ_MAX_SHIFT, std::max(JB_SUBSEQ_MIN_SHIFT, atoi(e)));
     for (uint32_t i : b->ss_images) {
         ImagePlan &pl = b->plans[i];
         pl.dev.sub_cap = (uint32_t)((pl.entropy_len * 8 + (1ull << b->ss_shift) - 1) >> b->ss_shift) + 1;
@@ -1052,6 +1073,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         JB_CUDA_B(cudaMallocAsync(&b->d_info, sizeof(JbSubInfo) * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_changed, sizeof(uint32_t) * 64, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_checks, sizeof(JbSubCheck) * JB_SUBSEQ_CHECKS * b->ss_total_sub, ctx->stream));
+        JB_CUDA_B(cudaMallocAsync(&b->d_sub_segs, sizeof(JbSegDesc) * b->ss_total_sub, ctx->stream));
         JB_CUDA_B(cudaMallocAsync(&b->d_chunk_kept, sizeof(uint32_t) * std::max<uint32_t>(b->ss_total_chunks, 1), ctx->stream));
     }
     for (auto &g : b->groups) {
@@ -1159,15 +1181,7 @@ static int launch_kernels(jb_batch *b)
         jb_k0b_segment_descs<<<ugrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
                                                               b->d_segs, b->d_status);
         mark("jb_k0b_segment_descs");
-        // CTA size: all segments resident in one wave when the batch allows it (one CTA per SM, up to 1024 lanes)
-        const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
-        uint32_t threads = ((b->total_segs + sms - 1) / sms + 31) / 32 * 32;
-        threads = std::min<uint32_t>(JB_K1F_MAX_THREADS, std::max<uint32_t>(128, threads));
-        const size_t smem = jb_k1f_smem_bytes((int)threads);
-        JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1_huff_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)jb_k1f_smem_bytes(JB_K1F_MAX_THREADS)));
-        jb_k1_huff_flat<<<(b->total_segs + threads - 1) / threads, threads, smem, st>>>(
-            b->d_images, b->d_segs, b->total_segs, b->d_tables32, reinterpret_cast<const uint32_t *>(b->d_arena), b->d_coef,
-            b->d_status);
+        if (int rc = launch_k1_flat<false>(b, b->d_segs, b->total_segs, b->d_arena)) return rc;
         mark("jb_k1_huff_segments");
         launches += 2;
     }
@@ -1185,10 +1199,10 @@ static int launch_kernels(jb_batch *b)
             jb_k1b_sync<1><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
                                                            b->d_used, b->d_info, b->d_checks, b->d_changed + r, b->ss_shift);
         jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status, b->ss_shift);
-        JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1b_write, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JB_K1B_WRITE_SMEM));
-        jb_k1b_write<<<grid, JB_K1B_THREADS, JB_K1B_WRITE_SMEM, st>>>(
-            b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status, b->ss_shift);
-        launches += 5 + JB_SS_ROUNDS;
+        dim3 dgrid((b->ss_max_sub + 255) / 256, nimg);
+        jb_k1b_descs<<<dgrid, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_exits, b->d_info, b->d_sub_segs, b->ss_shift);
+        if (int rc = launch_k1_flat<true>(b, b->d_sub_segs, (uint32_t)b->ss_total_sub, b->d_clean)) return rc;
+        launches += 6 + JB_SS_ROUNDS;
         mark("jb_k1b_selfsync_chain");
     }
     if (!b->prog_images.empty()) {
@@ -1322,8 +1336,9 @@ static int resync_and_rerun(jb_batch *b)
     jb_k1b_sync<2><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
                                                    b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
     jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status, b->ss_shift);
-    jb_k1b_write<<<grid, JB_K1B_THREADS, JB_K1B_WRITE_SMEM, st>>>(
-        b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits, b->d_info, b->d_coef, b->d_status, b->ss_shift);
+    dim3 dgrid((b->ss_max_sub + 255) / 256, nimg);
+    jb_k1b_descs<<<dgrid, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_exits, b->d_info, b->d_sub_segs, b->ss_shift);
+    if (int rc = launch_k1_flat<true>(b, b->d_sub_segs, (uint32_t)b->ss_total_sub, b->d_clean)) return rc;
     int dummy = 0;
     launch_render(b, &dummy);
     JB_CUDA(ctx, cudaGetLastError());
@@ -1443,6 +1458,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_changed) cudaFreeAsync(b->d_changed, b->ctx->stream);
     if (b->d_chunk_kept) cudaFreeAsync(b->d_chunk_kept, b->ctx->stream);
     if (b->d_checks) cudaFreeAsync(b->d_checks, b->ctx->stream);
+    if (b->d_sub_segs) cudaFreeAsync(b->d_sub_segs, b->ctx->stream);
     if (b->d_tmaps) cudaFreeAsync(b->d_tmaps, b->ctx->stream);
     if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
     if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);

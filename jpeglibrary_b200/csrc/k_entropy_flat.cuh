@@ -28,6 +28,14 @@ struct __align__(16) JbSegDesc {
     uint64_t coef_block; // first block of the segment in the coefficient store
     uint32_t image;
     uint32_t flags;      // bit 0: a restart marker / EOI must follow; bit 1: it does
+    // Sub-sequences of the self-synchronising path (K1b) are decoded by the same kernel from the un-stuffed
+    // stream: then word0/lead address the entry BIT (lead = 0..31 bits), nbytes is the number of real bits
+    // from there to the end of the image's stream, and the decoder starts in the middle of the MCU sequence:
+    int32_t pred[4];     // DC predictors at the entry
+    uint32_t state;      // block-in-mcu | zig-zag index << 8 | (1 << 16: the first block belongs to the
+                         // previous sub-sequence and is only skipped; it is counted in nblocks)
+    uint32_t endw;       // last padded word of the image's clean stream
+    uint32_t pad[2];
 };
 
 #define JB_K0B_THREADS 128
@@ -68,6 +76,10 @@ jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__re
     d.coef_block = im.coef_off + (uint64_t)seg * dri * im.bpm;
     d.image = image;
     d.flags = flags;
+    d.pred[0] = d.pred[1] = d.pred[2] = d.pred[3] = 0;
+    d.state = 0;
+    d.endw = 0;
+    d.pad[0] = d.pad[1] = 0;
     segs[im.seg_base + seg] = d;
     if (!reachable) atomicOr(status + image, JB_ST_EXPECT_RST);
 }
@@ -150,6 +162,9 @@ __host__ __device__ inline size_t jb_k1f_smem_bytes(int threads)
     return (size_t)JB_K1F_TABLES * JB_K1F_TABLE_WORDS * 4 + (size_t)threads * (JB_K1F_SLOT + 4);
 }
 
+// CLEAN = false: restart segments, read from the stuffed stream.  CLEAN = true: sub-sequences of K1b, read from
+// the un-stuffed stream with an entry state (see JbSegDesc).
+template <bool CLEAN>
 __global__ void __launch_bounds__(JB_K1F_MAX_THREADS, 1)
 jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restrict__ segs, uint32_t nsegs,
                 const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ arena_words,
@@ -221,7 +236,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     // that PeekBits produces, :166) takes the byte-wise path below.  `pad` counts padding bits: they are always
     // the last bits of the window.
     const uint32_t a0r = d.lead, a1r = d.lead + d.nbytes;     // segment bytes, relative to word0 * 4
-    const uint32_t endw = d.word0 + (a1r >> 2);               // first word not entirely inside the segment
+    const uint32_t endw = CLEAN ? d.endw : d.word0 + (a1r >> 2); // first word not entirely inside the segment
     uint32_t wabs = d.word0;
     uint32_t lim = a0r ? 0u : endw;                           // fast refills while wabs < lim (0: byte-wise path)
     bool carry = false;                                       // the last byte appended was a stuffed 0xFF candidate
@@ -235,17 +250,48 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
 
     uint32_t b = 0, k = 0; // block-in-mcu; next zig-zag index (0: the DC symbol comes next)
     int pred = 0;
-    uint32_t bi = s_bi[0]; // low half: DC table, high half: AC table | component << 14 (shared-memory word offsets)
+    bool skip = false;     // CLEAN: the block under way belongs to the previous sub-sequence
+    uint32_t nw = 0;       // CLEAN: words appended to the window
+    if (CLEAN && left) {
+        b = d.state & 0xFFu;
+        k = (d.state >> 8) & 0xFFu;
+        skip = (d.state >> 16) & 1u;
+        int *pp = reinterpret_cast<int *>(st + 128);
+        pp[0] = d.pred[0]; pp[1] = d.pred[1]; pp[2] = d.pred[2]; pp[3] = d.pred[3];
+        // window = the 64 bits at the entry bit
+        const uint32_t w0 = __byte_perm(wnext, 0, 0x0123), w1 = __byte_perm(wnext2, 0, 0x0123);
+        hi = __funnelshift_l(w1, w0, d.lead);
+        lo = w1 << d.lead;
+        n = 64 - (int)d.lead;
+        nw = 2;
+        wabs = min(wabs + 2, endw);
+        wnext = __ldg(arena_words + wabs);
+        wnext2 = __ldg(arena_words + min(wabs + 1, endw));
+        pred = pp[(s_bi[b] >> 30)];
+    }
+    uint32_t bi = s_bi[b]; // low half: DC table, high half: AC table | component << 14 (shared-memory word offsets)
     uint32_t tdc = bi & 0x3FFFu, tac = (bi >> 16) & 0x3FFFu;
     uint64_t gptr = reinterpret_cast<uint64_t>(coef + d.coef_block * 64);
 
     while (__any_sync(0xFFFFFFFFu, left != 0)) {
         if (left != 0) {
+            if (CLEAN) {
+                if (n < 32) { // un-stuffed stream: one predicated word append
+                    const uint32_t be = __byte_perm(wnext, 0, 0x0123);
+                    hi |= be >> n;
+                    lo |= __funnelshift_r(0u, be, n);
+                    n += 32;
+                    nw++;
+                    wabs = min(wabs + 1, endw);
+                    wnext = wnext2;
+                    wnext2 = __ldg(arena_words + min(wabs + 1, endw));
+                }
+            } else
             while (n < 32) {
                 const uint32_t w = wnext;
-                const uint32_t nw = ~w;
+                const uint32_t inv = ~w;
                 // 0x80 in every byte of w that is 0xFF (exact)
-                const uint32_t F = ~(((nw & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | nw) & 0x80808080u;
+                const uint32_t F = ~(((inv & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | inv) & 0x80808080u;
                 if (F == 0 && wabs < lim) {
                     const uint32_t be = __byte_perm(w, 0, 0x0123);
                     hi |= be >> n;
@@ -330,12 +376,12 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
             n -= (int)total;
             const uint32_t pos = min(k + run, 63u);
             if (is_dc) { v += pred; pred = v; }
-            if (s != 0 || is_dc) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
+            if ((s != 0 || is_dc) && !(CLEAN && skip)) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
             k += adv;
         }
         // ---- completed blocks leave the SM as full 128-byte lines: lanes 8g..8g+7 move the g-th finished lane's block
         const bool finished = k >= 64;
-        const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
+        const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished && !(CLEAN && skip));
         if (fin) {
             // every group of 8 lanes moves the finished blocks of its own 8 lanes, one block per round
             uint32_t mine = (fin >> (lane & 24)) & 0xFFu;
@@ -354,22 +400,29 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
             } while (__any_sync(0xFFFFFFFFu, mine != 0));
         }
         if (finished) {
-            gptr += 128;
+            if (!(CLEAN && skip)) gptr += 128;
             left--;
             k = 0;
             b = b + 1 == bpm ? 0 : b + 1;
             const uint32_t ni = s_bi[b];
             if ((ni ^ bi) >> 30) { // DC predictors are per component (:187-196)
                 int *pp = reinterpret_cast<int *>(st + 128);
-                pp[bi >> 30] = pred;
+                if (!(CLEAN && skip)) pp[bi >> 30] = pred;
                 pred = pp[ni >> 30];
             }
+            skip = false;
             bi = ni;
             tdc = ni & 0x3FFFu;
             tac = (ni >> 16) & 0x3FFFu;
         }
     }
     if (d.nblocks == 0) return;
+    if (CLEAN) {
+        // bits consumed beyond the real data => "The bit stream ended prematurely."
+        if (nw * 32 - (uint32_t)n - d.lead > d.nbytes) err |= JB_ST_PREMATURE_END;
+        if (err) atomicOr(status + d.image, err);
+        return;
+    }
     // bits consumed beyond the real data => "The bit stream ended prematurely."
     if (n < pad) err |= JB_ST_PREMATURE_END;
     else if (d.flags & 1u) {

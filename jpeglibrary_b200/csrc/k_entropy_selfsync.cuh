@@ -454,141 +454,55 @@ jb_k1b_scan(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
         if (tid < 5) s_carry[tid] += tot[tid];
         __syncthreads();
     }
+    if (tid == 0) { // slot nsub (every image reserves one more than it has sub-sequences): the totals
+        JbSubInfo x;
+        x.nblk = (uint32_t)s_carry[0]; x.dc[0] = s_carry[1]; x.dc[1] = s_carry[2]; x.dc[2] = s_carry[3]; x.dc[3] = s_carry[4];
+        a[nsub] = x;
+    }
     // fewer blocks in the stream than the frame needs => "The bit stream ended prematurely."
     if (tid == 0 && (uint32_t)s_carry[0] < im.total_mcus * im.bpm) atomicOr(status + image, JB_ST_PREMATURE_END);
 }
 
 // ---------------------------------------------------------------------------------------------
-// W: final decode + coefficient output.  Same symbol step, staging slots and warp-cooperative 128-byte line
-// flush as K1 (k_entropy_flat.cuh).
+// W: final decode + coefficient output = the restart-segment decoder (jb_k1_huff_flat<true>, k_entropy_flat.cuh)
+// run over the sub-sequences.  This kernel writes its descriptors from the converged entry states and the
+// prefix sums: a sub-sequence first skips the tail of the block its predecessor owns, then decodes exactly the
+// blocks whose DC symbol starts inside it.
 // ---------------------------------------------------------------------------------------------
-#define JB_K1B_SLOT 144 // 128 B coefficients + 16 B DC predictors per lane
-#define JB_K1B_WRITE_SMEM (JB_K1B_TABLES * JB_K1B_TABLE_WORDS * 4 + JB_K1B_THREADS * JB_K1B_SLOT)
-
-__global__ void __launch_bounds__(JB_K1B_THREADS)
-jb_k1b_write(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-             const JbHuffTable32 *__restrict__ tables, const uint8_t *__restrict__ clean,
+__global__ void __launch_bounds__(256)
+jb_k1b_descs(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
              const uint32_t *__restrict__ clean_len, const JbSubState *__restrict__ exits,
-             const JbSubInfo *__restrict__ info, int16_t *__restrict__ coef, uint32_t *__restrict__ status, int sub_shift)
+             const JbSubInfo *__restrict__ info, JbSegDesc *__restrict__ segs, int sub_shift)
 {
-    extern __shared__ __align__(16) uint8_t jb_k1b_smem[];
-    const uint32_t sub_bits = 1u << sub_shift;
-    __shared__ uint4 s_bi[JB_MAX_BLOCKS_PER_MCU];
-    uint32_t *s_tab = reinterpret_cast<uint32_t *>(jb_k1b_smem);
-    uint8_t *s_slots = jb_k1b_smem + JB_K1B_TABLES * JB_K1B_TABLE_WORDS * 4;
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t sub = blockIdx.x * 256 + threadIdx.x;
+    if (sub >= im.sub_cap) return;
     const uint32_t total_bits = clean_len[image] * 8;
-    if ((uint64_t)blockIdx.x * JB_K1B_THREADS * sub_bits >= total_bits && blockIdx.x > 0) return;
-    uint8_t *st = s_slots + tid * JB_K1B_SLOT;
-    uint8_t *warp_slots = s_slots + (tid & ~31) * JB_K1B_SLOT;
-#pragma unroll
-    for (int i = 0; i < JB_K1B_SLOT / 16; i++) reinterpret_cast<uint4 *>(st)[i] = make_uint4(0, 0, 0, 0);
-    jb_k1b_setup(im, tables, s_tab, s_bi, tid);
-
-    const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
-    const uint64_t start64 = (uint64_t)sub << sub_shift;
-    const uint32_t start_bit = (uint32_t)start64;
-    const uint32_t end_bit = start_bit + sub_bits;
+    const uint32_t nsub = (uint32_t)(((uint64_t)total_bits + (1u << sub_shift) - 1) >> sub_shift);
     const uint32_t gi = im.sub_base + sub;
     const uint32_t total_blocks = im.total_mcus * im.bpm;
-    const uint32_t bpm = im.bpm;
-    const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
-
-    bool active = start64 < total_bits;
-    JbCleanReader br;
-    uint32_t b = 0, k = 0;
-    uint32_t blk = 0;       // index of the block being decoded (scan order)
-    bool skipping = false;  // tail of a block owned by the previous sub-sequence
-    uint32_t err = 0;
-    int *pp = reinterpret_cast<int *>(st + 128);
-    if (active) {
+    JbSegDesc d;
+    d.word0 = 0; d.lead = 0; d.nbytes = 0; d.nblocks = 0; d.coef_block = 0; d.image = image; d.flags = 0;
+    d.pred[0] = d.pred[1] = d.pred[2] = d.pred[3] = 0;
+    d.state = 0; d.endw = 0; d.pad[0] = d.pad[1] = 0;
+    if (sub < nsub) {
         JbSubState entry;
         if (sub == 0) { entry.p = 0; entry.bk = 0; }
         else entry = exits[gi - 1];
-        const JbSubInfo base = info[gi];
-        blk = base.nblk;
-        pp[0] = base.dc[0]; pp[1] = base.dc[1]; pp[2] = base.dc[2]; pp[3] = base.dc[3];
-        b = entry.bk >> 8;
-        k = entry.bk & 0xFF;
-        skipping = k != 0;
-        br.seek(clean + im.data_off, entry.p);
-        if (entry.p >= end_bit && !skipping) active = false; // predecessor already covered my range
-        if (blk >= total_blocks && !skipping) active = false;
-    } else {
-        br.words = reinterpret_cast<const uint32_t *>(clean); br.wpos = 0; br.hi = br.lo = 0; br.n = 64;
+        const JbSubInfo base = info[gi], next = info[gi + 1]; // exclusive prefixes; slot nsub holds the totals
+        const uint32_t first = min(base.nblk, total_blocks), last = min(next.nblk, total_blocks);
+        const uint32_t k = entry.bk & 0xFFu;
+        const bool skip = k != 0 && sub != 0;
+        const uint64_t bit0 = im.data_off * 8 + entry.p;
+        d.word0 = (uint32_t)(bit0 >> 5);
+        d.lead = (uint32_t)(bit0 & 31u);
+        d.nbytes = entry.p < total_bits ? total_bits - entry.p : 0;
+        d.nblocks = (last - first) + (skip ? 1u : 0u);
+        d.coef_block = im.coef_off + first;
+        d.pred[0] = base.dc[0]; d.pred[1] = base.dc[1]; d.pred[2] = base.dc[2]; d.pred[3] = base.dc[3];
+        d.state = (entry.bk >> 8) | (k << 8) | (skip ? 1u << 16 : 0u);
+        d.endw = (uint32_t)(im.data_off >> 2) + ((clean_len[image] + 3) >> 2) + 8; // inside the 64 bytes of 0xFF padding
     }
-    uint4 bi = s_bi[b];
-    int pred = pp[bi.z];
-    uint64_t gptr = reinterpret_cast<uint64_t>(coef + (im.coef_off + (uint64_t)blk) * 64);
-    uint32_t guard = 0;
-
-    while (__any_sync(0xFFFFFFFFu, active)) {
-        if (active) {
-            br.refill();
-            const bool is_dc = k == 0;
-            const uint32_t toff = is_dc ? bi.x : bi.y;
-            uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, br.hi);
-            if (e == 0) {
-                const uint32_t id = im.table_index[is_dc ? im.blk_dc[b] : im.blk_ac[b]];
-                const uint32_t e1 = s_tab[toff + (br.hi >> (32 - JB_LUT_BITS))];
-                e = jb_huff32_escape(tables + id, e1, br.hi >> 16);
-            }
-            if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
-                err |= JB_ST_BAD_CODE;
-                e = is_dc ? 0x01000101u : 0x40000101u;
-            }
-            const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
-            const uint32_t s = total - len;
-            const uint32_t x = __funnelshift_l(br.lo, br.hi, len);
-            const uint32_t neg = ~(uint32_t)((int32_t)x >> 31);
-            const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
-            int v = (int)((t ^ neg) - neg);
-            br.skip(total);
-            const uint32_t pos = min(k + run, 63u);
-            if (is_dc) { v += pred; pred = v; }
-            if ((s != 0 || is_dc) && !skipping) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
-            k += adv;
-            if (++guard > 4 * sub_bits) { err |= JB_ST_BAD_CODE; active = false; }
-        }
-        const bool finished = active && k >= 64 && !skipping; // completed a block that this lane owns
-        const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
-        if (fin) {
-            uint32_t mine = (fin >> (lane & 24)) & 0xFFu;
-            do {
-                const int t = 31 - __clz((int)mine);
-                const int L = (lane & 24) + (t & 7);
-                const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)gptr, L);
-                const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(gptr >> 32), L);
-                if (t >= 0) {
-                    uint4 *sp = reinterpret_cast<uint4 *>(warp_slots + L * JB_K1B_SLOT) + (lane & 7);
-                    const uint4 q = *sp;
-                    *sp = make_uint4(0, 0, 0, 0);
-                    reinterpret_cast<uint4 *>(((uint64_t)ghi << 32) | glo)[lane & 7] = q;
-                }
-                mine &= ~(1u << (t & 31));
-            } while (__any_sync(0xFFFFFFFFu, mine != 0));
-        }
-        if (active && k >= 64) {
-            // block boundary
-            k = 0;
-            b = b + 1 == bpm ? 0 : b + 1;
-            const uint4 ni = s_bi[b];
-            if (!skipping) {
-                blk++;
-                gptr += 128;
-            }
-            if (ni.z != bi.z) { // DC predictors are per component
-                if (!skipping) pp[bi.z] = pred;
-                pred = pp[ni.z];
-            }
-            bi = ni;
-            skipping = false;
-            const uint32_t p = br.position();
-            if (blk == total_blocks && p > total_bits) err |= JB_ST_PREMATURE_END; // ran into the padding
-            if (p >= end_bit || blk >= total_blocks) active = false;
-        }
-    }
-    if (err) atomicOr(status + image, err);
+    segs[gi] = d;
 }

@@ -149,8 +149,8 @@ def test_batch_of_mixed_images_device_resident():
         b.run()
         assert b.status() == [0] * len(blobs)
         # restart scan + segment descriptors + segment Huffman + self-sync chain for lake.jpg (un-stuff count and
-        # copy, guess round, 5 sync rounds, prefix sums, write) + one IDCT/colour launch per sampling layout
-        assert b.launch_count() == 1 + 2 + (5 + 5) + 2
+        # copy, guess round, 5 sync rounds, prefix sums, descriptors, write) + one IDCT/colour launch per layout
+        assert b.launch_count() == 1 + 2 + (6 + 5) + 2
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run
