@@ -293,7 +293,7 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     const uint32_t sub = blockIdx.x * JB_K1B_THREADS + tid;
     const uint64_t start64 = (uint64_t)sub << sub_shift;
     const uint32_t start_bit = (uint32_t)start64;
-    const uint32_t end_bit = start_bit + sub_bits; // the last one simply runs into the padding
+    const uint32_t end_bit = min(start_bit + sub_bits, total_bits); // (reads stay inside the 64 bytes of padding)
     const uint32_t gi = im.sub_base + sub;
     bool work = start64 < total_bits;
     JbSubState entry;
@@ -319,8 +319,20 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
 
     const uint32_t bpm = im.bpm;
     const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
-    JbCleanReader br;
-    br.seek(clean + im.data_off, entry.p);
+    // bit window over the clean stream with two words of prefetch (words are big-endian in memory)
+    const uint32_t *words = reinterpret_cast<const uint32_t *>(clean + im.data_off);
+    uint32_t wpos = entry.p >> 5;
+    uint32_t hi, lo;
+    int n;
+    {
+        const uint32_t w0 = __byte_perm(__ldg(words + wpos), 0, 0x0123), w1 = __byte_perm(__ldg(words + wpos + 1), 0, 0x0123);
+        const int sk = (int)(entry.p & 31u);
+        hi = __funnelshift_l(w1, w0, sk);
+        lo = w1 << sk;
+        n = 64 - sk;
+        wpos += 2;
+    }
+    uint32_t wnext = __ldg(words + wpos), wnext2 = __ldg(words + wpos + 1);
     uint32_t b = entry.bk >> 8, k = entry.bk & 0xFF;
     uint4 bi = s_bi[b];
     uint32_t nblk = 0;
@@ -331,47 +343,61 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     const uint32_t cp_bits = sub_bits / JB_SUBSEQ_CHECKS;
     uint32_t next_cp = start_bit + cp_bits, cpj = 1;
     JbSubCheck *my_checks = checks + (size_t)gi * JB_SUBSEQ_CHECKS;
-    // a sub-sequence holds at most sub_bits symbols (>= 1 bit each); the guard also bounds corrupt data
-    for (uint32_t guard = 0; p < end_bit && guard < 2 * sub_bits; guard++) {
-        while (p >= next_cp && cpj < JB_SUBSEQ_CHECKS) {
-            JbSubCheck now;
-            now.p = p; now.bk = (b << 8) | k; now.nblk = nblk; now.pad = 0;
+    // every symbol consumes at least one bit, so the loop ends after at most sub_bits symbols
+    while (p < end_bit) {
+        if (p >= next_cp) {
+            while (p >= next_cp && cpj < JB_SUBSEQ_CHECKS) {
+                JbSubCheck now;
+                now.p = p; now.bk = (b << 8) | k; now.nblk = nblk; now.pad = 0;
 #pragma unroll
-            for (int c = 0; c < 4; c++) now.dc[c] = dcs[c] + ((uint32_t)c == bi.z ? dcur : 0);
-            if (MODE == 1) {
-                const JbSubCheck old = my_checks[cpj];
-                if (old.p == now.p && old.bk == now.bk) {
-                    // same state at the same bit as last time: the rest of the sub-sequence decodes identically
-                    JbSubInfo inf;
-                    inf.nblk = now.nblk + old.nblk;
+                for (int c = 0; c < 4; c++) now.dc[c] = dcs[c] + ((uint32_t)c == bi.z ? dcur : 0);
+                if (MODE == 1) {
+                    const JbSubCheck old = my_checks[cpj];
+                    if (old.p == now.p && old.bk == now.bk) {
+                        // same state at the same bit as last time: the rest of the sub-sequence decodes identically
+                        JbSubInfo inf;
+                        inf.nblk = now.nblk + old.nblk;
 #pragma unroll
-                    for (int c = 0; c < 4; c++) inf.dc[c] = now.dc[c] + old.dc[c];
-                    info[gi] = inf;
-                    jb_k1b_close_checks(my_checks, 1, cpj, inf);
-                    return; // the exit state stands
+                        for (int c = 0; c < 4; c++) inf.dc[c] = now.dc[c] + old.dc[c];
+                        info[gi] = inf;
+                        jb_k1b_close_checks(my_checks, 1, cpj, inf);
+                        return; // the exit state stands
+                    }
                 }
+                my_checks[cpj] = now; // prefix sums for now; turned into suffix sums when the totals are known
+                cpj++;
+                next_cp += cp_bits;
             }
-            my_checks[cpj] = now; // prefix sums for now; turned into suffix sums when the totals are known
-            cpj++;
-            next_cp += cp_bits;
+            if (cpj >= JB_SUBSEQ_CHECKS) next_cp = 0xFFFFFFFFu;
         }
-        br.refill();
+        if (n < 32) {
+            const uint32_t be = __byte_perm(wnext, 0, 0x0123);
+            hi |= be >> n;
+            lo |= __funnelshift_r(0u, be, n);
+            n += 32;
+            wpos++;
+            wnext = wnext2;
+            wnext2 = __ldg(words + wpos + 1);
+        }
         const bool is_dc = k == 0;
         const uint32_t toff = is_dc ? bi.x : bi.y;
-        uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, br.hi);
+        uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, hi);
         if (e == 0) {
             const uint32_t id = im.table_index[is_dc ? im.blk_dc[b] : im.blk_ac[b]];
-            const uint32_t e1 = s_tab[toff + (br.hi >> (32 - JB_LUT_BITS))];
-            e = jb_huff32_escape(tables + id, e1, br.hi >> 16);
+            const uint32_t e1 = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
+            e = jb_huff32_escape(tables + id, e1, hi >> 16);
         }
         if (e == JB_E32_BAD) e = is_dc ? 0x01000101u : 0x40000101u; // invalid code while speculating: keep moving
         const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, adv = e >> 24;
         const uint32_t s = total - len;
-        const uint32_t x = __funnelshift_l(br.lo, br.hi, len);
+        const uint32_t x = __funnelshift_l(lo, hi, len);
         const uint32_t neg = ~(uint32_t)((int32_t)x >> 31);
         const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
         const int v = (int)((t ^ neg) - neg);
-        br.skip(total);
+        hi = __funnelshift_lc(lo, hi, total);
+        lo = __funnelshift_lc(0u, lo, total);
+        n -= (int)total;
+        p += total;
         if (is_dc) { dcur += v; nblk++; }
         k += adv;
         if (k >= 64) {
@@ -384,7 +410,6 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
             }
             bi = ni;
         }
-        p = br.position();
     }
     dcs[bi.z] += dcur;
     *reinterpret_cast<volatile unsigned long long *>(&exits[gi]) =
