@@ -150,9 +150,10 @@ struct JbBitReader {
 
     __device__ __forceinline__ uint32_t ldw(uint32_t byte_off) const
     {
-        uint32_t v; // streamed once: keep it out of L1, which holds the Huffman tables
-        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(data + byte_off));
-        return v;
+        // plain read-only load: the 128-byte line stays in L1 for the next 31 words of this lane.  (An
+        // L1::no_allocate load is tagged evict-first in L2 as well: profiles/r1d showed every 4-byte word
+        // coming from DRAM.)
+        return __ldg(reinterpret_cast<const uint32_t *>(data + byte_off));
     }
     __device__ __forceinline__ void init(const uint8_t *d, uint32_t start, uint32_t stop)
     {
