@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -41,7 +42,44 @@ struct jb_ctx {
     std::string error;
     cudaDeviceProp prop{};
     jb_tmap_encode_fn tmap_encode = nullptr; // cuTensorMapEncodeTiled, resolved through the runtime (no libcuda link)
+    // Every context owns its memory pool: two contexts that pipeline chunks of a long job on two streams must
+    // not recycle each other's buffers, or the pool's cross-stream reuse dependencies serialise them.
+    cudaMemPool_t pool = nullptr;
+    // mapped pinned status mailboxes are recycled: cudaHostAlloc / cudaFreeHost synchronise the whole device
+    std::vector<std::pair<uint32_t *, size_t>> mailboxes; // free ones (pointer, capacity in words)
+    std::mutex mailbox_lock;
 };
+
+static uint32_t *jb_mailbox_get(jb_ctx *ctx, size_t words, size_t *cap)
+{
+    {
+        std::lock_guard<std::mutex> g(ctx->mailbox_lock);
+        for (size_t i = 0; i < ctx->mailboxes.size(); i++)
+            if (ctx->mailboxes[i].second >= words) {
+                uint32_t *p = ctx->mailboxes[i].first;
+                *cap = ctx->mailboxes[i].second;
+                ctx->mailboxes.erase(ctx->mailboxes.begin() + i);
+                return p;
+            }
+    }
+    uint32_t *p = nullptr;
+    *cap = std::max<size_t>(words, 4096);
+    if (cudaHostAlloc(reinterpret_cast<void **>(&p), sizeof(uint32_t) * *cap, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    return p;
+}
+
+static void jb_mailbox_put(jb_ctx *ctx, uint32_t *p, size_t cap)
+{
+    std::lock_guard<std::mutex> g(ctx->mailbox_lock);
+    ctx->mailboxes.emplace_back(p, cap);
+}
+
+// stream-ordered allocation from the context's own pool
+template <typename T>
+static cudaError_t jb_malloc_async(jb_ctx *ctx, T **p, size_t bytes)
+{
+    return cudaMallocFromPoolAsync(reinterpret_cast<void **>(p), bytes, ctx->pool, ctx->stream);
+}
 
 #define JB_CUDA(ctx, call)                                                                       \
     do {                                                                                         \
@@ -266,6 +304,43 @@ static void launch_k2_fast(int variant, dim3 grid, cudaStream_t st, const JbDevI
     else launch_k2_fast_fmt<2>(shape, grid, st, im, coef, q, list, tpc);
 }
 
+// Device memory is cleared by a kernel, not by cudaMemsetAsync: memsets may be executed by a copy engine, where they
+// queue behind another stream's large D2H copies and stall this stream's kernels (seen as a full serialisation of
+// two pipelined contexts).
+__global__ void jb_fill_u32(uint4 *__restrict__ p16, size_t n16, uint32_t *__restrict__ tail, uint32_t ntail, uint32_t value)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const uint4 v = make_uint4(value, value, value, value);
+    for (size_t k = i; k < n16; k += stride) p16[k] = v;
+    if (i < ntail) tail[i] = value;
+}
+
+__global__ void jb_post_status(uint32_t *__restrict__ mailbox, const uint32_t *__restrict__ status, int count,
+                               const uint32_t *__restrict__ changed_last)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) mailbox[i] = status[i];
+    if (i == 0) mailbox[count] = changed_last ? *changed_last : 0u;
+}
+
+// bytes must be a multiple of 4 and p 4-byte aligned; `value` is the 32-bit fill pattern
+static cudaError_t jb_fill_async(void *p, uint32_t value, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return cudaSuccess;
+    uint8_t *b = static_cast<uint8_t *>(p);
+    const size_t head = std::min<size_t>(bytes, (16 - (reinterpret_cast<uintptr_t>(b) & 15)) & 15);
+    if (head) jb_fill_u32<<<1, 32, 0, st>>>(nullptr, 0, reinterpret_cast<uint32_t *>(b), (uint32_t)(head / 4), value);
+    b += head;
+    bytes -= head;
+    const size_t n16 = bytes / 16;
+    const uint32_t ntail = (uint32_t)((bytes - n16 * 16) / 4);
+    if (n16 || ntail) {
+        const unsigned blocks = (unsigned)std::min<size_t>(148 * 8, std::max<size_t>(1, (n16 + 255) / 256));
+        jb_fill_u32<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4 *>(b), n16, reinterpret_cast<uint32_t *>(b + n16 * 16), ntail, value);
+    }
+    return cudaGetLastError();
+}
+
 struct jb_batch {
     jb_ctx *ctx = nullptr;
     int count = 0;
@@ -288,6 +363,10 @@ struct jb_batch {
     uint8_t *d_out_staging = nullptr;
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
+    // Status words come back through a mapped pinned mailbox written by a kernel at the end of the launch: a small
+    // cudaMemcpy D2H would queue on the copy engine behind another context's bulk pixel copies.
+    uint32_t *h_mailbox = nullptr; // [count] status words + [1] "changed in the last sync round"
+    size_t mailbox_cap = 0;
     uint32_t max_nseg = 1; // most restart segments any image of the K0b/K1 path has
     // flat restart-segment path (K0b + K1)
     std::vector<JbHuffTable32> tables32;
@@ -384,12 +463,21 @@ int jb_ctx_create(int device, jb_ctx **out)
         delete c;
         return JB_ERR_CUDA;
     }
-    // batch objects allocate from the stream-ordered pool; keep freed memory cached so that creating
+    // batch objects allocate from a stream-ordered pool; keep freed memory cached so that creating
     // the next batch of a streaming workload costs no cudaMalloc
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    {
+        cudaMemPoolProps props{};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->pool, &props) != cudaSuccess) {
+            cudaStreamDestroy(c->stream);
+            delete c;
+            return JB_ERR_CUDA;
+        }
         uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     {
         void *fn = nullptr;
@@ -408,7 +496,12 @@ void jb_ctx_destroy(jb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    if (ctx->pool) cudaMemPoolDestroy(ctx->pool);
+    for (auto &m : ctx->mailboxes) cudaFreeHost(m.first);
     delete ctx;
 }
 
@@ -1014,6 +1107,12 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     b->coef_blocks = blocks;
     b->out_staging_bytes = staging;
     b->h_status.assign(count, 0);
+    b->h_mailbox = jb_mailbox_get(ctx, (size_t)count + 1, &b->mailbox_cap);
+    if (!b->h_mailbox) {
+        ctx->error = "cudaHostAlloc of the status mailbox failed";
+        delete b;
+        return JB_ERR_NOMEM;
+    }
 
 #define JB_CUDA_B(call)                                            \
     do {                                                           \
@@ -1024,9 +1123,9 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             return e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA; \
         }                                                          \
     } while (0)
-    JB_CUDA_B(cudaMallocAsync(&b->d_arena, b->arena_bytes, ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_images, sizeof(JbDevImage) * count, ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_tables, sizeof(JbHuffTable) * b->tables.size(), ctx->stream));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_arena, b->arena_bytes));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_images, sizeof(JbDevImage) * count));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_tables, sizeof(JbHuffTable) * b->tables.size()));
     if (b->total_segs || !b->ss_images.empty()) {
         if (b->tables.size() * (sizeof(JbHuffTable32) / 4) >= (1ull << 31)) {
             ctx->error = "too many distinct Huffman tables in one batch";
@@ -1035,27 +1134,27 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         }
         b->tables32.resize(b->tables.size());
         for (size_t t = 0; t < b->tables.size(); t++) build_device_table32(b->tables[t], b->tables32[t]);
-        JB_CUDA_B(cudaMallocAsync(&b->d_tables32, sizeof(JbHuffTable32) * b->tables32.size(), ctx->stream));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_tables32, sizeof(JbHuffTable32) * b->tables32.size()));
         JB_CUDA_B(cudaMemcpyAsync(b->d_tables32, b->tables32.data(), sizeof(JbHuffTable32) * b->tables32.size(),
                                   cudaMemcpyHostToDevice, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_segs, sizeof(JbSegDesc) * std::max<uint32_t>(b->total_segs, 1), ctx->stream));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_segs, sizeof(JbSegDesc) * std::max<uint32_t>(b->total_segs, 1)));
         if (b->arena_bytes >= (1ull << 34)) {
             ctx->error = "compressed batch larger than 16 GiB";
             jb_decode_batch_destroy(b);
             return JB_ERR_NOT_SUPPORTED;
         }
     }
-    JB_CUDA_B(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1), ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_scan, sizeof(JbScanResult) * b->h_ranges.size(), ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_ranges, sizeof(JbScanRange) * b->h_ranges.size(), ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_scans, sizeof(JbDevScan) * std::max<size_t>(b->h_scans.size(), 1), ctx->stream));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_quant, sizeof(uint16_t) * b->quant.size()));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_marks, sizeof(uint32_t) * std::max<uint64_t>(marks, 1)));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_scan, sizeof(JbScanResult) * b->h_ranges.size()));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_ranges, sizeof(JbScanRange) * b->h_ranges.size()));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_scans, sizeof(JbDevScan) * std::max<size_t>(b->h_scans.size(), 1)));
     JB_CUDA_B(cudaMemcpyAsync(b->d_ranges, b->h_ranges.data(), sizeof(JbScanRange) * b->h_ranges.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!b->h_scans.empty())
         JB_CUDA_B(cudaMemcpyAsync(b->d_scans, b->h_scans.data(), sizeof(JbDevScan) * b->h_scans.size(), cudaMemcpyHostToDevice, ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_coef, blocks * 128, ctx->stream));
-    JB_CUDA_B(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, ctx->stream));
-    if (staging) JB_CUDA_B(cudaMallocAsync(&b->d_out_staging, staging, ctx->stream));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
+    if (staging) JB_CUDA_B(jb_malloc_async(ctx, &b->d_out_staging, staging));
     std::vector<uint32_t> h_list;
     b->seg_list_off = 0;
     h_list.insert(h_list.end(), b->seg_images.begin(), b->seg_images.end());
@@ -1066,21 +1165,21 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     b->ll_list_off = (uint32_t)h_list.size();
     h_list.insert(h_list.end(), b->ll_images.begin(), b->ll_images.end());
     if (!b->ss_images.empty()) {
-        JB_CUDA_B(cudaMallocAsync(&b->d_clean, b->arena_bytes, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_clean_len, sizeof(uint32_t) * count, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_exits, sizeof(JbSubState) * b->ss_total_sub, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_used, sizeof(JbSubState) * b->ss_total_sub, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_info, sizeof(JbSubInfo) * b->ss_total_sub, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_changed, sizeof(uint32_t) * 64, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_checks, sizeof(JbSubCheck) * JB_SUBSEQ_CHECKS * b->ss_total_sub, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_sub_segs, sizeof(JbSegDesc) * b->ss_total_sub, ctx->stream));
-        JB_CUDA_B(cudaMallocAsync(&b->d_chunk_kept, sizeof(uint32_t) * std::max<uint32_t>(b->ss_total_chunks, 1), ctx->stream));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_clean, b->arena_bytes));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_clean_len, sizeof(uint32_t) * count));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_exits, sizeof(JbSubState) * b->ss_total_sub));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_used, sizeof(JbSubState) * b->ss_total_sub));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_info, sizeof(JbSubInfo) * b->ss_total_sub));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_changed, sizeof(uint32_t) * 64));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_checks, sizeof(JbSubCheck) * JB_SUBSEQ_CHECKS * b->ss_total_sub));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_sub_segs, sizeof(JbSegDesc) * b->ss_total_sub));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_chunk_kept, sizeof(uint32_t) * std::max<uint32_t>(b->ss_total_chunks, 1)));
     }
     for (auto &g : b->groups) {
         g.list_off = (uint32_t)h_list.size();
         h_list.insert(h_list.end(), g.images.begin(), g.images.end());
     }
-    JB_CUDA_B(cudaMallocAsync(&b->d_image_list, sizeof(uint32_t) * std::max<size_t>(h_list.size(), 1), ctx->stream));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_image_list, sizeof(uint32_t) * std::max<size_t>(h_list.size(), 1)));
     if (!h_list.empty())
         JB_CUDA_B(cudaMemcpyAsync(b->d_image_list, h_list.data(), sizeof(uint32_t) * h_list.size(), cudaMemcpyHostToDevice, ctx->stream));
     for (int i = 0; i < count; i++) {
@@ -1121,7 +1220,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             any = true;
         }
         if (any) {
-            JB_CUDA_B(cudaMallocAsync(&b->d_tmaps, sizeof(CUtensorMap) * count, ctx->stream));
+            JB_CUDA_B(jb_malloc_async(ctx, &b->d_tmaps, sizeof(CUtensorMap) * count));
             JB_CUDA_B(cudaMemcpyAsync(b->d_tmaps, maps.data(), sizeof(CUtensorMap) * count, cudaMemcpyHostToDevice, ctx->stream));
             JB_CUDA_B(cudaStreamSynchronize(ctx->stream)); // `maps` goes out of scope
             for (int i = 0; i < count; i++)
@@ -1169,7 +1268,7 @@ static int launch_kernels(jb_batch *b)
             b->event_names.push_back(name);
         }
     };
-    JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+    JB_CUDA(ctx, jb_fill_async(b->d_status, 0, sizeof(uint32_t) * b->count, st));
     mark(nullptr);
     jb_k0_restart_scan<<<(unsigned)b->h_ranges.size(), JB_K0_THREADS, 0, st>>>(b->d_ranges, b->d_arena, b->d_marks, b->d_scan);
     launches++;
@@ -1191,7 +1290,7 @@ static int launch_kernels(jb_batch *b)
         dim3 ugrid(b->ss_max_chunks, nimg);
         jb_k1b_count<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept);
         jb_k1b_copy<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept, b->d_clean, b->d_clean_len);
-        JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t) * 64, st));
+        JB_CUDA(ctx, jb_fill_async(b->d_changed, 0, sizeof(uint32_t) * 64, st));
         dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
         jb_k1b_sync<0><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
                                                        b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
@@ -1207,7 +1306,7 @@ static int launch_kernels(jb_batch *b)
     }
     if (!b->prog_images.empty()) {
         // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
-        JB_CUDA(ctx, cudaMemsetAsync(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
+        JB_CUDA(ctx, jb_fill_async(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
         const int lanes = b->prog_max_nseg > 1 ? 32 : 1; // serial streams: one lane per warp
         dim3 grid((b->prog_max_nseg + lanes - 1) / lanes, (unsigned)b->prog_images.size(), b->prog_max_scans);
         for (uint32_t level = 0; level < b->prog_levels; level++) {
@@ -1233,6 +1332,8 @@ static int launch_kernels(jb_batch *b)
     }
     launch_render(b, &launches);
     mark("jb_k2_idct_color");
+    jb_post_status<<<(b->count + 255) / 256, 256, 0, st>>>(b->h_mailbox, b->d_status, b->count,
+                                                           b->ss_images.empty() ? nullptr : b->d_changed + JB_SS_ROUNDS);
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
     return JB_OK;
@@ -1323,7 +1424,7 @@ static int resync_and_rerun(jb_batch *b)
     dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
     for (int iter = 0; iter < 100000; iter++) {
         uint32_t changed = 0;
-        JB_CUDA(ctx, cudaMemsetAsync(b->d_changed, 0, sizeof(uint32_t), st));
+        JB_CUDA(ctx, jb_fill_async(b->d_changed, 0, sizeof(uint32_t), st));
         jb_k1b_sync<2><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
                                                        b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
         JB_CUDA(ctx, cudaMemcpyAsync(&changed, b->d_changed, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1332,7 +1433,7 @@ static int resync_and_rerun(jb_batch *b)
     }
     // the prefix-sum kernel works in place on d_info: re-derive the per-sub-sequence counts first
     // (a round over unchanged entries does not rewrite them), by one full round from the final states
-    JB_CUDA(ctx, cudaMemsetAsync(b->d_used, 0xFF, sizeof(JbSubState) * b->ss_total_sub, st));
+    JB_CUDA(ctx, jb_fill_async(b->d_used, 0xFFFFFFFFu, sizeof(JbSubState) * b->ss_total_sub, st));
     jb_k1b_sync<2><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,
                                                    b->d_used, b->d_info, b->d_checks, b->d_changed, b->ss_shift);
     jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status, b->ss_shift);
@@ -1370,20 +1471,16 @@ int jb_decode_batch_finish(jb_batch *b)
             JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
-    if (!b->ss_images.empty()) {
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!b->ss_images.empty() && b->h_mailbox[b->count] != 0) {
         // the last synchronisation round must not have changed anything; otherwise (sub-sequences that
         // need more than JB_SS_ROUNDS hops to synchronise: rare) keep iterating and redo the output
-        uint32_t last = 0;
-        JB_CUDA(ctx, cudaMemcpyAsync(&last, b->d_changed + JB_SS_ROUNDS, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        int rc = resync_and_rerun(b);
+        if (rc) return rc;
+        jb_post_status<<<(b->count + 255) / 256, 256, 0, ctx->stream>>>(b->h_mailbox, b->d_status, b->count, nullptr);
         JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (last != 0) {
-            int rc = resync_and_rerun(b);
-            if (rc) return rc;
-        }
     }
-    JB_CUDA(ctx, cudaMemcpyAsync(b->h_status.data(), b->d_status, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost,
-                                 ctx->stream));
-    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(b->h_status.data(), b->h_mailbox, sizeof(uint32_t) * b->count);
     int first = JB_OK;
     for (int i = 0; i < b->count; i++) {
         uint32_t s = b->h_status[i];
@@ -1459,6 +1556,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_chunk_kept) cudaFreeAsync(b->d_chunk_kept, b->ctx->stream);
     if (b->d_checks) cudaFreeAsync(b->d_checks, b->ctx->stream);
     if (b->d_sub_segs) cudaFreeAsync(b->d_sub_segs, b->ctx->stream);
+    if (b->h_mailbox) jb_mailbox_put(b->ctx, b->h_mailbox, b->mailbox_cap);
     if (b->d_tmaps) cudaFreeAsync(b->d_tmaps, b->ctx->stream);
     if (b->d_tables32) cudaFreeAsync(b->d_tables32, b->ctx->stream);
     if (b->d_segs) cudaFreeAsync(b->d_segs, b->ctx->stream);
@@ -1675,20 +1773,20 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
             return e_ == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA;                  \
         }                                                                                        \
     } while (0)
-    JB_CUDA_E(cudaMallocAsync(&b->d_images, sizeof(JbEncImage) * count, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_quant, sizeof(uint16_t) * b->quant.size(), st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_list, sizeof(uint32_t) * count, st));
-    if (pixels) JB_CUDA_E(cudaMallocAsync(&b->d_pixels, pixels, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_coef, blocks * 128, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_hist, sizeof(uint32_t) * 8 * 256 * count, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_tables, sizeof(JbEncTable) * 8 * count, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_scratch, sizeof(JbHSym) * 257 * 8 * count, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_bits, sizeof(uint32_t) * blocks, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_totals, sizeof(unsigned long long) * count, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_raw, raw, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_out, outb, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_out_len, sizeof(uint32_t) * count, st));
-    JB_CUDA_E(cudaMallocAsync(&b->d_status, sizeof(uint32_t) * count, st));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_images, sizeof(JbEncImage) * count));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_quant, sizeof(uint16_t) * b->quant.size()));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_list, sizeof(uint32_t) * count));
+    if (pixels) JB_CUDA_E(jb_malloc_async(ctx, &b->d_pixels, pixels));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_hist, sizeof(uint32_t) * 8 * 256 * count));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_tables, sizeof(JbEncTable) * 8 * count));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_scratch, sizeof(JbHSym) * 257 * 8 * count));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_bits, sizeof(uint32_t) * blocks));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_totals, sizeof(unsigned long long) * count));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_raw, raw + 4));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_out, outb));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_out_len, sizeof(uint32_t) * count));
+    JB_CUDA_E(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
     for (int i = 0; i < count; i++)
         b->images[i].pix_ptr = images[i].on_device ? reinterpret_cast<uint64_t>(images[i].pixels)
                                                    : reinterpret_cast<uint64_t>(b->d_pixels + b->pix_dev_off[i]);
@@ -1697,7 +1795,7 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
     JB_CUDA_E(cudaMemcpyAsync(b->d_images, b->images.data(), sizeof(JbEncImage) * count, cudaMemcpyHostToDevice, st));
     JB_CUDA_E(cudaMemcpyAsync(b->d_quant, b->quant.data(), sizeof(uint16_t) * b->quant.size(), cudaMemcpyHostToDevice, st));
     if (!list.empty()) JB_CUDA_E(cudaMemcpyAsync(b->d_list, list.data(), sizeof(uint32_t) * list.size(), cudaMemcpyHostToDevice, st));
-    JB_CUDA_E(cudaMemsetAsync(b->d_tables, 0, sizeof(JbEncTable) * 8 * count, st));
+    JB_CUDA_E(jb_fill_async(b->d_tables, 0, sizeof(JbEncTable) * 8 * count, st));
     JB_CUDA_E(cudaStreamSynchronize(st));
 #undef JB_CUDA_E
     *out = b;
@@ -1716,8 +1814,8 @@ int jb_encode_batch_transform(jb_encode_batch *b)
         else if (!b->descs[i].on_device)
             JB_CUDA(ctx, cudaMemcpyAsync(b->d_pixels + b->pix_dev_off[i], b->descs[i].pixels, b->pix_bytes[i], cudaMemcpyHostToDevice, st));
     }
-    JB_CUDA(ctx, cudaMemsetAsync(b->d_status, 0, sizeof(uint32_t) * b->count, st));
-    JB_CUDA(ctx, cudaMemsetAsync(b->d_hist, 0, sizeof(uint32_t) * 8 * 256 * b->count, st));
+    JB_CUDA(ctx, jb_fill_async(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+    JB_CUDA(ctx, jb_fill_async(b->d_hist, 0, sizeof(uint32_t) * 8 * 256 * b->count, st));
     b->launches = 0;
     for (const auto &g : b->groups) {
         dim3 grid(g.max_tiles, (unsigned)g.list.size());
@@ -1787,7 +1885,7 @@ int jb_encode_batch_pack(jb_encode_batch *b)
     jb_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     JB_CUDA(ctx, cudaSetDevice(ctx->device));
-    JB_CUDA(ctx, cudaMemsetAsync(b->d_raw, 0, b->raw_bytes, st));
+    JB_CUDA(ctx, jb_fill_async(b->d_raw, 0, (b->raw_bytes + 3) / 4 * 4, st));
     dim3 grid((b->max_blocks + 255) / 256, b->count);
     jb_k4a_block_bits<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits);
     jb_k4b_scan<<<b->count, 1024, 0, st>>>(b->d_images, b->d_bits, b->d_totals);

@@ -329,3 +329,18 @@ def test_lossless_missing_restart_marker():
     dec.SetOutputWriter(J.CudaOutputWriter(np.zeros((3, 32, 64), np.int16), J.JB_OUT_PLANAR_I16))
     with pytest.raises((J.InvalidOperationException, J.InvalidDataException)):
         dec.Decode()
+
+
+def test_pipelined_host_decode_matches_batch_decode():
+    """JpegPipelinedBatchDecoder (two streams, chunked) must fill the host buffer exactly like one batch."""
+    blobs = [synth.synth_jpeg(30 + i, 256 + 16 * (i % 3), 160, restart_rows=1 if i % 2 else 0) for i in range(7)]
+    ctx = J.Context.default()
+    out = ctx.pinned_array(8 * 1024 * 1024)
+    out[:] = 0
+    pipe = J.JpegPipelinedBatchDecoder([ctx, J.Context(0)], chunk=2, parse_threads=2)
+    offs = pipe.decode(blobs, out)
+    for i, blob in enumerate(blobs):
+        o = O.decode(blob)
+        got = out[offs[i]:offs[i] + o.rgb.size].reshape(o.rgb.shape)
+        assert np.array_equal(got, o.rgb)
+    ctx.pinned_free(out.ctypes.data)
