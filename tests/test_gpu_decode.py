@@ -87,6 +87,12 @@ SHAPES = [
     dict(width=256, height=256, subsampling="4:2:0", restart_rows=1, optimize=True),  # optimised tables (long codes)
     dict(width=160, height=96, gray=True, restart_blocks=5),
     dict(width=1920, height=1080, subsampling="4:2:0", restart_rows=1, quality=95),
+    # 16-byte aligned rows whose width/height are not multiples of the renderer's unit: the 2-D TMA tensor store
+    # clips the partial units at the right and bottom edges
+    dict(width=336, height=200, subsampling="4:2:0", restart_rows=1),
+    dict(width=352, height=120, subsampling="4:4:4", restart_blocks=9),
+    dict(width=400, height=104, subsampling="4:2:2", restart_rows=1),
+    dict(width=272, height=100, gray=True, restart_blocks=11),
 ]
 
 
@@ -102,6 +108,9 @@ def test_synthetic_streams(kw):
     diff = np.abs(rgb.astype(int) - o.rgb.astype(int))
     print("max|diff|", diff.max(), np.bincount(diff.ravel(), minlength=2)[:3].tolist())
     assert diff.max() <= 1
+    rgba = gpu_pixels(blob, J.JB_OUT_RGBA32, 4)
+    assert np.array_equal(rgba[..., :3], rgb) and (rgba[..., 3] == 255).all()
+    assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
 
 
 NO_RESTART_SHAPES = [
