@@ -257,7 +257,7 @@ struct ImagePlan {
 static int k2_variant(const JbDevImage &d, const std::vector<uint16_t> &quant)
 {
     if (d.precision != 8 || d.out_format > JB_OUT_YCBCR888) return -1;
-    // the fast kernel dequantises through the fp32 mantissa: exact for |q * c| < 2^22
+    // the fast kernel dequantises as fmul(float(q), float(c)): exact for |q * c| < 2^24, i.e. any int16 c with q <= 255
     for (int i = 0; i < d.ncomp * 64; i++)
         if (quant[d.quant_off + i] > 255) return -1;
     int shape;
@@ -1274,8 +1274,7 @@ static int launch_kernels(jb_batch *b)
     launches++;
     mark("jb_k0_restart_scan");
     if (!b->seg_images.empty()) {
-        // one warp per 32 segments; a CTA never spans images, so pick the CTA size that wastes the
-        // fewest warp slots for this batch (at most JB_K1_MAX_WARPS warps)
+        // descriptors of every restart segment of the batch, then one lane per segment
         dim3 ugrid((b->max_nseg + JB_K0B_THREADS - 1) / JB_K0B_THREADS, (unsigned)b->seg_images.size());
         jb_k0b_segment_descs<<<ugrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
                                                               b->d_segs, b->d_status);

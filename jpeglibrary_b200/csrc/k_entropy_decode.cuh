@@ -1,4 +1,5 @@
-// k_entropy_decode.cuh -- K0 (restart-marker index) and K1a (restart-segment-parallel Huffman decode).
+// k_entropy_decode.cuh -- K0 (restart-marker index) and the byte-stream bit reader / 16-bit table look-up used by the
+// progressive (K1c) and lossless (K1d) scan kernels.  The baseline decoder proper is k_entropy_flat.cuh.
 //
 // Replaces, for a whole batch of images at once:
 //   JpegBitReader.FillBuffer / PeekBits / TryReadBits        (JpegBitReader.cs:95-204)
@@ -261,166 +262,4 @@ __device__ __forceinline__ uint32_t jb_huff_lookup(const JbHuffTable *t, uint32_
         if (e != 0) return e;
     }
     return jb_huff_lookup_slow(t, code16);
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1a: one thread per restart segment, 32 consecutive segments of one image per warp.
-// Every lane runs the same flat loop -- one Huffman symbol per iteration -- over its own segment,
-// so lanes never wait for each other at block boundaries.  Each lane assembles its current 8x8
-// block in a rotated shared-memory staging tile; whenever lanes complete blocks, the warp flushes
-// them two at a time (16 lanes x 8 bytes per block), so every coefficient block leaves the SM as
-// one full 128-byte line and is written exactly once.
-// ---------------------------------------------------------------------------------------------
-#define JB_K1_MAX_WARPS 8 // warps per CTA are chosen at launch: ceil(segments per image / 32), at most 8
-#define JB_K1_STAGE_BYTES (32 * 128)
-
-__device__ __forceinline__ uint32_t jb_stage_off(int lane, int z)
-{ // byte offset of coefficient z of lane's block inside the warp's staging tile; 8-byte pairs are
-  // rotated by the lane index: per-lane scattered stores spread over the banks and the 16-lane
-  // flush reads are conflict-free
-    return (uint32_t)(lane * 128 + ((((z >> 2) + lane) & 15) << 3) + ((z & 3) << 1));
-}
-
-__global__ void __launch_bounds__(JB_K1_MAX_WARPS * 32)
-jb_k1_huff_segments(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-                    const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
-                    const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
-                    int16_t *__restrict__ coef, uint32_t *__restrict__ status)
-{
-    extern __shared__ uint4 jb_smem[];
-    __shared__ JbDevImage s_im;
-    __shared__ uint2 s_binfo[JB_MAX_BLOCKS_PER_MCU]; // per block-in-mcu: x = comp<<28 | dc table offset/16, y = ac table offset/16
-    // grid = (CTAs per image, images): a CTA decodes blockDim.x consecutive segments of one image
-    const uint32_t image = image_list[blockIdx.y], first_seg = blockIdx.x * blockDim.x;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (first_seg >= images[image].nseg) return;
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
-        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    if (tid < JB_MAX_BLOCKS_PER_MCU) // table offsets in units of 16 bytes from the device table array
-        s_binfo[tid] = make_uint2(((uint32_t)s_im.blk_comp[tid] << 28) |
-                                      (uint32_t)(s_im.table_index[s_im.blk_dc[tid]] * (sizeof(JbHuffTable) / 16)),
-                                  (uint32_t)(s_im.table_index[s_im.blk_ac[tid]] * (sizeof(JbHuffTable) / 16)));
-    uint8_t *s_stage = reinterpret_cast<uint8_t *>(jb_smem) + wid * JB_K1_STAGE_BYTES;
-    for (int i = lane; i < JB_K1_STAGE_BYTES / 16; i += 32) reinterpret_cast<uint4 *>(s_stage)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
-
-    const uint32_t nseg = s_im.nseg;
-    const uint32_t seg = first_seg + tid;
-    const uint32_t dri = s_im.dri ? s_im.dri : s_im.total_mcus;
-    const int bpm = s_im.bpm;
-    const JbScanResult sr = scanres[image];
-    const uint8_t *data = arena + s_im.data_off;
-    const uint32_t *mk = marks + s_im.mark_base;
-
-    // segment bounds from the marker index
-    uint32_t left = 0, start = 0, stop = 0, err = 0; // left = blocks this lane still has to decode
-    bool last_needs_marker = false;
-    if (seg < nseg) {
-        const uint32_t my_nmcu = min(dri, s_im.total_mcus - seg * dri);
-        left = my_nmcu * bpm;
-        if (seg > 0) {
-            if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
-            else { err |= JB_ST_EXPECT_RST; left = 0; }
-        }
-        stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
-        // the reference expects RSTn or EOI right after every *complete* interval
-        // (JpegHuffmanBaselineScanDecoder.cs:139-154)
-        last_needs_marker = s_im.dri != 0 && my_nmcu == dri;
-    }
-    const bool had_work = left > 0;
-
-    JbBitReader br;
-    br.init(data, start, stop);
-    // per-lane decoder state
-    int b = 0; // block-in-mcu of the current block
-    int k = 0; // next zig-zag index; 0 = the DC symbol comes next
-    int pred_cur = 0, p0 = 0, p1 = 0, p2 = 0, p3 = 0; // DC predictors (current component / saved)
-    uint2 binfo = s_binfo[0];
-    const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(tables);
-    // address of this lane's current block in the coefficient store
-    uint8_t *gptr = reinterpret_cast<uint8_t *>(coef) + (s_im.coef_off + (uint64_t)seg * dri * bpm) * 128;
-    const uint32_t lane8 = (lane & 15) * 8;
-
-    while (__any_sync(0xFFFFFFFFu, left != 0)) {
-        bool finished = false;
-        if (left != 0) {
-            br.ensure32();
-            const bool is_dc = k == 0;
-            const uint32_t toff = is_dc ? (binfo.x & 0x0FFFFFFFu) : binfo.y;
-            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)toff * 16), br.peek16());
-            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; if (!is_dc) k = 64; }
-            br.skip(e & 0xFF);
-            const int sym = (int)(e >> 8);
-            int s = is_dc ? sym : (sym & 15);
-            const int r = is_dc ? 0 : (sym >> 4);
-            if (s > 16) { err |= JB_ST_BAD_CODE; s = 0; }
-            int v = 0;
-            if (s != 0) v = jb_extend((int)br.take(s), s);
-            if (is_dc) {
-                // ReadBlockBaseline :187-196
-                v += pred_cur;
-                pred_cur = v;
-                *reinterpret_cast<int16_t *>(s_stage + jb_stage_off(lane, 0)) = (int16_t)v;
-                k = 1;
-            } else if (s != 0) {
-                // :206-211
-                k += r;
-                *reinterpret_cast<int16_t *>(s_stage + jb_stage_off(lane, min(k, 63))) = (int16_t)v;
-                k++;
-            } else {
-                k = r == 0 ? 64 : k + 16; // EOB, or any other s==0 symbol skips 16 (:213-219)
-            }
-            finished = k >= 64;
-        }
-        // ---- cooperative flush of the blocks completed in this iteration, two per round:
-        //      lanes 0-15 move the lowest finished lane's block, lanes 16-31 the next one
-        uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished);
-        while (fin) {
-            const uint32_t fin2 = fin & (fin - 1);
-            const uint32_t pick = (lane & 16) ? fin2 : fin;
-            const int L = __ffs(pick) - 1; // -1: nothing for this half
-            const uint32_t glo = __shfl_sync(0xFFFFFFFFu, (uint32_t)reinterpret_cast<uint64_t>(gptr), L & 31);
-            const uint32_t ghi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(reinterpret_cast<uint64_t>(gptr) >> 32), L & 31);
-            if (L >= 0) {
-                uint2 *sp = reinterpret_cast<uint2 *>(s_stage + L * 128 + ((((lane & 15) + L) & 15) << 3));
-                const uint2 val = *sp;
-                *sp = make_uint2(0, 0);
-                *reinterpret_cast<uint2 *>((((uint64_t)ghi << 32) | glo) + lane8) = val;
-            }
-            fin = fin2 & (fin2 - 1);
-        }
-        if (finished) {
-            left--;
-            gptr += 128;
-            k = 0;
-            if (++b == bpm) b = 0;
-            const uint2 ni = s_binfo[b];
-            if ((ni.x ^ binfo.x) >> 28) {
-                const int comp = binfo.x >> 28, nc = ni.x >> 28;
-                if (comp == 0) p0 = pred_cur; else if (comp == 1) p1 = pred_cur; else if (comp == 2) p2 = pred_cur; else p3 = pred_cur;
-                pred_cur = nc == 0 ? p0 : nc == 1 ? p1 : nc == 2 ? p2 : p3;
-            }
-            binfo = ni;
-        }
-    }
-
-    if (had_work) {
-        // bits consumed beyond the real data => "The bit stream ended prematurely."
-        if (br.n < br.pad) err |= JB_ST_PREMATURE_END;
-        if (last_needs_marker && !(err & JB_ST_PREMATURE_END)) {
-            // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may
-            // remain before the marker (fill bytes FF are skipped by FillBuffer)
-            const int real = br.n - br.pad;
-            uint32_t p = br.pos;
-            while (p < stop && data[p] == 0xFF) p++;
-            bool marker_ok = seg < sr.nmarkers; // an RSTn or terminator follows this segment
-            if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u; // EOI ends the scan
-            if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
-        }
-    }
-    if (err) atomicOr(status + image, err);
 }
