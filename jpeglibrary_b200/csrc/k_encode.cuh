@@ -427,11 +427,22 @@ __device__ __forceinline__ uint32_t jb_encode_block(const JbEncImage &im, const 
         emit(t->code[sym], t->len[sym]);
         if (nb > 0) emit((uint32_t)b2, nb);
     };
-    runlen(dct, 0, p[0] - pred);
+    // the block's 64 coefficients come in as eight 128-bit loads and stay in registers: the unrolled loop below
+    // indexes them at compile time (64 scalar loads per thread left this kernel latency-bound at 16-24 % issue rate)
+    uint32_t w[32];
+    {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint4 q = __ldg(p4 + j);
+            w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+        }
+    }
+    runlen(dct, 0, (int)(int16_t)(w[0] & 0xFFFFu) - pred);
     int run = 0;
-#pragma unroll 1
+#pragma unroll
     for (int i = 1; i < 64; i++) {
-        const int t = p[i];
+        const int t = (i & 1) ? ((int)w[i >> 1] >> 16) : (int)(int16_t)(w[i >> 1] & 0xFFFFu);
         if (t == 0) { run++; continue; }
         while (run > 15) { emit(act->code[0xF0], act->len[0xF0]); run -= 16; }
         runlen(act, run, t);
