@@ -115,7 +115,7 @@ def measured_traffic(kernel, images):
         return None, None
 
 
-def cpu_sample_size(blobs, threads, target_s=12.0):
+def cpu_sample_size(blobs, threads, target_s=18.0):
     """Images for a cpu_baseline sample of about `target_s` seconds: calibrated on one image per thread."""
     _, dt = cpu_reference(blobs, threads, threads)
     per_round = max(dt, 1e-3)

@@ -8,6 +8,7 @@
  *   JpegScanDecoder.ProcessScan            (src/JpegLibrary/ScanDecoder/JpegScanDecoder.cs:14)
  *   JpegHuffmanBaselineScanDecoder         (ScanDecoder/JpegHuffmanBaselineScanDecoder.cs:51-268)
  *   JpegHuffmanProgressiveScanDecoder      (ScanDecoder/JpegHuffmanProgressiveScanDecoder.cs:57-470)
+ *   JpegHuffmanLosslessScanDecoder         (ScanDecoder/JpegHuffmanLosslessScanDecoder.cs:52-223)
  *   JpegBlockOutputWriter.WriteBlock sinks (JpegBlockOutputWriter.cs:17; app sinks
  *                                           apps/JpegDecode/JpegBufferOutputWriter8Bit.cs:28-60,
  *                                           apps/JpegDecode/JpegYCbCrToRgbConverter.cs:171-205)
@@ -84,7 +85,7 @@ typedef struct jb_scan_desc {
 typedef struct jb_image_desc {
     const uint8_t *data; /* host pointer (pinned memory from jb_pinned_alloc avoids a staging copy) */
     uint64_t length;
-    uint8_t sof;         /* 0 baseline, 1 extended, 2 progressive (JpegMarker.StartOfFrame0..2) */
+    uint8_t sof;         /* 0 baseline, 1 extended, 2 progressive, 3 lossless (JpegMarker.StartOfFrame0..3) */
     uint8_t precision;   /* P */
     uint8_t component_count;
     uint8_t reserved0;

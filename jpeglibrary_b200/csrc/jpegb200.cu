@@ -1269,6 +1269,7 @@ static int launch_kernels(jb_batch *b)
         }
     };
     JB_CUDA(ctx, jb_fill_async(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+    launches++;
     mark(nullptr);
     jb_k0_restart_scan<<<(unsigned)b->h_ranges.size(), JB_K0_THREADS, 0, st>>>(b->d_ranges, b->d_arena, b->d_marks, b->d_scan);
     launches++;
@@ -1333,6 +1334,7 @@ static int launch_kernels(jb_batch *b)
     mark("jb_k2_idct_color");
     jb_post_status<<<(b->count + 255) / 256, 256, 0, st>>>(b->h_mailbox, b->d_status, b->count,
                                                            b->ss_images.empty() ? nullptr : b->d_changed + JB_SS_ROUNDS);
+    launches++;
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
     return JB_OK;

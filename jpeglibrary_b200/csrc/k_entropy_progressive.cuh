@@ -37,11 +37,17 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
     const JbDevImage &im = images[image];
     const uint32_t scan_index = blockIdx.z; // every scan of the requested dependency level runs concurrently
     if (scan_index >= im.nscans) return;
-    const JbDevScan &sc = scans[im.scan_base + scan_index];
+    const JbDevScan sc = scans[im.scan_base + scan_index]; // by value: its fields are used in every inner loop
     if (sc.level != level) return;
     const int lane = threadIdx.x;
-    if (lane >= lanes_per_warp) return;
-    const uint32_t seg = blockIdx.x * lanes_per_warp + lane;
+    // AC refinement scans of serial streams (one stream per warp) are decoded by lane 0 on a shared-memory copy of
+    // the current block that the whole warp loads (prefetched one block ahead) and stores back: the refinement
+    // loop reads and rewrites the block's coefficients one by one, which from global memory costs an L2 round
+    // trip per coefficient (a store evicts the line from L1)
+    const bool coop = lanes_per_warp == 1 && sc.ncomp == 1 && sc.ss != 0 && sc.ah != 0;
+    __shared__ uint32_t s_blk[32];
+    if (!coop && lane >= lanes_per_warp) return;
+    const uint32_t seg = coop ? blockIdx.x : blockIdx.x * lanes_per_warp + lane;
     if (seg >= sc.nseg) return;
 
     const JbScanResult sr = scanres[sc.range];
@@ -95,7 +101,73 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
         }
     };
 
-    if (sc.ncomp > 1) {
+    const int p1 = 1 << al, m1 = -(1 << al);
+    // ---- AC refinement of one block (:313-419)
+    auto refine_block = [&](int16_t *blk, int ss, int se) {
+        int k = ss;
+        if (eobrun == 0) {
+            for (; k <= se; k++) {
+                const int sym = huff(sc.ac_tab[0]);
+                int r = sym >> 4, s = sym & 15;
+                if (s != 0) {
+                    s = jb_prog_bits(br, 1) != 0 ? p1 : m1;
+                } else if (r != 15) {
+                    eobrun = 1 << r;
+                    if (r != 0) eobrun += (int)jb_prog_bits(br, r);
+                    break;
+                }
+                do {
+                    int cv = blk[k];
+                    if (cv != 0) {
+                        if (jb_prog_bits(br, 1) != 0) {
+                            if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv >= 0 ? p1 : m1));
+                        }
+                    } else {
+                        if (--r < 0) break;
+                    }
+                    k++;
+                } while (k <= se);
+                if (s != 0 && k < 64) blk[k] = (int16_t)s;
+            }
+        }
+        if (eobrun > 0) {
+            for (; k <= se; k++) {
+                int cv = blk[k];
+                if (cv != 0) {
+                    if (jb_prog_bits(br, 1) != 0) {
+                        if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv > 0 ? p1 : m1));
+                    }
+                }
+            }
+            --eobrun;
+        }
+    };
+
+    if (coop) {
+        // ---- AC refinement, one stream per warp: lane 0 decodes, the warp moves the blocks
+        const int c = sc.comp[0];
+        const uint32_t *plane = reinterpret_cast<const uint32_t *>(store + (size_t)im.comp_plane_off[c] * 64);
+        const uint32_t pw = im.comp_plane_w[c];
+        uint32_t by = first / sc.wb, bx = first - by * sc.wb;
+        uint32_t nxt = count ? __ldg(plane + ((size_t)by * pw + bx) * 32 + lane) : 0u;
+        for (uint32_t u = first; u < first + count; u++) {
+            uint32_t *gblk = const_cast<uint32_t *>(plane) + ((size_t)by * pw + bx) * 32;
+            s_blk[lane] = nxt;
+            if (++bx == sc.wb) { bx = 0; by++; }
+            if (u + 1 < first + count) nxt = __ldg(plane + ((size_t)by * pw + bx) * 32 + lane); // prefetch
+            __syncwarp();
+            if (lane == 0 && !err) refine_block(reinterpret_cast<int16_t *>(s_blk), sc.ss, sc.se);
+            __syncwarp();
+            // write back the scan's band only: scans of the same level refine other bands of the same block concurrently
+            {
+                const uint32_t v = s_blk[lane];
+                int16_t *g16 = reinterpret_cast<int16_t *>(gblk);
+                if (2 * lane >= sc.ss && 2 * lane <= sc.se) g16[2 * lane] = (int16_t)(v & 0xFFFFu);
+                if (2 * lane + 1 >= sc.ss && 2 * lane + 1 <= sc.se) g16[2 * lane + 1] = (int16_t)(v >> 16);
+            }
+        }
+        if (lane != 0) return;
+    } else if (sc.ncomp > 1) {
         // ---- interleaved DC scan (:92-138)
         for (uint32_t u = first; u < first + count && !err; u++) {
             const uint32_t my = u / im.mcus_per_line, mx = u - my * im.mcus_per_line;
@@ -112,7 +184,6 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
     } else {
         const int c = sc.comp[0];
         const int ss = sc.ss, se = sc.se;
-        const int p1 = 1 << al, m1 = -(1 << al);
         for (uint32_t u = first; u < first + count && !err; u++) {
             const uint32_t by = u / sc.wb, bx = u - by * sc.wb;
             int16_t *blk = store + ((size_t)im.comp_plane_off[c] + (size_t)by * im.comp_plane_w[c] + bx) * 64;
@@ -120,7 +191,12 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
                 dc_block(blk, 0);
             } else if (sc.ah == 0) {
                 // ---- AC first scan (:259-305)
-                if (eobrun != 0) { eobrun--; continue; }
+                if (eobrun != 0) { // the whole run of end-of-band blocks at once
+                    const uint32_t skip = min((uint32_t)eobrun, first + count - u);
+                    eobrun -= (int)skip;
+                    u += skip - 1;
+                    continue;
+                }
                 for (int i = ss; i <= se; i++) {
                     const int sym = huff(sc.ac_tab[0]);
                     const int r = sym >> 4, s = sym & 15;
@@ -137,43 +213,7 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
                 }
             } else {
                 // ---- AC refinement (:313-419)
-                int k = ss;
-                if (eobrun == 0) {
-                    for (; k <= se; k++) {
-                        const int sym = huff(sc.ac_tab[0]);
-                        int r = sym >> 4, s = sym & 15;
-                        if (s != 0) {
-                            s = jb_prog_bits(br, 1) != 0 ? p1 : m1;
-                        } else if (r != 15) {
-                            eobrun = 1 << r;
-                            if (r != 0) eobrun += (int)jb_prog_bits(br, r);
-                            break;
-                        }
-                        do {
-                            int cv = blk[k];
-                            if (cv != 0) {
-                                if (jb_prog_bits(br, 1) != 0) {
-                                    if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv >= 0 ? p1 : m1));
-                                }
-                            } else {
-                                if (--r < 0) break;
-                            }
-                            k++;
-                        } while (k <= se);
-                        if (s != 0 && k < 64) blk[k] = (int16_t)s;
-                    }
-                }
-                if (eobrun > 0) {
-                    for (; k <= se; k++) {
-                        int cv = blk[k];
-                        if (cv != 0) {
-                            if (jb_prog_bits(br, 1) != 0) {
-                                if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv > 0 ? p1 : m1));
-                            }
-                        }
-                    }
-                    --eobrun;
-                }
+                refine_block(blk, ss, se);
             }
         }
     }
