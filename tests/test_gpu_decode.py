@@ -354,3 +354,22 @@ def test_pipelined_host_decode_matches_batch_decode():
         got = out[offs[i]:offs[i] + o.rgb.size].reshape(o.rgb.shape)
         assert np.array_equal(got, o.rgb)
     ctx.pinned_free(out.ctypes.data)
+
+
+@pytest.mark.parametrize("restart", [1, 0], ids=["restart", "selfsync"])
+def test_batch_with_more_huffman_tables_than_the_shared_memory_cache(restart):
+    """Every image brings its own optimised Huffman tables, and the images are so small that one CTA of the
+    Huffman kernel spans all of them: only the first four tables fit its shared-memory cache, the other images
+    decode through the global-memory fallback of the look-up (k_entropy_flat.cuh, JB_K1F_NOTAB)."""
+    blobs = [synth.encode_jpeg(synth.synth_rgb(60 + i, 96 + 16 * (i % 2), 64 if restart else 160), quality=50 + 8 * i,
+                               subsampling="4:2:0" if i % 2 else "4:4:4", optimize=True,
+                               restart_rows=restart) for i in range(6)]
+    tables = {bytes(J.Parsed(b).desc.tables[t].values[:16]) + bytes(J.Parsed(b).desc.tables[t].bits) for b in blobs for t in range(4)}
+    assert len(tables) > 8
+    with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
+        b.run()
+        assert b.status() == [0] * len(blobs)
+        for i, blob in enumerate(blobs):
+            assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
+    for blob in blobs[:2]:
+        check_coefficients(blob)
