@@ -1,36 +1,251 @@
-// Sketch of the drop-in: JpegDecoder keeps its marker loop (ProcessMarkerForDecode is a protected virtual
-// hook, JpegDecoder.cs:558) and hands each SOS to the GPU instead of JpegScanDecoder.Create (:592-599).
-// NOT compiled here (no .NET toolchain in the build image).
+// JpegLibrary.Cuda -- the drop-in for the decode hot path, written against JpegLibrary's PUBLIC surface only.
+//
+// JpegDecoder keeps everything it does on the host: SetInput / Identify / the marker loop of Decode()
+// (JpegDecoder.cs:509-550) and its DQT/DRI registries.  CudaJpegDecoder overrides the protected virtual hook
+// ProcessMarkerForDecode (JpegDecoder.cs:558): it lets the base class handle every marker, keeps its own copy of
+// what the base class hides (frame header, raw DHT bytes -- JpegHuffmanDecodingTable does not retain the code
+// length counts), and at StartOfScan hands the entropy-coded segment to libjpegb200 instead of
+// JpegScanDecoder.ProcessScan (:592-599).  Sequential frames are decoded at their SOS; progressive frames collect
+// their scans and are decoded at EOI, exactly where JpegHuffmanProgressiveScanDecoder.Dispose renders (:421-470).
+//
+// NOT compiled in this repository's build image (no .NET toolchain); the same C-ABI calls, in the same order, are
+// exercised by jpeglibrary_b200/api.py (ctypes), which the tests and bench.py run on the GPU.
 using System;
 using System.Buffers;
+using System.Collections.Generic;
+using System.IO;
+using System.Runtime.InteropServices;
 
 namespace JpegLibrary.Cuda
 {
-    /// <summary>Recognised GPU-aware sink: kernels store RGB straight into its (pinned or device) buffer;
-    /// WriteBlock is never called on the fast path (SURVEY 8b).</summary>
+    /// <summary>Recognised GPU-aware sink: kernels store pixels straight into its (pinned or device) buffer with the
+    /// semantics of apps/JpegDecode (JpegBufferOutputWriter8Bit + JpegYCbCrToRgbConverter); WriteBlock is never
+    /// called on the fast path (SURVEY 8b).</summary>
     public sealed class CudaRgbOutputWriter : JpegBlockOutputWriter
     {
         public IntPtr Buffer; public long Pitch; public long Capacity; public bool OnDevice; public int Format = Native.JB_OUT_RGB24;
         public override void WriteBlock(ref short blockRef, int componentIndex, int x, int y) =>
-            throw new InvalidOperationException("filled by the GPU");
+            throw new InvalidOperationException("CudaRgbOutputWriter is filled by the GPU, not by WriteBlock calls");
     }
 
-    public sealed class CudaJpegDecoder : JpegDecoder
+    public sealed unsafe class CudaJpegDecoder : JpegDecoder, IDisposable
     {
         private readonly IntPtr _ctx;
-        public CudaJpegDecoder(int device = 0) { Native.Check(IntPtr.Zero, Native.jb_ctx_create(device, out _ctx)); }
+        private JpegBlockOutputWriter? _writer;
+        private ReadOnlyMemory<byte> _input;
+        private JpegFrameHeader _frame;
+        private JpegMarker _sof;
+        private readonly List<Native.HuffSpec> _tables = new List<Native.HuffSpec>();
+        private readonly int[,] _latest = new int[2, 4];           // [class, id] -> index into _tables, -1 = undefined
+        private readonly List<Native.ScanDesc> _scans = new List<Native.ScanDesc>();
+
+        public CudaJpegDecoder(int device = 0)
+        {
+            Native.Check(IntPtr.Zero, Native.jb_ctx_create(device, out _ctx));
+            for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) _latest[c, i] = -1;
+        }
+
+        public void Dispose() => Native.jb_ctx_destroy(_ctx);
+
+        // JpegDecoder.SetInput / SetOutputWriter are not virtual: keep our own references next to the base class's.
+        public new void SetInput(ReadOnlyMemory<byte> input) { _input = input; base.SetInput(input); }
+        public new void SetOutputWriter(JpegBlockOutputWriter outputWriter) { _writer = outputWriter; base.SetOutputWriter(outputWriter); }
 
         protected override bool ProcessMarkerForDecode(JpegMarker marker, ref JpegReader reader)
         {
-            if (marker != JpegMarker.StartOfScan) return base.ProcessMarkerForDecode(marker, ref reader); // DHT/DQT/DRI/SOF stay managed
-            // 1. parse the scan header with the reference's own JpegScanHeader.TryParse
-            // 2. fill Native.ImageDesc from GetFrameHeader(), GetHuffmanTable(), GetQuantizationTable(), GetRestartInterval()
-            // 3. if the output writer is a CudaRgbOutputWriter: jb_decode(ctx, &desc, &out, 1, null)
-            //    else: request JB_OUT_PLANAR_I16 into a pinned buffer and replay WriteBlock in the reference's
-            //    order (JpegHuffmanBaselineScanDecoder.cs:99-137, 238-268) -- see jpeglibrary_b200/api.py
-            //    _replay_write_blocks for the exact sequence
-            // 4. advance `reader` past the entropy-coded segment (JpegReader.TryReadMarker skips it anyway)
-            throw new NotImplementedException("illustrative");
+            switch (marker)
+            {
+                case JpegMarker.StartOfFrame0: case JpegMarker.StartOfFrame1: case JpegMarker.StartOfFrame2: case JpegMarker.StartOfFrame3:
+                {
+                    JpegReader peek = reader; // JpegReader is a struct: an independent cursor over the same bytes
+                    if (peek.TryReadLength(out ushort len) && peek.TryReadBytes(len, out ReadOnlySequence<byte> body) &&
+                        JpegFrameHeader.TryParse(body, false, out JpegFrameHeader fh, out _))
+                    {
+                        _frame = fh; _sof = marker; _scans.Clear();
+                    }
+                    return base.ProcessMarkerForDecode(marker, ref reader); // validation + the public Width/Height/... properties
+                }
+                case JpegMarker.DefineHuffmanTable:
+                {
+                    JpegReader peek = reader;
+                    if (peek.TryReadLength(out ushort len) && peek.TryReadBytes(len, out ReadOnlySequence<byte> body)) RememberTables(body);
+                    return base.ProcessMarkerForDecode(marker, ref reader);
+                }
+                case JpegMarker.StartOfScan:
+                    ProcessScanOnGpu(ref reader);
+                    return true;
+                case JpegMarker.EndOfImage:
+                    if (_sof == JpegMarker.StartOfFrame2 && _scans.Count > 0) Submit(); // progressive: render after the last scan
+                    return false;
+                default:
+                    return base.ProcessMarkerForDecode(marker, ref reader); // DQT, DRI, APPn, COM, RSTn stay managed
+            }
+        }
+
+        // DHT: Tc/Th byte, 16 counts, then the symbols (JpegHuffmanDecodingTable.TryParse :122-291)
+        private void RememberTables(ReadOnlySequence<byte> body)
+        {
+            byte[] b = body.ToArray();
+            int p = 0;
+            while (p + 17 <= b.Length)
+            {
+                var s = new Native.HuffSpec { TableClass = (byte)(b[p] >> 4), Identifier = (byte)(b[p] & 15) };
+                int n = 0;
+                for (int i = 0; i < 16; i++) { s.Bits[i] = b[p + 1 + i]; n += b[p + 1 + i]; }
+                if (n > 256 || p + 17 + n > b.Length || s.TableClass > 1 || s.Identifier > 3) return; // the base class reports it
+                for (int i = 0; i < n; i++) s.Values[i] = b[p + 17 + i];
+                s.ValueCount = (ushort)n;
+                _latest[s.TableClass, s.Identifier] = _tables.Count;
+                _tables.Add(s);
+                p += 17 + n;
+            }
+        }
+
+        private void ProcessScanOnGpu(ref JpegReader reader)
+        {
+            if (_frame.Components is null) throw new InvalidDataException("Failed to decode JPEG data. Scan header appears before frame header.");
+            if (!reader.TryReadLength(out ushort len) || !reader.TryReadBytes(len, out ReadOnlySequence<byte> body) ||
+                !JpegScanHeader.TryParse(body, false, out JpegScanHeader sh, out _))
+                throw new InvalidDataException("Failed to decode JPEG data. Failed to parse scan header.");
+            var sd = new Native.ScanDesc
+            {
+                ComponentCount = sh.NumberOfComponents,
+                Ss = sh.StartOfSpectralSelection, Se = sh.EndOfSpectralSelection,
+                Ah = sh.SuccessiveApproximationBitPositionHigh, Al = sh.SuccessiveApproximationBitPositionLow,
+                RestartInterval = GetRestartInterval(),
+                EntropyOffset = (ulong)reader.ConsumedByteCount,
+            };
+            for (int i = 0; i < sh.NumberOfComponents; i++)
+            {
+                JpegScanComponentSpecificationParameters sc = sh.Components![i];
+                int found = -1;
+                for (int j = 0; j < _frame.NumberOfComponents; j++)
+                    if (_frame.Components[j].Identifier == sc.ScanComponentSelector) found = j; // InitDecodeComponents :38-48
+                if (found < 0) throw new InvalidDataException("Failed to decode JPEG data. The specified component is missing.");
+                sd.ComponentIndex[i] = (byte)found;
+                sd.DcTable[i] = (short)_latest[0, sc.DcEntropyCodingTableSelector & 3];
+                sd.AcTable[i] = (short)_latest[1, sc.AcEntropyCodingTableSelector & 3];
+            }
+            // the entropy-coded segment ends at the first marker that is neither a stuffed zero, a fill byte nor RSTn
+            int end = FindScanEnd(reader.RemainingBytes);
+            sd.EntropyLength = (ulong)end;
+            _scans.Add(sd);
+            reader.TryAdvance(end);
+            if (_sof != JpegMarker.StartOfFrame2) { Submit(); _scans.Clear(); } // sequential and lossless frames: one scan
+        }
+
+        private static int FindScanEnd(ReadOnlySequence<byte> data)
+        {
+            int pos = 0, prev = -1;
+            foreach (ReadOnlyMemory<byte> seg in data)
+            {
+                ReadOnlySpan<byte> s = seg.Span;
+                for (int i = 0; i < s.Length; i++, pos++)
+                {
+                    int b = s[i];
+                    if (prev == 0xFF && b != 0x00 && b != 0xFF && (b < 0xD0 || b > 0xD7)) return pos - 1;
+                    prev = b;
+                }
+            }
+            return pos;
+        }
+
+        // One jb_decode call for the frame: jb_image_desc from the collected headers, jb_output_desc from the writer.
+        private void Submit()
+        {
+            int n = _frame.NumberOfComponents;
+            var img = new Native.ImageDesc
+            {
+                Length = (ulong)_input.Length,
+                Sof = (byte)(_sof - JpegMarker.StartOfFrame0), Precision = _frame.SamplePrecision, ComponentCount = (byte)n,
+                Width = _frame.SamplesPerLine, Height = _frame.NumberOfLines,
+                ScanCount = (uint)_scans.Count, TableCount = (uint)_tables.Count,
+            };
+            for (int c = 0; c < n; c++)
+            {
+                JpegFrameComponentSpecificationParameters fc = _frame.Components![c];
+                img.H[c] = fc.HorizontalSamplingFactor; img.V[c] = fc.VerticalSamplingFactor;
+                if (_sof != JpegMarker.StartOfFrame3)
+                {
+                    JpegQuantizationTable q = GetQuantizationTable(fc.QuantizationTableSelector);   // zig-zag order (JpegQuantizationTable.cs:21)
+                    if (q.IsEmpty) throw new InvalidDataException($"Failed to decode JPEG data. Quantization table of component {c} is not defined.");
+                    for (int i = 0; i < 64; i++) img.Quant[c * 64 + i] = q.Elements[i];
+                }
+            }
+            Native.ScanDesc[] scans = _scans.ToArray();
+            Native.HuffSpec[] tables = _tables.ToArray();
+            using MemoryHandle pin = _input.Pin();
+            fixed (Native.ScanDesc* ps = scans)
+            fixed (Native.HuffSpec* pt = tables)
+            {
+                img.Data = (byte*)pin.Pointer; img.Scans = ps; img.Tables = pt;
+                if (_writer is CudaRgbOutputWriter w)
+                {
+                    var o = new Native.OutputDesc { Dst = (void*)w.Buffer, Pitch = (ulong)w.Pitch, Capacity = (ulong)w.Capacity, Format = w.Format, OnDevice = w.OnDevice ? 1 : 0 };
+                    Native.Check(_ctx, Native.jb_decode(_ctx, &img, &o, 1, null));
+                    return;
+                }
+                // compatibility path: the exact samples WriteBlock receives come back as unclamped int16 planes and the
+                // reference's call sequence is replayed on the host
+                short[] planes = new short[n * img.Width * img.Height];
+                fixed (short* pp = planes)
+                {
+                    var o = new Native.OutputDesc { Dst = pp, Pitch = 0, Capacity = (ulong)planes.Length * 2, Format = Native.JB_OUT_PLANAR_I16, OnDevice = 0 };
+                    Native.Check(_ctx, Native.jb_decode(_ctx, &img, &o, 1, null));
+                }
+                ReplayWriteBlocks(planes, scans[0]);
+            }
+        }
+
+        // JpegHuffmanBaselineScanDecoder.ProcessScan :99-137 + WriteBlock :225-268 (sequential frames: MCU order, scan
+        // component order, v x h blocks, each expanded to hs x vs replicated 8x8 blocks); JpegBlockAllocator.Flush
+        // :120-149 (progressive: per component, block rows then columns).
+        private void ReplayWriteBlocks(short[] planes, Native.ScanDesc firstScan)
+        {
+            JpegBlockOutputWriter writer = _writer ?? throw new InvalidOperationException("The output buffer is not specified.");
+            int n = _frame.NumberOfComponents, W = _frame.SamplesPerLine, H = _frame.NumberOfLines;
+            int hmax = 1, vmax = 1;
+            foreach (JpegFrameComponentSpecificationParameters c in _frame.Components!) { hmax = Math.Max(hmax, c.HorizontalSamplingFactor); vmax = Math.Max(vmax, c.VerticalSamplingFactor); }
+            // lossless frames: JpegPartialScanlineAllocator flushes 8-row bands of 8x8 tiles as they complete; a clipping
+            // writer sees the same samples from the per-component order used here
+            int unit = _sof == JpegMarker.StartOfFrame3 ? 1 : 8;
+            Span<short> block = stackalloc short[64];
+            void Emit(int ci, int x, int y, Span<short> blk)
+            {
+                for (int r = 0; r < 8; r++)
+                    for (int c = 0; c < 8; c++)
+                        blk[r * 8 + c] = (y + r < H && x + c < W) ? planes[(ci * H + y + r) * W + x + c] : (short)0;
+                writer.WriteBlock(ref blk[0], ci, x, y);
+            }
+            if (_sof == JpegMarker.StartOfFrame2 || unit == 1)
+            {
+                int wblk = (W + 7) / 8, hblk = (H + 7) / 8;
+                for (int ci = 0; ci < n; ci++)
+                {
+                    int hs = hmax / _frame.Components[ci].HorizontalSamplingFactor, vs = vmax / _frame.Components[ci].VerticalSamplingFactor;
+                    int cw = (wblk + hs - 1) / hs, ch = (hblk + vs - 1) / vs;
+                    for (int row = 0; row < ch; row++)
+                        for (int col = 0; col < cw; col++)
+                            for (int sv = 0; sv < vs; sv++)
+                                for (int sh = 0; sh < hs; sh++)
+                                    Emit(ci, col * hs * 8 + 8 * sh, row * vs * 8 + 8 * sv, block);
+                }
+                return;
+            }
+            int mcusX = (W + 8 * hmax - 1) / (8 * hmax), mcusY = (H + 8 * vmax - 1) / (8 * vmax);
+            for (int my = 0; my < mcusY; my++)
+                for (int mx = 0; mx < mcusX; mx++)
+                    for (int k = 0; k < firstScan.ComponentCount; k++)
+                    {
+                        int ci = firstScan.ComponentIndex[k];
+                        int h = _frame.Components[ci].HorizontalSamplingFactor, v = _frame.Components[ci].VerticalSamplingFactor;
+                        int hs = hmax / h, vs = vmax / v;
+                        for (int by = 0; by < v; by++)
+                            for (int bx = 0; bx < h; bx++)
+                                for (int sv = 0; sv < vs; sv++)
+                                    for (int sh = 0; sh < hs; sh++)
+                                        Emit(ci, (mx * hmax + bx) * 8 + 8 * sh, (my * vmax + by) * 8 + 8 * sv, block);
+                    }
         }
     }
 }

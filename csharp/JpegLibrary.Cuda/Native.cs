@@ -47,6 +47,33 @@ namespace JpegLibrary.Cuda
         [DllImport(Lib)] public static extern int jb_decode_batch_status(IntPtr batch, int* status, int count);
         [DllImport(Lib)] public static extern void jb_decode_batch_destroy(IntPtr batch);
         [DllImport(Lib)] public static extern int jb_decode(IntPtr ctx, ImageDesc* images, OutputDesc* outputs, int count, int* status);
+        [DllImport(Lib)] public static extern int jb_decode_batch_upload(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_decode_batch_launch(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_decode_batch_finish(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_ctx_synchronize(IntPtr ctx);
+        [DllImport(Lib)] public static extern int jb_device_alloc(IntPtr ctx, UIntPtr bytes, out IntPtr p);
+        [DllImport(Lib)] public static extern int jb_device_free(IntPtr ctx, IntPtr p);
+
+        // encode path (JpegEncoder.TransformBlocks / BuildHuffmanTables / WritePreparedScanData, JpegEncoder.cs:414-656)
+        [StructLayout(LayoutKind.Sequential)]
+        public struct EncodeDesc
+        {
+            public void* Pixels; public ulong Pitch; public int OnDevice, Format;
+            public ushort Width, Height; public byte ComponentCount;
+            public fixed byte H[4]; public fixed byte V[4]; public fixed byte Tq[4]; public fixed byte Td[4]; public fixed byte Ta[4];
+            public fixed byte Reserved[3]; public fixed ushort Quant[4 * 64]; public fixed byte QuantPresent[4];
+        }
+        [DllImport(Lib)] public static extern int jb_encode_batch_create(IntPtr ctx, EncodeDesc* images, int count, out IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_encode_batch_transform(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_encode_batch_histograms(IntPtr batch, uint* hist, int count);
+        [DllImport(Lib)] public static extern int jb_encode_batch_build_tables(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_encode_batch_set_table(IntPtr batch, int image, HuffSpec* table);
+        [DllImport(Lib)] public static extern int jb_encode_batch_pack(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_encode_batch_finish(IntPtr batch);
+        [DllImport(Lib)] public static extern int jb_encode_batch_get_table(IntPtr batch, int image, int tableClass, int identifier, HuffSpec* table);
+        [DllImport(Lib)] public static extern int jb_encode_batch_scan_length(IntPtr batch, int image, ulong* length);
+        [DllImport(Lib)] public static extern int jb_encode_batch_read_scan(IntPtr batch, int image, byte* dst, ulong capacity);
+        [DllImport(Lib)] public static extern void jb_encode_batch_destroy(IntPtr batch);
 
         // status code -> the exception the managed decoder throws in the same situation
         public static void Check(IntPtr ctx, int rc)
