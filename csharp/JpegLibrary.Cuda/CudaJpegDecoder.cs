@@ -101,6 +101,32 @@ namespace JpegLibrary.Cuda
             }
         }
 
+        // Tables that did not come through this decoder's marker loop (JpegDecoder.LoadTables / SetHuffmanTable,
+        // JpegDecoder.cs:313-319, :768-860, used for TIFF-style abbreviated streams) are only visible as
+        // JpegHuffmanDecodingTable objects, which keep no code-length counts.  Their DHT form is recovered from the
+        // public Lookup(code16) (JpegHuffmanDecodingTable.cs:73-85): walking the 16-bit code space in increasing order
+        // visits the canonical codes in DHT order.
+        private int TableIndex(int tableClass, int identifier)
+        {
+            if (_latest[tableClass, identifier] >= 0) return _latest[tableClass, identifier];
+            JpegHuffmanDecodingTable? t = GetHuffmanTable(tableClass == 0, (byte)identifier);
+            if (t is null) return -1;
+            var s = new Native.HuffSpec { TableClass = (byte)tableClass, Identifier = (byte)identifier };
+            int n = 0;
+            for (int code = 0; code < 0x10000 && n < 256;)
+            {
+                JpegHuffmanDecodingTable.Entry e = t.Lookup(code);
+                if (e.CodeSize == 0 || e.CodeSize > 16) break;          // past the last code: only the all-ones prefix is left
+                s.Bits[e.CodeSize - 1]++;
+                s.Values[n++] = e.SymbolValue;
+                code += 1 << (16 - e.CodeSize);                          // first 16-bit pattern of the next canonical code
+            }
+            s.ValueCount = (ushort)n;
+            _latest[tableClass, identifier] = _tables.Count;
+            _tables.Add(s);
+            return _latest[tableClass, identifier];
+        }
+
         private void ProcessScanOnGpu(ref JpegReader reader)
         {
             if (_frame.Components is null) throw new InvalidDataException("Failed to decode JPEG data. Scan header appears before frame header.");
@@ -123,8 +149,8 @@ namespace JpegLibrary.Cuda
                     if (_frame.Components[j].Identifier == sc.ScanComponentSelector) found = j; // InitDecodeComponents :38-48
                 if (found < 0) throw new InvalidDataException("Failed to decode JPEG data. The specified component is missing.");
                 sd.ComponentIndex[i] = (byte)found;
-                sd.DcTable[i] = (short)_latest[0, sc.DcEntropyCodingTableSelector & 3];
-                sd.AcTable[i] = (short)_latest[1, sc.AcEntropyCodingTableSelector & 3];
+                sd.DcTable[i] = (short)TableIndex(0, sc.DcEntropyCodingTableSelector & 3);
+                sd.AcTable[i] = (short)TableIndex(1, sc.AcEntropyCodingTableSelector & 3);
             }
             // the entropy-coded segment ends at the first marker that is neither a stuffed zero, a fill byte nor RSTn
             int end = FindScanEnd(reader.RemainingBytes);

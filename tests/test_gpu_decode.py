@@ -281,7 +281,9 @@ def test_progressive_and_sequential_in_one_batch():
     blobs = [synth.synth_jpeg(3, 320, 240, progressive=True, subsampling="4:4:4"),
              synth.synth_jpeg(4, 320, 240, restart_rows=1),
              golden_bytes("progress.jpg"),
-             synth.synth_jpeg(5, 640, 360)]
+             synth.synth_jpeg(5, 640, 360),
+             golden_bytes("lossless4_s22.jpg"),
+             golden_bytes("cramps.jpg")]
     with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
         b.run()
         assert b.status() == [0] * len(blobs)
