@@ -1650,13 +1650,14 @@ struct jb_encode_batch {
 };
 
 static void launch_k3(int nc, int hs, int vs, dim3 grid, cudaStream_t st, const JbEncImage *im, const uint32_t *list,
-                      const uint16_t *q, int16_t *coef)
+                      const uint16_t *q, int16_t *coef, int upw)
 {
-    if (nc == 1) jb_k3_fdct_quant<1, 1, 1><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
-    else if (hs == 1 && vs == 1) jb_k3_fdct_quant<3, 1, 1><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
-    else if (hs == 2 && vs == 1) jb_k3_fdct_quant<3, 2, 1><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
-    else if (hs == 1 && vs == 2) jb_k3_fdct_quant<3, 1, 2><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
-    else jb_k3_fdct_quant<3, 2, 2><<<grid, JB_K3_THREADS, 0, st>>>(im, list, q, coef);
+    const int T = JB_K3W_WARPS * 32;
+    if (nc == 1) jb_k3_fdct_quant_warp<1, 1, 1><<<grid, T, 0, st>>>(im, list, q, coef, upw);
+    else if (hs == 1 && vs == 1) jb_k3_fdct_quant_warp<3, 1, 1><<<grid, T, 0, st>>>(im, list, q, coef, upw);
+    else if (hs == 2 && vs == 1) jb_k3_fdct_quant_warp<3, 2, 1><<<grid, T, 0, st>>>(im, list, q, coef, upw);
+    else if (hs == 1 && vs == 2) jb_k3_fdct_quant_warp<3, 1, 2><<<grid, T, 0, st>>>(im, list, q, coef, upw);
+    else jb_k3_fdct_quant_warp<3, 2, 2><<<grid, T, 0, st>>>(im, list, q, coef, upw);
 }
 
 extern "C" {
@@ -1758,7 +1759,7 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         for (auto &x : b->groups) if (x.nc == e.component_count && x.hs == hs && x.vs == vs) g = &x;
         if (!g) { b->groups.push_back({e.component_count, hs, vs, {}, 0, 0}); g = &b->groups.back(); }
         g->list.push_back((uint32_t)i);
-        const uint32_t tile_mcus = JB_K3_BLOCKS / bpm;
+        const uint32_t tile_mcus = e.component_count == 1 ? 16 : 32 / bpm; // MCUs a warp transforms per iteration (K3)
         g->max_tiles = std::max(g->max_tiles, (d.mcus_per_line + tile_mcus - 1) / tile_mcus * d.mcus_per_col);
     }
     b->coef_blocks = blocks; b->raw_bytes = raw; b->out_bytes = outb; b->pixel_bytes = pixels;
@@ -1819,8 +1820,11 @@ int jb_encode_batch_transform(jb_encode_batch *b)
     JB_CUDA(ctx, jb_fill_async(b->d_hist, 0, sizeof(uint32_t) * 8 * 256 * b->count, st));
     b->launches = 0;
     for (const auto &g : b->groups) {
-        dim3 grid(g.max_tiles, (unsigned)g.list.size());
-        launch_k3(g.nc, g.hs, g.vs, grid, st, b->d_images, b->d_list + g.list_off, b->d_quant, b->d_coef);
+        const uint64_t total = (uint64_t)g.max_tiles * g.list.size();
+        const int upw = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16 * 8)));
+        const uint32_t per_cta = (uint32_t)upw * JB_K3W_WARPS;
+        dim3 grid((g.max_tiles + per_cta - 1) / per_cta, (unsigned)g.list.size());
+        launch_k3(g.nc, g.hs, g.vs, grid, st, b->d_images, b->d_list + g.list_off, b->d_quant, b->d_coef, upw);
         b->launches++;
     }
     dim3 hgrid((b->max_blocks + 255) / 256, b->count);

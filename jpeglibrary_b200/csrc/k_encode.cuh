@@ -18,6 +18,7 @@
 #pragma once
 #include "jb_device.cuh"
 #include "k_idct_color_fast.cuh" // jb_c_nat2zz
+#include "k_idct_color_warp.cuh" // jb_nat2zz_c
 
 struct JbEncImage {
     uint64_t pix_ptr;   // device address of the input pixels
@@ -72,8 +73,6 @@ __device__ __forceinline__ void jb_fdct8(const float s[8], float d[8])
     d[7] = __fsub_rn(c0, c3);
 }
 
-#define JB_K3_THREADS 384
-#define JB_K3_BLOCKS 48
 
 // apps/JpegEncode/JpegRgbToYCbCrConverter.cs:40-56 evaluated in fp32 like the C#:
 // Fix(0.299)=19595 Fix(0.587)=38470 Fix(0.114)=7471 Fix(0.168735892)=11058 Fix(0.331264108)=21710
@@ -86,105 +85,188 @@ __device__ __forceinline__ void jb_rgb_to_ycc(int r, int g, int b, int &y, int &
     y &= 0xFF; cb &= 0xFF; cr &= 0xFF; // (byte) casts
 }
 
-// HS, VS: luma sampling factors (chroma is 1x1); NC = 1 or 3
+// ---------------------------------------------------------------------------------------------
+// K3 (second generation; the first one used 8 threads per block with CTA-wide phases): warp-autonomous, ONE THREAD PER 8x8
+// BLOCK like the decoder's K2 (k_idct_color_warp.cuh).  A warp owns a unit of 32/BPM MCUs: it converts the unit's
+// pixels into component planes in shared memory (4 pixels = three 32-bit loads per lane), then every lane gathers
+// its block (box filter for sub-sampled chroma), runs both FDCT passes in registers, quantises with true fp32
+// division and writes its 128-byte zig-zag block with eight 128-bit stores.  No transposes, no CTA barriers.
+// ---------------------------------------------------------------------------------------------
+#define JB_K3W_WARPS 4
+
+template <int K>
+__device__ __forceinline__ void jb_k3w_col(const float (&p1)[64], float (&F)[64])
+{
+    float y[8], d[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) y[e] = p1[e * 8 + K];
+    jb_fdct8(y, d); // pass 2: d[mr] = F[vertical mr][horizontal K]
+#pragma unroll
+    for (int mr = 0; mr < 8; mr++) F[mr * 8 + K] = d[mr];
+}
+
 template <int NC, int HS, int VS>
-__global__ void __launch_bounds__(JB_K3_THREADS)
-jb_k3_fdct_quant(const JbEncImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-                 const uint16_t *__restrict__ quant, int16_t *__restrict__ coef)
+__global__ void __launch_bounds__(JB_K3W_WARPS * 32, 4)
+jb_k3_fdct_quant_warp(const JbEncImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                      const uint16_t *__restrict__ quant, int16_t *__restrict__ coef, int units_per_warp)
 {
     constexpr int BPM = NC == 1 ? 1 : HS * VS + 2;
-    constexpr int TILE_MCUS = JB_K3_BLOCKS / BPM;
-    constexpr int TW = TILE_MCUS * 8 * HS, TH = 8 * VS;
-    __shared__ uint8_t s_c[3][TH][TW + 4];          // component planes at full resolution, 0 outside the image
-    __shared__ __align__(16) float s_f[JB_K3_BLOCKS * 72];
-    __shared__ __align__(16) int16_t s_out[JB_K3_BLOCKS * 64];
+    constexpr int UM = NC == 1 ? 16 : 32 / BPM; // MCUs per unit
+    constexpr int NB = UM * BPM;
+    constexpr int TW = UM * 8 * HS, TH = 8 * VS;
+    __shared__ __align__(16) uint8_t s_c[JB_K3W_WARPS][NC][TH][TW]; // component planes at full resolution, 0 outside the image
+    // 1 / (8 q) in fp64, NATURAL order.  ZigZagAndQuantizeBlock divides the fp32 coefficient (after the exact
+    // MultiplyInplace(0.125)) by the quantiser in fp32 (JpegEncoder.cs:812-826).  RN32(F / (8q)) is obtained here as
+    // RN32(RN64((double)F * RN64(1 / (8q)))): for a 24-bit F and an integer q < 2^16 the exact quotient is never an
+    // fp32 rounding tie (q's odd part would need a 25-bit multiple to fit 24 bits) and lies at least 2^-41 (relative)
+    // from the nearest fp32 rounding boundary unless it is exactly representable, while the fp64 product is within
+    // 2^-52 of it -- so the double rounding is innocuous.  Checked on 9.2e8 random and adversarial (F, q) pairs against
+    // IEEE fp32 division (0 mismatches); three instructions instead of the ~12-instruction div.rn sequence with its
+    // slow-path branch per coefficient.
+    __shared__ __align__(16) double s_rq[NC * 64];
     __shared__ JbEncImage s_im;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t image = image_list[blockIdx.y];
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
-        for (int i = tid; i < (int)(sizeof(JbEncImage) / 4); i += JB_K3_THREADS) dst[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(JbEncImage) / 4); i += JB_K3W_WARPS * 32) dst[i] = src[i];
     }
     __syncthreads();
-    const uint32_t strips = (s_im.mcus_per_line + TILE_MCUS - 1) / TILE_MCUS;
-    const uint32_t mcu_row = blockIdx.x / strips;
-    const uint32_t mcu_col0 = (blockIdx.x - mcu_row * strips) * TILE_MCUS;
-    if (mcu_row >= s_im.mcus_per_col) return;
-    const int nmcu = (int)min((uint32_t)TILE_MCUS, s_im.mcus_per_line - mcu_col0);
-    const int W = s_im.width, H = s_im.height;
-    const int x0 = mcu_col0 * 8 * HS, y0 = mcu_row * TH;
-    const uint8_t *pix = reinterpret_cast<const uint8_t *>(s_im.pix_ptr);
-    const int fmt = s_im.in_format;
-    const int bpp = fmt == 2 ? 1 : 3;
-
-    // ---- E1 + E2: pixels -> component planes (JpegBufferInputReader zero-fills outside the image)
-    for (int i = tid; i < TW * TH; i += JB_K3_THREADS) {
-        const int py = i / TW, px = i - py * TW;
-        const int x = x0 + px, y = y0 + py;
-        int c0 = 0, c1 = 0, c2 = 0;
-        if (x < W && y < H && px < nmcu * 8 * HS) {
-            const uint8_t *p = pix + (uint64_t)y * s_im.pix_pitch + (uint64_t)x * bpp;
-            if (fmt == 0) jb_rgb_to_ycc(p[0], p[1], p[2], c0, c1, c2);
-            else if (fmt == 1) { c0 = p[0]; c1 = p[1]; c2 = p[2]; }
-            else c0 = p[0];
-        }
-        s_c[0][py][px] = (uint8_t)c0;
-        if (NC == 3) { s_c[1][py][px] = (uint8_t)c1; s_c[2][py][px] = (uint8_t)c2; }
-    }
+    for (int i = tid; i < NC * 64; i += JB_K3W_WARPS * 32)
+        s_rq[i] = 0.125 / (double)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
     __syncthreads();
 
-    // ---- E3 + E4 + E5 per block: 8 threads per block, thread r owns row r (pass 1) / column r (pass 2)
-    const int j = tid >> 3, r = tid & 7;
+    const int j = lane;
     const int m = j / BPM, b = j - m * BPM;
-    const bool valid = m < nmcu;
     int c = 0, bx, by;
     if (NC == 1 || b < HS * VS) { bx = m * HS + (b % HS); by = b / HS; }
     else { c = b - HS * VS + 1; bx = m; by = 0; }
-    float *fb = s_f + j * 72;
-    float y8[8], d8[8];
-    if (valid) {
-        if (c == 0) {
+    const double *rq = s_rq + c * 64;
+    const int W = s_im.width, H = s_im.height;
+    const uint32_t mpl = s_im.mcus_per_line;
+    const uint32_t upr = (mpl + UM - 1) / UM, nunits = upr * s_im.mcus_per_col;
+    const uint8_t *pix = reinterpret_cast<const uint8_t *>(s_im.pix_ptr);
+    const uint64_t pitch = s_im.pix_pitch;
+    const int fmt = s_im.in_format;
+    const bool vec_ok = fmt != 2 && ((s_im.pix_ptr | pitch) & 3u) == 0; // 4 pixels = 12 bytes as three aligned words
+    uint8_t (*pl)[TH][TW] = s_c[wid];
+
+    uint32_t unit = (blockIdx.x * JB_K3W_WARPS + wid) * (uint32_t)units_per_warp;
+    const uint32_t unit_end = min(unit + (uint32_t)units_per_warp, nunits);
+    for (; unit < unit_end; unit++) {
+        const uint32_t mcu_row = unit / upr, ucol = unit - mcu_row * upr;
+        const uint32_t mcu_col0 = ucol * UM;
+        const int nmcu = (int)min((uint32_t)UM, mpl - mcu_col0);
+        const int x0 = mcu_col0 * 8 * HS, y0 = mcu_row * TH;
+        const int wlim = min(W - x0, nmcu * 8 * HS); // pixels of this unit's rows that exist
+
+        // ---- E1 + E2: pixels -> component planes (JpegBufferInputReader zero-fills outside the image)
+        __syncwarp();
+        for (int g = lane; g < TW * TH / 4; g += 32) {
+            const int py = g / (TW / 4), px = (g - py * (TW / 4)) * 4;
+            const int y = y0 + py;
+            uint32_t o0 = 0, o1 = 0, o2 = 0; // four samples of each component
+            if (y < H && px < wlim) {
+                const uint8_t *p = pix + (uint64_t)y * pitch + (uint64_t)(x0 + px) * (fmt == 2 ? 1 : 3);
+                if (vec_ok && px + 4 <= wlim) {
+                    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(p)), w1 = __ldg(reinterpret_cast<const uint32_t *>(p) + 1),
+                                   w2 = __ldg(reinterpret_cast<const uint32_t *>(p) + 2);
+                    // bytes: a0 b0 c0 a1 | b1 c1 a2 b2 | c2 a3 b3 c3
+                    const uint32_t a4 = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // a0 a1 a2 a3
+                    const uint32_t b4 = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // b0 b1 b2 b3
+                    const uint32_t c4 = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // c0 c1 c2 c3
+                    if (fmt == 1) { o0 = a4; o1 = b4; o2 = c4; }
+                    else {
 #pragma unroll
-            for (int e = 0; e < 8; e++) y8[e] = (float)((int)s_c[0][by * 8 + r][bx * 8 + e] - 128);
-        } else {
-            // box filter: sum of HS x VS samples, (sum + delta) >> shift (JpegEncoder.cs:777-785)
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                int sum = 0;
-#pragma unroll
-                for (int dy = 0; dy < VS; dy++)
-#pragma unroll
-                    for (int dx = 0; dx < HS; dx++) sum += s_c[c][r * VS + dy][(bx * 8 + e) * HS + dx];
-                constexpr int SH = (HS == 2 ? 1 : 0) + (VS == 2 ? 1 : 0);
-                if constexpr (SH > 0) sum = (sum + (1 << (SH - 1))) >> SH;
-                y8[e] = (float)(sum - 128);
+                        for (int i = 0; i < 4; i++) {
+                            int yy, cb, cr;
+                            jb_rgb_to_ycc((a4 >> (8 * i)) & 0xFF, (b4 >> (8 * i)) & 0xFF, (c4 >> (8 * i)) & 0xFF, yy, cb, cr);
+                            o0 |= (uint32_t)yy << (8 * i); o1 |= (uint32_t)cb << (8 * i); o2 |= (uint32_t)cr << (8 * i);
+                        }
+                    }
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 4; i++) {
+                        if (px + i >= wlim) break;
+                        const uint8_t *q = p + i * (fmt == 2 ? 1 : 3);
+                        int yy = 0, cb = 0, cr = 0;
+                        if (fmt == 0) jb_rgb_to_ycc(q[0], q[1], q[2], yy, cb, cr);
+                        else if (fmt == 1) { yy = q[0]; cb = q[1]; cr = q[2]; }
+                        else yy = q[0];
+                        o0 |= (uint32_t)yy << (8 * i); o1 |= (uint32_t)cb << (8 * i); o2 |= (uint32_t)cr << (8 * i);
+                    }
+                }
+            }
+            *reinterpret_cast<uint32_t *>(&pl[0][py][px]) = o0;
+            if (NC == 3) {
+                *reinterpret_cast<uint32_t *>(&pl[1][py][px]) = o1;
+                *reinterpret_cast<uint32_t *>(&pl[2][py][px]) = o2;
             }
         }
-        jb_fdct8(y8, d8); // pass 1 (src.TransposeInto(temp); FDCT over temp's rows = along this row)
+        __syncwarp();
+
+        // ---- E3 + E4 + E5: one block per lane
+        if (j < NB && m < nmcu) {
+            float p1[64];
 #pragma unroll
-        for (int k = 0; k < 8; k++) fb[k * 8 + r] = d8[k];
-    }
-    __syncwarp();
-    if (valid) {
-        const float4 lo = *reinterpret_cast<const float4 *>(fb + r * 8);
-        const float4 hi = *reinterpret_cast<const float4 *>(fb + r * 8 + 4);
-        y8[0] = lo.x; y8[1] = lo.y; y8[2] = lo.z; y8[3] = lo.w;
-        y8[4] = hi.x; y8[5] = hi.y; y8[6] = hi.z; y8[7] = hi.w;
-        jb_fdct8(y8, d8); // pass 2: d8[mr] = F[vertical mr][horizontal r]
-        const uint16_t *q = quant + s_im.quant_off + c * 64;
+            for (int r = 0; r < 8; r++) {
+                float s8[8], d8[8];
+                if (c == 0) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(&pl[0][by * 8 + r][bx * 8]);
 #pragma unroll
-        for (int mr = 0; mr < 8; mr++) {
-            const int z = jb_c_nat2zz[mr * 8 + r];
-            // MultiplyInplace(0.125), coefficient / element, MathF.Round -> (short)
-            const float v = __fdiv_rn(__fmul_rn(d8[mr], 0.125f), (float)q[z]);
-            s_out[j * 64 + z] = (int16_t)__float2int_rn(v);
+                    for (int e = 0; e < 8; e++) // (float)(sample - 128) through the fp32 magic number (no XU conversion)
+                        s8[e] = __fsub_rn(__int_as_float(0x4B400000 + (int)(((e < 4 ? v.x : v.y) >> (8 * (e & 3))) & 0xFF)), 12582912.0f + 128.0f);
+                } else {
+                    // box filter: sum of HS x VS samples, (sum + delta) >> shift (JpegEncoder.cs:777-785), on 16-bit
+                    // SIMD lanes: bytes of HS*8 consecutive samples of VS rows
+                    constexpr int SH = (HS == 2 ? 1 : 0) + (VS == 2 ? 1 : 0);
+                    uint32_t acc[4] = {0, 0, 0, 0}; // eight 16-bit sums: acc[i] = sum[2i] | sum[2i+1] << 16
+#pragma unroll
+                    for (int dy = 0; dy < VS; dy++) {
+                        const uint8_t *row = &pl[NC == 3 ? c : 0][r * VS + dy][bx * 8 * HS];
+                        if (HS == 2) {
+                            const uint4 v = *reinterpret_cast<const uint4 *>(row);
+                            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int i = 0; i < 4; i++) acc[i] += (w[i] & 0x00FF00FFu) + ((w[i] >> 8) & 0x00FF00FFu); // pairs
+                        } else {
+                            const uint2 v = *reinterpret_cast<const uint2 *>(row);
+                            acc[0] += __byte_perm(v.x, 0, 0x4140); acc[1] += __byte_perm(v.x, 0, 0x4342);
+                            acc[2] += __byte_perm(v.y, 0, 0x4140); acc[3] += __byte_perm(v.y, 0, 0x4342);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        int sum = (int)((acc[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+                        if constexpr (SH > 0) sum = (sum + (1 << (SH - 1))) >> SH;
+                        s8[e] = __fsub_rn(__int_as_float(0x4B400000 + sum), 12582912.0f + 128.0f);
+                    }
+                }
+                jb_fdct8(s8, d8); // pass 1: along row r
+#pragma unroll
+                for (int k = 0; k < 8; k++) p1[r * 8 + k] = d8[k];
+            }
+            float F[64];
+            jb_k3w_col<0>(p1, F); jb_k3w_col<1>(p1, F); jb_k3w_col<2>(p1, F); jb_k3w_col<3>(p1, F);
+            jb_k3w_col<4>(p1, F); jb_k3w_col<5>(p1, F); jb_k3w_col<6>(p1, F); jb_k3w_col<7>(p1, F);
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) pk[i] = 0;
+#pragma unroll
+            for (int n = 0; n < 64; n++) {
+                // MultiplyInplace(0.125), coefficient / element, MathF.Round -> (short)  (JpegEncoder.cs:812-826)
+                const float v = (float)((double)F[n] * rq[n]);
+                // MathF.Round (half to even) through the fp32 magic number: exact for |v| < 2^22
+                const uint32_t q16 = (uint32_t)(__float_as_int(__fadd_rn(v, 12582912.0f)) - 0x4B400000) & 0xFFFFu;
+                const int z = jb_nat2zz_c(n);
+                pk[z >> 1] |= q16 << (16 * (z & 1));
+            }
+            const uint64_t blk = s_im.coef_off + ((uint64_t)mcu_row * mpl + mcu_col0) * BPM + j;
+            uint4 *dst = reinterpret_cast<uint4 *>(coef + blk * 64);
+#pragma unroll
+            for (int i = 0; i < 8; i++) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
         }
-    }
-    __syncwarp();
-    if (valid) {
-        const uint64_t blk = s_im.coef_off + ((uint64_t)mcu_row * s_im.mcus_per_line + mcu_col0) * BPM + j;
-        reinterpret_cast<uint4 *>(coef + blk * 64)[r] = *reinterpret_cast<const uint4 *>(s_out + j * 64 + r * 8);
     }
 }
 
