@@ -161,17 +161,31 @@ jb_k3_fdct_quant_warp(const JbEncImage *__restrict__ images, const uint32_t *__r
         const int x0 = mcu_col0 * 8 * HS, y0 = mcu_row * TH;
         const int wlim = min(W - x0, nmcu * 8 * HS); // pixels of this unit's rows that exist
 
-        // ---- E1 + E2: pixels -> component planes (JpegBufferInputReader zero-fills outside the image)
+        // ---- E1 + E2: pixels -> component planes (JpegBufferInputReader zero-fills outside the image).
+        // All loads of the unit are issued before the first conversion so that their latencies overlap.
         __syncwarp();
-        for (int g = lane; g < TW * TH / 4; g += 32) {
+        constexpr int NG = (TW * TH / 4 + 31) / 32; // 4-pixel groups per lane
+        uint32_t lw[NG][3];
+#pragma unroll
+        for (int t = 0; t < NG; t++) {
+            const int g = lane + 32 * t;
+            const int py = g / (TW / 4), px = (g - py * (TW / 4)) * 4;
+            lw[t][0] = lw[t][1] = lw[t][2] = 0;
+            if (g < TW * TH / 4 && y0 + py < H && vec_ok && px + 4 <= wlim) {
+                const uint32_t *p = reinterpret_cast<const uint32_t *>(pix + (uint64_t)(y0 + py) * pitch + (uint64_t)(x0 + px) * 3);
+                lw[t][0] = __ldg(p); lw[t][1] = __ldg(p + 1); lw[t][2] = __ldg(p + 2);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NG; t++) {
+            const int g = lane + 32 * t;
+            if (g >= TW * TH / 4) break;
             const int py = g / (TW / 4), px = (g - py * (TW / 4)) * 4;
             const int y = y0 + py;
             uint32_t o0 = 0, o1 = 0, o2 = 0; // four samples of each component
             if (y < H && px < wlim) {
-                const uint8_t *p = pix + (uint64_t)y * pitch + (uint64_t)(x0 + px) * (fmt == 2 ? 1 : 3);
                 if (vec_ok && px + 4 <= wlim) {
-                    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(p)), w1 = __ldg(reinterpret_cast<const uint32_t *>(p) + 1),
-                                   w2 = __ldg(reinterpret_cast<const uint32_t *>(p) + 2);
+                    const uint32_t w0 = lw[t][0], w1 = lw[t][1], w2 = lw[t][2];
                     // bytes: a0 b0 c0 a1 | b1 c1 a2 b2 | c2 a3 b3 c3
                     const uint32_t a4 = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // a0 a1 a2 a3
                     const uint32_t b4 = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // b0 b1 b2 b3
@@ -186,6 +200,7 @@ jb_k3_fdct_quant_warp(const JbEncImage *__restrict__ images, const uint32_t *__r
                         }
                     }
                 } else {
+                    const uint8_t *p = pix + (uint64_t)y * pitch + (uint64_t)(x0 + px) * (fmt == 2 ? 1 : 3);
 #pragma unroll 1
                     for (int i = 0; i < 4; i++) {
                         if (px + i >= wlim) break;
