@@ -58,27 +58,51 @@ struct __align__(16) JbSubCheck {
 // counts the kept bytes of every 64 KB chunk, pass 2 compacts each chunk to the sum of the counts in
 // front of it.  The clean stream is padded with 0xFF bytes (PeekBits pads with 1-bits, :166).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t jb_k1b_keep16(const uint8_t *data, uint32_t pos0, uint32_t end, uint32_t (&w)[4])
-{ // keep mask of the 16 bytes at pos0 (pos0 is 16-byte aligned); bytes at or behind `end` are not kept
-    w[0] = w[1] = w[2] = w[3] = 0;
-    if (pos0 >= end) return 0;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos0));
-    w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-    const uint32_t nb = __ldg(data + pos0 + 16); // the arena is padded: safe
-    const uint32_t pb = pos0 ? __ldg(data + pos0 - 1) : 0u;
-    uint32_t keep = 0;
+// byte-permute selectors that pack the kept bytes of a little-endian word at its low end, in memory order:
+// index = 4-bit mask of kept bytes (bit i = memory byte i), unused result bytes select the zero operand
+__constant__ uint16_t jb_c_keepsel_le[16] = {0x4444, 0x4440, 0x4441, 0x4410, 0x4442, 0x4420, 0x4421, 0x4210,
+                                             0x4443, 0x4430, 0x4431, 0x4310, 0x4432, 0x4320, 0x4321, 0x3210};
+
+// One lane's 64 bytes of the stuffed stream (pos0 is 64-byte aligned): loads them and returns, per 32-bit word,
+// the 4-bit mask of bytes that stay (nib[i] in bits 4i..4i+3 of the two result words).  Bytes at or behind `end`
+// do not stay.  All four bytes of a word are classified at once with SWAR flags.
+__device__ __forceinline__ void jb_k1b_keep64(const uint8_t *data, uint32_t pos0, uint32_t end, uint32_t (&w)[16], uint64_t &nibs)
+{
+    nibs = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = 0;
+    if (pos0 >= end) return;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos0) + j); // the arena is padded: safe
+        w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+    const uint32_t nextb = __ldg(data + pos0 + 64);
+    const uint32_t prevb = pos0 ? __ldg(data + pos0 - 1) : 0u;
+    uint32_t F[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-        const uint32_t b = (w[i >> 2] >> ((i & 3) * 8)) & 0xFF;
-        const uint32_t bn = i < 15 ? (w[(i + 1) >> 2] >> (((i + 1) & 3) * 8)) & 0xFF : nb;
-        const uint32_t bp = i > 0 ? (w[(i - 1) >> 2] >> (((i - 1) & 3) * 8)) & 0xFF : pb;
-        const bool drop = (b == 0xFF && bn == 0xFF) || (b == 0 && bp == 0xFF);
-        if (pos0 + i < end && !drop) keep |= 1u << i;
+        const uint32_t inv = ~w[i];
+        F[i] = ~(((inv & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | inv) & 0x80808080u; // bytes that are 0xFF
     }
-    return keep;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t Z = ~(((w[i] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w[i]) & 0x80808080u; // bytes that are 0x00
+        const uint32_t nf = i < 15 ? (F[i + 1] << 24) & 0x80000000u : (nextb == 0xFFu ? 0x80000000u : 0u);
+        const uint32_t pf = i > 0 ? (F[i - 1] >> 24) & 0x80u : (prevb == 0xFFu ? 0x80u : 0u);
+        const uint32_t NF = (F[i] >> 8) | nf, PF = (F[i] << 8) | pf;
+        // FF FF: the first FF is a fill byte; FF 00: the zero is stuffing
+        uint32_t K = ~((F[i] & NF) | (Z & PF)) & 0x80808080u;
+        const uint32_t p = pos0 + 4 * i;
+        if (p + 4 > end) K &= p >= end ? 0u : (0xFFFFFFFFu >> (8 * (p + 4 - end)));
+        nibs |= (uint64_t)(((K >> 7) * 0x01020408u) >> 24) << (4 * i);
+    }
 }
 
-__global__ void __launch_bounds__(256)
+#define JB_K1B_UTHREADS 256
+#define JB_K1B_UTILE (JB_K1B_UTHREADS * 64) // bytes of stuffed stream per CTA iteration
+
+__global__ void __launch_bounds__(JB_K1B_UTHREADS)
 jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
              const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres, uint32_t *__restrict__ chunk_kept)
 {
@@ -88,9 +112,12 @@ jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     const uint32_t c0 = blockIdx.x * JB_K1B_CHUNK;
     if (c0 >= end && blockIdx.x > 0) return;
     const uint8_t *data = arena + im.data_off;
-    uint32_t cnt = 0, w[4];
-    for (uint32_t pos0 = c0 + threadIdx.x * 16; pos0 < c0 + JB_K1B_CHUNK; pos0 += 256 * 16)
-        cnt += __popc(jb_k1b_keep16(data, pos0, end, w));
+    uint32_t cnt = 0, w[16];
+    uint64_t nibs;
+    for (uint32_t pos0 = c0 + threadIdx.x * 64; pos0 < c0 + JB_K1B_CHUNK; pos0 += JB_K1B_UTILE) {
+        jb_k1b_keep64(data, pos0, end, w, nibs);
+        cnt += __popcll(nibs);
+    }
     __shared__ uint32_t s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -101,7 +128,9 @@ jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     if (threadIdx.x == 0) chunk_kept[im.chunk_base + blockIdx.x] = s_cnt;
 }
 
-__global__ void __launch_bounds__(256)
+// Pass 2: every lane compacts its 64 bytes through a 64-bit byte accumulator that emits aligned 32-bit words; only
+// the (at most three) bytes in front of the lane's first aligned word and behind its last one are byte stores.
+__global__ void __launch_bounds__(JB_K1B_UTHREADS)
 jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
             const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres,
             const uint32_t *__restrict__ chunk_kept, uint8_t *__restrict__ clean, uint32_t *__restrict__ clean_len)
@@ -113,7 +142,7 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     if (c0 >= end && blockIdx.x > 0) return;
     const uint8_t *data = arena + im.data_off;
     uint8_t *out = clean + im.data_off;
-    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_warp[JB_K1B_UTHREADS / 32];
     __shared__ uint32_t s_base;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -122,10 +151,11 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
         s_base = base;
     }
     __syncthreads();
-    for (uint32_t tile = c0; tile < c0 + JB_K1B_CHUNK && tile < end; tile += 256 * 16) {
-        uint32_t w[4];
-        const uint32_t keep = jb_k1b_keep16(data, tile + tid * 16, end, w);
-        const uint32_t cnt = __popc(keep);
+    for (uint32_t tile = c0; tile < c0 + JB_K1B_CHUNK && tile < end; tile += JB_K1B_UTILE) {
+        uint32_t w[16];
+        uint64_t nibs;
+        jb_k1b_keep64(data, tile + tid * 64, end, w, nibs);
+        const uint32_t cnt = __popcll(nibs);
         uint32_t incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -136,14 +166,39 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
         __syncthreads();
         uint32_t off = s_base + incl - cnt, total = 0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < JB_K1B_UTHREADS / 32; i++) {
             const uint32_t t = s_warp[i];
             if (i < wid) off += t;
             total += t;
         }
+        // bytes [off, off + cnt) of the clean stream are this lane's
+        uint64_t acc = 0;  // pending output bytes, memory order from bit 0
+        uint32_t na = 0;   // how many
+        uint32_t o = off;  // where the next pending byte goes
+        const uint32_t stop = off + cnt;
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-            if (keep & (1u << i)) out[off++] = (uint8_t)(w[i >> 2] >> ((i & 3) * 8));
+        for (int i = 0; i < 16; i++) {
+            const uint32_t nib = (uint32_t)(nibs >> (4 * i)) & 0xFu;
+            const uint32_t piece = __byte_perm(w[i], 0, jb_c_keepsel_le[nib]);
+            acc |= (uint64_t)piece << (8 * na);
+            na += __popc(nib);
+            // bytes in front of the first aligned word leave one by one (at most three per lane)
+            while (na != 0 && (o & 3u) != 0) {
+                out[o++] = (uint8_t)acc;
+                acc >>= 8;
+                na--;
+            }
+            if (na >= 4) {
+                *reinterpret_cast<uint32_t *>(out + o) = (uint32_t)acc;
+                acc >>= 32;
+                na -= 4;
+                o += 4;
+            }
+        }
+        while (o < stop) { // at most three bytes are left
+            out[o++] = (uint8_t)acc;
+            acc >>= 8;
+        }
         __syncthreads();
         if (tid == 0) s_base += total;
         __syncthreads();

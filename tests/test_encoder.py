@@ -183,3 +183,20 @@ def test_gpu_encoder_compatibility_reader_and_quirk_q4():
     # stale dummy block (quirk Q4); the GPU path refuses instead of inventing data
     with pytest.raises(J.NotSupportedException):
         J.encode_rgb(synth.synth_rgb(1, 24, 16), quality=75)
+
+
+def test_fp64_reciprocal_quantisation_equals_ieee_fp32_division():
+    """K3 quantises with RN32((double)F * RN64(1 / (8q))) instead of fp32 division (k_encode.cuh).  The identity
+    RN32(F * 0.125 / q) == that expression is argued in the kernel's comment; this checks it numerically (numpy's
+    float32 division is IEEE) on random, exactly divisible and near-half-integer dividends for every 8-bit
+    quantiser and a few 16-bit ones."""
+    rng = np.random.default_rng(7)
+    for q in list(range(1, 256)) + [256, 257, 1000, 4095, 32769, 65535]:
+        r8 = np.float64(0.125) / np.float64(q)
+        x = (rng.standard_normal(40000) * rng.choice([1, 10, 100, 1000, 8000], 40000)).astype(np.float32)
+        k = rng.integers(-40000, 40000, 10000)
+        xs = np.concatenate([x, (k * q * 8).astype(np.float32), ((k + 0.5) * q * 8).astype(np.float32),
+                             (k * q * 8).astype(np.float32) + np.float32(0.5)])
+        ref = (xs * np.float32(0.125)) / np.float32(q)
+        got = (xs.astype(np.float64) * r8).astype(np.float32)
+        assert np.array_equal(ref, got), q
