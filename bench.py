@@ -384,6 +384,9 @@ def main():
 
     # ---------------------------------------------------------------- e2e leg (host buffers, public API)
     eb = min(args.e2e_batch, args.batch)
+    if args.progressive:  # the progressive entropy kernels are serial-latency bound: only large chunks amortise them
+        eb = min(max(eb, 512), args.batch)
+        args.e2e_chunk = max(args.e2e_chunk, (eb + 1) // 2)
     e2e_blobs = batch_blobs[:eb]
     host_out = ctx.pinned_array(eb * ((WIDTH * HEIGHT * 3 + 255) // 256 * 256))
 
