@@ -375,3 +375,51 @@ def test_batch_with_more_huffman_tables_than_the_shared_memory_cache(restart):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
     for blob in blobs[:2]:
         check_coefficients(blob)
+
+
+def _with_fill_bytes(blob, every=1):
+    """Insert 0xFF fill bytes in front of RSTn / EOI markers (legal: B.1.1.2; FillBuffer skips them,
+    JpegBitReader.cs:108-128)."""
+    out = bytearray()
+    i, n, seen = 0, len(blob), 0
+    sos = blob.find(b"\xff\xda")
+    while i < n:
+        if i > sos and blob[i] == 0xFF and i + 1 < n and (0xD0 <= blob[i + 1] <= 0xD7 or blob[i + 1] == 0xD9):
+            seen += 1
+            if seen % every == 0:
+                out += b"\xff" * (1 + seen % 3)
+        out.append(blob[i])
+        i += 1
+    return bytes(out)
+
+
+@pytest.mark.parametrize("kw", [dict(restart_rows=1), dict(restart_blocks=5), dict()], ids=["rows", "blocks5", "norestart"])
+def test_fill_bytes_before_markers(kw):
+    rgb = synth.synth_rgb(41, 208, 144)
+    plain = synth.encode_jpeg(rgb, subsampling="4:2:0", **kw)
+    filled = _with_fill_bytes(plain, every=2 if kw else 1)
+    assert len(filled) > len(plain)
+    a = O.decode(plain)
+    b = O.decode(filled)
+    assert np.array_equal(a.planes, b.planes)
+    _, c0 = J.decode_coefficients(plain)
+    _, c1 = J.decode_coefficients(filled)
+    assert np.array_equal(c0, c1)
+    assert np.array_equal(gpu_pixels(filled), a.rgb)
+
+
+@pytest.mark.parametrize("kw", [dict(restart_rows=1), dict()], ids=["restart", "norestart"])
+def test_truncated_entropy_data_is_an_error(kw):
+    """A scan that ends early must not decode silently: ReceiveAndExtend / DecodeHuffmanCode throw
+    InvalidDataException, a missing RSTn gives InvalidOperationException (JpegHuffmanScanDecoder.cs:81-115,
+    JpegHuffmanBaselineScanDecoder.cs:139-154)."""
+    blob = synth.synth_jpeg(43, 320, 240, **kw)
+    assert blob.endswith(b"\xff\xd9")
+    cut = blob[:len(blob) - 2 - 600] + b"\xff\xd9"
+    with pytest.raises(O.OracleError):
+        O.decode(cut)
+    dec = J.JpegDecoder()
+    dec.SetInput(cut)
+    dec.SetOutputWriter(J.CudaOutputWriter(np.zeros((240, 320, 3), np.uint8)))
+    with pytest.raises((J.InvalidDataException, J.InvalidOperationException)):
+        dec.Decode()
