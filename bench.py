@@ -139,7 +139,7 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     blobs = make_blobs(min(args.distinct, 8), WIDTH, HEIGHT, quality=85, subsampling="4:2:0", restart_rows=1)
-    images = max(threads, min(2 * threads, 256))
+    images = max(threads, min(16 * threads, 512))  # a few seconds of work per step on all host threads
     for _ in range(args.warmup):
         cpu_reference(blobs, threads, max(2, images // 4))
     t0 = time.perf_counter()
