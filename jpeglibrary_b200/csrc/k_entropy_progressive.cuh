@@ -144,10 +144,18 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
     };
 
     if (coop) {
-        // ---- AC refinement, one stream per warp: lane 0 decodes, the warp moves the blocks
+        // ---- AC refinement, one stream per warp, decoded by the WHOLE warp.  Every lane runs the same bit reader and
+        // Huffman decode (identical state, broadcast loads), lane l owns coefficients l and l + 32 of the block.
+        // ReadBlockProgressiveACRefined (:313-419) walks the band position by position: a nonzero coefficient costs one
+        // correction bit, a zero one counts down the symbol's run.  Here the nonzero history of the block is a 64-bit
+        // ballot, so "the (r+1)-th zero from k on" is a prefix-popcount + ballot, the correction bits in front of it
+        // are read in one go and applied by all lanes at once.
         const int c = sc.comp[0];
         const uint32_t *plane = reinterpret_cast<const uint32_t *>(store + (size_t)im.comp_plane_off[c] * 64);
         const uint32_t pw = im.comp_plane_w[c];
+        const int ss = sc.ss, se = sc.se;
+        const uint64_t band = (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
+        const uint64_t below_lo = (1ull << lane) - 1ull, below_hi = (1ull << (lane + 32)) - 1ull; // positions in front of mine
         uint32_t by = first / sc.wb, bx = first - by * sc.wb;
         uint32_t nxt = count ? __ldg(plane + ((size_t)by * pw + bx) * 32 + lane) : 0u;
         for (uint32_t u = first; u < first + count; u++) {
@@ -156,15 +164,66 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
             if (++bx == sc.wb) { bx = 0; by++; }
             if (u + 1 < first + count) nxt = __ldg(plane + ((size_t)by * pw + bx) * 32 + lane); // prefetch
             __syncwarp();
-            if (lane == 0 && !err) refine_block(reinterpret_cast<int16_t *>(s_blk), sc.ss, sc.se);
+            int16_t *b16 = reinterpret_cast<int16_t *>(s_blk);
+            int c_lo = b16[lane], c_hi = b16[lane + 32];
+            bool beyond = false; // a coefficient was placed just behind the band (see below)
             __syncwarp();
-            // write back the scan's band only: scans of the same level refine other bands of the same block concurrently
-            {
-                const uint32_t v = s_blk[lane];
-                int16_t *g16 = reinterpret_cast<int16_t *>(gblk);
-                if (2 * lane >= sc.ss && 2 * lane <= sc.se) g16[2 * lane] = (int16_t)(v & 0xFFFFu);
-                if (2 * lane + 1 >= sc.ss && 2 * lane + 1 <= sc.se) g16[2 * lane + 1] = (int16_t)(v >> 16);
+            if (!err) {
+                const uint64_t Z = (((uint64_t)__ballot_sync(0xFFFFFFFFu, c_hi != 0) << 32) | __ballot_sync(0xFFFFFFFFu, c_lo != 0)) & band;
+                // correction bits for the nonzero-history positions in `nz` (ascending), read 16 at a time
+                auto correct = [&](uint64_t nz) {
+                    const int n = __popcll(nz);
+                    const int my_lo = (nz >> lane) & 1ull ? __popcll(nz & below_lo) : -1;
+                    const int my_hi = (nz >> (lane + 32)) & 1ull ? __popcll(nz & below_hi) : -1;
+                    for (int done = 0; done < n; done += 16) {
+                        const int cnt = min(16, n - done);
+                        const uint32_t v = jb_prog_bits(br, cnt); // first bit = lowest position
+                        if (my_lo >= done && my_lo < done + cnt && ((v >> (cnt - 1 - (my_lo - done))) & 1u) && (c_lo & p1) == 0)
+                            c_lo += c_lo >= 0 ? p1 : m1;
+                        if (my_hi >= done && my_hi < done + cnt && ((v >> (cnt - 1 - (my_hi - done))) & 1u) && (c_hi & p1) == 0)
+                            c_hi += c_hi >= 0 ? p1 : m1;
+                    }
+                };
+                int k = ss;
+                if (eobrun == 0) {
+                    while (k <= se) {
+                        const int sym = huff(sc.ac_tab[0]);
+                        int r = sym >> 4, s = sym & 15;
+                        if (s != 0) {
+                            s = jb_prog_bits(br, 1) != 0 ? p1 : m1;
+                        } else if (r != 15) {
+                            eobrun = 1 << r;
+                            if (r != 0) eobrun += (int)jb_prog_bits(br, r);
+                            break;
+                        }
+                        // the (r+1)-th zero-history position at or behind k; the band end if there are fewer
+                        const uint64_t from_k = ~((1ull << k) - 1ull);
+                        const uint64_t zeros = ~Z & band & from_k;
+                        const bool z_lo = (zeros >> lane) & 1ull, z_hi = (zeros >> (lane + 32)) & 1ull;
+                        const uint32_t hit_lo = __ballot_sync(0xFFFFFFFFu, z_lo && __popcll(zeros & below_lo) == r);
+                        const uint32_t hit_hi = __ballot_sync(0xFFFFFFFFu, z_hi && __popcll(zeros & below_hi) == r);
+                        const int k_end = hit_lo ? __ffs(hit_lo) - 1 : hit_hi ? 32 + __ffs(hit_hi) - 1 : se + 1;
+                        const uint64_t upto = k_end >= 64 ? ~0ull : ((1ull << k_end) - 1ull);
+                        correct(Z & from_k & upto);
+                        if (s != 0 && k_end < 64) { // (the reference writes at se + 1 when the run overshoots the band)
+                            if (k_end < 32) { if (lane == k_end) c_lo = s; }
+                            else if (lane == k_end - 32) c_hi = s;
+                            beyond |= k_end > se;
+                        }
+                        k = k_end + 1;
+                    }
+                }
+                if (eobrun > 0) {
+                    if (k <= se) correct(Z & ~((1ull << k) - 1ull));
+                    --eobrun;
+                }
             }
+            // write back the scan's band only: scans of the same level refine other bands of the same block concurrently
+            int16_t *g16 = reinterpret_cast<int16_t *>(gblk);
+            if (lane >= ss && lane <= se) g16[lane] = (int16_t)c_lo;
+            if (lane + 32 >= ss && lane + 32 <= se) g16[lane + 32] = (int16_t)c_hi;
+            if (beyond && lane == ((se + 1) & 31)) // the reference's write just behind the band (corrupt streams only)
+                g16[se + 1] = (int16_t)(se + 1 < 32 ? c_lo : c_hi);
         }
         if (lane != 0) return;
     } else if (sc.ncomp > 1) {
