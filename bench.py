@@ -282,7 +282,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic images (replicated to --batch)")
-    ap.add_argument("--e2e-batch", type=int, default=128, help="images per step of the host-buffer (e2e) leg")
+    ap.add_argument("--e2e-batch", type=int, default=256, help="images per step of the host-buffer (e2e) leg")
     ap.add_argument("--e2e-chunk", type=int, default=32, help="images per pipelined chunk of the e2e leg")
     ap.add_argument("--cpu-images", type=int, default=0, help="images of the cpu_baseline sample (0: auto)")
     ap.add_argument("--no-restart", action="store_true", help="configs[2]: same batch without restart markers")
