@@ -69,6 +69,25 @@ __device__ __forceinline__ void jb_idct8(const float y[8], float d[8])
 
 __device__ __forceinline__ int jb_clamp255(int v) { return min(max(v, 0), 255); }
 
+// One sample of a P-bit frame as the 8-bit value the reference's application writers store:
+//   P == 8: clamp                                   (apps/JpegDecode/JpegBufferOutputWriter8Bit.cs:28-60)
+//   P  > 8: clamp(sample >> (P - 8))                (JpegBufferOutputWriterGreaterThan8Bit.cs:34-68)
+//   P  < 8: clamp to [0, 2^P - 1], then repeat the P-bit pattern up to 8 bits; when P does not divide 8 the
+//           last partial copy takes the pattern's LOW bits (JpegBufferOutputWriterLessThan8Bit.cs:35-92)
+__device__ __forceinline__ int jb_sample_to_u8(int v, int precision)
+{
+    if (precision >= 8) return jb_clamp255(v >> (precision - 8));
+    uint32_t bits = (uint32_t)min(max(v, 0), (1 << precision) - 1);
+    int have = precision;
+    while (have < 8) { bits |= bits << precision; have += precision; }
+    if (have > 8) {
+        bits >>= precision; have -= precision;
+        const int rem = 8 - have;
+        bits = (bits << rem) | (bits & ((1u << rem) - 1u));
+    }
+    return (int)(bits & 255u);
+}
+
 // apps/JpegDecode/JpegYCbCrToRgbConverter.cs:93-121 evaluated in fp32 as the C# does:
 // d1 = Fix(2-2*0.299) = 91881, d2 = -Fix(0.299*f1/0.587) = -46802, d3 = Fix(2-2*0.114) = 116130,
 // d4 = -Fix(0.114*f3/0.587) = -22553; Code2V is the identity for the default reference black/white.
@@ -238,10 +257,9 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
         const int bpp = fmt == 1 ? 4 : 3;
 #pragma unroll
         for (int p = 0; p < 4; p++) {
-            // JpegBufferOutputWriter8Bit.ClampTo8Bit / GreaterThan8Bit: (sample >> (P-8)) clamped
-            const int yv = jb_clamp255(s[0][p] >> pshift);
-            const int cb = jb_clamp255(s[1][p] >> pshift);
-            const int cr = jb_clamp255(s[2][p] >> pshift);
+            const int yv = jb_sample_to_u8(s[0][p], s_im.precision);
+            const int cb = ncomp > 1 ? jb_sample_to_u8(s[1][p], s_im.precision) : 128;
+            const int cr = ncomp > 2 ? jb_sample_to_u8(s[2][p], s_im.precision) : 128;
             if (fmt == 2 /* JB_OUT_YCBCR888 */) {
                 px[p * 3] = (uint8_t)yv; px[p * 3 + 1] = (uint8_t)cb; px[p * 3 + 2] = (uint8_t)cr;
             } else {

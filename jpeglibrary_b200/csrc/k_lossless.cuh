@@ -162,10 +162,9 @@ jb_k5_lossless_output(const JbDevImage *__restrict__ images, const uint32_t *__r
         for (int c = 0; c < im.ncomp; c++) reinterpret_cast<int16_t *>(out + ((uint64_t)c * H + yy) * pitch)[x] = (int16_t)s[c];
         return;
     }
-    const int pshift = im.precision > 8 ? im.precision - 8 : 0;
-    const int yv = jb_clamp255(s[0] >> pshift);
-    const int cb = im.ncomp == 3 ? jb_clamp255(s[1] >> pshift) : 128;
-    const int cr = im.ncomp == 3 ? jb_clamp255(s[2] >> pshift) : 128;
+    const int yv = jb_sample_to_u8(s[0], im.precision);
+    const int cb = im.ncomp == 3 ? jb_sample_to_u8(s[1], im.precision) : 128;
+    const int cr = im.ncomp == 3 ? jb_sample_to_u8(s[2], im.precision) : 128;
     const int bpp = fmt == 1 ? 4 : 3;
     uint8_t *dst = out + (uint64_t)yy * pitch + (uint64_t)x * bpp;
     if (fmt == 2) { dst[0] = (uint8_t)yv; dst[1] = (uint8_t)cb; dst[2] = (uint8_t)cr; return; }

@@ -839,21 +839,45 @@ static void render_planes(dec_ctx *c)
     }
 }
 
+/* JpegBufferOutputWriterLessThan8Bit.cs:66-92: widen a P-bit value (P < 8) to 8 bits by repeating
+   its bit pattern; a trailing partial copy is made of the pattern's low bits (FastExpandBits).  */
+static int expand_bits_to_8(unsigned v, int p)
+{
+    unsigned bits = v;
+    int have = p;
+    while (have < 8) {
+        bits = (bits << p) | bits;
+        have += p;
+    }
+    if (have > 8) {
+        bits >>= p;
+        have -= p;
+        int rem = 8 - have;
+        bits = (bits << rem) | (bits & ((1u << rem) - 1u));
+    }
+    return (int)(bits & 0xFF);
+}
+
 /* apps/JpegDecode/DecodeAction.cs:38-74 with JpegBufferOutputWriter8Bit.cs:28-60 /
-   JpegBufferOutputWriterGreaterThan8Bit.cs:34-68 */
+   JpegBufferOutputWriterGreaterThan8Bit.cs:34-68 / JpegBufferOutputWriterLessThan8Bit.cs:35-64 */
 static void render_rgb(dec_ctx *c)
 {
     jo_image *im = c->img;
     size_t n = (size_t)im->width * im->height;
     int shift = im->precision > 8 ? im->precision - 8 : 0;
+    int max = (1 << im->precision) - 1;
     for (size_t i = 0; i < n; i++) {
         for (int ci = 0; ci < 3; ci++) {
             int v;
-            if (ci < im->ncomp) {
+            if (ci >= im->ncomp)
+                v = 128;
+            else if (im->precision < 8) {
+                v = im->planes[(size_t)ci * n + i];
+                v = expand_bits_to_8((unsigned)(v < 0 ? 0 : (v > max ? max : v)), im->precision);
+            } else {
                 v = im->planes[(size_t)ci * n + i] >> shift;
                 v = v < 0 ? 0 : (v > 255 ? 255 : v);
-            } else
-                v = 128;
+            }
             im->ycbcr[3 * i + ci] = (uint8_t)v;
         }
     }

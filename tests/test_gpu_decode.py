@@ -113,6 +113,35 @@ def test_synthetic_streams(kw):
     assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
 
 
+@pytest.mark.parametrize("shape", [(96, 112), (104, 80), (1024, 64)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_vertically_subsampled_440_streams(shape):
+    """Luma 1x2 (4:4:0): Pillow cannot write it, so the stream comes from the oracle's encoder.  Exercises the
+    renderer's <HS=1, VS=2> instantiation, with (96, 1024 px) and without (104 px) the TMA tensor store."""
+    w, h = shape
+    blob = O.encode_ycbcr(O.rgb_to_ycbcr(synth.synth_rgb(11, w, h)), quality=88, subsampling=(1, 2)).bytes
+    check_coefficients(blob)
+    o = O.decode(blob)
+    assert np.array_equal(gpu_planes(blob), o.planes)
+    rgb = gpu_pixels(blob)
+    assert np.abs(rgb.astype(int) - o.rgb.astype(int)).max() <= 1
+    rgba = gpu_pixels(blob, J.JB_OUT_RGBA32, 4)
+    assert np.array_equal(rgba[..., :3], rgb) and (rgba[..., 3] == 255).all()
+    assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
+
+
+@pytest.mark.parametrize("ss,shape", [((4, 1), (128, 40)), ((4, 2), (128, 48)), ((1, 4), (40, 64))],
+                         ids=lambda v: "x".join(map(str, v)))
+def test_sampling_factor_four_goes_through_the_generic_renderer(ss, shape):
+    """Factors of 4 (JpegEncoder.AddComponent accepts 1, 2 or 4) have no specialised renderer instance."""
+    w, h = shape
+    blob = O.encode_ycbcr(O.rgb_to_ycbcr(synth.synth_rgb(12, w, h)), quality=88, subsampling=ss).bytes
+    check_coefficients(blob)
+    o = O.decode(blob)
+    assert np.array_equal(gpu_planes(blob), o.planes)
+    assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
+    assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
+
+
 NO_RESTART_SHAPES = [
     dict(width=1920, height=1080, subsampling="4:2:0", quality=85),   # ~800 sub-sequences, several CTAs
     dict(width=1280, height=720, subsampling="4:4:4", quality=92),
@@ -328,6 +357,20 @@ def test_lossless_synthetic(kw):
     planes = gpu_planes(blob)
     assert np.array_equal(planes, coded)                      # round trip: what was coded comes back
     assert np.array_equal(planes, O.decode(blob, want_rgb=False).planes)
+
+
+@pytest.mark.parametrize("precision", [2, 3, 5, 7, 12, 16])
+def test_lossless_pixel_writers_of_other_precisions(precision):
+    """8-bit pixel output of P-bit frames follows the reference application's writers: P > 8 shifts down
+    (JpegBufferOutputWriterGreaterThan8Bit.cs:34-68), P < 8 repeats the bit pattern
+    (JpegBufferOutputWriterLessThan8Bit.cs:35-92)."""
+    blob, coded = synth.synth_lossless(9, 64, 40, precision=precision, predictor=4)
+    o = O.decode(blob)
+    assert np.array_equal(gpu_planes(blob), coded)
+    assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
+    assert np.array_equal(gpu_pixels(blob), o.rgb)
+    rgba = gpu_pixels(blob, J.JB_OUT_RGBA32, 4)
+    assert np.array_equal(rgba[..., :3], o.rgb) and (rgba[..., 3] == 255).all()
 
 
 def test_lossless_missing_restart_marker():

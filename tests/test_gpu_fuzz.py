@@ -1,0 +1,121 @@
+"""Corrupted entropy data: the CUDA path must do what the reference does with the same bytes.
+
+A damaged scan is still a decodable bit stream most of the time: the reference (restated by the oracle) walks on
+with wrong symbols and produces deterministic garbage, or it throws (bad code, bits running out, a restart
+marker that is not where it should be).  For every mutated stream the GPU result has to be that same garbage,
+bit for bit, or an error where the oracle reports one -- and never a hang or an out-of-bounds access
+(profiles/*sanitizer* records compute-sanitizer over these tests).
+"""
+import numpy as np
+import pytest
+
+import jpeglibrary_b200 as J
+import oracle_ffi as O
+import synth
+
+pytestmark = pytest.mark.gpu
+
+GPU_ERRORS = (J.InvalidDataException, J.InvalidOperationException, J.NotSupportedException)
+
+
+def entropy_ranges(blob):
+    """[(first, last+1)] byte ranges of entropy-coded data (behind every SOS header up to the next non-RST marker)"""
+    out, i, n = [], 2, len(blob)
+    while i + 4 <= n:
+        assert blob[i] == 0xFF
+        m = blob[i + 1]
+        ln = int.from_bytes(blob[i + 2:i + 4], "big")
+        i += 2 + ln
+        if m != 0xDA:
+            continue
+        j = i
+        while j + 1 < n and not (blob[j] == 0xFF and blob[j + 1] not in (0x00, 0xFF) and not 0xD0 <= blob[j + 1] <= 0xD7):
+            j += 1
+        out.append((i, j))
+        i = j
+        if blob[i + 1] == 0xD9:
+            break
+    return out
+
+
+def mutate(blob, rng, kind):
+    b = bytearray(blob)
+    ranges = entropy_ranges(blob)
+    lo, hi = ranges[int(rng.integers(len(ranges)))]
+    if kind == "flip":          # a few bit flips
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(lo, hi))] ^= 1 << int(rng.integers(8))
+    elif kind == "bytes":       # random byte values (may create or destroy stuffing and markers)
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(lo, hi))] = int(rng.integers(256))
+    elif kind == "drop":        # remove a short run
+        p = int(rng.integers(lo, hi))
+        del b[p:p + int(rng.integers(1, 6))]
+    elif kind == "dup":         # repeat a short run
+        p = int(rng.integers(lo, hi))
+        b[p:p] = b[p:p + int(rng.integers(1, 6))]
+    elif kind == "ones":        # a run of 0xFF fill bytes / 1-bits
+        p = int(rng.integers(lo, hi))
+        b[p:p + int(rng.integers(1, 4))] = b"\xff" * 3
+    return bytes(b)
+
+
+def run_oracle(blob):
+    try:
+        return O.decode(blob, want_rgb=False), None
+    except O.OracleError as e:
+        return None, e
+
+
+def run_gpu(blob):
+    try:
+        dec = J.JpegDecoder()
+        dec.SetInput(blob)
+        dec.Identify()
+        planes = np.zeros((dec.NumberOfComponents, dec.Height, dec.Width), dtype=np.int16)
+        dec.SetOutputWriter(J.CudaOutputWriter(planes, J.JB_OUT_PLANAR_I16))
+        dec.Decode()
+        return planes, None
+    except GPU_ERRORS as e:
+        return None, e
+
+
+def base_streams():
+    rgb = synth.synth_rgb(40, 160, 112)
+    return {
+        "restart": synth.encode_jpeg(rgb, quality=85, subsampling="4:2:0", restart_blocks=4),
+        "restart_rows_444": synth.encode_jpeg(rgb, quality=92, subsampling="4:4:4", restart_rows=1, optimize=True),
+        "plain": synth.encode_jpeg(synth.synth_rgb(41, 640, 360), quality=85, subsampling="4:2:0"),
+        "progressive": synth.encode_jpeg(rgb, quality=85, subsampling="4:2:0", progressive=True),
+        "progressive_restart": synth.encode_jpeg(rgb, quality=85, subsampling="4:4:4", progressive=True, restart_blocks=6),
+        "lossless": synth.synth_lossless(42, 96, 64, predictor=4, restart=24)[0],
+        "lossless_plain": synth.synth_lossless(43, 64, 48, predictor=7)[0],
+    }
+
+
+KINDS = ["flip", "bytes", "drop", "dup", "ones"]
+
+
+@pytest.mark.parametrize("name", list(base_streams()))
+def test_corrupted_scans_decode_like_the_reference(name):
+    blob = base_streams()[name]
+    rng = np.random.default_rng(sum(map(ord, name)))
+    problems, agree_ok, agree_err = [], 0, 0
+    for trial in range(40):
+        kind = KINDS[trial % len(KINDS)]
+        bad = mutate(blob, rng, kind)
+        want, werr = run_oracle(bad)
+        got, gerr = run_gpu(bad)
+        if werr is not None and gerr is not None:
+            agree_err += 1
+        elif werr is None and gerr is None:
+            if np.array_equal(got, want.planes):
+                agree_ok += 1
+            else:
+                problems.append(f"trial {trial} ({kind}): planes differ in {int((got != want.planes).sum())} samples")
+        elif werr is not None:
+            problems.append(f"trial {trial} ({kind}): oracle raised [{werr}] but the GPU decoded")
+        else:
+            problems.append(f"trial {trial} ({kind}): GPU raised [{type(gerr).__name__}: {gerr}] but the oracle decoded")
+    print(f"{name}: {agree_ok} identical decodes, {agree_err} errors on both sides, {len(problems)} disagreements")
+    assert not problems, "\n".join(problems)

@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_ffi as O
+import synth
 from conftest import GOLDEN_DIR, REFERENCE_ASSETS, golden_bytes
 
 ASSETS = ["cramps.jpg", "lake.jpg", "testorig12.jpg", "progress.jpg", "yellowcat_progressive_restart.jpg"] + \
@@ -105,3 +106,20 @@ def test_oracle_decodes_synthetic_lossless_streams(kw):
     d = O.decode(blob, want_rgb=False)
     assert (d.sof, d.width, d.height) == (3, w, h)
     assert np.array_equal(d.planes, coded)
+
+
+@pytest.mark.parametrize("precision", [2, 3, 4, 5, 6, 7])
+def test_oracle_less_than_8_bit_writer(precision):
+    """JpegBufferOutputWriterLessThan8Bit.cs:35-92 in closed form: floor(8/P) copies of the P-bit value, then
+    the value's LOW (8 mod P) bits -- e.g. P=3, 0b101 -> 0b10110101."""
+    blob, coded = synth.synth_lossless(4, 48, 32, precision=precision, predictor=1, ncomp=1)
+    o = O.decode(blob)
+    v = coded[0].astype(np.int64)
+    assert v.min() >= 0 and v.max() < (1 << precision)
+    want = np.zeros_like(v)
+    for _ in range(8 // precision):
+        want = (want << precision) | v
+    rem = 8 % precision
+    want = (want << rem) | (v & ((1 << rem) - 1))
+    assert np.array_equal(o.ycbcr[..., 0], want.astype(np.uint8))
+    assert (o.ycbcr[..., 1:] == 128).all()
