@@ -92,6 +92,7 @@ struct JbScanRange {
 };
 
 // one SOS of a progressive frame (JpegHuffmanProgressiveScanDecoder.ProcessScan, :57-90)
+#define JB_PROG_MAX_DEPS 6
 struct JbDevScan {
     uint64_t data_off;   // arena offset of the scan's entropy-coded bytes
     uint32_t data_len;
@@ -103,8 +104,23 @@ struct JbDevScan {
     uint8_t ncomp, ss, se, ah, al;
     uint8_t comp[4];
     uint8_t level;       // dependency level: scans of one level touch disjoint (component, band) sets
-    uint8_t pad[2];
+    uint8_t ndep;        // producers: earlier scans of the image that share a component and overlap in band
+    uint8_t dep_all;     // bit i: dep[i] must be COMPLETE before this scan starts (its unit order differs from mine);
+                         // otherwise unit u only needs the producer's units 0..u (same component(s), same order)
+    uint8_t has_consumer; // a later scan reads what this one writes: publish progress
+    uint8_t pad;
+    uint16_t dep[JB_PROG_MAX_DEPS]; // scan indices inside the image; ndep == 0xFF: wait for every earlier scan
     uint16_t dc_tab[4], ac_tab[4]; // device table indices, 0xFFFF = not defined
+};
+
+// One warp of K1c: a restart segment of an AC refinement scan (decoded by the whole warp) or up to 32 consecutive
+// segments of any other scan (one per lane).  Warps take jobs in list order through a ticket counter, and the
+// list holds producers in front of their consumers, so a warp never waits for a job that has not started.
+struct JbProgJob {
+    uint32_t image;  // batch index
+    uint32_t scan;   // scan index inside the image
+    uint32_t seg0;   // first restart segment
+    uint32_t lanes;  // segments of this job (1..32)
 };
 
 // per-range result of K0 (restart scan)
@@ -127,3 +143,4 @@ struct JbTileWork {
 #define JB_ST_BAD_CODE 1u        // invalid Huffman code / magnitude category  -> InvalidDataException
 #define JB_ST_PREMATURE_END 2u   // ran out of bits inside a segment            -> InvalidDataException
 #define JB_ST_EXPECT_RST 4u      // restart marker missing / misplaced          -> InvalidOperationException
+#define JB_ST_STALLED 8u         // K1c gave up waiting for a producer scan (never expected) -> JB_ERR_CUDA

@@ -248,6 +248,7 @@ struct ImagePlan {
     jb_coef_layout layout{};
     std::vector<JbDevScan> scans;          // progressive frames
     std::vector<uint64_t> scan_host_off;   // host offset of every scan's entropy bytes
+    std::vector<std::vector<bool>> scan_follows, scan_after; // transitive producers per scan (see plan_progressive)
 };
 
 } // namespace
@@ -376,6 +377,9 @@ struct jb_batch {
     // progressive frames
     std::vector<uint32_t> prog_images;
     uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1, prog_levels = 0;
+    std::vector<JbProgJob> h_prog_jobs;    // K1c warps in ticket order: producers in front of consumers
+    JbProgJob *d_prog_jobs = nullptr;
+    uint32_t *d_prog_progress = nullptr;   // per scan: units (one segment) or segments finished; last word: ticket counter
     uint64_t prog_coef_first = 0, prog_coef_blocks = 0; // contiguous slice of the store, zeroed per launch
     std::vector<JbDevScan> h_scans;
     std::vector<JbScanRange> h_ranges;
@@ -729,16 +733,41 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
         uint64_t len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
                                          : im.length - sc.entropy_offset;
         ds.data_len = (uint32_t)len;
-        // dependency level (JPEG scans commute unless they share a component and overlap in band)
+        // Producers: JPEG scans commute unless they share a component and overlap in band.  A consumer follows a
+        // producer block by block when both walk the same units in the same order (same component list, producer in
+        // one segment); otherwise it waits for the whole producer.  follows[s] / after[s]: every scan that has
+        // finished block u when s finishes block u / that is complete when s starts -- producers already implied by
+        // a nearer one are dropped (libjpeg's last luma refinement only watches the one before it).
         int level = 0;
-        for (size_t e = 0; e < pl.scans.size(); e++) {
-            const JbDevScan &pe = pl.scans[e];
+        const size_t me = pl.scans.size();
+        if (me >= 0xFFFF) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "too many scans");
+        std::vector<bool> follows(me, false), after(me, false);
+        for (size_t e = me; e-- > 0;) {
+            JbDevScan &pe = pl.scans[e];
             bool share = false;
             for (int a = 0; a < ds.ncomp; a++)
                 for (int bq = 0; bq < pe.ncomp; bq++) share |= ds.comp[a] == pe.comp[bq];
-            if (share && !(ds.se < pe.ss || pe.se < ds.ss)) level = std::max<int>(level, pe.level + 1);
+            if (!share || ds.se < pe.ss || pe.se < ds.ss) continue;
+            level = std::max<int>(level, pe.level + 1);
+            pe.has_consumer = 1;
+            if (ds.ndep == 0xFF || follows[e] || after[e]) continue;
+            if (ds.ndep == JB_PROG_MAX_DEPS) { ds.ndep = 0xFF; continue; } // too many: wait for every earlier scan
+            const bool blockwise = pe.nseg == 1 && ds.ncomp == pe.ncomp && memcmp(ds.comp, pe.comp, ds.ncomp) == 0;
+            ds.dep[ds.ndep] = (uint16_t)e;
+            if (!blockwise) ds.dep_all |= (uint8_t)(1u << ds.ndep);
+            ds.ndep++;
+            std::vector<bool> &into = blockwise ? follows : after;
+            into[e] = true;
+            for (size_t q = 0; q < e; q++) {
+                if (pl.scan_follows[e][q]) into[q] = true;   // e complete (or past block u) => so is what it followed
+                if (pl.scan_after[e][q]) after[q] = true;    // complete before e even started
+            }
         }
-        ds.level = (uint8_t)level;
+        if (ds.ndep == 0xFF)
+            for (auto &pe : pl.scans) pe.has_consumer = 1;
+        pl.scan_follows.push_back(follows);
+        pl.scan_after.push_back(after);
+        ds.level = (uint8_t)std::min(level, 255);
         pl.scan_host_off.push_back(sc.entropy_offset - lo);
         pl.scans.push_back(ds);
     }
@@ -1102,6 +1131,38 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         }
     }
     b->prog_coef_blocks = blocks - b->prog_coef_first;
+    {
+        // K1c job order.  weight(scan) = its bytes + the heaviest consumer's weight, so a producer always outweighs
+        // its consumers: ranking the scans of an image by falling weight is a topological order that starts the
+        // longest dependency chain first.  The list takes rank 0 of every image, then rank 1, ...
+        std::vector<std::vector<uint32_t>> order(b->prog_images.size());
+        for (size_t n = 0; n < b->prog_images.size(); n++) {
+            const ImagePlan &pl = b->plans[b->prog_images[n]];
+            const size_t ns = pl.scans.size();
+            std::vector<uint64_t> weight(ns, 0);
+            for (size_t k = ns; k-- > 0;) {
+                weight[k] += (uint64_t)pl.scans[k].data_len + 1;
+                const JbDevScan &ds = pl.scans[k];
+                if (ds.ndep == 0xFF) {
+                    for (size_t q = 0; q < k; q++) weight[q] = std::max(weight[q], weight[k]);
+                } else
+                    for (int q = 0; q < ds.ndep; q++) weight[ds.dep[q]] = std::max(weight[ds.dep[q]], weight[k]);
+            }
+            order[n].resize(ns);
+            for (size_t k = 0; k < ns; k++) order[n][k] = (uint32_t)k;
+            std::stable_sort(order[n].begin(), order[n].end(), [&](uint32_t a, uint32_t c) { return weight[a] > weight[c]; });
+        }
+        for (uint32_t rank = 0; rank < b->prog_max_scans; rank++)
+            for (size_t n = 0; n < b->prog_images.size(); n++) {
+                if (rank >= order[n].size()) continue;
+                const uint32_t k = order[n][rank];
+                const JbDevScan &ds = b->plans[b->prog_images[n]].scans[k];
+                const bool coop = ds.ncomp == 1 && ds.ss != 0 && ds.ah != 0; // (k_entropy_progressive.cuh)
+                const uint32_t per_job = coop ? 1u : 32u;
+                for (uint32_t seg = 0; seg < ds.nseg; seg += per_job)
+                    b->h_prog_jobs.push_back(JbProgJob{b->prog_images[n], k, seg, std::min(per_job, ds.nseg - seg)});
+            }
+    }
     b->arena_bytes = arena + 256;
     b->marks_count = marks;
     b->coef_blocks = blocks;
@@ -1150,8 +1211,12 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_ranges, sizeof(JbScanRange) * b->h_ranges.size()));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_scans, sizeof(JbDevScan) * std::max<size_t>(b->h_scans.size(), 1)));
     JB_CUDA_B(cudaMemcpyAsync(b->d_ranges, b->h_ranges.data(), sizeof(JbScanRange) * b->h_ranges.size(), cudaMemcpyHostToDevice, ctx->stream));
-    if (!b->h_scans.empty())
+    if (!b->h_scans.empty()) {
         JB_CUDA_B(cudaMemcpyAsync(b->d_scans, b->h_scans.data(), sizeof(JbDevScan) * b->h_scans.size(), cudaMemcpyHostToDevice, ctx->stream));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_jobs, sizeof(JbProgJob) * b->h_prog_jobs.size()));
+        JB_CUDA_B(cudaMemcpyAsync(b->d_prog_jobs, b->h_prog_jobs.data(), sizeof(JbProgJob) * b->h_prog_jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_progress, sizeof(uint32_t) * (b->h_scans.size() + 1)));
+    }
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
     if (staging) JB_CUDA_B(jb_malloc_async(ctx, &b->d_out_staging, staging));
@@ -1307,14 +1372,12 @@ static int launch_kernels(jb_batch *b)
     if (!b->prog_images.empty()) {
         // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
         JB_CUDA(ctx, jb_fill_async(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
-        const int lanes = b->prog_max_nseg > 1 ? 32 : 1; // serial streams: one lane per warp
-        dim3 grid((b->prog_max_nseg + lanes - 1) / lanes, (unsigned)b->prog_images.size(), b->prog_max_scans);
-        for (uint32_t level = 0; level < b->prog_levels; level++) {
-            jb_k1c_progressive_scan<<<grid, 32, 0, st>>>(b->d_images, b->d_image_list + b->prog_list_off, b->d_scans, (int)level,
-                                                         b->d_tables, b->d_arena, b->d_marks, b->d_scan, b->d_coef,
-                                                         b->d_status, lanes);
-            launches++;
-        }
+        JB_CUDA(ctx, jb_fill_async(b->d_prog_progress, 0, sizeof(uint32_t) * (b->h_scans.size() + 1), st));
+        const uint32_t njobs = (uint32_t)b->h_prog_jobs.size();
+        jb_k1c_progressive_scans<<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, njobs, b->d_tables, b->d_arena,
+                                                       b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
+                                                       b->d_prog_progress + b->h_scans.size());
+        launches += 2;
         mark("jb_k1c_progressive_scans");
     }
     if (!b->ll_images.empty()) {
@@ -1486,13 +1549,15 @@ int jb_decode_batch_finish(jb_batch *b)
     for (int i = 0; i < b->count; i++) {
         uint32_t s = b->h_status[i];
         int code = JB_OK;
-        if (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) code = JB_ERR_INVALID_DATA;
+        if (s & JB_ST_STALLED) code = JB_ERR_CUDA;
+        else if (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) code = JB_ERR_INVALID_DATA;
         else if (s & JB_ST_EXPECT_RST) code = JB_ERR_INVALID_OPERATION;
         if (code && !first) {
             first = code;
             char buf[200];
             snprintf(buf, sizeof buf, "image %d: %s", i,
                      code == JB_ERR_INVALID_DATA ? "Failed to decode JPEG data. Invalid Huffman code or premature end of the bit stream."
+                     : code == JB_ERR_CUDA       ? "progressive scan decoder stalled waiting for a producer scan"
                                                  : "Expect restart marker.");
             ctx->error = buf;
         }
@@ -1514,7 +1579,8 @@ int jb_decode_batch_status(jb_batch *b, int32_t *status, int count)
     if (!b || !status) return JB_ERR_ARGUMENT;
     for (int i = 0; i < count && i < b->count; i++) {
         uint32_t s = b->h_status[i];
-        status[i] = (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) ? JB_ERR_INVALID_DATA
+        status[i] = (s & JB_ST_STALLED)                          ? JB_ERR_CUDA
+                    : (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) ? JB_ERR_INVALID_DATA
                     : (s & JB_ST_EXPECT_RST)                     ? JB_ERR_INVALID_OPERATION
                                                                  : JB_OK;
     }
@@ -1547,6 +1613,8 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
     if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
     if (b->d_scans) cudaFreeAsync(b->d_scans, b->ctx->stream);
+    if (b->d_prog_jobs) cudaFreeAsync(b->d_prog_jobs, b->ctx->stream);
+    if (b->d_prog_progress) cudaFreeAsync(b->d_prog_progress, b->ctx->stream);
     if (b->d_ranges) cudaFreeAsync(b->d_ranges, b->ctx->stream);
     if (b->d_clean) cudaFreeAsync(b->d_clean, b->ctx->stream);
     if (b->d_clean_len) cudaFreeAsync(b->d_clean_len, b->ctx->stream);

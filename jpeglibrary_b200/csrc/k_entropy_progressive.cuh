@@ -1,4 +1,4 @@
-// k_entropy_progressive.cuh -- K1c: one scan of a progressive (SOF2) Huffman frame, for a whole batch.
+// k_entropy_progressive.cuh -- K1c: every scan of the progressive (SOF2) Huffman frames of a batch, ONE launch.
 //
 // Replaces JpegHuffmanProgressiveScanDecoder.ProcessScan and its block readers
 // (ScanDecoder/JpegHuffmanProgressiveScanDecoder.cs:57-419):
@@ -9,13 +9,17 @@
 // grid in HBM, zero-initialised per batch; blocks the reference routes to its shared dummy block
 // (out-of-range MCU padding, :108-111) simply land in the padding here and are never rendered.
 //
-// Parallelism: one thread per (image, scan, restart segment).  A scan only depends on earlier scans
-// that touch the same component with an overlapping spectral band (refinement of what they wrote), so
-// the host sorts scans into dependency levels and launches one kernel per level: libjpeg's 10-scan
-// script needs 4 launches ({DC}, {Y 1-5, Cr, Cb, Y 6-63}, {Y refine, DC refine, Cr refine, Cb refine},
-// {Y refine}).  Refinement scans read coefficient history, so they cannot be decoded speculatively;
-// streams without restart markers expose one thread per image and scan (batch-level parallelism only).
-// One lane per warp is used in that case so that every serial stream gets its own scheduler slot.
+// Parallelism.  A scan is a serial bit stream (restart intervals apart) and a refinement scan reads the
+// coefficient history earlier scans left, so it cannot be decoded speculatively.  What the format does allow:
+//   * scans commute unless they share a component and overlap in band (the host records those producers per scan);
+//   * a consumer needs block u of its producer only when it gets to block u itself: dependent scans run
+//     CONCURRENTLY, the consumer a few blocks behind the producer.  Producers publish their block count with a
+//     release store every JB_K1C_PUBLISH units, consumers acquire it (and read coefficients past L1, ld.cg).
+// libjpeg's 10-scan script has the chain {Y 1-5, Y 6-63} -> Y refine -> Y refine: instead of three passes in a row
+// (43 + 61 + 111 ms for a batch of 1080p frames) the frame takes about as long as its slowest scan.
+// One warp per job (JbProgJob): AC refinement scans are decoded by the whole warp, other scans by one lane per
+// restart segment.  Jobs are handed out through a ticket counter in list order -- the host puts producers in front
+// of consumers (and long dependency chains first) -- so a waiting warp's producers are always running or done.
 #pragma once
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
@@ -26,29 +30,44 @@ __device__ __forceinline__ uint32_t jb_prog_bits(JbBitReader &br, int k)
     return br.take(k);
 }
 
-__global__ void __launch_bounds__(32)
-jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-                        const JbDevScan *__restrict__ scans, int level, const JbHuffTable *__restrict__ tables,
-                        const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
-                        const JbScanResult *__restrict__ scanres, int16_t *__restrict__ coef,
-                        uint32_t *__restrict__ status, int lanes_per_warp)
+#define JB_K1C_PUBLISH 16u        // a single-segment scan publishes its progress every so many units
+#define JB_K1C_SPIN_LIMIT (1u << 22) // x 1 us: a producer that does not move for seconds -> JB_ST_STALLED, never a hang
+
+__device__ __forceinline__ uint32_t jb_ld_acquire(const uint32_t *p)
 {
-    const uint32_t image = image_list[blockIdx.y];
-    const JbDevImage &im = images[image];
-    const uint32_t scan_index = blockIdx.z; // every scan of the requested dependency level runs concurrently
-    if (scan_index >= im.nscans) return;
-    const JbDevScan sc = scans[im.scan_base + scan_index]; // by value: its fields are used in every inner loop
-    if (sc.level != level) return;
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void jb_st_release(uint32_t *p, uint32_t v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(32, 32)
+jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
+                         const JbProgJob *__restrict__ jobs, uint32_t njobs, const JbHuffTable *__restrict__ tables,
+                         const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
+                         const JbScanResult *__restrict__ scanres, int16_t *coef, uint32_t *__restrict__ status,
+                         uint32_t *progress, uint32_t *ticket)
+{
     const int lane = threadIdx.x;
-    // AC refinement scans of serial streams (one stream per warp) are decoded by lane 0 on a shared-memory copy of
-    // the current block that the whole warp loads (prefetched one block ahead) and stores back: the refinement
-    // loop reads and rewrites the block's coefficients one by one, which from global memory costs an L2 round
-    // trip per coefficient (a store evicts the line from L1)
-    const bool coop = lanes_per_warp == 1 && sc.ncomp == 1 && sc.ss != 0 && sc.ah != 0;
+    uint32_t turn = 0;
+    if (lane == 0) turn = atomicAdd(ticket, 1u);
+    turn = __shfl_sync(0xFFFFFFFFu, turn, 0);
+    if (turn >= njobs) return;
+    const JbProgJob job = jobs[turn];
+    const uint32_t image = job.image;
+    const JbDevImage &im = images[image];
+    const JbDevScan sc = scans[im.scan_base + job.scan]; // by value: its fields are used in every inner loop
+    uint32_t *const my_progress = progress + im.scan_base + job.scan;
+    // AC refinement scans are decoded by the whole warp on a shared-memory copy of the current block (prefetched one
+    // block ahead): the refinement loop reads and rewrites the block's coefficients one by one, which from global
+    // memory costs an L2 round trip per coefficient
+    const bool coop = sc.ncomp == 1 && sc.ss != 0 && sc.ah != 0;
     __shared__ uint32_t s_blk[32];
-    if (!coop && lane >= lanes_per_warp) return;
-    const uint32_t seg = coop ? blockIdx.x : blockIdx.x * lanes_per_warp + lane;
-    if (seg >= sc.nseg) return;
+    const bool active = coop || (uint32_t)lane < job.lanes;
+    const uint32_t seg = job.seg0 + (coop ? 0u : (uint32_t)lane);
 
     const JbScanResult sr = scanres[sc.range];
     const uint32_t *mk = marks + sc.mark_base;
@@ -57,17 +76,52 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
     const uint8_t *data = arena + im.data_off;
     const uint32_t rel = (uint32_t)(sc.data_off - im.data_off);
     const uint32_t per_seg = sc.dri ? sc.dri : sc.nunits;
-    const uint32_t first = seg * per_seg;
-    const uint32_t count = min(per_seg, sc.nunits - first);
+    const uint32_t first = min(seg * per_seg, sc.nunits);
+    uint32_t count = active ? min(per_seg, sc.nunits - first) : 0u;
     uint32_t start = 0, stop, err = 0;
-    if (seg > 0) {
+    if (active && seg > 0) {
         if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
-        else { atomicOr(status + image, JB_ST_EXPECT_RST); return; }
+        else { err = JB_ST_EXPECT_RST; count = 0; } // (the reference stops at the previous interval's end)
     }
+    const bool no_data = err != 0;
     stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
     start += rel;
     stop += rel;
+    if (no_data) start = stop;
     const bool needs_marker = sc.dri != 0 && count == per_seg;
+
+    // ---- producers.  `avail` = units of this scan whose history is final (every producer is past them)
+    uint32_t avail = sc.ndep ? 0u : 0xFFFFFFFFu;
+    auto wait_for = [&](uint32_t u) { // returns once unit u may be decoded
+        if (u < avail) return;
+        uint32_t a = 0xFFFFFFFFu;
+        const int nd = sc.ndep == 0xFF ? (int)job.scan : (int)sc.ndep;
+        for (int i = 0; i < nd; i++) {
+            const uint32_t ps = sc.ndep == 0xFF ? (uint32_t)i : (uint32_t)sc.dep[i];
+            const JbDevScan &pd = scans[im.scan_base + ps];
+            const bool whole = sc.ndep == 0xFF || ((sc.dep_all >> i) & 1u) || pd.nseg > 1;
+            const uint32_t total = pd.nseg > 1 ? pd.nseg : pd.nunits; // the count that means "complete"
+            const uint32_t *pp = progress + im.scan_base + ps;
+            uint32_t v, spins = 0;
+            for (;;) {
+                v = jb_ld_acquire(pp);
+                if (v >= total) { v = 0xFFFFFFFFu; break; }
+                if (!whole && v > u) break;
+                __nanosleep(spins < 32 ? 200 : 1000);
+                if (++spins > JB_K1C_SPIN_LIMIT) { err |= JB_ST_STALLED; v = 0xFFFFFFFFu; break; }
+            }
+            a = min(a, v);
+        }
+        avail = a;
+    };
+    uint32_t next_pub = first + JB_K1C_PUBLISH;
+    auto publish = [&](uint32_t done) { // single-segment scans: units 0..done-1 are final (called by every active lane)
+        if (sc.nseg != 1 || !sc.has_consumer || done < next_pub) return;
+        next_pub = done + JB_K1C_PUBLISH;
+        __threadfence();
+        if (coop) __syncwarp();
+        if (lane == 0) jb_st_release(my_progress, done);
+    };
 
     JbBitReader br;
     br.init(data, start, stop);
@@ -97,7 +151,7 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
             blk[0] = (int16_t)(v << al);
         } else { // refinement (:244-252)
             const int bit = (int)jb_prog_bits(br, 1);
-            blk[0] = (int16_t)(blk[0] | (int16_t)(bit << al));
+            blk[0] = (int16_t)(__ldcg(blk) | (int16_t)(bit << al)); // (history is read past L1: another SM wrote it)
         }
     };
 
@@ -117,7 +171,7 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
                     break;
                 }
                 do {
-                    int cv = blk[k];
+                    int cv = __ldcg(blk + k);
                     if (cv != 0) {
                         if (jb_prog_bits(br, 1) != 0) {
                             if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv >= 0 ? p1 : m1));
@@ -132,7 +186,7 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
         }
         if (eobrun > 0) {
             for (; k <= se; k++) {
-                int cv = blk[k];
+                int cv = __ldcg(blk + k);
                 if (cv != 0) {
                     if (jb_prog_bits(br, 1) != 0) {
                         if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv > 0 ? p1 : m1));
@@ -157,12 +211,16 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
         const uint64_t band = (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
         const uint64_t below_lo = (1ull << lane) - 1ull, below_hi = (1ull << (lane + 32)) - 1ull; // positions in front of mine
         uint32_t by = first / sc.wb, bx = first - by * sc.wb;
-        uint32_t nxt = count ? __ldg(plane + ((size_t)by * pw + bx) * 32 + lane) : 0u;
+        if (count) wait_for(first);
+        uint32_t nxt = count ? __ldcg(plane + ((size_t)by * pw + bx) * 32 + lane) : 0u;
         for (uint32_t u = first; u < first + count; u++) {
             uint32_t *gblk = const_cast<uint32_t *>(plane) + ((size_t)by * pw + bx) * 32;
             s_blk[lane] = nxt;
             if (++bx == sc.wb) { bx = 0; by++; }
-            if (u + 1 < first + count) nxt = __ldg(plane + ((size_t)by * pw + bx) * 32 + lane); // prefetch
+            if (u + 1 < first + count) { // prefetch
+                wait_for(u + 1);
+                nxt = __ldcg(plane + ((size_t)by * pw + bx) * 32 + lane);
+            }
             __syncwarp();
             int16_t *b16 = reinterpret_cast<int16_t *>(s_blk);
             int c_lo = b16[lane], c_hi = b16[lane + 32];
@@ -224,11 +282,12 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
             if (lane + 32 >= ss && lane + 32 <= se) g16[lane + 32] = (int16_t)c_hi;
             if (beyond && lane == ((se + 1) & 31)) // the reference's write just behind the band (corrupt streams only)
                 g16[se + 1] = (int16_t)(se + 1 < 32 ? c_lo : c_hi);
+            publish(u + 1);
         }
-        if (lane != 0) return;
     } else if (sc.ncomp > 1) {
         // ---- interleaved DC scan (:92-138)
         for (uint32_t u = first; u < first + count && !err; u++) {
+            wait_for(u);
             const uint32_t my = u / im.mcus_per_line, mx = u - my * im.mcus_per_line;
             for (int i = 0; i < sc.ncomp; i++) {
                 const int c = sc.comp[i];
@@ -239,11 +298,13 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
                         dc_block(blk, i);
                     }
             }
+            publish(u + 1);
         }
     } else {
         const int c = sc.comp[0];
         const int ss = sc.ss, se = sc.se;
         for (uint32_t u = first; u < first + count && !err; u++) {
+            wait_for(u);
             const uint32_t by = u / sc.wb, bx = u - by * sc.wb;
             int16_t *blk = store + ((size_t)im.comp_plane_off[c] + (size_t)by * im.comp_plane_w[c] + bx) * 64;
             if (ss == 0) {
@@ -254,6 +315,7 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
                     const uint32_t skip = min((uint32_t)eobrun, first + count - u);
                     eobrun -= (int)skip;
                     u += skip - 1;
+                    publish(u + 1);
                     continue;
                 }
                 for (int i = ss; i <= se; i++) {
@@ -274,17 +336,29 @@ jb_k1c_progressive_scan(const JbDevImage *__restrict__ images, const uint32_t *_
                 // ---- AC refinement (:313-419)
                 refine_block(blk, ss, se);
             }
+            publish(u + 1);
         }
     }
 
-    if (br.n < br.pad) err |= JB_ST_PREMATURE_END;
-    if (needs_marker && !err) {
-        const int real = br.n - br.pad;
-        uint32_t p = br.pos;
-        while (p < stop && data[p] == 0xFF) p++;
-        bool marker_ok = seg < sr.nmarkers;
-        if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u;
-        if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
+    if (active && (!coop || lane == 0)) {
+        if (br.n < br.pad) err |= JB_ST_PREMATURE_END;
+        if (needs_marker && !err) {
+            const int real = br.n - br.pad;
+            uint32_t p = br.pos;
+            while (p < stop && data[p] == 0xFF) p++;
+            bool marker_ok = seg < sr.nmarkers;
+            if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u;
+            if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
+        }
+        if (err) atomicOr(status + image, err);
     }
-    if (err) atomicOr(status + image, err);
+    // ---- this job's part of the scan is final, whatever happened: consumers must never wait for an error path
+    if (sc.has_consumer) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            if (sc.nseg == 1) jb_st_release(my_progress, sc.nunits);
+            else atomicAdd(my_progress, coop ? 1u : job.lanes);
+        }
+    }
 }

@@ -320,6 +320,23 @@ def test_progressive_and_sequential_in_one_batch():
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
 
 
+def test_progressive_batch_with_concurrent_dependent_scans():
+    """A few thousand K1c warps at once: every scan of every frame runs in one launch, refinement scans following
+    their producers block by block (more warps than the GPU holds at a time, so late jobs start behind early ones)."""
+    kinds = [dict(subsampling="4:4:4", quality=85), dict(subsampling="4:2:0", quality=92),
+             dict(subsampling="4:2:2", quality=70, restart_blocks=9), dict(gray=True, quality=88),
+             dict(subsampling="4:2:0", quality=80, restart_blocks=40)]
+    distinct = [synth.encode_jpeg(synth.synth_rgb(60 + i, 400 + 24 * i, 296 - 16 * i), progressive=True, **kinds[i % len(kinds)])
+                for i in range(10)]
+    want = [O.decode(blob).rgb for blob in distinct]
+    blobs = [distinct[i % len(distinct)] for i in range(600)]
+    with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
+        b.run()
+        assert b.status() == [0] * len(blobs)
+        for i in list(range(0, 600, 7)) + [599]:
+            assert np.array_equal(b.read_output(i), want[i % len(distinct)]), i
+
+
 # ------------------------------------------------------------------------------------------ lossless (SOF3)
 LOSSLESS_ASSETS = ["lossless%d_s22.jpg" % i for i in range(1, 8)]
 

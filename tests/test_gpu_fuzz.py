@@ -100,14 +100,18 @@ KINDS = ["flip", "bytes", "drop", "dup", "ones"]
 def test_corrupted_scans_decode_like_the_reference(name):
     blob = base_streams()[name]
     rng = np.random.default_rng(sum(map(ord, name)))
-    problems, agree_ok, agree_err = [], 0, 0
-    for trial in range(40):
+    problems, agree_ok, agree_err, same_class = [], 0, 0, 0
+    for trial in range(100):
         kind = KINDS[trial % len(KINDS)]
         bad = mutate(blob, rng, kind)
         want, werr = run_oracle(bad)
         got, gerr = run_gpu(bad)
         if werr is not None and gerr is not None:
             agree_err += 1
+            # several damaged intervals can fail in different ways: the reference reports the first one in stream
+            # order, the batch status word is the union -- the exception class is compared as a statistic only
+            same_class += isinstance(gerr, {-1: J.InvalidDataException, -2: J.InvalidOperationException,
+                                            -3: J.NotSupportedException}[werr.code])
         elif werr is None and gerr is None:
             if np.array_equal(got, want.planes):
                 agree_ok += 1
@@ -117,5 +121,6 @@ def test_corrupted_scans_decode_like_the_reference(name):
             problems.append(f"trial {trial} ({kind}): oracle raised [{werr}] but the GPU decoded")
         else:
             problems.append(f"trial {trial} ({kind}): GPU raised [{type(gerr).__name__}: {gerr}] but the oracle decoded")
-    print(f"{name}: {agree_ok} identical decodes, {agree_err} errors on both sides, {len(problems)} disagreements")
+    print(f"{name}: {agree_ok} identical decodes, {agree_err} errors on both sides ({same_class} of the same "
+          f"exception class), {len(problems)} disagreements")
     assert not problems, "\n".join(problems)
