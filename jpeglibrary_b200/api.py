@@ -385,6 +385,15 @@ class JpegBatchDecoder:
             _raise(k, self.ctx.last_error())
         return [(names[i].value.decode(), ms[i]) for i in range(k)]
 
+    def scan_trace(self):
+        """Progressive frames with profiling on: [(image, scan, segment, start_ns, end_ns, waited_ns)] per K1c job."""
+        n = N.cuda.jb_decode_batch_scan_trace(self.handle, None, 0)
+        if n <= 0:
+            return []
+        buf = np.zeros((n, 4), dtype=np.uint64)
+        N.cuda.jb_decode_batch_scan_trace(self.handle, buf.ctypes.data, n)
+        return [(int(k >> 32), int(k >> 16) & 0xFFFF, int(k) & 0xFFFF, int(a), int(e), int(w)) for k, a, e, w in buf.tolist()]
+
     def status(self):
         st = (C.c_int32 * self.count)()
         N.cuda.jb_decode_batch_status(self.handle, st, self.count)

@@ -113,14 +113,21 @@ struct JbDevScan {
     uint16_t dc_tab[4], ac_tab[4]; // device table indices, 0xFFFF = not defined
 };
 
-// One warp of K1c: a restart segment of an AC refinement scan (decoded by the whole warp) or up to 32 consecutive
-// segments of any other scan (one per lane).  Warps take jobs in list order through a ticket counter, and the
-// list holds producers in front of their consumers, so a warp never waits for a job that has not started.
-struct JbProgJob {
+// K1c work.  A lane entry is one restart segment of one scan; a job is one warp: either ONE segment of an AC
+// refinement scan, decoded by the whole warp, or up to 32 entries of other scans (of different images, same place
+// in their scan scripts), one per lane.  Warps take jobs in list order through a ticket counter, and the list holds
+// producers in front of their consumers, so a waiting warp's producers are always running or done.
+struct JbProgLane {
     uint32_t image;  // batch index
     uint32_t scan;   // scan index inside the image
-    uint32_t seg0;   // first restart segment
-    uint32_t lanes;  // segments of this job (1..32)
+    uint32_t seg;    // restart segment
+    uint32_t pad;
+};
+struct JbProgJob {
+    uint32_t first;  // first lane entry
+    uint32_t lanes;  // entries (1..32); 1 for a whole-warp job
+    uint32_t coop;   // whole-warp AC refinement
+    uint32_t pad;
 };
 
 // per-range result of K0 (restart scan)

@@ -378,8 +378,11 @@ struct jb_batch {
     std::vector<uint32_t> prog_images;
     uint32_t prog_list_off = 0, prog_max_scans = 0, prog_max_nseg = 1, prog_levels = 0;
     std::vector<JbProgJob> h_prog_jobs;    // K1c warps in ticket order: producers in front of consumers
+    std::vector<JbProgLane> h_prog_lanes;  // their lane entries
     JbProgJob *d_prog_jobs = nullptr;
+    JbProgLane *d_prog_lanes = nullptr;
     uint32_t *d_prog_progress = nullptr;   // per scan: units (one segment) or segments finished; last word: ticket counter
+    unsigned long long *d_prog_trace = nullptr; // profiling: {image|scan|seg, start, end, waited} ns per job
     uint64_t prog_coef_first = 0, prog_coef_blocks = 0; // contiguous slice of the store, zeroed per launch
     std::vector<JbDevScan> h_scans;
     std::vector<JbScanRange> h_ranges;
@@ -1152,16 +1155,40 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             for (size_t k = 0; k < ns; k++) order[n][k] = (uint32_t)k;
             std::stable_sort(order[n].begin(), order[n].end(), [&](uint32_t a, uint32_t c) { return weight[a] > weight[c]; });
         }
-        for (uint32_t rank = 0; rank < b->prog_max_scans; rank++)
+        // Whole-warp jobs (AC refinement, one per segment) first within a rank; the other scans of the rank are packed
+        // several lane entries to a warp.  Entries of one warp come from one rank, so they never wait for each other.
+        // A stream decodes fastest with a warp to itself; packing trades that for warp slots: pack just enough that
+        // all jobs can be resident at once (32 one-warp CTAs per SM).
+        uint64_t n_coop = 0, n_serial = 0;
+        for (uint32_t i : b->prog_images)
+            for (const JbDevScan &ds : b->plans[i].scans) (ds.ncomp == 1 && ds.ss != 0 && ds.ah != 0 ? n_coop : n_serial) += ds.nseg;
+        const uint64_t slots = 32ull * (uint64_t)ctx->prop.multiProcessorCount;
+        const uint64_t room = slots > n_coop + slots / 8 ? slots - n_coop : slots / 8;
+        uint32_t per_job = 1;
+        while (per_job < 32 && n_serial > room * per_job) per_job *= 2;
+        if (const char *e = getenv("JB_K1C_LANES")) per_job = (uint32_t)std::min(32, std::max(1, atoi(e))); // tuning knob
+        for (uint32_t rank = 0; rank < b->prog_max_scans; rank++) {
+            std::vector<JbProgLane> packed;
             for (size_t n = 0; n < b->prog_images.size(); n++) {
                 if (rank >= order[n].size()) continue;
                 const uint32_t k = order[n][rank];
                 const JbDevScan &ds = b->plans[b->prog_images[n]].scans[k];
                 const bool coop = ds.ncomp == 1 && ds.ss != 0 && ds.ah != 0; // (k_entropy_progressive.cuh)
-                const uint32_t per_job = coop ? 1u : 32u;
-                for (uint32_t seg = 0; seg < ds.nseg; seg += per_job)
-                    b->h_prog_jobs.push_back(JbProgJob{b->prog_images[n], k, seg, std::min(per_job, ds.nseg - seg)});
+                for (uint32_t seg = 0; seg < ds.nseg; seg++) {
+                    const JbProgLane e{b->prog_images[n], k, seg, 0};
+                    if (coop) {
+                        b->h_prog_jobs.push_back(JbProgJob{(uint32_t)b->h_prog_lanes.size(), 1, 1, 0});
+                        b->h_prog_lanes.push_back(e);
+                    } else
+                        packed.push_back(e);
+                }
             }
+            for (size_t at = 0; at < packed.size(); at += per_job) {
+                const uint32_t n = (uint32_t)std::min<size_t>(per_job, packed.size() - at);
+                b->h_prog_jobs.push_back(JbProgJob{(uint32_t)b->h_prog_lanes.size(), n, 0, 0});
+                b->h_prog_lanes.insert(b->h_prog_lanes.end(), packed.begin() + at, packed.begin() + at + n);
+            }
+        }
     }
     b->arena_bytes = arena + 256;
     b->marks_count = marks;
@@ -1215,6 +1242,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         JB_CUDA_B(cudaMemcpyAsync(b->d_scans, b->h_scans.data(), sizeof(JbDevScan) * b->h_scans.size(), cudaMemcpyHostToDevice, ctx->stream));
         JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_jobs, sizeof(JbProgJob) * b->h_prog_jobs.size()));
         JB_CUDA_B(cudaMemcpyAsync(b->d_prog_jobs, b->h_prog_jobs.data(), sizeof(JbProgJob) * b->h_prog_jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_lanes, sizeof(JbProgLane) * b->h_prog_lanes.size()));
+        JB_CUDA_B(cudaMemcpyAsync(b->d_prog_lanes, b->h_prog_lanes.data(), sizeof(JbProgLane) * b->h_prog_lanes.size(), cudaMemcpyHostToDevice, ctx->stream));
         JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_progress, sizeof(uint32_t) * (b->h_scans.size() + 1)));
     }
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
@@ -1374,9 +1403,10 @@ static int launch_kernels(jb_batch *b)
         JB_CUDA(ctx, jb_fill_async(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
         JB_CUDA(ctx, jb_fill_async(b->d_prog_progress, 0, sizeof(uint32_t) * (b->h_scans.size() + 1), st));
         const uint32_t njobs = (uint32_t)b->h_prog_jobs.size();
-        jb_k1c_progressive_scans<<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, njobs, b->d_tables, b->d_arena,
+        if (b->profiling && !b->d_prog_trace) JB_CUDA(ctx, jb_malloc_async(ctx, &b->d_prog_trace, sizeof(unsigned long long) * 4 * njobs));
+        jb_k1c_progressive_scans<<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables, b->d_arena,
                                                        b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                       b->d_prog_progress + b->h_scans.size());
+                                                       b->d_prog_progress + b->h_scans.size(), b->profiling ? b->d_prog_trace : nullptr);
         launches += 2;
         mark("jb_k1c_progressive_scans");
     }
@@ -1424,6 +1454,18 @@ int jb_decode_batch_set_profiling(jb_batch *b, int on)
     clear_events(b);
     b->profiling = on != 0;
     return JB_OK;
+}
+
+int jb_decode_batch_scan_trace(jb_batch *b, uint64_t *out, int cap)
+{
+    if (!b || (!out && cap > 0)) return JB_ERR_ARGUMENT;
+    jb_ctx *ctx = b->ctx;
+    const int n = (int)b->h_prog_jobs.size();
+    if (!b->d_prog_trace || cap <= 0) return b->d_prog_trace ? n : 0;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    JB_CUDA(ctx, cudaMemcpy(out, b->d_prog_trace, sizeof(uint64_t) * 4 * std::min(n, cap), cudaMemcpyDeviceToHost));
+    return std::min(n, cap);
 }
 
 int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap)
@@ -1614,7 +1656,9 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
     if (b->d_scans) cudaFreeAsync(b->d_scans, b->ctx->stream);
     if (b->d_prog_jobs) cudaFreeAsync(b->d_prog_jobs, b->ctx->stream);
+    if (b->d_prog_lanes) cudaFreeAsync(b->d_prog_lanes, b->ctx->stream);
     if (b->d_prog_progress) cudaFreeAsync(b->d_prog_progress, b->ctx->stream);
+    if (b->d_prog_trace) cudaFreeAsync(b->d_prog_trace, b->ctx->stream);
     if (b->d_ranges) cudaFreeAsync(b->d_ranges, b->ctx->stream);
     if (b->d_clean) cudaFreeAsync(b->d_clean, b->ctx->stream);
     if (b->d_clean_len) cudaFreeAsync(b->d_clean_len, b->ctx->stream);

@@ -17,9 +17,11 @@
 //     release store every JB_K1C_PUBLISH units, consumers acquire it (and read coefficients past L1, ld.cg).
 // libjpeg's 10-scan script has the chain {Y 1-5, Y 6-63} -> Y refine -> Y refine: instead of three passes in a row
 // (43 + 61 + 111 ms for a batch of 1080p frames) the frame takes about as long as its slowest scan.
-// One warp per job (JbProgJob): AC refinement scans are decoded by the whole warp, other scans by one lane per
-// restart segment.  Jobs are handed out through a ticket counter in list order -- the host puts producers in front
-// of consumers (and long dependency chains first) -- so a waiting warp's producers are always running or done.
+// One warp per job (JbProgJob): AC refinement scans are decoded by the whole warp (the serial symbol chain of one
+// stream is the bound, so its latency is what counts); the other scans are cheap per stream and are packed one per
+// lane, 32 images to a warp, so that they do not take warp slots and issue cycles from the refinement warps.  Jobs
+// are handed out through a ticket counter in list order -- the host puts producers in front of consumers (and long
+// dependency chains first) -- so a waiting warp's producers are always running or done.
 #pragma once
 #include "jb_device.cuh"
 #include "k_entropy_decode.cuh"
@@ -30,7 +32,7 @@ __device__ __forceinline__ uint32_t jb_prog_bits(JbBitReader &br, int k)
     return br.take(k);
 }
 
-#define JB_K1C_PUBLISH 16u        // a single-segment scan publishes its progress every so many units
+#define JB_K1C_PUBLISH 32u        // a single-segment scan publishes its progress every so many units
 #define JB_K1C_SPIN_LIMIT (1u << 22) // x 1 us: a producer that does not move for seconds -> JB_ST_STALLED, never a hang
 
 __device__ __forceinline__ uint32_t jb_ld_acquire(const uint32_t *p)
@@ -46,28 +48,33 @@ __device__ __forceinline__ void jb_st_release(uint32_t *p, uint32_t v)
 
 __global__ void __launch_bounds__(32, 32)
 jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
-                         const JbProgJob *__restrict__ jobs, uint32_t njobs, const JbHuffTable *__restrict__ tables,
+                         const JbProgJob *__restrict__ jobs, const JbProgLane *__restrict__ entries, uint32_t njobs,
+                         const JbHuffTable *__restrict__ tables,
                          const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
                          const JbScanResult *__restrict__ scanres, int16_t *coef, uint32_t *__restrict__ status,
-                         uint32_t *progress, uint32_t *ticket)
+                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace)
 {
     const int lane = threadIdx.x;
     uint32_t turn = 0;
     if (lane == 0) turn = atomicAdd(ticket, 1u);
     turn = __shfl_sync(0xFFFFFFFFu, turn, 0);
     if (turn >= njobs) return;
+    unsigned long long t_start = 0, t_wait = 0; // profiling only (jb_decode_batch_scan_trace)
+    if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     const JbProgJob job = jobs[turn];
-    const uint32_t image = job.image;
+    const bool coop = job.coop != 0;
+    const bool active = coop || (uint32_t)lane < job.lanes;
+    const JbProgLane ent = entries[job.first + (active && !coop ? (uint32_t)lane : 0u)];
+    const uint32_t image = ent.image;
     const JbDevImage &im = images[image];
-    const JbDevScan sc = scans[im.scan_base + job.scan]; // by value: its fields are used in every inner loop
-    uint32_t *const my_progress = progress + im.scan_base + job.scan;
+    const JbDevScan sc = scans[im.scan_base + ent.scan]; // by value: its fields are used in every inner loop
+    uint32_t *const my_progress = progress + im.scan_base + ent.scan;
     // AC refinement scans are decoded by the whole warp on a shared-memory copy of the current block (prefetched one
     // block ahead): the refinement loop reads and rewrites the block's coefficients one by one, which from global
     // memory costs an L2 round trip per coefficient
-    const bool coop = sc.ncomp == 1 && sc.ss != 0 && sc.ah != 0;
+    // (host: coop == (sc.ncomp == 1 && sc.ss != 0 && sc.ah != 0))
     __shared__ uint32_t s_blk[32];
-    const bool active = coop || (uint32_t)lane < job.lanes;
-    const uint32_t seg = job.seg0 + (coop ? 0u : (uint32_t)lane);
+    const uint32_t seg = ent.seg;
 
     const JbScanResult sr = scanres[sc.range];
     const uint32_t *mk = marks + sc.mark_base;
@@ -94,8 +101,10 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
     uint32_t avail = sc.ndep ? 0u : 0xFFFFFFFFu;
     auto wait_for = [&](uint32_t u) { // returns once unit u may be decoded
         if (u < avail) return;
+        unsigned long long t0 = 0, t1 = 0;
+        if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
         uint32_t a = 0xFFFFFFFFu;
-        const int nd = sc.ndep == 0xFF ? (int)job.scan : (int)sc.ndep;
+        const int nd = sc.ndep == 0xFF ? (int)ent.scan : (int)sc.ndep;
         for (int i = 0; i < nd; i++) {
             const uint32_t ps = sc.ndep == 0xFF ? (uint32_t)i : (uint32_t)sc.dep[i];
             const JbDevScan &pd = scans[im.scan_base + ps];
@@ -113,14 +122,18 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             a = min(a, v);
         }
         avail = a;
+        if (trace) {
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            t_wait += t1 - t0;
+        }
     };
     uint32_t next_pub = first + JB_K1C_PUBLISH;
-    auto publish = [&](uint32_t done) { // single-segment scans: units 0..done-1 are final (called by every active lane)
+    auto publish = [&](uint32_t done) { // single-segment scans: units 0..done-1 are final
         if (sc.nseg != 1 || !sc.has_consumer || done < next_pub) return;
         next_pub = done + JB_K1C_PUBLISH;
         __threadfence();
-        if (coop) __syncwarp();
-        if (lane == 0) jb_st_release(my_progress, done);
+        if (coop) __syncwarp(); // (every lane wrote part of the blocks)
+        if (!coop || lane == 0) jb_st_release(my_progress, done);
     };
 
     JbBitReader br;
@@ -201,15 +214,24 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         // ---- AC refinement, one stream per warp, decoded by the WHOLE warp.  Every lane runs the same bit reader and
         // Huffman decode (identical state, broadcast loads), lane l owns coefficients l and l + 32 of the block.
         // ReadBlockProgressiveACRefined (:313-419) walks the band position by position: a nonzero coefficient costs one
-        // correction bit, a zero one counts down the symbol's run.  Here the nonzero history of the block is a 64-bit
-        // ballot, so "the (r+1)-th zero from k on" is a prefix-popcount + ballot, the correction bits in front of it
-        // are read in one go and applied by all lanes at once.
+        // correction bit, a zero one counts down the symbol's run.  The history of a block does not change while the
+        // scan is at it (positions only move forward), so per block every lane ranks its two positions among the
+        // zero-history and among the nonzero-history positions of the band and the zero positions are listed in shared
+        // memory.  Per symbol, "the (r+1)-th zero from k on" is then one table look-up, the number of correction bits
+        // in front of it is arithmetic (k_end - k - r), they are read in one go and every lane picks its own by rank.
         const int c = sc.comp[0];
         const uint32_t *plane = reinterpret_cast<const uint32_t *>(store + (size_t)im.comp_plane_off[c] * 64);
         const uint32_t pw = im.comp_plane_w[c];
         const int ss = sc.ss, se = sc.se;
         const uint64_t band = (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
-        const uint64_t below_lo = (1ull << lane) - 1ull, below_hi = (1ull << (lane + 32)) - 1ull; // positions in front of mine
+        const uint32_t band_lo = (uint32_t)band, band_hi = (uint32_t)(band >> 32);
+        const uint32_t below = (1u << lane) - 1u; // lanes in front of mine
+        const bool in_lo = (band_lo >> lane) & 1u, in_hi = (band_hi >> lane) & 1u;
+        __shared__ uint8_t s_zpos[64];  // position of the t-th zero-history coefficient of the band
+        __shared__ uint16_t s_lut[1 << JB_LUT_BITS]; // first-level Huffman look-up of the scan's AC table
+        const JbHuffTable *actab = reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)sc.ac_tab[0] * sizeof(JbHuffTable));
+        for (int i = lane; i < (1 << JB_LUT_BITS) / 2; i += 32)
+            reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(actab->lut) + i);
         uint32_t by = first / sc.wb, bx = first - by * sc.wb;
         if (count) wait_for(first);
         uint32_t nxt = count ? __ldcg(plane + ((size_t)by * pw + bx) * 32 + lane) : 0u;
@@ -227,42 +249,62 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             bool beyond = false; // a coefficient was placed just behind the band (see below)
             __syncwarp();
             if (!err) {
-                const uint64_t Z = (((uint64_t)__ballot_sync(0xFFFFFFFFu, c_hi != 0) << 32) | __ballot_sync(0xFFFFFFFFu, c_lo != 0)) & band;
-                // correction bits for the nonzero-history positions in `nz` (ascending), read 16 at a time
-                auto correct = [&](uint64_t nz) {
-                    const int n = __popcll(nz);
-                    const int my_lo = (nz >> lane) & 1ull ? __popcll(nz & below_lo) : -1;
-                    const int my_hi = (nz >> (lane + 32)) & 1ull ? __popcll(nz & below_hi) : -1;
+                const uint32_t z_lo = __ballot_sync(0xFFFFFFFFu, c_lo == 0) & band_lo;  // zero history, in band
+                const uint32_t z_hi = __ballot_sync(0xFFFFFFFFu, c_hi == 0) & band_hi;
+                const uint32_t h_lo = band_lo & ~z_lo, h_hi = band_hi & ~z_hi;          // nonzero history, in band
+                const int nz_lo = __popc(z_lo), nzeros = nz_lo + __popc(z_hi);
+                const int nh_lo = __popc(h_lo), nhist = nh_lo + __popc(h_hi);
+                const bool mz_lo = (z_lo >> lane) & 1u, mz_hi = (z_hi >> lane) & 1u;
+                // my ranks among the nonzero-history positions (-1000: not one of them)
+                const int hr_lo = in_lo && !mz_lo ? __popc(h_lo & below) : -1000;
+                const int hr_hi = in_hi && !mz_hi ? nh_lo + __popc(h_hi & below) : -1000;
+                if (mz_lo) s_zpos[__popc(z_lo & below)] = (uint8_t)lane;
+                if (mz_hi) s_zpos[nz_lo + __popc(z_hi & below)] = (uint8_t)(lane + 32);
+                __syncwarp();
+                int zbase = 0, hbase = 0; // zero- / nonzero-history positions of the band in front of k
+                // n correction bits for the nonzero-history positions of rank hbase .. hbase + n - 1 (first bit = lowest)
+                auto correct = [&](int n) {
                     for (int done = 0; done < n; done += 16) {
                         const int cnt = min(16, n - done);
-                        const uint32_t v = jb_prog_bits(br, cnt); // first bit = lowest position
-                        if (my_lo >= done && my_lo < done + cnt && ((v >> (cnt - 1 - (my_lo - done))) & 1u) && (c_lo & p1) == 0)
-                            c_lo += c_lo >= 0 ? p1 : m1;
-                        if (my_hi >= done && my_hi < done + cnt && ((v >> (cnt - 1 - (my_hi - done))) & 1u) && (c_hi & p1) == 0)
-                            c_hi += c_hi >= 0 ? p1 : m1;
+                        if (br.n < cnt) br.ensure32();
+                        const uint32_t v = br.take(cnt);
+                        const int i_lo = hr_lo - hbase - done, i_hi = hr_hi - hbase - done;
+                        if ((unsigned)i_lo < (unsigned)cnt && ((v >> (cnt - 1 - i_lo)) & 1u) && (c_lo & p1) == 0) c_lo += c_lo >= 0 ? p1 : m1;
+                        if ((unsigned)i_hi < (unsigned)cnt && ((v >> (cnt - 1 - i_hi)) & 1u) && (c_hi & p1) == 0) c_hi += c_hi >= 0 ? p1 : m1;
                     }
+                    hbase += n;
                 };
                 int k = ss;
                 if (eobrun == 0) {
                     while (k <= se) {
-                        const int sym = huff(sc.ac_tab[0]);
-                        int r = sym >> 4, s = sym & 15;
-                        if (s != 0) {
-                            s = jb_prog_bits(br, 1) != 0 ? p1 : m1;
+                        br.ensure32(); // >= 33 bits: the code (<= 16), a sign bit or <= 14 run bits, and 16 more
+                        uint32_t e = s_lut[br.peek16() >> (16 - JB_LUT_BITS)];
+                        if ((e & 0xFFu) == 0) {
+                            e = jb_huff_lookup(actab, br.peek16());
+                            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; }
+                        }
+                        br.skip(e & 0xFFu);
+                        const int r = (int)(e >> 12), sz = (int)(e >> 8) & 15;
+                        int s = 0;
+                        if (sz != 0) {
+                            s = br.take(1) != 0 ? p1 : m1;
                         } else if (r != 15) {
                             eobrun = 1 << r;
-                            if (r != 0) eobrun += (int)jb_prog_bits(br, r);
+                            if (r != 0) eobrun += (int)br.take(r);
                             break;
                         }
                         // the (r+1)-th zero-history position at or behind k; the band end if there are fewer
-                        const uint64_t from_k = ~((1ull << k) - 1ull);
-                        const uint64_t zeros = ~Z & band & from_k;
-                        const bool z_lo = (zeros >> lane) & 1ull, z_hi = (zeros >> (lane + 32)) & 1ull;
-                        const uint32_t hit_lo = __ballot_sync(0xFFFFFFFFu, z_lo && __popcll(zeros & below_lo) == r);
-                        const uint32_t hit_hi = __ballot_sync(0xFFFFFFFFu, z_hi && __popcll(zeros & below_hi) == r);
-                        const int k_end = hit_lo ? __ffs(hit_lo) - 1 : hit_hi ? 32 + __ffs(hit_hi) - 1 : se + 1;
-                        const uint64_t upto = k_end >= 64 ? ~0ull : ((1ull << k_end) - 1ull);
-                        correct(Z & from_k & upto);
+                        const int target = zbase + r;
+                        int k_end, n;
+                        if (target < nzeros) {
+                            k_end = s_zpos[target];
+                            n = k_end - k - r;
+                            zbase = target + 1;
+                        } else {
+                            k_end = se + 1;
+                            n = nhist - hbase;
+                        }
+                        correct(n);
                         if (s != 0 && k_end < 64) { // (the reference writes at se + 1 when the run overshoots the band)
                             if (k_end < 32) { if (lane == k_end) c_lo = s; }
                             else if (lane == k_end - 32) c_hi = s;
@@ -272,7 +314,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                     }
                 }
                 if (eobrun > 0) {
-                    if (k <= se) correct(Z & ~((1ull << k) - 1ull));
+                    if (k <= se) correct(nhist - hbase);
                     --eobrun;
                 }
             }
@@ -285,19 +327,34 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             publish(u + 1);
         }
     } else if (sc.ncomp > 1) {
-        // ---- interleaved DC scan (:92-138)
+        // ---- interleaved DC scan (:92-138).  Component geometry is hoisted (compile-time indexed, so it stays in
+        // registers) and the MCU position is stepped instead of divided out per MCU.
+        int16_t *cbase[4];
+        uint32_t cpitch[4];
+        int ch[4], cv[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int c = sc.comp[i < sc.ncomp ? i : 0];
+            cbase[i] = store + (size_t)im.comp_plane_off[c] * 64;
+            cpitch[i] = im.comp_plane_w[c];
+            ch[i] = im.comp_h[c]; cv[i] = im.comp_v[c];
+        }
+        uint32_t my = first / im.mcus_per_line, mx = first - my * im.mcus_per_line;
+        const uint32_t mpl = im.mcus_per_line;
         for (uint32_t u = first; u < first + count && !err; u++) {
             wait_for(u);
-            const uint32_t my = u / im.mcus_per_line, mx = u - my * im.mcus_per_line;
-            for (int i = 0; i < sc.ncomp; i++) {
-                const int c = sc.comp[i];
-                const int h = im.comp_h[c], v = im.comp_v[c];
-                for (int y = 0; y < v; y++)
-                    for (int x = 0; x < h; x++) {
-                        int16_t *blk = store + ((size_t)im.comp_plane_off[c] + (size_t)(my * v + y) * im.comp_plane_w[c] + mx * h + x) * 64;
-                        dc_block(blk, i);
-                    }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (i >= sc.ncomp) break;
+                if (ch[i] == 1 && cv[i] == 1) {
+                    dc_block(cbase[i] + ((size_t)my * cpitch[i] + mx) * 64, i);
+                } else {
+                    for (int y = 0; y < cv[i]; y++)
+                        for (int x = 0; x < ch[i]; x++)
+                            dc_block(cbase[i] + ((size_t)(my * cv[i] + y) * cpitch[i] + mx * ch[i] + x) * 64, i);
+                }
             }
+            if (++mx == mpl) { mx = 0; my++; }
             publish(u + 1);
         }
     } else {
@@ -352,13 +409,19 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         }
         if (err) atomicOr(status + image, err);
     }
+    if (trace && lane == 0) {
+        unsigned long long t_end;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
+        trace[4 * turn] = ((unsigned long long)image << 32) | (ent.scan << 16) | min(ent.seg, 0xFFFFu);
+        trace[4 * turn + 1] = t_start; trace[4 * turn + 2] = t_end; trace[4 * turn + 3] = t_wait;
+    }
     // ---- this job's part of the scan is final, whatever happened: consumers must never wait for an error path
-    if (sc.has_consumer) {
+    if (coop ? sc.has_consumer != 0 : (active && sc.has_consumer)) {
         __threadfence();
-        __syncwarp();
-        if (lane == 0) {
+        if (coop) __syncwarp();
+        if (!coop || lane == 0) {
             if (sc.nseg == 1) jb_st_release(my_progress, sc.nunits);
-            else atomicAdd(my_progress, coop ? 1u : job.lanes);
+            else atomicAdd(my_progress, 1u);
         }
     }
 }

@@ -325,16 +325,30 @@ def test_progressive_batch_with_concurrent_dependent_scans():
     their producers block by block (more warps than the GPU holds at a time, so late jobs start behind early ones)."""
     kinds = [dict(subsampling="4:4:4", quality=85), dict(subsampling="4:2:0", quality=92),
              dict(subsampling="4:2:2", quality=70, restart_blocks=9), dict(gray=True, quality=88),
-             dict(subsampling="4:2:0", quality=80, restart_blocks=40)]
+             dict(subsampling="4:2:0", quality=80, restart_blocks=37)]
     distinct = [synth.encode_jpeg(synth.synth_rgb(60 + i, 400 + 24 * i, 296 - 16 * i), progressive=True, **kinds[i % len(kinds)])
                 for i in range(10)]
-    want = [O.decode(blob).rgb for blob in distinct]
+    want = []
+    for blob in distinct:  # (one of them ends a scan on a restart-interval boundary: the reference's quirk above)
+        try:
+            want.append(O.decode(blob).rgb)
+        except O.OracleError as e:
+            want.append(e.code)
+    assert sum(isinstance(w, int) for w in want) <= 2
     blobs = [distinct[i % len(distinct)] for i in range(600)]
     with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
-        b.run()
-        assert b.status() == [0] * len(blobs)
+        try:
+            b.run()
+        except (J.InvalidOperationException, J.InvalidDataException):
+            pass
+        st = b.status()
+        for i in range(600):
+            w = want[i % len(distinct)]
+            assert st[i] == (w if isinstance(w, int) else 0), i
         for i in list(range(0, 600, 7)) + [599]:
-            assert np.array_equal(b.read_output(i), want[i % len(distinct)]), i
+            w = want[i % len(distinct)]
+            if not isinstance(w, int):
+                assert np.array_equal(b.read_output(i), w), i
 
 
 # ------------------------------------------------------------------------------------------ lossless (SOF3)
