@@ -128,8 +128,9 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         }
     };
     uint32_t next_pub = first + JB_K1C_PUBLISH;
+    const bool publishes = sc.nseg == 1 && sc.has_consumer != 0;
     auto publish = [&](uint32_t done) { // single-segment scans: units 0..done-1 are final
-        if (sc.nseg != 1 || !sc.has_consumer || done < next_pub) return;
+        if (!publishes || done < next_pub) return;
         next_pub = done + JB_K1C_PUBLISH;
         __threadfence();
         if (coop) __syncwarp(); // (every lane wrote part of the blocks)
@@ -169,47 +170,6 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
     };
 
     const int p1 = 1 << al, m1 = -(1 << al);
-    // ---- AC refinement of one block (:313-419)
-    auto refine_block = [&](int16_t *blk, int ss, int se) {
-        int k = ss;
-        if (eobrun == 0) {
-            for (; k <= se; k++) {
-                const int sym = huff(sc.ac_tab[0]);
-                int r = sym >> 4, s = sym & 15;
-                if (s != 0) {
-                    s = jb_prog_bits(br, 1) != 0 ? p1 : m1;
-                } else if (r != 15) {
-                    eobrun = 1 << r;
-                    if (r != 0) eobrun += (int)jb_prog_bits(br, r);
-                    break;
-                }
-                do {
-                    int cv = __ldcg(blk + k);
-                    if (cv != 0) {
-                        if (jb_prog_bits(br, 1) != 0) {
-                            if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv >= 0 ? p1 : m1));
-                        }
-                    } else {
-                        if (--r < 0) break;
-                    }
-                    k++;
-                } while (k <= se);
-                if (s != 0 && k < 64) blk[k] = (int16_t)s;
-            }
-        }
-        if (eobrun > 0) {
-            for (; k <= se; k++) {
-                int cv = __ldcg(blk + k);
-                if (cv != 0) {
-                    if (jb_prog_bits(br, 1) != 0) {
-                        if ((cv & p1) == 0) blk[k] = (int16_t)(cv + (cv > 0 ? p1 : m1));
-                    }
-                }
-            }
-            --eobrun;
-        }
-    };
-
     if (coop) {
         // ---- AC refinement, one stream per warp, decoded by the WHOLE warp.  Every lane runs the same bit reader and
         // Huffman decode (identical state, broadcast loads), lane l owns coefficients l and l + 32 of the block.
@@ -232,13 +192,14 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         const JbHuffTable *actab = reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)sc.ac_tab[0] * sizeof(JbHuffTable));
         for (int i = lane; i < (1 << JB_LUT_BITS) / 2; i += 32)
             reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(actab->lut) + i);
-        uint32_t by = first / sc.wb, bx = first - by * sc.wb;
+        const uint32_t wb = sc.wb;
+        uint32_t by = first / wb, bx = first - by * wb;
         if (count) wait_for(first);
         uint32_t nxt = count ? __ldcg(plane + ((size_t)by * pw + bx) * 32 + lane) : 0u;
         for (uint32_t u = first; u < first + count; u++) {
             uint32_t *gblk = const_cast<uint32_t *>(plane) + ((size_t)by * pw + bx) * 32;
             s_blk[lane] = nxt;
-            if (++bx == sc.wb) { bx = 0; by++; }
+            if (++bx == wb) { bx = 0; by++; }
             if (u + 1 < first + count) { // prefetch
                 wait_for(u + 1);
                 nxt = __ldcg(plane + ((size_t)by * pw + bx) * 32 + lane);
@@ -357,43 +318,72 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (++mx == mpl) { mx = 0; my++; }
             publish(u + 1);
         }
-    } else {
+    } else if (sc.ss == 0) {
+        // ---- single-component DC scan (:140-194 with ReadBlockProgressiveDC)
         const int c = sc.comp[0];
-        const int ss = sc.ss, se = sc.se;
+        const uint32_t wb = sc.wb, pitch = im.comp_plane_w[c];
+        int16_t *base = store + (size_t)im.comp_plane_off[c] * 64;
+        uint32_t by = first / wb, bx = first - by * wb;
         for (uint32_t u = first; u < first + count && !err; u++) {
             wait_for(u);
-            const uint32_t by = u / sc.wb, bx = u - by * sc.wb;
-            int16_t *blk = store + ((size_t)im.comp_plane_off[c] + (size_t)by * im.comp_plane_w[c] + bx) * 64;
-            if (ss == 0) {
-                dc_block(blk, 0);
-            } else if (sc.ah == 0) {
-                // ---- AC first scan (:259-305)
-                if (eobrun != 0) { // the whole run of end-of-band blocks at once
-                    const uint32_t skip = min((uint32_t)eobrun, first + count - u);
-                    eobrun -= (int)skip;
-                    u += skip - 1;
-                    publish(u + 1);
-                    continue;
-                }
-                for (int i = ss; i <= se; i++) {
-                    const int sym = huff(sc.ac_tab[0]);
-                    const int r = sym >> 4, s = sym & 15;
-                    i += r;
-                    if (s != 0) {
-                        const int v = jb_extend((int)jb_prog_bits(br, s), s);
-                        blk[min(i, 63)] = (int16_t)(v << al);
-                    } else if (r != 15) {
-                        eobrun = 1 << r;
-                        if (r != 0) eobrun += (int)jb_prog_bits(br, r);
-                        --eobrun;
-                        break;
-                    }
-                }
-            } else {
-                // ---- AC refinement (:313-419)
-                refine_block(blk, ss, se);
-            }
+            dc_block(base + ((size_t)by * pitch + bx) * 64, 0);
+            if (++bx == wb) { bx = 0; by++; }
             publish(u + 1);
+        }
+    } else {
+        // ---- AC first scan (:259-305), ONE loop over symbols: the lanes of a packed warp are in different blocks of
+        // different images, and a loop nest per block would make every lane wait for the longest block of the warp
+        // at each block end.  (AC refinement scans never get here: they are whole-warp jobs.)
+        const int c = sc.comp[0];
+        const int ss = sc.ss, se = sc.se;
+        const uint32_t wb = sc.wb, pitch = im.comp_plane_w[c];
+        int16_t *base = store + (size_t)im.comp_plane_off[c] * 64;
+        const JbHuffTable *actab = reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)sc.ac_tab[0] * sizeof(JbHuffTable));
+        const uint32_t end = first + count;
+        uint32_t u = first;
+        uint32_t by = first / wb, bx = first - by * wb;
+        int16_t *blk = base + ((size_t)by * pitch + bx) * 64;
+        int i = ss;
+        if (count) wait_for(first);
+        while (u < end && !err) {
+            bool block_done = false;
+            if (eobrun != 0) { // the whole run of end-of-band blocks at once
+                const uint32_t skip = min((uint32_t)eobrun, end - u);
+                eobrun -= (int)skip;
+                u += skip;
+                by = u / wb; bx = u - by * wb;
+                blk = base + ((size_t)by * pitch + bx) * 64;
+                i = ss;
+                publish(u);
+                if (u < end) wait_for(u);
+                continue;
+            }
+            br.ensure32(); // >= 33 bits: the code (<= 16) and up to 16 magnitude / run bits
+            uint32_t e = jb_huff_lookup(actab, br.peek16());
+            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; }
+            br.skip(e & 0xFFu);
+            const int r = (int)(e >> 12), sz = (int)(e >> 8) & 15;
+            if (sz != 0) {
+                i += r;
+                const int v = jb_extend((int)br.take(sz), sz);
+                blk[min(i, 63)] = (int16_t)(v << al);
+                i++;
+            } else if (r == 15) {
+                i += 16;
+            } else {
+                eobrun = 1 << r;
+                if (r != 0) eobrun += (int)br.take(r);
+                --eobrun;
+                block_done = true;
+            }
+            if (block_done || i > se) {
+                u++;
+                i = ss;
+                if (++bx == wb) { bx = 0; by++; }
+                blk = base + ((size_t)by * pitch + bx) * 64;
+                publish(u);
+                if (u < end) wait_for(u);
+            }
         }
     }
 

@@ -1,11 +1,12 @@
 """K1c schedule of a progressive batch (jb_decode_batch_scan_trace): per scan start / end / time spent waiting for
-producer scans.  usage (on a GPU box): python profiles/prog_trace.py [batch]"""
+producer scans.  usage (on a GPU box): python profiles/prog_trace.py [batch [distinct images]]"""
 import sys, numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import jpeglibrary_b200 as J, synth
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-distinct = [synth.encode_jpeg(synth.synth_rgb(i, 1920, 1080), quality=85, subsampling="4:4:4", progressive=True) for i in range(4)]
-blobs = [distinct[i % 4] for i in range(batch)]
+ndist = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+distinct = [synth.encode_jpeg(synth.synth_rgb(i, 1920, 1080), quality=85, subsampling="4:4:4", progressive=True) for i in range(ndist)]
+blobs = [distinct[i % ndist] for i in range(batch)]
 with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
     b.run()
     b.set_profiling(True)
@@ -21,4 +22,5 @@ with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
     # per scan averages
     for s in range(10):
         xs = [t for t in tr if t[1] == s]
-        print("scan %d: mean start %.1f end %.1f busy %.1f waited %.1f" % (s, np.mean([(t[3]-t0)/1e6 for t in xs]), np.mean([(t[4]-t0)/1e6 for t in xs]), np.mean([(t[4]-t[3]-t[5])/1e6 for t in xs]), np.mean([t[5]/1e6 for t in xs])))
+        print("scan %d: max end %.1f;" % (s, max((t[4]-t0)/1e6 for t in xs)), end=" ")
+        print("mean start %.1f end %.1f busy %.1f waited %.1f" % (np.mean([(t[3]-t0)/1e6 for t in xs]), np.mean([(t[4]-t0)/1e6 for t in xs]), np.mean([(t[4]-t[3]-t[5])/1e6 for t in xs]), np.mean([t[5]/1e6 for t in xs])))
