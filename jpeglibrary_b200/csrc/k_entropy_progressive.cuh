@@ -164,8 +164,9 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (slot == 0) pred[0] = v; else if (slot == 1) pred[1] = v; else if (slot == 2) pred[2] = v; else pred[3] = v;
             blk[0] = (int16_t)(v << al);
         } else { // refinement (:244-252)
-            const int bit = (int)jb_prog_bits(br, 1);
-            blk[0] = (int16_t)(__ldcg(blk) | (int16_t)(bit << al)); // (history is read past L1: another SM wrote it)
+            // blk[0] |= bit << al without a load in the decoder's dependency chain: an OR reduction on the block's
+            // first word, resolved in L2 (blk[1], the other half of the word, may be written by an AC scan meanwhile)
+            if (jb_prog_bits(br, 1) != 0) atomicOr(reinterpret_cast<unsigned int *>(blk), 1u << al);
         }
     };
 
