@@ -199,7 +199,10 @@ typedef struct jb_encode_desc {
     uint8_t component_count;                 /* 1 or 3 */
     uint8_t h[JB_MAX_COMPONENTS], v[JB_MAX_COMPONENTS];   /* AddComponent sampling factors (JpegEncoder.cs:175) */
     uint8_t tq[JB_MAX_COMPONENTS], td[JB_MAX_COMPONENTS], ta[JB_MAX_COMPONENTS];
-    uint8_t reserved[3];
+    uint8_t reserved;
+    uint16_t restart_interval;               /* JB_IN_COEFFICIENTS only: MCUs per restart interval of the scan that is
+                                                re-packed (JpegOptimizer.CopyScanBaseline, JpegOptimizer.cs:772-812:
+                                                DC prediction restarts, 1-bit padding, RSTn written between intervals) */
     uint16_t quant[4][64];                   /* SetQuantizationTable, zig-zag order, by identifier */
     uint8_t quant_present[4];
 } jb_encode_desc;

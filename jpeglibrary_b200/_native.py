@@ -71,7 +71,7 @@ class EncodeDesc(C.Structure):
     _fields_ = [("pixels", C.c_void_p), ("pitch", C.c_uint64), ("on_device", C.c_int32), ("format", C.c_int32),
                 ("width", C.c_uint16), ("height", C.c_uint16), ("component_count", C.c_uint8),
                 ("h", C.c_uint8 * 4), ("v", C.c_uint8 * 4), ("tq", C.c_uint8 * 4), ("td", C.c_uint8 * 4),
-                ("ta", C.c_uint8 * 4), ("reserved", C.c_uint8 * 3), ("quant", (C.c_uint16 * 64) * 4),
+                ("ta", C.c_uint8 * 4), ("reserved", C.c_uint8), ("restart_interval", C.c_uint16), ("quant", (C.c_uint16 * 64) * 4),
                 ("quant_present", C.c_uint8 * 4)]
 
 

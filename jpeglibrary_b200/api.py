@@ -873,7 +873,10 @@ class JpegOptimizer:
     Optimize(strip): re-pack the same coefficients with the new tables (K4) and rewrite the stream like
     JpegOptimizer.Optimize (:546-647): SOI/APP0/SOF copied, the first DHT/DQT replaced by all tables, SOS
     copied with the new scan data, other segments dropped when `strip`.  No DCT is involved.
-    Restart intervals are refused (the reference itself drops DRI with strip=True while keeping RSTn: quirk Q6)."""
+    Restart intervals are preserved like CopyScanBaseline does (:772-812): DC prediction restarts, every interval is
+    padded with 1-bits and followed by its RSTn.  Deliberate deviation (quirk Q6): the reference drops the DRI segment
+    with strip=True while keeping the RSTn markers, which leaves a stream no decoder accepts -- the DRI segment is
+    always kept here."""
 
     def __init__(self, context=None):
         self._ctx = context
@@ -922,8 +925,6 @@ class JpegOptimizer:
         if d.scan_count < 1:
             raise InvalidDataException("No image data is read.")
         sc = d.scans[0]
-        if sc.restart_interval != 0:
-            raise NotSupportedException("restart intervals are not transcoded on the GPU path (reference quirk Q6)")
         hmax = max(d.h[i] for i in range(d.component_count))
         vmax = max(d.v[i] for i in range(d.component_count))
         nblk = ((d.width + 8 * hmax - 1) // (8 * hmax)) * ((d.height + 8 * vmax - 1) // (8 * vmax)) * \
@@ -936,6 +937,7 @@ class JpegOptimizer:
         e = N.EncodeDesc()
         e.pixels, e.on_device, e.format = self._coef_dev, 1, N.JB_IN_COEFFICIENTS
         e.width, e.height, e.component_count = d.width, d.height, sc.component_count
+        e.restart_interval = sc.restart_interval
         self._table_order = []
         for i in range(sc.component_count):
             c = sc.component_index[i]
@@ -1027,8 +1029,8 @@ class JpegOptimizer:
                 out += _marker_segment(0xDA, payload) + scan.tobytes()
             elif m == 0xD9:
                 out += b"\xff\xd9"
-            elif not strip:
-                out += _marker_segment(m, payload)
+            elif not strip or (m == 0xDD and self._parsed.desc.scans[0].restart_interval != 0):
+                out += _marker_segment(m, payload)   # (DRI is kept with strip too: see the class comment, quirk Q6)
         if hasattr(self._output, "write"):
             self._output.write(bytes(out))
         else:

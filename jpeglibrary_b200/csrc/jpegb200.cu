@@ -1741,6 +1741,7 @@ struct jb_encode_batch {
     std::vector<Group> groups;
     std::vector<uint64_t> pix_bytes, pix_dev_off;
     uint32_t max_blocks = 0;
+    uint32_t max_intervals = 0; // restart intervals of the image that has most (transcoding only)
     // device
     JbEncImage *d_images = nullptr;
     uint16_t *d_quant = nullptr;
@@ -1849,6 +1850,10 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
             }
         }
         d.bpm = (uint8_t)bpm;
+        if (e.restart_interval != 0 && !import) return bad(JB_ERR_NOT_SUPPORTED, "restart intervals are written when transcoding only (the reference encoder has none)");
+        d.dri = e.restart_interval;
+        d.nint = d.dri ? (d.total_mcus + d.dri - 1) / d.dri : 1;
+        b->max_intervals = std::max<uint32_t>(b->max_intervals, d.dri ? d.nint : 0);
         d.quant_off = (uint32_t)b->quant.size();
         for (int c = 0; c < e.component_count; c++)
             for (int k = 0; k < 64; k++) b->quant.push_back(import ? 1 : e.quant[e.tq[c]][k]);
@@ -1856,7 +1861,7 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         d.coef_off = blocks; d.bits_off = blocks;
         blocks += nblk;
         b->max_blocks = std::max<uint32_t>(b->max_blocks, (uint32_t)nblk);
-        d.raw_off = raw; d.raw_cap = align_up(nblk * 96 + 4096, 256); // 768 bits per block on average
+        d.raw_off = raw; d.raw_cap = align_up(nblk * 96 + 3ull * d.nint + 4096, 256); // 768 bits per block on average
         raw += d.raw_cap;
         d.out_off = outb; d.out_cap = align_up(d.raw_cap + d.raw_cap / 8 + 256, 256);
         outb += d.out_cap;
@@ -2005,9 +2010,14 @@ int jb_encode_batch_pack(jb_encode_batch *b)
     JB_CUDA(ctx, jb_fill_async(b->d_raw, 0, (b->raw_bytes + 3) / 4 * 4, st));
     dim3 grid((b->max_blocks + 255) / 256, b->count);
     jb_k4a_block_bits<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits);
+    if (b->max_intervals > 1) { // transcoding a scan with restart intervals
+        dim3 igrid((b->max_intervals + 7) / 8, b->count);
+        jb_k4a_interval_gaps<<<igrid, 256, 0, st>>>(b->d_images, b->d_bits);
+        b->launches++;
+    }
     jb_k4b_scan<<<b->count, 1024, 0, st>>>(b->d_images, b->d_bits, b->d_totals);
     jb_k4c_pack<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits, b->d_totals, b->d_raw, b->d_status);
-    jb_k4d_stuff<<<b->count, 256, 0, st>>>(b->d_images, b->d_totals, b->d_raw, b->d_out, b->d_out_len, b->d_status);
+    jb_k4d_stuff<<<b->count, 256, 0, st>>>(b->d_images, b->d_totals, b->d_bits, b->d_raw, b->d_out, b->d_out_len, b->d_status);
     b->launches += 4;
     JB_CUDA(ctx, cudaGetLastError());
     return JB_OK;

@@ -37,6 +37,8 @@ struct JbEncImage {
     uint8_t comp_td[4], comp_ta[4];
     uint8_t blk_comp[JB_MAX_BLOCKS_PER_MCU];
     uint8_t pad[5];
+    uint32_t dri;       // transcoding only: MCUs per restart interval (0: none)
+    uint32_t nint;      // number of restart intervals (1 without DRI)
 };
 
 struct JbEncTable {     // one optimised Huffman table
@@ -294,6 +296,7 @@ __device__ __forceinline__ int64_t jb_prev_block(const JbEncImage &im, uint32_t 
     const int c = im.blk_comp[b];
     if (b > 0 && im.blk_comp[b - 1] == c) return (int64_t)blk - 1;
     if (mcu == 0) return -1;
+    if (im.dri != 0 && mcu % im.dri == 0) return -1; // DC prediction restarts with every restart interval
     int last = b; // last block of component c inside an MCU
     while (last + 1 < im.bpm && im.blk_comp[last + 1] == c) last++;
     return (int64_t)(mcu - 1) * im.bpm + last;
@@ -555,6 +558,24 @@ __device__ __forceinline__ uint32_t jb_encode_block(const JbEncImage &im, const 
     return nbits;
 }
 
+// Restart intervals (transcoding): every interval starts on a byte boundary behind the previous interval's 1-bit
+// padding and the two marker bytes (JpegOptimizer.cs:794-812).  One warp per interval adds that gap to the bit count
+// of the interval's last block, so that the plain prefix sum of K4b yields the right offsets.
+__global__ void __launch_bounds__(256)
+jb_k4a_interval_gaps(const JbEncImage *__restrict__ images, uint32_t *__restrict__ block_bits)
+{
+    const JbEncImage &im = images[blockIdx.y];
+    const uint32_t k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (im.dri == 0 || k + 1 >= im.nint) return; // (the last interval is padded by K4d like any scan end)
+    const uint32_t per = im.dri * im.bpm;
+    uint32_t *a = block_bits + im.bits_off + (uint64_t)k * per;
+    uint32_t sum = 0;
+    for (uint32_t i = lane; i < per; i += 32) sum += a[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, d);
+    if (lane == 0) a[per - 1] += ((8u - (sum & 7u)) & 7u) + 16u;
+}
+
 __global__ void __launch_bounds__(256)
 jb_k4a_block_bits(const JbEncImage *__restrict__ images, const int16_t *__restrict__ coef,
                   const JbEncTable *__restrict__ tables, uint32_t *__restrict__ block_bits)
@@ -611,15 +632,29 @@ jb_k4c_pack(const JbEncImage *__restrict__ images, const int16_t *__restrict__ c
         return;
     }
     uint32_t *words = reinterpret_cast<uint32_t *>(raw + im.raw_off);
-    jb_encode_block<true>(im, coef, blk, tables, words, block_bits[im.bits_off + blk]);
+    const uint32_t at = block_bits[im.bits_off + blk];
+    const uint32_t nbits = jb_encode_block<true>(im, coef, blk, tables, words, at);
+    if (im.dri != 0) {
+        // the last block of a restart interval also writes the 1-bit padding and the RSTn marker behind it
+        const uint32_t per = im.dri * im.bpm, k = blk / per;
+        if (blk % per == per - 1 && k + 1 < im.nint) {
+            const uint32_t end = at + nbits, padbits = (8u - (end & 7u)) & 7u;
+            const uint32_t v = (((1u << padbits) - 1u) << 16) | 0xFFD0u | (k & 7u); // pad, FF, D0 + (k mod 8)
+            const uint32_t len = padbits + 16;                                      // <= 23 bits, MSB first at `end`
+            const uint32_t w = end >> 5, sh = end & 31u;
+            const uint64_t placed = ((uint64_t)v << (64 - len)) >> sh;
+            atomicOr(words + w, (uint32_t)(placed >> 32));
+            if ((uint32_t)placed) atomicOr(words + w + 1, (uint32_t)placed);
+        }
+    }
 }
 
 // ---- E9: byte stuffing + padding (JpegWriter.FlushRegister :104-128, ExitBitMode :141-167).
 // The un-stuffed stream holds big-endian 32-bit words; one CTA per image.
 __global__ void __launch_bounds__(256)
 jb_k4d_stuff(const JbEncImage *__restrict__ images, const unsigned long long *__restrict__ totals,
-             const uint8_t *__restrict__ raw, uint8_t *__restrict__ out, uint32_t *__restrict__ out_len,
-             uint32_t *__restrict__ status)
+             const uint32_t *__restrict__ block_bits, const uint8_t *__restrict__ raw, uint8_t *__restrict__ out,
+             uint32_t *__restrict__ out_len, uint32_t *__restrict__ status)
 {
     const JbEncImage &im = images[blockIdx.x];
     const unsigned long long bits = totals[blockIdx.x];
@@ -633,10 +668,29 @@ jb_k4d_stuff(const JbEncImage *__restrict__ images, const unsigned long long *__
     __syncthreads();
     if (bits + 64 > im.raw_cap * 8) { if (tid == 0) out_len[blockIdx.x] = 0; return; }
     const int padbits = (int)((8 - (bits & 7)) & 7);
+    // restart markers sit in the un-stuffed stream already (K4c); their FF must not be stuffed.  Marker k occupies the
+    // two bytes in front of interval k + 1, whose first block's bit offset is in block_bits.
+    const uint32_t per = im.dri * im.bpm;
+    const uint32_t nmark = im.dri ? im.nint - 1 : 0;
+    const uint32_t *first_bits = block_bits + im.bits_off;
+    auto marker_at = [&](uint32_t k) { return (first_bits[(uint64_t)(k + 1) * per] >> 3) - 2u; }; // byte offset of its FF
     for (uint32_t tile = 0; tile < nbytes; tile += 256 * 16) {
         const uint32_t pos0 = tile + tid * 16;
         uint8_t b[16];
         uint32_t cnt = 0;
+        uint32_t plain = 0; // bit e: byte pos0 + e is the FF of a marker (copied as it is)
+        if (nmark && pos0 < nbytes) {
+            uint32_t lo = 0, hi = nmark; // first marker at or behind pos0
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (marker_at(mid) < pos0) lo = mid + 1; else hi = mid;
+            }
+            for (; lo < nmark; lo++) {
+                const uint32_t m = marker_at(lo);
+                if (m >= pos0 + 16) break;
+                plain |= 1u << (m - pos0);
+            }
+        }
 #pragma unroll
         for (int q = 0; q < 4; q++) {
             const uint32_t w = pos0 + q * 4 < nbytes ? words[(pos0 >> 2) + q] : 0;
@@ -646,7 +700,7 @@ jb_k4d_stuff(const JbEncImage *__restrict__ images, const unsigned long long *__
                 const uint32_t p = pos0 + q * 4 + e;
                 if (p == nbytes - 1 && padbits) v |= (1u << padbits) - 1u; // final partial byte: 1-bits
                 b[q * 4 + e] = (uint8_t)v;
-                if (p < nbytes) cnt += v == 0xFF ? 2 : 1;
+                if (p < nbytes) cnt += (v == 0xFF && !((plain >> (q * 4 + e)) & 1u)) ? 2 : 1;
             }
         }
         uint32_t incl = cnt;
@@ -660,7 +714,7 @@ jb_k4d_stuff(const JbEncImage *__restrict__ images, const unsigned long long *__
         if ((unsigned long long)off + 32 <= im.out_cap) {
 #pragma unroll
             for (int e = 0; e < 16; e++)
-                if (pos0 + e < nbytes) { dst[off++] = b[e]; if (b[e] == 0xFF) dst[off++] = 0; }
+                if (pos0 + e < nbytes) { dst[off++] = b[e]; if (b[e] == 0xFF && !((plain >> e) & 1u)) dst[off++] = 0; }
         }
         __syncthreads();
         if (tid == 0) s_base += tot;

@@ -65,6 +65,46 @@ def test_optimizer_errors():
     opt.SetInput(golden_bytes("progress.jpg"))
     with pytest.raises(J.InvalidDataException):
         opt.Scan()                              # "Progressive JPEG is not supported currently."
-    opt.SetInput(synth.synth_jpeg(3, 64, 48, restart_rows=1))
-    with pytest.raises(J.NotSupportedException):
-        opt.Scan()
+
+
+@pytest.mark.parametrize("kw", [dict(width=640, height=400, subsampling="4:2:0", restart_rows=1),
+                                dict(width=333, height=211, subsampling="4:2:0", restart_blocks=7),   # partial last interval
+                                dict(width=200, height=120, subsampling="4:2:2", restart_blocks=1),   # DRI = 1
+                                dict(width=1920, height=1080, subsampling="4:4:4", restart_rows=2, quality=92),
+                                dict(width=160, height=96, gray=True, restart_blocks=5)],
+                         ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+@pytest.mark.parametrize("strip", [True, False])
+def test_optimize_keeps_restart_intervals(kw, strip):
+    """CopyScanBaseline (JpegOptimizer.cs:772-812): DC prediction restarts per interval, intervals are padded with
+    1-bits and separated by RSTn.  The DRI segment is kept even with strip (documented deviation, quirk Q6)."""
+    kw = dict(kw)
+    w, h = kw.pop("width"), kw.pop("height")
+    src = synth.synth_jpeg(14, w, h, **kw)
+    opt = J.JpegOptimizer()
+    opt.SetInput(src)
+    opt.Scan()
+    out = bytearray()
+    opt.SetOutput(out)
+    opt.Optimize(strip)
+    out = bytes(out)
+    assert len(out) < len(src)
+    pa, pb = J.Parsed(src), J.Parsed(out)
+    assert pb.desc.scans[0].restart_interval == pa.desc.scans[0].restart_interval != 0
+    a, b = O.decode(src, want_rgb=False), O.decode(out, want_rgb=False)   # the oracle checks every RSTn on its way
+    for ca, cb in zip(a.coef, b.coef):
+        assert np.array_equal(ca, cb)
+    sos = out.find(b"\xff\xda")
+    nint = -(-(a.mcus_per_line * a.mcus_per_col) // pa.desc.scans[0].restart_interval)
+    rst = [out[i + 1] for i in range(sos, len(out) - 1) if out[i] == 0xFF and 0xD0 <= out[i + 1] <= 0xD7]
+    assert rst == [0xD0 + (k & 7) for k in range(len(rst))] and len(rst) > 0
+    assert len(rst) == nint - 1
+    # the GPU decoder takes the result too (restart-segment path), and a second pass is a fixed point
+    lay, coef = J.decode_coefficients(out)
+    assert np.array_equal(coef, O.scan_order_coefficients(b).reshape(-1, 64))
+    opt2 = J.JpegOptimizer()
+    opt2.SetInput(out)
+    opt2.Scan()
+    out2 = bytearray()
+    opt2.SetOutput(out2)
+    opt2.Optimize(strip)
+    assert bytes(out2) == out
