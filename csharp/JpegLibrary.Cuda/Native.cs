@@ -61,7 +61,7 @@ namespace JpegLibrary.Cuda
             public void* Pixels; public ulong Pitch; public int OnDevice, Format;
             public ushort Width, Height; public byte ComponentCount;
             public fixed byte H[4]; public fixed byte V[4]; public fixed byte Tq[4]; public fixed byte Td[4]; public fixed byte Ta[4];
-            public fixed byte Reserved[3]; public fixed ushort Quant[4 * 64]; public fixed byte QuantPresent[4];
+            public byte Reserved; public ushort RestartInterval /* transcoding (JB_IN_COEFFICIENTS) only */; public fixed ushort Quant[4 * 64]; public fixed byte QuantPresent[4];
         }
         [DllImport(Lib)] public static extern int jb_encode_batch_create(IntPtr ctx, EncodeDesc* images, int count, out IntPtr batch);
         [DllImport(Lib)] public static extern int jb_encode_batch_transform(IntPtr batch);
