@@ -47,6 +47,28 @@ namespace JpegLibrary.Cuda
 
         public void Dispose() => Native.jb_ctx_destroy(_ctx);
 
+        /// <summary>The library context (one per GPU): shared with CudaJpegEncoder / CudaJpegOptimizer / PinnedMemoryPool.</summary>
+        public IntPtr Context => _ctx;
+
+        // Transcoding (CudaJpegOptimizer.Scan): the same marker walk, but the frame is only entropy-decoded -- zig-zag
+        // int16 blocks in scan order stay in device memory (JB_OUT_COEFFICIENTS) -- and the headers are handed out.
+        internal struct CoefficientResult
+        {
+            public IntPtr Coefficients; public ulong Blocks;
+            public byte Sof; public ushort Width, Height;
+            public byte[] H, V;                 // per frame component
+            public Native.ScanDesc Scan;        // the (only) scan of a sequential frame; EntropyOffset/Length locate its bytes
+            public Native.HuffSpec[] Tables;    // Scan.DcTable / AcTable index into this
+        }
+        private bool _coefficientsOnly;
+        private CoefficientResult _coefficientResult;
+        internal CoefficientResult DecodeCoefficients()
+        {
+            _coefficientsOnly = true;
+            try { Decode(); } finally { _coefficientsOnly = false; }
+            return _coefficientResult;
+        }
+
         // JpegDecoder.SetInput / SetOutputWriter are not virtual: keep our own references next to the base class's.
         public new void SetInput(ReadOnlyMemory<byte> input) { _input = input; base.SetInput(input); }
         public new void SetOutputWriter(JpegBlockOutputWriter outputWriter) { _writer = outputWriter; base.SetOutputWriter(outputWriter); }
@@ -205,6 +227,19 @@ namespace JpegLibrary.Cuda
             fixed (Native.HuffSpec* pt = tables)
             {
                 img.Data = (byte*)pin.Pointer; img.Scans = ps; img.Tables = pt;
+                if (_coefficientsOnly)
+                {
+                    int hmx = 1, vmx = 1, bpm = 0;
+                    byte[] hh = new byte[n], vv = new byte[n];
+                    for (int c = 0; c < n; c++) { hh[c] = img.H[c]; vv[c] = img.V[c]; hmx = Math.Max(hmx, hh[c]); vmx = Math.Max(vmx, vv[c]); bpm += hh[c] * vv[c]; }
+                    ulong blocks = (ulong)((img.Width + 8 * hmx - 1) / (8 * hmx)) * (ulong)((img.Height + 8 * vmx - 1) / (8 * vmx)) * (ulong)bpm;
+                    Native.Check(_ctx, Native.jb_device_alloc(_ctx, (UIntPtr)(blocks * 128), out IntPtr dev));
+                    var oc = new Native.OutputDesc { Dst = (void*)dev, Capacity = blocks * 128, Format = Native.JB_OUT_COEFFICIENTS, OnDevice = 1 };
+                    Native.Check(_ctx, Native.jb_decode(_ctx, &img, &oc, 1, null));               // K0 + K1 only
+                    _coefficientResult = new CoefficientResult { Coefficients = dev, Blocks = blocks, Sof = img.Sof, Width = img.Width, Height = img.Height,
+                                                                 H = hh, V = vv, Scan = scans[0], Tables = tables };
+                    return;
+                }
                 if (_writer is CudaRgbOutputWriter w)
                 {
                     var o = new Native.OutputDesc { Dst = (void*)w.Buffer, Pitch = (ulong)w.Pitch, Capacity = (ulong)w.Capacity, Format = w.Format, OnDevice = w.OnDevice ? 1 : 0 };
