@@ -384,6 +384,8 @@ def main():
 
     # ---------------------------------------------------------------- e2e leg (host buffers, public API)
     eb = min(args.e2e_batch, args.batch)
+    if world > 2:  # every rank pins its own RGB destination (24.9 MB per 4K image): keep the node's total bounded
+        eb = max(64, eb * 2 // world)
     if args.progressive:  # the progressive entropy kernels are serial-latency bound: only large chunks amortise them
         eb = min(max(eb, 512), args.batch)
         args.e2e_chunk = max(args.e2e_chunk, (eb + 1) // 2)

@@ -305,18 +305,23 @@ class JpegBatchDecoder:
     device arena and decoded by three kernel launches for the whole batch."""
 
     def __init__(self, blobs, format=N.JB_OUT_RGB24, context=None, device_output=True, parse_threads=8,
-                 host_outputs=None):
+                 host_outputs=None, parsed=None):
+        """parsed: marker-walk results (jbh_parse handles) of `blobs` when the caller has them already; ownership
+        passes to this object."""
         self.ctx = context or Context.default()
         n = len(blobs)
         self.count = n
         self._bufs = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for b in blobs]
-        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
-        lens = (C.c_uint64 * n)(*[b.size for b in self._bufs])
-        self._parsed = (C.c_void_p * n)()
-        failed = N.host.jbh_parse_batch(ptrs, lens, n, parse_threads, self._parsed)
-        if failed:
-            self._free_parsed()
-            raise InvalidDataException(f"{failed} of {n} streams failed the marker walk")
+        if parsed is not None:
+            self._parsed = parsed
+        else:
+            ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
+            lens = (C.c_uint64 * n)(*[b.size for b in self._bufs])
+            self._parsed = (C.c_void_p * n)()
+            failed = N.host.jbh_parse_batch(ptrs, lens, n, parse_threads, self._parsed)
+            if failed:
+                self._free_parsed()
+                raise InvalidDataException(f"{failed} of {n} streams failed the marker walk")
         self.descs = (N.ImageDesc * n)()
         N.host.jbh_collect_descs(self._parsed, n, self.descs)
         self.format = format
@@ -452,63 +457,79 @@ class JpegPipelinedBatchDecoder:
     def decode(self, blobs, host_out, format=N.JB_OUT_RGB24):
         """Decode `blobs` into the (pinned) uint8 array `host_out`; image i lands at self.offsets[i].
         Returns the per-image offsets."""
+        import queue
         import threading
         bpp = {N.JB_OUT_RGB24: 3, N.JB_OUT_RGBA32: 4, N.JB_OUT_YCBCR888: 3}[format]
         n = len(blobs)
         chunks = [(i, min(i + self.chunk, n)) for i in range(0, n, self.chunk)]
-        starts = [None] * len(chunks)
         errors = []
         lock = threading.Lock()
-        # output regions: every chunk needs its start offset before it runs -> sizes come from a first cheap pass
-        # over the frame headers (host only)
-        hdr = (N.ImageDesc * n)()
         bufs = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for b in blobs]
-        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
-        lens = (C.c_uint64 * n)(*[b.size for b in bufs])
-        handles = (C.c_void_p * n)()
-        failed = N.host.jbh_parse_batch(ptrs, lens, n, self.parse_threads, handles)
-        try:
-            if failed:
-                raise InvalidDataException(f"{failed} of {n} streams failed the marker walk")
-            N.host.jbh_collect_descs(handles, n, hdr)
+        offsets = [0] * n
+        ready = queue.Queue(maxsize=2 * len(self.contexts))  # parsed chunks, in order: (first, last, handles, start, end)
+
+        def parser():
+            # One marker walk per stream (host threads), running ahead of the GPU workers: a chunk's place in the
+            # output follows from the frame sizes of everything in front of it.
             off = 0
-            offsets = []
-            for i in range(n):
-                sz = hdr[i].width * hdr[i].height * bpp
-                offsets.append(off)
-                off += (sz + 255) // 256 * 256
-            if off > host_out.size:
-                raise ArgumentException("Destination buffer is too small.")
-        finally:
-            for i in range(n):
-                if handles[i]:
-                    N.host.jbh_free(handles[i])
-        for ci, (a, b) in enumerate(chunks):
-            starts[ci] = offsets[a]
-        self.offsets = offsets
-        ends = [offsets[b] if b < n else off for (_, b) in chunks]
+            try:
+                for a, b in chunks:
+                    m = b - a
+                    ptrs = (C.c_void_p * m)(*[x.ctypes.data for x in bufs[a:b]])
+                    lens = (C.c_uint64 * m)(*[x.size for x in bufs[a:b]])
+                    handles = (C.c_void_p * m)()
+                    failed = N.host.jbh_parse_batch(ptrs, lens, m, self.parse_threads, handles)
+                    if failed:
+                        for h in handles:
+                            if h:
+                                N.host.jbh_free(h)
+                        raise InvalidDataException(f"{failed} of {m} streams failed the marker walk")
+                    start = off
+                    for i in range(m):
+                        d = N.host.jbh_desc(handles[i]).contents
+                        offsets[a + i] = off
+                        off += (d.width * d.height * bpp + 255) // 256 * 256
+                    if off > host_out.size:
+                        for h in handles:
+                            N.host.jbh_free(h)
+                        raise ArgumentException("Destination buffer is too small.")
+                    ready.put((a, b, handles, start, off))
+                    if errors:
+                        break
+            except Exception as e:  # noqa: BLE001 - reported to the caller below
+                with lock:
+                    errors.append(e)
+            finally:
+                for _ in self.contexts:
+                    ready.put(None)
 
         def worker(w):
             ctx = self.contexts[w]
-            for ci in range(w, len(chunks), len(self.contexts)):
-                a, b = chunks[ci]
+            while True:
+                item = ready.get()
+                if item is None:
+                    return
+                a, b, handles, start, end = item
+                if errors:                      # drain: a chunk failed somewhere
+                    for h in handles:
+                        N.host.jbh_free(h)
+                    continue
                 try:
                     with JpegBatchDecoder(bufs[a:b], format, context=ctx, device_output=False,
-                                          host_outputs=host_out[starts[ci]:ends[ci]],
-                                          parse_threads=self.parse_threads) as d:
+                                          host_outputs=host_out[start:end], parsed=handles) as d:
                         d.run()
                 except Exception as e:  # noqa: BLE001 - reported to the caller below
                     with lock:
                         errors.append(e)
-                    return
 
-        threads = [threading.Thread(target=worker, args=(w,)) for w in range(len(self.contexts))]
+        threads = [threading.Thread(target=parser)] + [threading.Thread(target=worker, args=(w,)) for w in range(len(self.contexts))]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
         if errors:
             raise errors[0]
+        self.offsets = offsets
         return offsets
 
 
