@@ -222,16 +222,18 @@ bool build_device_table(const jb_huff_spec &s, JbHuffTable &d)
 void build_device_table32(const JbHuffTable &t, JbHuffTable32 &d)
 {
     memset(&d, 0, sizeof d);
-    auto conv = [&](uint16_t e) -> uint32_t {
+    auto conv = [&](uint16_t e, bool first_level) -> uint32_t {
         if ((e & 0xFF) == 0) return 0;
         const uint32_t v = jb_entry32(t.cls, e >> 8, e & 0xFF);
-        return v == JB_E32_BAD ? 0u : v; // resolved (and flagged) by the slow path
+        // an invalid symbol: flagged on the way through the escape path.  Second-level entries (codes of 11..16 bits) are
+        // re-resolved by the slow path; first-level ones carry a mark (the slow path only knows codes of 9 bits and more)
+        return v == JB_E32_BAD ? (first_level ? JB_E32_BADLUT : 0u) : v;
     };
     for (int p = 0; p < JB_LUT_SIZE; p++) {
         const uint16_t e = t.lut[p];
-        d.lut[p] = (e & 0xFF) ? conv(e) : (uint32_t)(e & 0xFF00); // escape: byte 1 = 1 + sub-table
+        d.lut[p] = (e & 0xFF) ? conv(e, true) : (uint32_t)(e & 0xFF00); // escape: byte 1 = 1 + sub-table
     }
-    for (int p = 0; p < JB_LUT2_SUBTABLES * 64; p++) d.lut2[p] = conv(t.lut2[p]);
+    for (int p = 0; p < JB_LUT2_SUBTABLES * 64; p++) d.lut2[p] = conv(t.lut2[p], false);
     memcpy(d.maxcode, t.maxcode, sizeof d.maxcode);
     memcpy(d.valoffset, t.valoffset, sizeof d.valoffset);
     memcpy(d.values, t.values, 256);
@@ -828,7 +830,9 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
     bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
     for (int i = 0; i < sc.component_count; i++) {
         const int c = sc.component_index[i];
-        if (c >= im.component_count || seen[c]) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+        if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+        if (seen[c]) // (the reference decodes the component twice, the second pass over the first)
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "lossless frames must consist of one interleaved scan (a component is named twice)");
         seen[c] = true;
         d.comp_h[c] = im.h[c]; d.comp_v[c] = im.v[c];
         d.comp_blk_off[c] = (uint8_t)bpm;
@@ -926,8 +930,9 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
     for (int i = 0; i < sc.component_count; i++) {
         int c = sc.component_index[i];
-        if (c >= im.component_count || seen[c])
-            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+        if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+        if (seen[c]) // (the reference decodes the component twice, the second pass over the first)
+            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "sequential frames must consist of one interleaved scan (a component is named twice)");
         seen[c] = true;
         d.comp_h[c] = im.h[c];
         d.comp_v[c] = im.v[c];
@@ -1417,7 +1422,7 @@ static int launch_kernels(jb_batch *b)
         dim3 grid((b->ll_max_nseg + lanes - 1) / lanes, nimg);
         jb_k1d_lossless_entropy<<<grid, 32, 0, st>>>(b->d_images, list, b->d_tables, b->d_arena, b->d_marks, b->d_scan, b->d_coef,
                                                     b->d_status, lanes);
-        jb_k1d_lossless_predict<<<nimg, 32 * JB_MAX_COMPONENTS_DEV, 0, st>>>(b->d_images, list, b->d_coef);
+        jb_k1d_lossless_predict<<<nimg, 32 * JB_MAX_COMPONENTS_DEV, 0, st>>>(b->d_images, list, b->d_marks, b->d_scan, b->d_coef);
         dim3 ogrid((b->ll_max_pixels + 255) / 256, nimg);
         jb_k5_lossless_output<<<ogrid, 256, 0, st>>>(b->d_images, list, b->d_coef);
         launches += 3;

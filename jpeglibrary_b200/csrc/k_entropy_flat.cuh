@@ -101,6 +101,9 @@ struct __align__(16) JbHuffTable32 {
 static_assert(sizeof(JbHuffTable32) % 16 == 0, "table size");
 
 #define JB_E32_BAD 0xFFFFFFFFu
+// first-level look-up entry of a code (<= 10 bits) whose symbol is invalid (DC magnitude category > 16): it must not go
+// to the slow path, which like the reference's LookupSlow starts at 9 bits and would take a short code for a long one
+#define JB_E32_BADLUT 0x0000FF00u
 
 // byte-permute selectors that left-align the kept bytes of a little-endian word in stream (big-endian) order:
 // index = 4-bit mask of kept bytes (bit i = memory byte i), unused result bytes select the zero operand
@@ -133,6 +136,7 @@ __device__ __noinline__ uint32_t jb_huff32_slow(const JbHuffTable32 *t, uint32_t
 
 __device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32_t e, uint32_t code16)
 {
+    if (e == JB_E32_BADLUT) return JB_E32_BAD;
     if (e != 0) {
         e = __ldg(&t->lut2[((e >> 8) - 1) * 64 + (code16 & 63)]);
         if (e != 0) return e;
@@ -351,8 +355,8 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
             if (toff != JB_K1F_NOTAB) e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
             if ((e & 0xFFu) == 0) {
                 uint32_t e2 = 0;
-                if (e != 0) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
-                if (e2 == 0) { // table not cached, or a code longer than 16 bits / not in the second level
+                if (e != 0 && e != JB_E32_BADLUT) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
+                if (e2 == 0) { // table not cached, a code longer than 16 bits / not in the second level, or a bad symbol
                     const uint4 gi = __ldg(&im->binfo[b]);
                     const uint32_t goff = is_dc ? gi.x : gi.y;
                     if (toff == JB_K1F_NOTAB) e = __ldg(tab_words + goff + (hi >> (32 - JB_LUT_BITS)));

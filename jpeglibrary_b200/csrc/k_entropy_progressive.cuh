@@ -88,13 +88,17 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
     uint32_t start = 0, stop, err = 0;
     if (active && seg > 0) {
         if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
-        else { err = JB_ST_EXPECT_RST; count = 0; } // (the reference stops at the previous interval's end)
+        else {
+            // no RSTn in front of this interval.  EOI at a restart boundary ends the scan quietly (HandleRestart
+            // :203-207): the intervals behind it are simply not there; any other marker is an error
+            if (sr.end_marker != 0xD9u) err = JB_ST_EXPECT_RST;
+            count = 0;
+        }
     }
-    const bool no_data = err != 0;
     stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
     start += rel;
     stop += rel;
-    if (no_data) start = stop;
+    if (active && count == 0) start = stop;
     const bool needs_marker = sc.dri != 0 && count == per_seg;
 
     // ---- producers.  `avail` = units of this scan whose history is final (every producer is past them)

@@ -259,6 +259,7 @@ __device__ __forceinline__ uint32_t jb_k1b_lookup(const uint32_t *s_tab, const u
     else e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
     if ((e & 0xFFu) == 0) {
         uint32_t e2 = 0;
+        if (e == JB_E32_BADLUT) return JB_E32_BAD;
         if (e != 0 && !(toff & JB_K1B_GLOBAL)) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
         if (e2 == 0) {
             // second-level miss or a table that is not cached: resolve against the table in global memory

@@ -39,7 +39,12 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *_
     uint32_t start = 0, err = 0;
     if (seg > 0) {
         if (seg - 1 < sr.nmarkers && (mk[seg - 1] & 8u) == 0) start = (mk[seg - 1] >> 4) + 2;
-        else { atomicOr(status + image, JB_ST_EXPECT_RST); return; }
+        else {
+            // no RSTn in front of this interval.  EOI at a restart boundary ends the scan quietly (:172-176): the
+            // intervals behind it are simply not there; any other marker is the previous interval's error
+            if (sr.end_marker != 0xD9u) atomicOr(status + image, JB_ST_EXPECT_RST);
+            return;
+        }
     }
     const uint32_t stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
     JbBitReader br;
@@ -96,9 +101,11 @@ __device__ __forceinline__ int jb_lossless_px(int predictor, int ra, int rb, int
 // l - 1, whose last two outputs arrive by shuffle (Rb, Rc); Ra is the lane's own previous output.
 __global__ void __launch_bounds__(32 * JB_MAX_COMPONENTS_DEV)
 jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                        const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
                         int16_t *__restrict__ store)
 {
-    const JbDevImage &im = images[image_list[blockIdx.x]];
+    const uint32_t image = image_list[blockIdx.x];
+    const JbDevImage &im = images[image];
     const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (c >= im.ncomp) return;
     const int h = im.comp_h[c], v = im.comp_v[c];
@@ -106,6 +113,10 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *_
     int16_t *plane = store + im.coef_off * 64 + (size_t)im.comp_plane_off[c] * 64;
     const int predictor = im.ll_predictor, initial = im.ll_initial;
     const uint32_t dri = im.dri, mpl = im.mcus_per_line;
+    // MCUs of intervals that are not in the stream (EOI at a restart boundary) keep the allocator's zeros
+    uint32_t nrst = scanres[image].nmarkers;
+    if (nrst && (marks[im.mark_base + nrst - 1] & 8u)) nrst--;
+    const uint32_t valid = dri ? min(im.total_mcus, (nrst + 1u) * dri) : im.total_mcus;
     for (int r0 = 0; r0 < rows; r0 += 32) {
         const int cy = r0 + lane;
         const bool rowok = cy < rows;
@@ -131,7 +142,7 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *_
                 } else {                         // :145-159
                     pred = jb_lossless_px(predictor, ra, rb, rc);
                 }
-                out = (int16_t)(line[cx] + pred);
+                out = (uint32_t)row * mpl + (uint32_t)col < valid ? (int16_t)(line[cx] + pred) : 0;
                 line[cx] = (int16_t)out;
                 ra = out;
             }

@@ -124,3 +124,58 @@ def test_corrupted_scans_decode_like_the_reference(name):
     print(f"{name}: {agree_ok} identical decodes, {agree_err} errors on both sides ({same_class} of the same "
           f"exception class), {len(problems)} disagreements")
     assert not problems, "\n".join(problems)
+
+
+def mutate_header(blob, rng, kind):
+    """damage somewhere between SOI and the first bytes of the first scan: marker codes, segment lengths, frame and
+    scan header fields, table definitions"""
+    b = bytearray(blob)
+    p = int(rng.integers(2, blob.find(b"\xff\xda") + 14))
+    if kind == 0:
+        b[p] ^= 1 << int(rng.integers(8))
+    elif kind == 1:
+        b[p] = int(rng.integers(256))
+    elif kind == 2:
+        del b[p:p + int(rng.integers(1, 4))]
+    else:
+        b[p:p] = bytes(rng.integers(0, 256, int(rng.integers(1, 4))).astype(np.uint8))
+    return bytes(b)
+
+
+@pytest.mark.parametrize("name", ["restart", "plain", "progressive", "lossless"])
+def test_corrupted_headers_decode_like_the_reference(name):
+    """The marker walk (JpegDecoder.cs:509-617, host side) and the device-side validation together must accept,
+    reject and decode damaged headers like the reference algorithm."""
+    blob = base_streams()[name]
+    rng = np.random.default_rng(7 + sum(map(ord, name)))
+    problems, agree_ok, agree_err, out_of_scope = [], 0, 0, 0
+    for trial in range(150):
+        bad = mutate_header(blob, rng, trial % 4)
+        want, werr = run_oracle(bad)
+        if werr is not None and "outside the oracle's scope" in str(werr):
+            continue  # arithmetic-coded frame types: the oracle stops where the reference would go on
+        try:
+            got, gerr = run_gpu(bad)
+        except (J.ArgumentException, MemoryError, ValueError) as e:  # absurd frame sizes: refused before any decode
+            got, gerr = None, e
+        if werr is None and isinstance(gerr, J.NotSupportedException) and "one interleaved scan" in str(gerr):
+            # documented scope limit (DESIGN section 1): a damaged scan header that leaves a sequential or lossless
+            # frame with a scan over only some of its components (or with no scan at all) is refused, where the
+            # reference decodes the components the scan names
+            out_of_scope += 1
+            continue
+        if werr is not None and gerr is not None:
+            agree_err += 1
+        elif werr is None and gerr is None:
+            if got.shape == want.planes.shape and np.array_equal(got, want.planes):
+                agree_ok += 1
+            else:
+                problems.append(f"trial {trial}: planes differ")
+        elif werr is not None:
+            problems.append(f"trial {trial}: oracle raised [{werr}] but the GPU decoded")
+        else:
+            problems.append(f"trial {trial}: GPU raised [{type(gerr).__name__}: {gerr}] but the oracle decoded")
+    print(f"{name}: {agree_ok} identical decodes, {agree_err} errors on both sides, {out_of_scope} refused as out of "
+          f"scope, {len(problems)} disagreements")
+    assert not problems, "\n".join(problems)
+    assert out_of_scope <= 20
