@@ -272,20 +272,21 @@ def _replay_write_blocks(d, planes, writer):
         writer.WriteBlock(blk, ci, x, y)
 
     if d.sof != 2:
-        sc = d.scans[0]
-        order = [sc.component_index[i] for i in range(sc.component_count)]
-        for my in range(mcus_y):
-            for mx in range(mcus_x):
-                for ci in order:
-                    h, v = d.h[ci], d.v[ci]
-                    hs, vs = hmax // h, vmax // v
-                    for by in range(v):
-                        for bx in range(h):
-                            x0 = (mx * hmax + bx) * 8  # :134; h is 1 or hmax on the GPU path
-                            y0 = (my * vmax + by) * 8
-                            for sv in range(vs):
-                                for sh in range(hs):
-                                    emit(ci, x0 + 8 * sh, y0 + 8 * sv)
+        for si in range(d.scan_count):   # (one scan normally; every scan is an MCU walk over its own components)
+            sc = d.scans[si]
+            order = [sc.component_index[i] for i in range(sc.component_count)]
+            for my in range(mcus_y):
+                for mx in range(mcus_x):
+                    for ci in order:
+                        h, v = d.h[ci], d.v[ci]
+                        hs, vs = hmax // h, vmax // v
+                        for by in range(v):
+                            for bx in range(h):
+                                x0 = (mx * hmax + bx) * 8  # :134; h is 1 or hmax on the GPU path
+                                y0 = (my * vmax + by) * 8
+                                for sv in range(vs):
+                                    for sh in range(hs):
+                                        emit(ci, x0 + 8 * sh, y0 + 8 * sv)
     else:
         wblk, hblk = (W + 7) // 8, (H + 7) // 8
         for ci in range(n):

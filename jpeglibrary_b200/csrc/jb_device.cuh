@@ -70,7 +70,8 @@ struct __align__(16) JbDevImage {
     uint32_t planar;                // 1: per-component planes of MCU-padded block grids
     uint32_t comp_plane_off[4];     // first block of each component plane (relative to coef_off)
     uint32_t comp_plane_w[4];       // blocks per row of each plane
-    uint32_t pad3;
+    uint32_t covered;               // scan-list frames: bit c = some scan names component c.  The reference's sequential
+                                    // decoder never calls WriteBlock for the others: their samples stay 0
     // lossless (SOF3): predictor selection Ss and 2^(P-Pt-1); planes reuse comp_plane_off (x64 samples) / comp_plane_w (samples per row)
     int32_t ll_predictor, ll_initial;
     // coefficient store
@@ -108,7 +109,9 @@ struct JbDevScan {
     uint8_t dep_all;     // bit i: dep[i] must be COMPLETE before this scan starts (its unit order differs from mine);
                          // otherwise unit u only needs the producer's units 0..u (same component(s), same order)
     uint8_t has_consumer; // a later scan reads what this one writes: publish progress
-    uint8_t pad;
+    uint8_t seq;         // scan of a SEQUENTIAL frame decoded through the scan list (several scans, or a scan that does
+                         // not name every component once): whole blocks, walked MCU by MCU with the component's own
+                         // h x v whatever the number of components (reference quirk Q2)
     uint16_t dep[JB_PROG_MAX_DEPS]; // scan indices inside the image; ndep == 0xFF: wait for every earlier scan
     uint16_t dc_tab[4], ac_tab[4]; // device table indices, 0xFFFF = not defined
 };

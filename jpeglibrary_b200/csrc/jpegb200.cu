@@ -260,6 +260,7 @@ struct ImagePlan {
 static int k2_variant(const JbDevImage &d, const std::vector<uint16_t> &quant)
 {
     if (d.precision != 8 || d.out_format > JB_OUT_YCBCR888) return -1;
+    if (d.planar && (d.covered & ((1u << d.ncomp) - 1u)) != (1u << d.ncomp) - 1u) return -1; // unwritten components
     // the fast kernel dequantises as fmul(float(q), float(c)): exact for |q * c| < 2^24, i.e. any int16 c with q <= 255
     for (int i = 0; i < d.ncomp * 64; i++)
         if (quant[d.quant_off + i] > 255) return -1;
@@ -635,9 +636,12 @@ static int intern_table(const jb_image_desc &im, int t, int want_class, std::vec
 }
 
 // SOF2: JpegHuffmanProgressiveScanDecoder ctor (:23-55) + per-scan set-up (:57-90, :140-147)
+// Also sequential frames that are not "one interleaved scan over every component" (sequential = true): the reference
+// walks each of their scans MCU by MCU with the component's own h x v (JpegHuffmanBaselineScanDecoder.cs:99-137, quirk
+// Q2) and decodes whole blocks; the scans go through the same scan list, planar store and renderer.
 static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl,
                             std::vector<JbHuffTable> &tables, std::map<std::string, int> &table_ids,
-                            std::vector<uint16_t> &quant)
+                            std::vector<uint16_t> &quant, bool sequential = false)
 {
     JbDevImage &d = pl.dev;
     if (im.precision < 2 || im.precision > 16) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
@@ -657,7 +661,9 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
                         "sampling factors must be 1 or the maximum, ratio 1/2/4 (reference quirk Q2)");
     }
-    d.width = im.width; d.height = im.height; d.ncomp = im.component_count; d.precision = im.precision; d.sof = 2;
+    d.width = im.width; d.height = im.height; d.ncomp = im.component_count; d.precision = im.precision;
+    d.sof = sequential ? im.sof : 2;
+    d.covered = sequential ? 0u : 0xFu; // (JpegBlockAllocator.Flush writes every block of a progressive frame)
     d.hmax = (uint8_t)hmax; d.vmax = (uint8_t)vmax;
     d.mcus_per_line = (im.width + 8 * hmax - 1) / (8 * hmax);
     d.mcus_per_col = (im.height + 8 * vmax - 1) / (8 * vmax);
@@ -706,10 +712,16 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
         JbDevScan ds{};
         ds.ncomp = sc.component_count;
         ds.ss = sc.ss; ds.se = sc.se; ds.ah = sc.ah; ds.al = sc.al;
+        if (sequential) { // whole blocks; the baseline reader never looks at Ss/Se/Ah/Al
+            ds.seq = 1; ds.ss = 0; ds.se = 63; ds.ah = ds.al = 0;
+            if (sc.component_count < 1 || sc.component_count > JB_MAX_COMPONENTS)
+                return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
+        } else {
         if (sc.component_count < 1 || sc.component_count > im.component_count || sc.se > 63 || sc.ss > sc.se || sc.al > 13)
             return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
         if (sc.component_count > 1 && sc.ss != 0)
             return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "interleaved progressive scans carry DC only");
+        }
         for (int i = 0; i < sc.component_count; i++) {
             int c = sc.component_index[i];
             if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
@@ -718,13 +730,14 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             int ac = intern_table(im, sc.ac_table[i], 1, tables, table_ids);
             if (dc == -2 || ac == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
             // :100-104, :149-152, :168-172: the table a scan actually uses must be defined
-            const bool need_dc = sc.ss == 0 && sc.ah == 0, need_ac = sc.ss != 0;
+            const bool need_dc = sequential || (sc.ss == 0 && sc.ah == 0), need_ac = sequential || sc.ss != 0;
+            d.covered |= 1u << c;
             if ((need_dc && dc < 0) || (need_ac && ac < 0))
                 return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
             ds.dc_tab[i] = dc < 0 ? 0xFFFF : (uint16_t)dc;
             ds.ac_tab[i] = ac < 0 ? 0xFFFF : (uint16_t)ac;
         }
-        if (sc.component_count == 1) {
+        if (sc.component_count == 1 && !sequential) {
             const int c = sc.component_index[0];
             const int hs = hmax / im.h[c], vs = vmax / im.v[c];
             ds.wb = (uint32_t)((im.width + 8 * hs - 1) / (8 * hs));
@@ -887,13 +900,20 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     if (im.sof == 3) return plan_lossless(ctx, idx, im, outp, pl, tables, table_ids);
     if (im.precision < 2 || im.precision > 16)
         return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
-    if (im.scan_count != 1 || !im.scans)
+    if (im.scan_count < 1 || !im.scans)
         return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
-                    "sequential frames must consist of one interleaved scan (reference quirk Q2)");
+                    "sequential frames must consist of one interleaved scan (this one has no scan at all)");
+    {
+        // the fast path takes ONE scan that names every component once; anything else goes through the scan list
+        bool plain = im.scan_count == 1 && im.scans[0].component_count == im.component_count;
+        bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
+        for (int i = 0; plain && i < im.scans[0].component_count; i++) {
+            const int c = im.scans[0].component_index[i];
+            if (c >= im.component_count || seen[c]) plain = false; else seen[c] = true;
+        }
+        if (!plain) return plan_progressive(ctx, idx, im, outp, pl, tables, table_ids, quant, true);
+    }
     const jb_scan_desc &sc = im.scans[0];
-    if (sc.component_count != im.component_count)
-        return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx,
-                    "sequential scan must contain every frame component (reference quirk Q2)");
 
     JbDevImage &d = pl.dev;
     int hmax = 1, vmax = 1;
@@ -1043,7 +1063,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         arena += align_up(pl.entropy_len + 64, 256);
         pl.dev.mark_base = (uint32_t)marks;
         marks += pl.dev.mark_cap;
-        if (pl.dev.sof != 2) { // sequential frames first; progressive stores follow as one slice
+        if (!pl.dev.planar) { // sequential frames first; scan-list (progressive) stores follow as one slice
             pl.dev.coef_off = blocks;
             blocks += pl.total_blocks;
         }
@@ -1054,7 +1074,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             staging += pl.out_bytes;
         } else
             pl.dev_out = pl.out.dst;
-        if (pl.dev.sof == 2) {
+        if (pl.dev.planar && pl.dev.sof != 3) {
             b->prog_images.push_back((uint32_t)i);
         } else if (pl.dev.sof == 3) {
             b->ll_images.push_back((uint32_t)i);
@@ -1112,7 +1132,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         ImagePlan &pl = b->plans[i];
         JbScanRange &r = b->h_ranges[i];
         r = JbScanRange{};
-        if (pl.dev.sof != 2) {
+        if (!(pl.dev.planar && pl.dev.sof != 3)) {
             r.data_off = pl.dev.data_off; r.data_len = pl.dev.data_len;
             r.mark_base = pl.dev.mark_base; r.mark_cap = pl.dev.mark_cap;
         }

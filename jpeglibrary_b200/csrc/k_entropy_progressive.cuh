@@ -174,6 +174,32 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         }
     };
 
+    // ---- one whole block of a sequential frame: ReadBlockBaseline (JpegHuffmanBaselineScanDecoder.cs:187-219)
+    auto seq_block = [&](int16_t *blk, int slot) {
+        uint4 *b4 = reinterpret_cast<uint4 *>(blk); // "outputBuffer = default" (:121): a later scan over the same
+#pragma unroll                                      // component replaces the block
+        for (int j = 0; j < 8; j++) b4[j] = make_uint4(0, 0, 0, 0);
+        int s = huff(sc.dc_tab[slot]);
+        if (s > 16) { err |= JB_ST_BAD_CODE; s = 0; }
+        int v = s != 0 ? jb_extend((int)jb_prog_bits(br, s), s) : 0;
+        const int p = slot == 0 ? pred[0] : slot == 1 ? pred[1] : slot == 2 ? pred[2] : pred[3];
+        v += p;
+        if (slot == 0) pred[0] = v; else if (slot == 1) pred[1] = v; else if (slot == 2) pred[2] = v; else pred[3] = v;
+        blk[0] = (int16_t)v;
+        for (int k = 1; k < 64 && !err;) {
+            const int sym = huff(sc.ac_tab[slot]);
+            const int r = sym >> 4, sz = sym & 15;
+            if (sz != 0) {
+                blk[min(k + r, 63)] = (int16_t)jb_extend((int)jb_prog_bits(br, sz), sz);
+                k += r + 1;
+            } else if (r == 0) {
+                break;      // end of block
+            } else {
+                k += 16;    // ZRL -- and, like the reference (:213-219), any other symbol with s == 0
+            }
+        }
+    };
+
     const int p1 = 1 << al, m1 = -(1 << al);
     if (coop) {
         // ---- AC refinement, one stream per warp, decoded by the WHOLE warp.  Every lane runs the same bit reader and
@@ -292,8 +318,8 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                 g16[se + 1] = (int16_t)(se + 1 < 32 ? c_lo : c_hi);
             publish(u + 1);
         }
-    } else if (sc.ncomp > 1) {
-        // ---- interleaved DC scan (:92-138).  Component geometry is hoisted (compile-time indexed, so it stays in
+    } else if (sc.ncomp > 1 || sc.seq) {
+        // ---- interleaved DC scan (:92-138), or any scan of a sequential frame (whole blocks, same MCU walk).  Component geometry is hoisted (compile-time indexed, so it stays in
         // registers) and the MCU position is stepped instead of divided out per MCU.
         int16_t *cbase[4];
         uint32_t cpitch[4];
@@ -312,13 +338,11 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (i >= sc.ncomp) break;
-                if (ch[i] == 1 && cv[i] == 1) {
-                    dc_block(cbase[i] + ((size_t)my * cpitch[i] + mx) * 64, i);
-                } else {
-                    for (int y = 0; y < cv[i]; y++)
-                        for (int x = 0; x < ch[i]; x++)
-                            dc_block(cbase[i] + ((size_t)(my * cv[i] + y) * cpitch[i] + mx * ch[i] + x) * 64, i);
-                }
+                for (int y = 0; y < cv[i]; y++)
+                    for (int x = 0; x < ch[i]; x++) {
+                        int16_t *blk = cbase[i] + ((size_t)(my * cv[i] + y) * cpitch[i] + mx * ch[i] + x) * 64;
+                        if (sc.seq) seq_block(blk, i); else dc_block(blk, i);
+                    }
             }
             if (++mx == mpl) { mx = 0; my++; }
             publish(u + 1);

@@ -157,6 +157,8 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
     if (j < nblk) {
         const int m = j / bpm, b = j - m * bpm;
         const int c = s_im.blk_comp[b];
+        // scan-list frames: a component no scan names is never written by the reference (its samples stay 0)
+        const bool unwritten = s_im.planar && !((s_im.covered >> c) & 1u);
         uint64_t blk;
         if (!s_im.planar) {
             blk = s_im.coef_off + ((uint64_t)tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0) * bpm + j;
@@ -208,7 +210,7 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
 #pragma unroll
         for (int mrow = 0; mrow < 8; mrow++) {
             const int v = __float2int_rn(__fmul_rn(d[mrow], 0.125f)) + shift;
-            pl[mrow * s_g.plane_pitch[c]] = (int16_t)v;
+            pl[mrow * s_g.plane_pitch[c]] = unwritten ? (int16_t)0 : (int16_t)v;
         }
     }
     __syncthreads();

@@ -817,6 +817,15 @@ static void render_planes(dec_ctx *c)
     int W = im->width, H = im->height;
     int shift = 1 << (im->precision - 1);
     for (int ci = 0; ci < im->ncomp; ci++) {
+        if (im->sof != 2) {
+            /* the sequential decoder hands a block to WriteBlock right after reading it (:119-134): a component
+               that no scan names is never written.  (Block-level: blocks behind an EOI at a restart boundary are
+               not written either; that is NOT modelled here -- every block of a named component is rendered.) */
+            int named = 0;
+            for (int s = 0; s < im->nscans; s++)
+                for (int k = 0; k < im->scans[s].ncomp; k++) named |= im->scans[s].comp_index[k] == ci;
+            if (!named) continue;
+        }
         int hs = im->hmax / im->comp_h[ci], vs = im->vmax / im->comp_v[ci];
         int16_t *plane = im->planes + (size_t)ci * W * H;
         int gw = im->sof == 2 ? im->alloc_w[ci] : im->coef_w[ci];
@@ -1131,7 +1140,7 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
     }
     if (!rc && (flags & (JO_WANT_PLANES | JO_WANT_RGB))) {
         size_t n = (size_t)img->width * img->height;
-        img->planes = malloc(n * img->ncomp * sizeof(int16_t));
+        img->planes = calloc(n * img->ncomp, sizeof(int16_t)); /* an application buffer starts out as zeros */
         if (!img->planes) rc = fail(c, JO_ERR_NOMEM, "out of memory");
         else {
             if (img->sof == 3) render_lossless_planes(c);

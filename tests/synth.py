@@ -210,3 +210,129 @@ def synth_lossless(i, width, height, precision=8, predictor=1, point_transform=0
     full = np.stack([np.repeat(np.repeat(p, vmax // v, axis=0), hmax // h, axis=1)
                      for p, (h, v) in zip(planes, sampling)]).astype(np.uint16).view(np.int16)
     return blob, full
+
+
+# --------------------------------------------------------------------------------------------------
+# Sequential frames with several scans (or scans over some of the components).  Pillow only writes one
+# interleaved scan, so an existing stream is re-sequenced: the quantised coefficients (from the oracle)
+# are entropy-coded again, scan by scan, with the stream's own Huffman tables, each scan in the order
+# the REFERENCE walks it -- MCU by MCU over the frame's MCU grid with the component's own h x v blocks,
+# whatever the number of components in the scan (JpegHuffmanBaselineScanDecoder.cs:99-137, quirk Q2;
+# the same as the standard's order only when every component is sampled 1x1).  Data generation only.
+# --------------------------------------------------------------------------------------------------
+def resequence_scans(blob, decoded, scans, restart=0):
+    """blob: a baseline JPEG with one interleaved scan; decoded: oracle_ffi.decode(blob); scans: list of lists
+    of frame component indices.  Returns the same frame coded as len(scans) scans."""
+    def segments(data):
+        i, out = 2, []
+        while data[i + 1] != 0xDA:
+            ln = int.from_bytes(data[i + 2:i + 4], "big")
+            out.append((data[i + 1], data[i + 4:i + 2 + ln]))
+            i += 2 + ln
+        ln = int.from_bytes(data[i + 2:i + 4], "big")
+        return out, data[i + 4:i + 2 + ln]
+
+    segs, sos = segments(blob)
+    codes = {}   # (class, id) -> {symbol: (code, length)}
+    comp_ids, sel = [], {}
+    for m, p in segs:
+        if m == 0xC4:
+            q = 0
+            while q < len(p):
+                tc, th = p[q] >> 4, p[q] & 15
+                bits = list(p[q + 1:q + 17])
+                vals = list(p[q + 17:q + 17 + sum(bits)])
+                q += 17 + sum(bits)
+                tab, code, k = {}, 0, 0
+                for ln in range(1, 17):
+                    for _ in range(bits[ln - 1]):
+                        tab[vals[k]] = (code, ln)
+                        code += 1
+                        k += 1
+                    code <<= 1
+                codes[(tc, th)] = tab
+        elif m in (0xC0, 0xC1):
+            n = p[5]
+            comp_ids = [p[6 + 3 * c] for c in range(n)]
+    for i in range(sos[0]):
+        sel[sos[1 + 2 * i]] = sos[2 + 2 * i]          # component id -> Td/Ta byte of the original scan
+    d = decoded
+    out = bytearray(b"\xff\xd8")
+    for m, p in segs:
+        if m != 0xDD:
+            out += bytes([0xFF, m]) + (len(p) + 2).to_bytes(2, "big") + p
+    if restart:
+        out += b"\xff\xdd\x00\x04" + restart.to_bytes(2, "big")
+
+    def size_of(v):
+        return abs(int(v)).bit_length()
+
+    for comps in scans:
+        out += b"\xff\xda" + (6 + 2 * len(comps)).to_bytes(2, "big") + bytes([len(comps)])
+        for c in comps:
+            out += bytes([comp_ids[c], sel[comp_ids[c]]])
+        out += bytes([0, 63, 0])
+        acc = nbits = 0
+        data = bytearray()
+
+        def put(value, length):
+            nonlocal acc, nbits
+            acc = (acc << length) | (value & ((1 << length) - 1))
+            nbits += length
+            while nbits >= 8:
+                b = (acc >> (nbits - 8)) & 0xFF
+                data.append(b)
+                if b == 0xFF:
+                    data.append(0)
+                nbits -= 8
+            acc &= (1 << nbits) - 1
+
+        def flush():
+            nonlocal acc, nbits
+            if nbits:
+                put((1 << (8 - nbits)) - 1, 8 - nbits)
+
+        pred = {c: 0 for c in comps}
+        before, rst = restart, 0
+        total = d.mcus_per_line * d.mcus_per_col
+        for mcu in range(total):
+            row, col = divmod(mcu, d.mcus_per_line)
+            for c in comps:
+                h, v = d.comp_h[c], d.comp_v[c]
+                dct, act = codes[(0, sel[comp_ids[c]] >> 4)], codes[(1, sel[comp_ids[c]] & 15)]
+                for y in range(v):
+                    for x in range(h):
+                        blk = d.coef[c][row * v + y, col * h + x]
+                        diff = int(blk[0]) - pred[c]
+                        pred[c] = int(blk[0])
+                        s = size_of(diff)
+                        put(*dct[s])
+                        if s:
+                            put(diff if diff >= 0 else diff - 1, s)
+                        run = 0
+                        for k in range(1, 64):
+                            t = int(blk[k])
+                            if t == 0:
+                                run += 1
+                                continue
+                            while run > 15:
+                                put(*act[0xF0])
+                                run -= 16
+                            s = size_of(t)
+                            put(*act[(run << 4) | s])
+                            put(t if t >= 0 else t - 1, s)
+                            run = 0
+                        if run:
+                            put(*act[0])
+            if restart:
+                before -= 1
+                if before == 0 and mcu != total - 1:
+                    flush()
+                    data += bytes([0xFF, 0xD0 + (rst & 7)])
+                    rst += 1
+                    before = restart
+                    pred = {c: 0 for c in comps}
+        flush()
+        out += data
+    out += b"\xff\xd9"
+    return bytes(out)

@@ -351,6 +351,36 @@ def test_progressive_batch_with_concurrent_dependent_scans():
                 assert np.array_equal(b.read_output(i), w), i
 
 
+# ------------------------------------------------------------------------------------------ sequential, several scans
+SCAN_SCRIPTS = [
+    dict(subsampling="4:4:4", scans=[[0], [1], [2]]),                      # the usual non-interleaved file
+    dict(subsampling="4:2:0", scans=[[0], [1], [2]]),                      # quirk Q2: luma walked MCU by MCU, 2x2 each
+    dict(subsampling="4:2:0", scans=[[0, 1], [2]], restart=5),
+    dict(subsampling="4:2:2", scans=[[2], [0], [1]], restart=3),
+    dict(subsampling="4:2:0", scans=[[0, 2, 2]]),                          # a component named twice, one never
+    dict(subsampling="4:4:4", scans=[[1]]),                                # two components never written
+    dict(subsampling="4:2:0", scans=[[0, 1, 2], [0]]),                     # a second pass over the luma blocks
+]
+
+
+@pytest.mark.parametrize("kw", SCAN_SCRIPTS, ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()).replace(" ", ""))
+def test_sequential_frames_with_several_scans(kw):
+    """SOF0 frames that are not one interleaved scan over every component go through the scan list (K1c): every
+    scan is an MCU walk with the component's own h x v blocks like the reference's baseline decoder does it
+    (JpegHuffmanBaselineScanDecoder.cs:99-137), components no scan names keep zero samples."""
+    src = synth.synth_jpeg(33, 200, 136, subsampling=kw["subsampling"], quality=88)
+    blob = synth.resequence_scans(src, O.decode(src, want_rgb=False), kw["scans"], kw.get("restart", 0))
+    o = check_progressive_coefficients(blob)      # planar store; the oracle walks the scans like the reference
+    o = O.decode(blob)
+    covered = sorted({c for sc in kw["scans"] for c in sc})
+    if covered == [0, 1, 2]:
+        assert np.array_equal(o.planes, O.decode(src, want_rgb=False).planes)   # the generator is sound
+    planes = gpu_planes(blob)
+    assert np.array_equal(planes, o.planes)
+    assert np.array_equal(gpu_pixels(blob, J.JB_OUT_YCBCR888), o.ycbcr)
+    assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
+
+
 # ------------------------------------------------------------------------------------------ lossless (SOF3)
 LOSSLESS_ASSETS = ["lossless%d_s22.jpg" % i for i in range(1, 8)]
 

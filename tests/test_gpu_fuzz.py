@@ -159,9 +159,9 @@ def test_corrupted_headers_decode_like_the_reference(name):
         except (J.ArgumentException, MemoryError, ValueError) as e:  # absurd frame sizes: refused before any decode
             got, gerr = None, e
         if werr is None and isinstance(gerr, J.NotSupportedException) and "one interleaved scan" in str(gerr):
-            # documented scope limit: a damaged scan header that leaves a sequential or lossless
-            # frame with a scan over only some of its components (or with no scan at all) is refused, where the
-            # reference decodes the components the scan names
+            # documented refusals: a lossless frame whose damaged scan header names only some of
+            # its components (the reference decodes those) and a sequential frame left without any scan (the
+            # reference returns without having written anything)
             out_of_scope += 1
             continue
         if werr is not None and gerr is not None:
