@@ -947,6 +947,9 @@ class JpegOptimizer:
         if d.scan_count < 1:
             raise InvalidDataException("No image data is read.")
         sc = d.scans[0]
+        named = [sc.component_index[i] for i in range(sc.component_count)]
+        if d.scan_count != 1 or sorted(named) != list(range(d.component_count)):
+            raise NotSupportedException("only frames coded as one interleaved scan over every component are transcoded on the GPU path")
         hmax = max(d.h[i] for i in range(d.component_count))
         vmax = max(d.v[i] for i in range(d.component_count))
         nblk = ((d.width + 8 * hmax - 1) // (8 * hmax)) * ((d.height + 8 * vmax - 1) // (8 * vmax)) * \

@@ -65,6 +65,10 @@ def test_optimizer_errors():
     opt.SetInput(golden_bytes("progress.jpg"))
     with pytest.raises(J.InvalidDataException):
         opt.Scan()                              # "Progressive JPEG is not supported currently."
+    src = synth.synth_jpeg(3, 64, 48, subsampling="4:4:4")
+    opt.SetInput(synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0], [1], [2]]))
+    with pytest.raises(J.NotSupportedException):
+        opt.Scan()                              # several scans: refused, not transcoded wrongly
 
 
 @pytest.mark.parametrize("kw", [dict(width=640, height=400, subsampling="4:2:0", restart_rows=1),
