@@ -803,7 +803,7 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
 {
     JbDevImage &d = pl.dev;
     if (im.precision < 2 || im.precision > 16) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
-    if (im.scan_count != 1 || !im.scans || im.scans[0].component_count != im.component_count)
+    if (im.scan_count != 1 || !im.scans || im.scans[0].component_count < 1 || im.scans[0].component_count > im.component_count)
         return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "lossless frames must consist of one interleaved scan");
     if (outp && outp->format == JB_OUT_COEFFICIENTS)
         return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "lossless frames have no DCT coefficients");
@@ -835,19 +835,21 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
             return fail(ctx, JB_ERR_INVALID_OPERATION, "image %d: %s", idx, "lossless MCU grid overhangs the component plane");
         d.comp_plane_off[c] = (uint32_t)blocks;
         d.comp_plane_w[c] = w;
+        d.comp_h[c] = im.h[c]; d.comp_v[c] = im.v[c];
         blocks += ((uint64_t)w * h + 63) / 64;
     }
     pl.total_blocks = blocks;
     int bpm = 0;
     std::map<int, int> slot_of_table;
     bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
+    d.covered = 0; // components the scan does not name keep the allocator's zeros
     for (int i = 0; i < sc.component_count; i++) {
         const int c = sc.component_index[i];
         if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
         if (seen[c]) // (the reference decodes the component twice, the second pass over the first)
             return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "lossless frames must consist of one interleaved scan (a component is named twice)");
         seen[c] = true;
-        d.comp_h[c] = im.h[c]; d.comp_v[c] = im.v[c];
+        d.covered |= 1u << c;
         d.comp_blk_off[c] = (uint8_t)bpm;
         const int gid = intern_table(im, sc.dc_table[i], 0, tables, table_ids);
         if (gid == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");

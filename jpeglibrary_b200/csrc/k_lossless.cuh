@@ -111,6 +111,11 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *_
     const int h = im.comp_h[c], v = im.comp_v[c];
     const int w = (int)im.comp_plane_w[c], rows = (int)im.mcus_per_col * v, cols = (int)im.mcus_per_line * h;
     int16_t *plane = store + im.coef_off * 64 + (size_t)im.comp_plane_off[c] * 64;
+    if (!((im.covered >> c) & 1u)) { // not in the scan: JpegPartialScanlineAllocator's zeros (the store is not cleared)
+        const int vs = im.vmax / v, hc = ((int)im.height + vs - 1) / vs;
+        for (int i = lane; i < w * hc; i += 32) plane[i] = 0;
+        return;
+    }
     const int predictor = im.ll_predictor, initial = im.ll_initial;
     const uint32_t dri = im.dri, mpl = im.mcus_per_line;
     // MCUs of intervals that are not in the stream (EOI at a restart boundary) keep the allocator's zeros

@@ -85,10 +85,12 @@ def _s16(v):
     return v - 0x10000 if v & 0x8000 else v
 
 
-def encode_lossless(planes, precision=8, predictor=1, point_transform=0, sampling=None, restart=0):
+def encode_lossless(planes, precision=8, predictor=1, point_transform=0, sampling=None, restart=0, scan_components=None):
     """planes: list of 2-D integer arrays at COMPONENT resolution (already divided by 2^Pt), component c of
-    size (mcus_y * v_c, mcus_x * h_c).  Returns a complete SOF3 stream with one interleaved scan."""
+    size (mcus_y * v_c, mcus_x * h_c).  Returns a complete SOF3 stream with one interleaved scan (over
+    `scan_components` when given: the other frame components are not coded)."""
     n = len(planes)
+    in_scan = list(range(n)) if scan_components is None else list(scan_components)
     sampling = sampling or [(1, 1)] * n
     hmax = max(h for h, _ in sampling)
     vmax = max(v for _, v in sampling)
@@ -132,7 +134,7 @@ def encode_lossless(planes, precision=8, predictor=1, point_transform=0, samplin
     before, rst = restart, 0
     for row in range(mcus_y):
         for col in range(mcus_x):
-            for c in range(n):
+            for c in in_scan:
                 h, v = sampling[c]
                 for y in range(v):
                     cy = row * v + y
@@ -182,15 +184,16 @@ def encode_lossless(planes, precision=8, predictor=1, point_transform=0, samplin
     s += seg(0xC4, bytes([0x00]) + bytes(bits) + bytes(vals))
     if restart:
         s += seg(0xDD, restart.to_bytes(2, "big"))
-    sos = bytes([n])
-    for c in range(n):
+    sos = bytes([len(in_scan)])
+    for c in in_scan:
         sos += bytes([c + 1, 0x00])
     s += seg(0xDA, sos + bytes([predictor, 0, point_transform]))
     s += out + b"\xff\xd9"
     return bytes(s)
 
 
-def synth_lossless(i, width, height, precision=8, predictor=1, point_transform=0, sampling=None, restart=0, ncomp=3):
+def synth_lossless(i, width, height, precision=8, predictor=1, point_transform=0, sampling=None, restart=0, ncomp=3,
+                   scan_components=None):
     """SOF3 stream of synthetic content; width/height are at full resolution and must be MCU multiples."""
     rng = np.random.default_rng(2000 + i)
     sampling = sampling or [(1, 1)] * ncomp
@@ -205,7 +208,9 @@ def synth_lossless(i, width, height, precision=8, predictor=1, point_transform=0
         if precision > 8:
             p = p + rng.integers(0, 1 << (precision - 8 - point_transform), size=p.shape)
         planes.append(np.ascontiguousarray(p))
-    blob = encode_lossless(planes, precision, predictor, point_transform, sampling, restart)
+    blob = encode_lossless(planes, precision, predictor, point_transform, sampling, restart, scan_components)
+    if scan_components is not None:   # components the scan does not name are never written: zeros
+        planes = [p if c in scan_components else np.zeros_like(p) for c, p in enumerate(planes)]
     # what a decoder must return: the coded samples as int16, replicated to full resolution
     full = np.stack([np.repeat(np.repeat(p, vmax // v, axis=0), hmax // h, axis=1)
                      for p, (h, v) in zip(planes, sampling)]).astype(np.uint16).view(np.int16)

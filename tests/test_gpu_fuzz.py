@@ -159,8 +159,7 @@ def test_corrupted_headers_decode_like_the_reference(name):
         except (J.ArgumentException, MemoryError, ValueError) as e:  # absurd frame sizes: refused before any decode
             got, gerr = None, e
         if werr is None and isinstance(gerr, J.NotSupportedException) and "one interleaved scan" in str(gerr):
-            # documented refusals: a lossless frame whose damaged scan header names only some of
-            # its components (the reference decodes those) and a sequential frame left without any scan (the
+            # documented refusal: a sequential or lossless frame left without any scan (the
             # reference returns without having written anything)
             out_of_scope += 1
             continue
