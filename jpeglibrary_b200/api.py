@@ -239,6 +239,10 @@ class JpegDecoder:
             self._parsed = Parsed(self._input)
         ctx = self._ctx or Context.default()
         d = self._parsed.desc
+        if d.scan_count == 0 and d.sof != 2:
+            # the marker loop met no SOS: the reference's sequential / lossless decoders are created at the frame header
+            # and never asked for anything, so no WriteBlock call happens and Decode returns (JpegDecoder.cs:509-550)
+            return
         if isinstance(self._writer, CudaOutputWriter):
             out = self._writer._output_desc()
             ctx.check(N.cuda.jb_decode(ctx.handle, C.byref(d), C.byref(out), 1, None))
