@@ -164,7 +164,8 @@ JB_API int jb_decode_batch_launch_count(jb_batch *b);
    in ms over all launches since profiling was switched on.  Returns the number of kernels. */
 JB_API int jb_decode_batch_set_profiling(jb_batch *b, int on);
 JB_API int jb_decode_batch_profile(jb_batch *b, char (*names)[48], float *ms, int cap);
-/* Progressive frames, profiling on: the schedule of the last launch's scan decoder warps, four words per job:
+/* Progressive frames, jb_decode_batch_set_profiling(b, 2): the schedule of the last launch's scan decoder warps (an
+   instrumented instance of the kernel runs instead of the production one), four words per job:
    (image << 32 | scan << 16 | first segment), start ns, end ns, ns spent waiting for producer scans.
    Returns the number of jobs written (all jobs when cap <= 0 and out == NULL is a size query). */
 JB_API int jb_decode_batch_scan_trace(jb_batch *b, uint64_t *out, int cap);

@@ -384,8 +384,9 @@ class JpegBatchDecoder:
     def launch_count(self):
         return N.cuda.jb_decode_batch_launch_count(self.handle)
 
-    def set_profiling(self, on):
-        self.ctx.check(N.cuda.jb_decode_batch_set_profiling(self.handle, 1 if on else 0))
+    def set_profiling(self, on, trace=False):
+        """on: time every kernel with events (profile()); trace: also record the K1c schedule (scan_trace())."""
+        self.ctx.check(N.cuda.jb_decode_batch_set_profiling(self.handle, (2 if trace else 1) if on else 0))
 
     def profile(self):
         names = ((C.c_char * 48) * 8)()
@@ -396,7 +397,8 @@ class JpegBatchDecoder:
         return [(names[i].value.decode(), ms[i]) for i in range(k)]
 
     def scan_trace(self):
-        """Progressive frames with profiling on: [(image, scan, segment, start_ns, end_ns, waited_ns)] per K1c job."""
+        """Progressive frames after set_profiling(True, trace=True): [(image, scan, segment, start_ns, end_ns, waited_ns)]
+        per K1c job."""
         n = N.cuda.jb_decode_batch_scan_trace(self.handle, None, 0)
         if n <= 0:
             return []

@@ -423,6 +423,7 @@ struct jb_batch {
     bool need_render = false;
     int launches = 0;
     bool profiling = false;
+    bool trace = false;                    // profiling level 2: K1c records its schedule (jb_decode_batch_scan_trace)
     std::vector<cudaEvent_t> events;       // profiling: one event per named mark
     std::vector<const char *> event_names; // name of the interval that ENDS at the event (nullptr: start of a launch)
 };
@@ -1430,10 +1431,15 @@ static int launch_kernels(jb_batch *b)
         JB_CUDA(ctx, jb_fill_async(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
         JB_CUDA(ctx, jb_fill_async(b->d_prog_progress, 0, sizeof(uint32_t) * (b->h_scans.size() + 1), st));
         const uint32_t njobs = (uint32_t)b->h_prog_jobs.size();
-        if (b->profiling && !b->d_prog_trace) JB_CUDA(ctx, jb_malloc_async(ctx, &b->d_prog_trace, sizeof(unsigned long long) * 4 * njobs));
-        jb_k1c_progressive_scans<<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables, b->d_arena,
-                                                       b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                       b->d_prog_progress + b->h_scans.size(), b->profiling ? b->d_prog_trace : nullptr);
+        if (b->trace && !b->d_prog_trace) JB_CUDA(ctx, jb_malloc_async(ctx, &b->d_prog_trace, sizeof(unsigned long long) * 4 * njobs));
+        if (b->trace)
+            jb_k1c_progressive_scans<true><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
+                                                                 b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
+                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace);
+        else
+            jb_k1c_progressive_scans<false><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
+                                                                  b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
+                                                                  b->d_prog_progress + b->h_scans.size(), nullptr);
         launches += 2;
         mark("jb_k1c_progressive_scans");
     }
@@ -1480,6 +1486,7 @@ int jb_decode_batch_set_profiling(jb_batch *b, int on)
     JB_CUDA(b->ctx, cudaStreamSynchronize(b->ctx->stream));
     clear_events(b);
     b->profiling = on != 0;
+    b->trace = on == 2;
     return JB_OK;
 }
 

@@ -33,7 +33,7 @@ __device__ __forceinline__ uint32_t jb_prog_bits(JbBitReader &br, int k)
 }
 
 #define JB_K1C_PUBLISH 32u        // a single-segment scan publishes its progress every so many units
-#define JB_K1C_SPIN_LIMIT (1u << 22) // x 1 us: a producer that does not move for seconds -> JB_ST_STALLED, never a hang
+#define JB_K1C_SPIN_LIMIT (1u << 19) // x 8 us: a producer that does not move for seconds -> JB_ST_STALLED, never a hang
 
 __device__ __forceinline__ uint32_t jb_ld_acquire(const uint32_t *p)
 {
@@ -46,7 +46,8 @@ __device__ __forceinline__ void jb_st_release(uint32_t *p, uint32_t v)
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(32, 32)
+template <bool TRACE> // TRACE: record the schedule (jb_decode_batch_scan_trace); a separate instance keeps its registers
+__global__ void __launch_bounds__(32, 32)   // out of the production kernel
 jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
                          const JbProgJob *__restrict__ jobs, const JbProgLane *__restrict__ entries, uint32_t njobs,
                          const JbHuffTable *__restrict__ tables,
@@ -60,7 +61,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
     turn = __shfl_sync(0xFFFFFFFFu, turn, 0);
     if (turn >= njobs) return;
     unsigned long long t_start = 0, t_wait = 0; // profiling only (jb_decode_batch_scan_trace)
-    if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    if (TRACE) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
     const JbProgJob job = jobs[turn];
     const bool coop = job.coop != 0;
     const bool active = coop || (uint32_t)lane < job.lanes;
@@ -106,7 +107,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
     auto wait_for = [&](uint32_t u) { // returns once unit u may be decoded
         if (u < avail) return;
         unsigned long long t0 = 0, t1 = 0;
-        if (trace) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        if (TRACE) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
         uint32_t a = 0xFFFFFFFFu;
         const int nd = sc.ndep == 0xFF ? (int)ent.scan : (int)sc.ndep;
         for (int i = 0; i < nd; i++) {
@@ -120,13 +121,15 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                 v = jb_ld_acquire(pp);
                 if (v >= total) { v = 0xFFFFFFFFu; break; }
                 if (!whole && v > u) break;
-                __nanosleep(spins < 32 ? 200 : 1000);
+                // back off quickly: a poll costs issue slots that the decoding warps of the SM need, and the producer
+                // only publishes every JB_K1C_PUBLISH units (tens of microseconds)
+                __nanosleep(spins < 4 ? 500 : spins < 16 ? 2000 : 8000);
                 if (++spins > JB_K1C_SPIN_LIMIT) { err |= JB_ST_STALLED; v = 0xFFFFFFFFu; break; }
             }
             a = min(a, v);
         }
         avail = a;
-        if (trace) {
+        if (TRACE) {
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
             t_wait += t1 - t0;
         }
@@ -295,12 +298,12 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                         } else {
                             k_end = se + 1;
                             n = nhist - hbase;
+                            beyond |= s != 0 && se < 63; // (the reference writes at se + 1 when the run overshoots the band)
                         }
                         correct(n);
-                        if (s != 0 && k_end < 64) { // (the reference writes at se + 1 when the run overshoots the band)
+                        if (s != 0 && k_end < 64) {
                             if (k_end < 32) { if (lane == k_end) c_lo = s; }
                             else if (lane == k_end - 32) c_hi = s;
-                            beyond |= k_end > se;
                         }
                         k = k_end + 1;
                     }
@@ -428,7 +431,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         }
         if (err) atomicOr(status + image, err);
     }
-    if (trace && lane == 0) {
+    if (TRACE && lane == 0) {
         unsigned long long t_end;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end));
         trace[4 * turn] = ((unsigned long long)image << 32) | (ent.scan << 16) | min(ent.seg, 0xFFFFu);

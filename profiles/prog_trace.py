@@ -9,7 +9,7 @@ distinct = [synth.encode_jpeg(synth.synth_rgb(i, 1920, 1080), quality=85, subsam
 blobs = [distinct[i % ndist] for i in range(batch)]
 with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
     b.run()
-    b.set_profiling(True)
+    b.set_profiling(True, trace=True)
     b.upload(); b.launch(); b.finish()
     print(b.profile())
     tr = b.scan_trace()
