@@ -10,14 +10,15 @@
 //
 //   U  jb_k1b_count/_copy  raw scan bytes -> "clean" stream (FF00 -> FF, fill bytes dropped, 1-padded), in 64 KB
 //                          chunks: kept bytes per chunk, then every chunk compacts to its prefix offset
-//   S0 jb_k1b_sync<0>      every thread decodes its 4096-bit sub-sequence from the guess
-//                          (p = start, b = 0, k = 0) and records its exit state
-//   Sr jb_k1b_sync<1>      every thread whose predecessor's exit state changed re-decodes from that
-//                          state (rounds until nothing changes; round 1 re-decodes everything)
+//   S0 jb_k1b_sync<0>      every thread decodes its sub-sequence (2^12..2^15 bits, chosen per batch) from the guess
+//                          (p = start, b = 0, k = 0) and records its exit state and 16 checkpoints on the way
+//   Sr jb_k1b_sync<1>      every thread whose predecessor's exit state changed re-decodes from that state and
+//                          stops at the first checkpoint it reproduces (the trajectories have merged there)
 //   P  jb_k1b_scan         per image exclusive prefix sums over sub-sequences: blocks started,
 //                          DC-difference sums per component  ->  first block index + DC predictors
-//   W  jb_k1b_write        final decode from the converged entry states, emitting DC-predicted
-//                          zig-zag blocks exactly like K1a (staging tile + 128-byte line flushes)
+//   D  jb_k1b_descs        one segment descriptor (JbSegDesc: entry bit, block-in-MCU, zig-zag index, DC predictors,
+//                          first block) per sub-sequence
+//   W  jb_k1_huff_flat<1>  the segment decoder of the restart path (k_entropy_flat.cuh) over those descriptors
 //
 // A block belongs to the sub-sequence in which its DC symbol starts; its owner finishes it even if it
 // runs past the sub-sequence end, and the next owner first skips the tail of that block.
