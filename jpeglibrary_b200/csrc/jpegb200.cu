@@ -392,7 +392,7 @@ struct jb_batch {
     JbDevScan *d_scans = nullptr;
     JbScanRange *d_ranges = nullptr;
     // self-synchronising path (images without restart markers)
-    std::vector<uint32_t> seg_images, ss_images; // K1a / K1b image lists
+    std::vector<uint32_t> seg_images, ss_images; // images on the restart-segment path (K0b + K1) / on the self-synchronising path (K1b chain)
     uint32_t ss_list_off = 0, seg_list_off = 0;
     // lossless frames (SOF3)
     std::vector<uint32_t> ll_images;
