@@ -428,20 +428,25 @@ struct jb_batch {
     std::vector<const char *> event_names; // name of the interval that ENDS at the event (nullptr: start of a launch)
 };
 
-// K1 over `nsegs` descriptors: CTA size chosen so that all of them are resident in one wave when the batch allows
-// it (one CTA per SM, up to 1024 lanes)
+// K1 over `nsegs` descriptors.  Large batches: 32 segments per warp and a CTA size such that all of them are resident
+// in one wave (one CTA per SM, up to 1024 lanes).  Small batches: fewer segments per warp, down to one, as long as
+// that still leaves about 16 warps per SM -- the latency of one restart interval is what a small batch waits for.
 template <bool CLEAN>
 static int launch_k1_flat(jb_batch *b, const JbSegDesc *segs, uint32_t nsegs, const uint8_t *stream)
 {
     jb_ctx *ctx = b->ctx;
     const uint32_t sms = (uint32_t)ctx->prop.multiProcessorCount;
-    uint32_t threads = ((nsegs + sms - 1) / sms + 31) / 32 * 32;
-    threads = std::min<uint32_t>(JB_K1F_MAX_THREADS, std::max<uint32_t>(128, threads));
+    uint32_t lanes = std::min<uint32_t>(32, std::max<uint32_t>(1, (nsegs + sms * 16 - 1) / (sms * 16)));
+    if (const char *e = getenv("JB_K1_LANES")) lanes = (uint32_t)std::min(32, std::max(1, atoi(e))); // tuning knob
+    const uint32_t warps = (nsegs + lanes - 1) / lanes;
+    uint32_t threads = ((warps + sms - 1) / sms) * 32;
+    threads = std::min<uint32_t>(JB_K1F_MAX_THREADS, std::max<uint32_t>(64, threads));
     const size_t smem = jb_k1f_smem_bytes((int)threads);
     JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1_huff_flat<CLEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)jb_k1f_smem_bytes(JB_K1F_MAX_THREADS)));
-    jb_k1_huff_flat<CLEAN><<<(nsegs + threads - 1) / threads, threads, smem, ctx->stream>>>(
-        b->d_images, segs, nsegs, b->d_tables32, reinterpret_cast<const uint32_t *>(stream), b->d_coef, b->d_status);
+    const uint32_t grid = (uint32_t)(((uint64_t)warps * 32 + threads - 1) / threads);
+    jb_k1_huff_flat<CLEAN><<<grid, threads, smem, ctx->stream>>>(
+        b->d_images, segs, nsegs, b->d_tables32, reinterpret_cast<const uint32_t *>(stream), b->d_coef, b->d_status, lanes);
     return JB_OK;
 }
 

@@ -172,7 +172,7 @@ template <bool CLEAN>
 __global__ void __launch_bounds__(JB_K1F_MAX_THREADS, 1)
 jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restrict__ segs, uint32_t nsegs,
                 const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ arena_words,
-                int16_t *__restrict__ coef, uint32_t *__restrict__ status)
+                int16_t *__restrict__ coef, uint32_t *__restrict__ status, uint32_t lanes_per_warp)
 {
     extern __shared__ __align__(16) uint8_t jb_k1f_smem[];
     __shared__ uint32_t s_tab_id[JB_K1F_TABLES];
@@ -183,12 +183,15 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     uint32_t *s_img = reinterpret_cast<uint32_t *>(s_slots + (size_t)nthreads * JB_K1F_SLOT);
     uint8_t *st = s_slots + tid * JB_K1F_SLOT;
     uint8_t *warp_slots = s_slots + (tid & ~31) * JB_K1F_SLOT;
-    const uint32_t g = blockIdx.x * nthreads + tid;
+    // Small batches spread their segments over more warps than they would fill (lanes_per_warp < 32): a warp steps
+    // at the pace of its slowest lane and pays every lane's refills and block hand-offs, so a lane decodes two to three
+    // times faster with a warp (nearly) to itself -- and a small batch has warps to spare.
+    const uint32_t g = ((blockIdx.x * nthreads + tid) >> 5) * lanes_per_warp + lane;
 #pragma unroll
     for (int i = 0; i < 9; i++) reinterpret_cast<uint4 *>(st)[i] = make_uint4(0, 0, 0, 0);
     JbSegDesc d;
     d.nblocks = 0; d.image = 0xFFFFFFFFu;
-    if (g < nsegs) d = segs[g];
+    if ((uint32_t)lane < lanes_per_warp && g < nsegs) d = segs[g];
     s_img[tid] = d.nblocks ? d.image : 0xFFFFFFFFu;
     __syncthreads();
     if (tid == 0) { // the CTA's table set: segments are numbered image-major, so images come in runs
