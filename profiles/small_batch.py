@@ -17,3 +17,24 @@ for name, kw in kinds.items():
             prof = b.profile()
         tot = sum(ms for _, ms in prof)
         print(f"{name:12s} batch {n:3d}: kernels {tot:7.2f} ms  ({8.2944 * n / tot:7.1f} GP/s)  " + ", ".join(f"{k.replace('jb_','')} {ms:.2f}" for k, ms in prof))
+
+# wall time of the single-image public API (JpegDecoder.Decode into pinned host RGB): marker walk + plan + H2D + kernels + D2H
+ctx = J.Context(0)
+for name, kw in kinds.items():
+    if name == "progressive":
+        continue
+    blob = synth.encode_jpeg(rgb[0], **kw)
+    pinned_in = ctx.pinned_array(len(blob)); pinned_in[:] = np.frombuffer(blob, np.uint8)
+    out = ctx.pinned_array(2160 * 3840 * 3).reshape(2160, 3840, 3)
+    def once():
+        dec = J.JpegDecoder(ctx)
+        dec.SetInput(pinned_in)
+        dec.SetOutputWriter(J.CudaOutputWriter(out))
+        dec.Decode()
+    for _ in range(3):
+        once()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        once()
+    dt = (time.perf_counter() - t0) / 20
+    print(f"{name:12s} JpegDecoder.Decode() wall {dt * 1e3:6.2f} ms per 4K frame ({8.2944 / dt / 1e3:5.2f} GP/s)")
