@@ -351,6 +351,23 @@ def test_progressive_batch_with_concurrent_dependent_scans():
                 assert np.array_equal(b.read_output(i), w), i
 
 
+def test_progressive_schedule_trace():
+    """jb_decode_batch_scan_trace: one record per K1c job; a consumer scan never ends before its producer."""
+    blobs = [synth.synth_jpeg(80 + i, 320, 240, progressive=True, subsampling="4:4:4") for i in range(3)]
+    with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
+        b.set_profiling(True, trace=True)
+        b.run()
+        trace = b.scan_trace()
+        assert np.array_equal(b.read_output(1), O.decode(blobs[1]).rgb)     # the instrumented kernel decodes the same
+    assert len(trace) == 3 * 10                                             # libjpeg's script: 10 scans, one segment each
+    for image, scan, seg, start, end, waited in trace:
+        assert 0 <= image < 3 and 0 <= scan < 10 and seg == 0 and end >= start and waited <= end - start
+    for image in range(3):
+        ends = {scan: end for im, scan, _, _, end, _ in trace if im == image}
+        assert ends[9] >= ends[5] >= max(ends[1], ends[4])                  # Y refine 2 follows Y refine 1 follows Y first scans
+        assert ends[6] >= ends[0] and ends[7] >= ends[2] and ends[8] >= ends[3]
+
+
 # ------------------------------------------------------------------------------------------ sequential, several scans
 SCAN_SCRIPTS = [
     dict(subsampling="4:4:4", scans=[[0], [1], [2]]),                      # the usual non-interleaved file
