@@ -235,6 +235,13 @@ JB_API void jb_encode_batch_destroy(jb_encode_batch *b);
 /* The table builder on the host (JpegHuffmanEncodingTableBuilder.Build(optimal: false), :62-176). */
 JB_API int jb_build_huffman_table(const uint32_t frequencies[256], int table_class, int identifier, jb_huff_spec *out);
 
+/* Host only (no device needed): how a frame that is decoded through the scan list (progressive, or sequential with
+   several scans) is planned.  Ten words per scan: its place in the job order, number of producer scans (255 = every
+   earlier scan), bit mask of producers that are waited for as a whole (the others are followed block by block), six
+   producer scan indices (-1 = unused), 1 if a later scan consumes it.  Returns the number of scans (0 for frames on
+   the single-scan fast paths) or JB_ERR_*. */
+JB_API int jb_plan_scans(const jb_image_desc *image, int32_t *out, int cap);
+
 JB_API const char *jb_version(void);
 
 #ifdef __cplusplus

@@ -114,6 +114,7 @@ _sigs = {
         "jb_decode_batch_set_profiling": (C.c_int, [_vp, C.c_int]),
         "jb_decode_batch_profile": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.c_int]),
         "jb_decode_batch_scan_trace": (C.c_int, [_vp, _vp, C.c_int]),
+        "jb_plan_scans": (C.c_int, [C.POINTER(ImageDesc), C.POINTER(C.c_int32), C.c_int]),
         "jb_decode_batch_destroy": (None, [_vp]),
         "jb_decode": (C.c_int, [_vp, C.POINTER(ImageDesc), C.POINTER(OutputDesc), C.c_int, C.POINTER(C.c_int32)]),
         "jb_encode_batch_create": (C.c_int, [_vp, C.POINTER(EncodeDesc), C.c_int, C.POINTER(_vp)]),

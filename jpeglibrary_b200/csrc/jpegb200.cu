@@ -450,12 +450,59 @@ static int launch_k1_flat(jb_batch *b, const JbSegDesc *segs, uint32_t nsegs, co
     return JB_OK;
 }
 
+// K1c job order inside one frame.  weight(scan) = its bytes + the heaviest consumer's weight, so a producer always
+// outweighs its consumers: ranking the scans by falling weight is a topological order that starts the longest
+// dependency chain first.
+static std::vector<uint32_t> rank_scans(const std::vector<JbDevScan> &scans)
+{
+    const size_t ns = scans.size();
+    std::vector<uint64_t> weight(ns, 0);
+    for (size_t k = ns; k-- > 0;) {
+        weight[k] += (uint64_t)scans[k].data_len + 1;
+        const JbDevScan &ds = scans[k];
+        if (ds.ndep == 0xFF) {
+            for (size_t q = 0; q < k; q++) weight[q] = std::max(weight[q], weight[k]);
+        } else
+            for (int q = 0; q < ds.ndep; q++) weight[ds.dep[q]] = std::max(weight[ds.dep[q]], weight[k]);
+    }
+    std::vector<uint32_t> order(ns);
+    for (size_t k = 0; k < ns; k++) order[k] = (uint32_t)k;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return weight[a] > weight[c]; });
+    return order;
+}
+
 static uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
 extern "C" {
 
 const char *jb_version(void) { return "jpegb200 0.1 (sm_100a)"; }
+
+static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl,
+                      std::vector<JbHuffTable> &tables, std::map<std::string, int> &table_ids,
+                      std::vector<uint16_t> &quant);
+
+int jb_plan_scans(const jb_image_desc *image, int32_t *out, int cap)
+{
+    if (!image || (!out && cap > 0)) return JB_ERR_ARGUMENT;
+    jb_ctx ctx; // host only: never touches the device
+    ImagePlan pl;
+    std::vector<JbHuffTable> tables;
+    std::map<std::string, int> table_ids;
+    std::vector<uint16_t> quant;
+    if (int rc = plan_image(&ctx, 0, *image, nullptr, pl, tables, table_ids, quant)) return rc;
+    const std::vector<uint32_t> order = rank_scans(pl.scans);
+    std::vector<int32_t> rank(order.size());
+    for (size_t r = 0; r < order.size(); r++) rank[order[r]] = (int32_t)r;
+    const int n = (int)pl.scans.size();
+    for (int k = 0; k < n && k < cap; k++) {
+        const JbDevScan &ds = pl.scans[k];
+        int32_t *o = out + (size_t)k * 10;
+        o[0] = rank[k]; o[1] = ds.ndep; o[2] = ds.dep_all; o[9] = ds.has_consumer;
+        for (int q = 0; q < JB_PROG_MAX_DEPS; q++) o[3 + q] = ds.ndep != 0xFF && q < ds.ndep ? (int32_t)ds.dep[q] : -1;
+    }
+    return n;
+}
 
 int jb_device_count(void)
 {
@@ -1172,22 +1219,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         // its consumers: ranking the scans of an image by falling weight is a topological order that starts the
         // longest dependency chain first.  The list takes rank 0 of every image, then rank 1, ...
         std::vector<std::vector<uint32_t>> order(b->prog_images.size());
-        for (size_t n = 0; n < b->prog_images.size(); n++) {
-            const ImagePlan &pl = b->plans[b->prog_images[n]];
-            const size_t ns = pl.scans.size();
-            std::vector<uint64_t> weight(ns, 0);
-            for (size_t k = ns; k-- > 0;) {
-                weight[k] += (uint64_t)pl.scans[k].data_len + 1;
-                const JbDevScan &ds = pl.scans[k];
-                if (ds.ndep == 0xFF) {
-                    for (size_t q = 0; q < k; q++) weight[q] = std::max(weight[q], weight[k]);
-                } else
-                    for (int q = 0; q < ds.ndep; q++) weight[ds.dep[q]] = std::max(weight[ds.dep[q]], weight[k]);
-            }
-            order[n].resize(ns);
-            for (size_t k = 0; k < ns; k++) order[n][k] = (uint32_t)k;
-            std::stable_sort(order[n].begin(), order[n].end(), [&](uint32_t a, uint32_t c) { return weight[a] > weight[c]; });
-        }
+        for (size_t n = 0; n < b->prog_images.size(); n++) order[n] = rank_scans(b->plans[b->prog_images[n]].scans);
         // Whole-warp jobs (AC refinement, one per segment) first within a rank; the other scans of the rank are packed
         // several lane entries to a warp.  Entries of one warp come from one rank, so they never wait for each other.
         // A stream decodes fastest with a warp to itself; packing trades that for warp slots: pack just enough that

@@ -67,3 +67,51 @@ def test_decode_call_order_errors():
         dec.Decode()  # "The output buffer is not specified."
     with pytest.raises(J.ArgumentException):
         dec.SetOutputWriter(None)
+
+
+# ----------------------------------------------------------------------------- scan-list planning (host only)
+def _plan(blob):
+    import ctypes as C
+    p = J.Parsed(blob)
+    n = p.desc.scan_count
+    out = (C.c_int32 * (10 * max(n, 1)))()
+    k = J._native.cuda.jb_plan_scans(C.byref(p.desc), out, n)
+    assert k >= 0, k
+    rows = [list(out[10 * i:10 * i + 10]) for i in range(k)]
+    return [dict(rank=r[0], ndep=r[1], whole=r[2], deps=[d for d in r[3:9] if d >= 0], consumed=bool(r[9])) for r in rows]
+
+
+def test_progressive_scan_dependencies_follow_component_and_band_overlap():
+    """libjpeg's script: 0 DC first (all), 1 Y 1-5, 2 Cr, 3 Cb, 4 Y 6-63, 5 Y refine, 6 DC refine, 7 Cr refine, 8 Cb refine,
+    9 Y refine.  Producers are transitively reduced and followed block by block (same component list, one segment)."""
+    import synth
+    plan = _plan(synth.synth_jpeg(3, 160, 112, progressive=True, subsampling="4:2:0"))
+    assert len(plan) == 10
+    assert [p["deps"] for p in plan] == [[], [], [], [], [], [4, 1], [0], [2], [3], [5]]
+    assert all(p["whole"] == 0 for p in plan)                                  # every producer has the consumer's unit order
+    assert [p["consumed"] for p in plan] == [True, True, True, True, True, True, False, False, False, False]
+    for k, p in enumerate(plan):                                               # job order: producers rank in front of consumers
+        assert all(plan[d]["rank"] < p["rank"] for d in p["deps"]), k
+    assert sorted(p["rank"] for p in plan) == list(range(10))
+    assert plan[9]["rank"] < plan[6]["rank"] and plan[5]["rank"] < plan[7]["rank"]   # the long luma chain starts first
+
+
+def test_progressive_scans_with_restart_intervals_are_waited_for_as_a_whole():
+    import synth
+    plan = _plan(synth.synth_jpeg(3, 160, 112, progressive=True, subsampling="4:4:4", restart_blocks=6))
+    assert plan[5]["deps"] == [4, 1] and plan[5]["whole"] == 0b11             # producers in several segments: no block-wise following
+    assert plan[9]["deps"] == [5] and plan[9]["whole"] == 1
+
+
+def test_sequential_scan_lists():
+    import oracle_ffi as O
+    import synth
+    src = synth.synth_jpeg(3, 96, 64, subsampling="4:2:0")
+    assert _plan(src) == []                                                    # the fast path: no scan list
+    d = O.decode(src, want_rgb=False)
+    plan = _plan(synth.resequence_scans(src, d, [[0], [1], [2]]))
+    assert [p["deps"] for p in plan] == [[], [], []]                           # different components: the scans commute
+    plan = _plan(synth.resequence_scans(src, d, [[0, 1, 2], [0]]))
+    assert plan[1]["deps"] == [0] and plan[1]["whole"] == 1                    # same blocks, another walk: wait for all of it
+    plan = _plan(synth.resequence_scans(src, d, [[0], [0]]))
+    assert plan[1]["deps"] == [0] and plan[1]["whole"] == 0                    # same walk: follow block by block
