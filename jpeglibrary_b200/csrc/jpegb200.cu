@@ -1438,6 +1438,12 @@ static int launch_kernels(jb_batch *b)
         dim3 ugrid((b->max_nseg + JB_K0B_THREADS - 1) / JB_K0B_THREADS, (unsigned)b->seg_images.size());
         jb_k0b_segment_descs<<<ugrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
                                                               b->d_segs, b->d_status);
+        if (b->max_nseg > 1) { // intervals the stream does not hold (EOI where an RSTn would be) keep zero blocks
+            dim3 cgrid((b->max_nseg + JB_K0B_THREADS / 32 - 1) / (JB_K0B_THREADS / 32), (unsigned)b->seg_images.size());
+            jb_k0c_clear_absent<<<cgrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
+                                                                 b->d_coef);
+            launches++;
+        }
         mark("jb_k0b_segment_descs");
         if (int rc = launch_k1_flat<false>(b, b->d_segs, b->total_segs, b->d_arena)) return rc;
         mark("jb_k1_huff_segments");

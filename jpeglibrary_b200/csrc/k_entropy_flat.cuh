@@ -81,7 +81,31 @@ jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__re
     d.endw = 0;
     d.pad[0] = d.pad[1] = 0;
     segs[im.seg_base + seg] = d;
-    if (!reachable) atomicOr(status + image, JB_ST_EXPECT_RST);
+    // An interval without RSTn in front of it is not decoded.  If the scan ended with EOI, that is how the reference
+    // ends too, quietly (JpegHuffmanBaselineScanDecoder.cs:144-150: the EOI sits where a restart marker would); any other
+    // marker there -- or none -- is "Expect restart marker.".  (If the EOI came in the middle of an interval, that
+    // interval's own decode reports the premature end.)
+    if (!reachable && sr.end_marker != 0xD9u) atomicOr(status + image, JB_ST_EXPECT_RST);
+}
+
+// K0c: intervals that are not in the stream (see above) leave their blocks as the allocator made them: zero.  The
+// coefficient store of sequential frames is not cleared per launch (K1 writes every block of every interval it
+// decodes), so the absent ones are cleared here; one warp per interval, which returns at once in the normal case.
+__global__ void __launch_bounds__(JB_K0B_THREADS)
+jb_k0c_clear_absent(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+                    const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres, int16_t *__restrict__ coef)
+{
+    const uint32_t image = image_list[blockIdx.y];
+    const JbDevImage &im = images[image];
+    const uint32_t seg = blockIdx.x * (JB_K0B_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (seg == 0 || seg >= im.nseg) return;
+    const JbScanResult sr = scanres[image];
+    if (seg - 1 < sr.nmarkers && (marks[im.mark_base + seg - 1] & 8u) == 0) return; // present
+    const uint32_t dri = im.dri ? im.dri : im.total_mcus;
+    const uint64_t first = im.coef_off + (uint64_t)seg * dri * im.bpm;
+    const uint64_t nblk = (uint64_t)min(dri, im.total_mcus - seg * dri) * im.bpm;
+    uint4 *p = reinterpret_cast<uint4 *>(coef + first * 64);
+    for (uint64_t i = lane; i < nblk * 8; i += 32) p[i] = make_uint4(0, 0, 0, 0);
 }
 
 // ---------------------------------------------------------------------------------------------

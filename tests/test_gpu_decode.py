@@ -186,10 +186,10 @@ def test_batch_of_mixed_images_device_resident():
     with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=True) as b:
         b.run()
         assert b.status() == [0] * len(blobs)
-        # restart scan + segment descriptors + segment Huffman + self-sync chain for lake.jpg (un-stuff count and
+        # restart scan + segment descriptors + absent-interval clear + segment Huffman + self-sync chain for lake.jpg (un-stuff count and
         # copy, guess round, 5 sync rounds, prefix sums, descriptors, write) + one IDCT/colour launch per layout
         # (+ the status clear at the start and the status mailbox post at the end)
-        assert b.launch_count() == 1 + 1 + 2 + (6 + 5) + 2 + 1
+        assert b.launch_count() == 1 + 1 + 3 + (6 + 5) + 2 + 1
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run
@@ -242,6 +242,27 @@ def test_error_codes_follow_reference_exceptions():
     dec.SetOutputWriter(J.CudaOutputWriter(np.zeros(100, np.uint8)))
     with pytest.raises(J.ArgumentException):
         dec.Decode()
+
+
+@pytest.mark.parametrize("kind", ["baseline", "lossless"])
+def test_eoi_at_a_restart_boundary_ends_the_scan_quietly(kind):
+    """A frame header that promises more MCU rows than the stream holds, with the EOI sitting exactly where the next
+    RSTn would be: the reference stops decoding without an error (JpegHuffmanBaselineScanDecoder.cs:144-150,
+    JpegHuffmanLosslessScanDecoder.cs:172-176).  (Progressive scans are followed by DHT/SOS, not EOI: there the same
+    situation is "Expect restart marker.", see test_progressive_complete_last_interval_quirk.)"""
+    if kind == "lossless":
+        blob = bytearray(synth.synth_lossless(6, 64, 40, predictor=2, restart=64)[0])   # one interval per row
+    else:
+        blob = bytearray(synth.synth_jpeg(6, 160, 112, subsampling="4:4:4", restart_rows=1))
+    sof = next(i for i in range(2, len(blob)) if blob[i] == 0xFF and blob[i + 1] in (0xC0, 0xC3))
+    height = int.from_bytes(blob[sof + 5:sof + 7], "big")
+    blob[sof + 5:sof + 7] = (height + 48).to_bytes(2, "big")
+    blob = bytes(blob)
+    o = O.decode(blob, want_rgb=False)          # no error
+    assert o.height == height + 48
+    planes = gpu_planes(blob)
+    assert np.array_equal(planes[:, :height], o.planes[:, :height])   # what was decoded is identical ...
+    assert np.array_equal(planes, o.planes)     # ... and so is the rest (lossless: zeros; sequential: see DESIGN, known deviation)
 
 
 # ------------------------------------------------------------------------------------------ progressive
