@@ -1068,6 +1068,7 @@ static int plan_image(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_ou
     if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
     d.data_len = (uint32_t)pl.entropy_len;
     d.use_selfsync = (d.dri == 0 && pl.entropy_len >= 1024) ? 1u : 0u;
+    if (getenv("JB_NO_SELFSYNC")) d.use_selfsync = 0; // debugging aid: the whole scan as one restart segment
     d.sub_cap = 0; // set once the batch's sub-sequence length is known
     pl.total_blocks = (uint64_t)d.total_mcus * bpm;
 
@@ -1453,8 +1454,8 @@ static int launch_kernels(jb_batch *b)
         const uint32_t *list = b->d_image_list + b->ss_list_off;
         const unsigned nimg = (unsigned)b->ss_images.size();
         dim3 ugrid(b->ss_max_chunks, nimg);
-        jb_k1b_count<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept);
-        jb_k1b_copy<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_chunk_kept, b->d_clean, b->d_clean_len);
+        jb_k1b_count<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_marks, b->d_chunk_kept);
+        jb_k1b_copy<<<ugrid, 256, 0, st>>>(b->d_images, list, b->d_arena, b->d_scan, b->d_marks, b->d_chunk_kept, b->d_clean, b->d_clean_len);
         JB_CUDA(ctx, jb_fill_async(b->d_changed, 0, sizeof(uint32_t) * 64, st));
         dim3 grid((b->ss_max_sub + JB_K1B_THREADS - 1) / JB_K1B_THREADS, nimg);
         jb_k1b_sync<0><<<grid, JB_K1B_THREADS, 0, st>>>(b->d_images, list, b->d_tables32, b->d_clean, b->d_clean_len, b->d_exits,

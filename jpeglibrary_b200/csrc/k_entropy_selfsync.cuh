@@ -59,6 +59,16 @@ struct __align__(16) JbSubCheck {
 // counts the kept bytes of every 64 KB chunk, pass 2 compacts each chunk to the sum of the counts in
 // front of it.  The clean stream is padded with 0xFF bytes (PeekBits pads with 1-bits, :166).
 // ---------------------------------------------------------------------------------------------
+// The stream ends at its FIRST marker of any kind: the bit reader stops feeding at FF xx whatever xx is
+// (JpegBitReader.cs:108-128), and a scan without restart interval never reads an RSTn -- one that turns up in a damaged
+// stream ends the data like EOI would.  K0 lists RSTn markers in front of the terminator, so the first entry is it.
+__device__ __forceinline__ uint32_t jb_k1b_stream_end(const JbDevImage &im, const JbScanResult &sr, const uint32_t *marks)
+{
+    uint32_t end = sr.end_pos;
+    if (sr.nmarkers) end = min(end, marks[im.mark_base] >> 4);
+    return min(end, im.data_len);
+}
+
 // byte-permute selectors that pack the kept bytes of a little-endian word at its low end, in memory order:
 // index = 4-bit mask of kept bytes (bit i = memory byte i), unused result bytes select the zero operand
 __constant__ uint16_t jb_c_keepsel_le[16] = {0x4444, 0x4440, 0x4441, 0x4410, 0x4442, 0x4420, 0x4421, 0x4210,
@@ -105,11 +115,12 @@ __device__ __forceinline__ void jb_k1b_keep64(const uint8_t *data, uint32_t pos0
 
 __global__ void __launch_bounds__(JB_K1B_UTHREADS)
 jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
-             const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres, uint32_t *__restrict__ chunk_kept)
+             const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres,
+             const uint32_t *__restrict__ marks, uint32_t *__restrict__ chunk_kept)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
-    const uint32_t end = min(scanres[image].end_pos, im.data_len);
+    const uint32_t end = jb_k1b_stream_end(im, scanres[image], marks);
     const uint32_t c0 = blockIdx.x * JB_K1B_CHUNK;
     if (c0 >= end && blockIdx.x > 0) return;
     const uint8_t *data = arena + im.data_off;
@@ -134,11 +145,12 @@ jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
 __global__ void __launch_bounds__(JB_K1B_UTHREADS)
 jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
             const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres,
-            const uint32_t *__restrict__ chunk_kept, uint8_t *__restrict__ clean, uint32_t *__restrict__ clean_len)
+            const uint32_t *__restrict__ marks, const uint32_t *__restrict__ chunk_kept, uint8_t *__restrict__ clean,
+            uint32_t *__restrict__ clean_len)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
-    const uint32_t end = min(scanres[image].end_pos, im.data_len);
+    const uint32_t end = jb_k1b_stream_end(im, scanres[image], marks);
     const uint32_t c0 = blockIdx.x * JB_K1B_CHUNK;
     if (c0 >= end && blockIdx.x > 0) return;
     const uint8_t *data = arena + im.data_off;

@@ -57,6 +57,14 @@ def mutate(blob, rng, kind):
     elif kind == "ones":        # a run of 0xFF fill bytes / 1-bits
         p = int(rng.integers(lo, hi))
         b[p:p + int(rng.integers(1, 4))] = b"\xff" * 3
+    elif kind == "rows":        # the frame header promises more or fewer lines than the scans hold
+        sof = next(i for i in range(2, len(b)) if b[i] == 0xFF and b[i + 1] in (0xC0, 0xC1, 0xC2, 0xC3))
+        h = int.from_bytes(b[sof + 5:sof + 7], "big")
+        b[sof + 5:sof + 7] = max(1, h + int(rng.integers(-40, 41))).to_bytes(2, "big")
+    elif kind == "cut":         # the scan stops at one of its restart markers, EOI follows
+        rst = [i for i in range(lo, hi - 1) if b[i] == 0xFF and 0xD0 <= b[i + 1] <= 0xD7]
+        p = rst[int(rng.integers(len(rst)))] if rst else int(rng.integers(lo, hi))
+        b[p:] = b"\xff\xd9"
     return bytes(b)
 
 
@@ -93,7 +101,7 @@ def base_streams():
     }
 
 
-KINDS = ["flip", "bytes", "drop", "dup", "ones"]
+KINDS = ["flip", "bytes", "drop", "dup", "ones", "rows", "cut"]
 
 
 @pytest.mark.parametrize("name", list(base_streams()))
@@ -101,7 +109,7 @@ def test_corrupted_scans_decode_like_the_reference(name):
     blob = base_streams()[name]
     rng = np.random.default_rng(sum(map(ord, name)))
     problems, agree_ok, agree_err, same_class = [], 0, 0, 0
-    for trial in range(100):
+    for trial in range(140):
         kind = KINDS[trial % len(KINDS)]
         bad = mutate(blob, rng, kind)
         want, werr = run_oracle(bad)
