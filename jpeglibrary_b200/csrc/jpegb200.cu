@@ -769,11 +769,14 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             ds.seq = 1; ds.ss = 0; ds.se = 63; ds.ah = ds.al = 0;
             if (sc.component_count < 1 || sc.component_count > JB_MAX_COMPONENTS)
                 return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
+        } else if (sc.component_count > 1) {
+            // DecodeProgressiveDataInterleaved (:92-138) reads DC blocks whatever Ss/Se say; Ah/Al are used as they are
+            if (sc.component_count > im.component_count)
+                return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
+            ds.ss = 0; ds.se = 0;
         } else {
-        if (sc.component_count < 1 || sc.component_count > im.component_count || sc.se > 63 || sc.ss > sc.se || sc.al > 13)
-            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
-        if (sc.component_count > 1 && sc.ss != 0)
-            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "interleaved progressive scans carry DC only");
+            if (sc.se > 63 || sc.ss > sc.se)
+                return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
         }
         for (int i = 0; i < sc.component_count; i++) {
             int c = sc.component_index[i];
@@ -783,7 +786,9 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             int ac = intern_table(im, sc.ac_table[i], 1, tables, table_ids);
             if (dc == -2 || ac == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
             // :100-104, :149-152, :168-172: the table a scan actually uses must be defined
-            const bool need_dc = sequential || (sc.ss == 0 && sc.ah == 0), need_ac = sequential || sc.ss != 0;
+            // :100-104 (every interleaved scan needs its DC tables, refinement or not), :149-152, :168-172
+            const bool need_dc = sequential || sc.component_count > 1 || (sc.ss == 0 && sc.ah == 0);
+            const bool need_ac = sequential || (sc.component_count == 1 && sc.ss != 0);
             d.covered |= 1u << c;
             if ((need_dc && dc < 0) || (need_ac && ac < 0))
                 return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
@@ -818,7 +823,12 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             bool share = false;
             for (int a = 0; a < ds.ncomp; a++)
                 for (int bq = 0; bq < pe.ncomp; bq++) share |= ds.comp[a] == pe.comp[bq];
-            if (!share || ds.se < pe.ss || pe.se < ds.ss) continue;
+            // the band a scan may WRITE is wider than Ss..Se when the stream is damaged: an AC first scan places a
+            // coefficient at min(i + r, 63) with i <= Se, r <= 15 (:283-290), a refinement scan just behind its band (:407)
+            auto top = [](const JbDevScan &x) -> int {
+                return x.ss == 0 || x.seq ? (int)x.se : std::min<int>(63, x.se + (x.ah == 0 ? 15 : 1));
+            };
+            if (!share || top(ds) < pe.ss || top(pe) < ds.ss) continue;
             level = std::max<int>(level, pe.level + 1);
             pe.has_consumer = 1;
             if (ds.ndep == 0xFF || follows[e] || after[e]) continue;
@@ -861,7 +871,6 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
     if (outp && outp->format == JB_OUT_COEFFICIENTS)
         return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "lossless frames have no DCT coefficients");
     const jb_scan_desc &sc = im.scans[0];
-    if (sc.al >= im.precision) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad point transform");
     int hmax = 1, vmax = 1;
     for (int c = 0; c < im.component_count; c++) {
         if (im.h[c] < 1 || im.h[c] > 4 || im.v[c] < 1 || im.v[c] > 4)
@@ -875,7 +884,9 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
     d.mcus_per_col = (im.height + vmax - 1) / vmax;
     d.total_mcus = d.mcus_per_line * d.mcus_per_col;
     d.ll_predictor = sc.ss;
-    d.ll_initial = 1 << (im.precision - sc.al - 1);
+    // 1 << (P - Pt - 1) as C# evaluates it (JpegHuffmanLosslessScanDecoder.cs:81): the shift count is taken modulo 32, so a
+    // damaged Pt >= P yields a value whose low 16 bits are 0 instead of an error
+    d.ll_initial = (int32_t)(1u << ((im.precision - sc.al - 1) & 31));
     uint64_t blocks = 0;
     for (int c = 0; c < im.component_count; c++) {
         if (hmax % im.h[c] || vmax % im.v[c])

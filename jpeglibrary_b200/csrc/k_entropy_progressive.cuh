@@ -386,6 +386,9 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                 by = u / wb; bx = u - by * wb;
                 blk = base + ((size_t)by * pitch + bx) * 64;
                 i = ss;
+                // the skipped blocks count as done by this scan only when its own producers are past them: a consumer
+                // that follows this scan relies on "block u done here => done in every scan this one follows"
+                wait_for(u - 1);
                 publish(u);
                 if (u < end) wait_for(u);
                 continue;

@@ -613,7 +613,8 @@ static int scan_lossless(dec_ctx *c, const jo_scan_info *s)
     const int restart = s->restart_interval;
     int before = restart;
     const int predictor = s->ss;
-    const int initial = 1 << (im->precision - s->al - 1);
+    /* C# takes the shift count modulo 32 (a damaged Pt >= P gives 1 << 31, 1 << 30, ... : low 16 bits 0) */
+    const int initial = (int)(1u << ((im->precision - s->al - 1) & 31));
     for (int row = 0; row < mpc; row++) {
         for (int col = 0; col < mpl; col++) {
             for (int k = 0; k < n; k++) {

@@ -372,6 +372,20 @@ def test_progressive_batch_with_concurrent_dependent_scans():
                 assert np.array_equal(b.read_output(i), w), i
 
 
+def test_progressive_large_batch_packed_scans_with_end_of_band_runs():
+    """More jobs than the GPU holds, the cheap scans packed 32 frames to a warp, low quality (long end-of-band runs: an
+    AC first scan that follows another one must not report skipped blocks as done before its producer is past them)."""
+    distinct = [synth.synth_jpeg(90 + i, 256, 192, progressive=True, subsampling="4:4:4", quality=35 + 10 * i) for i in range(4)]
+    want = [O.decode(b).rgb for b in distinct]
+    n = 2048
+    with J.JpegBatchDecoder([distinct[i % 4] for i in range(n)], J.JB_OUT_RGB24, device_output=True) as b:
+        for _ in range(3):
+            b.run()
+            assert b.status() == [0] * n
+        for i in list(range(0, n, 97)) + [n - 1]:
+            assert np.array_equal(b.read_output(i), want[i % 4]), i
+
+
 def test_progressive_schedule_trace():
     """jb_decode_batch_scan_trace: one record per K1c job; a consumer scan never ends before its producer."""
     blobs = [synth.synth_jpeg(80 + i, 320, 240, progressive=True, subsampling="4:4:4") for i in range(3)]
