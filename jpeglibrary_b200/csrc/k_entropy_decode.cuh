@@ -227,6 +227,13 @@ struct JbBitReader {
         lo <<= k;
         n -= k;
     }
+    // DecodeHuffmanCode advances min(code size, bits available) (JpegHuffmanScanDecoder.cs:85-86): a code whose tail lies
+    // in the 1-bit padding behind the data is accepted, only magnitude bits that are not there are an error
+    __device__ __forceinline__ void skip_code(int k)
+    {
+        skip(k);
+        n = max(n, pad);
+    }
     __device__ __forceinline__ uint32_t take(int k)
     { // k in 1..16
         uint32_t v = hi >> (32 - k);

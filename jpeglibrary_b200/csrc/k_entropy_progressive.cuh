@@ -157,7 +157,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)table_index * sizeof(JbHuffTable)),
                                     br.peek16());
         if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; }
-        br.skip(e & 0xFF);
+        br.skip_code(e & 0xFF);
         return (int)(e >> 8);
     };
     auto dc_block = [&](int16_t *blk, int slot) {
@@ -278,7 +278,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                             e = jb_huff_lookup(actab, br.peek16());
                             if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; }
                         }
-                        br.skip(e & 0xFFu);
+                        br.skip_code(e & 0xFFu);
                         const int r = (int)(e >> 12), sz = (int)(e >> 8) & 15;
                         int s = 0;
                         if (sz != 0) {
@@ -396,7 +396,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             br.ensure32(); // >= 33 bits: the code (<= 16) and up to 16 magnitude / run bits
             uint32_t e = jb_huff_lookup(actab, br.peek16());
             if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; }
-            br.skip(e & 0xFFu);
+            br.skip_code(e & 0xFFu);
             const int r = (int)(e >> 12), sz = (int)(e >> 8) & 15;
             if (sz != 0) {
                 i += r;

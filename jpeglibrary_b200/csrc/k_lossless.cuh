@@ -61,7 +61,7 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *_
             uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)im.table_index[im.blk_dc[b]] * sizeof(JbHuffTable)),
                                         br.peek16());
             if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; break; }
-            br.skip(e & 0xFF);
+            br.skip_code(e & 0xFF);
             const int t = (int)(e >> 8);
             int d = 0;
             if (t == 16) d = 32768;

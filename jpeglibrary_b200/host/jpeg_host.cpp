@@ -138,12 +138,17 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
             im.component_count = b[5];
             if (im.component_count < 1 || im.component_count > 4 || n < 6 + 3ull * im.component_count)
                 return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse frame header.");
+            // what no scan decoder can be built for is refused here, where the frame header is read (the device-side
+            // planning repeats these checks for descriptors that do not come from this walker)
+            if (im.width == 0 || im.height == 0 || im.precision < 2 || im.precision > 16)
+                return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse frame header.");
             for (int i = 0; i < im.component_count; i++) {
                 comp_id[i] = b[6 + 3 * i];
                 im.h[i] = b[7 + 3 * i] >> 4;
                 im.v[i] = b[7 + 3 * i] & 15;
                 comp_tq[i] = b[8 + 3 * i];
-                if (comp_tq[i] > 3) return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse frame header.");
+                if (comp_tq[i] > 3 || im.h[i] < 1 || im.h[i] > 4 || im.v[i] < 1 || im.v[i] > 4)
+                    return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse frame header.");
             }
             have_frame = true;
             break;
