@@ -910,8 +910,7 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
     for (int i = 0; i < sc.component_count; i++) {
         const int c = sc.component_index[i];
         if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
-        if (seen[c]) // (the reference decodes the component twice, the second pass over the first)
-            return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "lossless frames must consist of one interleaved scan (a component is named twice)");
+        // (a component named twice is decoded twice per MCU, the second pass over the first: the later differences win)
         seen[c] = true;
         d.covered |= 1u << c;
         d.comp_blk_off[c] = (uint8_t)bpm;
@@ -931,6 +930,7 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
             if (bpm >= JB_MAX_BLOCKS_PER_MCU) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "MCU too large");
             d.blk_comp[bpm] = (uint8_t)c;
             d.blk_dc[bpm] = (uint8_t)slot;
+            d.blk_ac[bpm] = (uint8_t)k; // lossless frames have no AC tables: the sample's place inside the MCU
             bpm++;
         }
     }

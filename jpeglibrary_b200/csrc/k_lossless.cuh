@@ -55,7 +55,7 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *_
         const uint32_t row = u / im.mcus_per_line, col = u - row * im.mcus_per_line;
         for (int b = 0; b < im.bpm; b++) { // blk_comp lists the scan's components, h*v samples each, in scan order
             const int c = im.blk_comp[b];
-            const int h = im.comp_h[c], bi = b - im.comp_blk_off[c];
+            const int h = im.comp_h[c], bi = im.blk_ac[b]; // sample index inside this occurrence of the component (host)
             const int x = bi % h, y = bi / h;
             br.ensure32();
             uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)im.table_index[im.blk_dc[b]] * sizeof(JbHuffTable)),

@@ -459,6 +459,7 @@ LOSSLESS_SHAPES = [
     dict(width=256, height=96, predictor=3, sampling=[(2, 1), (1, 1), (1, 1)], restart=64),
     dict(width=1, height=1, predictor=1, ncomp=1),
     dict(width=48, height=32, predictor=4, sampling=[(2, 2), (1, 1), (1, 1)], restart=4, scan_components=[0, 2]),  # partial scan
+    dict(width=48, height=32, predictor=5, sampling=[(2, 2), (1, 1), (1, 1)], scan_components=[0, 2, 2]),  # a component coded twice
 ]
 
 

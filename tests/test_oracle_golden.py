@@ -95,6 +95,7 @@ def test_oracle_errors():
     dict(width=48, height=32, predictor=7, sampling=[(2, 2), (1, 1), (1, 1)], restart=6),
     dict(width=30, height=20, predictor=5, precision=16),            # category 16 / (short) wrap-around
     dict(width=30, height=20, predictor=6, precision=12, point_transform=2),
+    dict(width=48, height=32, predictor=5, sampling=[(2, 2), (1, 1), (1, 1)], scan_components=[0, 2, 2]),
 ], ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
 def test_oracle_decodes_synthetic_lossless_streams(kw):
     """The test-only SOF3 generator (tests/synth.py) and the oracle (pinned by the 7 lossless goldens) agree:
