@@ -1,6 +1,6 @@
 """A longer run of the corrupted-stream parity tests (tests/test_gpu_fuzz.py) with other seeds: every disagreement
 between the GPU path and the oracle is printed and the stream is kept under gpurun_out/.
-usage (on a GPU box): python profiles/fuzz_campaign.py [trials per stream] [seed]"""
+usage (on a GPU box): python profiles/fuzz_campaign.py [trials per stream] [seed] [--more]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
@@ -10,7 +10,24 @@ trials = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
 os.makedirs("gpurun_out", exist_ok=True)
 total = bad = 0
-for name, blob in F.base_streams().items():
+import synth, oracle_ffi as O
+from conftest import golden_bytes
+bases = dict(F.base_streams())
+if "--more" in sys.argv:   # further frame types than the test suite mutates
+    rgb = synth.synth_rgb(50, 176, 120)
+    src = synth.encode_jpeg(rgb, quality=88, subsampling="4:2:0")
+    bases = {
+        "422_restart_optimized": synth.encode_jpeg(rgb, quality=90, subsampling="4:2:2", restart_blocks=5, optimize=True),
+        "gray_plain": synth.encode_jpeg(rgb, quality=80, gray=True),
+        "gray_progressive": synth.encode_jpeg(rgb, quality=80, gray=True, progressive=True),
+        "sequential_three_scans": synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0], [1], [2]], 4),
+        "sequential_two_scans": synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0, 1], [2]]),
+        "testorig12": golden_bytes("testorig12.jpg"),
+        "lossless_16bit_s22": synth.synth_lossless(51, 64, 48, precision=16, predictor=6, sampling=[(2, 2), (1, 1), (1, 1)], restart=8)[0],
+        "lossless_gray_5bit": synth.synth_lossless(52, 80, 40, precision=5, predictor=7, ncomp=1)[0],
+        "progressive_422": synth.encode_jpeg(rgb, quality=75, subsampling="4:2:2", progressive=True),
+    }
+for name, blob in bases.items():
     rng = np.random.default_rng(seed + sum(map(ord, name)))
     ok = err = 0
     for t in range(trials):
