@@ -394,8 +394,9 @@ def main():
 
     # two contexts (= two CUDA streams), chunks of 16 images: one chunk's marker walk + H2D + kernels overlap the
     # other chunk's D2H of RGB, which is what bounds a host-to-host decode
+    # (the marker walk of a 4K frame takes 0.2 ms on one core: a few threads per rank are plenty, and N ranks share the host)
     pipe = J.JpegPipelinedBatchDecoder([ctx, J.Context(local_rank)], chunk=args.e2e_chunk,
-                                       parse_threads=min(16, os.cpu_count() or 1))
+                                       parse_threads=max(2, min(16, (os.cpu_count() or 1) // max(1, world))))
 
     def e2e_step():
         pipe.decode(e2e_blobs, host_out, J.JB_OUT_RGB24)
