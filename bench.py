@@ -384,13 +384,20 @@ def main():
 
     # ---------------------------------------------------------------- e2e leg (host buffers, public API)
     eb = min(args.e2e_batch, args.batch)
-    if world > 2:  # every rank pins its own RGB destination (24.9 MB per 4K image): keep the node's total bounded
-        eb = max(64, eb * 2 // world)
     if args.progressive:  # the progressive entropy kernels are serial-latency bound: only large chunks amortise them
         eb = min(max(eb, 512), args.batch)
         args.e2e_chunk = max(args.e2e_chunk, (eb + 1) // 2)
+    # every rank pins its own RGB destination (24.9 MB per 4K image, 6.4 GB for 256): if the host refuses, halve it --
+    # but not up front: fewer chunks per step leave the two-stream pipeline mostly filling and draining
+    while True:
+        try:
+            host_out = ctx.pinned_array(eb * ((WIDTH * HEIGHT * 3 + 255) // 256 * 256))
+            break
+        except Exception:  # noqa: BLE001 - cudaHostAlloc failure surfaces as the package's exception types
+            if eb <= 32:
+                raise
+            eb //= 2
     e2e_blobs = batch_blobs[:eb]
-    host_out = ctx.pinned_array(eb * ((WIDTH * HEIGHT * 3 + 255) // 256 * 256))
 
     # two contexts (= two CUDA streams), chunks of 16 images: one chunk's marker walk + H2D + kernels overlap the
     # other chunk's D2H of RGB, which is what bounds a host-to-host decode
