@@ -51,6 +51,7 @@ namespace JpegLibrary.Cuda
         [DllImport(Lib)] public static extern int jb_decode_batch_launch(IntPtr batch);
         [DllImport(Lib)] public static extern int jb_decode_batch_finish(IntPtr batch);
         [DllImport(Lib)] public static extern int jb_ctx_synchronize(IntPtr ctx);
+        [DllImport(Lib)] public static extern int jb_ctx_trim(IntPtr ctx);
         [DllImport(Lib)] public static extern int jb_device_alloc(IntPtr ctx, UIntPtr bytes, out IntPtr p);
         [DllImport(Lib)] public static extern int jb_device_free(IntPtr ctx, IntPtr p);
 

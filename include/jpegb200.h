@@ -102,7 +102,7 @@ typedef struct jb_image_desc {
 typedef struct jb_output_desc {
     void *dst;          /* device pointer if on_device, else host pointer (pinned preferred) */
     uint64_t pitch;     /* bytes per pixel row (plane row for PLANAR_I16); 0 = tightly packed */
-    uint64_t capacity;  /* bytes available at dst */
+    uint64_t capacity;  /* bytes available at dst; mandatory (0 is refused): "Destination buffer is too small." */
     int32_t format;     /* JB_OUT_* */
     int32_t on_device;
 } jb_output_desc;
@@ -130,6 +130,9 @@ JB_API const char *jb_last_error(jb_ctx *ctx);
 /* cudaStream_t the context launches its kernels on (for CUDA-event timing by the caller). */
 JB_API void *jb_ctx_stream(jb_ctx *ctx);
 JB_API int jb_ctx_synchronize(jb_ctx *ctx);
+/* Returns the device memory the context's allocation pool has cached from destroyed batches to the driver
+   (batches allocate stream-ordered from a per-context pool that otherwise keeps everything for the next batch). */
+JB_API int jb_ctx_trim(jb_ctx *ctx);
 
 /* ---- memory ------------------------------------------------------------------- */
 JB_API int jb_pinned_alloc(jb_ctx *ctx, size_t bytes, void **out);

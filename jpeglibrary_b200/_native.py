@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBDIR = os.path.join(_HERE, "lib")
+_LIBDIR = os.environ.get("JB_LIBDIR") or os.path.join(_HERE, "lib")  # (JB_LIBDIR: A/B builds, see build.py)
 
 JB_OK = 0
 JB_ERR_INVALID_DATA = -1
@@ -97,6 +97,7 @@ _sigs = {
         "jb_last_error": (C.c_char_p, [_vp]),
         "jb_ctx_stream": (_vp, [_vp]),
         "jb_ctx_synchronize": (C.c_int, [_vp]),
+        "jb_ctx_trim": (C.c_int, [_vp]),
         "jb_pinned_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
         "jb_pinned_free": (C.c_int, [_vp, _vp]),
         "jb_device_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),

@@ -87,6 +87,10 @@ class Context:
     def synchronize(self):
         self.check(N.cuda.jb_ctx_synchronize(self.handle))
 
+    def trim(self):
+        """give the device memory cached from destroyed batches back to the driver"""
+        self.check(N.cuda.jb_ctx_trim(self.handle))
+
     def device_alloc(self, nbytes):
         p = C.c_void_p()
         self.check(N.cuda.jb_device_alloc(self.handle, nbytes, C.byref(p)))
@@ -157,6 +161,8 @@ class CudaOutputWriter(JpegBlockOutputWriter):
         self.format = format
         self.pitch = pitch
         self.on_device = on_device
+        if on_device and capacity <= 0:  # (a host array knows its size; a bare device pointer does not)
+            raise ArgumentException("capacity: the size of a device destination must be given")
         self.capacity = capacity if on_device else (buffer.nbytes if capacity == 0 else capacity)
 
     def _output_desc(self):
@@ -686,6 +692,20 @@ class JpegEncoder:
                 for x in range(0, W, 8):
                     r.ReadBlock(blk, ci, x, y)
                     buf[y:y + 8, x:x + 8, ci] = blk.reshape(8, 8).astype(np.uint8)
+        # MCU-padding blocks (JpegEncoder.cs:458-470 reads them into the allocator's dummy block): the GPU path
+        # computes them from zero samples, which is what JpegBufferInputReader.cs:36-39 returns outside the frame
+        hmax = max(c[4] for c in self._components)
+        vmax = max(c[5] for c in self._components)
+        for ci, (_, _, _, _, h, v) in enumerate(self._components):
+            if h != hmax or v != vmax:
+                continue
+            pads = [(x, 0) for x in range((W + 7) // 8 * 8, (W + 8 * hmax - 1) // (8 * hmax) * 8 * hmax, 8)]
+            pads += [(0, y) for y in range((H + 7) // 8 * 8, (H + 8 * vmax - 1) // (8 * vmax) * 8 * vmax, 8)]
+            for x, y in pads:
+                blk[:] = 0
+                r.ReadBlock(blk, ci, x, y)
+                if blk.any():
+                    raise NotSupportedException("input reader returns samples outside its own frame (MCU-padding blocks)")
         pix = np.ascontiguousarray(buf[:H, :W] if n == 3 else buf[:H, :W, 0])
         return CudaInputReader(pix, format=N.JB_IN_YCBCR888 if n == 3 else N.JB_IN_GRAY8)
 

@@ -8,7 +8,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB = os.path.join(HERE, "lib")
+# JB_LIBDIR / JB_BUILD_DEFINES: A/B builds of kernel variants for profiling (e.g. JB_BUILD_DEFINES="-DJB_K2_PACKED=0"
+# JB_LIBDIR=.../lib_scalar); the package loads JB_LIBDIR when it is set, the default build is what ships
+LIB = os.environ.get("JB_LIBDIR") or os.path.join(HERE, "lib")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("CXX", "g++")
 
@@ -21,7 +23,7 @@ HOST_DEPS = HOST_SRC + [os.path.join(HERE, "..", "include", f) for f in os.listd
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-diag-suppress", "550",
-]
+] + os.environ.get("JB_BUILD_DEFINES", "").split()
 
 
 def _stale(target, deps):

@@ -288,24 +288,24 @@ static uint32_t k2_fast_tiles(const JbDevImage &d)
 
 template <int FMT>
 static void launch_k2_fast_fmt(int shape, dim3 grid, cudaStream_t st, const JbDevImage *im, const int16_t *coef,
-                               const uint16_t *q, const uint32_t *list, int tpc)
+                               const uint16_t *q, const uint32_t *list, int tpc, const uint32_t *lim)
 {
     switch (shape) {
-    case 0: jb_k2_idct_color_warp<FMT, 1, 1, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
-    case 1: jb_k2_idct_color_warp<FMT, 3, 1, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
-    case 2: jb_k2_idct_color_warp<FMT, 3, 2, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
-    case 3: jb_k2_idct_color_warp<FMT, 3, 1, 2><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
-    default: jb_k2_idct_color_warp<FMT, 3, 2, 2><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc); break;
+    case 0: jb_k2_idct_color_warp<FMT, 1, 1, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc, lim, 0x8000000080000000ull); break;
+    case 1: jb_k2_idct_color_warp<FMT, 3, 1, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc, lim, 0x8000000080000000ull); break;
+    case 2: jb_k2_idct_color_warp<FMT, 3, 2, 1><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc, lim, 0x8000000080000000ull); break;
+    case 3: jb_k2_idct_color_warp<FMT, 3, 1, 2><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc, lim, 0x8000000080000000ull); break;
+    default: jb_k2_idct_color_warp<FMT, 3, 2, 2><<<grid, JB_K2W_WARPS * 32, 0, st>>>(im, coef, q, list, tpc, lim, 0x8000000080000000ull); break;
     }
 }
 
 static void launch_k2_fast(int variant, dim3 grid, cudaStream_t st, const JbDevImage *im, const int16_t *coef,
-                           const uint16_t *q, const uint32_t *list, int tpc)
+                           const uint16_t *q, const uint32_t *list, int tpc, const uint32_t *lim)
 {
     const int fmt = variant / 8, shape = variant % 8;
-    if (fmt == 0) launch_k2_fast_fmt<0>(shape, grid, st, im, coef, q, list, tpc);
-    else if (fmt == 1) launch_k2_fast_fmt<1>(shape, grid, st, im, coef, q, list, tpc);
-    else launch_k2_fast_fmt<2>(shape, grid, st, im, coef, q, list, tpc);
+    if (fmt == 0) launch_k2_fast_fmt<0>(shape, grid, st, im, coef, q, list, tpc, lim);
+    else if (fmt == 1) launch_k2_fast_fmt<1>(shape, grid, st, im, coef, q, list, tpc, lim);
+    else launch_k2_fast_fmt<2>(shape, grid, st, im, coef, q, list, tpc, lim);
 }
 
 // Device memory is cleared by a kernel, not by cudaMemsetAsync: memsets may be executed by a copy engine, where they
@@ -319,11 +319,24 @@ __global__ void jb_fill_u32(uint4 *__restrict__ p16, size_t n16, uint32_t *__res
     if (i < ntail) tail[i] = value;
 }
 
+// The arena comes from the pool uncleared and only the entropy-coded bytes of every image are uploaded; the bit readers
+// look a byte or a word past the end of a segment (is a trailing FF followed by 00, FF or a marker code?).  The spare
+// bytes behind every image are therefore cleared, so that a stream that stops without a marker decodes the same way
+// every time: one warp per image.
+__global__ void jb_clear_arena_tails(const JbDevImage *__restrict__ images, int count, uint8_t *__restrict__ arena)
+{
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= count) return;
+    const uint64_t from = images[i].data_off + images[i].data_len;
+    const uint64_t to = images[i].data_off + ((uint64_t)images[i].data_len + 64 + 255) / 256 * 256;
+    for (uint64_t p = from + lane; p < to; p += 32) arena[p] = 0;
+}
+
 __global__ void jb_post_status(uint32_t *__restrict__ mailbox, const uint32_t *__restrict__ status, int count,
-                               const uint32_t *__restrict__ changed_last)
+                               const uint32_t *__restrict__ changed_last, const uint32_t *__restrict__ limits)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) mailbox[i] = status[i];
+    if (i < count) { mailbox[i] = status[i]; mailbox[count + 1 + i] = limits[i]; }
     if (i == 0) mailbox[count] = changed_last ? *changed_last : 0u;
 }
 
@@ -364,12 +377,15 @@ struct jb_batch {
     int16_t *d_coef = nullptr;
     uint64_t coef_blocks = 0;
     uint32_t *d_status = nullptr;
+    uint32_t *d_limits = nullptr; // per image: MCUs that were decoded (0xFFFFFFFF: all); fewer when a sequential scan ends at
+                                  // an EOI on a restart boundary -- the reference never calls WriteBlock for the rest
+    bool may_truncate = false;    // some image has restart intervals and a host destination: its D2H copy waits for d_limits
     uint8_t *d_out_staging = nullptr;
     uint64_t out_staging_bytes = 0;
     std::vector<uint32_t> h_status;
     // Status words come back through a mapped pinned mailbox written by a kernel at the end of the launch: a small
     // cudaMemcpy D2H would queue on the copy engine behind another context's bulk pixel copies.
-    uint32_t *h_mailbox = nullptr; // [count] status words + [1] "changed in the last sync round"
+    uint32_t *h_mailbox = nullptr; // [count] status words + [1] "changed in the last sync round" + [count] MCU limits
     size_t mailbox_cap = 0;
     uint32_t max_nseg = 1; // most restart segments any image of the K0b/K1 path has
     // flat restart-segment path (K0b + K1)
@@ -579,6 +595,15 @@ int jb_ctx_synchronize(jb_ctx *ctx)
     return JB_OK;
 }
 
+int jb_ctx_trim(jb_ctx *ctx)
+{
+    if (!ctx) return JB_ERR_ARGUMENT;
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    JB_CUDA(ctx, cudaMemPoolTrimTo(ctx->pool, 0));
+    return JB_OK;
+}
+
 int jb_pinned_alloc(jb_ctx *ctx, size_t bytes, void **out)
 {
     if (!ctx || !out) return JB_ERR_ARGUMENT;
@@ -660,7 +685,7 @@ static int plan_output(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_o
             // apps/JpegDecode/DecodeAction.cs:30-34
             return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "This color space is not supported");
         if (!outp->dst) return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "null destination");
-        if (outp->capacity && outp->capacity < bytes)
+        if (outp->capacity < bytes) // (JpegBufferOutputWriter8Bit's constructor check; 0 = "unknown" is refused too)
             return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "Destination buffer is too small.");
         d.out_pitch = pitch;
         d.out_format = fmt;
@@ -816,7 +841,9 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
         // a nearer one are dropped (libjpeg's last luma refinement only watches the one before it).
         int level = 0;
         const size_t me = pl.scans.size();
-        if (me >= 0xFFFF) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "too many scans");
+        // (the dependency closure below is quadratic in the number of scans: a crafted file of 65k empty scans would cost
+        // 0.5 GB and 2e9 steps here; libjpeg's own scripts have 10 scans, its limit for user scripts is 64 per component)
+        if (me >= 1024) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "more than 1024 scans");
         std::vector<bool> follows(me, false), after(me, false);
         for (size_t e = me; e-- > 0;) {
             JbDevScan &pe = pl.scans[e];
@@ -1157,6 +1184,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         } else {
             b->max_nseg = std::max(b->max_nseg, pl.dev.nseg);
             b->seg_images.push_back((uint32_t)i);
+            if (pl.dev.nseg > 1 && !pl.out.on_device && pl.out.format != JB_OUT_COEFFICIENTS) b->may_truncate = true;
             pl.dev.seg_base = b->total_segs;
             b->total_segs += pl.dev.nseg;
         }
@@ -1272,7 +1300,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     b->coef_blocks = blocks;
     b->out_staging_bytes = staging;
     b->h_status.assign(count, 0);
-    b->h_mailbox = jb_mailbox_get(ctx, (size_t)count + 1, &b->mailbox_cap);
+    b->h_mailbox = jb_mailbox_get(ctx, 2 * (size_t)count + 1, &b->mailbox_cap);
     if (!b->h_mailbox) {
         ctx->error = "cudaHostAlloc of the status mailbox failed";
         delete b;
@@ -1325,6 +1353,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     }
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_limits, sizeof(uint32_t) * count));
     if (staging) JB_CUDA_B(jb_malloc_async(ctx, &b->d_out_staging, staging));
     std::vector<uint32_t> h_list;
     b->seg_list_off = 0;
@@ -1420,6 +1449,8 @@ int jb_decode_batch_upload(jb_batch *b)
         JB_CUDA(ctx, cudaMemcpyAsync(b->d_arena + pl.dev.data_off, b->host_data[i], pl.entropy_len,
                                      cudaMemcpyHostToDevice, ctx->stream));
     }
+    jb_clear_arena_tails<<<(b->count + 7) / 8, 256, 0, ctx->stream>>>(b->d_images, b->count, b->d_arena);
+    JB_CUDA(ctx, cudaGetLastError());
     return JB_OK;
 }
 
@@ -1440,7 +1471,8 @@ static int launch_kernels(jb_batch *b)
         }
     };
     JB_CUDA(ctx, jb_fill_async(b->d_status, 0, sizeof(uint32_t) * b->count, st));
-    launches++;
+    JB_CUDA(ctx, jb_fill_async(b->d_limits, 0xFFFFFFFFu, sizeof(uint32_t) * b->count, st));
+    launches += 2;
     mark(nullptr);
     jb_k0_restart_scan<<<(unsigned)b->h_ranges.size(), JB_K0_THREADS, 0, st>>>(b->d_ranges, b->d_arena, b->d_marks, b->d_scan);
     launches++;
@@ -1449,7 +1481,7 @@ static int launch_kernels(jb_batch *b)
         // descriptors of every restart segment of the batch, then one lane per segment
         dim3 ugrid((b->max_nseg + JB_K0B_THREADS - 1) / JB_K0B_THREADS, (unsigned)b->seg_images.size());
         jb_k0b_segment_descs<<<ugrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
-                                                              b->d_segs, b->d_status);
+                                                              b->d_segs, b->d_status, b->d_limits);
         if (b->max_nseg > 1) { // intervals the stream does not hold (EOI where an RSTn would be) keep zero blocks
             dim3 cgrid((b->max_nseg + JB_K0B_THREADS / 32 - 1) / (JB_K0B_THREADS / 32), (unsigned)b->seg_images.size());
             jb_k0c_clear_absent<<<cgrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
@@ -1514,7 +1546,7 @@ static int launch_kernels(jb_batch *b)
     launch_render(b, &launches);
     mark("jb_k2_idct_color");
     jb_post_status<<<(b->count + 255) / 256, 256, 0, st>>>(b->h_mailbox, b->d_status, b->count,
-                                                           b->ss_images.empty() ? nullptr : b->d_changed + JB_SS_ROUNDS);
+                                                           b->ss_images.empty() ? nullptr : b->d_changed + JB_SS_ROUNDS, b->d_limits);
     launches++;
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
@@ -1598,10 +1630,10 @@ static int launch_render(jb_batch *b, int *launches)
             int tpc = (int)std::min<uint64_t>(16, std::max<uint64_t>(1, total / (148 * 16 * 8)));
             const uint32_t per_cta = (uint32_t)tpc * JB_K2W_WARPS;
             dim3 grid((g.max_tiles + per_cta - 1) / per_cta, (unsigned)g.images.size());
-            launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc);
+            launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc, b->d_limits);
         } else {
             dim3 grid(g.max_tiles, (unsigned)g.images.size());
-            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list);
+            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list, b->d_limits);
         }
         (*launches)++;
     }
@@ -1655,6 +1687,12 @@ int jb_decode_batch_finish(jb_batch *b)
     if (!b) return JB_ERR_ARGUMENT;
     jb_ctx *ctx = b->ctx;
     JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // A sequential scan that ends at an EOI on a restart boundary leaves the MCUs behind it undecoded, and the
+    // reference never hands them to WriteBlock (JpegHuffmanBaselineScanDecoder.cs:144-150): the caller's pixels stay as
+    // they are.  Device destinations: K2 skips them.  Host destinations: only the decoded part of the staging area is
+    // copied back, which needs the per-image MCU limit first (one extra wait for the kernels, batches with restart
+    // intervals and host destinations only).
+    if (b->may_truncate) JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < b->count; i++) {
         const ImagePlan &pl = b->plans[i];
         const void *src = pl.dev_out;
@@ -1663,7 +1701,30 @@ int jb_decode_batch_finish(jb_batch *b)
             JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes,
                                          pl.out.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
         } else if (!pl.out.on_device) {
-            JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            const uint32_t limit = b->may_truncate ? b->h_mailbox[b->count + 1 + i] : 0xFFFFFFFFu;
+            const JbDevImage &d = pl.dev;
+            if (limit >= d.total_mcus) {
+                JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                continue;
+            }
+            // whole MCU rows, then the decoded MCUs of the row the scan ended in; per plane for planar output
+            const uint32_t bpp = pl.out.format == JB_OUT_PLANAR_I16 ? 2 : pl.out.format == JB_OUT_RGBA32 ? 4 : 3;
+            const uint32_t planes = pl.out.format == JB_OUT_PLANAR_I16 ? d.ncomp : 1;
+            const uint32_t rows_full = std::min<uint32_t>(d.height, limit / d.mcus_per_line * 8u * d.vmax);
+            const uint32_t rem_px = std::min<uint32_t>(d.width, limit % d.mcus_per_line * 8u * d.hmax);
+            const uint32_t rem_rows = std::min<uint32_t>(8u * d.vmax, d.height - rows_full);
+            for (uint32_t p = 0; p < planes; p++) {
+                const uint64_t off = (uint64_t)p * d.height * d.out_pitch;
+                uint8_t *dh = static_cast<uint8_t *>(pl.out.dst) + off;
+                const uint8_t *sd = static_cast<const uint8_t *>(src) + off;
+                if (rows_full)
+                    JB_CUDA(ctx, cudaMemcpy2DAsync(dh, d.out_pitch, sd, d.out_pitch, (size_t)d.width * bpp, rows_full,
+                                                   cudaMemcpyDeviceToHost, ctx->stream));
+                if (rem_px && rem_rows)
+                    JB_CUDA(ctx, cudaMemcpy2DAsync(dh + (uint64_t)rows_full * d.out_pitch, d.out_pitch,
+                                                   sd + (uint64_t)rows_full * d.out_pitch, d.out_pitch, (size_t)rem_px * bpp,
+                                                   rem_rows, cudaMemcpyDeviceToHost, ctx->stream));
+            }
         }
     }
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1672,7 +1733,7 @@ int jb_decode_batch_finish(jb_batch *b)
         // need more than JB_SS_ROUNDS hops to synchronise: rare) keep iterating and redo the output
         int rc = resync_and_rerun(b);
         if (rc) return rc;
-        jb_post_status<<<(b->count + 255) / 256, 256, 0, ctx->stream>>>(b->h_mailbox, b->d_status, b->count, nullptr);
+        jb_post_status<<<(b->count + 255) / 256, 256, 0, ctx->stream>>>(b->h_mailbox, b->d_status, b->count, nullptr, b->d_limits);
         JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     memcpy(b->h_status.data(), b->h_mailbox, sizeof(uint32_t) * b->count);
@@ -1741,6 +1802,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_scan) cudaFreeAsync(b->d_scan, b->ctx->stream);
     if (b->d_coef) cudaFreeAsync(b->d_coef, b->ctx->stream);
     if (b->d_status) cudaFreeAsync(b->d_status, b->ctx->stream);
+    if (b->d_limits) cudaFreeAsync(b->d_limits, b->ctx->stream);
     if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
     if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
     if (b->d_scans) cudaFreeAsync(b->d_scans, b->ctx->stream);
@@ -1788,28 +1850,38 @@ int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const i
     int rc = plan_image(ctx, 0, *image, output, pl, tables, ids, quant);
     if (rc) return rc;
     if (output->format == JB_OUT_COEFFICIENTS) return JB_ERR_ARGUMENT;
-    void *d_out = output->dst;
-    if (!output->on_device) JB_CUDA(ctx, cudaMalloc(&d_out, pl.out_bytes));
-    pl.dev.out_ptr = reinterpret_cast<uint64_t>(d_out);
-    pl.dev.coef_off = 0;
-    pl.dev.quant_off = 0;
+    // lossless frames have no coefficient blocks (their "MCU" is hmax x vmax samples): K2 would read far past the buffer
+    if (image->sof == 3 || pl.dev.sof == 3)
+        return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", 0, "lossless frames have no DCT coefficients to render");
+    void *d_out = nullptr;
     JbDevImage *d_im = nullptr;
     uint16_t *d_q = nullptr;
-    JB_CUDA(ctx, cudaMalloc(&d_im, sizeof(JbDevImage)));
-    JB_CUDA(ctx, cudaMalloc(&d_q, quant.size() * 2));
-    JB_CUDA(ctx, cudaMemcpyAsync(d_im, &pl.dev, sizeof(JbDevImage), cudaMemcpyHostToDevice, ctx->stream));
-    JB_CUDA(ctx, cudaMemcpyAsync(d_q, quant.data(), quant.size() * 2, cudaMemcpyHostToDevice, ctx->stream));
-    uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
-    uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
-    dim3 grid(strips * pl.dev.mcus_per_col, 1);
-    jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q, nullptr);
-    JB_CUDA(ctx, cudaGetLastError());
-    if (!output->on_device)
-        JB_CUDA(ctx, cudaMemcpyAsync(output->dst, d_out, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (!output->on_device) cudaFree(d_out);
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    if (!output->on_device) step(cudaMalloc(&d_out, pl.out_bytes));
+    pl.dev.out_ptr = reinterpret_cast<uint64_t>(output->on_device ? output->dst : d_out);
+    pl.dev.coef_off = 0;
+    pl.dev.quant_off = 0;
+    step(cudaMalloc(&d_im, sizeof(JbDevImage)));
+    step(cudaMalloc(&d_q, quant.size() * 2));
+    if (step(cudaMemcpyAsync(d_im, &pl.dev, sizeof(JbDevImage), cudaMemcpyHostToDevice, ctx->stream)) &&
+        step(cudaMemcpyAsync(d_q, quant.data(), quant.size() * 2, cudaMemcpyHostToDevice, ctx->stream))) {
+        uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
+        uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
+        dim3 grid(strips * pl.dev.mcus_per_col, 1);
+        jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q, nullptr, nullptr);
+        step(cudaGetLastError());
+        if (!output->on_device) step(cudaMemcpyAsync(output->dst, d_out, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    const cudaError_t es = cudaStreamSynchronize(ctx->stream); // (also on the error paths: nothing may still use the buffers)
+    step(es);
+    cudaFree(d_out);
     cudaFree(d_im);
     cudaFree(d_q);
+    if (e != cudaSuccess) {
+        ctx->error = std::string("jb_render_from_coefficients failed: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA;
+    }
     return JB_OK;
 }
 
@@ -1919,11 +1991,12 @@ int jb_encode_batch_create(jb_ctx *ctx, const jb_encode_desc *images, int count,
         if (e.component_count == 3 && (e.h[1] != 1 || e.v[1] != 1 || e.h[2] != 1 || e.v[2] != 1))
             return bad(JB_ERR_NOT_SUPPORTED, "chroma must be sampled 1x1");
         if (e.component_count == 1 && (hs != 1 || vs != 1)) return bad(JB_ERR_NOT_SUPPORTED, "grey frames must be sampled 1x1");
-        // reference quirk Q4: MCU-padding blocks alias the allocator's dummy block and are encoded with
-        // stale data; only frames whose block grid needs no such padding are handled
-        const int wblk = (e.width + 7) / 8, hblk = (e.height + 7) / 8;
-        if (wblk % hs != 0 || hblk % vs != 0)
-            return bad(JB_ERR_NOT_SUPPORTED, "frame needs MCU padding blocks, which the reference encodes from a stale dummy block (quirk Q4)");
+        // MCU-padding blocks (luma block columns / rows beyond ceil(W/8) x ceil(H/8); chroma is sampled 1x1 here and is
+        // never padded): the reference aliases them all to the allocator's dummy block (JpegBlockAllocator.cs:108-111),
+        // TransformBlocks writes it from the reader's zero fill (JpegEncoder.cs:458-470, JpegBufferInputReader.cs:36-39)
+        // and statistics + scan write read it back (:551-597, :640-647).  Every one of them lies entirely outside the
+        // image, so the dummy always holds the same DC-only block -- which is what K3 computes for such a block from
+        // its zero-filled component planes.  The store keeps them in MCU order like any other block.
         }
         d.width = e.width; d.height = e.height; d.ncomp = e.component_count;
         d.hs = (uint8_t)hs; d.vs = (uint8_t)vs; d.in_format = (uint8_t)e.format;
@@ -2090,13 +2163,25 @@ int jb_encode_batch_set_table(jb_encode_batch *b, int image, const jb_huff_spec 
     return JB_OK;
 }
 
+// K4c + K4d over the reserved stream buffers
+static int launch_pack_streams(jb_encode_batch *b)
+{
+    jb_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    JB_CUDA(ctx, jb_fill_async(b->d_raw, 0, (b->raw_bytes + 3) / 4 * 4, st));
+    dim3 grid((b->max_blocks + 255) / 256, b->count);
+    jb_k4c_pack<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits, b->d_totals, b->d_raw, b->d_status);
+    jb_k4d_stuff<<<b->count, 256, 0, st>>>(b->d_images, b->d_totals, b->d_bits, b->d_raw, b->d_out, b->d_out_len, b->d_status);
+    JB_CUDA(ctx, cudaGetLastError());
+    return JB_OK;
+}
+
 int jb_encode_batch_pack(jb_encode_batch *b)
 {
     if (!b) return JB_ERR_ARGUMENT;
     jb_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
     JB_CUDA(ctx, cudaSetDevice(ctx->device));
-    JB_CUDA(ctx, jb_fill_async(b->d_raw, 0, (b->raw_bytes + 3) / 4 * 4, st));
     dim3 grid((b->max_blocks + 255) / 256, b->count);
     jb_k4a_block_bits<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits);
     if (b->max_intervals > 1) { // transcoding a scan with restart intervals
@@ -2104,12 +2189,9 @@ int jb_encode_batch_pack(jb_encode_batch *b)
         jb_k4a_interval_gaps<<<igrid, 256, 0, st>>>(b->d_images, b->d_bits);
         b->launches++;
     }
-    jb_k4b_scan<<<b->count, 1024, 0, st>>>(b->d_images, b->d_bits, b->d_totals);
-    jb_k4c_pack<<<grid, 256, 0, st>>>(b->d_images, b->d_coef, b->d_tables, b->d_bits, b->d_totals, b->d_raw, b->d_status);
-    jb_k4d_stuff<<<b->count, 256, 0, st>>>(b->d_images, b->d_totals, b->d_bits, b->d_raw, b->d_out, b->d_out_len, b->d_status);
-    b->launches += 4;
-    JB_CUDA(ctx, cudaGetLastError());
-    return JB_OK;
+    jb_k4b_scan<<<b->count, 1024, 0, st>>>(b->d_images, b->d_bits, b->d_totals, b->d_status);
+    b->launches += 5; // K4a, K4b, clear, K4c, K4d
+    return launch_pack_streams(b);
 }
 
 int jb_encode_batch_finish(jb_encode_batch *b)
@@ -2117,15 +2199,49 @@ int jb_encode_batch_finish(jb_encode_batch *b)
     if (!b) return JB_ERR_ARGUMENT;
     jb_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
-    JB_CUDA(ctx, cudaMemcpyAsync(b->h_out_len.data(), b->d_out_len, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost, st));
-    JB_CUDA(ctx, cudaMemcpyAsync(b->h_status.data(), b->d_status, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost, st));
+    JB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int attempt = 0;; attempt++) {
+        JB_CUDA(ctx, cudaMemcpyAsync(b->h_out_len.data(), b->d_out_len, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost, st));
+        JB_CUDA(ctx, cudaMemcpyAsync(b->h_status.data(), b->d_status, sizeof(uint32_t) * b->count, cudaMemcpyDeviceToHost, st));
+        JB_CUDA(ctx, cudaStreamSynchronize(st));
+        bool overflow = false;
+        for (int i = 0; i < b->count; i++) {
+            if (b->h_status[i] & 16u) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", i, "entropy-coded data of 512 MiB or more");
+            overflow |= (b->h_status[i] & 8u) != 0;
+        }
+        if (!overflow) break;
+        if (attempt) return fail(ctx, JB_ERR_CUDA, "batch of %d: %s", b->count, "entropy-coded data still exceeds the reserved space");
+        // The space reserved at create time (768 bits per block on average) holds what optimised tables produce; caller-
+        // provided tables on noise-like content, or 12-bit coefficient transcodes, can need more.  The bit totals are
+        // known since K4b: reserve exactly that (stuffing at most doubles it) and pack again.
+        std::vector<unsigned long long> totals(b->count);
+        JB_CUDA(ctx, cudaMemcpyAsync(totals.data(), b->d_totals, sizeof(unsigned long long) * b->count, cudaMemcpyDeviceToHost, st));
+        JB_CUDA(ctx, cudaStreamSynchronize(st));
+        uint64_t raw = 0, outb = 0;
+        for (int i = 0; i < b->count; i++) {
+            JbEncImage &d = b->images[i];
+            d.raw_off = raw; d.raw_cap = align_up(totals[i] / 8 + 4096, 256);
+            raw += d.raw_cap;
+            d.out_off = outb; d.out_cap = align_up(2 * d.raw_cap + 256, 256);
+            outb += d.out_cap;
+        }
+        cudaFreeAsync(b->d_raw, st); b->d_raw = nullptr;
+        cudaFreeAsync(b->d_out, st); b->d_out = nullptr;
+        b->raw_bytes = raw; b->out_bytes = outb;
+        cudaError_t e = jb_malloc_async(ctx, &b->d_raw, raw + 4);
+        if (e == cudaSuccess) e = jb_malloc_async(ctx, &b->d_out, outb);
+        if (e != cudaSuccess) {
+            ctx->error = std::string("reserving the entropy-coded streams failed: ") + cudaGetErrorString(e);
+            return e == cudaErrorMemoryAllocation ? JB_ERR_NOMEM : JB_ERR_CUDA;
+        }
+        JB_CUDA(ctx, cudaMemcpyAsync(b->d_images, b->images.data(), sizeof(JbEncImage) * b->count, cudaMemcpyHostToDevice, st));
+        JB_CUDA(ctx, jb_fill_async(b->d_status, 0, sizeof(uint32_t) * b->count, st));
+        if (int rc = launch_pack_streams(b)) return rc;
+    }
     b->h_tables.resize((size_t)8 * b->count);
     JB_CUDA(ctx, cudaMemcpyAsync(b->h_tables.data(), b->d_tables, sizeof(JbEncTable) * 8 * b->count, cudaMemcpyDeviceToHost, st));
     JB_CUDA(ctx, cudaStreamSynchronize(st));
     b->tables_on_host_valid = true;
-    for (int i = 0; i < b->count; i++)
-        if (b->h_status[i]) return fail(ctx, JB_ERR_NOMEM, "image %d: %s", i, "entropy-coded data exceeds the reserved space");
-    // a symbol that occurs but has no code (host-provided table that does not cover the data)
     return JB_OK;
 }
 

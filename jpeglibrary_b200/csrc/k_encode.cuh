@@ -592,7 +592,8 @@ jb_k4a_block_bits(const JbEncImage *__restrict__ images, const int16_t *__restri
 
 // per-image exclusive scan of block_bits (in place -> bit offsets); total bits per image in totals[]
 __global__ void __launch_bounds__(1024)
-jb_k4b_scan(const JbEncImage *__restrict__ images, uint32_t *__restrict__ block_bits, unsigned long long *__restrict__ totals)
+jb_k4b_scan(const JbEncImage *__restrict__ images, uint32_t *__restrict__ block_bits, unsigned long long *__restrict__ totals,
+            uint32_t *__restrict__ status)
 {
     const JbEncImage &im = images[blockIdx.x];
     const uint32_t total = im.total_mcus * im.bpm;
@@ -613,12 +614,15 @@ jb_k4b_scan(const JbEncImage *__restrict__ images, uint32_t *__restrict__ block_
         uint32_t off = 0, tot = 0;
         for (int w = 0; w < 32; w++) { if (w < wid) off += s_w[w]; tot += s_w[w]; }
         const unsigned long long pos = s_carry + off + x - v;
-        if (i < total) a[i] = (uint32_t)pos; // images stay below 2^32 bits (512 MiB of scan data)
+        if (i < total) a[i] = (uint32_t)pos; // (a scan of 2^32 bits = 512 MiB or more is refused below)
         __syncthreads();
         if (tid == 0) s_carry += tot;
         __syncthreads();
     }
-    if (tid == 0) totals[blockIdx.x] = s_carry;
+    if (tid == 0) {
+        totals[blockIdx.x] = s_carry;
+        if (s_carry >> 32) atomicOr(status + blockIdx.x, 16u); // block offsets are 32-bit: nothing is packed
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -630,8 +634,9 @@ jb_k4c_pack(const JbEncImage *__restrict__ images, const int16_t *__restrict__ c
     const uint32_t total = im.total_mcus * im.bpm;
     const uint32_t blk = blockIdx.x * 256 + threadIdx.x;
     if (blk >= total) return;
-    if (totals[blockIdx.y] + 64 > im.raw_cap * 8) { // reserved space too small: reported, nothing written
-        if (blk == 0) atomicOr(status + blockIdx.y, 8u);
+    if ((totals[blockIdx.y] >> 32) != 0) return;    // refused by K4b
+    if (totals[blockIdx.y] + 64 > im.raw_cap * 8) { // reserved space too small: reported, nothing written; the host
+        if (blk == 0) atomicOr(status + blockIdx.y, 8u); // reserves what the totals ask for and packs again
         return;
     }
     uint32_t *words = reinterpret_cast<uint32_t *>(raw + im.raw_off);
@@ -669,7 +674,7 @@ jb_k4d_stuff(const JbEncImage *__restrict__ images, const unsigned long long *__
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) s_base = 0;
     __syncthreads();
-    if (bits + 64 > im.raw_cap * 8) { if (tid == 0) out_len[blockIdx.x] = 0; return; }
+    if ((bits >> 32) != 0 || bits + 64 > im.raw_cap * 8) { if (tid == 0) out_len[blockIdx.x] = 0; return; }
     const int padbits = (int)((8 - (bits & 7)) & 7);
     // restart markers sit in the un-stuffed stream already (K4c); their FF must not be stuffed.  Marker k occupies the
     // two bytes in front of interval k + 1, whose first block's bit offset is in block_bits.
@@ -714,7 +719,7 @@ jb_k4d_stuff(const JbEncImage *__restrict__ images, const unsigned long long *__
         uint32_t off = s_base + incl - cnt, tot = 0;
 #pragma unroll
         for (int w = 0; w < 8; w++) { if (w < wid) off += s_w[w]; tot += s_w[w]; }
-        if ((unsigned long long)off + 32 <= im.out_cap) {
+        if ((unsigned long long)off + cnt <= im.out_cap) { // (cnt <= 32; a tile that does not fit makes s_base > out_cap below)
 #pragma unroll
             for (int e = 0; e < 16; e++)
                 if (pos0 + e < nbytes) { dst[off++] = b[e]; if (b[e] == 0xFF && !((plain >> e) & 1u)) dst[off++] = 0; }

@@ -44,7 +44,7 @@ struct __align__(16) JbSegDesc {
 __global__ void __launch_bounds__(JB_K0B_THREADS)
 jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
                      const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
-                     JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status)
+                     JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status, uint32_t *__restrict__ mcu_limit)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
@@ -86,6 +86,13 @@ jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__re
     // marker there -- or none -- is "Expect restart marker.".  (If the EOI came in the middle of an interval, that
     // interval's own decode reports the premature end.)
     if (!reachable && sr.end_marker != 0xD9u) atomicOr(status + image, JB_ST_EXPECT_RST);
+    // ... and the reference returns from the MCU loop there: WriteBlock is never called for the MCUs of the absent
+    // intervals, so the renderer must leave their pixels alone.  Interval s is present iff markers 0..s-1 are RSTn.
+    if (seg == 0 && im.dri != 0) {
+        uint32_t rst = sr.nmarkers;
+        if (rst > 0 && (mk[rst - 1] & 8u) != 0) rst--;
+        if (rst + 1 < im.nseg) mcu_limit[image] = (rst + 1) * im.dri;
+    }
 }
 
 // K0c: intervals that are not in the stream (see above) leave their blocks as the allocator made them: zero.  The
@@ -260,29 +267,38 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     __syncthreads();
     const uint32_t *tab_words = reinterpret_cast<const uint32_t *>(tables);
 
-    // Bit window: hi:lo hold n valid bits, left-aligned, fed 32 bits at a time from the STUFFED stream
+    // Bit window: hi:lo hold n + pad valid bits, left-aligned, fed 32 bits at a time from the STUFFED stream
     // (JpegBitReader.FillBuffer, JpegBitReader.cs:95-138).  The common refill -- a whole word inside the
     // segment without any 0xFF byte and no stuffed FF pending -- appends the byte-swapped word; everything else
     // (FF 00 -> FF, FF FF fill bytes, the partial first and last words, the 1-bit padding behind the segment
-    // that PeekBits produces, :166) takes the byte-wise path below.  `pad` counts padding bits: they are always
-    // the last bits of the window.
+    // that PeekBits produces, :166) takes the byte-wise path below.
+    // n counts the REAL bits of the window, pad the padding bits behind them (always the last bits of the window);
+    // need = 32 - pad, so that "n < need" is "fewer than 32 bits in the window".  n goes negative when padding is
+    // consumed; whether that is an error depends on what consumed it (see `under` below).
     const uint32_t a0r = d.lead, a1r = d.lead + d.nbytes;     // segment bytes, relative to word0 * 4
-    const uint32_t endw = CLEAN ? d.endw : d.word0 + (a1r >> 2); // first word not entirely inside the segment
+    // first word not entirely inside the segment (CLEAN: d.nbytes counts the real BITS behind the entry bit)
+    const uint32_t endw = CLEAN ? d.endw : d.word0 + (a1r >> 2);
+    const uint32_t realw = CLEAN ? d.word0 + ((d.lead + d.nbytes) >> 5) : 0u; // CLEAN: first word not entirely real
     uint32_t wabs = d.word0;
-    uint32_t lim = a0r ? 0u : endw;                           // fast refills while wabs < lim (0: byte-wise path)
+    uint32_t lim = CLEAN ? min(realw, endw) : (a0r ? 0u : endw); // fast refills while wabs < lim (0: byte-wise path)
     bool carry = false;                                       // the last byte appended was a stuffed 0xFF candidate
     uint32_t hi = 0, lo = 0, wnext = 0, wnext2 = 0; // wnext: word at wabs, wnext2: the one after (both prefetched)
     if (left) {
         wnext = __ldg(arena_words + wabs);
         wnext2 = __ldg(arena_words + wabs + 1);
     }
-    int n = 0, pad = 0;
+    int n = 0, pad = 0, need = 32;
+    // DecodeHuffmanCode advances min(code size, bits available) and never fails; ReceiveAndExtend throws "The bit
+    // stream ended prematurely." when its s bits are not all there (JpegHuffmanScanDecoder.cs:81-110).  Behind the
+    // data the window holds 1-bits like PeekBits (JpegBitReader.cs:166), so the symbols come out the same either way
+    // and only the verdict is at stake: a symbol is an error iff it has magnitude bits (s > 0) and they end behind the
+    // data (n < 0 after it).  `under` collects n & -s: its sign bit is the verdict.
+    int under = 0;
     uint32_t err = 0;
 
     uint32_t b = 0, k = 0; // block-in-mcu; next zig-zag index (0: the DC symbol comes next)
     int pred = 0;
     bool skip = false;     // CLEAN: the block under way belongs to the previous sub-sequence
-    uint32_t nw = 0;       // CLEAN: words appended to the window
     if (CLEAN && left) {
         b = d.state & 0xFFu;
         k = (d.state >> 8) & 0xFFu;
@@ -293,8 +309,9 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
         const uint32_t w0 = __byte_perm(wnext, 0, 0x0123), w1 = __byte_perm(wnext2, 0, 0x0123);
         hi = __funnelshift_l(w1, w0, d.lead);
         lo = w1 << d.lead;
-        n = 64 - (int)d.lead;
-        nw = 2;
+        n = (int)min(64u - d.lead, d.nbytes);
+        pad = 64 - (int)d.lead - n;
+        need = 32 - pad;
         wabs = min(wabs + 2, endw);
         wnext = __ldg(arena_words + wabs);
         wnext2 = __ldg(arena_words + min(wabs + 1, endw));
@@ -307,18 +324,25 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     while (__any_sync(0xFFFFFFFFu, left != 0)) {
         if (left != 0) {
             if (CLEAN) {
-                if (n < 32) { // un-stuffed stream: one predicated word append
+                if (n < need) { // un-stuffed stream: one predicated word append
                     const uint32_t be = __byte_perm(wnext, 0, 0x0123);
-                    hi |= be >> n;
-                    lo |= __funnelshift_r(0u, be, n);
-                    n += 32;
-                    nw++;
+                    const int fill = n + pad;
+                    hi |= be >> fill;
+                    lo |= __funnelshift_r(0u, be, fill);
+                    if (wabs < lim) n += 32;
+                    else { // the word that holds the last real bits of the image's stream, or padding behind them
+                        const int real = wabs == realw ? (int)((d.lead + d.nbytes) & 31u) : 0;
+                        n += real;
+                        pad += 32 - real;
+                        need = 32 - pad;
+                        lim = 0;
+                    }
                     wabs = min(wabs + 1, endw);
                     wnext = wnext2;
                     wnext2 = __ldg(arena_words + min(wabs + 1, endw));
                 }
             } else
-            while (n < 32) {
+            while (n < need) {
                 const uint32_t w = wnext;
                 const uint32_t inv = ~w;
                 // 0x80 in every byte of w that is 0xFF (exact)
@@ -348,15 +372,14 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                     const uint32_t rel = (wabs - d.word0) * 4;
                     const uint32_t nb = wnext2 & 0xFFu;
                     uint32_t outw = 0, prv = carry ? 0xFFu : 0u;
-                    int bits = 0;
+                    int bits = 0, ones = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const uint32_t p = rel + i, bv = (w >> (8 * i)) & 0xFFu;
                         const uint32_t nx = i < 3 ? (w >> (8 * i + 8)) & 0xFFu : nb;
                         if (p >= a1r) { // behind the segment: 1-bits
-                            outw |= 0xFFu << (24 - bits);
-                            bits += 8;
-                            pad += 8;
+                            outw |= 0xFFu << (24 - bits - ones);
+                            ones += 8;
                         } else if (p >= a0r) {
                             const uint32_t pv = p == a0r ? 0u : prv;
                             if (!((bv == 0xFFu && nx == 0xFFu) || (bv == 0u && pv == 0xFFu))) {
@@ -368,9 +391,12 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                     }
                     carry = rel + 3 < a1r && (w >> 24) == 0xFFu;
                     lim = carry ? 0u : endw;
-                    hi |= outw >> n;
-                    lo |= __funnelshift_r(0u, outw, n);
+                    const int fill = n + pad;
+                    hi |= outw >> fill;
+                    lo |= __funnelshift_r(0u, outw, fill);
                     n += bits;
+                    pad += ones;
+                    need = 32 - pad;
                 }
                 wabs = min(wabs + 1, endw + 1);
                 wnext = wnext2;
@@ -405,6 +431,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
             hi = __funnelshift_lc(lo, hi, total);
             lo = __funnelshift_lc(0u, lo, total);
             n -= (int)total;
+            under |= n & (int)(len - total); // sign bit: magnitude bits (s > 0) that end behind the data (n < 0)
             const uint32_t pos = min(k + run, 63u);
             if (is_dc) { v += pred; pred = v; }
             if ((s != 0 || is_dc) && !(CLEAN && skip)) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
@@ -414,6 +441,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
         const bool finished = k >= 64;
         const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished && !(CLEAN && skip));
         if (fin) {
+            __syncwarp(); // the owners' coefficient stores above are read by other lanes below
             // every group of 8 lanes moves the finished blocks of its own 8 lanes, one block per round
             uint32_t mine = (fin >> (lane & 24)) & 0xFFu;
             do {
@@ -429,6 +457,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                 }
                 mine &= ~(1u << (t & 31));
             } while (__any_sync(0xFFFFFFFFu, mine != 0));
+            __syncwarp(); // the helpers' zeroing of the slots is ordered before the owners' next stores
         }
         if (finished) {
             if (!(CLEAN && skip)) gptr += 128;
@@ -448,21 +477,18 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
         }
     }
     if (d.nblocks == 0) return;
+    if (under < 0) err |= JB_ST_PREMATURE_END; // "The bit stream ended prematurely." (ReceiveAndExtend)
     if (CLEAN) {
-        // bits consumed beyond the real data => "The bit stream ended prematurely."
-        if (nw * 32 - (uint32_t)n - d.lead > d.nbytes) err |= JB_ST_PREMATURE_END;
         if (err) atomicOr(status + d.image, err);
         return;
     }
-    // bits consumed beyond the real data => "The bit stream ended prematurely."
-    if (n < pad) err |= JB_ST_PREMATURE_END;
-    else if (d.flags & 1u) {
+    if (!(err & JB_ST_PREMATURE_END) && (d.flags & 1u)) {
         // AdvanceAlignByte + TryReadMarker: after dropping the partial byte no whole byte may remain before the
         // marker (fill bytes FF are skipped by FillBuffer)
         const uint8_t *bytes = reinterpret_cast<const uint8_t *>(arena_words + d.word0);
         uint32_t p = max((wabs - d.word0) * 4, a0r);
         while (p < a1r && bytes[p] == 0xFFu) p++;
-        if (n - pad >= 8 || p < a1r || !(d.flags & 2u)) err |= JB_ST_EXPECT_RST;
+        if (n >= 8 || p < a1r || !(d.flags & 2u)) err |= JB_ST_EXPECT_RST;
     }
     if (err) atomicOr(status + d.image, err);
 }

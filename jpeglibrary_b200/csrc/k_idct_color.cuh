@@ -67,6 +67,63 @@ __device__ __forceinline__ void jb_idct8(const float y[8], float d[8])
     d[4] = __fsub_rn(a3, mb3);
 }
 
+// The same pass on TWO independent 1-D transforms at once, with packed fp32 (Blackwell add/sub/fma.rn.f32x2: SASS FADD2 /
+// FFMA2).  Every lane of a pair sees exactly the scalar operations above in the same order, each rounded once:
+//   * add.rn.f32x2 / sub.rn.f32x2 are the two scalar operations;
+//   * a product is written fma.rn.f32x2(a, C, -0.0): x + (-0.0) == x for every x including both zeros, so the result is
+//     RN(a * C), the scalar multiply.  It is NOT written mul.rn.f32x2: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
+//     into one FFMA2 (single rounding) even though both carry .rn and even with --fmad=false, and it folds a literal
+//     -0.0 addend back into a multiply first.  The -0.0 pair therefore comes in as a kernel argument (`nz`), which
+//     ptxas cannot see through; an fma result feeding an add cannot be contracted any further.
+typedef unsigned long long jb_f2;
+__device__ __forceinline__ jb_f2 jb_pack2(float lo, float hi) { jb_f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ float jb_lo2(jb_f2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return lo; }
+__device__ __forceinline__ float jb_hi2(jb_f2 v) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); return hi; }
+__device__ __forceinline__ jb_f2 jb_add2(jb_f2 a, jb_f2 b) { jb_f2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ jb_f2 jb_sub2(jb_f2 a, jb_f2 b) { jb_f2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ jb_f2 jb_fma2(jb_f2 a, jb_f2 b, jb_f2 c) { jb_f2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ jb_f2 jb_mulc2(jb_f2 a, float c, jb_f2 nz) { return jb_fma2(a, jb_pack2(c, c), nz); }
+
+__device__ __forceinline__ void jb_idct8x2(const jb_f2 y[8], jb_f2 d[8], const jb_f2 nz)
+{
+    const float C_1_175876 = 1.175875602f, C_1_961571 = -1.961570560f, C_0_390181 = -0.390180644f,
+                C_0_899976 = -0.899976223f, C_2_562915 = -2.562915447f, C_0_298631 = 0.298631336f,
+                C_2_053120 = 2.053119869f, C_3_072711 = 3.072711026f, C_1_501321 = 1.501321110f,
+                C_0_541196 = 0.541196100f, C_1_847759 = -1.847759065f, C_0_765367 = 0.765366865f;
+    const jb_f2 my1 = y[1], my7 = y[7], my3 = y[3], my5 = y[5];
+    jb_f2 mz0 = jb_add2(my1, my7);
+    jb_f2 mz2 = jb_add2(my3, my7);
+    jb_f2 mz1 = jb_add2(my3, my5);
+    jb_f2 mz3 = jb_add2(my1, my5);
+    jb_f2 mz4 = jb_mulc2(jb_add2(mz0, mz1), C_1_175876, nz);
+    mz2 = jb_add2(jb_mulc2(mz2, C_1_961571, nz), mz4);
+    mz3 = jb_add2(jb_mulc2(mz3, C_0_390181, nz), mz4);
+    mz0 = jb_mulc2(mz0, C_0_899976, nz);
+    mz1 = jb_mulc2(mz1, C_2_562915, nz);
+    const jb_f2 mb3 = jb_add2(jb_add2(jb_mulc2(my7, C_0_298631, nz), mz0), mz2);
+    const jb_f2 mb2 = jb_add2(jb_add2(jb_mulc2(my5, C_2_053120, nz), mz1), mz3);
+    const jb_f2 mb1 = jb_add2(jb_add2(jb_mulc2(my3, C_3_072711, nz), mz1), mz2);
+    const jb_f2 mb0 = jb_add2(jb_add2(jb_mulc2(my1, C_1_501321, nz), mz0), mz3);
+    const jb_f2 my2 = y[2], my6 = y[6], my0 = y[0], my4 = y[4];
+    mz4 = jb_mulc2(jb_add2(my2, my6), C_0_541196, nz);
+    mz0 = jb_add2(my0, my4);
+    mz1 = jb_sub2(my0, my4);
+    mz2 = jb_add2(mz4, jb_mulc2(my6, C_1_847759, nz));
+    mz3 = jb_add2(mz4, jb_mulc2(my2, C_0_765367, nz));
+    const jb_f2 a0 = jb_add2(mz0, mz3);
+    const jb_f2 a3 = jb_sub2(mz0, mz3);
+    const jb_f2 a1 = jb_add2(mz1, mz2);
+    const jb_f2 a2 = jb_sub2(mz1, mz2);
+    d[0] = jb_add2(a0, mb0);
+    d[7] = jb_sub2(a0, mb0);
+    d[1] = jb_add2(a1, mb1);
+    d[6] = jb_sub2(a1, mb1);
+    d[2] = jb_add2(a2, mb2);
+    d[5] = jb_sub2(a2, mb2);
+    d[3] = jb_add2(a3, mb3);
+    d[4] = jb_sub2(a3, mb3);
+}
+
 __device__ __forceinline__ int jb_clamp255(int v) { return min(max(v, 0), 255); }
 
 // One sample of a P-bit frame as the 8-bit value the reference's application writers store:
@@ -108,7 +165,7 @@ struct JbK2Geom {
 __global__ void __launch_bounds__(JB_K2_THREADS)
 jb_k2_idct_color(const JbDevImage *__restrict__ images,
                  const int16_t *__restrict__ coef, const uint16_t *__restrict__ quant,
-                 const uint32_t *__restrict__ image_list)
+                 const uint32_t *__restrict__ image_list, const uint32_t *__restrict__ mcu_limit)
 {
     __shared__ __align__(16) float s_f[JB_K2_MAX_BLOCKS * JB_K2_BLOCK_STRIDE];
     __shared__ __align__(16) int16_t s_plane[JB_K2_MAX_BLOCKS * 64];
@@ -134,6 +191,10 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
         tw.mcu_col0 = (blockIdx.x - tw.mcu_row * strips) * tile_mcus;
         tw.nmcu = min(tile_mcus, s_im.mcus_per_line - tw.mcu_col0);
         if (tw.mcu_row >= s_im.mcus_per_col) return;
+        // MCUs that were never decoded (scan ended at an EOI on a restart boundary) are not written (see K0b)
+        const uint32_t limit = mcu_limit ? mcu_limit[tw.image] : 0xFFFFFFFFu, mcu0 = tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0;
+        if (mcu0 >= limit) return;
+        tw.nmcu = min(tw.nmcu, limit - mcu0);
     }
     const int nmcu = tw.nmcu;
     if (tid < ncomp * 64) s_q[tid] = quant[s_im.quant_off + tid];

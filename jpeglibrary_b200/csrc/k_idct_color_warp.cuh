@@ -90,12 +90,64 @@ __device__ __forceinline__ void jb_k2w_col(const float (&d1)[64], uint32_t (&row
     }
 }
 
+#ifndef JB_K2_PACKED
+#define JB_K2_PACKED 1 // both IDCT passes on packed fp32 pairs (FADD2 / FFMA2), see jb_idct8x2
+#endif
+
+// Packed variants of the two passes: rows R, R + 1 run in lockstep (one f32x2 lane each), then columns C, C + 1.
+template <int R>
+__device__ __forceinline__ void jb_k2w_row2(const uint32_t (&pk)[32], const float *__restrict__ qn2, jb_f2 (&d1)[32], const jb_f2 nz)
+{
+    // qn2: the quantisers of rows R, R + 1 interleaved: {q[R][e], q[R + 1][e]} per e
+    jb_f2 y[8], d[8];
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) {
+        const ulonglong2 q = *reinterpret_cast<const ulonglong2 *>(qn2 + (R / 2) * 16 + e * 2);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int z0 = jb_nat2zz_c(R * 8 + e + u), z1 = jb_nat2zz_c((R + 1) * 8 + e + u);
+            float c0, c1;
+            if (z0 & 1) asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, hi; }" : "=f"(c0) : "r"(pk[z0 >> 1]));
+            else asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, lo; }" : "=f"(c0) : "r"(pk[z0 >> 1]));
+            if (z1 & 1) asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, hi; }" : "=f"(c1) : "r"(pk[z1 >> 1]));
+            else asm("{ .reg .b16 lo, hi; mov.b32 {lo, hi}, %1; cvt.rn.f32.s16 %0, lo; }" : "=f"(c1) : "r"(pk[z1 >> 1]));
+            // the product of two integers below 2^24 is exact: fma(q, c, -0.0) == fmul(q, c) == (float)(q * c)
+            y[e + u] = jb_fma2(u ? q.y : q.x, jb_pack2(c0, c1), nz);
+        }
+    }
+    jb_idct8x2(y, d, nz);
+#pragma unroll
+    for (int e = 0; e < 8; e++) d1[(R / 2) * 8 + e] = d[e]; // {d1[R][e], d1[R + 1][e]}
+}
+
+template <int C>
+__device__ __forceinline__ void jb_k2w_col2(const jb_f2 (&d1)[32], uint32_t (&rows)[16], const jb_f2 nz)
+{
+    jb_f2 y[8], d[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { // {d1[k][C], d1[k][C + 1]}
+        const jb_f2 a = d1[(k / 2) * 8 + C], b = d1[(k / 2) * 8 + C + 1];
+        y[k] = (k & 1) ? jb_pack2(jb_hi2(a), jb_hi2(b)) : jb_pack2(jb_lo2(a), jb_lo2(b));
+    }
+    jb_idct8x2(y, d, nz); // along columns C, C + 1
+    const jb_f2 eighth = jb_pack2(0.125f, 0.125f), bias = jb_pack2(12582912.0f + 128.0f, 12582912.0f + 128.0f);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        // MultiplyInplace(0.125) + MathF.Round (half-to-even) + level shift in one fma, then clamp to 0..255
+        const jb_f2 t = jb_fma2(d[k], eighth, bias);
+        const uint32_t v0 = (uint32_t)__viaddmin_s32_relu(__float_as_int(jb_lo2(t)), -0x4B400000, 255);
+        const uint32_t v1 = (uint32_t)__viaddmin_s32_relu(__float_as_int(jb_hi2(t)), -0x4B400000, 255);
+        if ((C & 3) == 0) rows[k * 2 + (C >> 2)] = v0 + (v1 << 8);
+        else rows[k * 2 + (C >> 2)] += (v0 << (8 * (C & 3))) + (v1 << (8 * (C & 3) + 8)); // disjoint bytes
+    }
+}
+
 // FMT: 0 RGB24, 1 RGBA32, 2 YCBCR888.  HS,VS: chroma subsampling (1 or 2).  NC: 1 or 3 components.
 template <int FMT, int NC, int HS, int VS>
 __global__ void __launch_bounds__(JB_K2W_WARPS * 32, 4)
 jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__restrict__ coef,
                       const uint16_t *__restrict__ quant, const uint32_t *__restrict__ image_list,
-                      int units_per_warp)
+                      int units_per_warp, const uint32_t *__restrict__ mcu_limit, const unsigned long long negzero2)
 {
     constexpr int BPM = NC == 1 ? 1 : (HS * VS + 2);
     constexpr int UM = NC == 1 ? 16 : 32 / BPM; // MCUs per unit (grey: 16, which keeps the tiles inside 48 KB)
@@ -112,7 +164,8 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     __shared__ __align__(16) uint8_t s_y[JB_K2W_WARPS][TW * TH];
     __shared__ __align__(16) uint8_t s_c[JB_K2W_WARPS][2][NC == 1 ? 16 : CW * 8];
     __shared__ __align__(128) uint8_t s_stage[JB_K2W_WARPS][TH * ROW_BYTES];
-    __shared__ __align__(16) float s_qn[NC * 64]; // quantisers in NATURAL order, one table per component
+    // quantisers in NATURAL order, one table per component (packed IDCT: rows 2r, 2r + 1 interleaved element-wise)
+    __shared__ __align__(16) float s_qn[NC * 64];
     constexpr int GROUPS = TW / 4;                // phase B works on items of 4 pixels x VS rows (one chroma row)
     constexpr int ITEMS = GROUPS * (TH / VS);
     static_assert(ITEMS % 32 == 0, "items must spread evenly over the lanes");
@@ -127,8 +180,14 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K2W_WARPS * 32) dst[i] = src[i];
     }
     __syncthreads();
-    for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32)
+    for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32) {
+#if JB_K2_PACKED
+        const int n = i & 63, r = ((n >> 4) << 1) | (n & 1), e = (n >> 1) & 7; // slot (r/2)*16 + e*2 + (r&1)
+        s_qn[i] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[r * 8 + e]];
+#else
         s_qn[i] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
+#endif
+    }
     for (int i = tid; i < ITEMS; i += JB_K2W_WARPS * 32) {
         const int cy = i / GROUPS, gx = (i - cy * GROUPS) * 4;
         s_item[i] = (uint32_t)(cy * CW + gx / HS) | ((uint32_t)(cy * VS * TW + gx) << 10) |
@@ -159,6 +218,9 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     const uint64_t tmap = s_im.tmap_ptr;
     const int tmap_shift = (int)s_im.tmap_shift;
     const bool planar = s_im.planar != 0;
+    // MCUs from here on were never decoded (the scan ended at an EOI on a restart boundary): the reference never calls
+    // WriteBlock for them (JpegHuffmanBaselineScanDecoder.cs:144-150), their pixels are left as they are
+    const uint32_t limit = mcu_limit ? mcu_limit[image] : 0xFFFFFFFFu;
     uint8_t *raw = s_raw[wid];
     uint8_t *yplane = s_y[wid];
     uint8_t *stage = s_stage[wid];
@@ -209,7 +271,10 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
 
     for (; unit < unit_end; unit++) {
         const uint32_t mcu_col0 = ucol * UM;
-        const int nmcu = (int)min((uint32_t)UM, mcus_per_line - mcu_col0);
+        int nmcu = (int)min((uint32_t)UM, mcus_per_line - mcu_col0);
+        const uint32_t mcu0 = mcu_row * mcus_per_line + mcu_col0;
+        const bool clipped = mcu0 + (uint32_t)nmcu > limit; // (never on intact streams)
+        if (clipped) nmcu = limit > mcu0 ? (int)(limit - mcu0) : 0;
         const bool valid = j < NB && m < nmcu;
         const uint32_t cur_row = mcu_row;
         if (++ucol == upr) { ucol = 0; mcu_row++; }
@@ -229,12 +294,20 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         __syncwarp();
         if (unit + 1 < unit_end) fetch(mcu_row, ucol); // the raw tile is free again: prefetch the next unit
         if (valid) {
+            uint32_t rows[16];
+#if JB_K2_PACKED
+            jb_f2 d1[32];
+            jb_k2w_row2<0>(pk, qn, d1, negzero2); jb_k2w_row2<2>(pk, qn, d1, negzero2);
+            jb_k2w_row2<4>(pk, qn, d1, negzero2); jb_k2w_row2<6>(pk, qn, d1, negzero2);
+            jb_k2w_col2<0>(d1, rows, negzero2); jb_k2w_col2<2>(d1, rows, negzero2);
+            jb_k2w_col2<4>(d1, rows, negzero2); jb_k2w_col2<6>(d1, rows, negzero2);
+#else
             float d1[64];
             jb_k2w_row<0>(pk, qn, d1); jb_k2w_row<1>(pk, qn, d1); jb_k2w_row<2>(pk, qn, d1); jb_k2w_row<3>(pk, qn, d1);
             jb_k2w_row<4>(pk, qn, d1); jb_k2w_row<5>(pk, qn, d1); jb_k2w_row<6>(pk, qn, d1); jb_k2w_row<7>(pk, qn, d1);
-            uint32_t rows[16];
             jb_k2w_col<0>(d1, rows); jb_k2w_col<1>(d1, rows); jb_k2w_col<2>(d1, rows); jb_k2w_col<3>(d1, rows);
             jb_k2w_col<4>(d1, rows); jb_k2w_col<5>(d1, rows); jb_k2w_col<6>(d1, rows); jb_k2w_col<7>(d1, rows);
+#endif
             uint8_t *pl = (c == 0 ? yplane + (by * 8) * TW : s_c[wid][c - 1]) + bx * 8;
             const int pp = c == 0 ? TW : CW;
 #pragma unroll
@@ -331,8 +404,8 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         // ------------------------------------------------ phase C: staging tile -> global
         const int x0 = mcu_col0 * 8 * HS, y0 = cur_row * TH;
         const int rows_out = min(TH, H - y0);
-        const int row_bytes = min(ROW_BYTES, (W - x0) * BPP);
-        if (tmap) {
+        const int row_bytes = clipped ? min(nmcu * 8 * HS, W - x0) * BPP : min(ROW_BYTES, (W - x0) * BPP);
+        if (tmap && !clipped) {
             // one 2-D TMA tensor store for the whole unit; the hardware clips at the right and bottom image edges
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> async proxy
             __syncwarp();
@@ -343,7 +416,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             bulk_pending = true;
-        } else if (bulk_ok && row_bytes == ROW_BYTES) {
+        } else if (bulk_ok && row_bytes == ROW_BYTES && !clipped) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes -> async proxy
             __syncwarp();
             if (lane < rows_out) {

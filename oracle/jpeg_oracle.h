@@ -71,6 +71,11 @@ typedef struct {
     uint8_t *rgb;            /* [height][width][3] */
     size_t consumed;         /* bytes consumed up to and including EOI (or len) */
     char error[160];
+    /* sequential frames: one byte per block of the padded grid, 1 = some scan read the block and handed it to
+       WriteBlock (...BaselineScanDecoder.cs:119-134).  Blocks behind an EOI that sits on a restart boundary
+       (:144-150) and components no scan names are never written: their samples in `planes` keep the 0 of a fresh
+       buffer.  NULL for progressive / lossless frames. */
+    uint8_t *written[JO_MAX_COMP];
 } jo_image;
 
 /* flags for jo_decode */
@@ -122,6 +127,9 @@ typedef struct {
     int dht_nvals[2][4];
     size_t scan_offset, scan_len;            /* entropy-coded bytes inside `bytes` */
     char error[160];
+    /* the allocator's dummy block (JpegBlockAllocator.cs:73-78,108-111) as the scan write finds it: every
+       MCU-padding block aliases it, so it holds what the LAST padding block of TransformBlocks left there */
+    int16_t dummy[64];
 } jo_encoded;
 
 /* Annex-K tables scaled like JpegStandardQuantizationTable.ScaleByQuality (:64-89). */

@@ -353,6 +353,9 @@ static int scan_baseline(dec_ctx *c, const jo_scan_info *s)
                         memset(blk, 0, 128); /* outputBuffer = default :121 */
                         read_block_baseline(c, &r, comp, blk);
                         if (c->err) return c->err;
+                        if (im->written[comp->component_index]) /* WriteBlock :133 */
+                            im->written[comp->component_index][(size_t)(row * comp->v + y) * im->coef_w[comp->component_index] +
+                                                               col * comp->h + x] = 1;
                     }
             }
             /* restart :139-163 */
@@ -818,15 +821,9 @@ static void render_planes(dec_ctx *c)
     int W = im->width, H = im->height;
     int shift = 1 << (im->precision - 1);
     for (int ci = 0; ci < im->ncomp; ci++) {
-        if (im->sof != 2) {
-            /* the sequential decoder hands a block to WriteBlock right after reading it (:119-134): a component
-               that no scan names is never written.  (Block-level: blocks behind an EOI at a restart boundary are
-               not written either; that is NOT modelled here -- every block of a named component is rendered.) */
-            int named = 0;
-            for (int s = 0; s < im->nscans; s++)
-                for (int k = 0; k < im->scans[s].ncomp; k++) named |= im->scans[s].comp_index[k] == ci;
-            if (!named) continue;
-        }
+        /* the sequential decoder hands a block to WriteBlock right after reading it (:119-134): a component that no
+           scan names, and the blocks behind an EOI that ends the scan at a restart boundary (:144-150), are never
+           written -- see `written` */
         int hs = im->hmax / im->comp_h[ci], vs = im->vmax / im->comp_v[ci];
         int16_t *plane = im->planes + (size_t)ci * W * H;
         int gw = im->sof == 2 ? im->alloc_w[ci] : im->coef_w[ci];
@@ -834,6 +831,7 @@ static void render_planes(dec_ctx *c)
         for (int by = 0; by < gh; by++)
             for (int bx = 0; bx < gw; bx++) {
                 int16_t px[64];
+                if (im->sof != 2 && im->written[ci] && !im->written[ci][(size_t)by * im->coef_w[ci] + bx]) continue;
                 jo_dequant_idct_block(coef_block(im, ci, bx, by), im->qt[ci], shift, px);
                 int x0 = bx * 8 * hs, y0 = by * 8 * vs;
                 for (int yy = 0; yy < 8 * vs; yy++) {
@@ -962,6 +960,8 @@ static int parse_frame(dec_ctx *c, int sof, const uint8_t *b, size_t n)
         free(im->coef[i]);
         im->coef[i] = calloc((size_t)im->coef_w[i] * im->coef_h[i] * 64, sizeof(int16_t));
         if (!im->coef[i]) return fail(c, JO_ERR_NOMEM, "out of memory");
+        free(im->written[i]);
+        im->written[i] = im->sof < 2 ? calloc((size_t)im->coef_w[i] * im->coef_h[i], 1) : NULL;
     }
     c->have_frame = 1;
     return JO_OK;
@@ -1165,6 +1165,8 @@ void jo_free(jo_image *img)
     for (int i = 0; i < JO_MAX_COMP; i++) {
         free(img->coef[i]);
         img->coef[i] = NULL;
+        free(img->written[i]);
+        img->written[i] = NULL;
     }
     free(img->planes);
     free(img->ycbcr);

@@ -336,8 +336,7 @@ int jo_encode_ycbcr(const uint8_t *ycbcr, const jo_encode_params *p, jo_encoded 
     for (int c = 0; c < nc; c++) { if (p->h[c] > hmax) hmax = p->h[c]; if (p->v[c] > vmax) vmax = p->v[c]; }
     const int mpl = (W + 8 * hmax - 1) / (8 * hmax), mpc = (H + 8 * vmax - 1) / (8 * vmax);
     const int wblk = (W + 7) / 8, hblk = (H + 7) / 8;
-    int16_t dummy[64];
-    memset(dummy, 0, sizeof dummy);
+    int16_t *dummy = out->dummy; /* (zero: memset above) */
     for (int c = 0; c < nc; c++) {
         int hs = hmax / p->h[c], vs = vmax / p->v[c];
         out->alloc_w[c] = (wblk + hs - 1) / hs;

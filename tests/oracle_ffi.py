@@ -47,6 +47,7 @@ class Image(C.Structure):
         ("rgb", C.POINTER(C.c_uint8)),
         ("consumed", C.c_size_t),
         ("error", C.c_char * 160),
+        ("written", C.POINTER(C.c_uint8) * JO_MAX_COMP),
     ]
 
 
@@ -72,6 +73,7 @@ class Encoded(C.Structure):
         ("dht_nvals", (C.c_int * 4) * 2),
         ("scan_offset", C.c_size_t), ("scan_len", C.c_size_t),
         ("error", C.c_char * 160),
+        ("dummy", C.c_int16 * 64),
     ]
 
 
@@ -144,6 +146,9 @@ def decode(data: bytes, want_rgb=True) -> Decoded:
             cnt = d.coef_w[i] * d.coef_h[i] * 64
             a = np.ctypeslib.as_array(img.coef[i], shape=(cnt,)).copy()
             d.coef.append(a.reshape(d.coef_h[i], d.coef_w[i], 64))
+        # sequential frames: which blocks some scan handed to WriteBlock (None: every block is written at the end)
+        d.written = [np.ctypeslib.as_array(img.written[i], shape=(d.coef_h[i] * d.coef_w[i],)).copy()
+                     .reshape(d.coef_h[i], d.coef_w[i]).astype(bool) if bool(img.written[i]) else None for i in range(n)]
         W, H = img.width, img.height
         d.planes = np.ctypeslib.as_array(img.planes, shape=(n * H * W,)).copy().reshape(n, H, W)
         if want_rgb and bool(img.rgb):
@@ -154,6 +159,19 @@ def decode(data: bytes, want_rgb=True) -> Decoded:
         return d
     finally:
         lib().jo_free(C.byref(img))
+
+
+def written_samples(d: Decoded) -> np.ndarray:
+    """bool [ncomp][H][W]: samples the reference's decoder hands to WriteBlock (all of them unless a sequential scan
+    ends early at an EOI on a restart boundary, or no scan names the component)"""
+    out = np.ones((d.ncomp, d.height, d.width), dtype=bool)
+    for ci in range(d.ncomp):
+        if d.written[ci] is None:
+            continue
+        hs, vs = d.hmax // d.comp_h[ci], d.vmax // d.comp_v[ci]
+        m = np.repeat(np.repeat(d.written[ci], 8 * vs, axis=0), 8 * hs, axis=1)
+        out[ci] = m[:d.height, :d.width]
+    return out
 
 
 def scan_order_coefficients(d: Decoded) -> np.ndarray:
@@ -247,6 +265,7 @@ def encode_ycbcr(ycbcr, quality=75, subsampling=(2, 2), gray=False):
         for c in range(p.ncomp):
             n = e.alloc_w[c] * e.alloc_h[c] * 64
             r.coef.append(np.ctypeslib.as_array(e.coef[c], shape=(n,)).copy().reshape(e.alloc_h[c], e.alloc_w[c], 64))
+        r.dummy = np.array(list(e.dummy), dtype=np.int16)
         r.hist = np.array([[list(e.hist[cls][t]) for t in range(4)] for cls in range(2)], dtype=np.uint32)
         r.dht = {}
         for cls in range(2):

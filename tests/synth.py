@@ -341,3 +341,62 @@ def resequence_scans(blob, decoded, scans, restart=0):
         out += data
     out += b"\xff\xd9"
     return bytes(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# Hand-made grey baseline streams whose Huffman tables use the ALL-ONES codes (DC category 0 = '1', AC end-of-block =
+# '11').  Behind the data the reference's bit reader supplies 1-bits (JpegBitReader.cs:166) and DecodeHuffmanCode
+# advances min(code size, bits available) (JpegHuffmanScanDecoder.cs:81-88), so with these tables a stream that is cut
+# short keeps decoding -- empty blocks -- without an error, unless a symbol with magnitude bits straddles the cut.
+def handmade_grey(blocks_w, blocks_h, seed=0, dri=0, cut=0, cut_interval=None):
+    """returns (jpeg bytes, expected zig-zag coefficient blocks [n][64] of the UNCUT stream).
+    cut: bytes removed from the end of the entropy-coded data (of restart interval `cut_interval`, default the last)."""
+    rng = np.random.default_rng(seed)
+    n = blocks_w * blocks_h
+    coef = np.zeros((n, 64), np.int16)
+    intervals, bits, pred = [], [], 0
+
+    def flush():
+        nonlocal bits
+        while len(bits) % 8:
+            bits.append(1)
+        by = np.packbits(np.array(bits, np.uint8)).tobytes() if bits else b""
+        intervals.append(by.replace(b"\xff", b"\xff\x00"))
+        bits = []
+
+    for i in range(n):
+        if dri and i and i % dri == 0:
+            flush()
+            pred = 0
+        d = int(rng.integers(-1, 2))
+        bits += [1] if d == 0 else [0, 1 if d > 0 else 0]            # DC: '1' = category 0, '0' = category 1 + 1 bit
+        pred += d
+        coef[i, 0] = pred
+        k = 1
+        for _ in range(int(rng.integers(0, 4))):
+            if rng.integers(2):
+                v = int(rng.choice([-1, 1]))
+                bits += [0, 1 if v > 0 else 0]                       # AC 0x01: '0' + 1 bit
+            else:
+                v = int(rng.choice([-3, -2, 2, 3]))
+                bits += [1, 0] + [int(x) for x in format(v if v > 0 else v + 3, "02b")]  # AC 0x02: '10' + 2 bits
+            coef[i, k] = v
+            k += 1
+        bits += [1, 1]                                               # EOB: '11'
+    flush()
+    if cut:
+        k = len(intervals) - 1 if cut_interval is None else cut_interval
+        intervals[k] = intervals[k][:max(0, len(intervals[k]) - cut)]
+    data = b"".join(iv + (bytes([0xFF, 0xD0 + (k & 7)]) if k + 1 < len(intervals) else b"") for k, iv in enumerate(intervals))
+
+    def seg(marker, payload):
+        return bytes([0xFF, marker]) + (len(payload) + 2).to_bytes(2, "big") + payload
+
+    out = b"\xff\xd8" + seg(0xDB, bytes([0]) + bytes([1] * 64))
+    out += seg(0xC0, bytes([8]) + (blocks_h * 8).to_bytes(2, "big") + (blocks_w * 8).to_bytes(2, "big") + bytes([1, 1, 0x11, 0]))
+    out += seg(0xC4, bytes([0x00]) + bytes([2] + [0] * 15) + bytes([1, 0]))          # DC: '0' -> 1, '1' -> 0
+    out += seg(0xC4, bytes([0x10]) + bytes([1, 2] + [0] * 14) + bytes([0x01, 0x02, 0x00]))  # AC: '0' 01, '10' 02, '11' EOB
+    if dri:
+        out += seg(0xDD, dri.to_bytes(2, "big"))
+    out += seg(0xDA, bytes([1, 1, 0x00, 0, 63, 0])) + data + b"\xff\xd9"
+    return out, coef

@@ -101,6 +101,13 @@ def scan_order(e, shape, subsampling):
     parts = []
     for c, a in enumerate(e.coef):
         h, v = (hs, vs) if c == 0 else (1, 1)
+        if a.shape[:2] != (my * v, mx * h):
+            # MCU-padding blocks alias the allocator's dummy block (JpegBlockAllocator.cs:108-111): in scan order every
+            # one of them reads what the last TransformBlocks call left there
+            full = np.empty((my * v, mx * h, 64), np.int16)
+            full[:] = e.dummy
+            full[:a.shape[0], :a.shape[1]] = a
+            a = full
         parts.append(a.reshape(my, v, mx, h, 64).transpose(0, 2, 1, 3, 4).reshape(mx * my, v * h, 64))
     return np.concatenate(parts, axis=1).reshape(-1, 64)
 
@@ -112,6 +119,14 @@ ENC_SHAPES = [
     dict(width=96, height=112, subsampling=(1, 2), quality=85),
     dict(width=640, height=480, subsampling=(2, 2), quality=30),
     dict(width=1920, height=1088, subsampling=(2, 2), quality=95),
+    # frames whose luma block grid is not a whole number of MCUs: padding blocks alias the allocator's dummy block
+    # (JpegBlockAllocator.cs:108-111, JpegEncoder.cs:458-470, 551-597, 640-647)
+    dict(width=1920, height=1080, subsampling=(2, 2), quality=75),  # 135 block rows
+    dict(width=24, height=16, subsampling=(2, 2), quality=75),     # 3 block columns
+    dict(width=40, height=24, subsampling=(2, 2), quality=50),     # both
+    dict(width=72, height=40, subsampling=(2, 1), quality=80),
+    dict(width=48, height=56, subsampling=(1, 2), quality=80),
+    dict(width=3, height=5, subsampling=(2, 2), quality=75),       # one MCU, three of four luma blocks are padding
 ]
 
 
@@ -128,6 +143,20 @@ def test_gpu_encoder_is_bit_identical_to_the_oracle(kw):
     assert got == want.bytes                                                                        # E8 + E9, headers
     d = O.decode(got)                                                                               # re-decodes under the reference restatement
     assert (d.width, d.height) == (kw["width"], kw["height"])
+    from PIL import Image
+    img = Image.open(io.BytesIO(got))                                                               # and under libjpeg-turbo
+    img.draft("YCbCr", img.size)
+    assert np.abs(np.array(img)[..., 0].astype(int) - d.ycbcr[..., 0].astype(int)).max() <= 2
+
+
+@pytest.mark.gpu
+def test_gpu_encoder_4k_frame_is_bit_identical_to_the_oracle():
+    """configs[4] at its full frame size (3840x2160 RGB -> q75 4:2:0 with optimised tables)."""
+    rgb = synth.synth_rgb(1004, 3840, 2160)
+    want = O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=75)
+    got, enc = J.encode_rgb(rgb, quality=75)
+    assert np.array_equal(enc.last_coefficients, scan_order(want, rgb.shape[:2], (2, 2)))
+    assert got == want.bytes
 
 
 @pytest.mark.gpu
@@ -153,7 +182,7 @@ def test_gpu_encode_then_gpu_decode_round_trip():
 
 
 @pytest.mark.gpu
-def test_gpu_encoder_compatibility_reader_and_quirk_q4():
+def test_gpu_encoder_compatibility_reader():
     class Reader(J.JpegBlockInputReader):  # apps/JpegEncode/JpegBufferInputReader.cs
         def __init__(self, ycc):
             self.ycc, (self.Height, self.Width) = ycc, ycc.shape[:2]
@@ -179,10 +208,23 @@ def test_gpu_encoder_compatibility_reader_and_quirk_q4():
     enc.SetOutput(out)
     enc.Encode()
     assert bytes(out) == O.encode_ycbcr(ycc, quality=75).bytes
-    # 24 px wide 4:2:0: three luma block columns -> the reference encodes an MCU-padding block from its
-    # stale dummy block (quirk Q4); the GPU path refuses instead of inventing data
+    # 24 px wide 4:2:0: three luma block columns -> one MCU-padding block per MCU row, read through the same reader
+    ycc = O.rgb_to_ycbcr(synth.synth_rgb(1, 24, 16))
+    enc.SetInputReader(Reader(ycc))
+    out = bytearray()
+    enc.SetOutput(out)
+    enc.Encode()
+    assert bytes(out) == O.encode_ycbcr(ycc, quality=75).bytes
+
+    class Odd(Reader):  # a reader that invents samples outside its own frame: not what the GPU path computes
+        def ReadBlock(self, blockRef, componentIndex, x, y):
+            super().ReadBlock(blockRef, componentIndex, x, y)
+            if x >= self.Width:
+                blockRef[:] = 7
+
+    enc.SetInputReader(Odd(ycc))
     with pytest.raises(J.NotSupportedException):
-        J.encode_rgb(synth.synth_rgb(1, 24, 16), quality=75)
+        enc.Encode()
 
 
 def test_fp64_reciprocal_quantisation_equals_ieee_fp32_division():
@@ -200,3 +242,33 @@ def test_fp64_reciprocal_quantisation_equals_ieee_fp32_division():
         ref = (xs * np.float32(0.125)) / np.float32(q)
         got = (xs.astype(np.float64) * r8).astype(np.float32)
         assert np.array_equal(ref, got), q
+
+
+@pytest.mark.gpu
+def test_caller_tables_on_noise_outgrow_the_reserved_stream_space():
+    """Annex-K tables installed by the caller (JpegEncoder.SetHuffmanTable(isDc, id, table)) on noise at quality 100 need
+    more than the 768 bits per block that are reserved up front: the pack stage reserves what the bit totals ask for
+    and runs again, instead of failing a frame the reference encodes."""
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)
+    std = J.Parsed(synth.encode_jpeg(rgb[:64, :64], quality=90, subsampling="4:4:4")).desc  # libjpeg writes the Annex-K tables
+    specs = {(std.tables[i].table_class, std.tables[i].identifier): std.tables[i] for i in range(std.table_count)}
+    assert len(specs) == 4
+    enc = J.JpegEncoder()
+    enc.SetQuantizationTable(J.JpegStandardQuantizationTable.ScaleByQuality(J.JpegStandardQuantizationTable.GetLuminanceTable(0, 0), 100))
+    enc.SetQuantizationTable(J.JpegStandardQuantizationTable.ScaleByQuality(J.JpegStandardQuantizationTable.GetChrominanceTable(0, 1), 100))
+    for (cls, ident), spec in specs.items():
+        enc.SetHuffmanTable(cls == 0, ident, spec)
+    enc.AddComponent(1, 0, 0, 0, 1, 1)
+    enc.AddComponent(2, 1, 1, 1, 1, 1)
+    enc.AddComponent(3, 1, 1, 1, 1, 1)
+    enc.SetInputReader(J.CudaInputReader(rgb, format=J.JB_IN_RGB24))
+    out = bytearray()
+    enc.SetOutput(out)
+    enc.Encode()
+    nblk = 3 * 64 * 64
+    assert len(out) > nblk * 96 + 4096                       # more than was reserved at create time
+    d = O.decode(bytes(out))
+    assert np.array_equal(O.scan_order_coefficients(d).reshape(-1, 64), enc.last_coefficients)
+    from PIL import Image
+    assert Image.open(io.BytesIO(bytes(out))).size == (512, 512)

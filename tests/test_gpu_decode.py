@@ -54,10 +54,22 @@ def test_golden_assets_coefficients_bit_exact(name):
     check_coefficients(golden_bytes(name))
 
 
+def reference_golden16(planes, precision):
+    """What the reference's test writer stores for unclamped int16 samples (Utils/JpegExtendingOutputWriter.cs:57,77-80:
+    (ushort) cast, clamp to 2^P - 1, expand to 16 bits): the bytes of <asset>.jpg.high.png / .low-diff.png."""
+    s = np.minimum(planes.astype(np.int16).view(np.uint16).astype(np.uint32), (1 << precision) - 1)
+    rem = 16 - precision
+    return np.ascontiguousarray(((s << rem) | (s & ((1 << rem) - 1))).astype(np.uint16).transpose(1, 2, 0))
+
+
 @pytest.mark.parametrize("name", BASELINE_ASSETS)
 def test_golden_assets_planes_match_reference_goldens(name, golden):
     planes = gpu_planes(golden_bytes(name))
-    assert hashlib.sha256(np.ascontiguousarray(planes).tobytes()).hexdigest() == golden["assets"][name]["planes_i16_sha256"]
+    g = golden["assets"][name]
+    # the reference's own golden vector (sha256 of the buffer its test compares against) ...
+    assert hashlib.sha256(reference_golden16(planes, g["precision"]).tobytes()).hexdigest() == g["golden16_sha256"]
+    # ... and the oracle's unclamped planes, which carry more information than the clamped golden
+    assert hashlib.sha256(np.ascontiguousarray(planes).tobytes()).hexdigest() == g["planes_i16_sha256"]
     o = O.decode(golden_bytes(name), want_rgb=False)
     assert np.array_equal(planes, o.planes)
 
@@ -188,8 +200,8 @@ def test_batch_of_mixed_images_device_resident():
         assert b.status() == [0] * len(blobs)
         # restart scan + segment descriptors + absent-interval clear + segment Huffman + self-sync chain for lake.jpg (un-stuff count and
         # copy, guess round, 5 sync rounds, prefix sums, descriptors, write) + one IDCT/colour launch per layout
-        # (+ the status clear at the start and the status mailbox post at the end)
-        assert b.launch_count() == 1 + 1 + 3 + (6 + 5) + 2 + 1
+        # (+ the status and MCU-limit clears at the start and the status mailbox post at the end)
+        assert b.launch_count() == 2 + 1 + 3 + (6 + 5) + 2 + 1
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run
@@ -262,7 +274,53 @@ def test_eoi_at_a_restart_boundary_ends_the_scan_quietly(kind):
     assert o.height == height + 48
     planes = gpu_planes(blob)
     assert np.array_equal(planes[:, :height], o.planes[:, :height])   # what was decoded is identical ...
-    assert np.array_equal(planes, o.planes)     # ... and so is the rest (lossless: zeros; sequential: see DESIGN, known deviation)
+    assert np.array_equal(planes, o.planes)     # ... and the rest was never written (a fresh buffer's zeros)
+
+
+def _decode_into(blob, out, fmt, ctx=None, on_device=False):
+    dec = J.JpegDecoder(ctx)
+    dec.SetInput(blob)
+    dec.Identify()
+    if on_device:
+        dev = ctx.device_alloc(out.nbytes)
+        ctx.h2d(dev, out)
+        dec.SetOutputWriter(J.CudaOutputWriter(dev, fmt, on_device=True, capacity=out.nbytes))
+        dec.Decode()
+        ctx.d2h(out, dev)
+        ctx.device_free(dev)
+    else:
+        dec.SetOutputWriter(J.CudaOutputWriter(out, fmt))
+        dec.Decode()
+
+
+@pytest.mark.parametrize("restart", [dict(restart_rows=1), dict(restart_blocks=7)], ids=["rows", "blocks7"])
+@pytest.mark.parametrize("subsampling", ["4:2:0", "4:4:4"])
+@pytest.mark.parametrize("on_device", [False, True], ids=["host", "device"])
+def test_eoi_at_a_restart_boundary_leaves_the_missing_intervals_unwritten(restart, subsampling, on_device):
+    """JpegHuffmanBaselineScanDecoder.cs:144-150: the scan returns at an EOI that sits where an RSTn would be; WriteBlock is
+    never called for the MCUs of the missing intervals, so whatever the destination held stays there."""
+    blob = bytearray(synth.synth_jpeg(9, 200, 136, subsampling=subsampling, **restart))
+    rst = [i for i in range(len(blob) - 1) if blob[i] == 0xFF and 0xD0 <= blob[i + 1] <= 0xD7]
+    cut = rst[len(rst) * 2 // 3]
+    blob[cut:] = b"\xff\xd9"                     # ends exactly where a restart marker was
+    blob = bytes(blob)
+    o = O.decode(blob)                            # no error
+    wr = O.written_samples(o)
+    assert 0 < wr[0].sum() < wr[0].size and not wr[0, -1].any()
+    assert not o.planes[~wr].any()
+    ctx = J.Context.default()
+    planes = np.full((3, o.height, o.width), 0x5A5A, np.int16)
+    _decode_into(blob, planes, J.JB_OUT_PLANAR_I16, ctx, on_device)
+    assert np.array_equal(planes[wr], o.planes[wr])
+    assert (planes[~wr] == 0x5A5A).all()
+    px = wr.all(axis=0)                           # pixels the application's converter gets all three samples of
+    assert np.array_equal(px, wr.any(axis=0))
+    for fmt, bpp in ((J.JB_OUT_RGB24, 3), (J.JB_OUT_RGBA32, 4), (J.JB_OUT_YCBCR888, 3)):
+        out = np.full((o.height, o.width, bpp), 0xA5, np.uint8)
+        _decode_into(blob, out, fmt, ctx, on_device)
+        want = o.ycbcr if fmt == J.JB_OUT_YCBCR888 else o.rgb
+        assert np.array_equal(out[px][:, :3], want[px])
+        assert (out[~px] == 0xA5).all()
 
 
 # ------------------------------------------------------------------------------------------ progressive
@@ -284,6 +342,7 @@ def test_progressive_golden_assets(name, golden):
     blob = golden_bytes(name)
     o = check_progressive_coefficients(blob)
     planes = gpu_planes(blob)
+    assert hashlib.sha256(reference_golden16(planes, golden["assets"][name]["precision"]).tobytes()).hexdigest() == golden["assets"][name]["golden16_sha256"]
     assert hashlib.sha256(np.ascontiguousarray(planes).tobytes()).hexdigest() == golden["assets"][name]["planes_i16_sha256"]
     assert np.array_equal(planes, o.planes)
     o = O.decode(blob)
@@ -442,6 +501,7 @@ def test_lossless_golden_assets_bit_exact(name, golden):
     """SOF3 output must be bit-exact (north_star): predictors 1..7 of the reference's own assets."""
     blob = golden_bytes(name)
     planes = gpu_planes(blob)
+    assert hashlib.sha256(reference_golden16(planes, golden["assets"][name]["precision"]).tobytes()).hexdigest() == golden["assets"][name]["golden16_sha256"]
     assert hashlib.sha256(np.ascontiguousarray(planes).tobytes()).hexdigest() == golden["assets"][name]["planes_i16_sha256"]
     o = O.decode(blob)
     assert np.array_equal(planes, o.planes)

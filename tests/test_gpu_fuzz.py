@@ -179,3 +179,33 @@ def test_corrupted_headers_decode_like_the_reference(name):
             problems.append(f"trial {trial}: GPU raised [{type(gerr).__name__}: {gerr}] but the oracle decoded")
     print(f"{name}: {agree_ok} identical decodes, {agree_err} errors on both sides, {len(problems)} disagreements")
     assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("shape", [dict(blocks_w=6, blocks_h=4), dict(blocks_w=9, blocks_h=7, dri=5), dict(blocks_w=11, blocks_h=6, dri=11),
+                                   dict(blocks_w=64, blocks_h=48)], ids=["one-segment", "dri5", "dri-rows", "self-sync"])
+def test_final_code_in_the_padding_is_accepted_like_the_reference(shape):
+    """DecodeHuffmanCode advances min(code size, bits available) and never fails; only magnitude bits that are not there
+    are "The bit stream ended prematurely." (JpegHuffmanScanDecoder.cs:81-110).  Streams whose tables use the all-ones
+    codes, cut short by 0..12 bytes at the end of the scan or of one restart interval: every verdict and every decoded
+    sample must be the oracle's (restart segments: K1; no restart markers and >= 1 KiB: the self-synchronising chain)."""
+    accepted = rejected = 0
+    intervals = [None] if not shape.get("dri") else [None, 0, 3]
+    for seed in range(3):
+        for iv in intervals:
+            for cut in range(0, 13):
+                blob, coef = synth.handmade_grey(seed=seed, cut=cut, cut_interval=iv, **shape)
+                want, werr = run_oracle(blob)
+                got, gerr = run_gpu(blob)
+                where = f"seed {seed} interval {iv} cut {cut}"
+                if werr is None:
+                    assert gerr is None, f"{where}: GPU raised [{type(gerr).__name__}: {gerr}] but the oracle decoded"
+                    assert np.array_equal(got, want.planes), where
+                    if cut == 0:
+                        assert np.array_equal(O.scan_order_coefficients(want).reshape(-1, 64), coef)
+                    accepted += 1
+                else:
+                    assert gerr is not None, f"{where}: oracle raised [{werr}] but the GPU decoded"
+                    assert isinstance(gerr, {-1: J.InvalidDataException, -2: J.InvalidOperationException}[werr.code]), where
+                    rejected += 1
+    print(f"{accepted} streams accepted, {rejected} rejected, on both sides")
+    assert accepted > 13 * len(intervals)  # cut streams among them
