@@ -466,6 +466,25 @@ class JpegPipelinedBatchDecoder:
         self.contexts = contexts or [Context(0), Context(0)]
         self.chunk = chunk
         self.parse_threads = parse_threads
+        self.reset_stats()
+
+    def reset_stats(self):
+        """per-phase wall-clock seconds, summed over chunks (and over the worker threads)"""
+        self.stats = {"walk": 0.0, "parser_blocked": 0.0, "worker_idle": 0.0, "create": 0.0, "upload_launch": 0.0,
+                      "finish_wait": 0.0, "destroy": 0.0, "chunks": 0}
+
+    def stats_summary(self, wall_seconds):
+        """phase times as fractions of the wall-clock time of the decode() calls since reset_stats(): walk and
+        parser_blocked belong to the one parser thread, the others are averaged over the worker threads"""
+        w = max(1, len(self.contexts))
+        s = self.stats
+        per = {k: s[k] / wall_seconds for k in ("walk", "parser_blocked")}
+        per.update({k: s[k] / w / wall_seconds for k in ("worker_idle", "create", "upload_launch", "finish_wait", "destroy")})
+        return {"fraction_of_wall": {k: round(v, 4) for k, v in per.items()}, "chunks": s["chunks"], "workers": w,
+                "meaning": "walk: marker walk of the next chunks; parser_blocked: parsed chunks waiting for a free worker; "
+                           "create: descriptors + jb_decode_batch_create (tables, plan, allocations); upload_launch: enqueue "
+                           "H2D + kernels; finish_wait: waiting for H2D + kernels + D2H of the chunk (the GPU / PCIe time); "
+                           "worker_idle: worker waiting for a parsed chunk"}
 
     def decode(self, blobs, host_out, format=N.JB_OUT_RGB24):
         """Decode `blobs` into the (pinned) uint8 array `host_out`; image i lands at self.offsets[i].
@@ -481,12 +500,16 @@ class JpegPipelinedBatchDecoder:
         offsets = [0] * n
         ready = queue.Queue(maxsize=2 * len(self.contexts))  # parsed chunks, in order: (first, last, handles, start, end)
 
+        import time as _time
+        st = self.stats
+
         def parser():
             # One marker walk per stream (host threads), running ahead of the GPU workers: a chunk's place in the
             # output follows from the frame sizes of everything in front of it.
             off = 0
             try:
                 for a, b in chunks:
+                    t0 = _time.perf_counter()
                     m = b - a
                     ptrs = (C.c_void_p * m)(*[x.ctypes.data for x in bufs[a:b]])
                     lens = (C.c_uint64 * m)(*[x.size for x in bufs[a:b]])
@@ -506,7 +529,11 @@ class JpegPipelinedBatchDecoder:
                         for h in handles:
                             N.host.jbh_free(h)
                         raise ArgumentException("Destination buffer is too small.")
+                    t1 = _time.perf_counter()
                     ready.put((a, b, handles, start, off))
+                    t2 = _time.perf_counter()
+                    st["walk"] += t1 - t0
+                    st["parser_blocked"] += t2 - t1
                     if errors:
                         break
             except Exception as e:  # noqa: BLE001 - reported to the caller below
@@ -519,7 +546,9 @@ class JpegPipelinedBatchDecoder:
         def worker(w):
             ctx = self.contexts[w]
             while True:
+                t0 = _time.perf_counter()
                 item = ready.get()
+                t1 = _time.perf_counter()
                 if item is None:
                     return
                 a, b, handles, start, end = item
@@ -528,9 +557,26 @@ class JpegPipelinedBatchDecoder:
                         N.host.jbh_free(h)
                     continue
                 try:
-                    with JpegBatchDecoder(bufs[a:b], format, context=ctx, device_output=False,
-                                          host_outputs=host_out[start:end], parsed=handles) as d:
-                        d.run()
+                    d = JpegBatchDecoder(bufs[a:b], format, context=ctx, device_output=False,
+                                         host_outputs=host_out[start:end], parsed=handles)
+                    try:
+                        t2 = _time.perf_counter()
+                        d.upload()
+                        d.launch()
+                        t3 = _time.perf_counter()
+                        d.finish()
+                        t4 = _time.perf_counter()
+                    finally:
+                        t5 = _time.perf_counter()
+                        d.close()
+                    t6 = _time.perf_counter()
+                    with lock:
+                        st["worker_idle"] += t1 - t0
+                        st["create"] += t2 - t1
+                        st["upload_launch"] += t3 - t2
+                        st["finish_wait"] += t4 - t3
+                        st["destroy"] += t6 - t5
+                        st["chunks"] += 1
                 except Exception as e:  # noqa: BLE001 - reported to the caller below
                     with lock:
                         errors.append(e)

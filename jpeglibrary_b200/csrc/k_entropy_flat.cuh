@@ -186,6 +186,9 @@ __device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32
 // JB_K1F_TABLES distinct tables reads the others through the read-only path.
 // The CTA size is chosen at launch so that all segments of a batch are resident in one wave when possible.
 // ---------------------------------------------------------------------------------------------
+#ifndef JB_K1_SYMBOLS_PER_ROUND
+#define JB_K1_SYMBOLS_PER_ROUND 2
+#endif
 #define JB_K1F_MAX_THREADS 1024
 #define JB_K1F_TABLES 4
 #define JB_K1F_TABLE_WORDS (JB_LUT_SIZE + JB_LUT2_SUBTABLES * 64)
@@ -402,40 +405,55 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                 wnext = wnext2;
                 wnext2 = __ldg(arena_words + wabs + 1);
             }
-            const bool is_dc = k == 0;
-            const uint32_t toff = is_dc ? tdc : tac;
-            uint32_t e = 0;
-            if (toff != JB_K1F_NOTAB) e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
-            if ((e & 0xFFu) == 0) {
-                uint32_t e2 = 0;
-                if (e != 0 && e != JB_E32_BADLUT) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
-                if (e2 == 0) { // table not cached, a code longer than 16 bits / not in the second level, or a bad symbol
-                    const uint4 gi = __ldg(&im->binfo[b]);
-                    const uint32_t goff = is_dc ? gi.x : gi.y;
-                    if (toff == JB_K1F_NOTAB) e = __ldg(tab_words + goff + (hi >> (32 - JB_LUT_BITS)));
-                    e2 = (e & 0xFFu) ? e : jb_huff32_escape(reinterpret_cast<const JbHuffTable32 *>(tab_words + goff), e, hi >> 16);
+            // One symbol.  FIRST: the symbol behind the refill (DC when k == 0).  The second call of an iteration is an
+            // AC symbol by construction (k > 0), so everything that concerns DC folds away there.
+            auto symbol = [&](const bool FIRST) {
+                const bool is_dc = FIRST && k == 0;
+                const uint32_t toff = is_dc ? tdc : tac;
+                uint32_t e = 0;
+                if (toff != JB_K1F_NOTAB) e = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
+                if ((e & 0xFFu) == 0) {
+                    uint32_t e2 = 0;
+                    if (e != 0 && e != JB_E32_BADLUT) e2 = s_tab[toff + JB_LUT_SIZE + ((e >> 8) - 1) * 64 + ((hi >> 16) & 63)];
+                    if (e2 == 0) { // table not cached, a code longer than 16 bits / not in the second level, or a bad symbol
+                        const uint4 gi = __ldg(&im->binfo[b]);
+                        const uint32_t goff = is_dc ? gi.x : gi.y;
+                        if (toff == JB_K1F_NOTAB) e = __ldg(tab_words + goff + (hi >> (32 - JB_LUT_BITS)));
+                        e2 = (e & 0xFFu) ? e : jb_huff32_escape(reinterpret_cast<const JbHuffTable32 *>(tab_words + goff), e, hi >> 16);
+                    }
+                    e = e2;
+                    if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
+                        err |= JB_ST_BAD_CODE;
+                        e = is_dc ? 0x01000101u : 0x40000101u;
+                    }
                 }
-                e = e2;
-                if (e == JB_E32_BAD) { // invalid code or magnitude category: flag, then finish the block
-                    err |= JB_ST_BAD_CODE;
-                    e = is_dc ? 0x01000101u : 0x40000101u;
-                }
-            }
-            const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
-            const uint32_t s = total - len;
-            // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
-            const uint32_t x = __funnelshift_l(lo, hi, len);
-            const uint32_t neg = ~(uint32_t)((int32_t)x >> 31); // all ones when the leading magnitude bit is 0
-            const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
-            int v = (int)((t ^ neg) - neg);
-            hi = __funnelshift_lc(lo, hi, total);
-            lo = __funnelshift_lc(0u, lo, total);
-            n -= (int)total;
-            under |= n & (int)(len - total); // sign bit: magnitude bits (s > 0) that end behind the data (n < 0)
-            const uint32_t pos = min(k + run, 63u);
-            if (is_dc) { v += pred; pred = v; }
-            if ((s != 0 || is_dc) && !(CLEAN && skip)) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
-            k += adv;
+                const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
+                const uint32_t s = total - len;
+                // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
+                const uint32_t x = __funnelshift_l(lo, hi, len);
+                const uint32_t neg = ~(uint32_t)((int32_t)x >> 31); // all ones when the leading magnitude bit is 0
+                const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+                int v = (int)((t ^ neg) - neg);
+                hi = __funnelshift_lc(lo, hi, total);
+                lo = __funnelshift_lc(0u, lo, total);
+                n -= (int)total;
+                under |= n & (int)(len - total); // sign bit: magnitude bits (s > 0) that end behind the data (n < 0)
+                const uint32_t pos = min(k + run, 63u);
+                if (is_dc) { v += pred; pred = v; }
+                if ((s != 0 || is_dc) && !(CLEAN && skip)) *reinterpret_cast<int16_t *>(st + pos * 2) = (int16_t)v;
+                k += adv;
+            };
+            symbol(true);
+#if JB_K1_SYMBOLS_PER_ROUND >= 2
+            // A second symbol in the same round when the block is not finished and the window still holds 32 bits (the
+            // guarantee the refill gives the first one).  A warp pays for the refill and the block hand-off of a round
+            // whatever the number of lanes that need them, so symbols per round is what the instruction count hangs on
+            // (profiles/r2*_decode: 146 -> ... warp-instructions per 32 symbols).
+            if (k < 64 && n >= need) symbol(false);
+#endif
+#if JB_K1_SYMBOLS_PER_ROUND >= 3
+            if (k < 64 && n >= need) symbol(false);
+#endif
         }
         // ---- completed blocks leave the SM as full 128-byte lines: lanes 8g..8g+7 move the g-th finished lane's block
         const bool finished = k >= 64;

@@ -553,8 +553,10 @@ jb_k1b_scan(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
         x.nblk = (uint32_t)s_carry[0]; x.dc[0] = s_carry[1]; x.dc[1] = s_carry[2]; x.dc[2] = s_carry[3]; x.dc[3] = s_carry[4];
         a[nsub] = x;
     }
-    // fewer blocks in the stream than the frame needs => "The bit stream ended prematurely."
-    if (tid == 0 && (uint32_t)s_carry[0] < im.total_mcus * im.bpm) atomicOr(status + image, JB_ST_PREMATURE_END);
+    // (Fewer blocks in the stream than the frame needs is not an error by itself: the reference decodes on behind the
+    // data, where PeekBits supplies 1-bits, and only fails on a symbol whose magnitude bits are not there
+    // (JpegHuffmanScanDecoder.cs:81-110).  The last sub-sequence of the final pass does the same, see jb_k1b_descs.)
+    (void)status;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -573,7 +575,8 @@ jb_k1b_descs(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     const uint32_t sub = blockIdx.x * 256 + threadIdx.x;
     if (sub >= im.sub_cap) return;
     const uint32_t total_bits = clean_len[image] * 8;
-    const uint32_t nsub = (uint32_t)(((uint64_t)total_bits + (1u << sub_shift) - 1) >> sub_shift);
+    // (a stream of fill bytes only leaves no bits at all: its one sub-sequence decodes the frame from the padding)
+    const uint32_t nsub = max(1u, (uint32_t)(((uint64_t)total_bits + (1u << sub_shift) - 1) >> sub_shift));
     const uint32_t gi = im.sub_base + sub;
     const uint32_t total_blocks = im.total_mcus * im.bpm;
     JbSegDesc d;
@@ -585,7 +588,9 @@ jb_k1b_descs(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
         if (sub == 0) { entry.p = 0; entry.bk = 0; }
         else entry = exits[gi - 1];
         const JbSubInfo base = info[gi], next = info[gi + 1]; // exclusive prefixes; slot nsub holds the totals
-        const uint32_t first = min(base.nblk, total_blocks), last = min(next.nblk, total_blocks);
+        // the last sub-sequence decodes whatever the frame still needs: behind the data the window holds 1-bits like the
+        // reference's PeekBits, and K1's per-symbol verdict decides whether that is an error
+        const uint32_t first = min(base.nblk, total_blocks), last = sub + 1 == nsub ? total_blocks : min(next.nblk, total_blocks);
         const uint32_t k = entry.bk & 0xFFu;
         const bool skip = k != 0 && sub != 0;
         const uint64_t bit0 = im.data_off * 8 + entry.p;

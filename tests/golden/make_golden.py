@@ -33,6 +33,9 @@ FILES = [
     "huffman_progressive/progress.jpg",
     "huffman_progressive/yellowcat_progressive_restart.jpg",
 ] + ["huffman_lossless/lossless%d_s22.jpg" % i for i in range(1, 8)]
+# inputs without a golden buffer in the reference: HETissueSlide.jpg is the asset of the reference's own benchmark
+# (tests/JpegLibrary.Benchmarks/DecoderBenchmark.cs:19-43) and of BASELINE.json configs[0]
+INPUT_ONLY = ["baseline/HETissueSlide.jpg"]
 IDENTIFY = {  # MetadataIdentifyTests.cs
     "cramps.jpg": dict(Width=800, Height=607, NumberOfComponents=1, Precision=8, JpegStreamSize=137766),
     "testorig12.jpg": dict(Width=227, Height=149, NumberOfComponents=3, Precision=12, JpegStreamSize=12394),
@@ -77,6 +80,10 @@ def main():
             "negative_samples": int((d.planes < 0).sum()),
         }
         print(rel, "oracle == reference golden (0 mismatches of %d samples)" % gold.size)
+    for rel in INPUT_ONLY:
+        name = os.path.basename(rel)
+        shutil.copyfile(os.path.join(ASSETS, rel), os.path.join(HERE, name))
+        os.chmod(os.path.join(HERE, name), 0o644)
     json.dump(out, open(os.path.join(HERE, "golden.json"), "w"), indent=1, sort_keys=True)
 
 

@@ -251,9 +251,18 @@ def test_caller_tables_on_noise_outgrow_the_reserved_stream_space():
     and runs again, instead of failing a frame the reference encodes."""
     rng = np.random.default_rng(3)
     rgb = rng.integers(0, 256, (512, 512, 3), dtype=np.uint8)
-    std = J.Parsed(synth.encode_jpeg(rgb[:64, :64], quality=90, subsampling="4:4:4")).desc  # libjpeg writes the Annex-K tables
-    specs = {(std.tables[i].table_class, std.tables[i].identifier): std.tables[i] for i in range(std.table_count)}
-    assert len(specs) == 4
+    parsed = J.Parsed(synth.encode_jpeg(rgb[:64, :64], quality=90, subsampling="4:4:4"))  # libjpeg writes the Annex-K tables
+    std, specs = parsed.desc, {}
+    for i in range(std.table_count):
+        s = J._native.HuffSpec()
+        C.memmove(C.byref(s), C.byref(std.tables[i]), C.sizeof(s))  # (the descriptor's memory belongs to `parsed`)
+        specs[(s.table_class, s.identifier)] = s
+    assert sorted(specs) == [(0, 0), (0, 1), (1, 0), (1, 1)]
+    for ident in (0, 1):  # a caller may install any table: these give the most frequent symbols the 16-bit codes
+        t = specs[(1, ident)]
+        vals = list(t.values[:t.value_count])[::-1]
+        for i, v in enumerate(vals):
+            t.values[i] = v
     enc = J.JpegEncoder()
     enc.SetQuantizationTable(J.JpegStandardQuantizationTable.ScaleByQuality(J.JpegStandardQuantizationTable.GetLuminanceTable(0, 0), 100))
     enc.SetQuantizationTable(J.JpegStandardQuantizationTable.ScaleByQuality(J.JpegStandardQuantizationTable.GetChrominanceTable(0, 1), 100))
