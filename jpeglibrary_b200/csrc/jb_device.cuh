@@ -72,8 +72,11 @@ struct __align__(16) JbDevImage {
     uint32_t comp_plane_w[4];       // blocks per row of each plane
     uint32_t covered;               // scan-list frames: bit c = some scan names component c.  The reference's sequential
                                     // decoder never calls WriteBlock for the others: their samples stay 0
-    // lossless (SOF3): predictor selection Ss and 2^(P-Pt-1); planes reuse comp_plane_off (x64 samples) / comp_plane_w (samples per row)
-    int32_t ll_predictor, ll_initial;
+    // lossless (SOF3): planes reuse comp_plane_off (x64 samples) / comp_plane_w (samples per row); every SOS is a JbDevScan
+    // (scan_base, nscans; ss = predictor selection, al = point transform); ll_comp_scan[c] = the LAST scan that names
+    // component c (0xFF: none) -- the reference decodes scan by scan into the same scanline store, later scans win
+    uint8_t ll_comp_scan[4];
+    int32_t ll_reserved;
     // coefficient store
     uint64_t coef_off;   // first block of this image in the coefficient store (in blocks)
     uint32_t quant_off;  // first of ncomp quant tables (64 x uint16 each) in the quant array

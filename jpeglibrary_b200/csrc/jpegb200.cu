@@ -412,7 +412,7 @@ struct jb_batch {
     uint32_t ss_list_off = 0, seg_list_off = 0;
     // lossless frames (SOF3)
     std::vector<uint32_t> ll_images;
-    uint32_t ll_list_off = 0, ll_max_nseg = 1, ll_max_pixels = 0;
+    uint32_t ll_list_off = 0, ll_max_nseg = 1, ll_max_pixels = 0, ll_max_scans = 0;
     uint32_t ss_max_sub = 0;
     uint64_t ss_total_sub = 0;
     uint8_t *d_clean = nullptr;
@@ -893,11 +893,10 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
 {
     JbDevImage &d = pl.dev;
     if (im.precision < 2 || im.precision > 16) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad sample precision");
-    if (im.scan_count != 1 || !im.scans || im.scans[0].component_count < 1 || im.scans[0].component_count > im.component_count)
-        return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "lossless frames must consist of one interleaved scan");
+    if (im.scan_count < 1 || !im.scans) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "no scans");
+    if (im.scan_count > 64) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "more than 64 scans in a lossless frame");
     if (outp && outp->format == JB_OUT_COEFFICIENTS)
         return fail(ctx, JB_ERR_ARGUMENT, "image %d: %s", idx, "lossless frames have no DCT coefficients");
-    const jb_scan_desc &sc = im.scans[0];
     int hmax = 1, vmax = 1;
     for (int c = 0; c < im.component_count; c++) {
         if (im.h[c] < 1 || im.h[c] > 4 || im.v[c] < 1 || im.v[c] > 4)
@@ -910,10 +909,6 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
     d.mcus_per_line = (im.width + hmax - 1) / hmax;   // :33-34: one MCU = hmax x vmax samples
     d.mcus_per_col = (im.height + vmax - 1) / vmax;
     d.total_mcus = d.mcus_per_line * d.mcus_per_col;
-    d.ll_predictor = sc.ss;
-    // 1 << (P - Pt - 1) as C# evaluates it (JpegHuffmanLosslessScanDecoder.cs:81): the shift count is taken modulo 32, so a
-    // damaged Pt >= P yields a value whose low 16 bits are 0 instead of an error
-    d.ll_initial = (int32_t)(1u << ((im.precision - sc.al - 1) & 31));
     uint64_t blocks = 0;
     for (int c = 0; c < im.component_count; c++) {
         if (hmax % im.h[c] || vmax % im.v[c])
@@ -927,51 +922,59 @@ static int plan_lossless(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb
         d.comp_plane_off[c] = (uint32_t)blocks;
         d.comp_plane_w[c] = w;
         d.comp_h[c] = im.h[c]; d.comp_v[c] = im.v[c];
+        d.ll_comp_scan[c] = 0xFF; // components no scan names keep the allocator's zeros
         blocks += ((uint64_t)w * h + 63) / 64;
     }
     pl.total_blocks = blocks;
-    int bpm = 0;
-    std::map<int, int> slot_of_table;
-    bool seen[JB_MAX_COMPONENTS] = {false, false, false, false};
-    d.covered = 0; // components the scan does not name keep the allocator's zeros
-    for (int i = 0; i < sc.component_count; i++) {
-        const int c = sc.component_index[i];
-        if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
-        // (a component named twice is decoded twice per MCU, the second pass over the first: the later differences win)
-        seen[c] = true;
-        d.covered |= 1u << c;
-        d.comp_blk_off[c] = (uint8_t)bpm;
-        const int gid = intern_table(im, sc.dc_table[i], 0, tables, table_ids);
-        if (gid == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
-        if (gid < 0) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
-        auto it = slot_of_table.find(gid);
-        int slot;
-        if (it == slot_of_table.end()) {
-            slot = (int)slot_of_table.size();
-            if (slot >= JB_MAX_TABLE_SLOTS) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "too many tables");
-            d.table_index[slot] = (uint16_t)gid;
-            slot_of_table[gid] = slot;
-        } else
-            slot = it->second;
-        for (int k = 0; k < im.h[c] * im.v[c]; k++) {
-            if (bpm >= JB_MAX_BLOCKS_PER_MCU) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "MCU too large");
-            d.blk_comp[bpm] = (uint8_t)c;
-            d.blk_dc[bpm] = (uint8_t)slot;
-            d.blk_ac[bpm] = (uint8_t)k; // lossless frames have no AC tables: the sample's place inside the MCU
-            bpm++;
-        }
+    d.covered = 0;
+    d.bpm = 1; d.ntables = 0;
+    d.dri = 0; d.nseg = 1; d.mark_cap = 0; d.use_selfsync = 0;
+    // The reference decodes scan by scan into one scanline store (JpegHuffmanLosslessScanDecoder.ProcessScan :52-205, one
+    // call per SOS): every scan is a JbDevScan here, entropy-decoded in scan order; the predictor pass then reconstructs
+    // every component with the parameters of the last scan that names it.  The whole tail of the file from the first
+    // scan on is staged once; scans point into it.
+    uint64_t lo = im.length, hi = 0;
+    for (uint32_t si = 0; si < im.scan_count; si++) {
+        const jb_scan_desc &sc = im.scans[si];
+        if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
+        const uint64_t len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
+                                               : im.length - sc.entropy_offset;
+        lo = std::min(lo, sc.entropy_offset);
+        hi = std::max(hi, sc.entropy_offset + len);
     }
-    d.bpm = (uint8_t)bpm;
-    d.ntables = (uint8_t)slot_of_table.size();
-    d.dri = sc.restart_interval;
-    d.nseg = d.dri ? (d.total_mcus + d.dri - 1) / d.dri : 1;
-    d.mark_cap = d.nseg + 1;
-    if (sc.entropy_offset >= im.length) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "scan data missing");
-    pl.entropy_off = sc.entropy_offset;
-    pl.entropy_len = sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
-                                       : im.length - sc.entropy_offset;
-    if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scan larger than 256 MiB");
+    pl.entropy_off = lo;
+    pl.entropy_len = hi - lo;
+    if (pl.entropy_len >= (1ull << 28)) return fail(ctx, JB_ERR_NOT_SUPPORTED, "image %d: %s", idx, "scans larger than 256 MiB");
     d.data_len = (uint32_t)pl.entropy_len;
+    for (uint32_t si = 0; si < im.scan_count; si++) {
+        const jb_scan_desc &sc = im.scans[si];
+        if (sc.component_count < 1 || sc.component_count > JB_MAX_COMPONENTS)
+            return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
+        JbDevScan ds{};
+        ds.ncomp = sc.component_count;
+        ds.ss = sc.ss; ds.se = sc.se; ds.ah = sc.ah; ds.al = sc.al; // ss: predictor selection, al: point transform
+        for (int i = 0; i < sc.component_count; i++) {
+            const int c = sc.component_index[i];
+            if (c >= im.component_count) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "bad scan component");
+            // (a component named twice in one scan is decoded twice per MCU, the second pass over the first)
+            ds.comp[i] = (uint8_t)c;
+            d.covered |= 1u << c;
+            d.ll_comp_scan[c] = (uint8_t)si;
+            const int gid = intern_table(im, sc.dc_table[i], 0, tables, table_ids);
+            if (gid == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
+            if (gid < 0) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Huffman table of component is not defined.");
+            ds.dc_tab[i] = (uint16_t)gid;
+            ds.ac_tab[i] = 0xFFFF;
+        }
+        ds.nunits = d.total_mcus;
+        ds.dri = sc.restart_interval;
+        ds.nseg = ds.dri ? (ds.nunits + ds.dri - 1) / ds.dri : 1;
+        ds.data_len = (uint32_t)(sc.entropy_length ? std::min<uint64_t>(sc.entropy_length + 2, im.length - sc.entropy_offset)
+                                                   : im.length - sc.entropy_offset);
+        pl.scan_host_off.push_back(sc.entropy_offset - lo);
+        pl.scans.push_back(ds);
+    }
+    d.nscans = (uint32_t)pl.scans.size();
     return plan_output(ctx, idx, im, outp, pl);
 }
 
@@ -1172,7 +1175,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             b->prog_images.push_back((uint32_t)i);
         } else if (pl.dev.sof == 3) {
             b->ll_images.push_back((uint32_t)i);
-            b->ll_max_nseg = std::max(b->ll_max_nseg, pl.dev.nseg);
+            b->ll_max_scans = std::max<uint32_t>(b->ll_max_scans, (uint32_t)pl.scans.size());
             b->ll_max_pixels = std::max<uint32_t>(b->ll_max_pixels, (uint32_t)pl.dev.width * pl.dev.height);
         } else if (pl.dev.use_selfsync) {
             b->ss_images.push_back((uint32_t)i);
@@ -1227,7 +1230,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         ImagePlan &pl = b->plans[i];
         JbScanRange &r = b->h_ranges[i];
         r = JbScanRange{};
-        if (!(pl.dev.planar && pl.dev.sof != 3)) {
+        if (!pl.dev.planar && pl.dev.sof != 3) { // (scan-list and lossless frames: one range per scan, below)
             r.data_off = pl.dev.data_off; r.data_len = pl.dev.data_len;
             r.mark_base = pl.dev.mark_base; r.mark_cap = pl.dev.mark_cap;
         }
@@ -1254,6 +1257,22 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         }
     }
     b->prog_coef_blocks = blocks - b->prog_coef_first;
+    for (uint32_t i : b->ll_images) { // lossless frames: per-scan K0 ranges and marker slots
+        ImagePlan &pl = b->plans[i];
+        pl.dev.scan_base = (uint32_t)b->h_scans.size();
+        for (size_t k = 0; k < pl.scans.size(); k++) {
+            JbDevScan ds = pl.scans[k];
+            ds.data_off = pl.dev.data_off + pl.scan_host_off[k];
+            ds.range = (uint32_t)b->h_ranges.size();
+            ds.mark_base = (uint32_t)marks;
+            JbScanRange r{};
+            r.data_off = ds.data_off; r.data_len = ds.data_len; r.mark_base = ds.mark_base; r.mark_cap = ds.nseg + 1;
+            marks += r.mark_cap;
+            b->h_ranges.push_back(r);
+            b->h_scans.push_back(ds);
+            b->ll_max_nseg = std::max(b->ll_max_nseg, ds.nseg);
+        }
+    }
     {
         // K1c job order.  weight(scan) = its bytes + the heaviest consumer's weight, so a producer always outweighs
         // its consumers: ranking the scans of an image by falling weight is a topological order that starts the
@@ -1345,10 +1364,12 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(cudaMemcpyAsync(b->d_ranges, b->h_ranges.data(), sizeof(JbScanRange) * b->h_ranges.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!b->h_scans.empty()) {
         JB_CUDA_B(cudaMemcpyAsync(b->d_scans, b->h_scans.data(), sizeof(JbDevScan) * b->h_scans.size(), cudaMemcpyHostToDevice, ctx->stream));
-        JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_jobs, sizeof(JbProgJob) * b->h_prog_jobs.size()));
-        JB_CUDA_B(cudaMemcpyAsync(b->d_prog_jobs, b->h_prog_jobs.data(), sizeof(JbProgJob) * b->h_prog_jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
-        JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_lanes, sizeof(JbProgLane) * b->h_prog_lanes.size()));
-        JB_CUDA_B(cudaMemcpyAsync(b->d_prog_lanes, b->h_prog_lanes.data(), sizeof(JbProgLane) * b->h_prog_lanes.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (!b->h_prog_jobs.empty()) { // (lossless frames have scans but no K1c jobs)
+            JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_jobs, sizeof(JbProgJob) * b->h_prog_jobs.size()));
+            JB_CUDA_B(cudaMemcpyAsync(b->d_prog_jobs, b->h_prog_jobs.data(), sizeof(JbProgJob) * b->h_prog_jobs.size(), cudaMemcpyHostToDevice, ctx->stream));
+            JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_lanes, sizeof(JbProgLane) * b->h_prog_lanes.size()));
+            JB_CUDA_B(cudaMemcpyAsync(b->d_prog_lanes, b->h_prog_lanes.data(), sizeof(JbProgLane) * b->h_prog_lanes.size(), cudaMemcpyHostToDevice, ctx->stream));
+        }
         JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_progress, sizeof(uint32_t) * (b->h_scans.size() + 1)));
     }
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
@@ -1535,12 +1556,15 @@ static int launch_kernels(jb_batch *b)
         const unsigned nimg = (unsigned)b->ll_images.size();
         const int lanes = b->ll_max_nseg > 1 ? 32 : 1;
         dim3 grid((b->ll_max_nseg + lanes - 1) / lanes, nimg);
-        jb_k1d_lossless_entropy<<<grid, 32, 0, st>>>(b->d_images, list, b->d_tables, b->d_arena, b->d_marks, b->d_scan, b->d_coef,
-                                                    b->d_status, lanes);
-        jb_k1d_lossless_predict<<<nimg, 32 * JB_MAX_COMPONENTS_DEV, 0, st>>>(b->d_images, list, b->d_marks, b->d_scan, b->d_coef);
+        for (uint32_t z = 0; z < b->ll_max_scans; z++) { // scan by scan: a later scan over the same component replaces the earlier one
+            jb_k1d_lossless_entropy<<<grid, 32, 0, st>>>(b->d_images, b->d_scans, list, z, b->d_tables, b->d_arena, b->d_marks, b->d_scan,
+                                                        b->d_coef, b->d_status, lanes);
+            launches++;
+        }
+        jb_k1d_lossless_predict<<<nimg, 32 * JB_MAX_COMPONENTS_DEV, 0, st>>>(b->d_images, b->d_scans, list, b->d_marks, b->d_scan, b->d_coef);
         dim3 ogrid((b->ll_max_pixels + 255) / 256, nimg);
         jb_k5_lossless_output<<<ogrid, 256, 0, st>>>(b->d_images, list, b->d_coef);
-        launches += 3;
+        launches += 2;
         mark("jb_k1d_lossless");
     }
     launch_render(b, &launches);
@@ -1693,6 +1717,18 @@ int jb_decode_batch_finish(jb_batch *b)
     // copied back, which needs the per-image MCU limit first (one extra wait for the kernels, batches with restart
     // intervals and host destinations only).
     if (b->may_truncate) JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // Whole results that lie back to back in the staging area AND at the destination leave as one copy: a batch that
+    // decodes into one pinned slab (JpegBatchDecoder, the pipelined decoder's chunks) needs one cudaMemcpyAsync instead
+    // of one per image (each costs ~10 us of copy-engine set-up: 2-3 % of the PCIe time of a 4K frame).
+    const uint8_t *run_src = nullptr;
+    uint8_t *run_dst = nullptr;
+    uint64_t run_len = 0;
+    auto flush_run = [&]() -> cudaError_t {
+        cudaError_t e = cudaSuccess;
+        if (run_len) e = cudaMemcpyAsync(run_dst, run_src, run_len, cudaMemcpyDeviceToHost, ctx->stream);
+        run_len = 0;
+        return e;
+    };
     for (int i = 0; i < b->count; i++) {
         const ImagePlan &pl = b->plans[i];
         const void *src = pl.dev_out;
@@ -1704,9 +1740,19 @@ int jb_decode_batch_finish(jb_batch *b)
             const uint32_t limit = b->may_truncate ? b->h_mailbox[b->count + 1 + i] : 0xFFFFFFFFu;
             const JbDevImage &d = pl.dev;
             if (limit >= d.total_mcus) {
-                JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, src, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                const uint8_t *s8 = static_cast<const uint8_t *>(src);
+                uint8_t *d8 = static_cast<uint8_t *>(pl.out.dst);
+                // (staging slots start 256-byte aligned: the gap to the next slot is part of the run when the
+                // destinations are spaced the same way)
+                if (run_len && s8 >= run_src + run_len && s8 - run_src == d8 - run_dst && (uint64_t)(s8 - run_src) - run_len < 256)
+                    run_len = (uint64_t)(s8 - run_src) + pl.out_bytes;
+                else {
+                    JB_CUDA(ctx, flush_run());
+                    run_src = s8; run_dst = d8; run_len = pl.out_bytes;
+                }
                 continue;
             }
+            JB_CUDA(ctx, flush_run());
             // whole MCU rows, then the decoded MCUs of the row the scan ended in; per plane for planar output
             const uint32_t bpp = pl.out.format == JB_OUT_PLANAR_I16 ? 2 : pl.out.format == JB_OUT_RGBA32 ? 4 : 3;
             const uint32_t planes = pl.out.format == JB_OUT_PLANAR_I16 ? d.ncomp : 1;
@@ -1727,6 +1773,7 @@ int jb_decode_batch_finish(jb_batch *b)
             }
         }
     }
+    JB_CUDA(ctx, flush_run());
     JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (!b->ss_images.empty() && b->h_mailbox[b->count] != 0) {
         // the last synchronisation round must not have changed anything; otherwise (sub-sequences that
@@ -1737,6 +1784,9 @@ int jb_decode_batch_finish(jb_batch *b)
         JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     memcpy(b->h_status.data(), b->h_mailbox, sizeof(uint32_t) * b->count);
+    if (getenv("JB_DEBUG_STATUS")) // debugging aid: the raw per-image status words (JB_ST_* bits) and the re-sync flag
+        for (int i = 0; i < b->count; i++)
+            fprintf(stderr, "jb status image %d: 0x%x (last sync round changed %u)\n", i, b->h_status[i], b->h_mailbox[b->count]);
     int first = JB_OK;
     for (int i = 0; i < b->count; i++) {
         uint32_t s = b->h_status[i];

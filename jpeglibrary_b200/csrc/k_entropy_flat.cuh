@@ -187,7 +187,7 @@ __device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32
 // The CTA size is chosen at launch so that all segments of a batch are resident in one wave when possible.
 // ---------------------------------------------------------------------------------------------
 #ifndef JB_K1_SYMBOLS_PER_ROUND
-#define JB_K1_SYMBOLS_PER_ROUND 2
+#define JB_K1_SYMBOLS_PER_ROUND 3
 #endif
 #define JB_K1F_MAX_THREADS 1024
 #define JB_K1F_TABLES 4
@@ -452,6 +452,9 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
             if (k < 64 && n >= need) symbol(false);
 #endif
 #if JB_K1_SYMBOLS_PER_ROUND >= 3
+            if (k < 64 && n >= need) symbol(false);
+#endif
+#if JB_K1_SYMBOLS_PER_ROUND >= 4
             if (k < 64 && n >= need) symbol(false);
 #endif
         }

@@ -4,10 +4,12 @@
 // ReadSampleLossless (:207-223) and the JpegPartialScanlineAllocator flush with pixel replication
 // (JpegPartialScanlineAllocator.cs:103-220).
 //
-//   jb_k1d_lossless_entropy  one thread per (image, restart segment): Huffman-decode the difference of every
+//   jb_k1d_lossless_entropy  one thread per (image, scan, restart segment): Huffman-decode the difference of every
 //                            sample of the segment's MCUs into the component planes (mod 2^16, as the reference's
-//                            (short) cast makes the reconstruction arithmetic modular)
-//   jb_k1d_lossless_predict  one thread per (image, component): raster-order reconstruction with the reference's
+//                            (short) cast makes the reconstruction arithmetic modular).  A frame may hold several
+//                            scans (one per component is the usual non-interleaved form): launched scan index by
+//                            scan index, so that a later scan over the same component replaces the earlier one
+//   jb_k1d_lossless_predict  one warp per (image, component): raster-order reconstruction with the reference's
 //                            predictor selection rules, which are a pure function of the sample position:
 //                            first MCU row or first MCU after a restart -> 1-D/initial rules (:109-139),
 //                            first MCU column -> Rb (:141-144), else predictor Ss (:145-159)
@@ -20,7 +22,8 @@
 #define JB_MAX_COMPONENTS_DEV 4
 
 __global__ void __launch_bounds__(32)
-jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
+                        const uint32_t *__restrict__ image_list, uint32_t scan_index,
                         const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
                         const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
                         int16_t *__restrict__ store, uint32_t *__restrict__ status, int lanes_per_warp)
@@ -28,13 +31,16 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *_
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
     const int lane = threadIdx.x;
-    if (lane >= lanes_per_warp) return;
+    if (lane >= lanes_per_warp || scan_index >= im.nscans) return;
+    const JbDevScan &sc = scans[im.scan_base + scan_index];
     const uint32_t seg = blockIdx.x * lanes_per_warp + lane;
-    if (seg >= im.nseg) return;
-    const JbScanResult sr = scanres[image];
-    const uint32_t *mk = marks + im.mark_base;
+    if (seg >= sc.nseg) return;
+    const JbScanResult sr = scanres[sc.range];
+    const uint32_t *mk = marks + sc.mark_base;
+    // the bit reader wants a 4-byte aligned base: the image's (256-byte aligned) arena slot, scan-relative positions shifted
     const uint8_t *data = arena + im.data_off;
-    const uint32_t per_seg = im.dri ? im.dri : im.total_mcus;
+    const uint32_t rel = (uint32_t)(sc.data_off - im.data_off);
+    const uint32_t per_seg = sc.dri ? sc.dri : im.total_mcus;
     const uint32_t first = seg * per_seg, count = min(per_seg, im.total_mcus - first);
     uint32_t start = 0, err = 0;
     if (seg > 0) {
@@ -46,32 +52,36 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const uint32_t *_
             return;
         }
     }
-    const uint32_t stop = seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos;
+    const uint32_t stop = (seg < sr.nmarkers ? (mk[seg] >> 4) : sr.end_pos) + rel;
+    start += rel;
     JbBitReader br;
     br.init(data, start, stop);
     int16_t *base = store + im.coef_off * 64;
     const uint8_t *tab_base = reinterpret_cast<const uint8_t *>(tables);
     for (uint32_t u = first; u < first + count && !err; u++) {
         const uint32_t row = u / im.mcus_per_line, col = u - row * im.mcus_per_line;
-        for (int b = 0; b < im.bpm; b++) { // blk_comp lists the scan's components, h*v samples each, in scan order
-            const int c = im.blk_comp[b];
-            const int h = im.comp_h[c], bi = im.blk_ac[b]; // sample index inside this occurrence of the component (host)
-            const int x = bi % h, y = bi / h;
-            br.ensure32();
-            uint32_t e = jb_huff_lookup(reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)im.table_index[im.blk_dc[b]] * sizeof(JbHuffTable)),
-                                        br.peek16());
-            if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; break; }
-            br.skip_code(e & 0xFF);
-            const int t = (int)(e >> 8);
-            int d = 0;
-            if (t == 16) d = 32768;
-            else if (t > 16) { err |= JB_ST_BAD_CODE; break; }
-            else if (t != 0) d = jb_extend((int)br.take(t), t);
-            base[(size_t)im.comp_plane_off[c] * 64 + (size_t)(row * im.comp_v[c] + y) * im.comp_plane_w[c] + col * h + x] = (int16_t)d;
+        for (int i = 0; i < sc.ncomp && !err; i++) { // the scan's components in scan order, h x v samples each (:86-100)
+            const int c = sc.comp[i];
+            const int h = im.comp_h[c], v = im.comp_v[c];
+            const JbHuffTable *tab = reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)sc.dc_tab[i] * sizeof(JbHuffTable));
+            int16_t *plane = base + (size_t)im.comp_plane_off[c] * 64;
+            for (int s = 0; s < h * v; s++) {
+                const int x = s % h, y = s / h;
+                br.ensure32();
+                uint32_t e = jb_huff_lookup(tab, br.peek16());
+                if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; break; }
+                br.skip_code(e & 0xFF);
+                const int t = (int)(e >> 8);
+                int d = 0;
+                if (t == 16) d = 32768;
+                else if (t > 16) { err |= JB_ST_BAD_CODE; break; }
+                else if (t != 0) d = jb_extend((int)br.take(t), t);
+                plane[(size_t)(row * v + y) * im.comp_plane_w[c] + col * h + x] = (int16_t)d;
+            }
         }
     }
     if (br.n < br.pad) err |= JB_ST_PREMATURE_END;
-    if (!err && im.dri != 0 && count == per_seg) {
+    if (!err && sc.dri != 0 && count == per_seg) {
         const int real = br.n - br.pad;
         uint32_t p = br.pos;
         while (p < stop && data[p] == 0xFF) p++;
@@ -100,7 +110,8 @@ __device__ __forceinline__ int jb_lossless_px(int predictor, int ra, int rb, int
 // 32 consecutive rows are reconstructed as a wavefront: lane l handles row r0 + l and runs l columns behind lane
 // l - 1, whose last two outputs arrive by shuffle (Rb, Rc); Ra is the lane's own previous output.
 __global__ void __launch_bounds__(32 * JB_MAX_COMPONENTS_DEV)
-jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
+jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
+                        const uint32_t *__restrict__ image_list,
                         const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
                         int16_t *__restrict__ store)
 {
@@ -111,16 +122,21 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const uint32_t *_
     const int h = im.comp_h[c], v = im.comp_v[c];
     const int w = (int)im.comp_plane_w[c], rows = (int)im.mcus_per_col * v, cols = (int)im.mcus_per_line * h;
     int16_t *plane = store + im.coef_off * 64 + (size_t)im.comp_plane_off[c] * 64;
-    if (!((im.covered >> c) & 1u)) { // not in the scan: JpegPartialScanlineAllocator's zeros (the store is not cleared)
+    if (im.ll_comp_scan[c] == 0xFF) { // in no scan: JpegPartialScanlineAllocator's zeros (the store is not cleared)
         const int vs = im.vmax / v, hc = ((int)im.height + vs - 1) / vs;
         for (int i = lane; i < w * hc; i += 32) plane[i] = 0;
         return;
     }
-    const int predictor = im.ll_predictor, initial = im.ll_initial;
-    const uint32_t dri = im.dri, mpl = im.mcus_per_line;
+    // the parameters of the scan that decoded this component (the last one that names it)
+    const JbDevScan &sc = scans[im.scan_base + im.ll_comp_scan[c]];
+    const int predictor = sc.ss;
+    // 1 << (P - Pt - 1) as C# evaluates it (JpegHuffmanLosslessScanDecoder.cs:81): the shift count is taken modulo 32, so a
+    // damaged Pt >= P yields a value whose low 16 bits are 0 instead of an error
+    const int initial = (int)(1u << ((im.precision - sc.al - 1) & 31));
+    const uint32_t dri = sc.dri, mpl = im.mcus_per_line;
     // MCUs of intervals that are not in the stream (EOI at a restart boundary) keep the allocator's zeros
-    uint32_t nrst = scanres[image].nmarkers;
-    if (nrst && (marks[im.mark_base + nrst - 1] & 8u)) nrst--;
+    uint32_t nrst = scanres[sc.range].nmarkers;
+    if (nrst && (marks[sc.mark_base + nrst - 1] & 8u)) nrst--;
     const uint32_t valid = dri ? min(im.total_mcus, (nrst + 1u) * dri) : im.total_mcus;
     for (int r0 = 0; r0 < rows; r0 += 32) {
         const int cy = r0 + lane;

@@ -217,6 +217,28 @@ def synth_lossless(i, width, height, precision=8, predictor=1, point_transform=0
     return blob, full
 
 
+def synth_lossless_scans(i, width, height, scans, precision=8, sampling=None, ncomp=3, restart=0):
+    """SOF3 frame coded as SEVERAL scans (the reference decodes scan by scan into one scanline store,
+    JpegHuffmanLosslessScanDecoder.ProcessScan :52-205).  scans: list of dicts with `components` (frame component
+    indices) and optionally `predictor`.  A component named by two scans is coded twice, with different content; the
+    later scan wins.  One restart interval for the whole frame (the reference's scan decoder reads it once, in its
+    constructor: JpegHuffmanLosslessScanDecoder.cs:32).  Returns (stream, expected int16 planes at full resolution)."""
+    sampling = sampling or [(1, 1)] * ncomp
+    stream, final = None, {}
+    for k, sc in enumerate(scans):
+        blob, full = synth_lossless(i + 17 * k, width, height, precision=precision, predictor=sc.get("predictor", 1),
+                                    sampling=sampling, restart=restart, ncomp=ncomp, scan_components=sc["components"])
+        for c in sc["components"]:
+            final[c] = full[c]
+        if stream is None:
+            stream = bytearray(blob[:-2])                     # SOI, SOF3, DHT, [DRI], SOS, data
+        else:
+            stream += blob[blob.index(b"\xff\xda"):-2]        # SOS header + entropy-coded data
+    stream += b"\xff\xd9"
+    want = np.stack([final.get(c, np.zeros((height, width), np.int16)) for c in range(ncomp)])
+    return bytes(stream), want
+
+
 # --------------------------------------------------------------------------------------------------
 # Sequential frames with several scans (or scans over some of the components).  Pillow only writes one
 # interleaved scan, so an existing stream is re-sequenced: the quantised coefficients (from the oracle)

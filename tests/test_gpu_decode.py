@@ -534,6 +534,38 @@ def test_lossless_synthetic(kw):
     assert np.array_equal(planes, O.decode(blob, want_rgb=False).planes)
 
 
+LOSSLESS_SCAN_LISTS = [
+    dict(scans=[dict(components=[0]), dict(components=[1], predictor=4), dict(components=[2], predictor=7)]),  # one scan per component
+    dict(scans=[dict(components=[0, 1], predictor=2), dict(components=[2], predictor=5)], restart=20),
+    dict(scans=[dict(components=[0, 1, 2]), dict(components=[1], predictor=3)], restart=7),       # the later scan over a component wins
+    dict(scans=[dict(components=[0], predictor=6), dict(components=[1, 2], predictor=1)], sampling=[(2, 2), (1, 1), (1, 1)]),
+    dict(scans=[dict(components=[2]), dict(components=[0])]),                                       # component 1 is never coded: zeros
+    dict(scans=[dict(components=[0]), dict(components=[1])], precision=12, restart=100, ncomp=2),
+]
+
+
+@pytest.mark.parametrize("kw", LOSSLESS_SCAN_LISTS, ids=lambda k: "+".join("".join(map(str, s["components"])) for s in k["scans"]))
+def test_lossless_frames_with_several_scans(kw):
+    """JpegHuffmanLosslessScanDecoder.ProcessScan (:52-205) runs once per SOS over one scanline store."""
+    blob, coded = synth.synth_lossless_scans(5, 64, 48, **kw)
+    o = O.decode(blob, want_rgb=False)
+    assert o.nscans == len(kw["scans"]) and np.array_equal(o.planes, coded)
+    planes = gpu_planes(blob)
+    assert np.array_equal(planes, coded)
+    if kw.get("ncomp", 3) == 3 and kw.get("precision", 8) == 8:
+        assert np.array_equal(gpu_pixels(blob), O.decode(blob).rgb)
+
+
+def test_lossless_scan_list_keeps_the_complete_last_interval_quirk():
+    """A scan whose last restart interval is complete looks for RSTn or EOI behind it (JpegHuffmanLosslessScanDecoder.cs
+    :164-178); the SOS of the next scan there is "Expect restart marker." -- in the reference and here."""
+    blob, _ = synth.synth_lossless_scans(5, 64, 48, scans=[dict(components=[0, 1]), dict(components=[2])], restart=16)
+    with pytest.raises(O.OracleError):
+        O.decode(blob, want_rgb=False)
+    with pytest.raises(J.InvalidOperationException):
+        gpu_planes(blob)
+
+
 @pytest.mark.parametrize("precision", [2, 3, 5, 7, 12, 16])
 def test_lossless_pixel_writers_of_other_precisions(precision):
     """8-bit pixel output of P-bit frames follows the reference application's writers: P > 8 shifts down
