@@ -1742,10 +1742,9 @@ int jb_decode_batch_finish(jb_batch *b)
             if (limit >= d.total_mcus) {
                 const uint8_t *s8 = static_cast<const uint8_t *>(src);
                 uint8_t *d8 = static_cast<uint8_t *>(pl.out.dst);
-                // (staging slots start 256-byte aligned: the gap to the next slot is part of the run when the
-                // destinations are spaced the same way)
-                if (run_len && s8 >= run_src + run_len && s8 - run_src == d8 - run_dst && (uint64_t)(s8 - run_src) - run_len < 256)
-                    run_len = (uint64_t)(s8 - run_src) + pl.out_bytes;
+                // (exactly adjacent only: bytes between two results belong to the caller and are never written)
+                if (run_len && s8 == run_src + run_len && d8 == run_dst + run_len)
+                    run_len += pl.out_bytes;
                 else {
                     JB_CUDA(ctx, flush_run());
                     run_src = s8; run_dst = d8; run_len = pl.out_bytes;
