@@ -60,6 +60,7 @@ namespace JpegLibrary.Cuda
             public Native.ScanDesc Scan;        // the (only) scan of a sequential frame; EntropyOffset/Length locate its bytes
             public Native.HuffSpec[] Tables;    // Scan.DcTable / AcTable index into this
         }
+        private ushort _restartAtFrame;
         private bool _coefficientsOnly;
         private CoefficientResult _coefficientResult;
         internal CoefficientResult DecodeCoefficients()
@@ -84,6 +85,12 @@ namespace JpegLibrary.Cuda
                         JpegFrameHeader.TryParse(body, false, out JpegFrameHeader fh, out _))
                     {
                         _frame = fh; _sof = marker; _scans.Clear();
+                        // The reference's sequential and lossless scan decoders are constructed HERE, at the frame header, and
+                        // read the restart interval once, in their constructors (JpegHuffmanBaselineScanDecoder.cs:38,
+                        // JpegHuffmanLosslessScanDecoder.cs:32): every scan of the frame uses the value in force now -- which,
+                        // unless a DRI segment precedes the SOF, is what Identify() left behind (the last DRI of the stream).
+                        // Progressive scans read it per scan (JpegHuffmanProgressiveScanDecoder.cs:78).
+                        _restartAtFrame = GetRestartInterval();
                     }
                     return base.ProcessMarkerForDecode(marker, ref reader); // validation + the public Width/Height/... properties
                 }
@@ -160,7 +167,7 @@ namespace JpegLibrary.Cuda
                 ComponentCount = sh.NumberOfComponents,
                 Ss = sh.StartOfSpectralSelection, Se = sh.EndOfSpectralSelection,
                 Ah = sh.SuccessiveApproximationBitPositionHigh, Al = sh.SuccessiveApproximationBitPositionLow,
-                RestartInterval = GetRestartInterval(),
+                RestartInterval = _sof == JpegMarker.StartOfFrame2 ? GetRestartInterval() : _restartAtFrame,
                 EntropyOffset = (ulong)reader.ConsumedByteCount,
             };
             for (int i = 0; i < sh.NumberOfComponents; i++)

@@ -107,7 +107,14 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
     uint16_t qt[4][64];
     bool qt_present[4] = {false, false, false, false};
     uint8_t comp_id[4] = {0, 0, 0, 0}, comp_tq[4] = {0, 0, 0, 0};
-    uint32_t restart_interval = 0;
+    // The reference's sequential and lossless scan decoders are created when the frame header is read and take the
+    // restart interval ONCE, in their constructors (JpegDecoder.cs:569, JpegHuffmanBaselineScanDecoder.cs:38,
+    // JpegHuffmanLosslessScanDecoder.cs:32): every scan of such a frame uses the value JpegDecoder holds at the SOF.  This
+    // walk stands for Identify() followed by Decode() (apps/JpegDecode, the reference's tests): Identify() has walked the
+    // whole stream before, so unless a DRI segment precedes the SOF that value is the LAST DRI of the stream.
+    // Progressive scans read it per scan (JpegHuffmanProgressiveScanDecoder.cs:78): the DRI in force at the SOS.
+    uint32_t restart_interval = 0, restart_at_sof = 0;
+    bool dri_before_sof = false, dri_seen = false;
     bool have_frame = false;
     // progressive `_components` slot emulation (JpegHuffmanProgressiveScanDecoder.cs:21,69,431-462)
     int slot_comp[4] = {-1, -1, -1, -1};
@@ -151,6 +158,8 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
                     return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse frame header.");
             }
             have_frame = true;
+            restart_at_sof = restart_interval;
+            dri_before_sof = dri_seen;
             break;
         }
         case 0xC5: case 0xC6: case 0xC7: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
@@ -189,6 +198,7 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
         case 0xDD:
             if (n < 2) return perr(JB_ERR_INVALID_DATA, seg_at, "Unexpected end of input data when reading segment content.");
             restart_interval = (uint32_t)((b[0] << 8) | b[1]);
+            dri_seen = true;
             break;
         case 0xDA: {
             if (!have_frame) return perr(JB_ERR_INVALID_DATA, seg_at, "Scan header appears before frame header.");
@@ -246,6 +256,8 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
             if (seen[i] != 1)
                 return perr(JB_ERR_NOT_SUPPORTED, w.pos, "progressive scan order leaves component slots inconsistent (reference quirk P6)");
     }
+    if (im.sof != 2)
+        for (jb_scan_desc &s : p->scans) s.restart_interval = dri_before_sof ? restart_at_sof : restart_interval;
     p->consumed = w.pos;
     im.scan_count = (uint32_t)p->scans.size();
     im.scans = p->scans.data();

@@ -220,6 +220,9 @@ typedef struct {
     uint16_t qt[4][64];
     int qt_present[4];
     int restart_interval;
+    int restart_at_sof; /* the sequential / lossless scan decoders are built at the SOF and take the restart interval once,
+                           in their constructors (JpegDecoder.cs:569, JpegHuffmanBaselineScanDecoder.cs:38,
+                           JpegHuffmanLosslessScanDecoder.cs:32) */
     int have_frame;
     /* progressive decoder state: `_components` slots survive across scans
        (JpegHuffmanProgressiveScanDecoder.cs:21,69) */
@@ -1024,8 +1027,29 @@ static int parse_sos(dec_ctx *c, const uint8_t *b, size_t n, jo_scan_info *s)
     s->se = t[1];
     s->ah = t[2] >> 4;
     s->al = t[2] & 15;
-    s->restart_interval = c->restart_interval;
+    /* progressive scans read the interval per scan (JpegHuffmanProgressiveScanDecoder.cs:78) */
+    s->restart_interval = c->img->sof == 2 ? c->restart_interval : c->restart_at_sof;
     return JO_OK;
+}
+
+/* JpegDecoder.Identify (JpegDecoder.cs:75-146) walks the whole stream before Decode() does (apps/JpegDecode/DecodeAction.cs,
+   the reference's tests): the decoder object keeps the LAST restart interval it met, and that is the value Decode() starts
+   with.  Returns it (0 without any DRI). */
+static int identify_last_dri(const uint8_t *data, size_t len)
+{
+    size_t pos = 2;
+    int dri = 0;
+    while (pos < len) {
+        int m = read_marker(data, len, &pos);
+        if (m < 0 || m == 0xD9) break;
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (pos + 2 > len) break;
+        size_t seglen = ((size_t)data[pos] << 8) | data[pos + 1];
+        if (seglen < 2 || pos + seglen > len) break;
+        if (m == 0xDD && seglen >= 4) dri = (data[pos + 2] << 8) | data[pos + 3];
+        pos += seglen; /* behind an SOS the search for the next marker runs over the entropy-coded data */
+    }
+    return dri;
 }
 
 int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
@@ -1044,6 +1068,7 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
     }
     pos = 2;
     int eoi = 0;
+    c->restart_interval = identify_last_dri(data, len);
     while (!eoi && pos < len) {
         int m = read_marker(data, len, &pos);
         if (m < 0) {
@@ -1071,6 +1096,7 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
         switch (m) {
         case 0xC0: case 0xC1: case 0xC2: case 0xC3:
             rc = parse_frame(c, m - 0xC0, body, blen);
+            c->restart_at_sof = c->restart_interval;
             break;
         case 0xC9: case 0xCA:
             rc = fail(c, JO_ERR_UNSUPPORTED, "SOF9/SOF10 (arithmetic coding) are outside the oracle's scope.");

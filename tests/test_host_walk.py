@@ -118,3 +118,34 @@ def test_sequential_scan_lists():
     assert plan[1]["deps"] == [0] and plan[1]["whole"] == 1                    # same blocks, another walk: wait for all of it
     plan = _plan(synth.resequence_scans(src, d, [[0], [0]]))
     assert plan[1]["deps"] == [0] and plan[1]["whole"] == 0                    # same walk: follow block by block
+
+
+def _dri(n):
+    return b"\xff\xdd\x00\x04" + n.to_bytes(2, "big")
+
+
+def test_sequential_frames_take_the_restart_interval_at_the_frame_header():
+    """The reference builds its sequential / lossless scan decoder when it reads the SOF and the decoder takes the restart
+    interval once, in its constructor (JpegDecoder.cs:569, JpegHuffmanBaselineScanDecoder.cs:38, ...Lossless...:32): every
+    scan of the frame uses the value JpegDecoder holds at that moment -- after Identify() that is the LAST DRI of the
+    stream, unless a DRI segment precedes the SOF.  Progressive scans read it per scan (...Progressive...:78).
+    Walker and oracle must agree on it."""
+    blob, _ = synth.synth_lossless_scans(3, 32, 24, scans=[dict(components=[0]), dict(components=[1, 2])], restart=5)
+    sos = [i for i in range(len(blob) - 1) if blob[i] == 0xFF and blob[i + 1] == 0xDA]
+    sof = blob.index(b"\xff\xc3")
+    assert len(sos) == 2 and blob.count(b"\xff\xdd") == 1
+    two = blob[:sos[1]] + _dri(9) + blob[sos[1]:]            # a second DRI in front of the second scan
+    early = two[:sof] + _dri(3) + two[sof:]                  # and one in front of the frame header
+    for stream, want in ((blob, 5), (two, 9), (early, 3)):
+        d = J.Parsed(stream).desc
+        assert [d.scans[i].restart_interval for i in range(d.scan_count)] == [want, want]
+        try:
+            o = O.decode(stream, want_rgb=False)
+            assert [s.restart_interval for s in o.scans] == [want, want]
+        except O.OracleError as e:                            # (coded with 5: the other intervals do not fit the data)
+            assert want != 5 and e.code in (-1, -2)
+    # progressive: the interval in force at each SOS
+    prog = synth.encode_jpeg(synth.synth_rgb(1, 48, 32), subsampling="4:4:4", progressive=True, restart_blocks=4)
+    sos = [i for i in range(len(prog) - 1) if prog[i] == 0xFF and prog[i + 1] == 0xDA]
+    d = J.Parsed(prog[:sos[2]] + _dri(0) + prog[sos[2]:]).desc
+    assert [d.scans[i].restart_interval for i in range(3)] == [4, 4, 0]
