@@ -104,7 +104,7 @@ namespace JpegLibrary.Cuda
                     ProcessScanOnGpu(ref reader);
                     return true;
                 case JpegMarker.EndOfImage:
-                    if (_sof == JpegMarker.StartOfFrame2 && _scans.Count > 0) Submit(); // progressive: render after the last scan
+                    if (_scans.Count > 0) Submit(); // progressive frames and scan lists: decode + render after the last scan
                     return false;
                 default:
                     return base.ProcessMarkerForDecode(marker, ref reader); // DQT, DRI, APPn, COM, RSTn stay managed
@@ -186,7 +186,26 @@ namespace JpegLibrary.Cuda
             sd.EntropyLength = (ulong)end;
             _scans.Add(sd);
             reader.TryAdvance(end);
-            if (_sof != JpegMarker.StartOfFrame2) { Submit(); _scans.Clear(); } // sequential and lossless frames: one scan
+            // A sequential or lossless frame coded as ONE scan over every component (what every mainstream encoder writes)
+            // is decoded right here, like the reference does.  Anything else -- several scans, a scan over some of the
+            // components -- is collected and handed over as one scan list at EOI, exactly what the Python mirror
+            // (jpeglibrary_b200/api.py) passes: a scan submitted alone would render the frame without the components
+            // of the other scans.  (A stream that ends without EOI loses such a scan list; the managed decoder would
+            // have written the scans it met.)
+            if (_sof != JpegMarker.StartOfFrame2 && _scans.Count == 1 && NamesEveryComponentOnce(sd)) { Submit(); _scans.Clear(); }
+        }
+
+        private bool NamesEveryComponentOnce(Native.ScanDesc sd)
+        {
+            if (sd.ComponentCount != _frame.NumberOfComponents) return false;
+            int seen = 0;
+            for (int i = 0; i < sd.ComponentCount; i++)
+            {
+                int bit = 1 << sd.ComponentIndex[i];
+                if ((seen & bit) != 0) return false;
+                seen |= bit;
+            }
+            return true;
         }
 
         private static int FindScanEnd(ReadOnlySequence<byte> data)
@@ -261,7 +280,9 @@ namespace JpegLibrary.Cuda
                     var o = new Native.OutputDesc { Dst = pp, Pitch = 0, Capacity = (ulong)planes.Length * 2, Format = Native.JB_OUT_PLANAR_I16, OnDevice = 0 };
                     Native.Check(_ctx, Native.jb_decode(_ctx, &img, &o, 1, null));
                 }
-                ReplayWriteBlocks(planes, scans[0]);
+                // sequential frames: the reference hands over every scan's blocks as it decodes them, scan after scan
+                if (_sof == JpegMarker.StartOfFrame2 || _sof == JpegMarker.StartOfFrame3) ReplayWriteBlocks(planes, scans[0]);
+                else foreach (Native.ScanDesc s in scans) ReplayWriteBlocks(planes, s);
             }
         }
 
