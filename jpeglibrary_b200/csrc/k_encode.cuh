@@ -489,15 +489,26 @@ __global__ void jb_k3c_build_tables(const uint32_t *__restrict__ hist, JbEncTabl
 }
 
 // ---- E8: bits per block / packing (EncodeBlock :828-870, EncodeRunLength :893-918)
-template <bool PACK>
-__device__ __forceinline__ uint32_t jb_encode_block(const JbEncImage &im, const int16_t *__restrict__ coef, uint32_t blk,
-                                                    const JbEncTable *__restrict__ tables, uint32_t *__restrict__ raw_words,
-                                                    uint64_t bitpos)
+// the block's 64 coefficients as eight 128-bit loads, and the DC predictor (previous block of the same component)
+__device__ __forceinline__ void jb_load_block(const JbEncImage &im, const int16_t *__restrict__ coef, uint32_t blk,
+                                              uint32_t (&w)[32], int &pred)
 {
-    const int16_t *p = coef + (im.coef_off + blk) * 64;
-    const int c = im.blk_comp[blk % im.bpm];
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(coef + (im.coef_off + blk) * 64);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 q = __ldg(p4 + j);
+        w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
+    }
     const int64_t pb = jb_prev_block(im, blk);
-    const int pred = pb < 0 ? 0 : coef[(im.coef_off + pb) * 64];
+    pred = pb < 0 ? 0 : coef[(im.coef_off + pb) * 64];
+}
+
+template <bool PACK>
+__device__ __forceinline__ uint32_t jb_encode_block_regs(const JbEncImage &im, const uint32_t (&w)[32], int pred, uint32_t blk,
+                                                         const JbEncTable *__restrict__ tables,
+                                                         uint32_t *__restrict__ raw_words, uint64_t bitpos)
+{
+    const int c = im.blk_comp[blk % im.bpm];
     const JbEncTable *dct = tables + im.table_base + im.comp_td[c];
     const JbEncTable *act = tables + im.table_base + 4 + im.comp_ta[c];
     uint32_t nbits = 0;
@@ -530,17 +541,8 @@ __device__ __forceinline__ uint32_t jb_encode_block(const JbEncImage &im, const 
         emit(t->code[sym], t->len[sym]);
         if (nb > 0) emit((uint32_t)b2, nb);
     };
-    // the block's 64 coefficients come in as eight 128-bit loads and stay in registers: the unrolled loop below
-    // indexes them at compile time (64 scalar loads per thread left this kernel latency-bound at 16-24 % issue rate)
-    uint32_t w[32];
-    {
-        const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const uint4 q = __ldg(p4 + j);
-            w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
-        }
-    }
+    // (the block's 64 coefficients stay in registers: the unrolled loop below indexes them at compile time; 64 scalar
+    // loads per thread left this kernel latency-bound at 16-24 % issue rate)
     runlen(dct, 0, (int)(int16_t)(w[0] & 0xFFFFu) - pred);
     int run = 0;
 #pragma unroll
@@ -559,6 +561,17 @@ __device__ __forceinline__ uint32_t jb_encode_block(const JbEncImage &im, const 
         atomicOr(raw_words + word, out);
     }
     return nbits;
+}
+
+template <bool PACK>
+__device__ __forceinline__ uint32_t jb_encode_block(const JbEncImage &im, const int16_t *__restrict__ coef, uint32_t blk,
+                                                    const JbEncTable *__restrict__ tables, uint32_t *__restrict__ raw_words,
+                                                    uint64_t bitpos)
+{
+    uint32_t w[32];
+    int pred;
+    jb_load_block(im, coef, blk, w, pred);
+    return jb_encode_block_regs<PACK>(im, w, pred, blk, tables, raw_words, bitpos);
 }
 
 // Restart intervals (transcoding): every interval starts on a byte boundary behind the previous interval's 1-bit

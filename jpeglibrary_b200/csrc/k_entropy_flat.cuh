@@ -189,11 +189,14 @@ __device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32
 #ifndef JB_K1_OWNER_COPY
 #define JB_K1_OWNER_COPY 0
 #endif
+#ifndef JB_K1_RANKED_COPY
+#define JB_K1_RANKED_COPY 1
+#endif
 #ifndef JB_K1_SYMBOLS_PER_ROUND
 #define JB_K1_SYMBOLS_PER_ROUND 3
 #endif
 #ifndef JB_K1F_MAX_THREADS
-#define JB_K1F_MAX_THREADS 1024
+#define JB_K1F_MAX_THREADS (JB_K1_RANKED_COPY ? 992 : 1024) // (what fits 227 KB of shared memory next to four tables)
 #endif
 #define JB_K1F_TABLES 4
 #define JB_K1F_TABLE_WORDS (JB_LUT_SIZE + JB_LUT2_SUBTABLES * 64)
@@ -204,7 +207,7 @@ __device__ __noinline__ uint32_t jb_huff32_escape(const JbHuffTable32 *t, uint32
 #define JB_K1F_NOTAB 0x3FFFu // table reference: not cached in shared memory
 __host__ __device__ inline size_t jb_k1f_smem_bytes(int threads)
 {
-    return (size_t)JB_K1F_TABLES * JB_K1F_TABLE_WORDS * 4 + (size_t)threads * (JB_K1F_SLOT + 4);
+    return (size_t)JB_K1F_TABLES * JB_K1F_TABLE_WORDS * 4 + (size_t)threads * (JB_K1F_SLOT + 4 + (JB_K1_RANKED_COPY ? 8 : 0));
 }
 
 // CLEAN = false: restart segments, read from the stuffed stream.  CLEAN = true: sub-sequences of K1b, read from
@@ -330,6 +333,11 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     uint32_t bi = s_bi[b]; // low half: DC table, high half: AC table | component << 14 (shared-memory word offsets)
     uint32_t tdc = bi & 0x3FFFu, tac = (bi >> 16) & 0x3FFFu;
     uint64_t gptr = reinterpret_cast<uint64_t>(coef + d.coef_block * 64);
+#if JB_K1_RANKED_COPY
+    uint32_t gblk = (uint32_t)d.coef_block;  // the same as a block index (a store of 2^32 blocks would be 512 GB)
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    uint2 *s_fin = reinterpret_cast<uint2 *>(s_slots + (size_t)nthreads * (JB_K1F_SLOT + 4)); // one (lane, block) entry per lane
+#endif
 
     while (__any_sync(0xFFFFFFFFu, left != 0)) {
         if (left != 0) {
@@ -482,6 +490,29 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                 gp[i] = q;
             }
         }
+#elif JB_K1_RANKED_COPY
+        // ---- completed blocks leave the SM as full 128-byte lines moved BY THE WARP: the finished lanes list themselves
+        // (lane, destination block) in shared memory by rank, then every group of 8 lanes moves the (4r + g)-th listed
+        // block in copy round r: ceil(finished / 4) rounds whatever groups the finished lanes sit in, no shuffles and no
+        // vote per round.  (First generation: every group moved the blocks of its OWN 8 lanes -- 2.6 copy rounds of 19
+        // instructions per decode round where 5 lanes finish; this one: 2 rounds of 11.)
+        const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished && !(CLEAN && skip));
+        if (fin) {
+            uint2 *list = s_fin + (tid & ~31);
+            if (finished && !(CLEAN && skip)) list[__popc(fin & lane_lt)] = make_uint2((uint32_t)lane, gblk);
+            __syncwarp(); // the list, and the owners' coefficient stores above, are read by other lanes below
+            const int nfin = __popc(fin);
+            for (int idx = lane >> 3; idx < ((nfin + 3) & ~3); idx += 4) {
+                if (idx < nfin) {
+                    const uint2 ent = list[idx];
+                    uint4 *sp = reinterpret_cast<uint4 *>(warp_slots + ent.x * JB_K1F_SLOT) + (lane & 7);
+                    const uint4 q = *sp;
+                    *sp = make_uint4(0, 0, 0, 0);
+                    reinterpret_cast<uint4 *>(coef + (size_t)ent.y * 64)[lane & 7] = q;
+                }
+            }
+            __syncwarp(); // the helpers' zeroing of the slots is ordered before the owners' next stores
+        }
 #else
         // ---- completed blocks leave the SM as full 128-byte lines: lanes 8g..8g+7 move the g-th finished lane's block
         const uint32_t fin = __ballot_sync(0xFFFFFFFFu, finished && !(CLEAN && skip));
@@ -506,6 +537,9 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
         }
 #endif
         if (finished) {
+#if JB_K1_RANKED_COPY
+            if (!(CLEAN && skip)) gblk++;
+#endif
             if (!(CLEAN && skip)) gptr += 128;
             left--;
             k = 0;

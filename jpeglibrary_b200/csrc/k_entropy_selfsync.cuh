@@ -230,6 +230,9 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
 // per-block table references.  s_bi[b] = {DC table, AC table, component}; table references are shared-memory
 // word offsets or JB_K1B_GLOBAL | word offset into the global table array.
 // ---------------------------------------------------------------------------------------------
+#ifndef JB_K1B_SYMBOLS_PER_ROUND
+#define JB_K1B_SYMBOLS_PER_ROUND 3
+#endif
 #define JB_K1B_GLOBAL 0x80000000u
 #define JB_K1B_TABLE_WORDS (JB_LUT_SIZE + JB_LUT2_SUBTABLES * 64)
 
@@ -448,37 +451,50 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
             wnext = wnext2;
             wnext2 = __ldg(words + wpos + 1);
         }
-        const bool is_dc = k == 0;
-        const uint32_t toff = is_dc ? bi.x : bi.y;
-        uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, hi);
-        if (e == 0) {
-            const uint32_t id = im.table_index[is_dc ? im.blk_dc[b] : im.blk_ac[b]];
-            const uint32_t e1 = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
-            e = jb_huff32_escape(tables + id, e1, hi >> 16);
-        }
-        if (e == JB_E32_BAD) e = is_dc ? 0x01000101u : 0x40000101u; // invalid code while speculating: keep moving
-        const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, adv = e >> 24;
-        const uint32_t s = total - len;
-        const uint32_t x = __funnelshift_l(lo, hi, len);
-        const uint32_t neg = ~(uint32_t)((int32_t)x >> 31);
-        const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
-        const int v = (int)((t ^ neg) - neg);
-        hi = __funnelshift_lc(lo, hi, total);
-        lo = __funnelshift_lc(0u, lo, total);
-        n -= (int)total;
-        p += total;
-        if (is_dc) { dcur += v; nblk++; }
-        k += adv;
-        if (k >= 64) {
-            k = 0;
-            b = b + 1 == bpm ? 0 : b + 1;
-            const uint4 ni = s_bi[b];
-            if (ni.z != bi.z) {
-                dcs[bi.z] += dcur;
-                dcur = 0;
+        // One symbol (the same step as K1's).  Up to three per round, like K1 (k_entropy_flat.cuh): the checkpoint test
+        // and the refill are paid per round by the whole warp, so symbols per round is what the instruction count hangs
+        // on.  A further symbol is taken while the window still holds 32 bits and neither the end of the sub-sequence
+        // nor the next checkpoint has been reached (a checkpoint records the state at the first symbol boundary behind it).
+        auto symbol = [&]() {
+            const bool is_dc = k == 0;
+            const uint32_t toff = is_dc ? bi.x : bi.y;
+            uint32_t e = jb_k1b_lookup(s_tab, tab_words, toff, hi);
+            if (e == 0) {
+                const uint32_t id = im.table_index[is_dc ? im.blk_dc[b] : im.blk_ac[b]];
+                const uint32_t e1 = s_tab[toff + (hi >> (32 - JB_LUT_BITS))];
+                e = jb_huff32_escape(tables + id, e1, hi >> 16);
             }
-            bi = ni;
-        }
+            if (e == JB_E32_BAD) e = is_dc ? 0x01000101u : 0x40000101u; // invalid code while speculating: keep moving
+            const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, adv = e >> 24;
+            const uint32_t s = total - len;
+            const uint32_t x = __funnelshift_l(lo, hi, len);
+            const uint32_t neg = ~(uint32_t)((int32_t)x >> 31);
+            const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+            const int v = (int)((t ^ neg) - neg);
+            hi = __funnelshift_lc(lo, hi, total);
+            lo = __funnelshift_lc(0u, lo, total);
+            n -= (int)total;
+            p += total;
+            if (is_dc) { dcur += v; nblk++; }
+            k += adv;
+            if (k >= 64) {
+                k = 0;
+                b = b + 1 == bpm ? 0 : b + 1;
+                const uint4 ni = s_bi[b];
+                if (ni.z != bi.z) {
+                    dcs[bi.z] += dcur;
+                    dcur = 0;
+                }
+                bi = ni;
+            }
+        };
+        symbol();
+#if JB_K1B_SYMBOLS_PER_ROUND >= 2
+        if (n >= 32 && p < end_bit && p < next_cp) symbol();
+#endif
+#if JB_K1B_SYMBOLS_PER_ROUND >= 3
+        if (n >= 32 && p < end_bit && p < next_cp) symbol();
+#endif
     }
     dcs[bi.z] += dcur;
     *reinterpret_cast<volatile unsigned long long *>(&exits[gi]) =
