@@ -4,8 +4,9 @@
  * In the C# integration this work is done by the reference's own JpegDecoder.Identify() /
  * marker loop (JpegDecoder.cs:75-162, :509-617) and the result is marshalled into
  * jb_image_desc.  No .NET toolchain exists in the build image, so the same walk is provided
- * here in C++ (host/jpeg_host.cpp) for the C++ mirror of the reference API
- * (include/JpegLibrary.hpp), for the Python bindings used by the tests, and for bench.py.
+ * here in C++ (jpeglibrary_b200/host/jpeg_host.cpp) for the Python mirror of the reference API
+ * (jpeglibrary_b200/api.py) that the tests and bench.py use.  It stands for Identify() followed by
+ * Decode(): sequential and lossless frames get the restart interval JpegDecoder holds at the SOF.
  * It is host code only: no decode arithmetic lives here.
  */
 #ifndef JPEGB200_HOST_H

@@ -13,9 +13,21 @@
 // K0: restart-marker index.  One CTA per image walks the entropy-coded bytes in 4 KB tiles and
 // records, in stream order, every FF xx with xx not in {00, FF}: RSTn markers (xx = D0..D7) and
 // the first other marker, which terminates the scan (JpegBitReader.cs:108-128 semantics).
-// HBM-bound: reads the compressed bytes once (uint4 per thread), writes ~4 B per restart interval.
+// HBM-bound: reads the compressed bytes once, writes ~4 B per restart interval.
+// The compressed bytes are BULK-LOADED BY TMA (round 2): one elected thread issues a 1-D cp.async.bulk of a whole tile
+// (+16 look-ahead bytes) into shared memory, completion is counted in bytes on an mbarrier, and two tiles are always
+// in flight (double buffer), so the CTA's serial tile loop -- load, test, barrier -- no longer waits a DRAM round trip
+// per tile, at no cost in registers (a register prefetch of the next tile had made the batch slower in round 1).
+// SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK.TRANS64.TRYWAIT.
 // ---------------------------------------------------------------------------------------------
 #define JB_K0_THREADS 256
+#ifndef JB_K0_TMA
+#define JB_K0_TMA 1
+#endif
+#define JB_K0_TILE (JB_K0_THREADS * 16)
+#define JB_K0_TILE_STRIDE (JB_K0_TILE + 128) // tile + look-ahead, 128-byte aligned
+
+__device__ __forceinline__ uint32_t jb_k0_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint32_t jb_ff_bytes(uint32_t w)
 {
@@ -55,26 +67,76 @@ jb_k0_restart_scan(const JbScanRange *__restrict__ ranges, const uint8_t *__rest
     __shared__ uint32_t s_warp[JB_K0_THREADS / 32];
     __shared__ uint32_t s_base, s_term_idx, s_term_pos, s_term_marker;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#if JB_K0_TMA
+    __shared__ __align__(128) uint8_t s_tile[2][JB_K0_TILE_STRIDE];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const uint32_t ntiles = (len + JB_K0_TILE - 1) / JB_K0_TILE;
+    // tile t -> buffer t & 1: the tile's bytes and 16 more (the look-ahead of its last thread), never past the image's
+    // arena slot (64 spare bytes behind every image)
+    auto issue = [&](uint32_t t) {
+        const uint32_t at = t * JB_K0_TILE;
+        const uint32_t bytes = min((uint32_t)JB_K0_TILE + 16u, ((len - at + 15u) & ~15u) + 16u);
+        const uint32_t bar = jb_k0_smem(&s_bar[t & 1]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(jb_k0_smem(s_tile[t & 1])), "l"(data + at), "r"(bytes), "r"(bar) : "memory");
+    };
+    auto wait = [&](uint32_t t) {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(ok) : "r"(jb_k0_smem(&s_bar[t & 1])), "r"((t >> 1) & 1u) : "memory");
+    };
+#endif
     if (tid == 0) {
         s_base = 0;
         s_term_idx = 0xFFFFFFFFu;
         s_term_pos = 0xFFFFFFFFu;
         s_term_marker = 0;
+#if JB_K0_TMA
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(jb_k0_smem(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(jb_k0_smem(&s_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+#endif
     }
     __syncthreads();
 
+#if JB_K0_TMA
+    uint32_t tnext = 0; // first tile that has not been waited for
+    for (uint32_t t = 0; t < ntiles; t++) {
+        const uint32_t tile = t * JB_K0_TILE;
+#else
     for (uint32_t tile = 0; tile < len; tile += JB_K0_THREADS * 16) {
+#endif
         const uint32_t pos0 = tile + tid * 16;
         uint32_t w[5] = {0, 0, 0, 0, 0};
+#if JB_K0_TMA
+        wait(t);
+        tnext = t + 1;
+        if (pos0 < len) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s_tile[t & 1] + tid * 16);
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            w[4] = *reinterpret_cast<const uint32_t *>(s_tile[t & 1] + tid * 16 + 16);
+        }
+#else
         if (pos0 < len) {
             // the arena is zero-padded by >= 32 bytes after every image: the over-read is safe
             uint4 v = __ldg(reinterpret_cast<const uint4 *>(data + pos0));
             w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             w[4] = __ldg(reinterpret_cast<const uint32_t *>(data + pos0 + 16));
         }
+#endif
         uint32_t cnt = 0;
         jb_foreach_marker(w, pos0, len, skew, [&](uint32_t, uint32_t) { cnt++; });
-        if (!__syncthreads_or(cnt != 0)) continue;
+        const bool any = __syncthreads_or(cnt != 0);
+#if JB_K0_TMA
+        // every thread holds its bytes in registers now: the buffer takes the tile after next (a terminator found in
+        // THIS tile stops the walk below; one bulk copy too many is waited for at the end)
+        if (tid == 0 && t + 2 < ntiles) issue(t + 2);
+#endif
+        if (!any) continue;
 
         // block-wide exclusive scan of cnt (rare path: only tiles that contain a marker)
         uint32_t incl = cnt;
@@ -109,6 +171,11 @@ jb_k0_restart_scan(const JbScanRange *__restrict__ ranges, const uint8_t *__rest
         __syncthreads();
         if (s_term_idx != 0xFFFFFFFFu) break;
     }
+#if JB_K0_TMA
+    // bulk copies still in flight (the walk stopped at a terminator) must land before the CTA gives its shared memory up
+    if (tid == 0)
+        for (uint32_t t = tnext; t < min(ntiles, tnext + 2); t++) wait(t);
+#endif
     __syncthreads();
     if (tid == 0) {
         JbScanResult r;
