@@ -39,6 +39,28 @@ __device__ __forceinline__ uint32_t jb_ff_bytes(uint32_t w)
 // A "zero byte" detector has false positives above a true zero byte only (borrow propagation);
 // callers re-check each flagged byte, so this is only used as a fast reject.
 
+// exact SWAR byte classifiers: 0x80 in every byte of w that equals 0xFF / 0x00
+__device__ __forceinline__ uint32_t jb_is_ff(uint32_t w)
+{
+    const uint32_t inv = ~w;
+    return ~(((inv & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | inv) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t jb_is_00(uint32_t w) { return ~(((w & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | w) & 0x80808080u; }
+
+// markers (FF followed by a byte that is neither 00 nor FF) among the 16 bytes w[0..3]; w[4] low byte = look-ahead byte.
+// Branch-free: the per-byte loop below ran with a handful of active lanes in every warp that met an FF byte (one 16-byte
+// group in five holds one), which made K0 issue-bound at 11 of 32 lanes per instruction.
+__device__ __forceinline__ uint32_t jb_count_markers16(const uint32_t w[5])
+{
+    uint32_t ff[5], stop[5]; // stop: bytes that make a preceding FF a non-marker (00 or FF)
+#pragma unroll
+    for (int i = 0; i < 5; i++) { ff[i] = jb_is_ff(w[i]); stop[i] = ff[i] | jb_is_00(w[i]); }
+    uint32_t n = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) n += __popc(ff[i] & ~((stop[i] >> 8) | (stop[i + 1] << 24)));
+    return n;
+}
+
 template <typename F>
 __device__ __forceinline__ void jb_foreach_marker(const uint32_t w[5], uint32_t pos0, uint32_t len, uint32_t skew, F f)
 {
@@ -129,7 +151,8 @@ jb_k0_restart_scan(const JbScanRange *__restrict__ ranges, const uint8_t *__rest
         }
 #endif
         uint32_t cnt = 0;
-        jb_foreach_marker(w, pos0, len, skew, [&](uint32_t, uint32_t) { cnt++; });
+        if (pos0 >= skew && pos0 + 17 < len) cnt = jb_count_markers16(w); // all 16 bytes and their successors lie inside the range
+        else jb_foreach_marker(w, pos0, len, skew, [&](uint32_t, uint32_t) { cnt++; });
         const bool any = __syncthreads_or(cnt != 0);
 #if JB_K0_TMA
         // every thread holds its bytes in registers now: the buffer takes the tile after next (a terminator found in

@@ -442,7 +442,9 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                         e = is_dc ? 0x01000101u : 0x40000101u;
                     }
                 }
-                const uint32_t total = e & 0xFFu, len = (e >> 8) & 0xFFu, run = (e >> 16) & 0xFFu, adv = e >> 24;
+                // (one PRMT per byte field: the shift-and-mask form costs two instructions for bytes 1 and 2)
+                const uint32_t total = __byte_perm(e, 0, 0x4440), len = __byte_perm(e, 0, 0x4441), run = __byte_perm(e, 0, 0x4442),
+                               adv = e >> 24;
                 const uint32_t s = total - len;
                 // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
                 const uint32_t x = __funnelshift_l(lo, hi, len);

@@ -477,24 +477,26 @@ jb_k1b_sync(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
             p += total;
             if (is_dc) { dcur += v; nblk++; }
             k += adv;
-            if (k >= 64) {
-                k = 0;
-                b = b + 1 == bpm ? 0 : b + 1;
-                const uint4 ni = s_bi[b];
-                if (ni.z != bi.z) {
-                    dcs[bi.z] += dcur;
-                    dcur = 0;
-                }
-                bi = ni;
-            }
         };
         symbol();
+        // (further symbols stop at the end of a block: the block change below then runs once per round for the couple
+        // of lanes that need it, not once per symbol step)
 #if JB_K1B_SYMBOLS_PER_ROUND >= 2
-        if (n >= 32 && p < end_bit && p < next_cp) symbol();
+        if (k < 64 && n >= 32 && p < end_bit && p < next_cp) symbol();
 #endif
 #if JB_K1B_SYMBOLS_PER_ROUND >= 3
-        if (n >= 32 && p < end_bit && p < next_cp) symbol();
+        if (k < 64 && n >= 32 && p < end_bit && p < next_cp) symbol();
 #endif
+        if (k >= 64) {
+            k = 0;
+            b = b + 1 == bpm ? 0 : b + 1;
+            const uint4 ni = s_bi[b];
+            if (ni.z != bi.z) {
+                dcs[bi.z] += dcur;
+                dcur = 0;
+            }
+            bi = ni;
+        }
     }
     dcs[bi.z] += dcur;
     *reinterpret_cast<volatile unsigned long long *>(&exits[gi]) =

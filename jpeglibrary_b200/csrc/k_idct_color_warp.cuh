@@ -160,15 +160,38 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     constexpr int CHUNKS = NB * 8;              // 16-byte pieces of the unit's coefficient blocks
     static_assert(ROW_BYTES % 16 == 0, "rows must be bulk-copyable");
 
+    // Shared-memory layout of a warp's sample planes.  The generic layout is dense (luma TW x TH, then Cb, then Cr,
+    // CW x 8 each).  The 4:2:0 instances (the headline shape) use a layout in which every access of the three phases is
+    // bank-conflict free (profiles/r2b_decode_batch1024.txt had 459 shared-memory wavefronts per unit against 198
+    // ideal, which at one wavefront per clock was 10.5 of the kernel's 11.9 ms):
+    //   * luma rows 8..15 start 64 bytes later, so the plane stores of the blocks of MCU row 0 and 1 (same columns,
+    //     640 bytes = 0 banks apart in the dense plane) land 16 banks apart;
+    //   * chroma rows are 80 bytes apart like luma rows (the relative position of luma and chroma stores is then the
+    //     same for each of the eight row stores), the five chroma blocks of a row sit in the order 2 3 4 - 0 1, Cb
+    //     starts at bank 4 and Cr at bank 20: the 16 lanes of either half warp store to 32 different banks;
+    //   * phase B takes its items (4 pixels x 2 rows) in the order of s_item: 4 chroma rows x 8 neighbouring groups per
+    //     round, whose luma loads (8 banks per chroma row), chroma loads and 12-byte staging stores (banks 3 g - 8 cy)
+    //     are all distinct; the 20 groups of a row leave one round of 8 rows x 4 groups that is 2-way (the optimum).
+    constexpr bool TUNED = NC == 3 && HS == 2 && VS == 2 && FMT != 1; // (RGBA32: the wider staging tile leaves no room)
+    constexpr int YGAP = TUNED ? 64 : 0;          // bytes skipped after every band of 8 luma rows
+    constexpr int CROW = TUNED ? 80 : CW;         // chroma row stride
+    constexpr int CPLANE = NC == 1 ? 16 : CROW * 8;
+    constexpr int CB0 = TUNED ? 1424 : TW * TH;   // byte offset of the Cb plane (tuned: word 356 = bank 4)
+    constexpr int CR0 = CB0 + CPLANE + YGAP;      // (tuned: word 532 = bank 20)
+    constexpr int PLANES = (CR0 + CPLANE + 127) & ~127;
+    static_assert(!TUNED || (TW * TH + YGAP <= CB0 && (CB0 / 4) % 32 == 4 && (CR0 / 4) % 32 == 20), "bank plan");
     __shared__ __align__(16) uint8_t s_raw[JB_K2W_WARPS][NB * JB_K2W_RAW_STRIDE];
-    __shared__ __align__(16) uint8_t s_y[JB_K2W_WARPS][TW * TH];
-    __shared__ __align__(16) uint8_t s_c[JB_K2W_WARPS][2][NC == 1 ? 16 : CW * 8];
+    __shared__ __align__(128) uint8_t s_pl[JB_K2W_WARPS][PLANES];
     __shared__ __align__(128) uint8_t s_stage[JB_K2W_WARPS][TH * ROW_BYTES];
-    // quantisers in NATURAL order, one table per component (packed IDCT: rows 2r, 2r + 1 interleaved element-wise)
-    __shared__ __align__(16) float s_qn[NC * 64];
+    // quantisers in NATURAL order, one table per component (packed IDCT: rows 2r, 2r + 1 interleaved element-wise); the
+    // tables are 68 floats apart: lanes of different components read the same 16-byte piece of their tables in one
+    // LDS.128, and 64 floats apart those were three addresses on the same four banks (12 wavefronts instead of 4)
+    constexpr int QSTRIDE = 68;
+    __shared__ __align__(16) float s_qn[NC * QSTRIDE];
     constexpr int GROUPS = TW / 4;                // phase B works on items of 4 pixels x VS rows (one chroma row)
     constexpr int ITEMS = GROUPS * (TH / VS);
     static_assert(ITEMS % 32 == 0, "items must spread evenly over the lanes");
+    static_assert(!TUNED || ITEMS == 160, "item order below");
     __shared__ uint32_t s_item[ITEMS];            // per item: chroma | luma << 10 | (staging >> 2) << 21 byte offsets
     __shared__ JbDevImage s_im;
 
@@ -183,15 +206,25 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32) {
 #if JB_K2_PACKED
         const int n = i & 63, r = ((n >> 4) << 1) | (n & 1), e = (n >> 1) & 7; // slot (r/2)*16 + e*2 + (r&1)
-        s_qn[i] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[r * 8 + e]];
+        s_qn[(i >> 6) * QSTRIDE + (i & 63)] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[r * 8 + e]];
 #else
-        s_qn[i] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
+        s_qn[(i >> 6) * QSTRIDE + (i & 63)] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
 #endif
     }
     for (int i = tid; i < ITEMS; i += JB_K2W_WARPS * 32) {
-        const int cy = i / GROUPS, gx = (i - cy * GROUPS) * 4;
-        s_item[i] = (uint32_t)(cy * CW + gx / HS) | ((uint32_t)(cy * VS * TW + gx) << 10) |
-                    ((uint32_t)((cy * VS * ROW_BYTES + gx * BPP) >> 2) << 21);
+        int cy, g;
+        if (TUNED) {
+            const int it = i >> 5, l = i & 31;
+            if (it < 4) { cy = (it >> 1) * 4 + (l >> 3); g = (it & 1) * 8 + (l & 7); }
+            else { cy = l >> 2; g = 16 + (l & 3); }
+        } else {
+            cy = i / GROUPS;
+            g = i - cy * GROUPS;
+        }
+        const int gx = g * 4, cx = gx / HS; // first pixel of the group, luma and chroma
+        const int coff = cy * CROW + (TUNED ? ((cx >> 3) + 4) % 6 * 8 + (cx & 7) : cx);
+        const int yoff = cy * VS * TW + ((cy * VS) >> 3) * YGAP + gx;
+        s_item[i] = (uint32_t)coff | ((uint32_t)yoff << 10) | ((uint32_t)((cy * VS * ROW_BYTES + gx * BPP) >> 2) << 21);
     }
     __syncthreads();
 
@@ -207,7 +240,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         bx = m;
         by = 0;
     }
-    const float *qn = s_qn + c * 64;
+    const float *qn = s_qn + c * QSTRIDE;
     const int W = s_im.width, H = s_im.height;
     const uint32_t mcus_per_line = s_im.mcus_per_line;
     const uint32_t upr = (mcus_per_line + UM - 1) / UM; // units per MCU row
@@ -222,7 +255,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     // WriteBlock for them (JpegHuffmanBaselineScanDecoder.cs:144-150), their pixels are left as they are
     const uint32_t limit = mcu_limit ? mcu_limit[image] : 0xFFFFFFFFu;
     uint8_t *raw = s_raw[wid];
-    uint8_t *yplane = s_y[wid];
+    uint8_t *yplane = s_pl[wid];
     uint8_t *stage = s_stage[wid];
 
     uint32_t unit = (blockIdx.x * JB_K2W_WARPS + wid) * (uint32_t)units_per_warp;
@@ -308,8 +341,9 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
             jb_k2w_col<0>(d1, rows); jb_k2w_col<1>(d1, rows); jb_k2w_col<2>(d1, rows); jb_k2w_col<3>(d1, rows);
             jb_k2w_col<4>(d1, rows); jb_k2w_col<5>(d1, rows); jb_k2w_col<6>(d1, rows); jb_k2w_col<7>(d1, rows);
 #endif
-            uint8_t *pl = (c == 0 ? yplane + (by * 8) * TW : s_c[wid][c - 1]) + bx * 8;
-            const int pp = c == 0 ? TW : CW;
+            uint8_t *pl = c == 0 ? yplane + by * (8 * TW + YGAP) + bx * 8
+                                 : yplane + (c == 1 ? CB0 : CR0) + (TUNED ? (bx + 4) % 6 : bx) * 8;
+            const int pp = c == 0 ? TW : CROW;
 #pragma unroll
             for (int k = 0; k < 8; k++) *reinterpret_cast<uint2 *>(pl + k * pp) = make_uint2(rows[2 * k], rows[2 * k + 1]);
         }
@@ -321,7 +355,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
 #pragma unroll
         for (int it = 0; it < ITEMS / 32; it++) {
             const uint32_t io = s_item[it * 32 + lane];
-            const uint8_t *cp = s_c[wid][0] + (io & 1023u);
+            const uint8_t *cp = yplane + CB0 + (io & 1023u);
             const uint8_t *yp = yplane + ((io >> 10) & 2047u);
             uint8_t *sp = stage + ((io >> 21) << 2);
             JbChromaTerms t0, t1, t2, t3;
@@ -329,10 +363,10 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
             if (NC == 3) {
                 if (HS == 2) {
                     cb4 = *reinterpret_cast<const uint16_t *>(cp);
-                    cr4 = *reinterpret_cast<const uint16_t *>(cp + CW * 8);
+                    cr4 = *reinterpret_cast<const uint16_t *>(cp + (CR0 - CB0));
                 } else {
                     cb4 = *reinterpret_cast<const uint32_t *>(cp);
-                    cr4 = *reinterpret_cast<const uint32_t *>(cp + CW * 8);
+                    cr4 = *reinterpret_cast<const uint32_t *>(cp + (CR0 - CB0));
                 }
             }
             if (FMT != 2) {
