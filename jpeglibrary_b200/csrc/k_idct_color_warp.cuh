@@ -352,6 +352,53 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         __syncwarp();
 
         // ------------------------------------------------ phase B: 4-pixel groups -> staging tile
+        if constexpr (TUNED && FMT == 0) {
+            // RGB24 from 4:2:0, the headline shape: the item order of s_item written out, so that every address is a
+            // per-lane base plus a compile-time offset, and the twelve bytes of a group built as three words
+            // [r0 g0 b0 r1] [g1 b1 r2 g2] [b2 r3 g3 b3] = even bytes | odd bytes << 8, where each half is ONE packed
+            // add-and-clamp of a luma pair and a term pair: 5 + 6 + 3 instructions per row of four pixels instead of
+            // 2 + 6 + 6, and the >> 16 of the chroma terms (jb_chroma_terms) is the byte selection that pairs them.
+            const int q = lane >> 3, r = lane & 7, q2 = lane >> 2, r2 = lane & 3;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const uint8_t *cp, *yp;
+                uint8_t *sp;
+                if (it < 4) { // chroma rows 4 (it / 2) + q, groups 8 (it % 2) + r
+                    cp = yplane + CB0 + q * CROW + 2 * r + (it >> 1) * (4 * CROW) + ((it & 1) ? 0 : 32);
+                    yp = yplane + q * (2 * TW) + 4 * r + (it >> 1) * (8 * TW + YGAP) + (it & 1) * 32;
+                    sp = stage + q * (2 * ROW_BYTES) + 12 * r + (it >> 1) * (8 * ROW_BYTES) + (it & 1) * 96;
+                } else {      // chroma rows q2, groups 16 + r2
+                    cp = yplane + CB0 + q2 * CROW + 2 * r2 + 16;
+                    yp = yplane + q2 * (2 * TW) + (q2 >> 2) * YGAP + 4 * r2 + 64;
+                    sp = stage + q2 * (2 * ROW_BYTES) + 12 * r2 + 192;
+                }
+                const uint32_t cbw = *reinterpret_cast<const uint16_t *>(cp);
+                const uint32_t crw = *reinterpret_cast<const uint16_t *>(cp + (CR0 - CB0));
+                const int cb0 = (int)(cbw & 0xFF), cb1 = (int)(cbw >> 8), cr0 = (int)(crw & 0xFF), cr1 = (int)(crw >> 8);
+                // the products of jb_k2w_chroma_terms before their >> 16
+                const uint32_t pr0 = (uint32_t)(91881 * cr0 + (32768 - 128 * 91881));
+                const uint32_t pr1 = (uint32_t)(91881 * cr1 + (32768 - 128 * 91881));
+                const uint32_t pg0 = (uint32_t)(-22553 * cb0 + (-46802 * cr0 + (32768 + 128 * 22553 + 128 * 46802)));
+                const uint32_t pg1 = (uint32_t)(-22553 * cb1 + (-46802 * cr1 + (32768 + 128 * 22553 + 128 * 46802)));
+                const uint32_t pb0 = (uint32_t)(116130 * cb0 + (32768 - 128 * 116130));
+                const uint32_t pb1 = (uint32_t)(116130 * cb1 + (32768 - 128 * 116130));
+                // term pairs: the upper halves of two products side by side
+                const uint32_t t_rb0 = __byte_perm(pr0, pb0, 0x7632), t_gr0 = __byte_perm(pg0, pr0, 0x7632);
+                const uint32_t t_g0r1 = __byte_perm(pg0, pr1, 0x7632), t_b0g1 = __byte_perm(pb0, pg1, 0x7632);
+                const uint32_t t_bg1 = __byte_perm(pb1, pg1, 0x7632), t_rb1 = __byte_perm(pr1, pb1, 0x7632);
+#pragma unroll
+                for (int rr = 0; rr < 2; rr++) {
+                    const uint32_t y4 = *reinterpret_cast<const uint32_t *>(yp + rr * TW);
+                    const uint32_t y00 = __byte_perm(y4, 0, 0x4040), y01 = __byte_perm(y4, 0, 0x4140);
+                    const uint32_t y12 = __byte_perm(y4, 0, 0x4241), y23 = __byte_perm(y4, 0, 0x4342);
+                    const uint32_t y33 = __byte_perm(y4, 0, 0x4343);
+                    uint32_t *dst = reinterpret_cast<uint32_t *>(sp + rr * ROW_BYTES);
+                    dst[0] = __byte_perm(jb_addclamp2(y00, t_rb0), jb_addclamp2(y01, t_gr0), 0x6240);   // r0 g0 b0 r1
+                    dst[1] = __byte_perm(jb_addclamp2(y12, t_g0r1), jb_addclamp2(y12, t_b0g1), 0x6240); // g1 b1 r2 g2
+                    dst[2] = __byte_perm(jb_addclamp2(y23, t_bg1), jb_addclamp2(y33, t_rb1), 0x6240);   // b2 r3 g3 b3
+                }
+            }
+        } else
 #pragma unroll
         for (int it = 0; it < ITEMS / 32; it++) {
             const uint32_t io = s_item[it * 32 + lane];
