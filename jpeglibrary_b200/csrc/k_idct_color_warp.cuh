@@ -133,12 +133,15 @@ __device__ __forceinline__ void jb_k2w_col2(const jb_f2 (&d1)[32], uint32_t (&ro
     const jb_f2 eighth = jb_pack2(0.125f, 0.125f), bias = jb_pack2(12582912.0f + 128.0f, 12582912.0f + 128.0f);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        // MultiplyInplace(0.125) + MathF.Round (half-to-even) + level shift in one fma, then clamp to 0..255
+        // MultiplyInplace(0.125) + MathF.Round (half-to-even) + level shift in one fma: the float's bits are
+        // 0x4B400000 + sample, so their low halves are the int16 the reference stores in its block (the (short) cast of
+        // ShiftDataLevel, JpegScanDecoder.cs:64-73, wrap-around included while |sample| < 2^22); two of them side by
+        // side are clamped to 0..255 by one VIMNMX.S16x2.RELU, the clamp of the 8-bit writers
         const jb_f2 t = jb_fma2(d[k], eighth, bias);
-        const uint32_t v0 = (uint32_t)__viaddmin_s32_relu(__float_as_int(jb_lo2(t)), -0x4B400000, 255);
-        const uint32_t v1 = (uint32_t)__viaddmin_s32_relu(__float_as_int(jb_hi2(t)), -0x4B400000, 255);
-        if ((C & 3) == 0) rows[k * 2 + (C >> 2)] = v0 + (v1 << 8);
-        else rows[k * 2 + (C >> 2)] += (v0 << (8 * (C & 3))) + (v1 << (8 * (C & 3) + 8)); // disjoint bytes
+        const uint32_t s2 = __byte_perm(__float_as_uint(jb_lo2(t)), __float_as_uint(jb_hi2(t)), 0x5410);
+        const uint32_t v = __vimin_s16x2_relu(s2, 0x00FF00FFu); // bytes: v(C) 0 v(C + 1) 0
+        if ((C & 3) == 0) rows[k * 2 + (C >> 2)] = v;
+        else rows[k * 2 + (C >> 2)] = __byte_perm(rows[k * 2 + (C >> 2)], v, 0x6420);
     }
 }
 

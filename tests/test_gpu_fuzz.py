@@ -134,6 +134,48 @@ def test_corrupted_scans_decode_like_the_reference(name):
     assert not problems, "\n".join(problems)
 
 
+def run_gpu_rgb(blob):
+    try:
+        dec = J.JpegDecoder()
+        dec.SetInput(blob)
+        dec.Identify()
+        out = np.zeros((dec.Height, dec.Width, 3), dtype=np.uint8)
+        dec.SetOutputWriter(J.CudaOutputWriter(out, J.JB_OUT_RGB24))
+        dec.Decode()
+        return out, None
+    except GPU_ERRORS as e:
+        return None, e
+
+
+@pytest.mark.parametrize("name", ["restart", "restart_rows_444", "plain"])
+def test_corrupted_scans_render_the_same_pixels(name):
+    """The same damage through the RGB24 sink, i.e. through the fast renderer (packed IDCT, 16-bit clamp, colour): wrong
+    symbols give samples far outside 0..255 -- the reference stores them as int16 (wrap-around included) and its 8-bit
+    writer clamps that; the pixels have to come out the same, byte for byte."""
+    blob = base_streams()[name]
+    rng = np.random.default_rng(1000 + sum(map(ord, name)))
+    problems, same, wild = [], 0, 0
+    for trial in range(70):
+        bad = mutate(blob, rng, KINDS[trial % len(KINDS)])
+        try:
+            want = O.decode(bad, want_rgb=True)
+        except O.OracleError:
+            continue
+        got, gerr = run_gpu_rgb(bad)
+        if gerr is not None:
+            problems.append(f"trial {trial}: GPU raised [{type(gerr).__name__}: {gerr}] but the oracle decoded")
+            continue
+        wild += int((np.abs(want.planes.astype(np.int32) - 128) > 300).any())
+        wr = O.written_samples(want).all(axis=0)  # (a scan cut at a restart marker leaves the rest of the frame alone)
+        if np.array_equal(got[wr], want.rgb[wr]) and not got[~wr].any():
+            same += 1
+        else:
+            d = np.abs(got.astype(int) - want.rgb.astype(int)) * wr[:, :, None]
+            problems.append(f"trial {trial}: {int((d > 0).sum())} bytes differ, max {int(d.max())}")
+    print(f"{name}: {same} identical renderings ({wild} with samples far outside 0..255), {len(problems)} disagreements")
+    assert same > 20 and not problems, "\n".join(problems)
+
+
 def mutate_header(blob, rng, kind):
     """damage somewhere between SOI and the first bytes of the first scan: marker codes, segment lengths, frame and
     scan header fields, table definitions"""
