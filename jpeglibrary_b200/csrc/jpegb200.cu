@@ -455,7 +455,11 @@ static int launch_k1_flat(jb_batch *b, const JbSegDesc *segs, uint32_t nsegs, co
     uint32_t lanes = std::min<uint32_t>(32, std::max<uint32_t>(1, (nsegs + sms * 16 - 1) / (sms * 16)));
     if (const char *e = getenv("JB_K1_LANES")) lanes = (uint32_t)std::min(32, std::max(1, atoi(e))); // tuning knob
     const uint32_t warps = (nsegs + lanes - 1) / lanes;
-    uint32_t threads = ((warps + sms - 1) / sms) * 32;
+    // one CTA per SM (the slots take the shared memory): all warps in one wave when they fit, else waves of equal size
+    // (419 000 sub-sequences in CTAs of 992 are 2.88 waves, the last one 88 % full; in CTAs of 960 they are 2.95)
+    const uint32_t max_warps = JB_K1F_MAX_THREADS / 32;
+    const uint32_t waves = (warps + sms * max_warps - 1) / (sms * max_warps);
+    uint32_t threads = ((warps + sms * waves - 1) / (sms * waves)) * 32;
     threads = std::min<uint32_t>(JB_K1F_MAX_THREADS, std::max<uint32_t>(64, threads));
     const size_t smem = jb_k1f_smem_bytes((int)threads);
     JB_CUDA(ctx, cudaFuncSetAttribute(jb_k1_huff_flat<CLEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -24,6 +24,9 @@
 #include "k_idct_color_fast.cuh"
 
 #define JB_K2W_WARPS 4
+#ifndef JB_K2W_MIN_CTAS
+#define JB_K2W_MIN_CTAS 4 // CTAs per SM the register allocation aims at (128 registers; 5 -> 96 registers and spills)
+#endif
 #define JB_K2W_RAW_STRIDE 144 // bytes per block in the raw tile: 128 + 16 so that the eight 128-bit loads of the
                               // eight lanes of a quarter warp hit different banks
 
@@ -90,6 +93,9 @@ __device__ __forceinline__ void jb_k2w_col(const float (&d1)[64], uint32_t (&row
     }
 }
 
+#ifndef JB_K2_COMBINE_MAD
+#define JB_K2_COMBINE_MAD 1 // the two halves of an RGB word are joined by a multiply-add (FMA pipe: the colour phase is ALU-heavy) instead of PRMT; A/B 10.49 -> 10.33 ms
+#endif
 #ifndef JB_K2_PACKED
 #define JB_K2_PACKED 1 // both IDCT passes on packed fp32 pairs (FADD2 / FFMA2), see jb_idct8x2
 #endif
@@ -147,7 +153,7 @@ __device__ __forceinline__ void jb_k2w_col2(const jb_f2 (&d1)[32], uint32_t (&ro
 
 // FMT: 0 RGB24, 1 RGBA32, 2 YCBCR888.  HS,VS: chroma subsampling (1 or 2).  NC: 1 or 3 components.
 template <int FMT, int NC, int HS, int VS>
-__global__ void __launch_bounds__(JB_K2W_WARPS * 32, 4)
+__global__ void __launch_bounds__(JB_K2W_WARPS * 32, JB_K2W_MIN_CTAS)
 jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__restrict__ coef,
                       const uint16_t *__restrict__ quant, const uint32_t *__restrict__ image_list,
                       int units_per_warp, const uint32_t *__restrict__ mcu_limit, const unsigned long long negzero2)
@@ -195,15 +201,25 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
     constexpr int ITEMS = GROUPS * (TH / VS);
     static_assert(ITEMS % 32 == 0, "items must spread evenly over the lanes");
     static_assert(!TUNED || ITEMS == 160, "item order below");
-    __shared__ uint32_t s_item[ITEMS];            // per item: chroma | luma << 10 | (staging >> 2) << 21 byte offsets
-    __shared__ JbDevImage s_im;
+    constexpr bool ITEM_TABLE = !(TUNED && FMT == 0); // (that instance has the order written out in phase B)
+    __shared__ uint32_t s_item[ITEM_TABLE ? ITEMS : 1]; // per item: chroma | luma << 10 | (staging >> 2) << 21 byte offsets
+    struct Im { // the fields of JbDevImage this kernel uses (the whole descriptor is 1.4 KB)
+        uint64_t out_ptr, out_pitch, tmap_ptr, coef_off;
+        uint32_t tmap_shift, quant_off, mcus_per_line, mcus_per_col, planar, width, height;
+        uint32_t comp_plane_off[4], comp_plane_w[4];
+    };
+    __shared__ Im s_im;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t image = image_list[blockIdx.y];
-    {
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(images + image);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_im);
-        for (int i = tid; i < (int)(sizeof(JbDevImage) / 4); i += JB_K2W_WARPS * 32) dst[i] = src[i];
+    if (tid == 0) {
+        const JbDevImage &g = images[image];
+        s_im.out_ptr = g.out_ptr; s_im.out_pitch = g.out_pitch; s_im.tmap_ptr = g.tmap_ptr; s_im.coef_off = g.coef_off;
+        s_im.tmap_shift = g.tmap_shift; s_im.quant_off = g.quant_off; s_im.mcus_per_line = g.mcus_per_line;
+        s_im.mcus_per_col = g.mcus_per_col; s_im.planar = g.planar; s_im.width = g.width; s_im.height = g.height;
+    } else if (tid < 5) {
+        s_im.comp_plane_off[tid - 1] = images[image].comp_plane_off[tid - 1];
+        s_im.comp_plane_w[tid - 1] = images[image].comp_plane_w[tid - 1];
     }
     __syncthreads();
     for (int i = tid; i < NC * 64; i += JB_K2W_WARPS * 32) {
@@ -214,7 +230,7 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
         s_qn[(i >> 6) * QSTRIDE + (i & 63)] = (float)quant[s_im.quant_off + (i >> 6) * 64 + jb_c_nat2zz[i & 63]];
 #endif
     }
-    for (int i = tid; i < ITEMS; i += JB_K2W_WARPS * 32) {
+    for (int i = tid; i < (ITEM_TABLE ? ITEMS : 0); i += JB_K2W_WARPS * 32) {
         int cy, g;
         if (TUNED) {
             const int it = i >> 5, l = i & 31;
@@ -396,9 +412,15 @@ jb_k2_idct_color_warp(const JbDevImage *__restrict__ images, const int16_t *__re
                     const uint32_t y12 = __byte_perm(y4, 0, 0x4241), y23 = __byte_perm(y4, 0, 0x4342);
                     const uint32_t y33 = __byte_perm(y4, 0, 0x4343);
                     uint32_t *dst = reinterpret_cast<uint32_t *>(sp + rr * ROW_BYTES);
+#if JB_K2_COMBINE_MAD
+                    dst[0] = jb_addclamp2(y00, t_rb0) + jb_addclamp2(y01, t_gr0) * 256u;   // r0 g0 b0 r1
+                    dst[1] = jb_addclamp2(y12, t_g0r1) + jb_addclamp2(y12, t_b0g1) * 256u; // g1 b1 r2 g2
+                    dst[2] = jb_addclamp2(y23, t_bg1) + jb_addclamp2(y33, t_rb1) * 256u;   // b2 r3 g3 b3
+#else
                     dst[0] = __byte_perm(jb_addclamp2(y00, t_rb0), jb_addclamp2(y01, t_gr0), 0x6240);   // r0 g0 b0 r1
                     dst[1] = __byte_perm(jb_addclamp2(y12, t_g0r1), jb_addclamp2(y12, t_b0g1), 0x6240); // g1 b1 r2 g2
                     dst[2] = __byte_perm(jb_addclamp2(y23, t_bg1), jb_addclamp2(y33, t_rb1), 0x6240);   // b2 r3 g3 b3
+#endif
                 }
             }
         } else
