@@ -422,3 +422,34 @@ def handmade_grey(blocks_w, blocks_h, seed=0, dri=0, cut=0, cut_interval=None):
         out += seg(0xDD, dri.to_bytes(2, "big"))
     out += seg(0xDA, bytes([1, 1, 0x00, 0, 63, 0])) + data + b"\xff\xd9"
     return out, coef
+
+
+def reorder_progressive_scans(blob, order):
+    """blob: a progressive JPEG whose scans each come behind their own DHT segments (Pillow / libjpeg with optimised
+    tables); order: a permutation (or selection) of scan indices.  Returns the same frame with its scans -- each together
+    with the tables in front of it -- in that order: the scan script of a damaged or hand-made file, which the
+    reference decodes in file order without checking the progression."""
+    i, head, chunks, cur = 2, [blob[:2]], [], []
+    seen_sos = False
+    while i < len(blob):
+        assert blob[i] == 0xFF
+        m = blob[i + 1]
+        if m == 0xD9:
+            break
+        ln = int.from_bytes(blob[i + 2:i + 4], "big")
+        seg = blob[i:i + 2 + ln]
+        i += 2 + ln
+        if m == 0xDA:
+            j = i
+            while True:
+                j = blob.index(b"\xff", j)
+                if blob[j + 1] != 0 and not 0xD0 <= blob[j + 1] <= 0xD7:
+                    break
+                j += 2
+            chunks.append(b"".join(cur) + seg + blob[i:j])
+            cur, i, seen_sos = [], j, True
+        elif m == 0xC4 or seen_sos:
+            cur.append(seg)
+        else:
+            head.append(seg)
+    return b"".join(head) + b"".join(chunks[k] for k in order) + b"".join(cur) + b"\xff\xd9"
