@@ -105,7 +105,6 @@ struct JbDevScan {
     uint32_t dri, nseg;
     uint32_t nunits;     // MCUs (interleaved scan) or blocks (single-component scan)
     uint32_t wb, hb;     // single-component scans: block grid of the component (:146-147)
-    uint32_t rec_off;    // AC refinement scans decoded one stream per lane: first record (JbRefineRecord) of the scan
     uint8_t ncomp, ss, se, ah, al;
     uint8_t comp[4];
     uint8_t level;       // dependency level: scans of one level touch disjoint (component, band) sets

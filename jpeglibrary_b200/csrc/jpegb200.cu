@@ -403,11 +403,6 @@ struct jb_batch {
     uint32_t *d_prog_progress = nullptr;   // per scan: units (one segment) or segments finished; last word: ticket counter
     unsigned long long *d_prog_trace = nullptr; // profiling: {image|scan|seg, start, end, waited} ns per job
     uint64_t prog_coef_first = 0, prog_coef_blocks = 0; // contiguous slice of the store, zeroed per launch
-    // AC refinement scans decoded one stream per lane (k_entropy_progressive.cuh): a 64-bit nonzero map per block of the
-    // progressive slice of the store, one 32-byte record per block of every such scan; both zeroed per launch
-    unsigned long long *d_nzmask = nullptr;
-    uint4 *d_records = nullptr;
-    uint64_t prog_rec_units = 0;
     std::vector<JbDevScan> h_scans;
     std::vector<JbScanRange> h_ranges;
     JbDevScan *d_scans = nullptr;
@@ -726,36 +721,6 @@ static int intern_table(const jb_image_desc &im, int t, int want_class, std::vec
 // Also sequential frames that are not "one interleaved scan over every component" (sequential = true): the reference
 // walks each of their scans MCU by MCU with the component's own h x v (JpegHuffmanBaselineScanDecoder.cs:99-137, quirk
 // Q2) and decodes whole blocks; the scans go through the same scan list, planar store and renderer.
-// AC refinement scan of a progressive frame (ReadBlockProgressiveACRefined)
-static bool is_ac_refinement(const JbDevScan &ds) { return !ds.seq && ds.ncomp == 1 && ds.ss != 0 && ds.ah != 0; }
-
-// May the AC refinement scans of this frame be decoded one stream per lane (records now, coefficients patched after the
-// entropy kernel)?  The patches land AFTER everything the other scans wrote, so no scan that writes coefficients directly
-// (an AC first scan) may follow a refinement scan over the same component and band: libjpeg's scripts and every legal
-// progression qualify (a band is refined only after it was coded), a damaged scan script that does not keeps the
-// whole-warp decoder, which works on the store in scan order.  JB_K1C_THIN=0 forces that decoder (A/B measurements).
-static bool thin_refinement_ok(const std::vector<JbDevScan> &scans)
-{
-    static const bool enabled = [] { const char *e = getenv("JB_K1C_THIN"); return !e || atoi(e) != 0; }();
-    if (!enabled) return false;
-    auto top = [](const JbDevScan &x) -> int { // last position a scan may write (plan_progressive)
-        return x.ss == 0 || x.seq ? (int)x.se : std::min<int>(63, x.se + (x.ah == 0 ? 15 : 1));
-    };
-    size_t n = 0;
-    for (size_t i = 0; i < scans.size(); i++) {
-        if (!is_ac_refinement(scans[i])) continue;
-        n++;
-        for (size_t j = i + 1; j < scans.size(); j++) {
-            const JbDevScan &l = scans[j];
-            if (is_ac_refinement(l)) continue;
-            bool share = false;
-            for (int a = 0; a < l.ncomp; a++) share |= l.comp[a] == scans[i].comp[0];
-            if (share && top(l) >= (int)scans[i].ss && top(scans[i]) >= (int)l.ss) return false;
-        }
-    }
-    return n > 0 && n <= 64; // (JB_K1C_APPLY_MAX_SCANS)
-}
-
 static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const jb_output_desc *outp, ImagePlan &pl,
                             std::vector<JbHuffTable> &tables, std::map<std::string, int> &table_ids,
                             std::vector<uint16_t> &quant, bool sequential = false)
@@ -1281,15 +1246,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         blocks += pl.total_blocks;
         pl.dev.scan_base = (uint32_t)b->h_scans.size();
         b->prog_max_scans = std::max<uint32_t>(b->prog_max_scans, (uint32_t)pl.scans.size());
-        const bool thin = thin_refinement_ok(pl.scans);
         for (size_t k = 0; k < pl.scans.size(); k++) {
-            JbDevScan &ps = pl.scans[k];
-            ps.rec_off = 0xFFFFFFFFu;
-            if (thin && is_ac_refinement(ps) && b->prog_rec_units + ps.nunits < 0xFFFFFFFFull) {
-                ps.rec_off = (uint32_t)b->prog_rec_units;
-                b->prog_rec_units += ps.nunits;
-            }
-            JbDevScan ds = ps;
+            JbDevScan ds = pl.scans[k];
             ds.data_off = pl.dev.data_off + pl.scan_host_off[k];
             ds.range = (uint32_t)b->h_ranges.size();
             ds.mark_base = (uint32_t)marks;
@@ -1329,20 +1287,17 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
         // several lane entries to a warp.  Entries of one warp come from one rank, so they never wait for each other.
         // A stream decodes fastest with a warp to itself; packing trades that for warp slots: pack just enough that
         // all jobs can be resident at once (32 one-warp CTAs per SM).
-        // AC refinement scans with a record slot are packed too (one stream per lane); the others are whole-warp jobs.
-        auto whole_warp = [](const JbDevScan &ds) { return is_ac_refinement(ds) && ds.rec_off == 0xFFFFFFFFu; };
         uint64_t n_coop = 0, n_serial = 0;
         for (uint32_t i : b->prog_images)
-            for (const JbDevScan &ds : b->plans[i].scans) (whole_warp(ds) ? n_coop : n_serial) += ds.nseg;
+            for (const JbDevScan &ds : b->plans[i].scans) (ds.ncomp == 1 && ds.ss != 0 && ds.ah != 0 ? n_coop : n_serial) += ds.nseg;
         const uint64_t slots = 32ull * (uint64_t)ctx->prop.multiProcessorCount;
         const uint64_t room = slots > n_coop + slots / 8 ? slots - n_coop : slots / 8;
         uint32_t per_job = 1;
         while (per_job < 32 && n_serial > room * per_job) per_job *= 2;
-        // packed streams cost issue slots per WARP: with refinement scans among them (most of the symbols of a frame) a
-        // batch that fills the machine at 4 streams per warp would be bound by instruction issue again
-        // (a stream alone in its warp issues about 0.4 instructions per cycle: keep to 1.5 warps per scheduler)
-        if (b->prog_rec_units)
-            while (per_job < 32 && n_serial > 6ull * (uint64_t)ctx->prop.multiProcessorCount * per_job) per_job *= 2;
+        // ... but no more than 8 streams to a warp: the lanes of a packed warp are at different places of the bit reader, and
+        // at 32 lanes nearly every refill of the warp runs the byte-wise path for some lane (FF bytes); late jobs simply start
+        // behind early ones.  Measured per 1024 frames: 32 lanes 143.7 ms, 16: 144.0, 8: 134.7, 4: 144.1, 2: 152.6.
+        per_job = std::min<uint32_t>(per_job, 8);
         if (const char *e = getenv("JB_K1C_LANES")) per_job = (uint32_t)std::min(32, std::max(1, atoi(e))); // tuning knob
         for (uint32_t rank = 0; rank < b->prog_max_scans; rank++) {
             std::vector<JbProgLane> packed;
@@ -1350,7 +1305,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
                 if (rank >= order[n].size()) continue;
                 const uint32_t k = order[n][rank];
                 const JbDevScan &ds = b->plans[b->prog_images[n]].scans[k];
-                const bool coop = whole_warp(ds); // (k_entropy_progressive.cuh)
+                const bool coop = ds.ncomp == 1 && ds.ss != 0 && ds.ah != 0; // (k_entropy_progressive.cuh)
                 for (uint32_t seg = 0; seg < ds.nseg; seg++) {
                     const JbProgLane e{b->prog_images[n], k, seg, 0};
                     if (coop) {
@@ -1424,10 +1379,6 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             JB_CUDA_B(cudaMemcpyAsync(b->d_prog_lanes, b->h_prog_lanes.data(), sizeof(JbProgLane) * b->h_prog_lanes.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
         JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_progress, sizeof(uint32_t) * (b->h_scans.size() + 1)));
-        if (b->prog_rec_units) {
-            JB_CUDA_B(jb_malloc_async(ctx, &b->d_nzmask, sizeof(unsigned long long) * b->prog_coef_blocks));
-            JB_CUDA_B(jb_malloc_async(ctx, &b->d_records, 32 * b->prog_rec_units));
-        }
     }
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
@@ -1595,33 +1546,17 @@ static int launch_kernels(jb_batch *b)
         // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
         JB_CUDA(ctx, jb_fill_async(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
         JB_CUDA(ctx, jb_fill_async(b->d_prog_progress, 0, sizeof(uint32_t) * (b->h_scans.size() + 1), st));
-        if (b->prog_rec_units) {
-            JB_CUDA(ctx, jb_fill_async(b->d_nzmask, 0, sizeof(unsigned long long) * b->prog_coef_blocks, st));
-            JB_CUDA(ctx, jb_fill_async(b->d_records, 0, 32 * b->prog_rec_units, st));
-            launches += 2;
-        }
         const uint32_t njobs = (uint32_t)b->h_prog_jobs.size();
         if (b->trace && !b->d_prog_trace) JB_CUDA(ctx, jb_malloc_async(ctx, &b->d_prog_trace, sizeof(unsigned long long) * 4 * njobs));
         if (b->trace)
             jb_k1c_progressive_scans<true><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
                                                                  b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace,
-                                                                 b->d_nzmask, b->d_records, b->prog_coef_first);
+                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace);
         else
             jb_k1c_progressive_scans<false><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
                                                                   b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                                  b->d_prog_progress + b->h_scans.size(), nullptr,
-                                                                  b->d_nzmask, b->d_records, b->prog_coef_first);
+                                                                  b->d_prog_progress + b->h_scans.size(), nullptr);
         launches += 2;
-        if (b->prog_rec_units) { // coefficient side of the refinement scans that were decoded one stream per lane
-            uint64_t most = 0;
-            for (uint32_t i : b->prog_images) most = std::max(most, b->plans[i].total_blocks);
-            const unsigned per_cta = JB_K1C_APPLY_WARPS * JB_K1C_APPLY_BLOCKS;
-            dim3 agrid((unsigned)((most + per_cta - 1) / per_cta), (unsigned)b->prog_images.size());
-            jb_k1c_apply_refinements<<<agrid, JB_K1C_APPLY_WARPS * 32, 0, st>>>(b->d_images, b->d_scans, b->d_image_list + b->prog_list_off,
-                                                                              b->d_records, b->d_coef);
-            launches++;
-        }
         mark("jb_k1c_progressive_scans");
     }
     if (!b->ll_images.empty()) {
@@ -1932,8 +1867,6 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_prog_lanes) cudaFreeAsync(b->d_prog_lanes, b->ctx->stream);
     if (b->d_prog_progress) cudaFreeAsync(b->d_prog_progress, b->ctx->stream);
     if (b->d_prog_trace) cudaFreeAsync(b->d_prog_trace, b->ctx->stream);
-    if (b->d_nzmask) cudaFreeAsync(b->d_nzmask, b->ctx->stream);
-    if (b->d_records) cudaFreeAsync(b->d_records, b->ctx->stream);
     if (b->d_ranges) cudaFreeAsync(b->d_ranges, b->ctx->stream);
     if (b->d_clean) cudaFreeAsync(b->d_clean, b->ctx->stream);
     if (b->d_clean_len) cudaFreeAsync(b->d_clean_len, b->ctx->stream);

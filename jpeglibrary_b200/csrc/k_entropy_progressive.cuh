@@ -14,7 +14,7 @@
 //   * scans commute unless they share a component and overlap in band (the host records those producers per scan);
 //   * a consumer needs block u of its producer only when it gets to block u itself: dependent scans run
 //     CONCURRENTLY, the consumer a few blocks behind the producer.  Producers publish their block count with a
-//     release store every JB_K1C_PUBLISH units, consumers acquire it (and read coefficients past L1, ld.cg).
+//     release store every JB_K1C_PUBLISH units, consumers poll it (relaxed) and read coefficients past L1 (ld.cg).
 // libjpeg's 10-scan script has the chain {Y 1-5, Y 6-63} -> Y refine -> Y refine: instead of three passes in a row
 // (43 + 61 + 111 ms for a batch of 1080p frames) the frame takes about as long as its slowest scan.
 // One warp per job (JbProgJob): AC refinement scans are decoded by the whole warp (the serial symbol chain of one
@@ -36,9 +36,9 @@ __device__ __forceinline__ uint32_t jb_prog_bits(JbBitReader &br, int k)
 #define JB_K1C_SPIN_LIMIT (1u << 19) // x 8 us: a producer that does not move for seconds -> JB_ST_STALLED, never a hang
 
 // A consumer polls its producer's progress with a RELAXED load.  An acquire load is a load plus CCTL.IVALL -- it throws the
-// SM's whole L1 away, and with it the Huffman tables and stream lines of every other warp of the SM (ncu, round 2: table
-// look-ups waiting on L2 were the top stall).  Nothing a producer publishes is ever read through L1 here: coefficients and
-// nonzero maps are read with ld.cg, and the loads are issued behind the branch that tests the progress value.
+// SM's whole L1 away, and with it the Huffman tables and stream lines of every other warp of the SM (150 -> 144 ms per
+// 1024 frames).  Nothing a producer publishes is ever read through L1 here: coefficients are read with ld.cg, and those
+// loads are issued behind the branch that tests the progress value.
 __device__ __forceinline__ uint32_t jb_ld_progress(const uint32_t *p)
 {
     uint32_t v;
@@ -57,8 +57,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                          const JbHuffTable *__restrict__ tables,
                          const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
                          const JbScanResult *__restrict__ scanres, int16_t *coef, uint32_t *__restrict__ status,
-                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace,
-                         unsigned long long *nzmask, uint4 *records, unsigned long long coef_first)
+                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace)
 {
     const int lane = threadIdx.x;
     uint32_t turn = 0;
@@ -369,137 +368,6 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (++bx == wb) { bx = 0; by++; }
             publish(u + 1);
         }
-    } else if (sc.ah != 0) {
-        // ---- AC refinement, ONE STREAM PER LANE (ReadBlockProgressiveACRefined :313-419; the host packs these jobs when the
-        // launch has the nonzero maps and the record buffer).  What the refinement decoder needs of a block's history is
-        // WHICH positions of the band are nonzero -- a nonzero position costs one correction bit, a zero one counts down
-        // the symbol's run -- never the values.  So the serial chain of a stream works on two 64-bit maps per block (zero /
-        // nonzero positions at or behind k) held in registers: "the (r+1)-th zero from k on" is a bit select, the number of
-        // correction bits in front of it a popcount.  It does not touch the coefficients at all: per block it leaves a
-        // record {new positions, their signs, the correction bits in the order read} and ORs the new positions into the
-        // block's map for the scans that follow it; jb_k1c_apply_refinements patches the store afterwards, every block
-        // in parallel.  One symbol costs one lane about 90 instructions where the whole-warp decoder spends 71 warp
-        // instructions on it: 8.5e10 warp instructions per 1024 frames become a few 1e9, and the kernel is bound by the
-        // latency of the longest scan chain instead of by instruction issue.
-        const int c = sc.comp[0];
-        const int ss = sc.ss, se = sc.se;
-        const uint64_t band = (se >= 63 ? ~0ull : ((1ull << (se + 1)) - 1ull)) & ~((1ull << ss) - 1ull);
-        const uint32_t band_lo = (uint32_t)band, band_hi = (uint32_t)(band >> 32);
-        const uint32_t wb = sc.wb, pitch = im.comp_plane_w[c];
-        unsigned long long *const mrow = nzmask + (im.coef_off - coef_first) + im.comp_plane_off[c];
-        uint4 *rec = records + ((size_t)sc.rec_off + first) * 2;
-        const JbHuffTable *actab = reinterpret_cast<const JbHuffTable *>(tab_base + (size_t)sc.ac_tab[0] * sizeof(JbHuffTable));
-        const uint32_t end = first + count;
-        uint32_t u = first;
-        uint32_t by = first / wb, bx = first - by * wb;
-        uint32_t zk_lo = 0, zk_hi = 0, hk_lo = 0, hk_hi = 0;    // zero / nonzero history positions of the band at or behind k
-        uint32_t nw_lo = 0, nw_hi = 0, sg_lo = 0, sg_hi = 0;    // this block's record: new positions, positive signs,
-        uint32_t cr_lo = 0, cr_hi = 0;                          // correction bits (bit t = the t-th nonzero position's)
-        int ncr = 0, k = ss;
-        unsigned long long nxt = 0;
-        bool have_nxt = false;
-        size_t cur = 0; // index of the open block in the plane
-        auto open_block = [&]() {
-            cur = (size_t)by * pitch + bx;
-            unsigned long long m;
-            if (have_nxt) m = nxt;
-            else { wait_for(u); m = __ldcg(mrow + cur); }
-            const uint32_t m_lo = (uint32_t)m, m_hi = (uint32_t)(m >> 32);
-            zk_lo = band_lo & ~m_lo; zk_hi = band_hi & ~m_hi;
-            hk_lo = band_lo & m_lo; hk_hi = band_hi & m_hi;
-            // the next block's map, when its history is final already (no waiting here: the load is off the chain)
-            have_nxt = u + 1 < end && u + 1 < avail;
-            if (have_nxt) {
-                const uint32_t nbx = bx + 1 == wb ? 0u : bx + 1, nby = bx + 1 == wb ? by + 1 : by;
-                nxt = __ldcg(mrow + (size_t)nby * pitch + nbx);
-            }
-        };
-        auto read_corr = [&](int n) { // n correction bits, appended to the record in the order read
-            while (n > 0) {
-                const int cnt = min(n, 24);
-                if (br.n < cnt) br.ensure32();
-                const uint32_t v = __brev(br.take(cnt)) >> (32 - cnt);
-                const int sh = ncr & 31;
-                const uint32_t a_lo = v << sh, a_hi = __funnelshift_l(v, 0u, sh);
-                if (ncr < 32) { cr_lo |= a_lo; cr_hi |= a_hi; } else cr_hi |= a_lo;
-                ncr += cnt;
-                n -= cnt;
-            }
-        };
-        if (count) open_block();
-        while (u < end && !err) {
-            bool fin = false;
-            if (eobrun == 0) {
-                br.ensure32(); // >= 33 bits: the code (<= 16), a sign bit or <= 14 run bits
-                uint32_t e = jb_huff_lookup(actab, br.peek16());
-                if (e == 0xFFFFFFFFu) { err |= JB_ST_BAD_CODE; e = 0x0001u; }
-                br.skip_code(e & 0xFFu);
-                const int r = (int)(e >> 12), sz = (int)(e >> 8) & 15;
-                int sgn = 0; // a new coefficient: +1 -> p1, -1 -> m1
-                bool eob = false;
-                if (sz != 0) {
-                    sgn = br.take(1) != 0 ? 1 : -1;
-                } else if (r != 15) {
-                    eobrun = 1 << r;
-                    if (r != 0) eobrun += (int)br.take(r);
-                    eob = true;
-                }
-                if (!eob) {
-                    // the (r+1)-th zero-history position at or behind k; the band end if there are fewer
-                    const int cl = __popc(zk_lo), nz = cl + __popc(zk_hi);
-                    int n;
-                    if (r < nz) {
-                        const bool in_lo = r < cl;
-                        uint32_t w = in_lo ? zk_lo : zk_hi;
-                        for (int i = in_lo ? r : r - cl; i > 0; i--) w &= w - 1;
-                        const int b = __ffs((int)w) - 1;
-                        const uint32_t bit = 1u << b, upto = bit | (bit - 1u); // the position and everything in front of it
-                        if (in_lo) {
-                            n = __popc(hk_lo & upto);
-                            zk_lo &= ~upto; hk_lo &= ~upto;
-                            if (sgn != 0) { nw_lo |= bit; if (sgn > 0) sg_lo |= bit; }
-                            k = b + 1;
-                        } else {
-                            n = __popc(hk_lo) + __popc(hk_hi & upto);
-                            zk_lo = 0; hk_lo = 0;
-                            zk_hi &= ~upto; hk_hi &= ~upto;
-                            if (sgn != 0) { nw_hi |= bit; if (sgn > 0) sg_hi |= bit; }
-                            k = b + 33;
-                        }
-                    } else {
-                        n = __popc(hk_lo) + __popc(hk_hi);
-                        zk_lo = zk_hi = hk_lo = hk_hi = 0;
-                        if (sgn != 0 && se < 63) { // (the reference writes at se + 1 when the run overshoots the band)
-                            const uint32_t bit = 1u << ((se + 1) & 31);
-                            if (se + 1 < 32) { nw_lo |= bit; if (sgn > 0) sg_lo |= bit; }
-                            else { nw_hi |= bit; if (sgn > 0) sg_hi |= bit; }
-                        }
-                        k = se + 2;
-                    }
-                    read_corr(n);
-                }
-            }
-            if (eobrun > 0) { // the rest of the band takes its correction bits and the block is done
-                read_corr(__popc(hk_lo) + __popc(hk_hi));
-                --eobrun;
-                fin = true;
-            }
-            if (fin || k > se) {
-                if (nw_lo | nw_hi) {
-                    rec[0] = make_uint4(nw_lo, nw_hi, sg_lo, sg_hi);
-                    atomicOr(mrow + cur, ((unsigned long long)nw_hi << 32) | nw_lo);
-                }
-                if (cr_lo | cr_hi) rec[1] = make_uint4(cr_lo, cr_hi, 0u, 0u);
-                rec += 2;
-                nw_lo = nw_hi = sg_lo = sg_hi = cr_lo = cr_hi = 0;
-                ncr = 0;
-                k = ss;
-                u++;
-                if (++bx == wb) { bx = 0; by++; }
-                publish(u);
-                if (u < end) open_block();
-            }
-        }
     } else {
         // ---- AC first scan (:259-305), ONE loop over symbols: the lanes of a packed warp are in different blocks of
         // different images, and a loop nest per block would make every lane wait for the longest block of the warp
@@ -514,10 +382,6 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         uint32_t by = first / wb, bx = first - by * wb;
         int16_t *blk = base + ((size_t)by * pitch + bx) * 64;
         int i = ss;
-        // one-stream-per-lane refinement scans read, per block, WHICH coefficients are nonzero and nothing else: the scans
-        // that place coefficients keep a 64-bit map per block next to the store (see the refinement branch above)
-        unsigned long long *mrow = nzmask ? nzmask + (im.coef_off - coef_first) + im.comp_plane_off[c] : nullptr;
-        uint32_t ms_lo = 0, ms_hi = 0;
         if (count) wait_for(first);
         while (u < end && !err) {
             bool block_done = false;
@@ -543,18 +407,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (sz != 0) {
                 i += r;
                 const int v = jb_extend((int)br.take(sz), sz);
-                const int p = min(i, 63);
-                const int16_t val = (int16_t)(v << al);
-                blk[p] = val;
-                if (mrow) {
-                    const uint32_t bit = 1u << (p & 31);
-                    if (val != 0) {
-                        if (p < 32) ms_lo |= bit; else ms_hi |= bit;
-                    } else { // (an absurd Al shifted the value out of the int16: the position reads as zero from here on)
-                        if (p < 32) ms_lo &= ~bit; else ms_hi &= ~bit;
-                        atomicAnd(mrow + (size_t)by * pitch + bx, ~(1ull << p));
-                    }
-                }
+                blk[min(i, 63)] = (int16_t)(v << al);
                 i++;
             } else if (r == 15) {
                 i += 16;
@@ -565,10 +418,6 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                 block_done = true;
             }
             if (block_done || i > se) {
-                if (ms_lo | ms_hi) {
-                    atomicOr(mrow + (size_t)by * pitch + bx, ((unsigned long long)ms_hi << 32) | ms_lo);
-                    ms_lo = ms_hi = 0;
-                }
                 u++;
                 i = ss;
                 if (++bx == wb) { bx = 0; by++; }
@@ -605,90 +454,5 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (sc.nseg == 1) jb_st_release(my_progress, sc.nunits);
             else atomicAdd(my_progress, 1u);
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K1c-apply: the coefficient side of the one-stream-per-lane AC refinement scans.  Per block and scan the entropy kernel
-// left {new positions, their signs, correction bits in the order read}; here one warp patches one block, every lane two
-// neighbouring coefficients, the refinement scans of the block's component in scan order (ReadBlockProgressiveACRefined
-// :313-419: a nonzero-history coefficient of the band whose correction bit is set and whose bit Al is clear moves away
-// from zero by 1 << Al; a new coefficient is +-(1 << Al)).  "The t-th nonzero position of the band" is a rank over two
-// ballots.  Blocks whose records are empty are not even loaded.
-// ---------------------------------------------------------------------------------------------
-#define JB_K1C_APPLY_WARPS 8
-#define JB_K1C_APPLY_BLOCKS 32   // blocks per warp
-#define JB_K1C_APPLY_MAX_SCANS 64
-struct JbApplyScan {
-    uint32_t rec_off, wb, hb, band_lo, band_hi;
-    int comp, al, pad;
-};
-
-__global__ void __launch_bounds__(JB_K1C_APPLY_WARPS * 32)
-jb_k1c_apply_refinements(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
-                         const uint32_t *__restrict__ image_list, const uint4 *__restrict__ records, int16_t *coef)
-{
-    __shared__ JbApplyScan s_scan[JB_K1C_APPLY_MAX_SCANS];
-    __shared__ int s_n;
-    const JbDevImage &im = images[image_list[blockIdx.y]];
-    const uint32_t total = im.comp_plane_off[im.ncomp - 1] +
-                           im.comp_plane_w[im.ncomp - 1] * im.mcus_per_col * im.comp_v[im.ncomp - 1];
-    const uint32_t cta_first = blockIdx.x * (JB_K1C_APPLY_WARPS * JB_K1C_APPLY_BLOCKS);
-    if (cta_first >= total) return;
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (uint32_t k = 0; k < im.nscans && n < JB_K1C_APPLY_MAX_SCANS; k++) {
-            const JbDevScan &sc = scans[im.scan_base + k];
-            if (sc.seq || sc.ncomp != 1 || sc.ss == 0 || sc.ah == 0 || sc.rec_off == 0xFFFFFFFFu) continue;
-            JbApplyScan a;
-            const uint64_t band = (sc.se >= 63 ? ~0ull : ((1ull << (sc.se + 1)) - 1ull)) & ~((1ull << sc.ss) - 1ull);
-            a.rec_off = sc.rec_off; a.wb = sc.wb; a.hb = sc.hb;
-            a.band_lo = (uint32_t)band; a.band_hi = (uint32_t)(band >> 32);
-            a.comp = sc.comp[0]; a.al = sc.al; a.pad = 0;
-            s_scan[n++] = a;
-        }
-        s_n = n;
-    }
-    __syncthreads();
-    const int nscan = s_n;
-    if (nscan == 0) return;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const uint32_t below = (1u << lane) - 1u;
-    const int sh = 2 * (lane & 15); // my two positions inside a 32-bit half of a 64-bit position map
-    uint32_t *store = reinterpret_cast<uint32_t *>(coef + im.coef_off * 64);
-    const uint32_t t0 = cta_first + wid * JB_K1C_APPLY_BLOCKS;
-    for (uint32_t t = t0; t < min(t0 + JB_K1C_APPLY_BLOCKS, total); t++) {
-        int c = 0;
-        for (int i = 1; i < im.ncomp; i++) if (t >= im.comp_plane_off[i]) c = i;
-        const uint32_t local = t - im.comp_plane_off[c], pw = im.comp_plane_w[c];
-        const uint32_t by = local / pw, bx = local - by * pw;
-        bool loaded = false, changed = false;
-        int c0 = 0, c1 = 0; // coefficients 2 * lane and 2 * lane + 1
-        for (int s = 0; s < nscan; s++) {
-            const JbApplyScan a = s_scan[s];
-            if (a.comp != c || bx >= a.wb || by >= a.hb) continue;
-            const uint4 *r = records + ((size_t)a.rec_off + (size_t)by * a.wb + bx) * 2;
-            const uint4 r0 = __ldg(r), r1 = __ldg(r + 1); // {new lo, new hi, sign lo, sign hi}, {corrections lo, hi}
-            if ((r0.x | r0.y | r1.x | r1.y) == 0) continue;
-            if (!loaded) {
-                const uint32_t w = store[(size_t)t * 32 + lane];
-                c0 = (int16_t)(w & 0xFFFFu); c1 = (int16_t)(w >> 16);
-                loaded = true;
-            }
-            const int p1 = 1 << a.al, m1 = -(1 << a.al);
-            const uint32_t bandw = (lane < 16 ? a.band_lo : a.band_hi) >> sh;
-            const bool h0 = (bandw & 1u) && c0 != 0, h1 = (bandw & 2u) && c1 != 0; // nonzero history inside the band
-            const uint32_t he = __ballot_sync(0xFFFFFFFFu, h0), ho = __ballot_sync(0xFFFFFFFFu, h1);
-            const int rank0 = __popc(he & below) + __popc(ho & below), rank1 = rank0 + (h0 ? 1 : 0);
-            const uint32_t cb0 = ((rank0 & 32 ? r1.y : r1.x) >> (rank0 & 31)) & 1u;
-            const uint32_t cb1 = ((rank1 & 32 ? r1.y : r1.x) >> (rank1 & 31)) & 1u;
-            if (h0 && cb0 && (c0 & p1) == 0) c0 = (int16_t)(c0 + (c0 >= 0 ? p1 : m1));
-            if (h1 && cb1 && (c1 & p1) == 0) c1 = (int16_t)(c1 + (c1 >= 0 ? p1 : m1));
-            const uint32_t nw = (lane < 16 ? r0.x : r0.y) >> sh, sg = (lane < 16 ? r0.z : r0.w) >> sh;
-            if (nw & 1u) c0 = (int16_t)(sg & 1u ? p1 : m1);
-            if (nw & 2u) c1 = (int16_t)(sg & 2u ? p1 : m1);
-            changed = true;
-        }
-        if (changed) store[(size_t)t * 32 + lane] = ((uint32_t)c0 & 0xFFFFu) | ((uint32_t)c1 << 16);
     }
 }

@@ -372,17 +372,17 @@ def test_progressive_synthetic(kw):
 
 
 @pytest.mark.parametrize("order", [
-    [0, 1, 4, 5, 9, 2, 3, 7, 8, 6],          # luma chain first: legal progression, refinement scans one stream per lane
+    [0, 1, 4, 5, 9, 2, 3, 7, 8, 6],          # luma chain first: a legal progression in another order
     [0, 2, 3, 7, 8, 1, 4, 5, 9, 6],          # chroma first
-    [0, 1, 4, 5, 9, 1, 2, 3, 7, 8, 6],       # an AC first scan BEHIND the refinement of its band: whole-warp decoder
+    [0, 1, 4, 5, 9, 1, 2, 3, 7, 8, 6],       # an AC first scan BEHIND the refinement of its band
     [0, 1, 2, 3, 5, 4, 6, 7, 8, 9],          # refinement in front of the band's first scan: the stream does not decode
     [0, 1, 2, 3, 4, 5, 6, 7, 8, 5, 9],       # a refinement scan twice: the second pass does not decode
 ], ids=lambda o: "".join(map(str, o)))
 def test_progressive_scan_scripts_out_of_order(order):
     """The reference decodes the scans of a progressive frame in file order whatever the progression
-    (JpegHuffmanProgressiveScanDecoder.ProcessScan :57-90).  Scripts that refine a band only after it was coded go through
-    the one-stream-per-lane refinement decoder + jb_k1c_apply_refinements, the others through the whole-warp decoder on
-    the store: both must give what the oracle gives, coefficient by coefficient, or the same error."""
+    (JpegHuffmanProgressiveScanDecoder.ProcessScan :57-90).  K1c runs the scans concurrently behind their producers (scans
+    that share a component and overlap in band): any script must give what the oracle gives, coefficient by coefficient,
+    or the same error."""
     base = synth.synth_jpeg(9, 320, 240, progressive=True, subsampling="4:4:4", quality=85)
     blob = synth.reorder_progressive_scans(base, order)
     try:
