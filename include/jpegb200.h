@@ -237,6 +237,9 @@ JB_API int jb_encode_batch_launch_count(jb_encode_batch *b);
 JB_API void jb_encode_batch_destroy(jb_encode_batch *b);
 /* The table builder on the host (JpegHuffmanEncodingTableBuilder.Build(optimal: false), :62-176). */
 JB_API int jb_build_huffman_table(const uint32_t frequencies[256], int table_class, int identifier, jb_huff_spec *out);
+/* The same with MostOptimalCoding = true: JpegHuffmanEncodingTableBuilder.Build(optimal: true), package merge (:287-413).
+   Host only: histograms from jb_encode_batch_histograms, tables back in through jb_encode_batch_set_table. */
+JB_API int jb_build_huffman_table_optimal(const uint32_t frequencies[256], int table_class, int identifier, jb_huff_spec *out);
 
 /* Host only (no device needed): how a frame that is decoded through the scan list (progressive, or sequential with
    several scans) is planned.  Ten words per scan: its place in the job order, number of producer scans (255 = every

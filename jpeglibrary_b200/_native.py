@@ -132,6 +132,7 @@ _sigs = {
         "jb_encode_batch_launch_count": (C.c_int, [_vp]),
         "jb_encode_batch_destroy": (None, [_vp]),
         "jb_build_huffman_table": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(HuffSpec)]),
+        "jb_build_huffman_table_optimal": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(HuffSpec)]),
         "jb_render_from_coefficients": (C.c_int, [_vp, C.POINTER(ImageDesc), _vp, C.POINTER(OutputDesc)]),
     },
     host: {

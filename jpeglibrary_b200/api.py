@@ -779,8 +779,6 @@ class JpegEncoder:
             raise InvalidOperationException("Output is not specified.")
         if not self._components:
             raise InvalidOperationException("No component is specified.")
-        if self.MostOptimalCoding:
-            raise NotSupportedException("package-merge table construction is not on the GPU path")
         ctx = self._ctx or Context.default()
         reader = self._reader_pixels()
         desc = self._desc(reader)
@@ -789,14 +787,17 @@ class JpegEncoder:
         try:
             ctx.check(N.cuda.jb_encode_batch_transform(h))
             build = [t for t in self._tables if t[2] is None]
-            if build and not self.use_host_table_builder:
+            # MostOptimalCoding (JpegEncoder.cs:43, builder.Build(optimal: true)): the package-merge builder runs on the host
+            # over the histograms K3b left, like a caller-side builder would
+            if build and not self.use_host_table_builder and not self.MostOptimalCoding:
                 ctx.check(N.cuda.jb_encode_batch_build_tables(h))
             elif build:
                 hist = np.zeros((8, 256), dtype=np.uint32)
                 ctx.check(N.cuda.jb_encode_batch_histograms(h, hist.ctypes.data, 1))
+                builder = N.cuda.jb_build_huffman_table_optimal if self.MostOptimalCoding else N.cuda.jb_build_huffman_table
                 for cls, ident, _ in build:
                     spec = N.HuffSpec()
-                    rc = N.cuda.jb_build_huffman_table(hist[cls * 4 + ident].ctypes.data, cls, ident, C.byref(spec))
+                    rc = builder(hist[cls * 4 + ident].ctypes.data, cls, ident, C.byref(spec))
                     if rc:
                         raise InvalidOperationException("No symbol is recorded.")
                     ctx.check(N.cuda.jb_encode_batch_set_table(h, 0, C.byref(spec)))
@@ -859,10 +860,11 @@ class JpegEncoder:
             self._output += data
 
 
-def encode_rgb(rgb, quality=75, subsampling=(2, 2), context=None, host_builder=False):
+def encode_rgb(rgb, quality=75, subsampling=(2, 2), context=None, host_builder=False, most_optimal=False):
     """apps/JpegEncode/EncodeAction.cs:37-63 with --optimize-coding, on the GPU. Returns (bytes, encoder)."""
     enc = JpegEncoder(context)
     enc.use_host_table_builder = host_builder
+    enc.MostOptimalCoding = most_optimal
     enc.SetQuantizationTable(JpegStandardQuantizationTable.ScaleByQuality(JpegStandardQuantizationTable.GetLuminanceTable(0, 0), quality))
     enc.SetQuantizationTable(JpegStandardQuantizationTable.ScaleByQuality(JpegStandardQuantizationTable.GetChrominanceTable(0, 1), quality))
     for isdc, ident in ((True, 0), (False, 0), (True, 1), (False, 1)):
@@ -1008,8 +1010,6 @@ class JpegOptimizer:
     def Scan(self):                # :72-154
         if self._input is None or len(self._input) == 0:
             raise InvalidOperationException("Input buffer is not specified.")
-        if self.MostOptimalCoding:
-            raise NotSupportedException("package-merge table construction is not on the GPU path")
         ctx = self._ctx or Context.default()
         self._close()
         p = Parsed(self._input)
@@ -1049,7 +1049,16 @@ class JpegOptimizer:
         ctx.check(N.cuda.jb_encode_batch_create(ctx.handle, C.byref(e), 1, C.byref(h)))
         self._batch = h
         ctx.check(N.cuda.jb_encode_batch_transform(h))
-        ctx.check(N.cuda.jb_encode_batch_build_tables(h))
+        if self.MostOptimalCoding:  # JpegOptimizer.cs:39: builder.Build(optimal: true) over the scan's symbol statistics
+            hist = np.zeros((8, 256), dtype=np.uint32)
+            ctx.check(N.cuda.jb_encode_batch_histograms(h, hist.ctypes.data, 1))
+            for cls, ident in self._table_order:
+                spec = N.HuffSpec()
+                if N.cuda.jb_build_huffman_table_optimal(hist[cls * 4 + ident].ctypes.data, cls, ident, C.byref(spec)):
+                    raise InvalidOperationException("No symbol is recorded.")
+                ctx.check(N.cuda.jb_encode_batch_set_table(h, 0, C.byref(spec)))
+        else:
+            ctx.check(N.cuda.jb_encode_batch_build_tables(h))
         self._parsed = p
 
     def Optimize(self, strip=True):  # :546-647

@@ -1991,6 +1991,143 @@ static void launch_k3(int nc, int hs, int vs, dim3 grid, cudaStream_t st, const 
     else jb_k3_fdct_quant_warp<3, 2, 2><<<grid, T, 0, st>>>(im, list, q, coef, upw);
 }
 
+// ------------------------------------------------------------------------------------------------
+// JpegHuffmanEncodingTableBuilder.BuildUsingPackageMerge (JpegHuffmanEncodingTableBuilder.cs:287-413): the table that
+// MostOptimalCoding = true asks for.  Host only -- the histograms come back from K3b (jb_encode_batch_histograms), the
+// tables go in through jb_encode_batch_set_table.  Its sorts are the runtime's unstable introsort (Array.Sort /
+// List<T>.Sort with a Comparison), so the order of equal keys is part of the result: net_sort below is that algorithm
+// (the one jb_hs_introsort in k_encode.cuh specialises for the standard method) over any element and comparison.
+namespace {
+
+template <typename T, typename Cmp>
+struct NetSort {
+    T *k;
+    Cmp cmp;
+    void swap(int i, int j) { if (i != j) std::swap(k[i], k[j]); }
+    void swap_if_greater(int i, int j) { if (i != j && cmp(k[i], k[j]) > 0) std::swap(k[i], k[j]); }
+    void down_heap(int lo, int i, int n)
+    {
+        T d = k[lo + i - 1];
+        while (i <= n / 2) {
+            int child = 2 * i;
+            if (child < n && cmp(k[lo + child - 1], k[lo + child]) < 0) child++;
+            if (!(cmp(d, k[lo + child - 1]) < 0)) break;
+            k[lo + i - 1] = k[lo + child - 1];
+            i = child;
+        }
+        k[lo + i - 1] = d;
+    }
+    void intro(int lo, int n, int depth)
+    {
+        while (n > 1) {
+            if (n <= 16) {
+                if (n == 2) { swap_if_greater(lo, lo + 1); return; }
+                if (n == 3) { swap_if_greater(lo, lo + 1); swap_if_greater(lo, lo + 2); swap_if_greater(lo + 1, lo + 2); return; }
+                for (int i = lo; i < lo + n - 1; i++) { // insertion sort
+                    T t = k[i + 1];
+                    int j = i;
+                    while (j >= lo && cmp(t, k[j]) < 0) { k[j + 1] = k[j]; j--; }
+                    k[j + 1] = t;
+                }
+                return;
+            }
+            if (depth == 0) { // heap sort
+                for (int i = n / 2; i >= 1; i--) down_heap(lo, i, n);
+                for (int i = n; i > 1; i--) { swap(lo, lo + i - 1); down_heap(lo, 1, i - 1); }
+                return;
+            }
+            depth--;
+            const int hi = lo + n - 1, mid = lo + ((n - 1) >> 1);
+            swap_if_greater(lo, mid);
+            swap_if_greater(lo, hi);
+            swap_if_greater(mid, hi);
+            const T pivot = k[mid];
+            swap(mid, hi - 1);
+            int left = lo, right = hi - 1;
+            while (left < right) {
+                while (cmp(k[++left], pivot) < 0) ;
+                while (cmp(pivot, k[--right]) < 0) ;
+                if (left >= right) break;
+                swap(left, right);
+            }
+            if (left != hi - 1) swap(left, hi - 1);
+            intro(left + 1, hi - left, depth);
+            n = left - lo;
+        }
+    }
+};
+
+template <typename T, typename Cmp>
+void net_sort(T *keys, int n, Cmp cmp)
+{
+    if (n < 2) return;
+    int depth = 0;
+    for (int t = n; t > 0; t >>= 1) depth++;
+    NetSort<T, Cmp>{keys, cmp}.intro(0, n, 2 * depth);
+}
+
+struct PmNode { long long freq; int index, left, right; }; // left < 0: a leaf (Node :456-476)
+
+int build_table_package_merge(const uint32_t *freq, uint8_t bits[16], uint8_t vals[256])
+{
+    std::vector<JbHSym> sy;
+    for (int i = 0; i < 256; i++)
+        if (freq[i]) sy.push_back(JbHSym{(long long)freq[i], (short)i, 0, 0});
+    memset(bits, 0, 16);
+    const int count = (int)sy.size();
+    if (count == 0) return 0;
+    sy.push_back(JbHSym{0, -1, 0, 0}); // the sentinel: frequency 0 here (:316-321), not 1 like the standard method's
+    const int n = count + 1;
+    net_sort(sy.data(), n, [](const JbHSym &x, const JbHSym &y) { return (y.freq > x.freq) - (y.freq < x.freq); });
+    std::vector<PmNode> pool;
+    pool.reserve((size_t)n * 34);
+    std::vector<std::vector<int>> level(16);
+    for (int l = 15; l >= 0; l--)
+        for (int i = 0; i < n; i++) {
+            level[l].push_back((int)pool.size());
+            pool.push_back(PmNode{sy[i].freq, i, -1, -1});
+        }
+    auto by_freq_desc = [&](int a, int b) { return (pool[b].freq > pool[a].freq) - (pool[b].freq < pool[a].freq); };
+    for (int l = 15; l > 0; l--) {
+        std::vector<int> &nodes = level[l];
+        net_sort(nodes.data(), (int)nodes.size(), by_freq_desc);
+        while (nodes.size() >= 2) { // package the two smallest, merge the package into the next level
+            const int n1 = nodes[nodes.size() - 1], n2 = nodes[nodes.size() - 2];
+            nodes.resize(nodes.size() - 2);
+            level[l - 1].push_back((int)pool.size());
+            pool.push_back(PmNode{pool[n1].freq + pool[n2].freq, 0, n1, n2});
+        }
+    }
+    net_sort(level[0].data(), (int)level[0].size(), [&](int a, int b) { return by_freq_desc(b, a); });
+    const int select = std::max(1, 2 * (n - 1));
+    std::vector<int> stack;
+    for (int i = 0; i < select; i++) { // TraverseNode :394-409: one more bit for every leaf under the node
+        stack.assign(1, level[0][i]);
+        while (!stack.empty()) {
+            const PmNode nd = pool[stack.back()];
+            stack.pop_back();
+            if (nd.left < 0) sy[nd.index].code_size++;
+            else { stack.push_back(nd.left); stack.push_back(nd.right); }
+        }
+    }
+    net_sort(sy.data(), n, [](const JbHSym &x, const JbHSym &y) { // SymbolComparer :428-453
+        if (x.code_size != y.code_size) return x.code_size > y.code_size ? 1 : -1;
+        if (x.freq != y.freq) return x.freq > y.freq ? -1 : 1;
+        return 0;
+    });
+    int at = 0;
+    for (int i = n - 1; i >= 0; i--)
+        if (sy[i].value == -1) { at = i; break; }
+    sy.erase(sy.begin() + at);
+    for (int i = 0; i < count; i++) {
+        if (sy[i].code_size >= 1 && sy[i].code_size <= 16) bits[sy[i].code_size - 1]++;
+        vals[i] = (uint8_t)sy[i].value;
+    }
+    return count;
+}
+
+} // namespace
+
 extern "C" {
 
 void jb_encode_batch_destroy(jb_encode_batch *b)
@@ -2366,6 +2503,18 @@ int jb_build_huffman_table(const uint32_t frequencies[256], int table_class, int
     out->identifier = (uint8_t)identifier;
     memcpy(out->bits, t.bits, 16);
     memcpy(out->values, t.vals, 256);
+    out->value_count = (uint16_t)n;
+    return JB_OK;
+}
+
+int jb_build_huffman_table_optimal(const uint32_t frequencies[256], int table_class, int identifier, jb_huff_spec *out)
+{
+    if (!frequencies || !out) return JB_ERR_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    const int n = build_table_package_merge(frequencies, out->bits, out->values);
+    if (n == 0) return JB_ERR_INVALID_OPERATION;
+    out->table_class = (uint8_t)table_class;
+    out->identifier = (uint8_t)identifier;
     out->value_count = (uint16_t)n;
     return JB_OK;
 }

@@ -112,7 +112,7 @@ typedef struct {
     int tq[JO_MAX_COMP], td[JO_MAX_COMP], ta[JO_MAX_COMP];
     uint16_t qt[4][64];                      /* zig-zag order, as SetQuantizationTable */
     int qt_present[4];
-    int optimize;                            /* 1: optimised Huffman (config 5) */
+    int optimize;                            /* 1: optimised Huffman (config 5); 2: MostOptimalCoding (package merge) */
 } jo_encode_params;
 
 typedef struct {
@@ -141,6 +141,8 @@ void jo_encoded_free(jo_encoded *e);
 /* Optimised table construction from a histogram: BuildUsingStandardMethod
    (JpegHuffmanEncodingTableBuilder.cs:69-176). Returns number of symbols. */
 int jo_build_huffman_table(const uint32_t freq[256], uint8_t bits[16], uint8_t vals[256]);
+/* The same with MostOptimalCoding = true: BuildUsingPackageMerge (JpegHuffmanEncodingTableBuilder.cs:287-413). */
+int jo_build_huffman_table_optimal(const uint32_t freq[256], uint8_t bits[16], uint8_t vals[256]);
 
 #ifdef __cplusplus
 }

