@@ -75,6 +75,10 @@ namespace JpegLibrary.Cuda
         [DllImport(Lib)] public static extern int jb_encode_batch_scan_length(IntPtr batch, int image, ulong* length);
         [DllImport(Lib)] public static extern int jb_encode_batch_read_scan(IntPtr batch, int image, byte* dst, ulong capacity);
         [DllImport(Lib)] public static extern void jb_encode_batch_destroy(IntPtr batch);
+        // table construction on the native side for callers without a managed builder at hand (the encoder subclass uses
+        // JpegHuffmanEncodingTableBuilder.Build(MostOptimalCoding) itself)
+        [DllImport(Lib)] public static extern int jb_build_huffman_table(uint* frequencies, int tableClass, int identifier, HuffSpec* table);
+        [DllImport(Lib)] public static extern int jb_build_huffman_table_optimal(uint* frequencies, int tableClass, int identifier, HuffSpec* table);
 
         // status code -> the exception the managed decoder throws in the same situation
         public static void Check(IntPtr ctx, int rc)
