@@ -449,7 +449,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
                 // ReceiveAndExtend (JpegHuffmanScanDecoder.cs:100-115): s magnitude bits follow the code
                 const uint32_t x = __funnelshift_l(lo, hi, len);
                 const uint32_t neg = ~(uint32_t)((int32_t)x >> 31); // all ones when the leading magnitude bit is 0
-                const uint32_t t = ((x ^ neg) >> 1) >> (31 - s);
+                const uint32_t t = __funnelshift_l(x ^ neg, 0u, s); // the top s bits (0 for s = 0): one SHF, not two and a subtraction
                 int v = (int)((t ^ neg) - neg);
                 hi = __funnelshift_lc(lo, hi, total);
                 lo = __funnelshift_lc(0u, lo, total);
