@@ -140,8 +140,14 @@ jb_k1b_count(const JbDevImage *__restrict__ images, const uint32_t *__restrict__
     if (threadIdx.x == 0) chunk_kept[im.chunk_base + blockIdx.x] = s_cnt;
 }
 
-// Pass 2: every lane compacts its 64 bytes through a 64-bit byte accumulator that emits aligned 32-bit words; only
-// the (at most three) bytes in front of the lane's first aligned word and behind its last one are byte stores.
+// Pass 2: every lane compacts its 64 bytes through a 64-bit byte accumulator that emits aligned 32-bit words -- into a
+// shared-memory image of the tile's output, laid out so that shared offset i is global byte (tile start & ~15) + i; the
+// CTA then writes the image out as 128-bit stores (only the partial 16-byte lines at its two ends go byte by byte).
+// Round 2: the lanes used to store their words straight to global memory, 32 lanes 64 bytes apart -- 32 sectors per
+// store instruction, 8x the sector writes the data needs, and the kernel ran at 34 % issue rate behind the LSU.
+#ifndef JB_K1B_STAGED_COPY
+#define JB_K1B_STAGED_COPY 1
+#endif
 __global__ void __launch_bounds__(JB_K1B_UTHREADS)
 jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
             const uint8_t *__restrict__ arena, const JbScanResult *__restrict__ scanres,
@@ -154,9 +160,12 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
     const uint32_t c0 = blockIdx.x * JB_K1B_CHUNK;
     if (c0 >= end && blockIdx.x > 0) return;
     const uint8_t *data = arena + im.data_off;
-    uint8_t *out = clean + im.data_off;
+    uint8_t *gout = clean + im.data_off; // (256-byte aligned)
     __shared__ uint32_t s_warp[JB_K1B_UTHREADS / 32];
     __shared__ uint32_t s_base;
+#if JB_K1B_STAGED_COPY
+    __shared__ __align__(16) uint8_t s_img[JB_K1B_UTILE + 32];
+#endif
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
         uint32_t base = 0;
@@ -177,7 +186,8 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
         }
         if (lane == 31) s_warp[wid] = incl;
         __syncthreads();
-        uint32_t off = s_base + incl - cnt, total = 0;
+        const uint32_t tile_out = s_base; // first byte of the clean stream this tile writes
+        uint32_t off = tile_out + incl - cnt, total = 0;
 #pragma unroll
         for (int i = 0; i < JB_K1B_UTHREADS / 32; i++) {
             const uint32_t t = s_warp[i];
@@ -185,6 +195,13 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
             total += t;
         }
         // bytes [off, off + cnt) of the clean stream are this lane's
+#if JB_K1B_STAGED_COPY
+        uint8_t *const out = s_img;
+        const uint32_t adj = tile_out & ~15u; // global byte offset - adj = its place in the image
+#else
+        uint8_t *const out = gout;
+        const uint32_t adj = 0;
+#endif
         uint64_t acc = 0;  // pending output bytes, memory order from bit 0
         uint32_t na = 0;   // how many
         uint32_t o = off;  // where the next pending byte goes
@@ -197,29 +214,45 @@ jb_k1b_copy(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ 
             na += __popc(nib);
             // bytes in front of the first aligned word leave one by one (at most three per lane)
             while (na != 0 && (o & 3u) != 0) {
-                out[o++] = (uint8_t)acc;
+                out[o++ - adj] = (uint8_t)acc;
                 acc >>= 8;
                 na--;
             }
             if (na >= 4) {
-                *reinterpret_cast<uint32_t *>(out + o) = (uint32_t)acc;
+                *reinterpret_cast<uint32_t *>(out + (o - adj)) = (uint32_t)acc;
                 acc >>= 32;
                 na -= 4;
                 o += 4;
             }
         }
         while (o < stop) { // at most three bytes are left
-            out[o++] = (uint8_t)acc;
+            out[o++ - adj] = (uint8_t)acc;
             acc >>= 8;
         }
         __syncthreads();
+#if JB_K1B_STAGED_COPY
+        {
+            const uint32_t g0 = tile_out & ~15u;                   // global offset of image byte 0
+            const uint32_t first = tile_out - g0, last = first + total; // the image's valid bytes
+            const uint32_t body0 = (first + 15u) & ~15u, body1 = last & ~15u; // whole 16-byte lines
+            for (uint32_t i = body0 + tid * 16; i < body1; i += JB_K1B_UTHREADS * 16)
+                *reinterpret_cast<uint4 *>(gout + g0 + i) = *reinterpret_cast<const uint4 *>(s_img + i);
+            // the partial lines at the two ends (a neighbouring tile or chunk owns their other bytes)
+            if (body0 > body1) { // everything lies inside one line
+                if (first + tid < last) gout[g0 + first + tid] = s_img[first + tid];
+            } else {
+                if (first + tid < body0) gout[g0 + first + tid] = s_img[first + tid];
+                if (body1 + tid < last) gout[g0 + body1 + tid] = s_img[body1 + tid];
+            }
+        }
+#endif
         if (tid == 0) s_base += total;
         __syncthreads();
     }
     // the chunk that holds the end of the stream pads it and publishes the clean length
     if (c0 + JB_K1B_CHUNK >= end) {
         const uint32_t n = s_base;
-        if (tid < 64) out[n + tid] = 0xFF; // padding (the arena keeps 64 spare bytes per image)
+        if (tid < 64) gout[n + tid] = 0xFF; // padding (the arena keeps 64 spare bytes per image)
         if (tid == 0) clean_len[image] = n;
     }
 }
