@@ -803,7 +803,12 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             if (sc.component_count > im.component_count)
                 return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
             ds.ss = 0; ds.se = 0;
+        } else if (sc.ss == 0) {
+            // a single-component scan with Ss = 0 is a DC scan whatever Se says (:149-166; the reference never validates
+            // the spectral selection)
+            ds.se = 0;
         } else {
+            // (AC scans with Ss > Se would decode nothing, with Se > 63 the reference indexes out of the block: refused)
             if (sc.se > 63 || sc.ss > sc.se)
                 return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse scan header.");
         }
@@ -816,7 +821,8 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
             if (dc == -2 || ac == -2) return fail(ctx, JB_ERR_INVALID_DATA, "image %d: %s", idx, "Failed to parse Huffman table.");
             // :100-104, :149-152, :168-172: the table a scan actually uses must be defined
             // :100-104 (every interleaved scan needs its DC tables, refinement or not), :149-152, :168-172
-            const bool need_dc = sequential || sc.component_count > 1 || (sc.ss == 0 && sc.ah == 0);
+            // (:149-152 asks for the DC table of every single-component scan with Ss = 0, DC refinement scans included)
+            const bool need_dc = sequential || sc.component_count > 1 || sc.ss == 0;
             const bool need_ac = sequential || (sc.component_count == 1 && sc.ss != 0);
             d.covered |= 1u << c;
             if ((need_dc && dc < 0) || (need_ac && ac < 0))

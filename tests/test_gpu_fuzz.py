@@ -251,3 +251,20 @@ def test_final_code_in_the_padding_is_accepted_like_the_reference(shape):
                     rejected += 1
     print(f"{accepted} streams accepted, {rejected} rejected, on both sides")
     assert accepted > 13 * len(intervals)  # cut streams among them
+
+
+def test_streams_the_campaign_found():
+    """profiles/r2_fuzz_campaign.txt: a gray progressive frame whose first scan says Ss 0 / Se 119 (a DC scan all the same:
+    the reference never looks at Se there) and one whose DC table definition was swallowed by a damaged segment length
+    (the reference asks for the DC table of every single-component scan with Ss = 0, the DC refinement scan included)."""
+    import os
+    here = os.path.join(os.path.dirname(__file__), "fixtures")
+    blob = open(os.path.join(here, "fuzz_gray_progressive_dc_scan_with_se.jpg"), "rb").read()
+    want = O.decode(blob, want_rgb=False)
+    got, err = run_gpu(blob)
+    assert err is None and np.array_equal(got, want.planes)
+    blob = open(os.path.join(here, "fuzz_gray_progressive_dc_refine_without_table.jpg"), "rb").read()
+    with pytest.raises(O.OracleError):
+        O.decode(blob, want_rgb=False)
+    got, err = run_gpu(blob)
+    assert isinstance(err, J.InvalidDataException)

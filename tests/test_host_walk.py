@@ -149,3 +149,23 @@ def test_sequential_frames_take_the_restart_interval_at_the_frame_header():
     sos = [i for i in range(len(prog) - 1) if prog[i] == 0xFF and prog[i + 1] == 0xDA]
     d = J.Parsed(prog[:sos[2]] + _dri(0) + prog[sos[2]:]).desc
     assert [d.scans[i].restart_interval for i in range(3)] == [4, 4, 0]
+
+
+def test_scan_header_checks_follow_the_reference():
+    """Two streams the corrupted-stream campaign found (profiles/r2_fuzz_campaign.txt).  The reference never validates the
+    spectral selection: a single-component scan with Ss = 0 is a DC scan whatever Se says (JpegHuffmanProgressiveScanDecoder
+    .cs:149-166) -- and it asks for the DC table of EVERY such scan, DC refinement scans included (:149-152)."""
+    import ctypes as C
+    import os
+    here = os.path.join(os.path.dirname(__file__), "fixtures")
+    accepted = open(os.path.join(here, "fuzz_gray_progressive_dc_scan_with_se.jpg"), "rb").read()      # first scan: Ss 0, Se 119
+    refused = open(os.path.join(here, "fuzz_gray_progressive_dc_refine_without_table.jpg"), "rb").read()  # DHT of the DC table swallowed
+    O.decode(accepted, want_rgb=False)
+    with pytest.raises(O.OracleError) as e:
+        O.decode(refused, want_rgb=False)
+    assert e.value.code == -1 and "Huffman table" in str(e.value)
+    for blob, ok in ((accepted, True), (refused, False)):
+        p = J.Parsed(blob)
+        out = (C.c_int32 * (10 * p.desc.scan_count))()
+        k = J._native.cuda.jb_plan_scans(C.byref(p.desc), out, p.desc.scan_count)
+        assert (k == p.desc.scan_count) if ok else (k == J._native.JB_ERR_INVALID_DATA), k
