@@ -321,15 +321,18 @@ __global__ void jb_fill_u32(uint4 *__restrict__ p16, size_t n16, uint32_t *__res
 
 // The arena comes from the pool uncleared and only the entropy-coded bytes of every image are uploaded; the bit readers
 // look a byte or a word past the end of a segment (is a trailing FF followed by 00, FF or a marker code?).  The spare
-// bytes behind every image are therefore cleared, so that a stream that stops without a marker decodes the same way
-// every time: one warp per image.
+// bytes behind every image are therefore set, so that a stream that stops without a marker decodes the same way
+// every time (and like the reference, see below): one warp per image.
 __global__ void jb_clear_arena_tails(const JbDevImage *__restrict__ images, int count, uint8_t *__restrict__ arena)
 {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= count) return;
     const uint64_t from = images[i].data_off + images[i].data_len;
     const uint64_t to = images[i].data_off + ((uint64_t)images[i].data_len + 64 + 255) / 256 * 256;
-    for (uint64_t p = from + lane; p < to; p += 32) arena[p] = 0;
+    // 0xFF, not 0: a stream that stops behind an FF byte has no "next byte" in the reference, which then drops the FF
+    // (JpegBitReader.FillBuffer :113-117: TryPeekNextByte fails, "the stream ended prematurely").  FF FF drops the first FF
+    // as a fill byte in every reader here -- the same outcome; FF 00 would have kept it as a stuffed data byte.
+    for (uint64_t p = from + lane; p < to; p += 32) arena[p] = 0xFF;
 }
 
 __global__ void jb_post_status(uint32_t *__restrict__ mailbox, const uint32_t *__restrict__ status, int count,

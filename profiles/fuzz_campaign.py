@@ -9,7 +9,7 @@ import test_gpu_fuzz as F
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
 os.makedirs("gpurun_out", exist_ok=True)
-total = bad = 0
+total = bad = known = 0
 import synth, oracle_ffi as O
 from conftest import golden_bytes
 bases = dict(F.base_streams())
@@ -26,6 +26,21 @@ if "--more" in sys.argv:   # further frame types than the test suite mutates
         "lossless_16bit_s22": synth.synth_lossless(51, 64, 48, precision=16, predictor=6, sampling=[(2, 2), (1, 1), (1, 1)], restart=8)[0],
         "lossless_gray_5bit": synth.synth_lossless(52, 80, 40, precision=5, predictor=7, ncomp=1)[0],
         "progressive_422": synth.encode_jpeg(rgb, quality=75, subsampling="4:2:2", progressive=True),
+    }
+if "--wide" in sys.argv:   # layouts and scan scripts neither of the other two sets holds
+    rgb = synth.synth_rgb(53, 200, 136)
+    src = synth.encode_jpeg(rgb, quality=85, subsampling="4:2:0")
+    prog = synth.encode_jpeg(rgb, quality=85, subsampling="4:4:4", progressive=True)
+    bases = {
+        "oracle_encoded_440": O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=88, subsampling=(1, 2)).bytes,
+        "oracle_encoded_h4": O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=80, subsampling=(4, 1)).bytes,
+        "oracle_encoded_gray": O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=70, gray=True).bytes,
+        "progressive_420_restart": synth.encode_jpeg(rgb, quality=90, subsampling="4:2:0", progressive=True, restart_blocks=11),
+        "progressive_444_luma_first": synth.reorder_progressive_scans(prog, [0, 1, 4, 5, 9, 2, 3, 7, 8, 6]),
+        "progressive_444_scan_behind_its_refinement": synth.reorder_progressive_scans(prog, [0, 1, 4, 5, 9, 1, 2, 3, 7, 8, 6]),
+        "sequential_three_scans_no_restart": synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0], [1], [2]]),
+        "sequential_luma_then_chroma_pair": synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0], [1, 2]], 7),
+        "no_restart_420_large": synth.encode_jpeg(synth.synth_rgb(54, 1280, 720), quality=85, subsampling="4:2:0"),
     }
 for name, blob in bases.items():
     rng = np.random.default_rng(seed + sum(map(ord, name)))
@@ -46,10 +61,13 @@ for name, blob in bases.items():
             err += 1
         elif werr is None and gerr is None and got.shape == want.planes.shape and np.array_equal(got, want.planes):
             ok += 1
+        elif (werr is None and gerr is None and name.startswith("sequential_") and got.shape == want.planes.shape
+              and not O.written_samples(want).all()):
+            known += 1  # DESIGN.md section 6, deviation (1): EOI at a restart boundary of a multi-scan sequential frame
         else:
             bad += 1
             fn = f"gpurun_out/fuzz_{name}_{t}.jpg"
             open(fn, "wb").write(mut)
             print(f"{name} trial {t} ({'header' if header else kind}): oracle [{werr}] GPU [{type(gerr).__name__ if gerr else 'decoded'}: {gerr}] -> {fn}", flush=True)
     print(f"{name}: {ok} identical, {err} errors on both sides", flush=True)
-print(f"{total} streams, {bad} disagreements")
+print(f"{total} streams, {bad} disagreements, {known} of the known deviation (multi-scan sequential frame, EOI at a restart boundary)")

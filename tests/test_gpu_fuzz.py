@@ -268,3 +268,11 @@ def test_streams_the_campaign_found():
         O.decode(blob, want_rgb=False)
     got, err = run_gpu(blob)
     assert isinstance(err, J.InvalidDataException)
+    # the file ends "... FF FF FF" instead of "... 5F FF D9": the reference drops an FF that has no next byte (JpegBitReader.cs
+    # :113-117), the last DC refinement bits are missing and ReadBlockProgressiveDC fails ("Unexpected end of JPEG data
+    # stream."); a zero behind the stream in the device arena had turned that FF into a stuffed data byte
+    blob = open(os.path.join(here, "fuzz_progressive_trailing_ff_without_eoi.jpg"), "rb").read()
+    with pytest.raises(O.OracleError):
+        O.decode(blob, want_rgb=False)
+    got, err = run_gpu(blob)
+    assert isinstance(err, J.InvalidDataException)
