@@ -59,7 +59,9 @@ struct __align__(16) JbDevImage {
     uint8_t blk_ac[JB_MAX_BLOCKS_PER_MCU];
     uint16_t table_index[JB_MAX_TABLE_SLOTS]; // slot -> index into the device table array
     uint8_t ntables;
-    uint8_t pad0[3];
+    uint8_t seq_dri;     // scan-list frame of a SEQUENTIAL process whose scans have restart intervals: a scan may end at an EOI
+                         // on a restart boundary and leave the intervals behind it unwritten (per-component MCU limits)
+    uint8_t pad0[2];
     // self-synchronising decode (scans without restart markers)
     uint32_t use_selfsync; // 1: K1b path
     uint32_t sub_base;     // first sub-sequence slot of this image in the sub-sequence arrays

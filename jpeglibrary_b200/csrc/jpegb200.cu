@@ -261,6 +261,7 @@ static int k2_variant(const JbDevImage &d, const std::vector<uint16_t> &quant)
 {
     if (d.precision != 8 || d.out_format > JB_OUT_YCBCR888) return -1;
     if (d.planar && (d.covered & ((1u << d.ncomp) - 1u)) != (1u << d.ncomp) - 1u) return -1; // unwritten components
+    if (d.seq_dri) return -1; // components may be written up to different MCUs (scans that end at an EOI on a restart boundary)
     // the fast kernel dequantises as fmul(float(q), float(c)): exact for |q * c| < 2^24, i.e. any int16 c with q <= 255
     for (int i = 0; i < d.ncomp * 64; i++)
         if (quant[d.quant_off + i] > 255) return -1;
@@ -404,6 +405,9 @@ struct jb_batch {
     JbProgJob *d_prog_jobs = nullptr;
     JbProgLane *d_prog_lanes = nullptr;
     uint32_t *d_prog_progress = nullptr;   // per scan: units (one segment) or segments finished; last word: ticket counter
+    uint32_t *d_scan_limits = nullptr;     // per scan of a sequential scan-list frame: first MCU it did not reach (0xFFFFFFFF: none)
+    uint32_t *d_comp_limits = nullptr;     // per image x 4 components: MCUs the component was written for (jb_k1c_sequential_limits)
+    bool prog_seq_dri = false;
     unsigned long long *d_prog_trace = nullptr; // profiling: {image|scan|seg, start, end, waited} ns per job
     uint64_t prog_coef_first = 0, prog_coef_blocks = 0; // contiguous slice of the store, zeroed per launch
     std::vector<JbDevScan> h_scans;
@@ -893,6 +897,9 @@ static int plan_progressive(jb_ctx *ctx, int idx, const jb_image_desc &im, const
         pl.scans.push_back(ds);
     }
     d.nscans = (uint32_t)pl.scans.size();
+    d.seq_dri = 0;
+    if (sequential)
+        for (const JbDevScan &q : pl.scans) d.seq_dri |= q.dri != 0;
     d.quant_off = (uint32_t)quant.size();
     for (int c = 0; c < im.component_count; c++)
         for (int i = 0; i < 64; i++) quant.push_back(im.quant[c][i]);
@@ -1186,6 +1193,10 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             pl.dev_out = pl.out.dst;
         if (pl.dev.planar && pl.dev.sof != 3) {
             b->prog_images.push_back((uint32_t)i);
+            if (pl.dev.seq_dri) {
+                b->prog_seq_dri = true;
+                if (!pl.out.on_device && pl.out.format != JB_OUT_COEFFICIENTS) b->may_truncate = true;
+            }
         } else if (pl.dev.sof == 3) {
             b->ll_images.push_back((uint32_t)i);
             b->ll_max_scans = std::max<uint32_t>(b->ll_max_scans, (uint32_t)pl.scans.size());
@@ -1388,6 +1399,8 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
             JB_CUDA_B(cudaMemcpyAsync(b->d_prog_lanes, b->h_prog_lanes.data(), sizeof(JbProgLane) * b->h_prog_lanes.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
         JB_CUDA_B(jb_malloc_async(ctx, &b->d_prog_progress, sizeof(uint32_t) * (b->h_scans.size() + 1)));
+        JB_CUDA_B(jb_malloc_async(ctx, &b->d_scan_limits, sizeof(uint32_t) * (b->h_scans.size() + 1)));
+        if (b->prog_seq_dri) JB_CUDA_B(jb_malloc_async(ctx, &b->d_comp_limits, sizeof(uint32_t) * 4 * count));
     }
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
@@ -1582,17 +1595,27 @@ static int launch_kernels(jb_batch *b)
         // JpegBlockAllocator.Allocate clears the store (JpegBlockAllocator.cs:82-83); scans then refine it
         JB_CUDA(ctx, jb_fill_async(b->d_coef + b->prog_coef_first * 64, 0, b->prog_coef_blocks * 128, st));
         JB_CUDA(ctx, jb_fill_async(b->d_prog_progress, 0, sizeof(uint32_t) * (b->h_scans.size() + 1), st));
+        if (b->prog_seq_dri) {
+            JB_CUDA(ctx, jb_fill_async(b->d_scan_limits, 0xFFFFFFFFu, sizeof(uint32_t) * (b->h_scans.size() + 1), st));
+            launches++;
+        }
         const uint32_t njobs = (uint32_t)b->h_prog_jobs.size();
         if (b->trace && !b->d_prog_trace) JB_CUDA(ctx, jb_malloc_async(ctx, &b->d_prog_trace, sizeof(unsigned long long) * 4 * njobs));
         if (b->trace)
             jb_k1c_progressive_scans<true><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
                                                                  b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace);
+                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace, b->d_scan_limits);
         else
             jb_k1c_progressive_scans<false><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
                                                                   b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                                  b->d_prog_progress + b->h_scans.size(), nullptr);
+                                                                  b->d_prog_progress + b->h_scans.size(), nullptr, b->d_scan_limits);
         launches += 2;
+        if (b->prog_seq_dri) { // where the scans of sequential scan-list frames stopped -> per-component MCU limits
+            const int nimg = (int)b->prog_images.size();
+            jb_k1c_sequential_limits<<<(nimg + 127) / 128, 128, 0, st>>>(b->d_images, b->d_scans, b->d_image_list + b->prog_list_off, nimg,
+                                                                      b->d_scan_limits, b->d_comp_limits, b->d_limits);
+            launches++;
+        }
         mark("jb_k1c_progressive_scans");
     }
     if (!b->ll_images.empty()) {
@@ -1701,7 +1724,7 @@ static int launch_render(jb_batch *b, int *launches)
             launch_k2_fast(g.variant, grid, st, b->d_images, b->d_coef, b->d_quant, list, tpc, b->d_limits);
         } else {
             dim3 grid(g.max_tiles, (unsigned)g.images.size());
-            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list, b->d_limits);
+            jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, st>>>(b->d_images, b->d_coef, b->d_quant, list, b->d_limits, b->d_comp_limits);
         }
         (*launches)++;
     }
@@ -1902,6 +1925,8 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_prog_jobs) cudaFreeAsync(b->d_prog_jobs, b->ctx->stream);
     if (b->d_prog_lanes) cudaFreeAsync(b->d_prog_lanes, b->ctx->stream);
     if (b->d_prog_progress) cudaFreeAsync(b->d_prog_progress, b->ctx->stream);
+    if (b->d_scan_limits) cudaFreeAsync(b->d_scan_limits, b->ctx->stream);
+    if (b->d_comp_limits) cudaFreeAsync(b->d_comp_limits, b->ctx->stream);
     if (b->d_prog_trace) cudaFreeAsync(b->d_prog_trace, b->ctx->stream);
     if (b->d_ranges) cudaFreeAsync(b->d_ranges, b->ctx->stream);
     if (b->d_clean) cudaFreeAsync(b->d_clean, b->ctx->stream);
@@ -1962,7 +1987,7 @@ int jb_render_from_coefficients(jb_ctx *ctx, const jb_image_desc *image, const i
         uint32_t tile_mcus = JB_K2_MAX_BLOCKS / pl.dev.bpm;
         uint32_t strips = (pl.dev.mcus_per_line + tile_mcus - 1) / tile_mcus;
         dim3 grid(strips * pl.dev.mcus_per_col, 1);
-        jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q, nullptr, nullptr);
+        jb_k2_idct_color<<<grid, JB_K2_THREADS, 0, ctx->stream>>>(d_im, coef_device, d_q, nullptr, nullptr, nullptr);
         step(cudaGetLastError());
         if (!output->on_device) step(cudaMemcpyAsync(output->dst, d_out, pl.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }

@@ -57,7 +57,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                          const JbHuffTable *__restrict__ tables,
                          const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
                          const JbScanResult *__restrict__ scanres, int16_t *coef, uint32_t *__restrict__ status,
-                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace)
+                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace, uint32_t *scan_limit)
 {
     const int lane = threadIdx.x;
     uint32_t turn = 0;
@@ -97,6 +97,9 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             // no RSTn in front of this interval.  EOI at a restart boundary ends the scan quietly (HandleRestart
             // :203-207): the intervals behind it are simply not there; any other marker is an error
             if (sr.end_marker != 0xD9u) err = JB_ST_EXPECT_RST;
+            // a scan of a sequential frame that ends here never calls WriteBlock for the MCUs behind this point
+            // (JpegHuffmanBaselineScanDecoder.cs:144-150): the renderer takes the first such point of every scan
+            else if (sc.seq) atomicMin(scan_limit + im.scan_base + ent.scan, first);
             count = 0;
         }
     }
@@ -455,4 +458,31 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             else atomicAdd(my_progress, 1u);
         }
     }
+}
+
+// Scan-list frames of a sequential process with restart intervals: MCUs a component was written for.  A block reaches
+// WriteBlock iff some scan that names its component got to its MCU; a scan that met EOI on a restart boundary stopped at
+// scan_limit (0xFFFFFFFF: it ran to the end).  comp_limit[image * 4 + c] = the furthest any scan naming c got,
+// mcu_limit[image] = the furthest any component got (the renderer and the partial D2H copy stop there).
+__global__ void jb_k1c_sequential_limits(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
+                                         const uint32_t *__restrict__ image_list, int nimg,
+                                         const uint32_t *__restrict__ scan_limit, uint32_t *__restrict__ comp_limit,
+                                         uint32_t *__restrict__ mcu_limit)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nimg) return;
+    const uint32_t image = image_list[i];
+    const JbDevImage &im = images[image];
+    if (!im.seq_dri) return;
+    uint32_t lim[4] = {0, 0, 0, 0}, most = 0;
+    for (uint32_t k = 0; k < im.nscans; k++) {
+        const JbDevScan &sc = scans[im.scan_base + k];
+        const uint32_t l = min(scan_limit[im.scan_base + k], im.total_mcus);
+        for (int a = 0; a < sc.ncomp; a++) lim[sc.comp[a] & 3] = max(lim[sc.comp[a] & 3], l);
+    }
+    for (int c = 0; c < 4; c++) {
+        comp_limit[image * 4 + c] = lim[c] >= im.total_mcus ? 0xFFFFFFFFu : lim[c];
+        if (c < im.ncomp) most = max(most, lim[c]);
+    }
+    mcu_limit[image] = most >= im.total_mcus ? 0xFFFFFFFFu : most;
 }

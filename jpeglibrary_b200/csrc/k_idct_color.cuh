@@ -165,7 +165,8 @@ struct JbK2Geom {
 __global__ void __launch_bounds__(JB_K2_THREADS)
 jb_k2_idct_color(const JbDevImage *__restrict__ images,
                  const int16_t *__restrict__ coef, const uint16_t *__restrict__ quant,
-                 const uint32_t *__restrict__ image_list, const uint32_t *__restrict__ mcu_limit)
+                 const uint32_t *__restrict__ image_list, const uint32_t *__restrict__ mcu_limit,
+                 const uint32_t *__restrict__ comp_limit)
 {
     __shared__ __align__(16) float s_f[JB_K2_MAX_BLOCKS * JB_K2_BLOCK_STRIDE];
     __shared__ __align__(16) int16_t s_plane[JB_K2_MAX_BLOCKS * 64];
@@ -218,8 +219,11 @@ jb_k2_idct_color(const JbDevImage *__restrict__ images,
     if (j < nblk) {
         const int m = j / bpm, b = j - m * bpm;
         const int c = s_im.blk_comp[b];
-        // scan-list frames: a component no scan names is never written by the reference (its samples stay 0)
-        const bool unwritten = s_im.planar && !((s_im.covered >> c) & 1u);
+        // scan-list frames: a component no scan names is never written by the reference (its samples stay 0), and
+        // neither are the MCUs behind the point where the component's scans ended at an EOI on a restart boundary
+        const bool unwritten = s_im.planar && (!((s_im.covered >> c) & 1u) ||
+                                               (comp_limit && s_im.seq_dri &&
+                                                tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0 + (uint32_t)m >= comp_limit[tw.image * 4 + c]));
         uint64_t blk;
         if (!s_im.planar) {
             blk = s_im.coef_off + ((uint64_t)tw.mcu_row * s_im.mcus_per_line + tw.mcu_col0) * bpm + j;

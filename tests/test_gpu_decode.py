@@ -516,6 +516,51 @@ def test_sequential_frames_with_several_scans(kw):
     assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("which", [0, 1, 2])
+@pytest.mark.parametrize("on_device", [False, True])
+def test_sequential_scan_list_cut_at_a_restart_marker(which, on_device):
+    """A multi-scan sequential frame whose scan `which` stops at one of its restart markers with EOI behind it: the
+    reference's baseline decoder ends that scan quietly and never calls WriteBlock for the intervals behind the cut
+    (JpegHuffmanBaselineScanDecoder.cs:144-150), the scans behind it do not exist.  Components are therefore written up
+    to different MCUs: samples of a component behind its cut read 0 as far as any component was written (the writer's
+    untouched buffer), and nothing is written behind the furthest cut -- checked with a pre-filled destination."""
+    src = synth.synth_jpeg(34, 176, 120, subsampling="4:2:0", quality=88)
+    # (88 MCUs in intervals of 5: a last interval that is complete would trip the reference's "Expect restart marker." quirk)
+    blob = synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0], [1], [2]], 5)
+    sos = [i for i in range(len(blob) - 1) if blob[i] == 0xFF and blob[i + 1] == 0xDA]
+    assert len(sos) == 3
+    lo, hi = sos[which], (sos[which + 1] if which < 2 else len(blob) - 2)
+    rst = [i for i in range(lo, hi - 1) if blob[i] == 0xFF and 0xD0 <= blob[i + 1] <= 0xD7]
+    cut = blob[:rst[len(rst) // 2]] + b"\xff\xd9"
+    want = O.decode(cut, want_rgb=False)
+    wr = O.written_samples(want)
+    assert wr.any() and not wr.all()
+    dec = J.JpegDecoder()
+    dec.SetInput(cut)
+    dec.Identify()
+    if on_device:
+        ctx = J.Context.default()
+        nbytes = 3 * dec.Height * dec.Width * 2
+        dev = ctx.device_alloc(nbytes)
+        fill = np.full((3, dec.Height, dec.Width), 0x5A5A, dtype=np.int16)
+        ctx.check(J._native.cuda.jb_memcpy_h2d(ctx.handle, dev, fill.ctypes.data, nbytes))
+        dec.SetOutputWriter(J.CudaOutputWriter(dev, J.JB_OUT_PLANAR_I16, on_device=True, capacity=nbytes))
+        dec.Decode()
+        planes = np.empty_like(fill)
+        ctx.check(J._native.cuda.jb_memcpy_d2h(ctx.handle, planes.ctypes.data, dev, nbytes))
+        ctx.device_free(dev)
+    else:
+        planes = np.full((3, dec.Height, dec.Width), 0x5A5A, dtype=np.int16)
+        dec.SetOutputWriter(J.CudaOutputWriter(planes, J.JB_OUT_PLANAR_I16))
+        dec.Decode()
+    assert np.array_equal(planes[wr], want.planes[wr])
+    some = wr.any(axis=0)                       # pixels some component was written for
+    rows = np.nonzero(some.any(axis=1))[0]
+    assert (planes[:, rows.max() + 1:, :] == 0x5A5A).all()          # whole MCU rows behind the furthest cut: untouched
+    inside = np.broadcast_to(some, wr.shape) & ~wr
+    assert (planes[inside] == 0).all()                              # behind a component's own cut, inside the written part
+
+
 # ------------------------------------------------------------------------------------------ lossless (SOF3)
 LOSSLESS_ASSETS = ["lossless%d_s22.jpg" % i for i in range(1, 8)]
 
