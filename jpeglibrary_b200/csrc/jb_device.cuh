@@ -159,3 +159,21 @@ struct JbTileWork {
 #define JB_ST_PREMATURE_END 2u   // ran out of bits inside a segment            -> InvalidDataException
 #define JB_ST_EXPECT_RST 4u      // restart marker missing / misplaced          -> InvalidOperationException
 #define JB_ST_STALLED 8u         // K1c gave up waiting for a producer scan (never expected) -> JB_ERR_CUDA
+
+// Which exception does the reference throw for a stream with several defects?  The one it meets FIRST: it decodes scan by
+// scan, interval by interval, and stops at the first failure.  The kernels decode everything at once and OR their status
+// bits per image, so next to the bits every failure also takes part in an atomicMin on a key that orders it in the
+// stream: (scan << 20 | 2 * interval + after) << 2 | class, `after` = 1 for what is checked behind an interval's data
+// (the restart marker), class 1 = InvalidDataException (bad code, premature end), 2 = InvalidOperationException
+// ("Expect restart marker.").  The host reports the class of the smallest key.
+__device__ __forceinline__ void jb_report_error(uint32_t *status, uint32_t *first_error, uint32_t image, uint32_t err,
+                                                uint32_t scan, uint32_t interval)
+{
+    if (!err) return;
+    atomicOr(status + image, err);
+    if (!first_error) return;
+    const bool data = (err & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) != 0; // (met inside the interval: before its end check)
+    const uint32_t unit = min(2u * interval + (data ? 0u : 1u), (1u << 20) - 1u);
+    atomicMin(first_error + image, ((min(scan, 1023u) << 20 | unit) << 2) | (data ? 1u : 2u));
+}
+

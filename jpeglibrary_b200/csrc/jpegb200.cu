@@ -337,10 +337,11 @@ __global__ void jb_clear_arena_tails(const JbDevImage *__restrict__ images, int 
 }
 
 __global__ void jb_post_status(uint32_t *__restrict__ mailbox, const uint32_t *__restrict__ status, int count,
-                               const uint32_t *__restrict__ changed_last, const uint32_t *__restrict__ limits)
+                               const uint32_t *__restrict__ changed_last, const uint32_t *__restrict__ limits,
+                               const uint32_t *__restrict__ first_error)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) { mailbox[i] = status[i]; mailbox[count + 1 + i] = limits[i]; }
+    if (i < count) { mailbox[i] = status[i]; mailbox[count + 1 + i] = limits[i]; mailbox[2 * count + 1 + i] = first_error[i]; }
     if (i == 0) mailbox[count] = changed_last ? *changed_last : 0u;
 }
 
@@ -381,6 +382,7 @@ struct jb_batch {
     int16_t *d_coef = nullptr;
     uint64_t coef_blocks = 0;
     uint32_t *d_status = nullptr;
+    uint32_t *d_first_error = nullptr; // per image: smallest jb_report_error key (which failure the reference meets first)
     uint32_t *d_limits = nullptr; // per image: MCUs that were decoded (0xFFFFFFFF: all); fewer when a sequential scan ends at
                                   // an EOI on a restart boundary -- the reference never calls WriteBlock for the rest
     bool may_truncate = false;    // some image has restart intervals and a host destination: its D2H copy waits for d_limits
@@ -389,7 +391,7 @@ struct jb_batch {
     std::vector<uint32_t> h_status;
     // Status words come back through a mapped pinned mailbox written by a kernel at the end of the launch: a small
     // cudaMemcpy D2H would queue on the copy engine behind another context's bulk pixel copies.
-    uint32_t *h_mailbox = nullptr; // [count] status words + [1] "changed in the last sync round" + [count] MCU limits
+    uint32_t *h_mailbox = nullptr; // [count] status words + [1] "changed in the last sync round" + [count] MCU limits + [count] first-error keys
     size_t mailbox_cap = 0;
     uint32_t max_nseg = 1; // most restart segments any image of the K0b/K1 path has
     // flat restart-segment path (K0b + K1)
@@ -473,7 +475,7 @@ static int launch_k1_flat(jb_batch *b, const JbSegDesc *segs, uint32_t nsegs, co
                                       (int)jb_k1f_smem_bytes(JB_K1F_MAX_THREADS)));
     const uint32_t grid = (uint32_t)(((uint64_t)warps * 32 + threads - 1) / threads);
     jb_k1_huff_flat<CLEAN><<<grid, threads, smem, ctx->stream>>>(
-        b->d_images, segs, nsegs, b->d_tables32, reinterpret_cast<const uint32_t *>(stream), b->d_coef, b->d_status, lanes);
+        b->d_images, segs, nsegs, b->d_tables32, reinterpret_cast<const uint32_t *>(stream), b->d_coef, b->d_status, lanes, b->d_first_error);
     return JB_OK;
 }
 
@@ -1347,7 +1349,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     b->coef_blocks = blocks;
     b->out_staging_bytes = staging;
     b->h_status.assign(count, 0);
-    b->h_mailbox = jb_mailbox_get(ctx, 2 * (size_t)count + 1, &b->mailbox_cap);
+    b->h_mailbox = jb_mailbox_get(ctx, 3 * (size_t)count + 1, &b->mailbox_cap);
     if (!b->h_mailbox) {
         ctx->error = "cudaHostAlloc of the status mailbox failed";
         delete b;
@@ -1405,6 +1407,7 @@ int jb_decode_batch_create(jb_ctx *ctx, const jb_image_desc *images, const jb_ou
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_coef, blocks * 128));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_status, sizeof(uint32_t) * count));
     JB_CUDA_B(jb_malloc_async(ctx, &b->d_limits, sizeof(uint32_t) * count));
+    JB_CUDA_B(jb_malloc_async(ctx, &b->d_first_error, sizeof(uint32_t) * count));
     if (staging) JB_CUDA_B(jb_malloc_async(ctx, &b->d_out_staging, staging));
     std::vector<uint32_t> h_list;
     b->seg_list_off = 0;
@@ -1550,7 +1553,8 @@ static int launch_kernels(jb_batch *b)
     };
     JB_CUDA(ctx, jb_fill_async(b->d_status, 0, sizeof(uint32_t) * b->count, st));
     JB_CUDA(ctx, jb_fill_async(b->d_limits, 0xFFFFFFFFu, sizeof(uint32_t) * b->count, st));
-    launches += 2;
+    JB_CUDA(ctx, jb_fill_async(b->d_first_error, 0xFFFFFFFFu, sizeof(uint32_t) * b->count, st));
+    launches += 3;
     mark(nullptr);
     jb_k0_restart_scan<<<(unsigned)b->h_ranges.size(), JB_K0_THREADS, 0, st>>>(b->d_ranges, b->d_arena, b->d_marks, b->d_scan);
     launches++;
@@ -1559,7 +1563,7 @@ static int launch_kernels(jb_batch *b)
         // descriptors of every restart segment of the batch, then one lane per segment
         dim3 ugrid((b->max_nseg + JB_K0B_THREADS - 1) / JB_K0B_THREADS, (unsigned)b->seg_images.size());
         jb_k0b_segment_descs<<<ugrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
-                                                              b->d_segs, b->d_status, b->d_limits);
+                                                              b->d_segs, b->d_status, b->d_limits, b->d_first_error);
         if (b->max_nseg > 1) { // intervals the stream does not hold (EOI where an RSTn would be) keep zero blocks
             dim3 cgrid((b->max_nseg + JB_K0B_THREADS / 32 - 1) / (JB_K0B_THREADS / 32), (unsigned)b->seg_images.size());
             jb_k0c_clear_absent<<<cgrid, JB_K0B_THREADS, 0, st>>>(b->d_images, b->d_image_list + b->seg_list_off, b->d_marks, b->d_scan,
@@ -1604,11 +1608,11 @@ static int launch_kernels(jb_batch *b)
         if (b->trace)
             jb_k1c_progressive_scans<true><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
                                                                  b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace, b->d_scan_limits);
+                                                                 b->d_prog_progress + b->h_scans.size(), b->d_prog_trace, b->d_scan_limits, b->d_first_error);
         else
             jb_k1c_progressive_scans<false><<<njobs, 32, 0, st>>>(b->d_images, b->d_scans, b->d_prog_jobs, b->d_prog_lanes, njobs, b->d_tables,
                                                                   b->d_arena, b->d_marks, b->d_scan, b->d_coef, b->d_status, b->d_prog_progress,
-                                                                  b->d_prog_progress + b->h_scans.size(), nullptr, b->d_scan_limits);
+                                                                  b->d_prog_progress + b->h_scans.size(), nullptr, b->d_scan_limits, b->d_first_error);
         launches += 2;
         if (b->prog_seq_dri) { // where the scans of sequential scan-list frames stopped -> per-component MCU limits
             const int nimg = (int)b->prog_images.size();
@@ -1625,7 +1629,7 @@ static int launch_kernels(jb_batch *b)
         dim3 grid((b->ll_max_nseg + lanes - 1) / lanes, nimg);
         for (uint32_t z = 0; z < b->ll_max_scans; z++) { // scan by scan: a later scan over the same component replaces the earlier one
             jb_k1d_lossless_entropy<<<grid, 32, 0, st>>>(b->d_images, b->d_scans, list, z, b->d_tables, b->d_arena, b->d_marks, b->d_scan,
-                                                        b->d_coef, b->d_status, lanes);
+                                                        b->d_coef, b->d_status, lanes, b->d_first_error);
             launches++;
         }
         jb_k1d_lossless_predict<<<nimg, 32 * JB_MAX_COMPONENTS_DEV, 0, st>>>(b->d_images, b->d_scans, list, b->d_marks, b->d_scan, b->d_coef);
@@ -1637,7 +1641,8 @@ static int launch_kernels(jb_batch *b)
     launch_render(b, &launches);
     mark("jb_k2_idct_color");
     jb_post_status<<<(b->count + 255) / 256, 256, 0, st>>>(b->h_mailbox, b->d_status, b->count,
-                                                           b->ss_images.empty() ? nullptr : b->d_changed + JB_SS_ROUNDS, b->d_limits);
+                                                           b->ss_images.empty() ? nullptr : b->d_changed + JB_SS_ROUNDS, b->d_limits,
+                                                           b->d_first_error);
     launches++;
     JB_CUDA(ctx, cudaGetLastError());
     b->launches = launches;
@@ -1773,6 +1778,19 @@ static int resync_and_rerun(jb_batch *b)
     return JB_OK;
 }
 
+// Status bits of one image -> the reference's exception class.  A stream with several defects throws whatever the
+// reference meets first: `first` is the smallest jb_report_error key of the image (low two bits: 1 InvalidDataException,
+// 2 InvalidOperationException); images whose kernels do not order their failures fall back to the bits.
+static int status_code(uint32_t s, uint32_t first)
+{
+    if (s & JB_ST_STALLED) return JB_ERR_CUDA;
+    if (first != 0xFFFFFFFFu && (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END | JB_ST_EXPECT_RST)))
+        return (first & 3u) == 2u ? JB_ERR_INVALID_OPERATION : JB_ERR_INVALID_DATA;
+    if (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) return JB_ERR_INVALID_DATA;
+    if (s & JB_ST_EXPECT_RST) return JB_ERR_INVALID_OPERATION;
+    return JB_OK;
+}
+
 int jb_decode_batch_finish(jb_batch *b)
 {
     if (!b) return JB_ERR_ARGUMENT;
@@ -1846,7 +1864,7 @@ int jb_decode_batch_finish(jb_batch *b)
         // need more than JB_SS_ROUNDS hops to synchronise: rare) keep iterating and redo the output
         int rc = resync_and_rerun(b);
         if (rc) return rc;
-        jb_post_status<<<(b->count + 255) / 256, 256, 0, ctx->stream>>>(b->h_mailbox, b->d_status, b->count, nullptr, b->d_limits);
+        jb_post_status<<<(b->count + 255) / 256, 256, 0, ctx->stream>>>(b->h_mailbox, b->d_status, b->count, nullptr, b->d_limits, b->d_first_error);
         JB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     memcpy(b->h_status.data(), b->h_mailbox, sizeof(uint32_t) * b->count);
@@ -1857,9 +1875,7 @@ int jb_decode_batch_finish(jb_batch *b)
     for (int i = 0; i < b->count; i++) {
         uint32_t s = b->h_status[i];
         int code = JB_OK;
-        if (s & JB_ST_STALLED) code = JB_ERR_CUDA;
-        else if (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) code = JB_ERR_INVALID_DATA;
-        else if (s & JB_ST_EXPECT_RST) code = JB_ERR_INVALID_OPERATION;
+        code = status_code(s, b->h_mailbox[2 * (size_t)b->count + 1 + i]);
         if (code && !first) {
             first = code;
             char buf[200];
@@ -1886,11 +1902,7 @@ int jb_decode_batch_status(jb_batch *b, int32_t *status, int count)
 {
     if (!b || !status) return JB_ERR_ARGUMENT;
     for (int i = 0; i < count && i < b->count; i++) {
-        uint32_t s = b->h_status[i];
-        status[i] = (s & JB_ST_STALLED)                          ? JB_ERR_CUDA
-                    : (s & (JB_ST_BAD_CODE | JB_ST_PREMATURE_END)) ? JB_ERR_INVALID_DATA
-                    : (s & JB_ST_EXPECT_RST)                     ? JB_ERR_INVALID_OPERATION
-                                                                 : JB_OK;
+        status[i] = status_code(b->h_status[i], b->h_mailbox ? b->h_mailbox[2 * (size_t)b->count + 1 + i] : 0xFFFFFFFFu);
     }
     return JB_OK;
 }
@@ -1919,6 +1931,7 @@ void jb_decode_batch_destroy(jb_batch *b)
     if (b->d_coef) cudaFreeAsync(b->d_coef, b->ctx->stream);
     if (b->d_status) cudaFreeAsync(b->d_status, b->ctx->stream);
     if (b->d_limits) cudaFreeAsync(b->d_limits, b->ctx->stream);
+    if (b->d_first_error) cudaFreeAsync(b->d_first_error, b->ctx->stream);
     if (b->d_out_staging) cudaFreeAsync(b->d_out_staging, b->ctx->stream);
     if (b->d_image_list) cudaFreeAsync(b->d_image_list, b->ctx->stream);
     if (b->d_scans) cudaFreeAsync(b->d_scans, b->ctx->stream);

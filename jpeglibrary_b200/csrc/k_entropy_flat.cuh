@@ -44,7 +44,7 @@ struct __align__(16) JbSegDesc {
 __global__ void __launch_bounds__(JB_K0B_THREADS)
 jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__restrict__ image_list,
                      const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
-                     JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status, uint32_t *__restrict__ mcu_limit)
+                     JbSegDesc *__restrict__ segs, uint32_t *__restrict__ status, uint32_t *__restrict__ mcu_limit, uint32_t *__restrict__ first_error)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
@@ -85,7 +85,7 @@ jb_k0b_segment_descs(const JbDevImage *__restrict__ images, const uint32_t *__re
     // ends too, quietly (JpegHuffmanBaselineScanDecoder.cs:144-150: the EOI sits where a restart marker would); any other
     // marker there -- or none -- is "Expect restart marker.".  (If the EOI came in the middle of an interval, that
     // interval's own decode reports the premature end.)
-    if (!reachable && sr.end_marker != 0xD9u) atomicOr(status + image, JB_ST_EXPECT_RST);
+    if (!reachable && sr.end_marker != 0xD9u) jb_report_error(status, first_error, image, JB_ST_EXPECT_RST, 0, seg - 1); // (behind interval seg - 1)
     // ... and the reference returns from the MCU loop there: WriteBlock is never called for the MCUs of the absent
     // intervals, so the renderer must leave their pixels alone.  Interval s is present iff markers 0..s-1 are RSTn.
     if (seg == 0 && im.dri != 0) {
@@ -216,7 +216,8 @@ template <bool CLEAN>
 __global__ void __launch_bounds__(JB_K1F_MAX_THREADS, 1)
 jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restrict__ segs, uint32_t nsegs,
                 const JbHuffTable32 *__restrict__ tables, const uint32_t *__restrict__ arena_words,
-                int16_t *__restrict__ coef, uint32_t *__restrict__ status, uint32_t lanes_per_warp)
+                int16_t *__restrict__ coef, uint32_t *__restrict__ status, uint32_t lanes_per_warp,
+                uint32_t *__restrict__ first_error)
 {
     extern __shared__ __align__(16) uint8_t jb_k1f_smem[];
     __shared__ uint32_t s_tab_id[JB_K1F_TABLES];
@@ -561,7 +562,7 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
     if (d.nblocks == 0) return;
     if (under < 0) err |= JB_ST_PREMATURE_END; // "The bit stream ended prematurely." (ReceiveAndExtend)
     if (CLEAN) {
-        if (err) atomicOr(status + d.image, err);
+        if (err) atomicOr(status + d.image, err); // (no restart intervals: every failure is an InvalidDataException)
         return;
     }
     if (!(err & JB_ST_PREMATURE_END) && (d.flags & 1u)) {
@@ -572,5 +573,5 @@ jb_k1_huff_flat(const JbDevImage *__restrict__ images, const JbSegDesc *__restri
         while (p < a1r && bytes[p] == 0xFFu) p++;
         if (n >= 8 || p < a1r || !(d.flags & 2u)) err |= JB_ST_EXPECT_RST;
     }
-    if (err) atomicOr(status + d.image, err);
+    if (err) jb_report_error(status, first_error, d.image, err, 0, g - images[d.image].seg_base);
 }

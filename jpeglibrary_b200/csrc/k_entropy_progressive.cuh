@@ -57,7 +57,8 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
                          const JbHuffTable *__restrict__ tables,
                          const uint8_t *__restrict__ arena, const uint32_t *__restrict__ marks,
                          const JbScanResult *__restrict__ scanres, int16_t *coef, uint32_t *__restrict__ status,
-                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace, uint32_t *scan_limit)
+                         uint32_t *progress, uint32_t *ticket, unsigned long long *trace, uint32_t *scan_limit,
+                         uint32_t *first_error)
 {
     const int lane = threadIdx.x;
     uint32_t turn = 0;
@@ -441,7 +442,11 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u;
             if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
         }
-        if (err) atomicOr(status + image, err);
+        if (err) {
+            // ("no RSTn in front of this interval" is met behind the previous one; count == 0 then and nothing else can fail)
+            const bool in_front = count == 0 && seg > 0 && err == JB_ST_EXPECT_RST;
+            jb_report_error(status, first_error, image, err, ent.scan, in_front ? seg - 1 : seg);
+        }
     }
     if (TRACE && lane == 0) {
         unsigned long long t_end;

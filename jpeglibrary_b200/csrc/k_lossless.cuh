@@ -26,7 +26,8 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const JbDevScan *
                         const uint32_t *__restrict__ image_list, uint32_t scan_index,
                         const JbHuffTable *__restrict__ tables, const uint8_t *__restrict__ arena,
                         const uint32_t *__restrict__ marks, const JbScanResult *__restrict__ scanres,
-                        int16_t *__restrict__ store, uint32_t *__restrict__ status, int lanes_per_warp)
+                        int16_t *__restrict__ store, uint32_t *__restrict__ status, int lanes_per_warp,
+                        uint32_t *__restrict__ first_error)
 {
     const uint32_t image = image_list[blockIdx.y];
     const JbDevImage &im = images[image];
@@ -48,7 +49,7 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const JbDevScan *
         else {
             // no RSTn in front of this interval.  EOI at a restart boundary ends the scan quietly (:172-176): the
             // intervals behind it are simply not there; any other marker is the previous interval's error
-            if (sr.end_marker != 0xD9u) atomicOr(status + image, JB_ST_EXPECT_RST);
+            if (sr.end_marker != 0xD9u) jb_report_error(status, first_error, image, JB_ST_EXPECT_RST, scan_index, seg - 1);
             return;
         }
     }
@@ -89,7 +90,7 @@ jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const JbDevScan *
         if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u;
         if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
     }
-    if (err) atomicOr(status + image, err);
+    if (err) jb_report_error(status, first_error, image, err, scan_index, seg);
 }
 
 __device__ __forceinline__ int jb_lossless_px(int predictor, int ra, int rb, int rc)

@@ -200,8 +200,8 @@ def test_batch_of_mixed_images_device_resident():
         assert b.status() == [0] * len(blobs)
         # restart scan + segment descriptors + absent-interval clear + segment Huffman + self-sync chain for lake.jpg (un-stuff count and
         # copy, guess round, 5 sync rounds, prefix sums, descriptors, write) + one IDCT/colour launch per layout
-        # (+ the status and MCU-limit clears at the start and the status mailbox post at the end)
-        assert b.launch_count() == 2 + 1 + 3 + (6 + 5) + 2 + 1
+        # (+ the status, MCU-limit and first-error clears at the start and the status mailbox post at the end)
+        assert b.launch_count() == 3 + 1 + 3 + (6 + 5) + 2 + 1
         for i, blob in enumerate(blobs):
             assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
         b.upload(); b.launch(); b.finish()   # a batch object can be re-run

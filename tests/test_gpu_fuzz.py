@@ -276,3 +276,32 @@ def test_streams_the_campaign_found():
         O.decode(blob, want_rgb=False)
     got, err = run_gpu(blob)
     assert isinstance(err, J.InvalidDataException)
+
+
+def test_a_stream_with_two_defects_raises_what_the_reference_meets_first():
+    """Restart-coded baseline frame with one truncated interval (the bit stream ends prematurely: InvalidDataException) and
+    one restart marker overwritten by an SOI (InvalidOperationException, "Expect restart marker."): the reference
+    stops at whichever comes first in the stream.  The kernels decode all intervals at once; every failure takes part in an
+    atomicMin on its place in the stream (jb_report_error) and the host reports the class of the smallest."""
+    base = synth.encode_jpeg(synth.synth_rgb(44, 320, 240), quality=85, subsampling="4:2:0", restart_rows=1)
+    sos = base.find(b"\xff\xda")
+    rst = [i for i in range(sos, len(base) - 1) if base[i] == 0xFF and 0xD0 <= base[i + 1] <= 0xD7]
+    assert len(rst) >= 13
+    seen = []
+    for marker_at, short_at in ((3, 8), (8, 3), (5, 5), (2, 12), (12, 2), (6, 7), (7, 6)):
+        b = bytearray(base)
+        b[rst[marker_at] + 1] = 0xD8                                   # an SOI where an RSTn is due
+        lo, hi = rst[short_at] + 2, rst[short_at + 1]
+        del b[lo + 3:hi]                                               # (behind the marker edit: its position stays valid
+        blob = bytes(b)                                                #  only when short_at > marker_at, so redo it)
+        if short_at < marker_at:
+            b = bytearray(base)
+            del b[lo + 3:hi]
+            b[rst[marker_at] + 1 - (hi - lo - 3)] = 0xD8
+            blob = bytes(b)
+        want, werr = run_oracle(blob)
+        got, gerr = run_gpu(blob)
+        assert werr is not None and gerr is not None, (marker_at, short_at)
+        assert isinstance(gerr, J.InvalidDataException if werr.code == -1 else J.InvalidOperationException), (marker_at, short_at, werr)
+        seen.append(werr.code)
+    assert set(seen) == {-1, -2}, seen
