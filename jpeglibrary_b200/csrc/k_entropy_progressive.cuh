@@ -97,7 +97,9 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
         else {
             // no RSTn in front of this interval.  EOI at a restart boundary ends the scan quietly (HandleRestart
             // :203-207): the intervals behind it are simply not there; any other marker is an error
-            if (sr.end_marker != 0xD9u) err = JB_ST_EXPECT_RST;
+            // ("no RSTn in front of this interval" is met behind the previous one: reported with that place, here and now --
+            // nothing else can fail in a job that decodes nothing)
+            if (sr.end_marker != 0xD9u) jb_report_error(status, first_error, image, JB_ST_EXPECT_RST, ent.scan, seg - 1);
             // a scan of a sequential frame that ends here never calls WriteBlock for the MCUs behind this point
             // (JpegHuffmanBaselineScanDecoder.cs:144-150): the renderer takes the first such point of every scan
             else if (sc.seq) atomicMin(scan_limit + im.scan_base + ent.scan, first);
@@ -442,11 +444,7 @@ jb_k1c_progressive_scans(const JbDevImage *__restrict__ images, const JbDevScan 
             if (marker_ok && (mk[seg] & 8u) != 0) marker_ok = sr.end_marker == 0xD9u;
             if (real >= 8 || p < stop || !marker_ok) err |= JB_ST_EXPECT_RST;
         }
-        if (err) {
-            // ("no RSTn in front of this interval" is met behind the previous one; count == 0 then and nothing else can fail)
-            const bool in_front = count == 0 && seg > 0 && err == JB_ST_EXPECT_RST;
-            jb_report_error(status, first_error, image, err, ent.scan, in_front ? seg - 1 : seg);
-        }
+        if (err) jb_report_error(status, first_error, image, err, ent.scan, seg);
     }
     if (TRACE && lane == 0) {
         unsigned long long t_end;
