@@ -336,6 +336,13 @@ __global__ void jb_clear_arena_tails(const JbDevImage *__restrict__ images, int 
     for (uint64_t p = from + lane; p < to; p += 32) arena[p] = 0xFF;
 }
 
+// a[list[i]] = 0 (status words of the images of one path)
+__global__ void jb_clear_listed_u32(uint32_t *__restrict__ a, const uint32_t *__restrict__ list, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[list[i]] = 0;
+}
+
 __global__ void jb_post_status(uint32_t *__restrict__ mailbox, const uint32_t *__restrict__ status, int count,
                                const uint32_t *__restrict__ changed_last, const uint32_t *__restrict__ limits,
                                const uint32_t *__restrict__ first_error)
@@ -1762,6 +1769,10 @@ static int resync_and_rerun(jb_batch *b)
     jb_k1b_scan<<<nimg, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_info, b->d_status, b->ss_shift);
     dim3 dgrid((b->ss_max_sub + 255) / 256, nimg);
     jb_k1b_descs<<<dgrid, 256, 0, st>>>(b->d_images, list, b->d_clean_len, b->d_exits, b->d_info, b->d_sub_segs, b->ss_shift);
+    // The write pass that ran on the entry states of round JB_SS_ROUNDS decoded some sub-sequences from the wrong place:
+    // whatever it flagged there (a bad code in what is not a code) is void, the pass below gives the verdict.  (Found by
+    // profiles/fuzz_shapes.py: a valid 57 x 218 noise frame at quality 96 needs more rounds and came back as InvalidData.)
+    jb_clear_listed_u32<<<(nimg + 255) / 256, 256, 0, st>>>(b->d_status, list, (int)nimg);
     if (int rc = launch_k1_flat<true>(b, b->d_sub_segs, (uint32_t)b->ss_total_sub, b->d_clean)) return rc;
     int dummy = 0;
     launch_render(b, &dummy);
@@ -1862,6 +1873,7 @@ int jb_decode_batch_finish(jb_batch *b)
     if (!b->ss_images.empty() && b->h_mailbox[b->count] != 0) {
         // the last synchronisation round must not have changed anything; otherwise (sub-sequences that
         // need more than JB_SS_ROUNDS hops to synchronise: rare) keep iterating and redo the output
+        if (getenv("JB_DEBUG_STATUS")) fprintf(stderr, "jb: the last sync round changed %u sub-sequences: iterating to convergence\n", b->h_mailbox[b->count]);
         int rc = resync_and_rerun(b);
         if (rc) return rc;
         jb_post_status<<<(b->count + 255) / 256, 256, 0, ctx->stream>>>(b->h_mailbox, b->d_status, b->count, nullptr, b->d_limits, b->d_first_error);

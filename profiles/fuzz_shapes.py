@@ -1,0 +1,117 @@
+"""VALID streams of random geometry through the GPU path and the oracle: decode (baseline / progressive, every Pillow
+sampling, restart intervals in rows or blocks, optimised tables, grey; sizes 1..400 px) and encode (random size, sampling,
+quality and content; standard and package-merge tables), plus the optimizer on the decoder's inputs.  Geometry edge
+cases -- images smaller than a block, one-MCU rows, restart intervals longer than the scan -- live here.
+usage (on a GPU box): python profiles/fuzz_shapes.py [trials] [seed]"""
+import os
+import sys
+import numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import jpeglibrary_b200 as J
+import oracle_ffi as O
+import synth
+
+trials = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 4242
+rng = np.random.default_rng(seed)
+os.makedirs("gpurun_out", exist_ok=True)
+
+
+def content(w, h):
+    k = int(rng.integers(4))
+    if k == 0:
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)                       # noise
+    if k == 1:
+        return np.full((h, w, 3), rng.integers(0, 256, 3), dtype=np.uint8)           # flat
+    if k == 2:
+        return synth.synth_rgb(int(rng.integers(1 << 20)), w, h)
+    g = (np.add.outer(np.arange(h), np.arange(w)) * int(rng.integers(1, 9))) & 255  # gradient
+    return np.stack([g, 255 - g, g // 2], axis=-1).astype(np.uint8)
+
+
+def size():
+    return [int(rng.integers(1, 17)), int(rng.integers(1, 65)), int(rng.integers(1, 401))][int(rng.integers(3))]
+
+
+bad = dec_n = enc_n = opt_n = 0
+for t in range(trials):
+    w, h = size(), size()
+    rgb = content(w, h)
+    # ---- decode
+    kw = dict(quality=int(rng.integers(1, 101)))
+    gray = rng.integers(6) == 0
+    if gray:
+        kw["gray"] = True
+    else:
+        kw["subsampling"] = ["4:4:4", "4:2:2", "4:2:0"][int(rng.integers(3))]
+    if rng.integers(2):
+        kw["progressive"] = True
+    r = int(rng.integers(4))
+    if r == 1:
+        kw["restart_rows"] = int(rng.integers(1, 4))
+    elif r == 2:
+        kw["restart_blocks"] = int(rng.integers(1, 40))
+    if rng.integers(3) == 0:
+        kw["optimize"] = True
+    try:
+        blob = synth.encode_jpeg(rgb, **kw)
+    except OSError:  # (Pillow refuses some combinations, e.g. its output buffer is too small for noise at quality 100)
+        continue
+    what = f"decode {w}x{h} {kw}"
+    try:
+        want = O.decode(blob)
+        werr = None
+    except O.OracleError as e:
+        want, werr = None, e
+    try:
+        dec = J.JpegDecoder(); dec.SetInput(blob); dec.Identify()
+        planes = np.zeros((dec.NumberOfComponents, dec.Height, dec.Width), dtype=np.int16)
+        dec.SetOutputWriter(J.CudaOutputWriter(planes, J.JB_OUT_PLANAR_I16)); dec.Decode()
+        out = np.zeros((dec.Height, dec.Width, 3), dtype=np.uint8)
+        dec = J.JpegDecoder(); dec.SetInput(blob); dec.Identify()
+        dec.SetOutputWriter(J.CudaOutputWriter(out, J.JB_OUT_RGB24)); dec.Decode()
+        gerr = None
+    except (J.InvalidDataException, J.InvalidOperationException, J.NotSupportedException) as e:
+        gerr = e
+    dec_n += 1
+    ok = (werr is None) == (gerr is None)
+    if ok and werr is None:
+        wr = O.written_samples(want)
+        ok = np.array_equal(planes[wr], want.planes[wr]) and int(np.abs(out.astype(int) - want.rgb.astype(int))[wr.all(axis=0)].max(initial=0)) <= 1
+    if not ok:
+        bad += 1
+        open(f"gpurun_out/shape_{t}.jpg", "wb").write(blob)
+        print(f"trial {t}: {what}: oracle [{werr}] GPU [{gerr}]", flush=True)
+    # ---- optimizer on the same stream (sequential single-scan frames only)
+    if werr is None and not kw.get("progressive"):
+        try:
+            opt = J.JpegOptimizer(); opt.MostOptimalCoding = bool(rng.integers(2)); opt.SetInput(blob); opt.Scan()
+            o2 = bytearray(); opt.SetOutput(o2); opt.Optimize(bool(rng.integers(2)))
+            back = O.decode(bytes(o2), want_rgb=False)
+            same = all(np.array_equal(a, b) for a, b in zip(want.coef, back.coef))
+        except Exception as e:  # noqa: BLE001
+            same = False
+            print(f"trial {t}: optimize {what}: {type(e).__name__}: {e}", flush=True)
+        opt_n += 1
+        if not same:
+            bad += 1
+            open(f"gpurun_out/shape_opt_{t}.jpg", "wb").write(blob)
+            print(f"trial {t}: optimize {what}: coefficients differ", flush=True)
+    # ---- encode
+    ss = [(1, 1), (2, 1), (1, 2), (2, 2)][int(rng.integers(4))]
+    q = int(rng.integers(1, 101))
+    mo = bool(rng.integers(3) == 0)
+    what = f"encode {w}x{h} q{q} {ss} most_optimal={mo}"
+    try:
+        wantb = O.encode_ycbcr(O.rgb_to_ycbcr(rgb), quality=q, subsampling=ss, optimal=mo).bytes
+        got, _ = J.encode_rgb(rgb, quality=q, subsampling=ss, most_optimal=mo)
+        same = got == wantb
+    except Exception as e:  # noqa: BLE001
+        same = False
+        print(f"trial {t}: {what}: {type(e).__name__}: {e}", flush=True)
+    enc_n += 1
+    if not same:
+        bad += 1
+        np.save(f"gpurun_out/shape_enc_{t}.npy", rgb)
+        print(f"trial {t}: {what}: streams differ", flush=True)
+print(f"{dec_n} decodes, {opt_n} optimizer runs, {enc_n} encodes: {bad} disagreements")

@@ -178,6 +178,23 @@ def test_self_synchronising_decode_without_restart_markers(kw):
     assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
 
 
+def test_self_sync_stream_that_needs_more_rounds_than_the_launch_runs():
+    """A valid noise frame at quality 96 (long codes, little to synchronise on): after the five re-sync rounds of the
+    launch some entry states still move, the host iterates to convergence and redoes the write pass -- whose verdict
+    counts, not what the first write pass flagged while it decoded from wrong entry states (profiles/fuzz_shapes.py
+    found the stale InvalidDataException)."""
+    import os
+    blob = open(os.path.join(os.path.dirname(__file__), "fixtures", "valid_420_no_restart_slow_to_synchronise.jpg"), "rb").read()
+    check_coefficients(blob)
+    o = O.decode(blob)
+    assert np.array_equal(gpu_planes(blob), o.planes)
+    assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
+    with J.JpegBatchDecoder([blob, synth.synth_jpeg(3, 320, 240), blob], J.JB_OUT_RGB24, device_output=True) as b:
+        b.run()
+        assert b.status() == [0, 0, 0]
+        assert np.abs(b.read_output(2).astype(int) - o.rgb.astype(int)).max() <= 1
+
+
 def test_self_sync_equals_restart_decode_on_same_pixels():
     """Size-independent property at the bench's full size: the same 4K pixels coded with and without
     restart markers must give identical coefficients through the two different GPU entropy paths."""
