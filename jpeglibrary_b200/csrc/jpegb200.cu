@@ -1743,6 +1743,42 @@ static int launch_render(jb_batch *b, int *launches)
     return JB_OK;
 }
 
+// One image's pixels (or sample planes) from the device staging buffer to the caller's host buffer, row by row: only the
+// bytes of the pixels are written -- the padding of a pitch wider than a row stays the caller's -- and only the MCUs that
+// were decoded (`limit`, see d_limits): whole MCU rows, then the decoded MCUs of the row the scan ended in.
+static cudaError_t copy_rows_to_host(jb_batch *b, int i, uint32_t limit)
+{
+    const ImagePlan &pl = b->plans[i];
+    const JbDevImage &d = pl.dev;
+    limit = std::min<uint32_t>(limit, d.total_mcus);
+    const uint32_t bpp = pl.out.format == JB_OUT_PLANAR_I16 ? 2 : pl.out.format == JB_OUT_RGBA32 ? 4 : 3;
+    const uint32_t planes = pl.out.format == JB_OUT_PLANAR_I16 ? d.ncomp : 1;
+    const uint32_t rows_full = std::min<uint32_t>(d.height, limit / d.mcus_per_line * 8u * d.vmax);
+    const uint32_t rem_px = std::min<uint32_t>(d.width, limit % d.mcus_per_line * 8u * d.hmax);
+    const uint32_t rem_rows = std::min<uint32_t>(8u * d.vmax, d.height - rows_full);
+    for (uint32_t p = 0; p < planes; p++) {
+        const uint64_t off = (uint64_t)p * d.height * d.out_pitch;
+        uint8_t *dh = static_cast<uint8_t *>(pl.out.dst) + off;
+        const uint8_t *sd = static_cast<const uint8_t *>(pl.dev_out) + off;
+        cudaError_t e = cudaSuccess;
+        if (rows_full)
+            e = cudaMemcpy2DAsync(dh, d.out_pitch, sd, d.out_pitch, (size_t)d.width * bpp, rows_full, cudaMemcpyDeviceToHost,
+                                  b->ctx->stream);
+        if (e == cudaSuccess && rem_px && rem_rows)
+            e = cudaMemcpy2DAsync(dh + (uint64_t)rows_full * d.out_pitch, d.out_pitch, sd + (uint64_t)rows_full * d.out_pitch,
+                                  d.out_pitch, (size_t)rem_px * bpp, rem_rows, cudaMemcpyDeviceToHost, b->ctx->stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// is the destination tightly packed (a row's pixels fill its pitch)?  Then the whole result is one contiguous copy.
+static bool tightly_packed(const ImagePlan &pl)
+{
+    const uint32_t bpp = pl.out.format == JB_OUT_PLANAR_I16 ? 2 : pl.out.format == JB_OUT_RGBA32 ? 4 : 3;
+    return pl.dev.out_pitch == (uint64_t)pl.dev.width * bpp;
+}
+
 // slow path of the self-synchronising decoder: iterate rounds until one changes nothing, then redo
 // prefix sums, coefficient output and rendering
 static int resync_and_rerun(jb_batch *b)
@@ -1783,8 +1819,10 @@ static int resync_and_rerun(jb_batch *b)
         if (pl.out.format == JB_OUT_COEFFICIENTS)
             JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, b->d_coef + pl.dev.coef_off * 64, pl.out_bytes,
                                          pl.out.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
-        else if (!pl.out.on_device)
-            JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, pl.dev_out, pl.out_bytes, cudaMemcpyDeviceToHost, st));
+        else if (!pl.out.on_device) {
+            if (tightly_packed(pl)) JB_CUDA(ctx, cudaMemcpyAsync(pl.out.dst, pl.dev_out, pl.out_bytes, cudaMemcpyDeviceToHost, st));
+            else JB_CUDA(ctx, copy_rows_to_host(b, i, 0xFFFFFFFFu));
+        }
     }
     return JB_OK;
 }
@@ -1835,7 +1873,7 @@ int jb_decode_batch_finish(jb_batch *b)
         } else if (!pl.out.on_device) {
             const uint32_t limit = b->may_truncate ? b->h_mailbox[b->count + 1 + i] : 0xFFFFFFFFu;
             const JbDevImage &d = pl.dev;
-            if (limit >= d.total_mcus) {
+            if (limit >= d.total_mcus && tightly_packed(pl)) {
                 const uint8_t *s8 = static_cast<const uint8_t *>(src);
                 uint8_t *d8 = static_cast<uint8_t *>(pl.out.dst);
                 // (exactly adjacent only: bytes between two results belong to the caller and are never written)
@@ -1848,24 +1886,7 @@ int jb_decode_batch_finish(jb_batch *b)
                 continue;
             }
             JB_CUDA(ctx, flush_run());
-            // whole MCU rows, then the decoded MCUs of the row the scan ended in; per plane for planar output
-            const uint32_t bpp = pl.out.format == JB_OUT_PLANAR_I16 ? 2 : pl.out.format == JB_OUT_RGBA32 ? 4 : 3;
-            const uint32_t planes = pl.out.format == JB_OUT_PLANAR_I16 ? d.ncomp : 1;
-            const uint32_t rows_full = std::min<uint32_t>(d.height, limit / d.mcus_per_line * 8u * d.vmax);
-            const uint32_t rem_px = std::min<uint32_t>(d.width, limit % d.mcus_per_line * 8u * d.hmax);
-            const uint32_t rem_rows = std::min<uint32_t>(8u * d.vmax, d.height - rows_full);
-            for (uint32_t p = 0; p < planes; p++) {
-                const uint64_t off = (uint64_t)p * d.height * d.out_pitch;
-                uint8_t *dh = static_cast<uint8_t *>(pl.out.dst) + off;
-                const uint8_t *sd = static_cast<const uint8_t *>(src) + off;
-                if (rows_full)
-                    JB_CUDA(ctx, cudaMemcpy2DAsync(dh, d.out_pitch, sd, d.out_pitch, (size_t)d.width * bpp, rows_full,
-                                                   cudaMemcpyDeviceToHost, ctx->stream));
-                if (rem_px && rem_rows)
-                    JB_CUDA(ctx, cudaMemcpy2DAsync(dh + (uint64_t)rows_full * d.out_pitch, d.out_pitch,
-                                                   sd + (uint64_t)rows_full * d.out_pitch, d.out_pitch, (size_t)rem_px * bpp,
-                                                   rem_rows, cudaMemcpyDeviceToHost, ctx->stream));
-            }
+            JB_CUDA(ctx, copy_rows_to_host(b, i, limit));
         }
     }
     JB_CUDA(ctx, flush_run());

@@ -33,7 +33,28 @@ def size():
     return [int(rng.integers(1, 17)), int(rng.integers(1, 65)), int(rng.integers(1, 401))][int(rng.integers(3))]
 
 
-bad = dec_n = enc_n = opt_n = 0
+bad = dec_n = enc_n = opt_n = ll_n = fmt_n = batch_n = 0
+pool = []  # valid streams with their RGB, decoded again as one mixed batch every 48 trials
+
+
+def check_batch():
+    global bad, batch_n
+    if not pool:
+        return
+    blobs = [p[0] for p in pool]
+    for device_output in (True, False):
+        with J.JpegBatchDecoder(blobs, J.JB_OUT_RGB24, device_output=device_output) as b:
+            b.run()
+            st = b.status()
+            for i, (blob, rgbw) in enumerate(pool):
+                batch_n += 1
+                if st[i] != 0 or not np.array_equal(b.read_output(i), rgbw):
+                    bad += 1
+                    open(f"gpurun_out/shape_batch_{batch_n}.jpg", "wb").write(blob)
+                    print(f"batch image {i} (device_output={device_output}): status {st[i]} or pixels differ from its own single decode", flush=True)
+    pool.clear()
+
+
 for t in range(trials):
     w, h = size(), size()
     rgb = content(w, h)
@@ -82,6 +103,58 @@ for t in range(trials):
         bad += 1
         open(f"gpurun_out/shape_{t}.jpg", "wb").write(blob)
         print(f"trial {t}: {what}: oracle [{werr}] GPU [{gerr}]", flush=True)
+    if werr is None and gerr is None:
+        pool.append((blob, out.copy()))
+        # ---- the other sinks: RGBA32, YCbCr888, a padded pitch, a device destination
+        try:
+            dec = J.JpegDecoder(); dec.SetInput(blob); dec.Identify()
+            H, W = dec.Height, dec.Width
+            rgba = np.zeros((H, W, 4), np.uint8)
+            dec.SetOutputWriter(J.CudaOutputWriter(rgba, J.JB_OUT_RGBA32)); dec.Decode()
+            dec = J.JpegDecoder(); dec.SetInput(blob); dec.Identify()
+            ycc = np.zeros((H, W, 3), np.uint8)
+            dec.SetOutputWriter(J.CudaOutputWriter(ycc, J.JB_OUT_YCBCR888)); dec.Decode()
+            pitch = (3 * W + int(rng.integers(1, 40)) + 3) // 4 * 4
+            padded = np.full((H, pitch), 0xA5, np.uint8)
+            dec = J.JpegDecoder(); dec.SetInput(blob); dec.Identify()
+            dec.SetOutputWriter(J.CudaOutputWriter(padded, J.JB_OUT_RGB24, pitch=pitch)); dec.Decode()
+            same = (np.array_equal(rgba[..., :3], out) and (rgba[..., 3] == 255).all() and np.array_equal(ycc, want.ycbcr)
+                    and np.array_equal(padded[:, :3 * W].reshape(H, W, 3), out) and (padded[:, 3 * W:] == 0xA5).all())
+        except Exception as e:  # noqa: BLE001
+            same = False
+            print(f"trial {t}: sinks {what}: {type(e).__name__}: {e}", flush=True)
+        fmt_n += 1
+        if not same:
+            bad += 1
+            open(f"gpurun_out/shape_fmt_{t}.jpg", "wb").write(blob)
+            print(f"trial {t}: sinks {what}: RGBA32 / YCbCr888 / padded pitch differ", flush=True)
+    if len(pool) >= 48:
+        check_batch()
+    # ---- lossless (SOF3) of random geometry
+    if t % 3 == 0:
+        ncomp = [1, 3, 3][int(rng.integers(3))]
+        samp = [(1, 1)] * ncomp
+        if ncomp == 3 and rng.integers(2):
+            samp = [[(2, 2), (1, 1), (1, 1)], [(2, 1), (1, 1), (1, 1)], [(1, 2), (1, 1), (1, 1)]][int(rng.integers(3))]
+        hm, vm = max(a for a, _ in samp), max(b for _, b in samp)
+        lw, lh = max(hm, size() // 4 // hm * hm), max(vm, size() // 4 // vm * vm)
+        prec = int(rng.integers(2, 17))
+        lkw = dict(precision=prec, predictor=int(rng.integers(1, 8)), sampling=samp, ncomp=ncomp,
+                   point_transform=int(rng.integers(0, min(prec - 8, 4) + 1)) if prec > 8 and rng.integers(3) == 0 else 0,
+                   restart=int(rng.integers(1, 60)) if rng.integers(2) else 0)
+        try:
+            lblob, coded = synth.synth_lossless(int(rng.integers(1 << 16)), lw, lh, **lkw)
+            dec = J.JpegDecoder(); dec.SetInput(lblob); dec.Identify()
+            lp = np.zeros((dec.NumberOfComponents, dec.Height, dec.Width), dtype=np.int16)
+            dec.SetOutputWriter(J.CudaOutputWriter(lp, J.JB_OUT_PLANAR_I16)); dec.Decode()
+            same = np.array_equal(lp, coded) and np.array_equal(lp, O.decode(lblob, want_rgb=False).planes)
+        except Exception as e:  # noqa: BLE001
+            same = False
+            print(f"trial {t}: lossless {lw}x{lh} {lkw}: {type(e).__name__}: {e}", flush=True)
+        ll_n += 1
+        if not same:
+            bad += 1
+            print(f"trial {t}: lossless {lw}x{lh} {lkw}: planes differ", flush=True)
     # ---- optimizer on the same stream (sequential single-scan frames only)
     if werr is None and not kw.get("progressive"):
         try:
@@ -114,4 +187,6 @@ for t in range(trials):
         bad += 1
         np.save(f"gpurun_out/shape_enc_{t}.npy", rgb)
         print(f"trial {t}: {what}: streams differ", flush=True)
-print(f"{dec_n} decodes, {opt_n} optimizer runs, {enc_n} encodes: {bad} disagreements")
+check_batch()
+print(f"{dec_n} decodes, {fmt_n} x 3 other sinks, {batch_n} batch images, {ll_n} lossless frames, {opt_n} optimizer runs, {enc_n} encodes: "
+      f"{bad} disagreements")

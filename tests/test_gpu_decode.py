@@ -178,6 +178,23 @@ def test_self_synchronising_decode_without_restart_markers(kw):
     assert np.abs(gpu_pixels(blob).astype(int) - o.rgb.astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("kw", [dict(subsampling="4:2:0", restart_rows=1), dict(subsampling="4:4:4"), dict(gray=True),
+                                dict(subsampling="4:2:2", progressive=True)], ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()))
+def test_host_destination_with_a_padded_pitch_keeps_its_padding(kw):
+    """A pitch wider than a row of pixels: the bytes between the rows are the caller's (the reference's writer touches
+    pixels only); the result leaves the staging buffer row by row, not as one block."""
+    blob = synth.synth_jpeg(21, 77, 45, **kw)
+    want = gpu_pixels(blob)
+    pitch = 3 * 77 + 29
+    padded = np.full((45, pitch), 0xA5, np.uint8)
+    dec = J.JpegDecoder()
+    dec.SetInput(blob)
+    dec.SetOutputWriter(J.CudaOutputWriter(padded, J.JB_OUT_RGB24, pitch=pitch))
+    dec.Decode()
+    assert np.array_equal(padded[:, :3 * 77].reshape(45, 77, 3), want)
+    assert (padded[:, 3 * 77:] == 0xA5).all()
+
+
 def test_self_sync_stream_that_needs_more_rounds_than_the_launch_runs():
     """A valid noise frame at quality 96 (long codes, little to synchronise on): after the five re-sync rounds of the
     launch some entry states still move, the host iterates to convergence and redoes the write pass -- whose verdict
