@@ -52,9 +52,24 @@ def check_batch():
                     bad += 1
                     open(f"gpurun_out/shape_batch_{batch_n}.jpg", "wb").write(blob)
                     print(f"batch image {i} (device_output={device_output}): status {st[i]} or pixels differ from its own single decode", flush=True)
+    # the host-to-host pipeline (chunks on two contexts) over the same streams
+    global pipe, pinned
+    if pipe is None:
+        ctx = J.Context.default()
+        pipe = J.JpegPipelinedBatchDecoder([ctx, J.Context(0)], chunk=int(rng.integers(1, 9)), parse_threads=2)
+        pinned = ctx.pinned_array(64 * 1024 * 1024)
+    pinned[:] = 0
+    offs = pipe.decode(blobs, pinned)
+    for i, (blob, rgbw) in enumerate(pool):
+        batch_n += 1
+        if not np.array_equal(pinned[offs[i]:offs[i] + rgbw.size].reshape(rgbw.shape), rgbw):
+            bad += 1
+            open(f"gpurun_out/shape_pipe_{batch_n}.jpg", "wb").write(blob)
+            print(f"pipelined image {i}: pixels differ from its own single decode", flush=True)
     pool.clear()
 
 
+pipe = pinned = None
 for t in range(trials):
     w, h = size(), size()
     rgb = content(w, h)
