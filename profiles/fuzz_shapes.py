@@ -2,7 +2,7 @@
 sampling, restart intervals in rows or blocks, optimised tables, grey; sizes 1..400 px) and encode (random size, sampling,
 quality and content; standard and package-merge tables), plus the optimizer on the decoder's inputs.  Geometry edge
 cases -- images smaller than a block, one-MCU rows, restart intervals longer than the scan -- live here.
-usage (on a GPU box): python profiles/fuzz_shapes.py [trials] [seed]"""
+usage (on a GPU box): python profiles/fuzz_shapes.py [trials] [seed] [largest side, default 400]"""
 import os
 import sys
 import numpy as np
@@ -13,6 +13,7 @@ import synth
 
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 300
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 4242
+maxsize = int(sys.argv[3]) if len(sys.argv) > 3 else 400
 rng = np.random.default_rng(seed)
 os.makedirs("gpurun_out", exist_ok=True)
 
@@ -30,7 +31,7 @@ def content(w, h):
 
 
 def size():
-    return [int(rng.integers(1, 17)), int(rng.integers(1, 65)), int(rng.integers(1, 401))][int(rng.integers(3))]
+    return [int(rng.integers(1, 17)), int(rng.integers(1, 65)), int(rng.integers(1, maxsize + 1))][int(rng.integers(3))]
 
 
 bad = dec_n = enc_n = opt_n = ll_n = fmt_n = batch_n = 0
@@ -57,7 +58,7 @@ def check_batch():
     if pipe is None:
         ctx = J.Context.default()
         pipe = J.JpegPipelinedBatchDecoder([ctx, J.Context(0)], chunk=int(rng.integers(1, 9)), parse_threads=2)
-        pinned = ctx.pinned_array(64 * 1024 * 1024)
+        pinned = ctx.pinned_array(max(64, 48 * 3 * maxsize * maxsize // (1 << 20) // 3 + 64) * 1024 * 1024)
     pinned[:] = 0
     offs = pipe.decode(blobs, pinned)
     for i, (blob, rgbw) in enumerate(pool):
