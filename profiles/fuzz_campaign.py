@@ -42,6 +42,23 @@ if "--wide" in sys.argv:   # layouts and scan scripts neither of the other two s
         "sequential_luma_then_chroma_pair": synth.resequence_scans(src, O.decode(src, want_rgb=False), [[0], [1, 2]], 7),
         "no_restart_420_large": synth.encode_jpeg(synth.synth_rgb(54, 1280, 720), quality=85, subsampling="4:2:0"),
     }
+if "--cmyk" in sys.argv:   # four components (planar int16 output only: the reference's app sink takes 1 or 3)
+    import io
+    from PIL import Image
+    rgb = synth.synth_rgb(60, 120, 88)
+    cmyk = np.concatenate([rgb, rgb[..., :1][..., ::-1]], axis=-1).astype(np.uint8)
+
+    def enc(**kw):
+        buf = io.BytesIO()
+        Image.fromarray(cmyk, "CMYK").save(buf, format="JPEG", **kw)
+        return buf.getvalue()
+    bases = {
+        "cmyk_444": enc(quality=85),
+        "cmyk_444_restart": enc(quality=90, restart_marker_blocks=6),
+        "cmyk_420": enc(quality=75, subsampling="4:2:0"),
+        "cmyk_420_restart_optimized": enc(quality=80, subsampling="4:2:0", restart_marker_rows=1, optimize=True),
+        "cmyk_progressive": enc(quality=80, progressive=True),   # (the reference refuses its scan script: quirk P6)
+    }
 for name, blob in bases.items():
     rng = np.random.default_rng(seed + sum(map(ord, name)))
     ok = err = 0
