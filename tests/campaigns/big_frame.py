@@ -1,5 +1,5 @@
 """One very large frame (default 40000 x 36000 = 1.44 GP: RGB output and coefficient store both above 4 GiB) through
-the GPU path and the oracle: 32-bit overflow check.  usage (on a GPU box): python profiles/big_frame.py [width height] [--no-restart]"""
+the GPU path and the oracle: 32-bit overflow check.  usage (on a GPU box): python tests/campaigns/big_frame.py [width height] [--no-restart]"""
 import sys, time, hashlib, io
 import numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")

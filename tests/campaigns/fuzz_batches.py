@@ -1,7 +1,7 @@
 """Damaged streams decoded as BATCHES: streams of every base type mixed in one jb_decode_batch call (good ones among them),
 every image compared with the oracle -- a damaged image must fail (or decode to garbage) alone, whatever shares its
 batch, its warps, its table cache and its arena neighbours.
-usage (on a GPU box): python profiles/fuzz_batches.py [batches] [images per batch] [seed]"""
+usage (on a GPU box): python tests/campaigns/fuzz_batches.py [batches] [images per batch] [seed]"""
 import ctypes as C
 import os
 import sys

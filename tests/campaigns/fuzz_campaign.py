@@ -1,6 +1,6 @@
 """A longer run of the corrupted-stream parity tests (tests/test_gpu_fuzz.py) with other seeds: every disagreement
 between the GPU path and the oracle is printed and the stream is kept under gpurun_out/.
-usage (on a GPU box): python profiles/fuzz_campaign.py [trials per stream] [seed] [--more]"""
+usage (on a GPU box): python tests/campaigns/fuzz_campaign.py [trials per stream] [seed] [--more]"""
 import os, sys
 import numpy as np
 sys.path.insert(0, "."); sys.path.insert(0, "tests")

@@ -2,7 +2,7 @@
 sampling, restart intervals in rows or blocks, optimised tables, grey; sizes 1..400 px) and encode (random size, sampling,
 quality and content; standard and package-merge tables), plus the optimizer on the decoder's inputs.  Geometry edge
 cases -- images smaller than a block, one-MCU rows, restart intervals longer than the scan -- live here.
-usage (on a GPU box): python profiles/fuzz_shapes.py [trials] [seed] [largest side, default 400]"""
+usage (on a GPU box): python tests/campaigns/fuzz_shapes.py [trials] [seed] [largest side, default 400]"""
 import os
 import sys
 import numpy as np

@@ -198,7 +198,7 @@ def test_host_destination_with_a_padded_pitch_keeps_its_padding(kw):
 def test_self_sync_stream_that_needs_more_rounds_than_the_launch_runs():
     """A valid noise frame at quality 96 (long codes, little to synchronise on): after the five re-sync rounds of the
     launch some entry states still move, the host iterates to convergence and redoes the write pass -- whose verdict
-    counts, not what the first write pass flagged while it decoded from wrong entry states (profiles/fuzz_shapes.py
+    counts, not what the first write pass flagged while it decoded from wrong entry states (tests/campaigns/fuzz_shapes.py
     found the stale InvalidDataException)."""
     import os
     blob = open(os.path.join(os.path.dirname(__file__), "fixtures", "valid_420_no_restart_slow_to_synchronise.jpg"), "rb").read()
