@@ -137,12 +137,15 @@ _sigs = {
     },
     host: {
         "jbh_parse": (C.c_int, [_vp, C.c_uint64, C.POINTER(_vp)]),
+        "jbh_parse_with_tables": (C.c_int, [_vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(_vp)]),
+        "jbh_check_tables": (C.c_int, [_vp, C.c_uint64, C.POINTER(C.c_uint64)]),
         "jbh_desc": (C.POINTER(ImageDesc), [_vp]),
         "jbh_consumed": (C.c_uint64, [_vp]),
         "jbh_sof_marker": (C.c_int, [_vp]),
         "jbh_free": (None, [_vp]),
         "jbh_last_parse_error": (C.c_char_p, []),
         "jbh_parse_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+        "jbh_parse_batch_with_tables": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int, C.c_int, _vp]),
         "jbh_collect_descs": (C.c_int, [_vp, C.c_int, C.POINTER(ImageDesc)]),
     },
 }

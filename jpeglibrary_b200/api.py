@@ -122,10 +122,15 @@ class Context:
 class Parsed:
     """Result of the host marker walk for one stream (owns the native descriptor)."""
 
-    def __init__(self, data):
+    def __init__(self, data, tables=None):
         self._buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
         h = C.c_void_p()
-        rc = N.host.jbh_parse(self._buf.ctypes.data, self._buf.size, C.byref(h))
+        if tables is not None and len(tables):
+            # an abbreviated stream behind JpegDecoder.LoadTables (JpegDecoder.cs:313-360)
+            t = tables if isinstance(tables, np.ndarray) else np.frombuffer(tables, dtype=np.uint8)
+            rc = N.host.jbh_parse_with_tables(t.ctypes.data, t.size, self._buf.ctypes.data, self._buf.size, C.byref(h))
+        else:
+            rc = N.host.jbh_parse(self._buf.ctypes.data, self._buf.size, C.byref(h))
         if rc:
             _raise(rc, N.host.jbh_last_parse_error())
         self.handle = h
@@ -186,17 +191,35 @@ class JpegDecoder:
         self._input = None
         self._parsed = None
         self._writer = None
+        self._tables = b""
 
     # JpegDecoder.cs:49-62
     def SetInput(self, data):
         self._input = data
         self._parsed = None
 
+    # JpegDecoder.cs:313-360: DHT / DQT / DRI segments of a separate tables stream (abbreviated streams, e.g. the
+    # JPEGTables field of a TIFF file) become the state the marker loop of the next streams starts from.  Successive
+    # calls add up like they do in the reference's table registries (a later definition of an identifier wins).
+    def LoadTables(self, content):
+        content = np.frombuffer(bytes(content), dtype=np.uint8)
+        used = C.c_uint64(0)
+        rc = N.host.jbh_check_tables(content.ctypes.data, content.size, C.byref(used)) if content.size else 0
+        if rc:
+            _raise(rc, N.host.jbh_last_parse_error())
+        self._tables += content[:used.value].tobytes()  # without the EOI that ends the walk: the next call's bytes follow
+        self._parsed = None
+
+    # JpegDecoder.cs:960-973 (the registries LoadTables filled are emptied)
+    def ResetTables(self):
+        self._tables = b""
+        self._parsed = None
+
     # JpegDecoder.cs:75-105
     def Identify(self, loadQuantizationTables=False):
         if self._input is None or len(self._input) == 0:
             raise InvalidOperationException("Input buffer is not specified.")
-        self._parsed = Parsed(self._input)
+        self._parsed = Parsed(self._input, self._tables)
         return self._parsed.consumed
 
     def _frame(self):
@@ -242,7 +265,7 @@ class JpegDecoder:
         if self._writer is None:
             raise InvalidOperationException("The output buffer is not specified.")
         if self._parsed is None:
-            self._parsed = Parsed(self._input)
+            self._parsed = Parsed(self._input, self._tables)
         ctx = self._ctx or Context.default()
         d = self._parsed.desc
         if d.scan_count == 0 and d.sof != 2:
@@ -316,9 +339,10 @@ class JpegBatchDecoder:
     device arena and decoded by three kernel launches for the whole batch."""
 
     def __init__(self, blobs, format=N.JB_OUT_RGB24, context=None, device_output=True, parse_threads=8,
-                 host_outputs=None, parsed=None):
+                 host_outputs=None, parsed=None, tables=None):
         """parsed: marker-walk results (jbh_parse handles) of `blobs` when the caller has them already; ownership
-        passes to this object."""
+        passes to this object.  tables: one tables stream every blob is an abbreviated stream of (JpegDecoder.LoadTables,
+        JpegDecoder.cs:313-360: the strips / tiles of a TIFF file with its JPEGTables field)."""
         self.ctx = context or Context.default()
         n = len(blobs)
         self.count = n
@@ -329,7 +353,12 @@ class JpegBatchDecoder:
             ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
             lens = (C.c_uint64 * n)(*[b.size for b in self._bufs])
             self._parsed = (C.c_void_p * n)()
-            failed = N.host.jbh_parse_batch(ptrs, lens, n, parse_threads, self._parsed)
+            self._tables = None if tables is None else np.frombuffer(bytes(tables), dtype=np.uint8)
+            if self._tables is not None and self._tables.size:
+                failed = N.host.jbh_parse_batch_with_tables(self._tables.ctypes.data, self._tables.size, ptrs, lens, n,
+                                                            parse_threads, self._parsed)
+            else:
+                failed = N.host.jbh_parse_batch(ptrs, lens, n, parse_threads, self._parsed)
             if failed:
                 self._free_parsed()
                 raise InvalidDataException(f"{failed} of {n} streams failed the marker walk")
@@ -486,9 +515,9 @@ class JpegPipelinedBatchDecoder:
                            "H2D + kernels; finish_wait: waiting for H2D + kernels + D2H of the chunk (the GPU / PCIe time); "
                            "worker_idle: worker waiting for a parsed chunk"}
 
-    def decode(self, blobs, host_out, format=N.JB_OUT_RGB24):
+    def decode(self, blobs, host_out, format=N.JB_OUT_RGB24, tables=None):
         """Decode `blobs` into the (pinned) uint8 array `host_out`; image i lands at self.offsets[i].
-        Returns the per-image offsets."""
+        Returns the per-image offsets.  tables: see JpegBatchDecoder."""
         import queue
         import threading
         bpp = {N.JB_OUT_RGB24: 3, N.JB_OUT_RGBA32: 4, N.JB_OUT_YCBCR888: 3}[format]
@@ -497,6 +526,7 @@ class JpegPipelinedBatchDecoder:
         errors = []
         lock = threading.Lock()
         bufs = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        tbuf = None if tables is None else np.frombuffer(bytes(tables), dtype=np.uint8)
         offsets = [0] * n
         ready = queue.Queue(maxsize=2 * len(self.contexts))  # parsed chunks, in order: (first, last, handles, start, end)
 
@@ -514,7 +544,10 @@ class JpegPipelinedBatchDecoder:
                     ptrs = (C.c_void_p * m)(*[x.ctypes.data for x in bufs[a:b]])
                     lens = (C.c_uint64 * m)(*[x.size for x in bufs[a:b]])
                     handles = (C.c_void_p * m)()
-                    failed = N.host.jbh_parse_batch(ptrs, lens, m, self.parse_threads, handles)
+                    if tbuf is not None and tbuf.size:
+                        failed = N.host.jbh_parse_batch_with_tables(tbuf.ctypes.data, tbuf.size, ptrs, lens, m, self.parse_threads, handles)
+                    else:
+                        failed = N.host.jbh_parse_batch(ptrs, lens, m, self.parse_threads, handles)
                     if failed:
                         for h in handles:
                             if h:

@@ -83,15 +83,21 @@ extern "C" {
 
 const char *jbh_last_parse_error(void) { return g_parse_error.c_str(); }
 
-int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
+// `tables`: what JpegDecoder.LoadTables was given before the stream (abbreviated streams, e.g. the JPEGTables of a
+// TIFF file): its DHT / DQT / DRI segments are the state the marker loop of the stream starts from.
+// tables_used != nullptr: only the tables stream is walked (what LoadTables itself would raise), and the caller learns
+// how many of its bytes the walk took (an EOI, or bytes without a further marker, are left out).
+static int parse_impl(const uint8_t *tables, uint64_t tables_len, const uint8_t *data, uint64_t length, jbh_parsed **out,
+                      uint64_t *tables_used = nullptr)
 {
+    jbh_parsed *dummy = nullptr;
+    if (tables_used) { out = &dummy; *tables_used = 0; }
     if (!out) return JB_ERR_ARGUMENT;
     *out = nullptr;
-    if (!data || length == 0) {
+    if (!tables_used && (!data || length == 0)) {
         g_parse_error = "Input buffer is not specified.";
         return JB_ERR_INVALID_OPERATION;
     }
-    if (length < 2 || data[0] != 0xFF || data[1] != 0xD8) return perr(JB_ERR_INVALID_DATA, 0, "Marker StartOfImage not found.");
     jbh_parsed *p = new jbh_parsed;
     struct Guard {
         jbh_parsed *p;
@@ -120,6 +126,72 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
     int slot_comp[4] = {-1, -1, -1, -1};
     uint16_t slot_qt[4][64];
 
+    // DHT: possibly several tables per segment (JpegDecoder.ProcessDefineHuffmanTable)
+    auto on_dht = [&](const uint8_t *b, uint64_t n, uint64_t seg_at) -> int {
+        while (n > 0) {
+            if (n < 17) return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse Huffman table.");
+            jb_huff_spec s{};
+            s.table_class = b[0] >> 4;
+            s.identifier = b[0] & 15;
+            int cnt = 0;
+            for (int i = 0; i < 16; i++) { s.bits[i] = b[1 + i]; cnt += b[1 + i]; }
+            if (cnt > 256 || n < 17ull + cnt || s.table_class > 1 || s.identifier > 3)
+                return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse Huffman table.");
+            memcpy(s.values, b + 17, (size_t)cnt);
+            s.value_count = (uint16_t)cnt;
+            huff_latest[s.table_class][s.identifier] = (int)p->tables.size();
+            p->tables.push_back(s);
+            b += 17 + cnt;
+            n -= 17 + cnt;
+        }
+        return JB_OK;
+    };
+    auto on_dqt = [&](const uint8_t *b, uint64_t n, uint64_t seg_at) -> int {
+        while (n > 0) {
+            int pq = b[0] >> 4, tq = b[0] & 15;
+            uint64_t need = pq ? 129 : 65;
+            if (pq > 1 || tq > 3 || n < need) return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse quantization table.");
+            for (int i = 0; i < 64; i++) qt[tq][i] = pq ? (uint16_t)((b[1 + 2 * i] << 8) | b[2 + 2 * i]) : b[1 + i];
+            qt_present[tq] = true;
+            b += need;
+            n -= need;
+        }
+        return JB_OK;
+    };
+    auto on_dri = [&](const uint8_t *b, uint64_t n, uint64_t seg_at, bool in_stream) -> int {
+        if (n < 2) return perr(JB_ERR_INVALID_DATA, seg_at, "Unexpected end of input data when reading segment content.");
+        restart_interval = (uint32_t)((b[0] << 8) | b[1]);
+        if (in_stream) dri_seen = true;
+        return JB_OK;
+    };
+
+    // JpegDecoder.LoadTables (JpegDecoder.cs:319-360): SOI and RSTn are passed over, DHT / DQT / DRI are taken, anything
+    // else with a length is skipped, EOI or the end of the data ends the walk without complaint.  Its DRI is the value the
+    // decoder object holds when Identify() starts: it stays in force unless the stream brings its own.
+    if (tables && tables_len) {
+        Walker t{tables, tables_len, 0};
+        while (t.pos < tables_len) {
+            if (tables_used) *tables_used = t.pos;
+            int m = t.next_marker();
+            if (m < 0 || m == 0xD9) break;
+            if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7)) continue;
+            if (t.pos + 2 > tables_len) return perr(JB_ERR_INVALID_DATA, t.pos, "Unexpected end of input data when reading segment length.");
+            uint64_t seglen = ((uint64_t)tables[t.pos] << 8) | tables[t.pos + 1];
+            if (seglen < 2 || t.pos + seglen > tables_len) return perr(JB_ERR_INVALID_DATA, t.pos, "Unexpected end of input data reached.");
+            const uint8_t *b = tables + t.pos + 2;
+            const uint64_t n = seglen - 2, seg_at = t.pos;
+            t.pos += seglen;
+            int rc = JB_OK;
+            if (m == 0xC4) rc = on_dht(b, n, seg_at);
+            else if (m == 0xDB) rc = on_dqt(b, n, seg_at);
+            else if (m == 0xDD) rc = on_dri(b, n, seg_at, false);
+            if (rc) return rc;
+            if (tables_used) *tables_used = t.pos;
+        }
+    }
+    if (tables_used) return JB_OK; // (the guard frees p)
+
+    if (length < 2 || data[0] != 0xFF || data[1] != 0xD8) return perr(JB_ERR_INVALID_DATA, 0, "Marker StartOfImage not found.");
     Walker w{data, length, 2};
     bool eoi = false;
     while (!eoi && w.pos < length) {
@@ -164,41 +236,14 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
         }
         case 0xC5: case 0xC6: case 0xC7: case 0xCB: case 0xCD: case 0xCE: case 0xCF:
             return perr(JB_ERR_INVALID_DATA, seg_at, "This type of JPEG stream is not supported.");
-        case 0xC4: { // DHT: possibly several tables per segment
-            while (n > 0) {
-                if (n < 17) return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse Huffman table.");
-                jb_huff_spec s{};
-                s.table_class = b[0] >> 4;
-                s.identifier = b[0] & 15;
-                int cnt = 0;
-                for (int i = 0; i < 16; i++) { s.bits[i] = b[1 + i]; cnt += b[1 + i]; }
-                if (cnt > 256 || n < 17ull + cnt || s.table_class > 1 || s.identifier > 3)
-                    return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse Huffman table.");
-                memcpy(s.values, b + 17, (size_t)cnt);
-                s.value_count = (uint16_t)cnt;
-                huff_latest[s.table_class][s.identifier] = (int)p->tables.size();
-                p->tables.push_back(s);
-                b += 17 + cnt;
-                n -= 17 + cnt;
-            }
+        case 0xC4:
+            if (int rc = on_dht(b, n, seg_at)) return rc;
             break;
-        }
-        case 0xDB: {
-            while (n > 0) {
-                int pq = b[0] >> 4, tq = b[0] & 15;
-                uint64_t need = pq ? 129 : 65;
-                if (pq > 1 || tq > 3 || n < need) return perr(JB_ERR_INVALID_DATA, seg_at, "Failed to parse quantization table.");
-                for (int i = 0; i < 64; i++) qt[tq][i] = pq ? (uint16_t)((b[1 + 2 * i] << 8) | b[2 + 2 * i]) : b[1 + i];
-                qt_present[tq] = true;
-                b += need;
-                n -= need;
-            }
+        case 0xDB:
+            if (int rc = on_dqt(b, n, seg_at)) return rc;
             break;
-        }
         case 0xDD:
-            if (n < 2) return perr(JB_ERR_INVALID_DATA, seg_at, "Unexpected end of input data when reading segment content.");
-            restart_interval = (uint32_t)((b[0] << 8) | b[1]);
-            dri_seen = true;
+            if (int rc = on_dri(b, n, seg_at, true)) return rc;
             break;
         case 0xDA: {
             if (!have_frame) return perr(JB_ERR_INVALID_DATA, seg_at, "Scan header appears before frame header.");
@@ -268,12 +313,33 @@ int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out)
     return JB_OK;
 }
 
+int jbh_parse(const uint8_t *data, uint64_t length, jbh_parsed **out) { return parse_impl(nullptr, 0, data, length, out); }
+
+int jbh_parse_with_tables(const uint8_t *tables, uint64_t tables_length, const uint8_t *data, uint64_t length, jbh_parsed **out)
+{
+    return parse_impl(tables, tables_length, data, length, out);
+}
+
+int jbh_check_tables(const uint8_t *tables, uint64_t tables_length, uint64_t *used)
+{
+    uint64_t u = 0;
+    int rc = parse_impl(tables, tables_length, nullptr, 0, nullptr, &u);
+    if (used) *used = u;
+    return rc;
+}
+
 const jb_image_desc *jbh_desc(const jbh_parsed *p) { return p ? &p->desc : nullptr; }
 uint64_t jbh_consumed(const jbh_parsed *p) { return p ? p->consumed : 0; }
 int jbh_sof_marker(const jbh_parsed *p) { return p ? p->sof_marker : 0; }
 void jbh_free(jbh_parsed *p) { delete p; }
 
 int jbh_parse_batch(const uint8_t *const *data, const uint64_t *length, int count, int threads, jbh_parsed **out)
+{
+    return jbh_parse_batch_with_tables(nullptr, 0, data, length, count, threads, out);
+}
+
+int jbh_parse_batch_with_tables(const uint8_t *tables, uint64_t tables_length, const uint8_t *const *data,
+                                const uint64_t *length, int count, int threads, jbh_parsed **out)
 {
     if (!data || !length || !out || count < 0) return -1;
     if (threads < 1) threads = 1;
@@ -282,7 +348,7 @@ int jbh_parse_batch(const uint8_t *const *data, const uint64_t *length, int coun
         for (;;) {
             int i = next.fetch_add(1);
             if (i >= count) break;
-            if (jbh_parse(data[i], length[i], &out[i]) != JB_OK) failed.fetch_add(1);
+            if (parse_impl(tables, tables_length, data[i], length[i], &out[i]) != JB_OK) failed.fetch_add(1);
         }
     };
     std::vector<std::thread> pool;

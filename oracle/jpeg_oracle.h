@@ -87,6 +87,10 @@ typedef struct {
 /* Decode one JPEG (SOF0/SOF1/SOF2 Huffman).  Returns JO_OK or an error code;
    img->error holds the message.  Always call jo_free(img) afterwards. */
 int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img);
+/* The same behind JpegDecoder.LoadTables(tables) (JpegDecoder.cs:313-360): an abbreviated stream whose DHT / DQT / DRI
+   segments live in a separate tables stream. */
+int jo_decode_with_tables(const uint8_t *tables, size_t tables_len, const uint8_t *data, size_t len, int flags,
+                          jo_image *img);
 void jo_free(jo_image *img);
 
 /* Stand-alone block math (used by unit tests of the kernels). */

@@ -1034,11 +1034,10 @@ static int parse_sos(dec_ctx *c, const uint8_t *b, size_t n, jo_scan_info *s)
 
 /* JpegDecoder.Identify (JpegDecoder.cs:75-146) walks the whole stream before Decode() does (apps/JpegDecode/DecodeAction.cs,
    the reference's tests): the decoder object keeps the LAST restart interval it met, and that is the value Decode() starts
-   with.  Returns it (0 without any DRI). */
-static int identify_last_dri(const uint8_t *data, size_t len)
+   with.  Returns it (`dri`, what the object held before -- 0, or LoadTables' value -- without any DRI). */
+static int identify_last_dri(const uint8_t *data, size_t len, int dri)
 {
     size_t pos = 2;
-    int dri = 0;
     while (pos < len) {
         int m = read_marker(data, len, &pos);
         if (m < 0 || m == 0xD9) break;
@@ -1052,7 +1051,41 @@ static int identify_last_dri(const uint8_t *data, size_t len)
     return dri;
 }
 
+/* JpegDecoder.LoadTables (JpegDecoder.cs:319-360): the tables stream of an abbreviated image (a TIFF file's JPEGTables).
+   SOI and RSTn are passed over, DHT / DQT (always loaded) / DRI are processed, every other segment is skipped, EOI or
+   "no further marker" ends the walk silently. */
+static int load_tables(dec_ctx *c, const uint8_t *t, size_t tlen)
+{
+    size_t pos = 0;
+    while (pos < tlen) {
+        int m = read_marker(t, tlen, &pos);
+        if (m < 0 || m == 0xD9) return JO_OK;
+        if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (pos + 2 > tlen) return fail(c, JO_ERR_INVALID_DATA, "Unexpected end of input data when reading segment length.");
+        size_t seglen = ((size_t)t[pos] << 8) | t[pos + 1];
+        if (seglen < 2 || pos + seglen > tlen) return fail(c, JO_ERR_INVALID_DATA, "Unexpected end of input data reached.");
+        const uint8_t *body = t + pos + 2;
+        size_t blen = seglen - 2;
+        pos += seglen;
+        int rc = JO_OK;
+        if (m == 0xC4) rc = parse_dht(c, body, blen);
+        else if (m == 0xDB) rc = parse_dqt(c, body, blen);
+        else if (m == 0xDD) {
+            if (blen < 2) rc = fail(c, JO_ERR_INVALID_DATA, "Unexpected end of input data when reading segment content.");
+            else c->restart_interval = (body[0] << 8) | body[1];
+        }
+        if (rc) return rc;
+    }
+    return JO_OK;
+}
+
 int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
+{
+    return jo_decode_with_tables(NULL, 0, data, len, flags, img);
+}
+
+/* LoadTables(tables); SetInput(data); Identify(); Decode() */
+int jo_decode_with_tables(const uint8_t *tables, size_t tables_len, const uint8_t *data, size_t len, int flags, jo_image *img)
 {
     dec_ctx *c = calloc(1, sizeof(dec_ctx));
     memset(img, 0, sizeof(*img));
@@ -1062,13 +1095,17 @@ int jo_decode(const uint8_t *data, size_t len, int flags, jo_image *img)
     c->len = len;
     size_t pos = 0;
     int rc = JO_OK;
+    if (tables && tables_len) {
+        rc = load_tables(c, tables, tables_len);
+        if (rc) goto done;
+    }
     if (len < 2 || data[0] != 0xFF || data[1] != 0xD8) {
         rc = fail(c, JO_ERR_INVALID_DATA, "Marker StartOfImage not found.");
         goto done;
     }
     pos = 2;
     int eoi = 0;
-    c->restart_interval = identify_last_dri(data, len);
+    c->restart_interval = identify_last_dri(data, len, c->restart_interval);
     while (!eoi && pos < len) {
         int m = read_marker(data, len, &pos);
         if (m < 0) {

@@ -93,6 +93,8 @@ def lib():
         _lib = C.CDLL(build())
         _lib.jo_decode.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Image)]
         _lib.jo_decode.restype = C.c_int
+        _lib.jo_decode_with_tables.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Image)]
+        _lib.jo_decode_with_tables.restype = C.c_int
         _lib.jo_free.argtypes = [C.POINTER(Image)]
         _lib.jo_dequant_idct_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.jo_ycbcr_to_rgb.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
@@ -121,10 +123,15 @@ class Decoded:
     """numpy view of a jo_image (copies, so the C memory is freed immediately)."""
 
 
-def decode(data: bytes, want_rgb=True) -> Decoded:
+def decode(data: bytes, want_rgb=True, tables: bytes = None) -> Decoded:
+    """tables: what JpegDecoder.LoadTables is given before the (abbreviated) stream"""
     buf = np.frombuffer(data, dtype=np.uint8)
     img = Image()
-    rc = lib().jo_decode(buf.ctypes.data, buf.size, 7 if want_rgb else 3, C.byref(img))
+    if tables:
+        tbuf = np.frombuffer(tables, dtype=np.uint8)
+        rc = lib().jo_decode_with_tables(tbuf.ctypes.data, tbuf.size, buf.ctypes.data, buf.size, 7 if want_rgb else 3, C.byref(img))
+    else:
+        rc = lib().jo_decode(buf.ctypes.data, buf.size, 7 if want_rgb else 3, C.byref(img))
     try:
         if rc != 0:
             raise OracleError(rc, img.error.decode())

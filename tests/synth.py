@@ -453,3 +453,24 @@ def reorder_progressive_scans(blob, order):
         else:
             head.append(seg)
     return b"".join(head) + b"".join(chunks[k] for k in order) + b"".join(cur) + b"\xff\xd9"
+
+
+def split_tables(blob, move=(0xC4, 0xDB), tables_dri=None):
+    """blob: a JPEG whose table segments all precede the first SOS.  Returns (tables, abbreviated): the DHT / DQT (and,
+    with 0xDD in `move`, DRI) segments as a stand-alone tables stream SOI .. EOI -- what a TIFF writer puts into the
+    JPEGTables field and a caller hands to JpegDecoder.LoadTables -- and the image without them.  tables_dri: a DRI
+    segment of that value added to the tables stream."""
+    i, tables, rest = 2, [b"\xff\xd8"], [b"\xff\xd8"]
+    while i < len(blob):
+        assert blob[i] == 0xFF
+        m = blob[i + 1]
+        ln = int.from_bytes(blob[i + 2:i + 4], "big")
+        seg = blob[i:i + 2 + ln]
+        if m == 0xDA:
+            rest.append(blob[i:])
+            break
+        (tables if m in move else rest).append(seg)
+        i += 2 + ln
+    if tables_dri is not None:
+        tables.append(b"\xff\xdd\x00\x04" + int(tables_dri).to_bytes(2, "big"))
+    return b"".join(tables) + b"\xff\xd9", b"".join(rest)

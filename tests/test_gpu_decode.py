@@ -782,3 +782,56 @@ def test_truncated_entropy_data_is_an_error(kw):
     dec.SetOutputWriter(J.CudaOutputWriter(np.zeros((240, 320, 3), np.uint8)))
     with pytest.raises((J.InvalidDataException, J.InvalidOperationException)):
         dec.Decode()
+
+
+# ---- abbreviated streams behind JpegDecoder.LoadTables (JpegDecoder.cs:313-360): the strips of a TIFF file ----------
+@pytest.mark.parametrize("kw", [dict(restart_rows=1), dict(), dict(subsampling="4:4:4", restart_blocks=5), dict(progressive=True)], ids=str)
+def test_abbreviated_stream_behind_load_tables(kw):
+    blob = synth.synth_jpeg(40, 200, 136, **kw)
+    tables, rest = synth.split_tables(blob, move=(0xC4, 0xDB, 0xDD))
+    want = O.decode(rest, tables=tables)
+    assert np.array_equal(want.rgb, O.decode(blob).rgb)  # the oracle's two walks agree with each other
+    dec = J.JpegDecoder()
+    dec.LoadTables(tables)
+    dec.SetInput(rest)
+    dec.Identify()
+    planes = np.zeros((3, dec.Height, dec.Width), dtype=np.int16)
+    dec.SetOutputWriter(J.CudaOutputWriter(planes, J.JB_OUT_PLANAR_I16))
+    dec.Decode()
+    assert np.array_equal(planes, want.planes)
+    rgb = np.zeros((dec.Height, dec.Width, 3), dtype=np.uint8)
+    dec.SetOutputWriter(J.CudaOutputWriter(rgb, J.JB_OUT_RGB24))
+    dec.Decode()
+    assert np.array_equal(rgb, want.rgb)
+    # without the tables the same stream is refused like the reference refuses it
+    bare = J.JpegDecoder()
+    bare.SetInput(rest)
+    if not kw.get("progressive"):
+        with pytest.raises(J.InvalidDataException):
+            bare.Identify()
+
+
+def test_batch_of_strips_sharing_one_tables_stream():
+    """Strips of one TIFF image: equal tables (libjpeg's standard ones), one JPEGTables stream, many abbreviated
+    streams -- through the batch facade and the host-to-host pipeline."""
+    blobs = [synth.synth_jpeg(50 + i, 256, 64 + 16 * (i % 2), restart_rows=i % 2) for i in range(6)]
+    split = [synth.split_tables(b) for b in blobs]
+    tables = split[0][0]
+    assert all(t == tables for t, _ in split)  # same quality, standard Huffman tables
+    strips = [r for _, r in split]
+    with J.JpegBatchDecoder(strips, J.JB_OUT_RGB24, device_output=True, tables=tables) as b:
+        b.run()
+        assert b.status() == [0] * len(strips)
+        for i, blob in enumerate(blobs):
+            assert np.array_equal(b.read_output(i), O.decode(strips[i], tables=tables).rgb)
+            assert np.array_equal(b.read_output(i), O.decode(blob).rgb)
+    with pytest.raises(J.InvalidDataException):
+        J.JpegBatchDecoder(strips, J.JB_OUT_RGB24, device_output=True)
+    ctx = J.Context.default()
+    out = ctx.pinned_array(2 * 1024 * 1024)
+    out[:] = 0
+    offs = J.JpegPipelinedBatchDecoder([ctx], chunk=4, parse_threads=2).decode(strips, out, tables=tables)
+    for i, blob in enumerate(blobs):
+        o = O.decode(blob)
+        assert np.array_equal(out[offs[i]:offs[i] + o.rgb.size].reshape(o.rgb.shape), o.rgb)
+    ctx.pinned_free(out.ctypes.data)

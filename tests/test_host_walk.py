@@ -169,3 +169,79 @@ def test_scan_header_checks_follow_the_reference():
         out = (C.c_int32 * (10 * p.desc.scan_count))()
         k = J._native.cuda.jb_plan_scans(C.byref(p.desc), out, p.desc.scan_count)
         assert (k == p.desc.scan_count) if ok else (k == J._native.JB_ERR_INVALID_DATA), k
+
+
+# ---- abbreviated streams behind JpegDecoder.LoadTables (JpegDecoder.cs:313-360) -------------------------------------
+def _same_descriptor(a, b, offset_shift):
+    assert (a.width, a.height, a.component_count, a.precision, a.sof, a.scan_count) == (b.width, b.height, b.component_count, b.precision, b.sof, b.scan_count)
+    for c in range(a.component_count):
+        assert (a.h[c], a.v[c]) == (b.h[c], b.v[c]) and list(a.quant[c]) == list(b.quant[c])
+    for i in range(a.scan_count):
+        s, t = a.scans[i], b.scans[i]
+        assert (s.ss, s.se, s.ah, s.al, s.restart_interval, s.entropy_length, s.component_count) == (t.ss, t.se, t.ah, t.al, t.restart_interval, t.entropy_length, t.component_count)
+        assert s.entropy_offset + offset_shift == t.entropy_offset
+        for k in range(s.component_count):
+            for x, y in ((s.dc_table[k], t.dc_table[k]), (s.ac_table[k], t.ac_table[k])):
+                assert (x < 0) == (y < 0)
+                if x >= 0:
+                    u, v = a.tables[x], b.tables[y]
+                    assert (u.table_class, u.identifier, list(u.bits), u.value_count, list(u.values)[:u.value_count]) == \
+                           (v.table_class, v.identifier, list(v.bits), v.value_count, list(v.values)[:v.value_count])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(restart_rows=1), dict(subsampling="4:4:4"), dict(progressive=True)], ids=str)
+def test_abbreviated_stream_behind_load_tables_gives_the_descriptor_of_the_whole_stream(kw):
+    blob = synth.synth_jpeg(5, 72, 40, **kw)
+    progressive = kw.get("progressive", False)
+    # (a progressive file of libjpeg carries further DHT segments between its scans: only the ones in front move)
+    tables, rest = synth.split_tables(blob, move=(0xC4, 0xDB, 0xDD))
+    assert len(tables) > 100 and len(rest) < len(blob)
+    with pytest.raises(J.InvalidDataException):  # the abbreviated stream alone refers to tables nobody defined
+        if progressive:
+            raise J.InvalidDataException("n/a")
+        J.Parsed(rest)
+    whole, abbr = J.Parsed(blob), J.Parsed(rest, tables)
+    _same_descriptor(abbr.desc, whole.desc, len(blob) - len(rest))
+    # the oracle walks the two streams the same way
+    o = O.decode(rest, want_rgb=False, tables=tables)
+    w = O.decode(blob, want_rgb=False)
+    assert all((a == b).all() for a, b in zip(o.coef, w.coef)) and (o.planes == w.planes).all()
+    assert o.restart_interval == w.restart_interval
+
+
+def test_load_tables_call_sequence_and_errors():
+    blob = synth.synth_jpeg(6, 48, 32, restart_rows=1)
+    dht_dqt, rest = synth.split_tables(blob, move=(0xC4, 0xDB, 0xDD))
+    dqt_only, _ = synth.split_tables(blob, move=(0xDB,))
+    dht_only, _ = synth.split_tables(blob, move=(0xC4,))
+    dri_only = b"\xff\xd8\xff\xdd\x00\x04" + (3).to_bytes(2, "big")  # no EOI: the walk ends with the data
+    dec = J.JpegDecoder()
+    dec.SetInput(rest)
+    with pytest.raises(J.InvalidDataException):
+        dec.Identify()  # "Quantization table of component is not defined."
+    # two calls add up (the first stream's EOI ends ITS walk only), a DRI loaded this way stays in force when the
+    # stream brings none -- and the value Identify() leaves is the stream's own when it has one
+    dec.LoadTables(dqt_only)
+    dec.LoadTables(dht_only)
+    dec.Identify()
+    assert dec._parsed.desc.scans[0].restart_interval == 0  # the DRI segment went away with the tables
+    dec.LoadTables(dri_only)
+    dec.Identify()
+    assert dec._parsed.desc.scans[0].restart_interval == 3 == J.Parsed(blob).desc.scans[0].restart_interval
+    o = O.decode(rest, want_rgb=False, tables=dqt_only[:-2] + dht_only[:-2] + dri_only)
+    assert o.restart_interval == 3
+    assert (dec.Width, dec.Height) == (48, 32)
+    dec.ResetTables()
+    with pytest.raises(J.InvalidDataException):
+        dec.Identify()
+    # what LoadTables itself raises: a DHT segment cut short, a segment running past the end of the data
+    bad = bytearray(dht_only)
+    bad[4:6] = (5).to_bytes(2, "big")
+    with pytest.raises(J.InvalidDataException, match="Failed to parse Huffman table"):
+        dec.LoadTables(bytes(bad))
+    with pytest.raises(J.InvalidDataException, match="Unexpected end of input data"):
+        dec.LoadTables(dht_only[:40])
+    with pytest.raises(O.OracleError, match="Failed to parse Huffman table"):
+        O.decode(rest, want_rgb=False, tables=bytes(bad))
+    dec.LoadTables(b"")            # nothing to walk
+    dec.LoadTables(b"\x00\x01\x02")  # no marker at all: ends silently (JpegDecoder.cs:326-329)
