@@ -8,7 +8,7 @@ from . import _native
 from ._native import (JB_IN_COEFFICIENTS, JB_IN_GRAY8, JB_IN_RGB24, JB_IN_YCBCR888, JB_OUT_COEFFICIENTS, JB_OUT_PLANAR_I16, JB_OUT_RGB24, JB_OUT_RGBA32,
                       JB_OUT_YCBCR888)
 from .api import (ArgumentException, Context, CudaInputReader, CudaOutputWriter, CudaRuntimeError,
-                  InvalidDataException, InvalidOperationException, JpegBatchDecoder, JpegBatchEncoder, JpegPipelinedBatchDecoder,
+                  InvalidDataException, InvalidOperationException, JpegBatchDecoder, JpegBatchEncoder, JpegBatchOptimizer, JpegPipelinedBatchDecoder,
                   JpegBlockInputReader, JpegBlockOutputWriter, JpegDecoder, JpegEncoder, JpegOptimizer, JpegQuantizationTable,
                   JpegStandardQuantizationTable, NotSupportedException, Parsed, decode_coefficients, encode_rgb)
 

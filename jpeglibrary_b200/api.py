@@ -997,6 +997,129 @@ class JpegBatchEncoder:
 # ==========================================================================================
 # Optimizer mirror (src/JpegLibrary/JpegOptimizer.cs): lossless transcode with optimised Huffman tables
 # ==========================================================================================
+def _transcode_plan(d):
+    """What JpegOptimizer.Scan checks of a parsed stream (JpegOptimizer.cs:72-154); returns (blocks of the store, its scan)."""
+    if d.sof > 1:
+        raise InvalidDataException("Progressive JPEG is not supported currently.")
+    if d.scan_count < 1:
+        raise InvalidDataException("No image data is read.")
+    sc = d.scans[0]
+    named = [sc.component_index[i] for i in range(sc.component_count)]
+    if d.scan_count != 1 or sorted(named) != list(range(d.component_count)):
+        raise NotSupportedException("only frames coded as one interleaved scan over every component are transcoded on the GPU path")
+    hmax = max(d.h[i] for i in range(d.component_count))
+    vmax = max(d.v[i] for i in range(d.component_count))
+    nblk = ((d.width + 8 * hmax - 1) // (8 * hmax)) * ((d.height + 8 * vmax - 1) // (8 * vmax)) * \
+        sum(d.h[i] * d.v[i] for i in range(d.component_count))
+    return nblk, sc
+
+
+def _transcode_desc(e, d, sc, coef_dev):
+    """Fill the jb_encode_desc that re-packs the device coefficient store of one decoded frame (JB_IN_COEFFICIENTS):
+    components in SCAN order (that is the store's block order).  Returns the (class, identifier) pairs of the tables in
+    GetOrCreateTableBuilder order (JpegOptimizer.cs:394-395)."""
+    e.pixels, e.on_device, e.format = coef_dev, 1, N.JB_IN_COEFFICIENTS
+    e.width, e.height, e.component_count = d.width, d.height, sc.component_count
+    e.restart_interval = sc.restart_interval
+    order = []
+    for i in range(sc.component_count):
+        c = sc.component_index[i]
+        e.h[i], e.v[i] = d.h[c], d.v[c]
+        td = d.tables[sc.dc_table[i]].identifier
+        ta = d.tables[sc.ac_table[i]].identifier
+        e.td[i], e.ta[i] = td, ta
+        for key in ((0, td), (1, ta)):
+            if key not in order:
+                order.append(key)
+    return order
+
+
+def _optimal_tables_from_histograms(ctx, h, image, hist, order):
+    """MostOptimalCoding (JpegOptimizer.cs:39): builder.Build(optimal: true) over the scan's symbol statistics"""
+    for cls, ident in order:
+        spec = N.HuffSpec()
+        if N.cuda.jb_build_huffman_table_optimal(hist[cls * 4 + ident].ctypes.data, cls, ident, C.byref(spec)):
+            raise InvalidOperationException("No symbol is recorded.")
+        ctx.check(N.cuda.jb_encode_batch_set_table(h, image, C.byref(spec)))
+
+
+def _read_transcoded(ctx, h, image, order):
+    """(scan bytes, tables in `order`) of one image of a packed encode batch"""
+    n = C.c_uint64()
+    N.cuda.jb_encode_batch_scan_length(h, image, C.byref(n))
+    scan = np.empty(n.value, dtype=np.uint8)
+    ctx.check(N.cuda.jb_encode_batch_read_scan(h, image, scan.ctypes.data, scan.size))
+    specs = []
+    for cls, ident in order:
+        s = N.HuffSpec()
+        ctx.check(N.cuda.jb_encode_batch_get_table(h, image, cls, ident, C.byref(s)))
+        specs.append(s)
+    return scan, specs
+
+
+def _rewrite_stream(data, sc, scan, specs, strip):
+    """JpegOptimizer.Optimize (:546-647): SOI / APP0 / SOF copied, the first DHT / DQT replaced by all tables, SOS copied
+    with the new scan data, other segments dropped when `strip` (the DRI segment of a frame with restart intervals is
+    always kept: quirk Q6, see JpegOptimizer below)."""
+    data = bytes(data)
+    # quantisation tables in definition order, latest definition wins (ProcessDefineQuantizationTable)
+    qts = {}
+    pos = 2
+    segs = []  # (marker, payload_start, payload_end)
+    while pos + 2 <= len(data):
+        if data[pos] != 0xFF:
+            pos += 1
+            continue
+        m = data[pos + 1]
+        if m == 0xFF:
+            pos += 1
+            continue
+        if m == 0xD9:
+            segs.append((m, pos + 2, pos + 2))
+            break
+        if m == 0x00 or 0xD0 <= m <= 0xD7 or m == 0xD8:
+            pos += 2
+            continue
+        if pos + 4 > len(data):
+            raise InvalidDataException("Unexpected end of input data when reading segment length.")
+        ln = int.from_bytes(data[pos + 2:pos + 4], "big")
+        segs.append((m, pos + 4, pos + 2 + ln))
+        if m == 0xDB:
+            q = data[pos + 4:pos + 2 + ln]
+            i = 0
+            while i < len(q):
+                size = 129 if q[i] >> 4 else 65
+                qts[q[i] & 15] = q[i:i + size]
+                i += size
+        pos += 2 + ln
+        if m == 0xDA:
+            pos = sc.entropy_offset + sc.entropy_length
+    out = bytearray(b"\xff\xd8")
+    dht_written = dqt_written = False
+    for m, a, b in segs:
+        payload = data[a:b]
+        if m in (0xE0, 0xC0, 0xC1):
+            out += _marker_segment(m, payload)
+        elif m == 0xC4:
+            if not dht_written:
+                body = bytearray()
+                for s in specs:
+                    body += bytes([(s.table_class << 4) | (s.identifier & 15)]) + bytes(s.bits) + bytes(s.values[:s.value_count])
+                out += _marker_segment(0xC4, bytes(body))
+                dht_written = True
+        elif m == 0xDB:
+            if not dqt_written:
+                out += _marker_segment(0xDB, b"".join(qts[k] for k in qts))
+                dqt_written = True
+        elif m == 0xDA:
+            out += _marker_segment(0xDA, payload) + scan.tobytes()
+        elif m == 0xD9:
+            out += b"\xff\xd9"
+        elif not strip or (m == 0xDD and sc.restart_interval != 0):
+            out += _marker_segment(m, payload)   # (DRI is kept with strip too: see the class comment, quirk Q6)
+    return out
+
+
 class JpegOptimizer:
     """Scan(): entropy-decode on the GPU (K0/K1), histogram the symbols (K3b), build optimised tables (K3c).
     Optimize(strip): re-pack the same coefficients with the new tables (K4) and rewrite the stream like
@@ -1047,37 +1170,13 @@ class JpegOptimizer:
         self._close()
         p = Parsed(self._input)
         d = p.desc
-        if d.sof > 1:
-            raise InvalidDataException("Progressive JPEG is not supported currently.")
-        if d.scan_count < 1:
-            raise InvalidDataException("No image data is read.")
-        sc = d.scans[0]
-        named = [sc.component_index[i] for i in range(sc.component_count)]
-        if d.scan_count != 1 or sorted(named) != list(range(d.component_count)):
-            raise NotSupportedException("only frames coded as one interleaved scan over every component are transcoded on the GPU path")
-        hmax = max(d.h[i] for i in range(d.component_count))
-        vmax = max(d.v[i] for i in range(d.component_count))
-        nblk = ((d.width + 8 * hmax - 1) // (8 * hmax)) * ((d.height + 8 * vmax - 1) // (8 * vmax)) * \
-            sum(d.h[i] * d.v[i] for i in range(d.component_count))
+        nblk, sc = _transcode_plan(d)
         self._nblk = nblk
         self._coef_dev = ctx.device_alloc(nblk * 128)
         out = CudaOutputWriter(self._coef_dev, N.JB_OUT_COEFFICIENTS, on_device=True, capacity=nblk * 128)._output_desc()
         ctx.check(N.cuda.jb_decode(ctx.handle, C.byref(d), C.byref(out), 1, None))
-        # transcode descriptor: components in SCAN order (that is the store's block order)
         e = N.EncodeDesc()
-        e.pixels, e.on_device, e.format = self._coef_dev, 1, N.JB_IN_COEFFICIENTS
-        e.width, e.height, e.component_count = d.width, d.height, sc.component_count
-        e.restart_interval = sc.restart_interval
-        self._table_order = []
-        for i in range(sc.component_count):
-            c = sc.component_index[i]
-            e.h[i], e.v[i] = d.h[c], d.v[c]
-            td = d.tables[sc.dc_table[i]].identifier
-            ta = d.tables[sc.ac_table[i]].identifier
-            e.td[i], e.ta[i] = td, ta
-            for key in ((0, td), (1, ta)):   # GetOrCreateTableBuilder order (:394-395)
-                if key not in self._table_order:
-                    self._table_order.append(key)
+        self._table_order = _transcode_desc(e, d, sc, self._coef_dev)
         h = C.c_void_p()
         ctx.check(N.cuda.jb_encode_batch_create(ctx.handle, C.byref(e), 1, C.byref(h)))
         self._batch = h
@@ -1085,11 +1184,7 @@ class JpegOptimizer:
         if self.MostOptimalCoding:  # JpegOptimizer.cs:39: builder.Build(optimal: true) over the scan's symbol statistics
             hist = np.zeros((8, 256), dtype=np.uint32)
             ctx.check(N.cuda.jb_encode_batch_histograms(h, hist.ctypes.data, 1))
-            for cls, ident in self._table_order:
-                spec = N.HuffSpec()
-                if N.cuda.jb_build_huffman_table_optimal(hist[cls * 4 + ident].ctypes.data, cls, ident, C.byref(spec)):
-                    raise InvalidOperationException("No symbol is recorded.")
-                ctx.check(N.cuda.jb_encode_batch_set_table(h, 0, C.byref(spec)))
+            _optimal_tables_from_histograms(ctx, h, 0, hist, self._table_order)
         else:
             ctx.check(N.cuda.jb_encode_batch_build_tables(h))
         self._parsed = p
@@ -1103,74 +1198,126 @@ class JpegOptimizer:
         h = self._batch
         ctx.check(N.cuda.jb_encode_batch_pack(h))
         ctx.check(N.cuda.jb_encode_batch_finish(h))
-        n = C.c_uint64()
-        N.cuda.jb_encode_batch_scan_length(h, 0, C.byref(n))
-        scan = np.empty(n.value, dtype=np.uint8)
-        ctx.check(N.cuda.jb_encode_batch_read_scan(h, 0, scan.ctypes.data, scan.size))
-        specs = []
-        for cls, ident in self._table_order:
-            s = N.HuffSpec()
-            ctx.check(N.cuda.jb_encode_batch_get_table(h, 0, cls, ident, C.byref(s)))
-            specs.append(s)
+        scan, specs = _read_transcoded(ctx, h, 0, self._table_order)
         self.last_tables = specs
-        data = bytes(self._input)
-        # quantisation tables in definition order, latest definition wins (ProcessDefineQuantizationTable)
-        qts = {}
-        pos = 2
-        segs = []  # (marker, payload_start, payload_end)
-        while pos + 2 <= len(data):
-            if data[pos] != 0xFF:
-                pos += 1
-                continue
-            m = data[pos + 1]
-            if m == 0xFF:
-                pos += 1
-                continue
-            if m == 0xD9:
-                segs.append((m, pos + 2, pos + 2))
-                break
-            if m == 0x00 or 0xD0 <= m <= 0xD7 or m == 0xD8:
-                pos += 2
-                continue
-            if pos + 4 > len(data):
-                raise InvalidDataException("Unexpected end of input data when reading segment length.")
-            ln = int.from_bytes(data[pos + 2:pos + 4], "big")
-            segs.append((m, pos + 4, pos + 2 + ln))
-            if m == 0xDB:
-                q = data[pos + 4:pos + 2 + ln]
-                i = 0
-                while i < len(q):
-                    size = 129 if q[i] >> 4 else 65
-                    qts[q[i] & 15] = q[i:i + size]
-                    i += size
-            pos += 2 + ln
-            if m == 0xDA:
-                sc = self._parsed.desc.scans[0]
-                pos = sc.entropy_offset + sc.entropy_length
-        out = bytearray(b"\xff\xd8")
-        dht_written = dqt_written = False
-        for m, a, b in segs:
-            payload = data[a:b]
-            if m in (0xE0, 0xC0, 0xC1):
-                out += _marker_segment(m, payload)
-            elif m == 0xC4:
-                if not dht_written:
-                    body = bytearray()
-                    for s in specs:
-                        body += bytes([(s.table_class << 4) | (s.identifier & 15)]) + bytes(s.bits) + bytes(s.values[:s.value_count])
-                    out += _marker_segment(0xC4, bytes(body))
-                    dht_written = True
-            elif m == 0xDB:
-                if not dqt_written:
-                    out += _marker_segment(0xDB, b"".join(qts[k] for k in qts))
-                    dqt_written = True
-            elif m == 0xDA:
-                out += _marker_segment(0xDA, payload) + scan.tobytes()
-            elif m == 0xD9:
-                out += b"\xff\xd9"
-            elif not strip or (m == 0xDD and self._parsed.desc.scans[0].restart_interval != 0):
-                out += _marker_segment(m, payload)   # (DRI is kept with strip too: see the class comment, quirk Q6)
+        out = _rewrite_stream(self._input, self._parsed.desc.scans[0], scan, specs, strip)
         if hasattr(self._output, "write"):
             self._output.write(bytes(out))
         else:
             self._output += out
+
+
+class JpegBatchOptimizer:
+    """JpegOptimizer (Scan + Optimize) over a batch of baseline / extended streams in one pass on the device: K0/K1 decode
+    every stream into zig-zag coefficient stores that stay in device memory (JB_OUT_COEFFICIENTS), K3b histograms the
+    symbols, K3c builds the optimised tables (or, with most_optimal, the host builds package-merge tables from the
+    histograms), K4 re-packs -- the same C-ABI calls as JpegOptimizer, with `count` images per call.  Everything between
+    upload and finish is enqueued on the context's stream without a host synchronisation."""
+
+    def __init__(self, blobs, context=None, most_optimal=False, parse_threads=8):
+        self.ctx = ctx = context or Context.default()
+        self.count = n = len(blobs)
+        self.most_optimal = most_optimal
+        self._dec = self._enc = self._coef_dev = None
+        self._bufs = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for b in blobs]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in self._bufs])
+        lens = (C.c_uint64 * n)(*[b.size for b in self._bufs])
+        self._parsed = (C.c_void_p * n)()
+        failed = N.host.jbh_parse_batch(ptrs, lens, n, parse_threads, self._parsed)
+        if failed:
+            self.close()
+            raise InvalidDataException(f"{failed} of {n} streams failed the marker walk")
+        self.descs = (N.ImageDesc * n)()
+        N.host.jbh_collect_descs(self._parsed, n, self.descs)
+        try:
+            plans = [_transcode_plan(self.descs[i]) for i in range(n)]
+            offs, total = [], 0
+            for nblk, _sc in plans:
+                offs.append(total)
+                total += (nblk * 128 + 255) // 256 * 256
+            self._coef_dev = ctx.device_alloc(max(total, 256))
+            outs = (N.OutputDesc * n)()
+            self._edescs = (N.EncodeDesc * n)()
+            self._orders = []
+            for i, (nblk, sc) in enumerate(plans):
+                o = outs[i]
+                o.dst, o.pitch, o.capacity, o.format, o.on_device = self._coef_dev + offs[i], 0, nblk * 128, N.JB_OUT_COEFFICIENTS, 1
+                self._orders.append(_transcode_desc(self._edescs[i], self.descs[i], sc, self._coef_dev + offs[i]))
+            h = C.c_void_p()
+            ctx.check(N.cuda.jb_decode_batch_create(ctx.handle, self.descs, outs, n, C.byref(h)))
+            self._dec = h
+            h = C.c_void_p()
+            ctx.check(N.cuda.jb_encode_batch_create(ctx.handle, self._edescs, n, C.byref(h)))
+            self._enc = h
+        except Exception:
+            self.close()
+            raise
+        self._uploaded = False
+
+    def upload(self):
+        self.ctx.check(N.cuda.jb_decode_batch_upload(self._dec))
+        self._uploaded = True
+
+    def launch(self):
+        """Scan() and the device half of Optimize() for every stream"""
+        ctx = self.ctx
+        if not self._uploaded:
+            self.upload()
+        ctx.check(N.cuda.jb_decode_batch_launch(self._dec))
+        # a stream the decoder refuses raises what JpegOptimizer.Scan would have raised for it; the coefficient stores
+        # reach their destinations here (jb_decode_batch_finish delivers JB_OUT_COEFFICIENTS results)
+        ctx.check(N.cuda.jb_decode_batch_finish(self._dec))
+        ctx.check(N.cuda.jb_encode_batch_transform(self._enc))  # takes the stores over (device to device) + histograms
+        if self.most_optimal:
+            hist = np.zeros((self.count, 8, 256), dtype=np.uint32)
+            ctx.check(N.cuda.jb_encode_batch_histograms(self._enc, hist.ctypes.data, self.count))  # synchronises
+            for i in range(self.count):
+                _optimal_tables_from_histograms(ctx, self._enc, i, hist[i], self._orders[i])
+        else:
+            ctx.check(N.cuda.jb_encode_batch_build_tables(self._enc))
+        ctx.check(N.cuda.jb_encode_batch_pack(self._enc))
+
+    def finish(self):
+        self.ctx.check(N.cuda.jb_encode_batch_finish(self._enc))
+
+    def launch_count(self):
+        return N.cuda.jb_decode_batch_launch_count(self._dec) + N.cuda.jb_encode_batch_launch_count(self._enc)
+
+    def scan_length(self, i):
+        n = C.c_uint64()
+        N.cuda.jb_encode_batch_scan_length(self._enc, i, C.byref(n))
+        return n.value
+
+    def stream(self, i, strip=True):
+        """The optimised file of stream i (JpegOptimizer.Optimize, :546-647)"""
+        scan, specs = _read_transcoded(self.ctx, self._enc, i, self._orders[i])
+        return bytes(_rewrite_stream(self._bufs[i].tobytes(), self.descs[i].scans[0], scan, specs, strip))
+
+    def run(self, strip=True):
+        self.launch()
+        self.finish()
+        return [self.stream(i, strip) for i in range(self.count)]
+
+    def close(self):
+        if self._enc is not None:
+            N.cuda.jb_encode_batch_destroy(self._enc)
+            self._enc = None
+        if self._dec is not None:
+            N.cuda.jb_decode_batch_destroy(self._dec)
+            self._dec = None
+        if self._coef_dev is not None:
+            self.ctx.device_free(self._coef_dev)
+            self._coef_dev = None
+        parsed = getattr(self, "_parsed", None)
+        if parsed is not None:
+            for i in range(self.count):
+                if parsed[i]:
+                    N.host.jbh_free(parsed[i])
+                    parsed[i] = None
+            self._parsed = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

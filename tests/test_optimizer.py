@@ -136,3 +136,54 @@ def test_optimize_keeps_restart_intervals(kw, strip):
     opt2.SetOutput(out2)
     opt2.Optimize(strip)
     assert bytes(out2) == out
+
+
+def _optimize_one(src, strip=True, most_optimal=False):
+    opt = J.JpegOptimizer()
+    opt.MostOptimalCoding = most_optimal
+    opt.SetInput(src)
+    opt.Scan()
+    out = bytearray()
+    opt.SetOutput(out)
+    opt.Optimize(strip)
+    return bytes(out)
+
+
+@pytest.mark.parametrize("most_optimal", [False, True], ids=["standard", "package-merge"])
+def test_batch_optimizer_equals_one_optimizer_per_stream(most_optimal):
+    """JpegBatchOptimizer: every stream of a mixed batch (sizes, sampling, grey, restart intervals, a real photo) comes
+    out byte for byte as JpegOptimizer writes it alone, and decodes to the coefficients it went in with."""
+    srcs = [synth.synth_jpeg(60, 320, 200, subsampling="4:2:0"),
+            synth.synth_jpeg(61, 200, 136, subsampling="4:4:4", quality=93),
+            synth.synth_jpeg(62, 256, 144, subsampling="4:2:0", restart_rows=1),
+            synth.synth_jpeg(63, 96, 64, gray=True),
+            synth.synth_jpeg(64, 200, 120, subsampling="4:2:2", restart_blocks=7),
+            golden_bytes("lake.jpg")]
+    with J.JpegBatchOptimizer(srcs, most_optimal=most_optimal) as b:
+        outs = b.run()
+        assert b.launch_count() > 0
+        again = b.run(strip=False)  # the batch object can be re-run
+    for i, (src, out) in enumerate(zip(srcs, outs)):
+        assert out == _optimize_one(src, True, most_optimal), f"stream {i}"
+        assert again[i] == _optimize_one(src, False, most_optimal), f"stream {i} (strip=False)"
+        assert len(out) < len(src)
+        a, c = O.decode(src, want_rgb=False), O.decode(out, want_rgb=False)
+        assert all(np.array_equal(x, y) for x, y in zip(a.coef, c.coef))
+
+
+def test_batch_optimizer_errors():
+    good = synth.synth_jpeg(65, 128, 96, restart_rows=1)
+    with pytest.raises(J.InvalidDataException, match="Progressive"):
+        J.JpegBatchOptimizer([good, synth.synth_jpeg(66, 64, 64, progressive=True)])
+    with pytest.raises(J.InvalidDataException):
+        J.JpegBatchOptimizer([good, b"\x00\x01\x02"])
+    # a damaged scan: the decoder's verdict is what Scan() raises
+    p0, p1 = good.index(b"\xff\xd0"), good.index(b"\xff\xd1")
+    bad = good[:p0 + 2] + good[p1:]  # the second restart interval is empty: "Invalid Huffman code encountered."
+    with pytest.raises(O.OracleError):
+        O.decode(bad)
+    with J.JpegBatchOptimizer([good, bad]) as b:
+        with pytest.raises(J.InvalidDataException):
+            b.run()
+    with pytest.raises(J.InvalidDataException):
+        _optimize_one(bad)
