@@ -20,6 +20,9 @@
 #include "k_idct_color.cuh"
 
 #define JB_MAX_COMPONENTS_DEV 4
+#ifndef JB_K1D_PREFETCH
+#define JB_K1D_PREFETCH 8 // steps of the reconstruction wavefront whose inputs are loaded at once (1: a load per step)
+#endif
 
 __global__ void __launch_bounds__(32)
 jb_k1d_lossless_entropy(const JbDevImage *__restrict__ images, const JbDevScan *__restrict__ scans,
@@ -145,28 +148,42 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const JbDevScan *
         int16_t *line = plane + (size_t)cy * w;
         const int row = cy / v, y = cy - row * v;
         int ra = 0, rb = 0, rc = 0, out = 0;
-        for (int t = 0; t < cols + 31; t++) {
-            int above = __shfl_up_sync(0xFFFFFFFFu, out, 1);
-            const int cx = t - lane;
-            const bool act = rowok && cx >= 0 && cx < cols;
-            if (lane == 0) above = (act && cy > 0) ? (int)__ldcg(line - w + cx) : 0; // last row of the previous band
-            rc = rb;
-            rb = above;
-            if (act) {
-                const int col = cx / h, x = cx - col * h;
-                const bool after_restart = dri > 0 && ((uint32_t)row * mpl + (uint32_t)col) % dri == 0;
-                int pred;
-                if (row == 0 || after_restart) { // :109-139
-                    if (col == 0 && x == 0) pred = initial;
-                    else pred = jb_lossless_px(predictor, ra, y == 0 ? initial : rb, y == 0 ? initial : rc);
-                } else if (col == 0) {           // :141-144
-                    pred = rb;
-                } else {                         // :145-159
-                    pred = jb_lossless_px(predictor, ra, rb, rc);
+        // The differences of the lane's row and (lane 0) the row above the band do not depend on the reconstruction: they
+        // are fetched JB_K1D_PREFETCH steps at a time, so that a step of the serial chain no longer waits for two L2 round
+        // trips (measured with one load per step: 700 ns per step, 23.6 ms for 1024 x 1024 frames whatever the batch).
+        for (int t0 = 0; t0 < cols + 31; t0 += JB_K1D_PREFETCH) {
+            int dv[JB_K1D_PREFETCH], av[JB_K1D_PREFETCH];
+#pragma unroll
+            for (int j = 0; j < JB_K1D_PREFETCH; j++) {
+                const int cx = t0 + j - lane;
+                const bool act = rowok && cx >= 0 && cx < cols;
+                dv[j] = act ? (int)line[cx] : 0;
+                av[j] = (lane == 0 && act && cy > 0) ? (int)__ldcg(line - w + cx) : 0; // last row of the previous band
+            }
+#pragma unroll
+            for (int j = 0; j < JB_K1D_PREFETCH; j++) {
+                int above = __shfl_up_sync(0xFFFFFFFFu, out, 1);
+                const int cx = t0 + j - lane;
+                const bool act = rowok && cx >= 0 && cx < cols;
+                if (lane == 0) above = av[j];
+                rc = rb;
+                rb = above;
+                if (act) {
+                    const int col = cx / h, x = cx - col * h;
+                    const bool after_restart = dri > 0 && ((uint32_t)row * mpl + (uint32_t)col) % dri == 0;
+                    int pred;
+                    if (row == 0 || after_restart) { // :109-139
+                        if (col == 0 && x == 0) pred = initial;
+                        else pred = jb_lossless_px(predictor, ra, y == 0 ? initial : rb, y == 0 ? initial : rc);
+                    } else if (col == 0) {           // :141-144
+                        pred = rb;
+                    } else {                         // :145-159
+                        pred = jb_lossless_px(predictor, ra, rb, rc);
+                    }
+                    out = (uint32_t)row * mpl + (uint32_t)col < valid ? (int16_t)(dv[j] + pred) : 0;
+                    line[cx] = (int16_t)out;
+                    ra = out;
                 }
-                out = (uint32_t)row * mpl + (uint32_t)col < valid ? (int16_t)(line[cx] + pred) : 0;
-                line[cx] = (int16_t)out;
-                ra = out;
             }
         }
         __syncwarp();
