@@ -148,9 +148,14 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const JbDevScan *
         int16_t *line = plane + (size_t)cy * w;
         const int row = cy / v, y = cy - row * v;
         int ra = 0, rb = 0, rc = 0, out = 0;
+        // position of the lane's next sample, kept incrementally (a division per step was most of a step's instructions):
+        // MCU column, sample inside the MCU, MCU number and its place inside the restart interval
+        int col = 0, x = 0;
+        uint32_t mcu = (uint32_t)row * mpl, in_interval = dri ? mcu % dri : 1u;
         // The differences of the lane's row and (lane 0) the row above the band do not depend on the reconstruction: they
         // are fetched JB_K1D_PREFETCH steps at a time, so that a step of the serial chain no longer waits for two L2 round
-        // trips (measured with one load per step: 700 ns per step, 23.6 ms for 1024 x 1024 frames whatever the batch).
+        // trips (measured on 64 frames of 1024 x 1024 x 3: one load per step 23.6 ms, eight at a time 11.6 ms, and 7.2 ms with
+        // the sample position kept incrementally; profiles/r2f_lossless_launches_*.csv).
         for (int t0 = 0; t0 < cols + 31; t0 += JB_K1D_PREFETCH) {
             int dv[JB_K1D_PREFETCH], av[JB_K1D_PREFETCH];
 #pragma unroll
@@ -169,8 +174,7 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const JbDevScan *
                 rc = rb;
                 rb = above;
                 if (act) {
-                    const int col = cx / h, x = cx - col * h;
-                    const bool after_restart = dri > 0 && ((uint32_t)row * mpl + (uint32_t)col) % dri == 0;
+                    const bool after_restart = in_interval == 0; // (dri == 0: never)
                     int pred;
                     if (row == 0 || after_restart) { // :109-139
                         if (col == 0 && x == 0) pred = initial;
@@ -180,9 +184,15 @@ jb_k1d_lossless_predict(const JbDevImage *__restrict__ images, const JbDevScan *
                     } else {                         // :145-159
                         pred = jb_lossless_px(predictor, ra, rb, rc);
                     }
-                    out = (uint32_t)row * mpl + (uint32_t)col < valid ? (int16_t)(dv[j] + pred) : 0;
+                    out = mcu < valid ? (int16_t)(dv[j] + pred) : 0;
                     line[cx] = (int16_t)out;
                     ra = out;
+                    if (++x == h) {
+                        x = 0;
+                        col++;
+                        mcu++;
+                        if (++in_interval == dri) in_interval = 0;
+                    }
                 }
             }
         }
