@@ -245,3 +245,63 @@ def test_load_tables_call_sequence_and_errors():
         O.decode(rest, want_rgb=False, tables=bytes(bad))
     dec.LoadTables(b"")            # nothing to walk
     dec.LoadTables(b"\x00\x01\x02")  # no marker at all: ends silently (JpegDecoder.cs:326-329)
+
+
+def test_damaged_tables_streams_get_the_oracles_verdict():
+    """Differential: 400 damaged tables streams (byte flips, cuts, duplicated and dropped segments) in front of one
+    abbreviated image -- the host walk (LoadTables, then Identify + the walk of Decode) and the oracle accept and refuse
+    the same ones, with the same message, and agree on the quantisation tables of what they accept."""
+    import ctypes as C
+    import numpy as np
+    from jpeglibrary_b200 import _native as N
+    rng = np.random.default_rng(77)
+    blob = synth.synth_jpeg(8, 64, 48, restart_rows=1)
+    tables, rest = synth.split_tables(blob, move=(0xC4, 0xDB, 0xDD))
+    verdicts = {"ok": 0, "load": 0, "walk": 0, "plan": 0}
+    for trial in range(400):
+        t = bytearray(tables)
+        kind = trial % 4
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                t[int(rng.integers(2, len(t)))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            t = t[:int(rng.integers(2, len(t)))]
+        elif kind == 2:
+            a = int(rng.integers(2, len(t) - 4))
+            t = t[:a] + t[a + int(rng.integers(1, 40)):]
+        else:
+            a = int(rng.integers(2, len(t) - 4))
+            t = t[:a] + bytes([0xFF, int(rng.integers(0xC0, 0x100))]) + t[a:]
+        t = bytes(t)
+        try:
+            want, werr = O.decode(rest, want_rgb=False, tables=t), None
+        except O.OracleError as e:
+            want, werr = None, str(e)
+        dec = J.JpegDecoder()
+        got, gerr, stage = None, None, "load"
+        try:
+            dec.LoadTables(t)
+            stage = "walk"
+            dec.SetInput(rest)
+            dec.Identify()
+            got = dec._parsed.desc
+            stage = "plan"  # jb_decode_batch_create's host-side planning (never touches the device): missing tables, ...
+            rc = N.cuda.jb_plan_scans(C.byref(got), None, 0)
+            if rc < 0:
+                gerr = f"planning refused the descriptor ({rc})"
+        except (J.InvalidDataException, J.InvalidOperationException) as e:
+            gerr = str(e)
+        if werr is not None and any(k in werr for k in ("Invalid Huffman code", "magnitude category", "bit stream ended", "restart marker", "end of JPEG data stream")):
+            # the tables parse but the image does not decode with them: the scan's failure is the GPU path's to report
+            assert gerr is None, (trial, werr, gerr)
+            continue
+        assert (werr is None) == (gerr is None), (trial, werr, gerr)
+        if werr is None:
+            verdicts["ok"] += 1
+            for c in range(3):
+                assert list(got.quant[c]) == list(want.qt[c]), trial
+        else:
+            if stage != "plan":
+                assert gerr.split(". ", 1)[-1].rstrip(".") in werr, (trial, werr, gerr)
+            verdicts[stage] += 1
+    assert verdicts["ok"] > 20 and verdicts["load"] > 50, verdicts
