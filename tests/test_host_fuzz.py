@@ -1,0 +1,104 @@
+"""CPU differential fuzz of the HOST side of the path: the marker walk (jpeglibrary_b200/host/jpeg_host.cpp, standing
+for JpegDecoder.Identify + the marker loop of Decode, JpegDecoder.cs:75-162, :509-617) followed by the planning that
+jb_decode_batch_create runs on the host (jb_plan_scans: never touches the device) must accept and refuse damaged
+headers like the oracle's walk does.  What only the scan decoders can find (bad codes, premature end, missing restart
+markers) is the kernels' to report and is covered by the -m gpu fuzz tests."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import jpeglibrary_b200 as J
+import oracle_ffi as O
+import synth
+from conftest import golden_bytes
+from jpeglibrary_b200 import _native as N
+from test_gpu_fuzz import mutate_header
+
+SCAN_FAILURES = ("Invalid Huffman code", "magnitude category", "bit stream ended", "restart marker", "end of JPEG data stream")
+
+
+def _bases():
+    rgb = synth.synth_rgb(40, 160, 112)
+    return {
+        "restart": synth.encode_jpeg(rgb, quality=85, subsampling="4:2:0", restart_blocks=4),
+        "plain_444": synth.encode_jpeg(rgb, quality=90, subsampling="4:4:4", optimize=True),
+        "progressive": synth.encode_jpeg(rgb, quality=85, subsampling="4:2:0", progressive=True),
+        "lossless": synth.synth_lossless(42, 96, 64, predictor=4, restart=24)[0],
+        "gray_rows": synth.encode_jpeg(rgb, quality=80, gray=True, restart_rows=1),
+        "extended_12bit": golden_bytes("testorig12.jpg"),
+        "progressive_restart": golden_bytes("yellowcat_progressive_restart.jpg"),
+        "lossless_golden": golden_bytes("lossless3_s22.jpg"),
+    }
+
+
+BASES = _bases()
+
+
+@pytest.mark.parametrize("name", list(BASES))
+def test_damaged_headers_get_the_oracles_verdict_from_walk_and_planning(name):
+    blob = BASES[name]
+    rng = np.random.default_rng(11 + sum(map(ord, name)))
+    counts = {"ok": 0, "refused": 0, "scan": 0, "out of scope": 0, "deviation 6": 0}
+    problems = []
+    for trial in range(int(os.environ.get("JB_HOST_FUZZ_TRIALS", "600"))):
+        bad = mutate_header(blob, rng, trial % 4)
+        try:
+            want, werr, wcode = O.decode(bad, want_rgb=False), None, 0
+        except O.OracleError as e:
+            want, werr, wcode = None, str(e), e.code  # JO_ERR_* = JB_ERR_* for the three exception classes
+        if werr is not None and ("outside the oracle's scope" in werr or "out of memory" in werr or "overhangs the component plane" in werr):
+            continue  # (the last: lossless sampling factors with which the reference indexes out of its scanline store and
+            #            dies of an ArgumentOutOfRangeException; refused as NOT_SUPPORTED here)
+        desc, gerr, gcode = None, None, 0
+        try:
+            p = J.Parsed(bad)
+            desc = p.desc
+            if desc.scan_count:  # (a frame without scans never reaches the C-ABI)
+                gcode = min(0, N.cuda.jb_plan_scans(C.byref(desc), None, 0))
+                if gcode:
+                    gerr = f"planning refused the descriptor ({gcode})"
+        except J.InvalidDataException as e:
+            gerr, gcode = str(e), N.JB_ERR_INVALID_DATA
+        except J.InvalidOperationException as e:
+            gerr, gcode = str(e), N.JB_ERR_INVALID_OPERATION
+        except J.NotSupportedException as e:
+            gerr, gcode = str(e), N.JB_ERR_NOT_SUPPORTED
+        if gcode == N.JB_ERR_NOT_SUPPORTED and (werr is None or any(k in werr for k in SCAN_FAILURES)):
+            counts["out of scope"] += 1  # a layout the GPU path documents as unsupported: no CPU path, no verdict
+            continue
+        if werr is not None and any(k in werr for k in SCAN_FAILURES):
+            # the oracle walks into the scan and fails there.  The host either leaves that to the kernels or has refused
+            # the headers already (a later scan without its table, ...): then with the SAME exception class
+            counts["scan"] += 1
+            if gerr is not None and wcode == N.JB_ERR_INVALID_OPERATION and gcode == N.JB_ERR_INVALID_DATA:
+                # documented deviation (deviation 6): a stream with SEVERAL defects whose earlier scan
+                # fails with "Expect restart marker." (InvalidOperationException) while the host-side checks, made for the
+                # whole file before anything is decoded, have met a later defect (a scan without its table, a component
+                # slot without scans) and raise InvalidDataException
+                counts["deviation 6"] += 1
+                continue
+            if gerr is not None and gcode != wcode:
+                problems.append(f"trial {trial}: the scan fails in the oracle [{werr}] but the host refused the headers [{gerr}]")
+            continue
+        if (werr is None) != (gerr is None):
+            problems.append(f"trial {trial}: oracle [{werr}] host [{gerr}]")
+            continue
+        if werr is None:
+            counts["ok"] += 1
+            same = (desc.width, desc.height, desc.component_count, desc.precision, desc.sof, desc.scan_count) == \
+                   (want.width, want.height, want.ncomp, want.precision, want.sof, want.nscans)
+            same = same and all(list(desc.quant[c]) == list(want.qt[c]) for c in range(want.ncomp) if want.sof != 3)
+            same = same and all((desc.scans[i].ss, desc.scans[i].se, desc.scans[i].ah, desc.scans[i].al, desc.scans[i].restart_interval, desc.scans[i].entropy_offset) ==
+                                (want.scans[i].ss, want.scans[i].se, want.scans[i].ah, want.scans[i].al, want.scans[i].restart_interval, want.scans[i].entropy_offset)
+                                for i in range(want.nscans))
+            if not same:
+                problems.append(f"trial {trial}: both accept, descriptors differ")
+        else:
+            counts["refused"] += 1
+            if gcode != wcode:
+                problems.append(f"trial {trial}: exception classes differ: oracle [{werr}] host [{gerr}]")
+    print(name, counts, len(problems))
+    assert not problems, "\n".join(problems[:20])
+    assert counts["ok"] > 10 and counts["refused"] > 10 and counts["deviation 6"] <= max(1, counts["scan"] // 50)
