@@ -2617,6 +2617,7 @@ int jb_build_huffman_table(const uint32_t frequencies[256], int table_class, int
     std::vector<JbHSym> scratch(257);
     const int n = jb_build_encoder_table(frequencies, &t, scratch.data());
     if (n == 0) return JB_ERR_INVALID_OPERATION; // "No symbol is recorded." (JpegHuffmanEncodingTableBuilder.cs:83-86)
+    if (n < 0) return JB_ERR_INVALID_OPERATION;  // 256 codes of one size: the reference's byte counters wrap and it dies of an IndexOutOfRangeException (:117-160)
     memset(out, 0, sizeof *out);
     out->table_class = (uint8_t)table_class;
     out->identifier = (uint8_t)identifier;

@@ -451,18 +451,29 @@ __host__ __device__ inline int jb_build_encoder_table(const uint32_t *freq, JbEn
     for (int i = 0; i < 264; i++) bits[i] = 0;
     int index = 32;
     for (int i = 0; i < n; i++) { const int cs = sy[i].code_size; if (cs > 0) { if (cs > index) index = cs; bits[cs - 1]++; } }
+    // The reference counts the codes of a size in BYTES (`Span<byte> bits`, :117): 256 codes of one size -- 255 symbols of
+    // equal weight and the sentinel, a perfectly balanced tree -- wrap to 0, the searches below run off the front of the
+    // span and the reference dies of an IndexOutOfRangeException.  No coefficient histogram gets there (at most 162 AC
+    // symbols at 8 bits, 242 at 12), a caller of jb_build_huffman_table can: the host build stops (-1) where the reference
+    // throws; the device code, which only ever sees K3b's histograms, is left as it was validated.
+#ifndef __CUDA_ARCH__
+#define JB_BUILDER_BOUND(i) if ((i) < 0) return -1
+#else
+#define JB_BUILDER_BOUND(i)
+#endif
     for (;;) { // K.3 :129-160
         while (bits[index] > 0) {
             int jj = index - 1;
-            do { jj -= 1; } while (bits[jj] == 0);
+            do { jj -= 1; JB_BUILDER_BOUND(jj); } while (bits[jj] == 0);
             bits[index] -= 2; bits[index - 1] += 1; bits[jj + 1] += 2; bits[jj] -= 1;
         }
         index -= 1;
         if (index != 15) continue;
-        while (bits[index] == 0) index--;
+        while (bits[index] == 0) { index--; JB_BUILDER_BOUND(index); }
         bits[index]--;
         break;
     }
+#undef JB_BUILDER_BOUND
     for (int i = 0; i < n; i++) if (sy[i].value == -1) sy[i].code_size = 0xFFFF;
     jb_hs_introsort(sy, n);
     int code = 0, kk = 0;

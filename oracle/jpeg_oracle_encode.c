@@ -267,7 +267,7 @@ int jo_build_huffman_table(const uint32_t freq[256], uint8_t bits_out[16], uint8
     for (;;) {
         while (bits[index] > 0) {
             int j = index - 1;
-            do { j -= 1; } while (bits[j] == 0);
+            do { j -= 1; if (j < 0) return -1; } while (bits[j] == 0); /* IndexOutOfRangeException in the reference */
             bits[index] -= 2;
             bits[index - 1] += 1;
             bits[j + 1] += 2;
@@ -275,7 +275,8 @@ int jo_build_huffman_table(const uint32_t freq[256], uint8_t bits_out[16], uint8
         }
         index -= 1;
         if (index != 15) continue;
-        while (bits[index] == 0) index--;
+        /* `Span<byte> bits` (:117): 256 codes of one size wrap to 0 and the reference runs off the front of the span */
+        while (bits[index] == 0) { index--; if (index < 0) return -1; }
         bits[index]--;
         break;
     }

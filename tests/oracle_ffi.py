@@ -243,6 +243,8 @@ def build_huffman_table(freq, optimal=False):
     vals = np.zeros(256, dtype=np.uint8)
     fn = lib().jo_build_huffman_table_optimal if optimal else lib().jo_build_huffman_table
     n = fn(f.ctypes.data, bits.ctypes.data, vals.ctypes.data)
+    if n < 0:  # 256 codes of one size: the reference's byte counters wrap (JpegHuffmanEncodingTableBuilder.cs:117-160)
+        raise OracleError(n, "IndexOutOfRangeException in the reference's table builder")
     return bits, vals[:n].copy()
 
 

@@ -343,3 +343,46 @@ def test_caller_tables_on_noise_outgrow_the_reserved_stream_space():
     assert np.array_equal(O.scan_order_coefficients(d).reshape(-1, 64), enc.last_coefficients)
     from PIL import Image
     assert Image.open(io.BytesIO(bytes(out))).size == (512, 512)
+
+
+@pytest.mark.parametrize("optimal", [False, True], ids=["standard", "package-merge"])
+def test_table_builders_agree_on_random_histograms(optimal):
+    """Differential campaign on the CPU: 1500 histograms of every shape that came to mind (heavy tails that need the
+    16-bit limit, long runs of ties for the unstable sorts, one / two symbols, counts next to 2^31, geometric decays) --
+    the product's host builders and the oracle's restatements write the same DHT."""
+    rng = np.random.default_rng(4242 + optimal)
+    fn = J._native.cuda.jb_build_huffman_table_optimal if optimal else J._native.cuda.jb_build_huffman_table
+    crashes = 0
+    for trial in range(1500):
+        n = int(rng.choice([1, 2, 3, 5, 9, 17, 33, 64, 100, 162, 255, 256]))
+        freq = np.zeros(256, dtype=np.uint32)
+        idx = rng.choice(256, size=n, replace=False)
+        kind = trial % 6
+        if kind == 0:
+            f = rng.pareto(0.5, size=n) * 5 + 1
+        elif kind == 1:
+            f = rng.integers(1, 4, size=n)                      # ties everywhere
+        elif kind == 2:
+            f = 2.0 ** rng.integers(0, 31, size=n)              # powers of two up to 2^30
+        elif kind == 3:
+            f = np.maximum(1, (1 << 20) * 0.6 ** np.arange(n))  # geometric: code lengths want to exceed 16
+        elif kind == 4:
+            f = rng.integers(1, 1 << 16, size=n)
+        else:
+            f = np.full(n, int(rng.integers(1, 1000)))           # all equal
+        freq[idx] = np.minimum(f, 2 ** 31 - 1).astype(np.uint32)
+        spec = J._native.HuffSpec()
+        try:
+            bits, vals = O.build_huffman_table(freq, optimal=optimal)
+        except O.OracleError:
+            # 255 symbols of equal weight + the sentinel = 256 codes of 8 bits: the reference counts them in a byte, finds
+            # no code at all and dies of an IndexOutOfRangeException (standard method only)
+            assert not optimal and n == 255 and kind == 5, (trial, kind, n)
+            assert fn(freq.ctypes.data, 0, 1, C.byref(spec)) == J._native.JB_ERR_INVALID_OPERATION
+            crashes += 1
+            continue
+        assert fn(freq.ctypes.data, 0, 1, C.byref(spec)) == 0, trial
+        assert list(spec.bits) == bits.tolist(), (trial, kind, n)
+        assert list(spec.values[:spec.value_count]) == vals.tolist(), (trial, kind, n)
+        assert int(bits.sum()) == n and kraft(bits) < 1.0 and max(l + 1 for l, c in enumerate(bits) if c) <= 16, (trial, kind, n)
+    assert optimal or crashes > 0
