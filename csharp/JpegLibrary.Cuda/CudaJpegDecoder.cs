@@ -38,6 +38,13 @@ namespace JpegLibrary.Cuda
         private readonly List<Native.HuffSpec> _tables = new List<Native.HuffSpec>();
         private readonly int[,] _latest = new int[2, 4];           // [class, id] -> index into _tables, -1 = undefined
         private readonly List<Native.ScanDesc> _scans = new List<Native.ScanDesc>();
+        // Quantisation tables as the reference's scan decoders capture them: a sequential component is rendered with the
+        // table in force at ITS scan (JpegHuffmanBaselineScanDecoder via InitDecodeComponents, JpegHuffmanScanDecoder.cs:38-66);
+        // a progressive frame is rendered at Dispose from the `_components` slots the LAST scans left behind -- slot i
+        // belongs to the i-th component of a scan (JpegHuffmanProgressiveScanDecoder.cs:69, :431-462; quirk P6).
+        private readonly ushort[] _componentQuant = new ushort[4 * 64];
+        private readonly int[] _slotComponent = { -1, -1, -1, -1 };
+        private readonly ushort[] _slotQuant = new ushort[4 * 64];
 
         public CudaJpegDecoder(int device = 0)
         {
@@ -85,6 +92,7 @@ namespace JpegLibrary.Cuda
                         JpegFrameHeader.TryParse(body, false, out JpegFrameHeader fh, out _))
                     {
                         _frame = fh; _sof = marker; _scans.Clear();
+                        for (int i = 0; i < 4; i++) _slotComponent[i] = -1;
                         // The reference's sequential and lossless scan decoders are constructed HERE, at the frame header, and
                         // read the restart interval once, in their constructors (JpegHuffmanBaselineScanDecoder.cs:38,
                         // JpegHuffmanLosslessScanDecoder.cs:32): every scan of the frame uses the value in force now -- which,
@@ -178,6 +186,17 @@ namespace JpegLibrary.Cuda
                     if (_frame.Components[j].Identifier == sc.ScanComponentSelector) found = j; // InitDecodeComponents :38-48
                 if (found < 0) throw new InvalidDataException("Failed to decode JPEG data. The specified component is missing.");
                 sd.ComponentIndex[i] = (byte)found;
+                if (_sof != JpegMarker.StartOfFrame3) // lossless frames carry no DQT
+                {
+                    JpegQuantizationTable q = GetQuantizationTable(_frame.Components[found].QuantizationTableSelector); // zig-zag order (JpegQuantizationTable.cs:21)
+                    if (q.IsEmpty) throw new InvalidDataException("Failed to decode JPEG data. Quantization table of component is not defined.");
+                    _slotComponent[i] = found;
+                    for (int k = 0; k < 64; k++)
+                    {
+                        _slotQuant[i * 64 + k] = q.Elements[k];
+                        if (_sof != JpegMarker.StartOfFrame2) _componentQuant[found * 64 + k] = q.Elements[k];
+                    }
+                }
                 sd.DcTable[i] = (short)TableIndex(0, sc.DcEntropyCodingTableSelector & 3);
                 sd.AcTable[i] = (short)TableIndex(1, sc.AcEntropyCodingTableSelector & 3);
             }
@@ -239,11 +258,21 @@ namespace JpegLibrary.Cuda
             {
                 JpegFrameComponentSpecificationParameters fc = _frame.Components![c];
                 img.H[c] = fc.HorizontalSamplingFactor; img.V[c] = fc.VerticalSamplingFactor;
-                if (_sof != JpegMarker.StartOfFrame3)
+                if (_sof != JpegMarker.StartOfFrame3 && _sof != JpegMarker.StartOfFrame2)
+                    for (int i = 0; i < 64; i++) img.Quant[c * 64 + i] = _componentQuant[c * 64 + i]; // (0 for a component no scan names: never rendered)
+            }
+            if (_sof == JpegMarker.StartOfFrame2)
+            {
+                // what Dispose renders with (the same rule as the host walk of this repository, jpeg_host.cpp): slot i -> its
+                // component and the table captured with it; a scan order that leaves the slots inconsistent is refused
+                int seen = 0;
+                for (int i = 0; i < n; i++)
                 {
-                    JpegQuantizationTable q = GetQuantizationTable(fc.QuantizationTableSelector);   // zig-zag order (JpegQuantizationTable.cs:21)
-                    if (q.IsEmpty) throw new InvalidDataException($"Failed to decode JPEG data. Quantization table of component {c} is not defined.");
-                    for (int i = 0; i < 64; i++) img.Quant[c * 64 + i] = q.Elements[i];
+                    int c = _slotComponent[i];
+                    if (c < 0) throw new InvalidDataException("Failed to decode JPEG data. progressive frame leaves a component slot without scans");
+                    if ((seen & (1 << c)) != 0) throw new NotSupportedException("progressive scan order leaves component slots inconsistent (reference quirk P6)");
+                    seen |= 1 << c;
+                    for (int k = 0; k < 64; k++) img.Quant[c * 64 + k] = _slotQuant[i * 64 + k];
                 }
             }
             Native.ScanDesc[] scans = _scans.ToArray();
