@@ -552,6 +552,12 @@ static int scan_progressive(dec_ctx *c, const jo_scan_info *s)
             if (!comp->dc) return fail(c, JO_ERR_INVALID_DATA, "Huffman table is not defined.");
         } else if (!comp->ac)
             return fail(c, JO_ERR_INVALID_DATA, "Huffman table is not defined.");
+        /* The reference never validates Ss / Se.  An AC REFINEMENT scan with Se > 63 walks `ref short` positions past the
+           end of the block (Unsafe.Add, :313-419): it reads and rewrites the neighbouring blocks and, at the end of the
+           store, foreign memory -- undefined behaviour with no result to be at parity with.  The oracle stops there with
+           the verdict of the GPU path, which refuses such a scan header (deviation 3).  (An AC-first scan
+           clamps its position to 63 and is decoded as the reference decodes it.) */
+        if (s->ss != 0 && s->ah != 0 && s->se > 63) return fail(c, JO_ERR_INVALID_DATA, "Failed to parse scan header.");
         for (int by = 0; by < hb; by++)
             for (int bx = 0; bx < wb; bx++) {
                 int16_t *blk = prog_block(c, ci, bx, by);

@@ -19,6 +19,11 @@ from test_gpu_fuzz import mutate_header
 SCAN_FAILURES = ("Invalid Huffman code", "magnitude category", "bit stream ended", "restart marker", "end of JPEG data stream")
 
 
+def _scan_list(scans, restart):
+    src = synth.synth_jpeg(33, 120, 88, subsampling="4:2:0", quality=88)
+    return synth.resequence_scans(src, O.decode(src, want_rgb=False), scans, restart)
+
+
 def _bases():
     rgb = synth.synth_rgb(40, 160, 112)
     return {
@@ -30,20 +35,54 @@ def _bases():
         "extended_12bit": golden_bytes("testorig12.jpg"),
         "progressive_restart": golden_bytes("yellowcat_progressive_restart.jpg"),
         "lossless_golden": golden_bytes("lossless3_s22.jpg"),
+        "scan_list": _scan_list([[0, 1], [2]], 5),
+        "scan_list_second_pass": _scan_list([[0, 1, 2], [0]], 0),
+        "lossless_scans": synth.synth_lossless_scans(44, 48, 32, [dict(components=[0], predictor=1), dict(components=[1, 2], predictor=4)])[0],
     }
 
 
 BASES = _bases()
 
 
+def _segments(blob):
+    """(position, length) of every marker segment that carries a length: the headers in front of and BETWEEN the scans"""
+    out, i = [], 2
+    while i + 4 <= len(blob):
+        if blob[i] != 0xFF or blob[i + 1] in (0x00, 0xFF) or 0xD0 <= blob[i + 1] <= 0xD9:
+            i += 1
+            continue
+        ln = int.from_bytes(blob[i + 2:i + 4], "big")
+        out.append((i, 2 + ln))
+        i += 2 + ln
+    return out
+
+
+def mutate_any_segment(blob, rng, kind, segments):
+    """like mutate_header, anywhere a segment lies: the tables, DRI and scan headers between the scans of a progressive
+    frame or a scan list as well"""
+    at, ln = segments[int(rng.integers(len(segments)))]
+    b = bytearray(blob)
+    p = at + int(rng.integers(0, min(ln, 24)))
+    if kind == 0:
+        b[p] ^= 1 << int(rng.integers(8))
+    elif kind == 1:
+        b[p] = int(rng.integers(256))
+    elif kind == 2:
+        del b[p:p + int(rng.integers(1, 4))]
+    else:
+        b[p:p] = bytes(rng.integers(0, 256, int(rng.integers(1, 4))).astype(np.uint8))
+    return bytes(b)
+
+
 @pytest.mark.parametrize("name", list(BASES))
 def test_damaged_headers_get_the_oracles_verdict_from_walk_and_planning(name):
     blob = BASES[name]
     rng = np.random.default_rng(11 + sum(map(ord, name)))
-    counts = {"ok": 0, "refused": 0, "scan": 0, "out of scope": 0, "deviation 6": 0}
+    counts = {"ok": 0, "refused": 0, "scan": 0, "out of scope": 0, "deviation 6": 0, "deviation 3": 0}
+    segments = _segments(blob)
     problems = []
     for trial in range(int(os.environ.get("JB_HOST_FUZZ_TRIALS", "600"))):
-        bad = mutate_header(blob, rng, trial % 4)
+        bad = mutate_header(blob, rng, trial % 4) if trial % 2 else mutate_any_segment(blob, rng, (trial // 2) % 4, segments)
         try:
             want, werr, wcode = O.decode(bad, want_rgb=False), None, 0
         except O.OracleError as e:
@@ -65,6 +104,14 @@ def test_damaged_headers_get_the_oracles_verdict_from_walk_and_planning(name):
             gerr, gcode = str(e), N.JB_ERR_INVALID_OPERATION
         except J.NotSupportedException as e:
             gerr, gcode = str(e), N.JB_ERR_NOT_SUPPORTED
+        if gcode == N.JB_ERR_INVALID_DATA and desc is not None and (werr is None or any(k in werr for k in SCAN_FAILURES)) and any(
+                desc.scans[i].component_count == 1 and desc.scans[i].ss > 0 and (desc.scans[i].se > 63 or desc.scans[i].ss > desc.scans[i].se)
+                for i in range(desc.scan_count)) and desc.sof == 2:
+            # documented deviation (deviation 3): single-component AC scans with Ss > Se or Se > 63 are
+            # refused ("Failed to parse scan header."); the reference validates neither (the first decodes nothing, the
+            # second clamps or -- refinement scans -- runs past the block, where the oracle stops as well)
+            counts["deviation 3"] += 1
+            continue
         if gcode == N.JB_ERR_NOT_SUPPORTED and (werr is None or any(k in werr for k in SCAN_FAILURES)):
             counts["out of scope"] += 1  # a layout the GPU path documents as unsupported: no CPU path, no verdict
             continue
