@@ -110,7 +110,7 @@ static int parse_impl(const uint8_t *tables, uint64_t tables_len, const uint8_t 
     int huff_latest[2][4];
     for (auto &a : huff_latest)
         for (auto &b : a) b = -1;
-    uint16_t qt[4][64];
+    uint16_t qt[4][64] = {}; // (lossless frames carry no DQT: their descriptor holds zeros, not stack contents)
     bool qt_present[4] = {false, false, false, false};
     uint8_t comp_id[4] = {0, 0, 0, 0}, comp_tq[4] = {0, 0, 0, 0};
     // The reference's sequential and lossless scan decoders are created when the frame header is read and take the
@@ -124,7 +124,7 @@ static int parse_impl(const uint8_t *tables, uint64_t tables_len, const uint8_t 
     bool have_frame = false;
     // progressive `_components` slot emulation (JpegHuffmanProgressiveScanDecoder.cs:21,69,431-462)
     int slot_comp[4] = {-1, -1, -1, -1};
-    uint16_t slot_qt[4][64];
+    uint16_t slot_qt[4][64] = {};
 
     // DHT: possibly several tables per segment (JpegDecoder.ProcessDefineHuffmanTable)
     auto on_dht = [&](const uint8_t *b, uint64_t n, uint64_t seg_at) -> int {

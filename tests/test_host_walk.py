@@ -305,3 +305,16 @@ def test_damaged_tables_streams_get_the_oracles_verdict():
                 assert gerr.split(". ", 1)[-1].rstrip(".") in werr, (trial, werr, gerr)
             verdicts[stage] += 1
     assert verdicts["ok"] > 20 and verdicts["load"] > 50, verdicts
+
+
+@pytest.mark.parametrize("name", ["lake.jpg", "cramps.jpg", "testorig12.jpg", "progress.jpg", "lossless1_s22.jpg", "lossless5_s22.jpg"])
+def test_golden_assets_split_into_tables_and_abbreviated_streams(name):
+    """The reference's own assets as TIFF-style pairs (tables stream + abbreviated stream): same descriptor from the host
+    walk, same coefficients and planes from the oracle as the whole file -- whose planes are pinned on the reference's
+    golden PNGs (tests/test_oracle_golden.py)."""
+    blob = golden_bytes(name)
+    tables, rest = synth.split_tables(blob, move=(0xC4, 0xDB, 0xDD))
+    whole, abbr = J.Parsed(blob), J.Parsed(rest, tables)
+    _same_descriptor(abbr.desc, whole.desc, len(blob) - len(rest))
+    o, w = O.decode(rest, want_rgb=False, tables=tables), O.decode(blob, want_rgb=False)
+    assert (o.planes == w.planes).all() and all((a == b).all() for a, b in zip(o.coef, w.coef))
