@@ -46,13 +46,24 @@ namespace JpegLibrary.Cuda
         private readonly int[] _slotComponent = { -1, -1, -1, -1 };
         private readonly ushort[] _slotQuant = new ushort[4 * 64];
 
+        private readonly bool _ownsContext;
+
         public CudaJpegDecoder(int device = 0)
         {
             Native.Check(IntPtr.Zero, Native.jb_ctx_create(device, out _ctx));
+            _ownsContext = true;
             for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) _latest[c, i] = -1;
         }
 
-        public void Dispose() => Native.jb_ctx_destroy(_ctx);
+        /// <summary>A decoder on somebody else's context (the walkers of CudaJpegBatchDecoder.Create share the batch's).</summary>
+        internal CudaJpegDecoder(IntPtr sharedContext)
+        {
+            _ctx = sharedContext;
+            _ownsContext = false;
+            for (int c = 0; c < 2; c++) for (int i = 0; i < 4; i++) _latest[c, i] = -1;
+        }
+
+        public void Dispose() { if (_ownsContext) Native.jb_ctx_destroy(_ctx); }
 
         /// <summary>The library context (one per GPU): shared with CudaJpegEncoder / CudaJpegOptimizer / PinnedMemoryPool.</summary>
         public IntPtr Context => _ctx;
@@ -73,8 +84,45 @@ namespace JpegLibrary.Cuda
         internal CoefficientResult DecodeCoefficients()
         {
             _coefficientsOnly = true;
+            EnsureWriterForWalk();
             try { Decode(); } finally { _coefficientsOnly = false; }
             return _coefficientResult;
+        }
+
+        // JpegDecoder.Decode() refuses to start without an output writer (JpegDecoder.cs:515-518); the walks that produce no
+        // pixels (coefficients only, descriptor only) give the base class a sink that is never written to.
+        private void EnsureWriterForWalk()
+        {
+            if (_writer is null) base.SetOutputWriter(new CudaRgbOutputWriter());
+        }
+
+        /// <summary>What one stream contributes to a batch: its descriptor and everything the descriptor points to, pinned
+        /// until Dispose (after jb_decode_batch_finish).</summary>
+        internal sealed class CollectedImage : IDisposable
+        {
+            public Native.ImageDesc Desc;
+            internal GCHandle Scans, Tables;
+            internal MemoryHandle Input;
+            public void Dispose()
+            {
+                if (Scans.IsAllocated) Scans.Free();
+                if (Tables.IsAllocated) Tables.Free();
+                Input.Dispose();
+            }
+        }
+        private bool _collectOnly;
+        private CollectedImage? _collected;
+
+        /// <summary>The marker loop of Decode() without decoding: the jb_image_desc CudaJpegBatchDecoder hands to
+        /// jb_decode_batch_create.  Tables loaded before (LoadTables, SetHuffmanTable, SetQuantizationTable) take part like
+        /// they do in Decode().</summary>
+        internal CollectedImage Collect()
+        {
+            _collectOnly = true;
+            _collected = null;
+            EnsureWriterForWalk();
+            try { Decode(); } finally { _collectOnly = false; }
+            return _collected ?? throw new InvalidDataException("Failed to decode JPEG data. No image data is read.");
         }
 
         // JpegDecoder.SetInput / SetOutputWriter are not virtual: keep our own references next to the base class's.
@@ -277,6 +325,19 @@ namespace JpegLibrary.Cuda
             }
             Native.ScanDesc[] scans = _scans.ToArray();
             Native.HuffSpec[] tables = _tables.ToArray();
+            if (_collectOnly)
+            {
+                // descriptor only: the arrays and the input stay pinned with the CollectedImage (a frame whose scans are
+                // submitted one by one -- there is none on this path: single-scan frames call Submit once, scan lists at EOI)
+                var held = new CollectedImage { Scans = GCHandle.Alloc(scans, GCHandleType.Pinned), Tables = GCHandle.Alloc(tables, GCHandleType.Pinned), Input = _input.Pin() };
+                img.Data = (byte*)held.Input.Pointer;
+                img.Scans = (Native.ScanDesc*)held.Scans.AddrOfPinnedObject();
+                img.Tables = (Native.HuffSpec*)held.Tables.AddrOfPinnedObject();
+                held.Desc = img;
+                _collected?.Dispose();
+                _collected = held;
+                return;
+            }
             using MemoryHandle pin = _input.Pin();
             fixed (Native.ScanDesc* ps = scans)
             fixed (Native.HuffSpec* pt = tables)
