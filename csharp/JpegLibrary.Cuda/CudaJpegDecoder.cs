@@ -38,6 +38,7 @@ namespace JpegLibrary.Cuda
         private readonly List<Native.HuffSpec> _tables = new List<Native.HuffSpec>();
         private readonly int[,] _latest = new int[2, 4];           // [class, id] -> index into _tables, -1 = undefined
         private readonly List<Native.ScanDesc> _scans = new List<Native.ScanDesc>();
+        private readonly List<byte> _quantOrder = new List<byte>();
         // Quantisation tables as the reference's scan decoders capture them: a sequential component is rendered with the
         // table in force at ITS scan (JpegHuffmanBaselineScanDecoder via InitDecodeComponents, JpegHuffmanScanDecoder.cs:38-66);
         // a progressive frame is rendered at Dispose from the `_components` slots the LAST scans left behind -- slot i
@@ -77,6 +78,7 @@ namespace JpegLibrary.Cuda
             public byte[] H, V;                 // per frame component
             public Native.ScanDesc Scan;        // the (only) scan of a sequential frame; EntropyOffset/Length locate its bytes
             public Native.HuffSpec[] Tables;    // Scan.DcTable / AcTable index into this
+            public JpegQuantizationTable[] QuantizationTables; // every table of the stream, in the order of first definition
         }
         private ushort _restartAtFrame;
         private bool _coefficientsOnly;
@@ -126,7 +128,7 @@ namespace JpegLibrary.Cuda
         }
 
         // JpegDecoder.SetInput / SetOutputWriter are not virtual: keep our own references next to the base class's.
-        public new void SetInput(ReadOnlyMemory<byte> input) { _input = input; base.SetInput(input); }
+        public new void SetInput(ReadOnlyMemory<byte> input) { _input = input; _quantOrder.Clear(); base.SetInput(input); }
         public new void SetOutputWriter(JpegBlockOutputWriter outputWriter) { _writer = outputWriter; base.SetOutputWriter(outputWriter); }
 
         protected override bool ProcessMarkerForDecode(JpegMarker marker, ref JpegReader reader)
@@ -154,6 +156,22 @@ namespace JpegLibrary.Cuda
                 {
                     JpegReader peek = reader;
                     if (peek.TryReadLength(out ushort len) && peek.TryReadBytes(len, out ReadOnlySequence<byte> body)) RememberTables(body);
+                    return base.ProcessMarkerForDecode(marker, ref reader);
+                }
+                case JpegMarker.DefineQuantizationTable:
+                {
+                    // the order in which identifiers are FIRST defined: JpegOptimizer writes its tables in that order
+                    // (a later definition replaces the table in place, JpegOptimizer.cs ProcessDefineQuantizationTable)
+                    JpegReader peek = reader;
+                    if (peek.TryReadLength(out ushort len) && peek.TryReadBytes(len, out ReadOnlySequence<byte> body))
+                    {
+                        byte[] b = body.ToArray();
+                        for (int p = 0; p < b.Length; p += (b[p] >> 4) != 0 ? 129 : 65)
+                        {
+                            byte id = (byte)(b[p] & 15);
+                            if (id < 4 && !_quantOrder.Contains(id)) _quantOrder.Add(id);
+                        }
+                    }
                     return base.ProcessMarkerForDecode(marker, ref reader);
                 }
                 case JpegMarker.StartOfScan:
@@ -352,8 +370,10 @@ namespace JpegLibrary.Cuda
                     Native.Check(_ctx, Native.jb_device_alloc(_ctx, (UIntPtr)(blocks * 128), out IntPtr dev));
                     var oc = new Native.OutputDesc { Dst = (void*)dev, Capacity = blocks * 128, Format = Native.JB_OUT_COEFFICIENTS, OnDevice = 1 };
                     Native.Check(_ctx, Native.jb_decode(_ctx, &img, &oc, 1, null));               // K0 + K1 only
+                    var qts = new List<JpegQuantizationTable>();
+                    foreach (byte id in _quantOrder) { JpegQuantizationTable q = GetQuantizationTable(id); if (!q.IsEmpty) qts.Add(q); }
                     _coefficientResult = new CoefficientResult { Coefficients = dev, Blocks = blocks, Sof = img.Sof, Width = img.Width, Height = img.Height,
-                                                                 H = hh, V = vv, Scan = scans[0], Tables = tables };
+                                                                 H = hh, V = vv, Scan = scans[0], Tables = tables, QuantizationTables = qts.ToArray() };
                     return;
                 }
                 if (_writer is CudaRgbOutputWriter w)

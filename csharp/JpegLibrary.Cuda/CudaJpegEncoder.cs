@@ -74,16 +74,16 @@ namespace JpegLibrary.Cuda
                 var tables = new JpegHuffmanEncodingTableCollection();
                 foreach (var c in _components)
                 {
-                    InstallTable(batch, tables, hist, 0, c.td);
-                    InstallTable(batch, tables, hist, 1, c.ta);
+                    InstallTable(batch, ref tables, hist, 0, c.td);
+                    InstallTable(batch, ref tables, hist, 1, c.ta);
                 }
                 Native.Check(_ctx, Native.jb_encode_batch_pack(batch));                 // E8 + E9
                 Native.Check(_ctx, Native.jb_encode_batch_finish(batch));
 
                 var writer = new JpegWriter(output, 4096);
                 WriteStartOfImage(ref writer);                                          // protected helpers of the base class
-                WriteQuantizationTables(ref writer);                                    //   (JpegEncoder.cs:340-412); a maintainer
-                WriteStartOfFrame(ref writer);                                          //   makes them protected instead of private
+                WriteQuantizationTables(ref writer);                                    //   (JpegEncoder.cs:296-387, :930)
+                WriteStartOfFrame(ref writer);
                 tables.Write(ref writer);
                 WriteStartOfScan(ref writer);
                 ulong length;
@@ -97,7 +97,8 @@ namespace JpegLibrary.Cuda
             finally { Native.jb_encode_batch_destroy(batch); }
         }
 
-        private void InstallTable(IntPtr batch, JpegHuffmanEncodingTableCollection tables, uint[] hist, int tableClass, byte id)
+        // (JpegHuffmanEncodingTableCollection is a mutable struct that creates its list on the first AddTable: by reference)
+        private void InstallTable(IntPtr batch, ref JpegHuffmanEncodingTableCollection tables, uint[] hist, int tableClass, byte id)
         {
             if (tables.GetTable(tableClass == 0, id) is not null) return;
             var builder = new JpegHuffmanEncodingTableBuilder();

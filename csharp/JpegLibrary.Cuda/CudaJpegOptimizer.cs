@@ -123,11 +123,41 @@ namespace JpegLibrary.Cuda
             writer.WriteBytes(body.Slice(0, n));
         }
 
-        // WriteQuantizationTables / CopySegment / SkipSegment: the reference's private helpers WriteQuantizationTables
-        // (:649-668), CopyMarkerData (:680-700) and SkipMarkerData (:649-659), unchanged.
-        private void WriteQuantizationTables(ref JpegWriter writer) => throw new NotImplementedException("reuse JpegOptimizer.WriteQuantizationTables");
-        private static void CopySegment(ref JpegReader reader, ref JpegWriter writer) => throw new NotImplementedException("reuse JpegOptimizer.CopyMarkerData");
-        private static void SkipSegment(ref JpegReader reader) => throw new NotImplementedException("reuse JpegOptimizer.SkipMarkerData");
+        // The three helpers below do what JpegOptimizer's private WriteQuantizationTables, CopyMarkerData and SkipMarkerData do
+        // (JpegOptimizer.cs:649-716), on what the walker collected.
+        private void WriteQuantizationTables(ref JpegWriter writer)
+        {
+            JpegQuantizationTable[] tables = _frame.QuantizationTables;
+            if (tables is null || tables.Length == 0) throw new InvalidOperationException();
+            int total = 0;
+            foreach (JpegQuantizationTable t in tables) total += t.BytesRequired;
+            writer.WriteMarker(JpegMarker.DefineQuantizationTable);
+            writer.WriteLength((ushort)total);
+            foreach (JpegQuantizationTable t in tables)
+            {
+                Span<byte> dst = writer.GetSpan(t.BytesRequired);
+                t.TryWrite(dst, out int written);
+                writer.Advance(written);
+            }
+        }
+
+        private static void CopySegment(ref JpegReader reader, ref JpegWriter writer)
+        {
+            if (!reader.TryReadLength(out ushort length)) // (the payload length: TryReadLength takes the two length bytes off)
+                throw new System.IO.InvalidDataException($"Failed to decode JPEG data at offset {reader.ConsumedByteCount}. Unexpected end of input data when reading segment length.");
+            if (!reader.TryReadBytes(length, out ReadOnlySequence<byte> payload))
+                throw new System.IO.InvalidDataException($"Failed to decode JPEG data at offset {reader.ConsumedByteCount}. Unexpected end of input data when reading segment content.");
+            writer.WriteLength(length);
+            writer.WriteBytes(payload);
+        }
+
+        private static void SkipSegment(ref JpegReader reader)
+        {
+            if (!reader.TryReadLength(out ushort length))
+                throw new System.IO.InvalidDataException($"Failed to decode JPEG data at offset {reader.ConsumedByteCount}. Unexpected end of input data when reading segment length.");
+            if (!reader.TryAdvance(length))
+                throw new System.IO.InvalidDataException($"Failed to decode JPEG data at offset {reader.ConsumedByteCount}. Unexpected end of input data when reading segment content.");
+        }
 
         private void Release()
         {
